@@ -1,0 +1,230 @@
+"""CPU tests: pin the oracle (C restatement + numpy twin) against the 50-digit known answers and the
+identities the reference's own tests assert.  No GPU, no reference at run time."""
+import numpy as np
+import pytest
+
+from oracle import oracle_c as oc
+from oracle import oracle_np as onp
+from tests.helpers import METRIC_KINDS, MODEL_KINDS, case_arrays, golden_cases, rel_err
+
+GOLD = golden_cases()
+
+
+def _c_objs(case, a):
+    model = oc.Model(MODEL_KINDS[case["model"]], case["D"], a["p0"], a["p1"], case["c0"])
+    metric = oc.Metric(METRIC_KINDS[case["metric"]], a["Minv"])
+    return model, metric
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_c_oracle_matches_mp50(case):
+    a = case_arrays(case)
+    model, metric = _c_objs(case, a)
+    z0 = oc.phasepoint(model, metric, a["theta0"], a["r0"])
+    z1, status, done = oc.leapfrog(model, metric, a["eps"], z0, case["n_steps"], case["temper_alpha"] or 0.0)
+    assert (status == 0).all() and (done == abs(case["n_steps"])).all()
+    tol = 2e-12  # fp64 op-order result vs exact: 1e-16..1e-13 (chaotic funnel amplifies a little)
+    assert rel_err(z1.theta, a["theta"]) < tol
+    assert rel_err(z1.r, a["r"]) < tol
+    assert rel_err(z1.lp_gradient, a["lp_gradient"]) < tol
+    assert rel_err(z1.lp_value, a["lp_value"]) < tol
+    assert rel_err(z1.lk_value, a["lk_value"]) < tol
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_numpy_twin_matches_c_oracle(case):
+    a = case_arrays(case)
+    model, metric = _c_objs(case, a)
+    z0 = oc.phasepoint(model, metric, a["theta0"], a["r0"])
+    z1, _, _ = oc.leapfrog(model, metric, a["eps"], z0, case["n_steps"], case["temper_alpha"] or 0.0)
+    nm = onp.Model(MODEL_KINDS[case["model"]], case["D"], a["p0"], a["p1"], case["c0"])
+    me = onp.Metric(METRIC_KINDS[case["metric"]], a["Minv"])
+    y0 = onp.phasepoint(nm, me, a["theta0"], a["r0"])
+    assert rel_err(y0.lp_value, z0.lp_value) < 1e-14 and rel_err(y0.lk_value, z0.lk_value) < 1e-14
+    y1 = onp.step(nm, me, a["eps"], y0, case["n_steps"], temper_alpha=case["temper_alpha"])
+    for f in ("theta", "r", "lp_gradient", "lp_value", "lk_value", "lk_gradient"):
+        assert rel_err(getattr(y1, f), getattr(z1, f)) < 5e-13, f
+
+
+def test_survey_spot_values():
+    """SURVEY 8c spot vectors: fp64 op-order results recorded there to 16 digits."""
+    model = oc.Model(oc.DIAG_GAUSS, 1, [0.0], [1.0])
+    metric = oc.Metric(oc.DIAG, [1.0])
+    z0 = oc.phasepoint(model, metric, np.array([[1.0]]), np.array([[0.5]]))
+    z1, _, _ = oc.leapfrog(model, metric, 0.1, z0, 32)
+    assert z1.theta[0, 0] == pytest.approx(-1.0281066785335988139, rel=1e-14)
+    assert z1.r[0, 0] == pytest.approx(-0.43947601289572651662, rel=1e-14)
+    assert z1.lp_value[0] == pytest.approx(-0.5 * z1.theta[0, 0] ** 2, rel=1e-15)
+    assert z1.lk_value[0] == pytest.approx(-0.09656958295536232, rel=1e-13)
+    s = GOLD["survey_spots"]
+    assert s[0]["theta"].startswith("-1.02810667853359881") and s[2]["r"].startswith("1.30542169799302271")
+
+
+def test_energy_identities():
+    """test/hamiltonian.jl:54-79: neg_energy / dHdr identities for Unit, Diag, Dense."""
+    rng = np.random.default_rng(1)
+    D = 5
+    for _ in range(10):
+        r = rng.normal(size=D)
+        mu = oc.Metric(oc.UNIT)
+        assert -oc.neg_kinetic(mu, r) == np.sum(r * r) / 2
+        assert (oc.dHdr(mu, r) == r).all()
+        Mi = 1 + np.abs(rng.normal(size=D))
+        me = oc.Metric(oc.DIAG, Mi)
+        assert (oc.dHdr(me, r) == Mi * r).all()
+        assert -oc.neg_kinetic(me, r) == pytest.approx(r @ np.diag(Mi) @ r / 2, rel=1e-14)
+        m = rng.normal(size=(D, D))
+        Md = m.T @ m
+        md = oc.Metric(oc.DENSE, Md)
+        assert np.allclose(oc.dHdr(md, r), Md @ r, rtol=1e-13)
+        assert -oc.neg_kinetic(md, r) == pytest.approx(r @ Md @ r / 2, rel=1e-13)
+
+
+def test_step_n_equals_n_steps_of_one():
+    """test/integrator.jl:17-32 (there atol 5e-3; here bit-identical by construction)."""
+    rng = np.random.default_rng(2)
+    D, N = 5, 7
+    model, metric = oc.Model(oc.STD_NORMAL, D), oc.Metric(oc.UNIT)
+    z = oc.phasepoint(model, metric, rng.normal(size=(D, N)), rng.normal(size=(D, N)))
+    zn, _, _ = oc.leapfrog(model, metric, 0.01, z, 10)
+    zl = z
+    for _ in range(10):
+        zl, _, _ = oc.leapfrog(model, metric, 0.01, zl, 1)
+    assert (zl.theta == zn.theta).all() and (zl.r == zn.r).all()
+
+
+def test_harmonic_oscillator_invariants():
+    """test/integrator.jl:108-153: radius and energy constant within 2e-3 over 10^4 steps, eps=0.01."""
+    model, metric = oc.Model(oc.STD_NORMAL, 1), oc.Metric(oc.UNIT)
+    rng = np.random.default_rng(3)
+    z = oc.phasepoint(model, metric, rng.normal(size=(1, 1)), rng.normal(size=(1, 1)))
+    traj, done = oc.leapfrog_trajectory(model, metric, 0.01, z, 10_000)
+    assert done[0] == 10_000
+    q, p = traj["theta"][0, 0, 999:], traj["r"][0, 0, 999:]
+    H = -(traj["lp_value"][0, 999:] + traj["lk_value"][0, 999:])
+    rs = np.sqrt(q**2 + p**2)
+    assert np.all(np.abs(rs - rs.mean()) < 2e-3) and np.all(np.abs(H - H.mean()) < 2e-3)
+
+
+def test_reversibility_backward_steps():
+    """n_steps<0 integrates backward (integrator.jl:221-226): fwd n then bwd n returns to start."""
+    rng = np.random.default_rng(4)
+    D, N = 6, 3
+    s = np.exp(rng.uniform(-1, 1, D))
+    model, metric = oc.Model(oc.DIAG_GAUSS, D, rng.normal(size=D), s), oc.Metric(oc.DIAG, s * s)
+    z = oc.phasepoint(model, metric, rng.normal(size=(D, N)), rng.normal(size=(D, N)))
+    z1, _, _ = oc.leapfrog(model, metric, 0.1, z, 17)
+    z2, _, _ = oc.leapfrog(model, metric, 0.1, z1, -17)
+    assert rel_err(z2.theta, z.theta) < 1e-13 and rel_err(z2.r, z.r) < 1e-13
+
+
+def test_nonfinite_break_per_chain_and_compat():
+    """integrator.jl:252-258 + hamiltonian.jl:95-104,141-142 (quirk Q1)."""
+    D, N = 3, 4
+    model, metric = oc.Model(oc.STD_NORMAL, D), oc.Metric(oc.UNIT)
+    th = np.ones((D, N))
+    th[:, 2] = 1e200  # kinetic/potential overflow for chain 2 at the first step
+    z = oc.phasepoint(model, metric, th, np.ones((D, N)))
+    z1, status, done = oc.leapfrog(model, metric, 0.1, z, 5)
+    assert list(status) == [0, 0, 1, 0] and list(done) == [5, 5, 1, 5]
+    assert z1.lp_value[2] == -np.inf
+    z2, status2, done2 = oc.leapfrog(model, metric, 0.1, z, 5, compat_break_all=True)
+    assert list(done2) == [1, 1, 1, 1] and list(status2) == [0, 0, 1, 0]
+    ref, _, _ = oc.leapfrog(model, metric, 0.1, z, 1)
+    assert (z2.theta == ref.theta).all()
+    # numpy twin = the reference's matrix mode: breaks all chains too
+    y = onp.step(onp.Model(onp.STD_NORMAL, D), onp.Metric(onp.UNIT), 0.1,
+                 onp.phasepoint(onp.Model(onp.STD_NORMAL, D), onp.Metric(onp.UNIT), th, np.ones((D, N))), 5)
+    assert np.allclose(y.theta[:, 0], z2.theta[:, 0], rtol=1e-15)
+
+
+def test_chain_independence():
+    """test/sampler-vec.jl:69-80, test/metric.jl:4-22: identical columns stay identical; a chain's
+    result does not depend on its neighbours."""
+    rng = np.random.default_rng(5)
+    D = 5
+    th, r = rng.normal(size=(D, 1)), rng.normal(size=(D, 1))
+    model, metric = oc.Model(oc.FUNNEL, D), oc.Metric(oc.UNIT)
+    z = oc.phasepoint(model, metric, np.repeat(th, 6, 1), np.repeat(r, 6, 1))
+    z1, _, _ = oc.leapfrog(model, metric, 0.05, z, 11)
+    assert all((z1.theta[:, j] == z1.theta[:, 0]).all() for j in range(6))
+    zs = oc.phasepoint(model, metric, th, r)
+    z1s, _, _ = oc.leapfrog(model, metric, 0.05, zs, 11)
+    assert (z1s.theta[:, 0] == z1.theta[:, 3]).all()
+
+
+def test_hmc_transition_c_vs_numpy():
+    rng = np.random.default_rng(6)
+    D, N = 6, 9
+    s = np.exp(rng.uniform(-0.5, 0.5, D))
+    a = (oc.DIAG_GAUSS, D, rng.normal(size=D), s)
+    model, metric = oc.Model(*a), oc.Metric(oc.DIAG, s * s)
+    nm, me = onp.Model(*a), onp.Metric(onp.DIAG, s * s)
+    th = rng.normal(size=(D, N))
+    z = oc.phasepoint(model, metric, th, rng.normal(size=(D, N)))
+    nt, et = rng.normal(size=(D, N)), rng.exponential(size=N) * 0.05
+    zc, st = oc.hmc_transition(model, metric, 0.45, 12, z, nt, et)
+    yn, sn = onp.hmc_transition(nm, me, 0.45, 12, onp.phasepoint(nm, me, np.asfortranarray(th), z.r), np.asfortranarray(nt), et)
+    assert 0 < st.is_accept.sum() < N  # both branches exercised
+    assert (st.is_accept.astype(bool) == sn["is_accept"]).all()
+    for f in ("theta", "r", "lp_gradient", "lp_value", "lk_value"):
+        assert rel_err(getattr(zc, f), getattr(yn, f)) < 1e-13, f
+    assert rel_err(st.acceptance_rate, sn["acceptance_rate"]) < 1e-12
+    assert rel_err(st.hamiltonian_energy_error, sn["hamiltonian_energy_error"]) < 1e-9
+    # rejected chains keep theta, momentum flipped (trajectory.jl:283,312-332)
+    rej = ~st.is_accept.astype(bool)
+    assert (zc.theta[:, rej] == th[:, rej]).all()
+
+
+def test_stan_window_schedule_pin():
+    """test/adaptation.jl:131-151: n_adapts=1000 -> start 76, end 950, splits [100,150,250,450,950]."""
+    assert oc.stan_windows(1000) == (76, 950, [100, 150, 250, 450, 950])
+    ws, we, sp = oc.stan_windows(100)
+    assert ws == 76 and we == 50 and sp == []
+
+
+def test_welford_against_naive():
+    """test/adaptation.jl:63-99: Welford var/cov equal the naive estimators (+ Stan regularisation)."""
+    rng = np.random.default_rng(7)
+    D, n = 4, 200
+    X = rng.normal(size=(n, D)) * np.array([1.0, 2.0, 0.5, 3.0])
+    wv, wc = oc.WelfordVar((D,)), oc.WelfordCov(D)
+    for x in X:
+        wv.push(x)
+        wc.push(x)
+    reg = lambda M: n / ((n + 5.0)) * M + 1e-3 * (5.0 / (n + 5.0))
+    assert np.allclose(wv.estimate(), reg(X.var(axis=0, ddof=1)), rtol=1e-12)
+    C = np.cov(X.T, ddof=1)
+    assert np.allclose(wc.estimate(), n / (n + 5.0) * C + 1e-3 * (5.0 / (n + 5.0)) * np.eye(D), rtol=1e-11, atol=1e-14)
+
+
+def test_dual_averaging_closed_form():
+    """stepsize.jl:178-210 restated inline in numpy and compared; finalize -> exp(x_bar)."""
+    da = oc.DualAveraging([0.1, 0.3], delta=0.8)
+    mu = np.log(10 * np.array([0.1, 0.3]))
+    xb, Hb = np.zeros(2), np.zeros(2)
+    rng = np.random.default_rng(8)
+    for m in range(1, 40):
+        alpha = rng.uniform(0, 1.3, size=2)
+        da.adapt(alpha)
+        eta = 1.0 / (m + 10.0)
+        Hb = (1 - eta) * Hb + eta * (0.8 - np.minimum(1.0, alpha))
+        x = mu - Hb * (np.sqrt(m) / 0.05)
+        ex = m ** (-0.75)
+        xb = (1 - ex) * xb + ex * x
+        assert np.allclose(da.eps, np.exp(x), rtol=1e-14) and da.m == m
+    da.finalize()
+    assert np.allclose(da.eps, np.exp(xb), rtol=1e-14)
+
+
+def test_cpu_fused_matches_oracle():
+    from tests.helpers import synth_diag_gauss
+
+    D, N = 128, 64
+    m, s, Minv, th, r = synth_diag_gauss(D, N, 20260923)
+    model, metric = oc.Model(oc.DIAG_GAUSS, D, m, s), oc.Metric(oc.DIAG, Minv)
+    z = oc.phasepoint(model, metric, th, r)
+    a, _, _ = oc.leapfrog(model, metric, 0.1, z, 32)
+    b = oc.leapfrog_omp(model, metric, 0.1, z, 32, n_threads=2)
+    for f in ("theta", "r", "lp_gradient", "lp_value", "lk_value"):
+        assert rel_err(getattr(b, f), getattr(a, f)) < 1e-12, f
