@@ -1,0 +1,99 @@
+"""_lib.py -- ctypes binding of libahmc_b200.so (include/ahmc_b200.h).  Plain pointers and sizes only.
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device is usable the import of
+the product path fails loudly (RuntimeError)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libahmc_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_CALLBACK = 0, -1, -2, -3, -4, -5
+METRIC_UNIT, METRIC_DIAG, METRIC_DENSE = 0, 1, 2
+MODEL_STD_NORMAL, MODEL_DIAG_GAUSS, MODEL_DENSE_GAUSS, MODEL_FUNNEL, MODEL_CALLBACK = 0, 1, 2, 3, 4
+FLAG_HOST_BUFFERS, FLAG_COMPAT_BREAK_ALL, FLAG_ASYNC, FLAG_EXACT_CHECKS, FLAG_NO_REFRESH = 1, 2, 4, 8, 16
+STATUS_NONFINITE = 1
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+
+class Metric(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("Minv", _vp), ("chain_stride", C.c_int64), ("cholU", _vp)]
+
+
+class PhasePoint(C.Structure):
+    _fields_ = [("theta", _vp), ("r", _vp), ("lp_value", _vp), ("lp_gradient", _vp), ("lk_value", _vp),
+                ("lk_gradient", _vp), ("ld", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_steps", _vp), ("is_accept", _vp), ("acceptance_rate", _vp), ("log_density", _vp),
+                ("hamiltonian_energy", _vp), ("hamiltonian_energy_error", _vp),
+                ("max_hamiltonian_energy_error", _vp), ("tree_depth", _vp), ("numerical_error", _vp)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64), ("normal_tape", _vp), ("exp_tape", _vp),
+                ("exp_stride", C.c_int64), ("dir_tape", _vp), ("dir_stride", C.c_int64)]
+
+
+LOGP_GRAD_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _vp, _vp, C.c_int32, C.c_int64, C.c_int64, _vp)
+
+# name -> (restype, argtypes): exactly the entry points include/ahmc_b200.h declares
+PROTOTYPES = {
+    "ahmc_version": (C.c_char_p, []),
+    "ahmc_create": (C.c_int, [C.POINTER(_vp), C.c_int32, _vp]),
+    "ahmc_destroy": (C.c_int, [_vp]),
+    "ahmc_last_error": (C.c_char_p, [_vp]),
+    "ahmc_synchronize": (C.c_int, [_vp]),
+    "ahmc_launch_count": (C.c_int64, [_vp]),
+    "ahmc_model_create": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp, _dp, C.c_double, C.POINTER(_vp)]),
+    "ahmc_model_create_callback": (C.c_int, [_vp, C.c_int32, LOGP_GRAD_FN, _vp, C.POINTER(_vp)]),
+    "ahmc_model_destroy": (C.c_int, [_vp, _vp]),
+    "ahmc_phasepoint_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.POINTER(PhasePoint),
+                                      C.c_uint32]),
+    "ahmc_leapfrog_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp, C.c_int32,
+                                    C.c_double, C.POINTER(PhasePoint), C.POINTER(PhasePoint), _vp, _vp, C.c_uint32]),
+    "ahmc_rand_momentum_f64": (C.c_int, [_vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.POINTER(Rng), _vp,
+                                         C.c_int64, C.c_uint32]),
+    "ahmc_hmc_transition_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp,
+                                          C.c_int32, C.POINTER(Rng), C.POINTER(PhasePoint), C.POINTER(PhasePoint),
+                                          C.POINTER(Stats), C.c_uint32]),
+    "ahmc_nuts_transition_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp,
+                                           C.c_int32, C.c_double, C.POINTER(Rng), C.POINTER(PhasePoint),
+                                           C.POINTER(PhasePoint), C.POINTER(Stats), C.c_uint32]),
+    "ahmc_adapt_summary_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libahmc_b200.so and bind every prototype.  Raises if the library is absent (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python advancedhmc.jl_b200/build.py` "
+            "(or __graft_entry__.build()). There is no CPU fallback for the product path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class AhmcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ahmc error {code}: {msg}")
+        self.code = code
+
+
+class InvalidArgument(AhmcError, ValueError):
+    """AHMC_ERR_INVALID -- the ArgumentError / @argcheck analogue of the reference."""

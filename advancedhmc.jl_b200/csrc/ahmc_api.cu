@@ -1,0 +1,712 @@
+// ahmc_api.cu -- the C ABI of libahmc_b200 (include/ahmc_b200.h): context, models, argument
+// validation, host-buffer staging and kernel dispatch.  No torch types, no exceptions across the ABI.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ahmc_kernels.cuh"
+
+using namespace ahmc;
+
+struct ahmc_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+    int* d_min_break = nullptr;   // device int for COMPAT_BREAK_ALL
+    char* arena = nullptr;        // grow-only device arena used by HOST_BUFFERS staging
+    size_t arena_bytes = 0;
+    double* nuts_scratch = nullptr;  // per-chain NUTS tree workspace
+    size_t nuts_scratch_bytes = 0;
+    double* adapt_scratch = nullptr;
+    size_t adapt_scratch_bytes = 0;
+};
+
+struct ahmc_model {
+    int kind = 0;
+    int D = 0;
+    double* d_p0 = nullptr;
+    double* d_p1 = nullptr;
+    double c0 = 0.0;
+    ahmc_logp_grad_fn fn = nullptr;
+    void* user = nullptr;
+};
+
+namespace {
+
+int fail(ahmc_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(ctx, AHMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                     \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Maps caller arrays to device arrays.  Device-pointer mode: identity.  HOST_BUFFERS mode: bump-allocates
+// from the context arena, copies inputs host->device on the context stream and outputs device->host in finish().
+class Stager {
+public:
+    Stager(ahmc_ctx* c, bool host) : ctx_(c), host_(host) {}
+    // first pass: reserve; second pass: bind.  (two passes so the arena is sized before any copy)
+    size_t need = 0;
+    void reserve(size_t bytes) { need += (bytes + 255) & ~(size_t)255; }
+    int prepare() {
+        if (!host_) return AHMC_OK;
+        ahmc_ctx* ctx = ctx_;
+        if (need > ctx->arena_bytes) {
+            if (ctx->arena) {
+                CU(cudaStreamSynchronize(ctx->stream));
+                CU(cudaFree(ctx->arena));
+                ctx->arena = nullptr;
+                ctx->arena_bytes = 0;
+            }
+            size_t cap = need + need / 4;
+            cudaError_t e = cudaMalloc((void**)&ctx->arena, cap);
+            if (e != cudaSuccess) return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc(%zu) for staging failed: %s", cap, cudaGetErrorString(e));
+            ctx->arena_bytes = cap;
+        }
+        off_ = 0;
+        return AHMC_OK;
+    }
+    template <class T>
+    int in(const T* h, size_t count, const T** d) {
+        if (!h) { *d = nullptr; return AHMC_OK; }
+        if (!host_) { *d = h; return AHMC_OK; }
+        ahmc_ctx* ctx = ctx_;
+        T* p = (T*)alloc(count * sizeof(T));
+        CU(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        *d = p;
+        return AHMC_OK;
+    }
+    template <class T>
+    int out(T* h, size_t count, T** d) {
+        if (!h) { *d = nullptr; return AHMC_OK; }
+        if (!host_) { *d = h; return AHMC_OK; }
+        T* p = (T*)alloc(count * sizeof(T));
+        outs_.push_back({(void*)h, (void*)p, count * sizeof(T)});
+        *d = p;
+        return AHMC_OK;
+    }
+    int finish() {
+        ahmc_ctx* ctx = ctx_;
+        for (auto& o : outs_) CU(cudaMemcpyAsync(o.h, o.d, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return AHMC_OK;
+    }
+    bool host() const { return host_; }
+
+private:
+    struct Out { void* h; void* d; size_t bytes; };
+    void* alloc(size_t bytes) {
+        void* p = ctx_->arena + off_;
+        off_ += (bytes + 255) & ~(size_t)255;
+        return p;
+    }
+    ahmc_ctx* ctx_;
+    bool host_;
+    size_t off_ = 0;
+    std::vector<Out> outs_;
+};
+
+int check_common(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N) {
+    if (!ctx) return AHMC_ERR_INVALID;
+    if (D < 1) return fail(ctx, AHMC_ERR_INVALID, "D must be >= 1 (got %d)", D);
+    if (N < 0) return fail(ctx, AHMC_ERR_INVALID, "N must be >= 0 (got %lld)", (long long)N);
+    if (model) {
+        if (model->D != D)
+            return fail(ctx, AHMC_ERR_INVALID, "AxesMismatch: model has dimension %d but theta has %d rows", model->D, D);
+    }
+    if (metric) {
+        if (metric->kind < AHMC_METRIC_UNIT || metric->kind > AHMC_METRIC_DENSE)
+            return fail(ctx, AHMC_ERR_INVALID, "unknown metric kind %d", metric->kind);
+        if (metric->kind != AHMC_METRIC_UNIT && !metric->Minv)
+            return fail(ctx, AHMC_ERR_INVALID, "metric.Minv is NULL for a Diag/Dense metric");
+        if (metric->kind == AHMC_METRIC_DIAG && metric->chain_stride != 0 && metric->chain_stride < D)
+            return fail(ctx, AHMC_ERR_INVALID, "AxesMismatch: per-chain Minv stride %lld < D=%d (hamiltonian.jl:53-57)",
+                        (long long)metric->chain_stride, D);
+    }
+    int G, E;
+    if (!pick_layout(D, &G, &E))
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "D=%d is outside the register-resident range (1..512) of this build", D);
+    return AHMC_OK;
+}
+
+int check_pp(ahmc_ctx* ctx, const ahmc_phasepoint* z, int32_t D, const char* name, bool need_cache) {
+    if (!z) return fail(ctx, AHMC_ERR_INVALID, "%s is NULL", name);
+    if (!z->theta || !z->r) return fail(ctx, AHMC_ERR_INVALID, "%s.theta / %s.r is NULL", name, name);
+    if (need_cache && (!z->lp_value || !z->lp_gradient || !z->lk_value))
+        return fail(ctx, AHMC_ERR_INVALID, "%s.lp_value / lp_gradient / lk_value is NULL", name);
+    if (z->ld < D)
+        return fail(ctx, AHMC_ERR_INVALID, "%s.ld=%lld < D=%d: length(theta)==length(r)==length(gradient) violated (hamiltonian.jl:94)",
+                    name, (long long)z->ld, D);
+    return AHMC_OK;
+}
+
+size_t metric_minv_count(const ahmc_metric* m, int32_t D, int64_t N) {
+    if (m->kind == AHMC_METRIC_DIAG) return m->chain_stride ? (size_t)m->chain_stride * (size_t)N : (size_t)D;
+    if (m->kind == AHMC_METRIC_DENSE) return (size_t)D * D;
+    return 0;
+}
+
+ModelDev model_dev(const ahmc_model* m) { return ModelDev{m->kind, m->D, m->d_p0, m->d_p1, m->c0}; }
+
+// stage the metric descriptor (device or host pointers) into a MetricDev
+int stage_metric(Stager& st, const ahmc_metric* m, int32_t D, int64_t N, MetricDev* out) {
+    out->kind = m->kind;
+    out->chain_stride = m->kind == AHMC_METRIC_DIAG ? m->chain_stride : 0;
+    int rc = st.in(m->Minv, metric_minv_count(m, D, N), &out->Minv);
+    if (rc) return rc;
+    return st.in(m->kind == AHMC_METRIC_DENSE ? m->cholU : (const double*)nullptr, (size_t)D * D, &out->cholU);
+}
+void reserve_metric(Stager& st, const ahmc_metric* m, int32_t D, int64_t N) {
+    st.reserve(metric_minv_count(m, D, N) * sizeof(double));
+    if (m->kind == AHMC_METRIC_DENSE) st.reserve((size_t)D * D * sizeof(double));
+}
+
+int finish_call(ahmc_ctx* ctx, Stager& st, uint32_t flags) {
+    int rc = st.finish();
+    if (rc) return rc;
+    if (!(flags & AHMC_FLAG_ASYNC) || st.host()) CU(cudaStreamSynchronize(ctx->stream));
+    return AHMC_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* ahmc_version(void) { return "ahmc_b200 0.1.0 (sm_100a)"; }
+
+int ahmc_create(ahmc_ctx** out, int32_t device, void* cuda_stream) {
+    if (!out) return AHMC_ERR_INVALID;
+    *out = nullptr;
+    ahmc_ctx* ctx = new (std::nothrow) ahmc_ctx();
+    if (!ctx) return AHMC_ERR_NOMEM;
+    ctx->device = device;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        // no silent CPU fallback: the product path needs the GPU
+        fprintf(stderr, "ahmc_create: no usable CUDA device %d (%s)\n", device, e != cudaSuccess ? cudaGetErrorString(e) : "out of range");
+        delete ctx;
+        return AHMC_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return AHMC_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    if (cudaMalloc((void**)&ctx->d_min_break, sizeof(int)) != cudaSuccess) {
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return AHMC_ERR_NOMEM;
+    }
+    *out = ctx;
+    return AHMC_OK;
+}
+
+int ahmc_destroy(ahmc_ctx* ctx) {
+    if (!ctx) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_min_break);
+    cudaFree(ctx->arena);
+    cudaFree(ctx->nuts_scratch);
+    cudaFree(ctx->adapt_scratch);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return AHMC_OK;
+}
+
+const char* ahmc_last_error(const ahmc_ctx* ctx) { return ctx ? ctx->err.c_str() : "ahmc: NULL context"; }
+
+int ahmc_synchronize(ahmc_ctx* ctx) {
+    if (!ctx) return AHMC_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return AHMC_OK;
+}
+
+int64_t ahmc_launch_count(const ahmc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- models
+int ahmc_model_create(ahmc_ctx* ctx, int32_t kind, int32_t D, const double* p0, const double* p1, double c0,
+                      ahmc_model** out) {
+    if (!ctx || !out) return AHMC_ERR_INVALID;
+    *out = nullptr;
+    if (D < 1) return fail(ctx, AHMC_ERR_INVALID, "model dimension must be >= 1");
+    if (kind < AHMC_MODEL_STD_NORMAL || kind > AHMC_MODEL_FUNNEL)
+        return fail(ctx, AHMC_ERR_INVALID, "unknown built-in model kind %d", kind);
+    if ((kind == AHMC_MODEL_DIAG_GAUSS || kind == AHMC_MODEL_DENSE_GAUSS) && (!p0 || !p1))
+        return fail(ctx, AHMC_ERR_INVALID, "model kind %d needs p0 and p1", kind);
+    DeviceGuard g(ctx->device);
+    ahmc_model* m = new (std::nothrow) ahmc_model();
+    if (!m) return AHMC_ERR_NOMEM;
+    m->kind = kind;
+    m->D = D;
+    m->c0 = c0;
+    if (kind == AHMC_MODEL_DIAG_GAUSS) {
+        std::vector<double> w((size_t)D);
+        for (int d = 0; d < D; ++d) w[d] = 1.0 / (p1[d] * p1[d]);  // 1/s^2
+        if (cudaMalloc((void**)&m->d_p0, sizeof(double) * D) != cudaSuccess ||
+            cudaMalloc((void**)&m->d_p1, sizeof(double) * D) != cudaSuccess) {
+            ahmc_model_destroy(ctx, m);
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc for model parameters failed");
+        }
+        cudaMemcpy(m->d_p0, p0, sizeof(double) * D, cudaMemcpyHostToDevice);
+        cudaMemcpy(m->d_p1, w.data(), sizeof(double) * D, cudaMemcpyHostToDevice);
+    } else if (kind == AHMC_MODEL_DENSE_GAUSS) {
+        if (cudaMalloc((void**)&m->d_p0, sizeof(double) * D) != cudaSuccess ||
+            cudaMalloc((void**)&m->d_p1, sizeof(double) * (size_t)D * D) != cudaSuccess) {
+            ahmc_model_destroy(ctx, m);
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc for model parameters failed");
+        }
+        cudaMemcpy(m->d_p0, p0, sizeof(double) * D, cudaMemcpyHostToDevice);
+        cudaMemcpy(m->d_p1, p1, sizeof(double) * (size_t)D * D, cudaMemcpyHostToDevice);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ahmc_model_destroy(ctx, m);
+        return fail(ctx, AHMC_ERR_CUDA, "copying model parameters failed: %s", cudaGetErrorString(e));
+    }
+    *out = m;
+    return AHMC_OK;
+}
+
+int ahmc_model_create_callback(ahmc_ctx* ctx, int32_t D, ahmc_logp_grad_fn fn, void* user, ahmc_model** out) {
+    if (!ctx || !out) return AHMC_ERR_INVALID;
+    *out = nullptr;
+    if (D < 1 || !fn) return fail(ctx, AHMC_ERR_INVALID, "callback model needs D >= 1 and a function");
+    ahmc_model* m = new (std::nothrow) ahmc_model();
+    if (!m) return AHMC_ERR_NOMEM;
+    m->kind = AHMC_MODEL_CALLBACK;
+    m->D = D;
+    m->fn = fn;
+    m->user = user;
+    *out = m;
+    return AHMC_OK;
+}
+
+int ahmc_model_destroy(ahmc_ctx* ctx, ahmc_model* m) {
+    if (!m) return AHMC_OK;
+    if (ctx) {
+        DeviceGuard g(ctx->device);
+        cudaFree(m->d_p0);
+        cudaFree(m->d_p1);
+    }
+    delete m;
+    return AHMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- phasepoint
+int ahmc_phasepoint_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                        const ahmc_phasepoint* z, uint32_t flags) {
+    if (!ctx || !model || !metric) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric");
+    int rc = check_common(ctx, model, metric, D, N);
+    if (rc) return rc;
+    if ((rc = check_pp(ctx, z, D, "z", true))) return rc;
+    if (model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
+    if (N == 0) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
+    const size_t DN = (size_t)z->ld * N * sizeof(double), Nb = (size_t)N * sizeof(double);
+    reserve_metric(st, metric, D, N);
+    st.reserve(DN * 4);
+    st.reserve(Nb * 2);
+    if ((rc = st.prepare())) return rc;
+    PhasepointArgs a{};
+    a.model = model_dev(model);
+    if ((rc = stage_metric(st, metric, D, N, &a.metric))) return rc;
+    a.D = D;
+    a.N = N;
+    a.ld = z->ld;
+    if ((rc = st.in((const double*)z->theta, (size_t)z->ld * N, &a.th))) return rc;
+    if ((rc = st.in((const double*)z->r, (size_t)z->ld * N, &a.r))) return rc;
+    if ((rc = st.out(z->lp_value, (size_t)N, &a.lp))) return rc;
+    if ((rc = st.out(z->lp_gradient, (size_t)z->ld * N, &a.g))) return rc;
+    if ((rc = st.out(z->lk_value, (size_t)N, &a.lk))) return rc;
+    if ((rc = st.out(z->lk_gradient, (size_t)z->ld * N, &a.dr))) return rc;
+    int nl = 0;
+    CU(launch_phasepoint(a, ctx->stream, &nl));
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
+// ---------------------------------------------------------------------------------------------- leapfrog
+static int copy_pp_device(ahmc_ctx* ctx, int32_t D, int64_t N, const ahmc_phasepoint* a, const ahmc_phasepoint* b,
+                          cudaMemcpyKind kind) {
+    auto cp2 = [&](double* dst, const double* src) -> cudaError_t {
+        if (!dst || !src || dst == src) return cudaSuccess;
+        return cudaMemcpy2DAsync(dst, (size_t)b->ld * sizeof(double), src, (size_t)a->ld * sizeof(double),
+                                 (size_t)D * sizeof(double), (size_t)N, kind, ctx->stream);
+    };
+    auto cp1 = [&](double* dst, const double* src) -> cudaError_t {
+        if (!dst || !src || dst == src) return cudaSuccess;
+        return cudaMemcpyAsync(dst, src, (size_t)N * sizeof(double), kind, ctx->stream);
+    };
+    CU(cp2(b->theta, a->theta));
+    CU(cp2(b->r, a->r));
+    CU(cp2(b->lp_gradient, a->lp_gradient));
+    CU(cp2(b->lk_gradient, a->lk_gradient));
+    CU(cp1(b->lp_value, a->lp_value));
+    CU(cp1(b->lk_value, a->lk_value));
+    return AHMC_OK;
+}
+
+int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                      double eps, const double* eps_chain, int32_t n_steps, double temper_alpha,
+                      const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, uint32_t* status,
+                      int32_t* steps_done, uint32_t flags) {
+    if (!ctx || !model || !metric) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric");
+    int rc = check_common(ctx, model, metric, D, N);
+    if (rc) return rc;
+    if ((rc = check_pp(ctx, z_in, D, "z_in", true))) return rc;
+    if ((rc = check_pp(ctx, z_out, D, "z_out", true))) return rc;
+    if (model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
+    if (N == 0) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    const bool host = flags & AHMC_FLAG_HOST_BUFFERS;
+    const int n_abs = n_steps < 0 ? -n_steps : n_steps;
+    if (n_abs == 0) {  // the loop body never runs: z is returned unchanged (integrator.jl:233)
+        rc = copy_pp_device(ctx, D, N, z_in, z_out, host ? cudaMemcpyHostToHost : cudaMemcpyDeviceToDevice);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (host) {
+            if (status) memset(status, 0, sizeof(uint32_t) * (size_t)N);
+            if (steps_done) memset(steps_done, 0, sizeof(int32_t) * (size_t)N);
+        } else {
+            if (status) CU(cudaMemsetAsync(status, 0, sizeof(uint32_t) * (size_t)N, ctx->stream));
+            if (steps_done) CU(cudaMemsetAsync(steps_done, 0, sizeof(int32_t) * (size_t)N, ctx->stream));
+            if (!(flags & AHMC_FLAG_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+        }
+        return AHMC_OK;
+    }
+    Stager st(ctx, host);
+    const size_t cin = (size_t)z_in->ld * N, cout = (size_t)z_out->ld * N;
+    reserve_metric(st, metric, D, N);
+    st.reserve(cin * 8 * 3);
+    st.reserve(cout * 8 * 4);
+    st.reserve((size_t)N * 8 * 6);
+    if ((rc = st.prepare())) return rc;
+    LeapfrogArgs a{};
+    a.model = model_dev(model);
+    if ((rc = stage_metric(st, metric, D, N, &a.metric))) return rc;
+    a.D = D;
+    a.N = N;
+    a.eps = eps;
+    if ((rc = st.in(eps_chain, (size_t)N, &a.eps_chain))) return rc;
+    a.n_steps = n_abs;
+    a.fwd = n_steps > 0;
+    a.temper_alpha = temper_alpha;
+    a.ld_in = z_in->ld;
+    a.ld_out = z_out->ld;
+    if ((rc = st.in((const double*)z_in->theta, cin, &a.th_in))) return rc;
+    if ((rc = st.in((const double*)z_in->r, cin, &a.r_in))) return rc;
+    if ((rc = st.in((const double*)z_in->lp_gradient, cin, &a.g_in))) return rc;
+    a.lp_in = nullptr;
+    a.lk_in = nullptr;
+    if ((rc = st.out(z_out->theta, cout, &a.th_out))) return rc;
+    if ((rc = st.out(z_out->r, cout, &a.r_out))) return rc;
+    if ((rc = st.out(z_out->lp_gradient, cout, &a.g_out))) return rc;
+    if ((rc = st.out(z_out->lk_gradient, cout, &a.dr_out))) return rc;
+    if ((rc = st.out(z_out->lp_value, (size_t)N, &a.lp_out))) return rc;
+    if ((rc = st.out(z_out->lk_value, (size_t)N, &a.lk_out))) return rc;
+    if ((rc = st.out(status, (size_t)N, &a.status))) return rc;
+    if ((rc = st.out(steps_done, (size_t)N, &a.steps_done))) return rc;
+    a.flags = flags;
+    const bool compat = flags & AHMC_FLAG_COMPAT_BREAK_ALL;
+    a.min_break = nullptr;
+    if (compat) {
+        const int big = 0x7fffffff;
+        CU(cudaMemcpyAsync(ctx->d_min_break, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        a.min_break = ctx->d_min_break;
+    }
+    int nl = 0;
+    CU(launch_leapfrog(a, ctx->stream, &nl));
+    if (compat) {
+        // reference quirk Q1: `isfinite(z)` is all(...) over every chain, so the first non-finite step
+        // stops ALL chains.  Re-run everyone for exactly that many steps (inputs are untouched unless
+        // the caller aliased z_out = z_in, which COMPAT mode therefore forbids).
+        int mb = 0;
+        CU(cudaMemcpyAsync(&mb, ctx->d_min_break, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (mb < n_abs) {
+            if (!host && z_in->theta == z_out->theta)
+                return fail(ctx, AHMC_ERR_INVALID, "COMPAT_BREAK_ALL cannot re-run an in-place call (z_out aliases z_in)");
+            a.n_steps = mb;
+            a.min_break = nullptr;
+            a.flags |= AHMC_FLAG_EXACT_CHECKS;
+            CU(launch_leapfrog(a, ctx->stream, &nl));
+        }
+    }
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
+// ---------------------------------------------------------------------------------------------- rand_momentum
+int ahmc_rand_momentum_f64(ahmc_ctx* ctx, const ahmc_metric* metric, int32_t D, int64_t N, const ahmc_rng* rng,
+                           double* r, int64_t ld, uint32_t flags) {
+    if (!ctx || !metric || !rng || !r) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/metric/rng/r");
+    int rc = check_common(ctx, nullptr, metric, D, N);
+    if (rc) return rc;
+    if (ld < D) return fail(ctx, AHMC_ERR_INVALID, "ld < D");
+    if (metric->kind == AHMC_METRIC_DENSE && !metric->cholU)
+        return fail(ctx, AHMC_ERR_INVALID, "Dense metric needs cholU for rand_momentum (metric.jl:311-320)");
+    if (N == 0) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
+    reserve_metric(st, metric, D, N);
+    st.reserve((size_t)D * N * 8);
+    st.reserve((size_t)ld * N * 8);
+    if ((rc = st.prepare())) return rc;
+    MomentumArgs a{};
+    if ((rc = stage_metric(st, metric, D, N, &a.metric))) return rc;
+    a.D = D;
+    a.N = N;
+    a.seed = rng->seed;
+    a.offset = rng->offset;
+    if ((rc = st.in(rng->normal_tape, (size_t)D * N, &a.normal_tape))) return rc;
+    if ((rc = st.out(r, (size_t)ld * N, &a.r))) return rc;
+    a.ld = ld;
+    int nl = 0;
+    CU(launch_rand_momentum(a, ctx->stream, &nl));
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
+// ---------------------------------------------------------------------------------------------- transitions
+static int stage_stats(Stager& st, const ahmc_stats* s, int64_t N, StatsDev* d) {
+    memset(d, 0, sizeof *d);
+    if (!s) return AHMC_OK;
+    int rc;
+    if ((rc = st.out(s->n_steps, (size_t)N, &d->n_steps))) return rc;
+    if ((rc = st.out(s->is_accept, (size_t)N, &d->is_accept))) return rc;
+    if ((rc = st.out(s->acceptance_rate, (size_t)N, &d->acceptance_rate))) return rc;
+    if ((rc = st.out(s->log_density, (size_t)N, &d->log_density))) return rc;
+    if ((rc = st.out(s->hamiltonian_energy, (size_t)N, &d->hamiltonian_energy))) return rc;
+    if ((rc = st.out(s->hamiltonian_energy_error, (size_t)N, &d->hamiltonian_energy_error))) return rc;
+    if ((rc = st.out(s->max_hamiltonian_energy_error, (size_t)N, &d->max_hamiltonian_energy_error))) return rc;
+    if ((rc = st.out(s->tree_depth, (size_t)N, &d->tree_depth))) return rc;
+    if ((rc = st.out(s->numerical_error, (size_t)N, &d->numerical_error))) return rc;
+    return AHMC_OK;
+}
+
+static int stage_rng(Stager& st, const ahmc_rng* r, int32_t D, int64_t N, bool nuts, RngDev* d) {
+    d->seed = r->seed;
+    d->offset = r->offset;
+    d->exp_stride = nuts ? r->exp_stride : 1;
+    d->dir_stride = r->dir_stride;
+    int rc;
+    if ((rc = st.in(r->normal_tape, (size_t)D * N, &d->normal_tape))) return rc;
+    if ((rc = st.in(r->exp_tape, (size_t)(nuts ? r->exp_stride : 1) * N, &d->exp_tape))) return rc;
+    if ((rc = st.in(nuts ? r->dir_tape : (const uint8_t*)nullptr, (size_t)r->dir_stride * N, &d->dir_tape))) return rc;
+    return AHMC_OK;
+}
+
+int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                            double eps, const double* eps_chain, int32_t n_steps, const ahmc_rng* rng,
+                            const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, const ahmc_stats* stats,
+                            uint32_t flags) {
+    if (!ctx || !model || !metric || !rng) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric/rng");
+    int rc = check_common(ctx, model, metric, D, N);
+    if (rc) return rc;
+    if ((rc = check_pp(ctx, z_in, D, "z_in", true))) return rc;
+    if ((rc = check_pp(ctx, z_out, D, "z_out", true))) return rc;
+    if (n_steps < 1) return fail(ctx, AHMC_ERR_INVALID, "n_steps must be >= 1 (nsteps(tau) = max(1, ...), trajectory.jl:240-243)");
+    if (model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
+    if (flags & AHMC_FLAG_COMPAT_BREAK_ALL)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "COMPAT_BREAK_ALL is only available on ahmc_leapfrog_f64");
+    if (metric->kind == AHMC_METRIC_DENSE && !metric->cholU && !(flags & AHMC_FLAG_NO_REFRESH))
+        return fail(ctx, AHMC_ERR_INVALID, "Dense metric needs cholU for the momentum refresh (metric.jl:311-320)");
+    if (z_out->lk_gradient)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "transition entry points do not emit lk_gradient; call ahmc_phasepoint_f64 if needed");
+    if (N == 0) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
+    const size_t cin = (size_t)z_in->ld * N, cout = (size_t)z_out->ld * N;
+    reserve_metric(st, metric, D, N);
+    st.reserve(cin * 8 * 3);
+    st.reserve(cout * 8 * 3);
+    st.reserve((size_t)D * N * 8);
+    st.reserve((size_t)N * 8 * 16);
+    if ((rc = st.prepare())) return rc;
+    HmcArgs h{};
+    LeapfrogArgs& a = h.lf;
+    a.model = model_dev(model);
+    if ((rc = stage_metric(st, metric, D, N, &a.metric))) return rc;
+    a.D = D;
+    a.N = N;
+    a.eps = eps;
+    if ((rc = st.in(eps_chain, (size_t)N, &a.eps_chain))) return rc;
+    a.n_steps = n_steps;
+    a.fwd = 1;
+    a.temper_alpha = 0.0;
+    a.ld_in = z_in->ld;
+    a.ld_out = z_out->ld;
+    if ((rc = st.in((const double*)z_in->theta, cin, &a.th_in))) return rc;
+    if ((rc = st.in((const double*)z_in->r, cin, &a.r_in))) return rc;
+    if ((rc = st.in((const double*)z_in->lp_gradient, cin, &a.g_in))) return rc;
+    if ((rc = st.in((const double*)z_in->lp_value, (size_t)N, &a.lp_in))) return rc;
+    if ((rc = st.out(z_out->theta, cout, &a.th_out))) return rc;
+    if ((rc = st.out(z_out->r, cout, &a.r_out))) return rc;
+    if ((rc = st.out(z_out->lp_gradient, cout, &a.g_out))) return rc;
+    if ((rc = st.out(z_out->lp_value, (size_t)N, &a.lp_out))) return rc;
+    if ((rc = st.out(z_out->lk_value, (size_t)N, &a.lk_out))) return rc;
+    a.dr_out = nullptr;
+    a.flags = flags;
+    if ((rc = stage_rng(st, rng, D, N, false, &h.rng))) return rc;
+    if ((rc = stage_stats(st, stats, N, &h.st))) return rc;
+    h.refresh = (flags & AHMC_FLAG_NO_REFRESH) ? 0 : 1;
+    int nl = 0;
+    CU(launch_hmc(h, ctx->stream, &nl));
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
+int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                             double eps, const double* eps_chain, int32_t max_depth, double delta_max,
+                             const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
+                             const ahmc_stats* stats, uint32_t flags) {
+    if (!ctx || !model || !metric || !rng) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric/rng");
+    int rc = check_common(ctx, model, metric, D, N);
+    if (rc) return rc;
+    if ((rc = check_pp(ctx, z_in, D, "z_in", true))) return rc;
+    if ((rc = check_pp(ctx, z_out, D, "z_out", true))) return rc;
+    if (max_depth < 0 || max_depth > 20) return fail(ctx, AHMC_ERR_INVALID, "max_depth must be in 0..20");
+    if (model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
+    if (metric->kind == AHMC_METRIC_DENSE && !metric->cholU && !(flags & AHMC_FLAG_NO_REFRESH))
+        return fail(ctx, AHMC_ERR_INVALID, "Dense metric needs cholU for the momentum refresh (metric.jl:311-320)");
+    if (z_out->lk_gradient)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "transition entry points do not emit lk_gradient; call ahmc_phasepoint_f64 if needed");
+    if (rng->exp_tape && rng->exp_stride < 1) return fail(ctx, AHMC_ERR_INVALID, "exp_tape needs exp_stride >= 1");
+    if (rng->dir_tape && rng->dir_stride < max_depth) return fail(ctx, AHMC_ERR_INVALID, "dir_tape needs dir_stride >= max_depth");
+    if (N == 0) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
+    const size_t cin = (size_t)z_in->ld * N, cout = (size_t)z_out->ld * N;
+    reserve_metric(st, metric, D, N);
+    st.reserve(cin * 8 * 3);
+    st.reserve(cout * 8 * 3);
+    st.reserve((size_t)D * N * 8);
+    st.reserve((size_t)N * 8 * 16);
+    if (rng->exp_tape) st.reserve((size_t)rng->exp_stride * N * 8);
+    if (rng->dir_tape) st.reserve((size_t)rng->dir_stride * N);
+    if ((rc = st.prepare())) return rc;
+    NutsArgs a{};
+    a.model = model_dev(model);
+    if ((rc = stage_metric(st, metric, D, N, &a.metric))) return rc;
+    a.D = D;
+    a.N = N;
+    a.eps = eps;
+    if ((rc = st.in(eps_chain, (size_t)N, &a.eps_chain))) return rc;
+    a.max_depth = max_depth;
+    a.delta_max = delta_max;
+    a.refresh = (flags & AHMC_FLAG_NO_REFRESH) ? 0 : 1;
+    a.ld_in = z_in->ld;
+    a.ld_out = z_out->ld;
+    if ((rc = st.in((const double*)z_in->theta, cin, &a.th_in))) return rc;
+    if ((rc = st.in((const double*)z_in->r, cin, &a.r_in))) return rc;
+    if ((rc = st.in((const double*)z_in->lp_gradient, cin, &a.g_in))) return rc;
+    if ((rc = st.in((const double*)z_in->lp_value, (size_t)N, &a.lp_in))) return rc;
+    if ((rc = st.out(z_out->theta, cout, &a.th_out))) return rc;
+    if ((rc = st.out(z_out->r, cout, &a.r_out))) return rc;
+    if ((rc = st.out(z_out->lp_gradient, cout, &a.g_out))) return rc;
+    if ((rc = st.out(z_out->lp_value, (size_t)N, &a.lp_out))) return rc;
+    if ((rc = st.out(z_out->lk_value, (size_t)N, &a.lk_out))) return rc;
+    a.dr_out = nullptr;
+    if ((rc = stage_rng(st, rng, D, N, true, &a.rng))) return rc;
+    if ((rc = stage_stats(st, stats, N, &a.st))) return rc;
+    // per-chain tree workspace
+    a.scratch_stride = nuts_scratch_doubles_per_chain(D, max_depth);
+    size_t need = (size_t)a.scratch_stride * (size_t)N * sizeof(double);
+    if (need > ctx->nuts_scratch_bytes) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->nuts_scratch);
+        ctx->nuts_scratch = nullptr;
+        ctx->nuts_scratch_bytes = 0;
+        cudaError_t e = cudaMalloc((void**)&ctx->nuts_scratch, need);
+        if (e != cudaSuccess) return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc(%zu) for the NUTS workspace failed: %s", need, cudaGetErrorString(e));
+        ctx->nuts_scratch_bytes = need;
+    }
+    a.scratch = ctx->nuts_scratch;
+    int nl = 0;
+    CU(launch_nuts(a, ctx->stream, &nl));
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
+// ---------------------------------------------------------------------------------------------- adaptor stats
+int ahmc_adapt_summary_f64(ahmc_ctx* ctx, int32_t D, int64_t N, const double* theta, int64_t ld,
+                           const double* acceptance_rate, double* out, uint32_t flags) {
+    if (!ctx || !theta || !out) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/theta/out");
+    if (D < 1 || N < 1 || ld < D) return fail(ctx, AHMC_ERR_INVALID, "need D >= 1, N >= 1, ld >= D");
+    DeviceGuard g(ctx->device);
+    const int blocks = (int)(N < 148 ? N : 148);
+    const size_t need = ((size_t)blocks * (D + 1) + 2) * sizeof(double);
+    if (need > ctx->adapt_scratch_bytes) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->adapt_scratch);
+        ctx->adapt_scratch = nullptr;
+        ctx->adapt_scratch_bytes = 0;
+        if (cudaMalloc((void**)&ctx->adapt_scratch, need) != cudaSuccess)
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc(%zu) for the adaptor workspace failed", need);
+        ctx->adapt_scratch_bytes = need;
+        CU(cudaMemsetAsync(ctx->adapt_scratch, 0, need, ctx->stream));
+    }
+    Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
+    st.reserve((size_t)ld * N * 8);
+    st.reserve((size_t)N * 8);
+    st.reserve((size_t)(2 + 2 * D) * 8);
+    int rc = st.prepare();
+    if (rc) return rc;
+    const double *d_theta, *d_alpha;
+    double* d_out;
+    if ((rc = st.in(theta, (size_t)ld * N, &d_theta))) return rc;
+    if ((rc = st.in(acceptance_rate, (size_t)N, &d_alpha))) return rc;
+    if ((rc = st.out(out, (size_t)(2 + 2 * D), &d_out))) return rc;
+    // workspace: [counter (as 2 doubles)] [partials]
+    unsigned* counter = (unsigned*)ctx->adapt_scratch;
+    double* partial = ctx->adapt_scratch + 2;
+    int nl = 0;
+    CU(launch_adapt_summary(D, N, d_theta, ld, d_alpha, d_out, partial, counter, blocks, ctx->stream, &nl));
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
+}  // extern "C"

@@ -1,0 +1,391 @@
+// ahmc_device.cuh -- device-side building blocks shared by every kernel of libahmc_b200 (sm_100a).
+//
+// Work decomposition ("group-distributed vectors"): one chain is owned by a GROUP of G consecutive
+// lanes of a warp (G in {4,8,16,32}); lane l of the group holds E coordinates d = l + G*e, e < E, so a
+// chain's D <= G*E doubles live in registers for the whole trajectory and every global access of the
+// group is a run of G consecutive doubles (Julia column-major D x N: a chain is contiguous).  Per-chain
+// scalars (log pi, kinetic energy, U-turn dots) are xor-butterfly shuffles inside the group, so all
+// lanes of a group hold bit-identical sums.  No shared memory, no block barrier on the Unit/Diag path.
+//
+// Reference semantics implemented here (citations relative to the AdvancedHMC.jl checkout):
+//   dH/dtheta = (lp, -grad lp)        src/hamiltonian.jl:45-48
+//   dH/dr, neg_energy                 src/hamiltonian.jl:50-68, 155-184
+//   PhasePoint -Inf mapping, isfinite src/hamiltonian.jl:95-104, 141-142
+//   one leapfrog step                 src/integrator.jl:233-247  (+ temper :198-209)
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/ahmc_b200.h"
+
+namespace ahmc {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+struct ModelDev {
+    int kind;
+    int D;
+    const double* p0;  // DIAG_GAUSS: mean; DENSE_GAUSS: mean
+    const double* p1;  // DIAG_GAUSS: w = 1/s^2 ; DENSE_GAUSS: precision D x D (column-major)
+    double c0;
+};
+
+struct MetricDev {
+    int kind;
+    const double* Minv;
+    long long chain_stride;
+    const double* cholU;
+};
+
+// ------------------------------------------------------------------------------------------------
+// group collectives
+// ------------------------------------------------------------------------------------------------
+template <int G>
+struct Grp {
+    static __device__ __forceinline__ double sum(double v) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        return v;
+    }
+    static __device__ __forceinline__ double max(double v) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+        return v;
+    }
+    // value held by lane `src` (0..G-1) of my group
+    static __device__ __forceinline__ double bcast(double v, int src) { return __shfl_sync(FULL, v, src, G); }
+    static __device__ __forceinline__ unsigned gmask() {
+        if (G == 32) return FULL;
+        unsigned lane = threadIdx.x & 31u;
+        return ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));
+    }
+    static __device__ __forceinline__ bool all(bool p) {
+        unsigned b = __ballot_sync(FULL, p);
+        unsigned m = gmask();
+        return (b & m) == m;
+    }
+    static __device__ __forceinline__ bool any(bool p) {
+        unsigned b = __ballot_sync(FULL, p);
+        return (b & gmask()) != 0u;
+    }
+};
+
+__device__ __forceinline__ bool finite_d(double x) { return (__double2hiint(x) & 0x7ff00000) != 0x7ff00000; }
+// exponent field of x >= biased exponent `ebits` (pre-shifted by 20); NaN/Inf always "big"
+__device__ __forceinline__ bool big_d(double x, int ebits) { return (__double2hiint(x) & 0x7ff00000) >= ebits; }
+__device__ __forceinline__ double map_nonfinite(double v) { return finite_d(v) ? v : -CUDART_INF; }
+constexpr int expo_bits(int e) { return (1023 + e) << 20; }
+
+// ------------------------------------------------------------------------------------------------
+// group-distributed vector I/O:  element e of lane l  <->  d = l + G*e
+// ------------------------------------------------------------------------------------------------
+template <int G, int E>
+__device__ __forceinline__ void vload(double (&x)[E], const double* __restrict__ base, int l, int D) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int d = l + G * e;
+        x[e] = (d < D) ? __ldg(base + d) : 0.0;
+    }
+}
+template <int G, int E>
+__device__ __forceinline__ void vload_nc(double (&x)[E], const double* base, int l, int D) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int d = l + G * e;
+        x[e] = (d < D) ? base[d] : 0.0;
+    }
+}
+template <int G, int E>
+__device__ __forceinline__ void vstore(double* base, const double (&x)[E], int l, int D) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int d = l + G * e;
+        if (d < D) base[d] = x[e];
+    }
+}
+
+// y = A x for a D x D column-major matrix in global memory, x/y group-distributed.
+// xs: this group's private slab of >= D doubles in shared memory.  (Dense metric / dense Gaussian
+// target; the register-tiled CTA kernel for these shapes is a separate code path.)
+template <int G, int E>
+__device__ __forceinline__ void matvec(const double* __restrict__ A, int D, const double (&x)[E], double (&y)[E],
+                                       double* xs, int l) {
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        int d = l + G * e;
+        if (d < D) xs[d] = x[e];
+        y[e] = 0.0;
+    }
+    __syncwarp();
+    for (int k = 0; k < D; ++k) {
+        double xk = xs[k];
+        const double* col = A + (long long)D * k;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int d = l + G * e;
+            if (d < D) y[e] = fma(__ldg(col + d), xk, y[e]);
+        }
+    }
+}
+
+// solve U x = z (U upper triangular, column-major) for a group-distributed vector; result in x.
+// Back substitution, one pivot per iteration (metric.jl:311-320 `ldiv!(cholMinv, r)`).
+template <int G, int E>
+__device__ __forceinline__ void upper_solve(const double* __restrict__ U, int D, double (&x)[E], int l) {
+    for (int i = D - 1; i >= 0; --i) {
+        int le = i % G, ee = i / G;
+        double xi = 0.0;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (e == ee) xi = x[e];
+        xi = Grp<G>::bcast(xi, le) / __ldg(U + i + (long long)D * i);
+        const double* col = U + (long long)D * i;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int d = l + G * e;
+            if (d == i)
+                x[e] = xi;
+            else if (d < i)
+                x[e] = fma(-__ldg(col + d), xi, x[e]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// metric:  dH/dr and the kinetic lane-partial  sum_e r_e * (dH/dr)_e   (neg_energy = -sum/2)
+// ------------------------------------------------------------------------------------------------
+template <int METRIC, int G, int E>
+struct MetricOps {
+    double Minv[E];  // Diag only
+    const double* A; // Dense only
+    const double* U;
+    int D;
+
+    __device__ __forceinline__ void load(const MetricDev& m, long long chain, int l, int D_) {
+        D = D_;
+        A = m.Minv;
+        U = m.cholU;
+        if (METRIC == AHMC_METRIC_DIAG) {
+            vload<G, E>(Minv, m.Minv + m.chain_stride * chain, l, D);
+        }
+    }
+    // dr = dH/dr(r)   (hamiltonian.jl:50-68)
+    __device__ __forceinline__ void dHdr(const double (&r)[E], double (&dr)[E], double* xs, int l) const {
+        if (METRIC == AHMC_METRIC_UNIT) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) dr[e] = r[e];
+        } else if (METRIC == AHMC_METRIC_DIAG) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) dr[e] = Minv[e] * r[e];
+        } else {
+            matvec<G, E>(A, D, r, dr, xs, l);
+        }
+    }
+    // r from standard normals z (metric.jl:290-320)
+    __device__ __forceinline__ void rand_momentum(double (&r)[E], int l) const {
+        if (METRIC == AHMC_METRIC_DIAG) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                int d = l + G * e;
+                r[e] = (d < D) ? r[e] / sqrt(Minv[e]) : 0.0;
+            }
+        } else if (METRIC == AHMC_METRIC_DENSE) {
+            upper_solve<G, E>(U, D, r, l);
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// models:  eval(theta) -> g = MINUS grad log pi (what PhasePoint caches), returns log pi (all lanes)
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int G, int E>
+struct ModelOps {
+    double m[E];
+    double w[E];
+    const double* P;
+    double c0;
+    int D;
+
+    __device__ __forceinline__ void load(const ModelDev& md, int l, int D_) {
+        D = D_;
+        c0 = md.c0;
+        P = md.p1;
+        if (MODEL == AHMC_MODEL_DIAG_GAUSS) {
+            vload<G, E>(m, md.p0, l, D);
+            vload<G, E>(w, md.p1, l, D);
+        } else if (MODEL == AHMC_MODEL_DENSE_GAUSS) {
+            vload<G, E>(m, md.p0, l, D);
+        }
+    }
+
+    __device__ __forceinline__ double eval(const double (&th)[E], double (&g)[E], double* xs, int l) const {
+        double part = 0.0;
+        if (MODEL == AHMC_MODEL_STD_NORMAL) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                g[e] = th[e];
+                part = fma(th[e], th[e], part);
+            }
+            return fma(-0.5, Grp<G>::sum(part), c0);
+        } else if (MODEL == AHMC_MODEL_DIAG_GAUSS) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                double diff = th[e] - m[e];
+                g[e] = diff * w[e];
+                part = fma(diff, g[e], part);
+            }
+            return fma(-0.5, Grp<G>::sum(part), c0);
+        } else if (MODEL == AHMC_MODEL_DENSE_GAUSS) {
+            double diff[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) diff[e] = th[e] - m[e];
+            matvec<G, E>(P, D, diff, g, xs, l);
+#pragma unroll
+            for (int e = 0; e < E; ++e) part = fma(diff[e], g[e], part);
+            return fma(-0.5, Grp<G>::sum(part), c0);
+        } else {  // FUNNEL
+            double v = Grp<G>::bcast(th[0], 0);
+            double ev = exp(-v);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                int d = l + G * e;
+                double xe = (d >= 1 && d < D) ? th[e] : 0.0;
+                g[e] = xe * ev;  // -d lp / d th_i = th_i e^{-v}
+                part = fma(xe, g[e], part);
+            }
+            double S = Grp<G>::sum(part);
+            double Dm1 = (double)(D - 1);
+            if (l == 0) g[0] = v / 9.0 - (S - Dm1) * 0.5;  // -(d lp/dv) = v/9 - (S-(D-1))/2
+            return c0 - v * v / 18.0 - (S + Dm1 * v) * 0.5;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// one chain's phase point in registers + one exact leapfrog step
+// ------------------------------------------------------------------------------------------------
+template <int E>
+struct ChainState {
+    double th[E], r[E], g[E];
+    double lp, lk;
+};
+
+// neg kinetic energy and (optionally) dH/dr of the current r
+template <int METRIC, int G, int E>
+__device__ __forceinline__ double kinetic(const MetricOps<METRIC, G, E>& me, const double (&r)[E], double (&dr)[E],
+                                          double* xs, int l) {
+    me.dHdr(r, dr, xs, l);
+    double part = 0.0;
+    if (METRIC == AHMC_METRIC_DIAG) {
+        // -sum(abs2.(r) .* Minv)/2  (hamiltonian.jl:173-177)
+#pragma unroll
+        for (int e = 0; e < E; ++e) part = fma(r[e] * r[e], me.Minv[e], part);
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) part = fma(r[e], dr[e], part);
+    }
+    return -0.5 * Grp<G>::sum(part);
+}
+
+// One leapfrog step (integrator.jl:235-247) with signed step size eps.  Returns isfinite(z)
+// (hamiltonian.jl:141-142), identical on all lanes of the group.  s.lp / s.lk get the -Inf mapping.
+// dr receives dH/dr of the final momentum (PhasePoint.lk.gradient).
+// temper_mul1/2: multiply r before the first / after the second half kick (1.0 = no tempering).
+template <int MODEL, int METRIC, int G, int E>
+__device__ __forceinline__ bool leapfrog_step(ChainState<E>& s, const ModelOps<MODEL, G, E>& mo,
+                                              const MetricOps<METRIC, G, E>& me, double eps, double (&dr)[E],
+                                              double* xs, int l, double temper_mul1 = 1.0,
+                                              double temper_mul2 = 1.0) {
+    const double he = 0.5 * eps;
+    if (temper_mul1 != 1.0) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) s.r[e] *= temper_mul1;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) s.r[e] = fma(-he, s.g[e], s.r[e]);  // r - eps/2 .* gradient
+    me.dHdr(s.r, dr, xs, l);
+#pragma unroll
+    for (int e = 0; e < E; ++e) s.th[e] = fma(eps, dr[e], s.th[e]);  // theta + eps .* dH/dr
+    double lp = mo.eval(s.th, s.g, xs, l);                           // dH/dtheta
+#pragma unroll
+    for (int e = 0; e < E; ++e) s.r[e] = fma(-he, s.g[e], s.r[e]);
+    if (temper_mul2 != 1.0) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) s.r[e] *= temper_mul2;
+    }
+    double lk = kinetic<METRIC, G, E>(me, s.r, dr, xs, l);
+    bool fin = true;
+#pragma unroll
+    for (int e = 0; e < E; ++e) fin = fin && finite_d(s.g[e]) && finite_d(dr[e]);
+    fin = Grp<G>::all(fin) && finite_d(lp) && finite_d(lk);
+    s.lp = map_nonfinite(lp);
+    s.lk = map_nonfinite(lk);
+    return fin;
+}
+
+// ------------------------------------------------------------------------------------------------
+// counter-based RNG: Philox4x32-10 (Salmon et al. 2011), keyed by seed, counter = (chain, draw, stream, offset)
+// ------------------------------------------------------------------------------------------------
+struct Philox {
+    static __device__ __forceinline__ void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+        uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0;
+        c[1] = n1;
+        c[2] = n2;
+        c[3] = n3;
+    }
+    static __device__ __forceinline__ void gen(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t (&out)[4]) {
+        uint32_t c[4] = {(uint32_t)ctr_lo, (uint32_t)(ctr_lo >> 32), (uint32_t)ctr_hi, (uint32_t)(ctr_hi >> 32)};
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            round(c, k0, k1);
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        out[0] = c[0];
+        out[1] = c[1];
+        out[2] = c[2];
+        out[3] = c[3];
+    }
+    // uniform in (0,1): 53 random bits, never 0 or 1
+    static __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
+        uint64_t x = (((uint64_t)a << 32) | b) >> 11;  // 53 bits
+        return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+    }
+};
+
+// stream ids for the counter's high word
+constexpr uint64_t STREAM_NORMAL = 1, STREAM_EXP = 2, STREAM_DIR = 3;
+
+// standard normal for (chain, coordinate d) of transition `offset` (Box-Muller on one Philox block:
+// one block yields two normals; coordinate d uses block d/2, component d%2)
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t offset, long long chain, int d) {
+    uint32_t o[4];
+    Philox::gen(seed, (uint64_t)chain, (offset << 24) ^ (STREAM_NORMAL << 60) ^ (uint64_t)(d >> 1), o);
+    double u1 = Philox::u01(o[0], o[1]), u2 = Philox::u01(o[2], o[3]);
+    double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    return (d & 1) ? rad * s : rad * c;
+}
+// standard exponential, k-th draw of (chain, transition)
+__device__ __forceinline__ double philox_exp(uint64_t seed, uint64_t offset, long long chain, int k) {
+    uint32_t o[4];
+    Philox::gen(seed, (uint64_t)chain, (offset << 24) ^ (STREAM_EXP << 60) ^ (uint64_t)(k >> 1), o);
+    double u = (k & 1) ? Philox::u01(o[2], o[3]) : Philox::u01(o[0], o[1]);
+    return -log(u);
+}
+// direction bit, k-th draw
+__device__ __forceinline__ bool philox_bit(uint64_t seed, uint64_t offset, long long chain, int k) {
+    uint32_t o[4];
+    Philox::gen(seed, (uint64_t)chain, (offset << 24) ^ (STREAM_DIR << 60) ^ (uint64_t)(k >> 7), o);
+    return (o[(k >> 5) & 3] >> (k & 31)) & 1u;
+}
+
+}  // namespace ahmc

@@ -1,0 +1,117 @@
+// ahmc_kernels.cuh -- kernel argument blocks + launch dispatch declarations (host side sees only these).
+#pragma once
+#include "ahmc_device.cuh"
+
+namespace ahmc {
+
+struct LeapfrogArgs {
+    ModelDev model;
+    MetricDev metric;
+    int D;
+    long long N;
+    double eps;               // scalar step size (used when eps_chain == nullptr), sign applied by `fwd`
+    const double* eps_chain;  // per-chain step sizes or nullptr
+    int n_steps;              // >= 1 (absolute)
+    int fwd;                  // 1: forward, 0: backward (integrator.jl:221-226)
+    double temper_alpha;      // <= 0: none
+    const double *th_in, *r_in, *g_in, *lp_in, *lk_in;
+    long long ld_in;
+    double *th_out, *r_out, *g_out, *lp_out, *lk_out, *dr_out;
+    long long ld_out;
+    uint32_t* status;
+    int32_t* steps_done;
+    int* min_break;  // device int: atomicMin of the first non-finite step over all chains (COMPAT_BREAK_ALL)
+    uint32_t flags;
+};
+
+struct PhasepointArgs {
+    ModelDev model;
+    MetricDev metric;
+    int D;
+    long long N;
+    const double *th, *r;
+    double *lp, *g, *lk, *dr;
+    long long ld;
+};
+
+struct MomentumArgs {
+    MetricDev metric;
+    int D;
+    long long N;
+    uint64_t seed, offset;
+    const double* normal_tape;  // D x N contiguous (ld = D) or nullptr
+    double* r;
+    long long ld;
+};
+
+struct StatsDev {
+    int32_t* n_steps;
+    uint8_t* is_accept;
+    double* acceptance_rate;
+    double* log_density;
+    double* hamiltonian_energy;
+    double* hamiltonian_energy_error;
+    double* max_hamiltonian_energy_error;
+    int32_t* tree_depth;
+    uint8_t* numerical_error;
+};
+
+struct RngDev {
+    uint64_t seed, offset;
+    const double* normal_tape;
+    const double* exp_tape;
+    long long exp_stride;
+    const uint8_t* dir_tape;
+    long long dir_stride;
+};
+
+struct HmcArgs {
+    LeapfrogArgs lf;  // th_in/r_in/g_in/lp_in = current phase point; outputs = new phase point
+    RngDev rng;
+    StatsDev st;
+    int refresh;  // 1: draw new momentum
+};
+
+struct NutsArgs {
+    ModelDev model;
+    MetricDev metric;
+    int D;
+    long long N;
+    double eps;
+    const double* eps_chain;
+    int max_depth;
+    double delta_max;
+    RngDev rng;
+    int refresh;
+    const double *th_in, *r_in, *g_in, *lp_in;
+    long long ld_in;
+    double *th_out, *r_out, *g_out, *lp_out, *lk_out, *dr_out;
+    long long ld_out;
+    StatsDev st;
+    double* scratch;          // per-chain tree workspace (see ahmc_nuts.cu)
+    long long scratch_stride; // doubles per chain
+};
+
+// choose (G, E) for a dimension: returns false if D is out of the register-resident range
+bool pick_layout(int D, int* G, int* E);
+
+// launchers (defined in the .cu files); all enqueue on `stream` and return the cudaError_t of the launch
+cudaError_t launch_leapfrog(const LeapfrogArgs& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_nuts(const NutsArgs& a, cudaStream_t stream, int* n_launches);
+long long nuts_scratch_doubles_per_chain(int D, int max_depth);
+cudaError_t launch_adapt_summary(int D, long long N, const double* theta, long long ld, const double* alpha,
+                                 double* out, double* partial, unsigned* counter, int blocks, cudaStream_t st,
+                                 int* n_launches);
+
+constexpr int kBlockThreads = 128;
+
+// dynamic shared memory needed by the dense paths: one D-double slab per group
+inline size_t smem_bytes(int model_kind, int metric_kind, int D, int G) {
+    bool dense = (model_kind == AHMC_MODEL_DENSE_GAUSS) || (metric_kind == AHMC_METRIC_DENSE);
+    return dense ? (size_t)(kBlockThreads / G) * (size_t)D * sizeof(double) : 0;
+}
+
+}  // namespace ahmc

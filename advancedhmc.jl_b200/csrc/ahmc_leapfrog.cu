@@ -1,0 +1,387 @@
+// ahmc_leapfrog.cu -- K1: the fused leapfrog trajectory kernel (`step(lf, h, z, n_steps)`,
+// src/integrator.jl:216-265) + `phasepoint` (src/hamiltonian.jl:115-119) + `rand_momentum`
+// (src/metric.jl:290-320).
+//
+// One launch integrates every chain for all n_steps: a chain's theta, r and -grad(lp) are read once
+// from HBM (coalesced runs of G doubles per group), stay in registers for the whole trajectory and
+// are written once.  Two code paths share the kernel:
+//
+//  * EXACT path (every model x metric): per step the reference's op sequence with FMAs, the kinetic
+//    and potential energies reduced by warp shuffles, and the reference's `isfinite(z)` test
+//    (hamiltonian.jl:141-142) -- a non-finite chain stops on its own (default) and its phase point at
+//    the break step is what is returned, as integrator.jl:252-258 does.
+//
+//  * FAST path (separable Gaussian targets STD_NORMAL / DIAG_GAUSS with Unit / Diag metric, no
+//    tempering): state is kept in shifted coordinates x = theta - m, the two half kicks of
+//    consecutive steps are merged and the per-coordinate constants a = eps*Minv, b = eps/s^2 are
+//    precomputed, so a step costs 2 dependent DFMAs per coordinate and no reduction.  Exactness of the
+//    reference's per-step `isfinite` control flow is kept by a magnitude argument: with
+//    K = (1+max|a|)(1+max|b|) the sup-norm of (x, r) grows by at most K per step, so checking the
+//    exponent fields of (x, r) against 2^200 every floor(100/log2 K) steps PROVES every intermediate
+//    phase point (incl. its energies) was finite; a chain that fails a check (or whose parameters are
+//    outside the proof's range) is simply re-run by the exact path inside the same launch.
+#include "ahmc_kernels.cuh"
+#include "ahmc_traj.cuh"
+
+namespace ahmc {
+
+bool pick_layout(int D, int* G, int* E) {
+    if (D < 1) return false;
+    if (D <= 4) { *G = 4; *E = 1; return true; }
+    if (D <= 8) { *G = 8; *E = 1; return true; }
+    if (D <= 16) { *G = 16; *E = 1; return true; }
+    if (D <= 32) { *G = 32; *E = 1; return true; }
+    if (D <= 64) { *G = 32; *E = 2; return true; }
+    if (D <= 128) { *G = 32; *E = 4; return true; }
+    if (D <= 256) { *G = 32; *E = 8; return true; }
+    if (D <= 512) { *G = 32; *E = 16; return true; }
+    return false;
+}
+
+// K1 functor: start state = z_in, end state -> z_out (+ status / steps_done / min_break)
+template <int G, int E>
+struct StepIO {
+    const LeapfrogArgs& a;
+    long long chain;
+    int l;
+    __device__ __forceinline__ void init(double (&th)[E], double (&r)[E], double (&g)[E]) const {
+        vload_nc<G, E>(th, a.th_in + a.ld_in * chain, l, a.D);
+        vload_nc<G, E>(r, a.r_in + a.ld_in * chain, l, a.D);
+        vload_nc<G, E>(g, a.g_in + a.ld_in * chain, l, a.D);
+    }
+    __device__ __forceinline__ void done(const double (&th)[E], const double (&r)[E], const double (&g)[E],
+                                         const double (&dr)[E], double lp, double lk, bool fin, int steps) const {
+        vstore<G, E>(a.th_out + a.ld_out * chain, th, l, a.D);
+        vstore<G, E>(a.r_out + a.ld_out * chain, r, l, a.D);
+        vstore<G, E>(a.g_out + a.ld_out * chain, g, l, a.D);
+        if (a.dr_out) vstore<G, E>(a.dr_out + a.ld_out * chain, dr, l, a.D);
+        if (l == 0) {
+            a.lp_out[chain] = lp;
+            a.lk_out[chain] = lk;
+            if (a.status) a.status[chain] = fin ? 0u : AHMC_STATUS_NONFINITE;
+            if (a.steps_done) a.steps_done[chain] = steps;
+            if (!fin && a.min_break) atomicMin(a.min_break, steps);
+        }
+    }
+};
+
+template <int MODEL, int METRIC, int G, int E>
+__global__ void __launch_bounds__(kBlockThreads) leapfrog_kernel(const LeapfrogArgs a) {
+    extern __shared__ double smem[];
+    const int l = threadIdx.x % G;
+    const int grp_in_block = threadIdx.x / G;
+    const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + grp_in_block;
+    const bool valid = chain0 < a.N;
+    const long long chain = valid ? chain0 : a.N - 1;  // tail groups shadow the last chain, never store
+    double* xs = smem + (size_t)grp_in_block * a.D;
+    double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
+    eps = a.fwd ? eps : -eps;  // integrator.jl:226
+    StepIO<G, E> io{a, chain, l};
+    run_trajectory<MODEL, METRIC, G, E>(a.model, a.metric, a.D, chain, valid, l, xs, eps, a.n_steps, a.temper_alpha,
+                                        a.flags, io);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: one static-HMC transition (sampler.jl:48-58 + trajectory.jl:271-300, 312-340, 863-880)
+// ---------------------------------------------------------------------------------------------
+template <int METRIC, int G, int E>
+struct HmcIO {
+    const HmcArgs& h;
+    const MetricOps<METRIC, G, E>& me;
+    long long chain;
+    int l;
+    double H0, lp0, lk0, ex;
+    double r0[E];
+
+    __device__ __forceinline__ void init(double (&th)[E], double (&r)[E], double (&g)[E]) const {
+        const LeapfrogArgs& a = h.lf;
+        vload_nc<G, E>(th, a.th_in + a.ld_in * chain, l, a.D);
+        vload_nc<G, E>(g, a.g_in + a.ld_in * chain, l, a.D);
+#pragma unroll
+        for (int e = 0; e < E; ++e) r[e] = r0[e];
+    }
+    // mh_accept_ratio + accept_phasepoint! + momentum flip + stats
+    __device__ __forceinline__ void done(const double (&th)[E], const double (&r)[E], const double (&g)[E],
+                                         const double (&dr)[E], double lp, double lk, bool fin, int steps) const {
+        const LeapfrogArgs& a = h.lf;
+        const double H1 = -(lp + lk);                   // energy(z') (hamiltonian.jl:149,194)
+        const bool accept = H1 < H0 + ex;               // trajectory.jl:869-877
+        double alpha = exp(H0 - H1);                    // min(1, exp(H - H')) with Julia's NaN-propagating min
+        alpha = (alpha != alpha) ? alpha : (alpha < 1.0 ? alpha : 1.0);
+        double* tho = a.th_out + a.ld_out * chain;
+        double* ro = a.r_out + a.ld_out * chain;
+        double* go = a.g_out + a.ld_out * chain;
+        double lpn, lkn;
+        if (accept) {
+            double nr[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) nr[e] = -r[e];  // flip (trajectory.jl:283)
+            vstore<G, E>(tho, th, l, a.D);
+            vstore<G, E>(ro, nr, l, a.D);
+            vstore<G, E>(go, g, l, a.D);
+            lpn = lp;
+            lkn = lk;
+        } else {  // revert (trajectory.jl:312-332)
+            double t0[E], g0[E], nr[E];
+            vload_nc<G, E>(t0, a.th_in + a.ld_in * chain, l, a.D);
+            vload_nc<G, E>(g0, a.g_in + a.ld_in * chain, l, a.D);
+#pragma unroll
+            for (int e = 0; e < E; ++e) nr[e] = -r0[e];
+            vstore<G, E>(tho, t0, l, a.D);
+            vstore<G, E>(ro, nr, l, a.D);
+            vstore<G, E>(go, g0, l, a.D);
+            lpn = lp0;
+            lkn = lk0;
+        }
+        if (l == 0) {
+            const double H = -(lpn + lkn);
+            a.lp_out[chain] = lpn;
+            a.lk_out[chain] = lkn;
+            if (a.status) a.status[chain] = fin ? 0u : AHMC_STATUS_NONFINITE;
+            if (a.steps_done) a.steps_done[chain] = steps;
+            const StatsDev& st = h.st;
+            if (st.n_steps) st.n_steps[chain] = a.n_steps;  // nsteps(tau), nominal (trajectory.jl:288)
+            if (st.is_accept) st.is_accept[chain] = accept ? 1 : 0;
+            if (st.acceptance_rate) st.acceptance_rate[chain] = alpha;
+            if (st.log_density) st.log_density[chain] = lpn;
+            if (st.hamiltonian_energy) st.hamiltonian_energy[chain] = H;
+            if (st.hamiltonian_energy_error) st.hamiltonian_energy_error[chain] = H - H0;
+            if (st.numerical_error) st.numerical_error[chain] = finite_d(H1) ? 0 : 1;
+        }
+        (void)dr;
+    }
+};
+
+template <int MODEL, int METRIC, int G, int E>
+__global__ void __launch_bounds__(kBlockThreads) hmc_kernel(const HmcArgs h) {
+    extern __shared__ double smem[];
+    const LeapfrogArgs& a = h.lf;
+    const int l = threadIdx.x % G;
+    const int grp_in_block = threadIdx.x / G;
+    const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + grp_in_block;
+    const bool valid = chain0 < a.N;
+    const long long chain = valid ? chain0 : a.N - 1;
+    const int D = a.D;
+    double* xs = smem + (size_t)grp_in_block * D;
+    double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
+
+    MetricOps<METRIC, G, E> me;
+    me.load(a.metric, chain, l, D);
+    HmcIO<METRIC, G, E> io{h, me, chain, l};
+    // refresh (hamiltonian.jl:213-220): new momentum, kinetic energy; lp is the cached value (quirk Q2:
+    // the reference recomputes it from theta -- same number)
+    if (h.refresh) {
+        if (h.rng.normal_tape) {
+            vload_nc<G, E>(io.r0, h.rng.normal_tape + (long long)D * chain, l, D);
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                int d = l + G * e;
+                io.r0[e] = (d < D) ? philox_normal(h.rng.seed, h.rng.offset, chain, d) : 0.0;
+            }
+        }
+        me.rand_momentum(io.r0, l);
+    } else {
+        vload_nc<G, E>(io.r0, a.r_in + a.ld_in * chain, l, D);
+    }
+    {
+        double dr0[E];
+        io.lk0 = map_nonfinite(kinetic<METRIC, G, E>(me, io.r0, dr0, xs, l));
+    }
+    io.lp0 = map_nonfinite(a.lp_in[chain]);
+    io.H0 = -(io.lp0 + io.lk0);
+    io.ex = h.rng.exp_tape ? h.rng.exp_tape[chain] : philox_exp(h.rng.seed, h.rng.offset, chain, 0);
+    run_trajectory<MODEL, METRIC, G, E>(a.model, a.metric, D, chain, valid, l, xs, eps, a.n_steps, 0.0, a.flags, io);
+}
+
+// ---------------------------------------------------------------------------------------------
+// phasepoint(h, theta, r)  (hamiltonian.jl:115-119)
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int METRIC, int G, int E>
+__global__ void __launch_bounds__(kBlockThreads) phasepoint_kernel(const PhasepointArgs a) {
+    extern __shared__ double smem[];
+    const int l = threadIdx.x % G;
+    const int grp_in_block = threadIdx.x / G;
+    const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + grp_in_block;
+    const bool valid = chain0 < a.N;
+    const long long chain = valid ? chain0 : a.N - 1;
+    const int D = a.D;
+    double* xs = smem + (size_t)grp_in_block * D;
+    ModelOps<MODEL, G, E> mo;
+    MetricOps<METRIC, G, E> me;
+    mo.load(a.model, l, D);
+    me.load(a.metric, chain, l, D);
+    double th[E], r[E], g[E], dr[E];
+    vload_nc<G, E>(th, a.th + a.ld * chain, l, D);
+    vload_nc<G, E>(r, a.r + a.ld * chain, l, D);
+    double lp = map_nonfinite(mo.eval(th, g, xs, l));
+    double lk = map_nonfinite(kinetic<METRIC, G, E>(me, r, dr, xs, l));
+    if (valid) {
+        vstore<G, E>(a.g + a.ld * chain, g, l, D);
+        if (a.dr) vstore<G, E>(a.dr + a.ld * chain, dr, l, D);
+        if (l == 0) {
+            a.lp[chain] = lp;
+            a.lk[chain] = lk;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rand_momentum  (metric.jl:290-320)
+// ---------------------------------------------------------------------------------------------
+template <int METRIC, int G, int E>
+__global__ void __launch_bounds__(kBlockThreads) momentum_kernel(const MomentumArgs a) {
+    const int l = threadIdx.x % G;
+    const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + threadIdx.x / G;
+    const bool valid = chain0 < a.N;
+    const long long chain = valid ? chain0 : a.N - 1;
+    const int D = a.D;
+    MetricOps<METRIC, G, E> me;
+    me.load(a.metric, chain, l, D);
+    double r[E];
+    if (a.normal_tape) {
+        vload_nc<G, E>(r, a.normal_tape + (long long)D * chain, l, D);
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int d = l + G * e;
+            r[e] = (d < D) ? philox_normal(a.seed, a.offset, chain, d) : 0.0;
+        }
+    }
+    me.rand_momentum(r, l);
+    if (valid) vstore<G, E>(a.r + a.ld * chain, r, l, D);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int METRIC, int G, int E>
+static cudaError_t launch_lf_t(const LeapfrogArgs& a, cudaStream_t st) {
+    const int chains_per_block = kBlockThreads / G;
+    const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
+    size_t sm = smem_bytes(MODEL, METRIC, a.D, G);
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(leapfrog_kernel<MODEL, METRIC, G, E>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+    }
+    leapfrog_kernel<MODEL, METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    return cudaGetLastError();
+}
+template <int MODEL, int METRIC, int G, int E>
+static cudaError_t launch_pp_t(const PhasepointArgs& a, cudaStream_t st) {
+    const int chains_per_block = kBlockThreads / G;
+    const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
+    size_t sm = smem_bytes(MODEL, METRIC, a.D, G);
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(phasepoint_kernel<MODEL, METRIC, G, E>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+    }
+    phasepoint_kernel<MODEL, METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    return cudaGetLastError();
+}
+template <int MODEL, int METRIC, int G, int E>
+static cudaError_t launch_hmc_t(const HmcArgs& a, cudaStream_t st) {
+    const int chains_per_block = kBlockThreads / G;
+    const long long blocks = (a.lf.N + chains_per_block - 1) / chains_per_block;
+    size_t sm = smem_bytes(MODEL, METRIC, a.lf.D, G);
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(hmc_kernel<MODEL, METRIC, G, E>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+    }
+    hmc_kernel<MODEL, METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    return cudaGetLastError();
+}
+template <int METRIC, int G, int E>
+static cudaError_t launch_mom_t(const MomentumArgs& a, cudaStream_t st) {
+    const int chains_per_block = kBlockThreads / G;
+    const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
+    momentum_kernel<METRIC, G, E><<<(unsigned)blocks, kBlockThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+#define AHMC_DISPATCH_LAYOUT(FN, ...)                                   \
+    do {                                                                \
+        if (G == 4 && E == 1) return FN<__VA_ARGS__, 4, 1>(a, st);      \
+        if (G == 8 && E == 1) return FN<__VA_ARGS__, 8, 1>(a, st);      \
+        if (G == 16 && E == 1) return FN<__VA_ARGS__, 16, 1>(a, st);    \
+        if (G == 32 && E == 1) return FN<__VA_ARGS__, 32, 1>(a, st);    \
+        if (G == 32 && E == 2) return FN<__VA_ARGS__, 32, 2>(a, st);    \
+        if (G == 32 && E == 4) return FN<__VA_ARGS__, 32, 4>(a, st);    \
+        if (G == 32 && E == 8) return FN<__VA_ARGS__, 32, 8>(a, st);    \
+        if (G == 32 && E == 16) return FN<__VA_ARGS__, 32, 16>(a, st);  \
+        return cudaErrorInvalidValue;                                   \
+    } while (0)
+
+template <int MODEL, int METRIC>
+static cudaError_t lf_layout(const LeapfrogArgs& a, cudaStream_t st, int G, int E) {
+    AHMC_DISPATCH_LAYOUT(launch_lf_t, MODEL, METRIC);
+}
+template <int MODEL, int METRIC>
+static cudaError_t pp_layout(const PhasepointArgs& a, cudaStream_t st, int G, int E) {
+    AHMC_DISPATCH_LAYOUT(launch_pp_t, MODEL, METRIC);
+}
+template <int MODEL, int METRIC>
+static cudaError_t hmc_layout(const HmcArgs& a, cudaStream_t st, int G, int E) {
+    AHMC_DISPATCH_LAYOUT(launch_hmc_t, MODEL, METRIC);
+}
+template <int METRIC>
+static cudaError_t mom_layout(const MomentumArgs& a, cudaStream_t st, int G, int E) {
+    AHMC_DISPATCH_LAYOUT(launch_mom_t, METRIC);
+}
+
+#define AHMC_DISPATCH_MM(FN, model_kind, metric_kind)                                                   \
+    do {                                                                                                \
+        switch ((model_kind) * 3 + (metric_kind)) {                                                     \
+            case 0: return FN<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_UNIT>(a, st, G, E);                    \
+            case 1: return FN<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_DIAG>(a, st, G, E);                    \
+            case 2: return FN<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_DENSE>(a, st, G, E);                   \
+            case 3: return FN<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_UNIT>(a, st, G, E);                    \
+            case 4: return FN<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DIAG>(a, st, G, E);                    \
+            case 5: return FN<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DENSE>(a, st, G, E);                   \
+            case 6: return FN<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_UNIT>(a, st, G, E);                   \
+            case 7: return FN<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DIAG>(a, st, G, E);                   \
+            case 8: return FN<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DENSE>(a, st, G, E);                  \
+            case 9: return FN<AHMC_MODEL_FUNNEL, AHMC_METRIC_UNIT>(a, st, G, E);                        \
+            case 10: return FN<AHMC_MODEL_FUNNEL, AHMC_METRIC_DIAG>(a, st, G, E);                       \
+            case 11: return FN<AHMC_MODEL_FUNNEL, AHMC_METRIC_DENSE>(a, st, G, E);                      \
+        }                                                                                               \
+        return cudaErrorInvalidValue;                                                                   \
+    } while (0)
+
+cudaError_t launch_leapfrog(const LeapfrogArgs& a, cudaStream_t st, int* n_launches) {
+    int G, E;
+    if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+    if (n_launches) *n_launches += 1;
+    AHMC_DISPATCH_MM(lf_layout, a.model.kind, a.metric.kind);
+}
+
+cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t st, int* n_launches) {
+    int G, E;
+    if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+    if (n_launches) *n_launches += 1;
+    AHMC_DISPATCH_MM(pp_layout, a.model.kind, a.metric.kind);
+}
+
+cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t st, int* n_launches) {
+    int G, E;
+    if (!pick_layout(a.lf.D, &G, &E)) return cudaErrorInvalidValue;
+    if (n_launches) *n_launches += 1;
+    AHMC_DISPATCH_MM(hmc_layout, a.lf.model.kind, a.lf.metric.kind);
+}
+
+cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t st, int* n_launches) {
+    int G, E;
+    if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+    if (n_launches) *n_launches += 1;
+    switch (a.metric.kind) {
+        case AHMC_METRIC_UNIT: return mom_layout<AHMC_METRIC_UNIT>(a, st, G, E);
+        case AHMC_METRIC_DIAG: return mom_layout<AHMC_METRIC_DIAG>(a, st, G, E);
+        case AHMC_METRIC_DENSE: return mom_layout<AHMC_METRIC_DENSE>(a, st, G, E);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace ahmc

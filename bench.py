@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 leapfrog engine (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass of the hot path over one batch: the fused L=32-step leapfrog trajectory
+(`step(Leapfrog(0.1), h, z, 32)`, src/integrator.jl:216-265) of 4096 chains x D=128 on a diagonal Gaussian
+target with a Diag-Euclidean metric -- the configuration BASELINE.json's metric is quoted on.
+Metric: leapfrog-steps*dims/s.  Weak scaling: every rank runs the same 4096-chain batch (chains shard
+with no data-path collective), value = all ranks' units / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CHAINS, DIM, L_STEPS, EPS = 4096, 128, 32, 0.1
+METRIC_NAME = "leapfrog-steps*dims/sec"
+WORKLOAD = "north-star headline: 4096 chains x D=128 diag-Gaussian (s log-spaced 0.1..10), DiagEuclidean Minv=s^2, Leapfrog(0.1), L=32 fused steps per launch"
+SEED = 20260923
+
+
+def synth(N, D, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    s = np.exp(np.linspace(np.log(0.1), np.log(10.0), D))
+    m = np.zeros(D)
+    th = rng.normal(size=(N, D))
+    r = rng.normal(size=(N, D)) / s
+    return m, s, s * s, th, r
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, reasons, mx = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_baselines(m, s, Minv, th, r, full=True):
+    """Timed CPU restatements of the same workload on this box's host cores (oracle/ = test+bench infra).
+    numpy twin = op-for-op with the reference's temporaries, single thread like Julia's broadcast;
+    C/OpenMP = fused good-CPU bound, all cores."""
+    from oracle import oracle_c as oc
+    from oracle import oracle_np as onp
+
+    N, D = th.shape
+    units = N * D * L_STEPS
+    cores = os.cpu_count() or 1
+    om, ome = oc.Model(oc.DIAG_GAUSS, D, m, s), oc.Metric(oc.DIAG, Minv)
+    z0 = oc.phasepoint(om, ome, th.T, r.T)
+    out = oc.PhasePoint(D, N, with_lk_gradient=False)
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        oc.leapfrog_omp(om, ome, EPS, z0, L_STEPS, n_threads=cores, out=out)
+        ts.append(time.perf_counter() - t0)
+    omp = units / float(np.median(ts[1:]))
+    res = {"omp": omp, "cores": cores}
+    if full:
+        nm, nme = onp.Model(onp.DIAG_GAUSS, D, m, s), onp.Metric(onp.DIAG, Minv)
+        y0 = onp.phasepoint(nm, nme, np.asfortranarray(th.T), np.asfortranarray(r.T))
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            onp.step(nm, nme, EPS, y0, L_STEPS)
+            ts.append(time.perf_counter() - t0)
+        res["numpy_1thread"] = units / float(np.median(ts))
+    return res
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The Julia reference cannot
+    run here (no julia binary, nothing to compile into oracle/_ref), so this arm times the oracle port
+    with all host threads (fused C/OpenMP) and reports the single-thread op-for-op numpy twin beside it."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    m, s, Minv, th, r = synth(N_CHAINS, DIM, SEED)
+    from oracle import oracle_c as oc
+
+    cores = os.cpu_count() or 1
+    om, ome = oc.Model(oc.DIAG_GAUSS, DIM, m, s), oc.Metric(oc.DIAG, Minv)
+    z0 = oc.phasepoint(om, ome, th.T, r.T)
+    out = oc.PhasePoint(DIM, N_CHAINS, with_lk_gradient=False)
+    units = N_CHAINS * DIM * L_STEPS
+    for _ in range(args.warmup):
+        oc.leapfrog_omp(om, ome, EPS, z0, L_STEPS, n_threads=cores, out=out)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oc.leapfrog_omp(om, ome, EPS, z0, L_STEPS, n_threads=cores, out=out)
+    dt = time.perf_counter() - t0
+    value = units * args.steps / dt
+    extra = cpu_baselines(m, s, Minv, th, r, full=True)
+    line = {
+        "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "steps*dims/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "chains": N_CHAINS, "D": DIM, "L": L_STEPS, "eps": EPS},
+        "cpu_baseline": {"value": value, "unit": "steps*dims/s", "cores": cores, "kind": "port",
+                         "sample": "full workload per step (4096x128x32), fused C/OpenMP oracle port, all host threads; "
+                                   "the Julia reference itself cannot run here (no julia binary)",
+                         "numpy_twin_1thread": extra.get("numpy_1thread")},
+        "e2e": {"value": value, "unit": "steps*dims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import ahmc_b200 as A
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = A.get_context(local, stream=stream.cuda_stream)
+    hbm_peak, peak_src = peaks()
+
+    m, s, Minv, th, r = synth(N_CHAINS, DIM, SEED + rank)
+    h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s))
+    lf = A.Leapfrog(EPS)
+    K, W = args.steps, args.warmup
+    units_per_step = N_CHAINS * DIM * L_STEPS
+
+    with torch.cuda.stream(stream):
+        z0 = A.phasepoint(h, torch.as_tensor(th, device=dev), torch.as_tensor(r, device=dev))
+        flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 512 MiB > 126 MB L2
+
+        def one_step():
+            return A.step(lf, h, z0, L_STEPS, flags=A.FLAG_ASYNC, with_lk_gradient=False)
+
+        for _ in range(max(W, 3)):
+            flush.zero_()
+            one_step()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        l0 = ctx.launches
+        for i in range(K):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            ev[i][0].record(stream)
+            one_step()
+            ev[i][1].record(stream)
+        torch.cuda.synchronize()
+        launches = ctx.launches - l0
+        # keep the sampler alive for a moment of sustained load so clocks are seen under load
+        t_end = time.time() + 0.4
+        while time.time() < t_end:
+            one_step()
+        torch.cuda.synchronize()
+        clocks = sampler.stop()
+        if world > 1:
+            dist.barrier()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        dev_ms = float(sum(step_ms))
+
+        # ---- HBM-honest shape: 2^20 chains x D=128, ONE leapfrog step per launch, in place (3 GiB of state)
+        honest = None
+        if rank == 0 and not args.no_extras:
+            Nh = 1 << 20
+            g = torch.Generator(device=dev).manual_seed(1)
+            st = torch.as_tensor(s, device=dev)
+            zh = A.phasepoint(h, torch.randn((Nh, DIM), generator=g, dtype=torch.float64, device=dev) * st,
+                              torch.randn((Nh, DIM), generator=g, dtype=torch.float64, device=dev) / st)
+            import ctypes as C
+
+            md, keep = h.metric._desc(DIM, Nh, zh.theta)
+            zc = zh._c(False)
+            call = lambda: ctx.check(ctx.lib.ahmc_leapfrog_f64(ctx.h, h.target.handle(ctx), C.byref(md), DIM, Nh, EPS, None, 1,
+                                                               0.0, C.byref(zc), C.byref(zc), None, None, A.FLAG_ASYNC))
+            for _ in range(3):
+                call()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record(stream)
+            for _ in range(reps):
+                call()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            bytes_launch = Nh * DIM * 48 + Nh * 16
+            honest = {"workload": "2^20 chains x D=128, 1 step per launch, in place (3 GiB state >> L2)",
+                      "ms_per_launch": ms, "achieved": bytes_launch / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": bytes_launch / ms / 1e6 / hbm_peak, "rate_steps_dims_per_s": Nh * DIM / ms * 1e3}
+            del zh
+
+        # ---- K2: fused static-HMC transition (refresh + 32 steps + MH) on the same batch
+        k2 = None
+        if rank == 0 and not args.no_extras:
+            kern = A.HMCKernel(A.Trajectory(A.EndPointTS, lf, A.FixedNSteps(L_STEPS)))
+            prng = A.PhiloxRNG(7)
+            for _ in range(3):
+                A.transition(prng, h, kern, z0, flags=A.FLAG_ASYNC)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(10):
+                A.transition(prng, h, kern, z0, flags=A.FLAG_ASYNC)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            k2 = {"workload": "HMC transition (Philox refresh + 32 fused steps + MH), 4096x128, L2-warm",
+                  "ms": e0.elapsed_time(e1) / 10, "rate_steps_dims_per_s": units_per_step / (e0.elapsed_time(e1) / 10) * 1e3}
+
+    # ---- e2e: the public call with HOST (pinned) buffers, copies inside the timed region
+    thp = torch.as_tensor(th).pin_memory()
+    rp = torch.as_tensor(r).pin_memory()
+    z0h = A.phasepoint(h, thp.numpy(), rp.numpy())
+    gp = torch.as_tensor(z0h.lp.gradient).pin_memory()
+    z0h.theta, z0h.r, z0h.lp.gradient = thp.numpy(), rp.numpy(), gp.numpy()
+    pin = lambda shape: torch.empty(shape, dtype=torch.float64).pin_memory()
+    outs = [pin((N_CHAINS, DIM)) for _ in range(3)] + [pin((N_CHAINS,)) for _ in range(2)]
+    zout = A.PhasePoint(outs[0].numpy(), outs[1].numpy(), A.DualValue(outs[3].numpy(), outs[2].numpy()),
+                        A.DualValue(outs[4].numpy(), None))
+
+    def e2e_step():
+        return A.step(lf, h, z0h, L_STEPS, out=zout)
+
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        ze = e2e_step()
+        _ = float(ze.lp.value[0])  # device->host read of the step's result
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = 3 * N_CHAINS * DIM * 8 + DIM * 8
+    d2h = 3 * N_CHAINS * DIM * 8 + N_CHAINS * (8 + 8 + 4 + 4)
+
+    # ---- reduce over ranks (max time)
+    tt = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = tt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * units_per_step * K / (dev_ms_max * 1e-3)
+    e2e_value = world * units_per_step * K / (e2e_ms_max * 1e-3)
+    B = 48.0 + 24.0 / DIM  # SURVEY 8d streaming-model bytes per step*dim
+    kernel_ms = dev_ms / K  # one launch per step: the event pair brackets exactly the fused kernel
+    achieved = units_per_step * B / (kernel_ms * 1e-3) / 1e9
+    compulsory = (N_CHAINS * DIM * 48 + N_CHAINS * 24) / (kernel_ms * 1e-3) / 1e9
+    fp64_ops = units_per_step * 2 * 2  # 2 DFMA per step*dim on the fast path
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "traffic": None, "peak_source": peak_src, "kernel": "leapfrog_kernel<DIAG_GAUSS,DIAG,G=32,E=4>",
+        "kernel_ms": kernel_ms,
+        "model": "SURVEY 8d streaming contract: (48+24/D) B per step*dim x N*D*L units per launch; the fused L-step "
+                 "kernel keeps state in registers, so its COMPULSORY traffic is 1/L of that (next keys)",
+        "compulsory_bytes_per_launch": N_CHAINS * DIM * 48 + N_CHAINS * 24,
+        "achieved_compulsory": compulsory, "frac_compulsory": compulsory / hbm_peak,
+        "fp64_tflops_fastpath": fp64_ops / (kernel_ms * 1e-3) / 1e12,
+    }
+    cpu = cpu_baselines(m, s, Minv, th, r, full=True) if world == 1 else None
+    line = {
+        "metric": METRIC_NAME, "value": value, "unit": "steps*dims/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "chains_per_gpu": N_CHAINS, "D": DIM, "L": L_STEPS, "eps": EPS,
+                   "parallelism": f"chains sharded x{world}, no data-path collective",
+                   "l2": "flushed between timed iterations (512 MiB memset outside the event pair)"},
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": "steps*dims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_max / K, "path": "ahmc_leapfrog_f64(AHMC_FLAG_HOST_BUFFERS) via ahmc_b200.step on pinned host arrays"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
+    }
+    if cpu:
+        line["cpu_baseline"] = {"value": cpu["numpy_1thread"], "unit": "steps*dims/s", "cores": 1, "kind": "port",
+                                "sample": "full workload (4096x128x32) x3, median; numpy twin op-for-op with the reference's "
+                                          "temporaries, 1 thread like Julia broadcast",
+                                "omp_all_cores": {"value": cpu["omp"], "cores": cpu["cores"]}}
+    if honest:
+        line["roofline_hbm_honest"] = honest
+    if k2:
+        line["hmc_transition"] = k2
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,188 @@
+/*
+ * ahmc_b200.h -- C ABI of libahmc_b200: the B200-native (sm_100a) many-chain leapfrog / HMC / NUTS
+ * engine that slots under AdvancedHMC.jl's `AbstractIntegrator` / `Hamiltonian` / `AbstractMetric`
+ * plugin surface (see INTEGRATION.md for the Julia `ccall` shim that binds every entry point).
+ *
+ * Conventions
+ *  - All entry points are `extern "C"`, return an `int` status (AHMC_OK or a negative AHMC_ERR_*),
+ *    never throw; the message of the last failure is `ahmc_last_error(ctx)`.  Numerical trouble is
+ *    DATA, never an error: non-finite energies are mapped to -Inf exactly like the PhasePoint
+ *    constructor (src/hamiltonian.jl:95-104) and reported in per-chain status/statistics.
+ *  - Arrays are Julia column-major D x N: element (d, chain c) at `d + ld*c` (each chain contiguous).
+ *    Unless AHMC_FLAG_HOST_BUFFERS is passed every array pointer is a DEVICE pointer (e.g. the
+ *    `pointer(::CuArray)` of the reference's CUDA extension, ext/AdvancedHMCCUDAExt.jl).
+ *    With AHMC_FLAG_HOST_BUFFERS they are host pointers; the library stages them through pinned
+ *    memory on the context stream (host->device, kernels, device->host inside the call).
+ *  - The caller owns every buffer; the library neither frees nor retains pointers past the call
+ *    (model / metric parameter arrays are copied at creation).  Outputs may alias inputs
+ *    (z_out == z_in works: every element is read and written by the same thread).
+ *  - A context is bound to one device and one stream and is not thread-safe; calls synchronise the
+ *    stream before returning unless AHMC_FLAG_ASYNC is passed.
+ *  - `lp_gradient` holds MINUS grad log pi, which is what PhasePoint.lp.gradient caches in the
+ *    reference (`dH/dtheta` returns DualValue(lp, -grad), src/hamiltonian.jl:45-48).
+ *
+ * All `file:line` citations are relative to the reference checkout (AdvancedHMC.jl v0.8.6).
+ */
+#ifndef AHMC_B200_H
+#define AHMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AHMC_OK 0
+#define AHMC_ERR_INVALID (-1)     /* bad argument: the ArgumentError / @argcheck analogue (hamiltonian.jl:55-57,94) */
+#define AHMC_ERR_CUDA (-2)        /* CUDA runtime failure */
+#define AHMC_ERR_UNSUPPORTED (-3) /* valid request this build has no kernel for */
+#define AHMC_ERR_NOMEM (-4)
+#define AHMC_ERR_CALLBACK (-5)    /* user gradient callback returned non-zero */
+
+/* metric kinds -- src/metric.jl:17-35 (Unit), :52-72 (Diag), :89-120 (Dense) */
+#define AHMC_METRIC_UNIT 0
+#define AHMC_METRIC_DIAG 1
+#define AHMC_METRIC_DENSE 2
+
+/* built-in log-density models (the `lp` / `dlp/dtheta` closures of `Hamiltonian`, src/hamiltonian.jl:1-6) */
+#define AHMC_MODEL_STD_NORMAL 0  /* lp = c0 - sum(th^2)/2 */
+#define AHMC_MODEL_DIAG_GAUSS 1  /* p0 = mean[D], p1 = std[D]; lp = c0 - sum(((th-m)/s)^2)/2 (test/common.jl:35-77) */
+#define AHMC_MODEL_DENSE_GAUSS 2 /* p0 = mean[D], p1 = precision[DxD] col-major; lp = c0 - (th-mu)'P(th-mu)/2 */
+#define AHMC_MODEL_FUNNEL 3      /* Neal's funnel: v=th[0]; lp = c0 - v^2/18 - sum_{i>=1}(th_i^2 e^{-v} + v)/2 */
+#define AHMC_MODEL_CALLBACK 4    /* user-supplied gradient callback (split-step mode) */
+
+/* flags */
+#define AHMC_FLAG_HOST_BUFFERS 0x1u    /* array arguments are host pointers (staged by the library) */
+#define AHMC_FLAG_COMPAT_BREAK_ALL 0x2u /* mirror the reference's matrix-mode quirk: the first non-finite chain
+                                           stops ALL chains at that step (hamiltonian.jl:141-142 + integrator.jl:252-258).
+                                           Default: each chain stops on its own. */
+#define AHMC_FLAG_ASYNC 0x4u           /* do not synchronise the context stream before returning */
+#define AHMC_FLAG_EXACT_CHECKS 0x8u    /* force the per-step energy/finiteness path (disables the fused fast path) */
+#define AHMC_FLAG_NO_REFRESH 0x10u     /* transitions: keep z_in.r instead of drawing a new momentum */
+
+/* per-chain status bits */
+#define AHMC_STATUS_NONFINITE 0x1u /* !isfinite(z) hit (integrator.jl:252-258) */
+
+typedef struct ahmc_ctx ahmc_ctx;
+typedef struct ahmc_model ahmc_model;
+
+/* Metric descriptor.  `Minv`: Diag -> D entries (chain_stride 0) or D x N per-chain (chain_stride = D,
+ * metric.jl:64); Dense -> D x D column-major.  `cholU`: Dense only, upper factor of cholesky(Minv)
+ * (metric.jl:104-109), needed by ahmc_rand_momentum_f64 and the transition kernels.  Device pointers
+ * (host pointers with AHMC_FLAG_HOST_BUFFERS). */
+typedef struct ahmc_metric {
+    int32_t kind;
+    const double* Minv;
+    int64_t chain_stride;
+    const double* cholU;
+} ahmc_metric;
+
+/* PhasePoint (src/hamiltonian.jl:88-107) as a struct of arrays. */
+typedef struct ahmc_phasepoint {
+    double* theta;       /* D x N */
+    double* r;           /* D x N */
+    double* lp_value;    /* N   : log pi(theta)              (PhasePoint.lp.value)    */
+    double* lp_gradient; /* D x N: MINUS grad log pi(theta)  (PhasePoint.lp.gradient) */
+    double* lk_value;    /* N   : minus kinetic energy       (PhasePoint.lk.value)    */
+    double* lk_gradient; /* D x N or NULL: dH/dr             (PhasePoint.lk.gradient) */
+    int64_t ld;          /* leading dimension, >= D */
+} ahmc_phasepoint;
+
+/* Per-chain transition statistics = the `stat` NamedTuple of src/trajectory.jl:286-298 (static) and
+ * :726-739 (NUTS).  Any pointer may be NULL. */
+typedef struct ahmc_stats {
+    int32_t* n_steps;
+    uint8_t* is_accept;
+    double* acceptance_rate;
+    double* log_density;
+    double* hamiltonian_energy;
+    double* hamiltonian_energy_error;
+    double* max_hamiltonian_energy_error; /* NUTS only */
+    int32_t* tree_depth;                  /* NUTS only */
+    uint8_t* numerical_error;
+} ahmc_stats;
+
+/* Random inputs of one transition.  Tapes (device pointers, or host with HOST_BUFFERS) make a
+ * transition a pure function, which is how parity with the CPU oracle is defined (the reference's
+ * MersenneTwister/Xoshiro streams are not reproducible off-Julia).  Where a tape is NULL
+ * the value comes from the built-in counter-based Philox4x32-10 generator keyed by (seed, chain, draw). */
+typedef struct ahmc_rng {
+    uint64_t seed;
+    uint64_t offset;           /* transition counter: advance by 1 per transition call */
+    const double* normal_tape; /* D x N standard normals for rand_momentum (metric.jl:290-320) */
+    const double* exp_tape;    /* static: N; NUTS: exp_stride x N, consumed in the reference's order */
+    int64_t exp_stride;
+    const uint8_t* dir_tape;   /* NUTS: dir_stride x N direction bits (`rand(rng,Bool)`, trajectory.jl:693) */
+    int64_t dir_stride;
+} ahmc_rng;
+
+/* User gradient callback for AHMC_MODEL_CALLBACK (replaces the Julia closure h.dlp/dth, hamiltonian.jl:45-48).
+ * Must enqueue, on `stream`, work that fills lp[N] and grad[D x N] (PLUS gradient of log pi, column-major,
+ * leading dimension ld) from theta (device pointers).  Return 0 on success. */
+typedef int (*ahmc_logp_grad_fn)(void* user, const double* theta, double* lp, double* grad, int32_t D, int64_t N,
+                                 int64_t ld, void* stream);
+
+/* ---- context --------------------------------------------------------------------------------- */
+const char* ahmc_version(void);
+int ahmc_create(ahmc_ctx** out, int32_t device, void* cuda_stream /* cudaStream_t or NULL = new stream */);
+int ahmc_destroy(ahmc_ctx* ctx);
+const char* ahmc_last_error(const ahmc_ctx* ctx);
+int ahmc_synchronize(ahmc_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches evidence) */
+int64_t ahmc_launch_count(const ahmc_ctx* ctx);
+
+/* ---- models ---------------------------------------------------------------------------------- */
+/* p0/p1 are HOST pointers (copied to the device at creation); meaning per AHMC_MODEL_*. */
+int ahmc_model_create(ahmc_ctx* ctx, int32_t kind, int32_t D, const double* p0, const double* p1, double c0,
+                      ahmc_model** out);
+int ahmc_model_create_callback(ahmc_ctx* ctx, int32_t D, ahmc_logp_grad_fn fn, void* user, ahmc_model** out);
+int ahmc_model_destroy(ahmc_ctx* ctx, ahmc_model* model);
+
+/* ---- hot path -------------------------------------------------------------------------------- */
+/* phasepoint(h, theta, r)  (src/hamiltonian.jl:115-119): fills z->lp_value, lp_gradient, lk_value
+ * (and lk_gradient if non-NULL) from z->theta, z->r. */
+int ahmc_phasepoint_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                        const ahmc_phasepoint* z, uint32_t flags);
+
+/* step(lf, h, z, n_steps)  (src/integrator.jl:216-265) for Leapfrog / TemperedLeapfrog
+ * (JitteredLeapfrog = caller passes the jittered per-chain eps, integrator.jl:140-156).
+ *   eps_chain == NULL -> scalar step size `eps`; else per-chain eps_chain[N] (`AbstractScalarOrVec`).
+ *   n_steps < 0 integrates backward (integrator.jl:221-226).  temper_alpha <= 0: no tempering.
+ *   status[N] / steps_done[N] may be NULL. */
+int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                      double eps, const double* eps_chain, int32_t n_steps, double temper_alpha,
+                      const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, uint32_t* status,
+                      int32_t* steps_done, uint32_t flags);
+
+/* rand_momentum(rng, metric, kinetic, theta)  (src/metric.jl:290-320): r[D x N] from normals (tape or Philox). */
+int ahmc_rand_momentum_f64(ahmc_ctx* ctx, const ahmc_metric* metric, int32_t D, int64_t N, const ahmc_rng* rng,
+                           double* r, int64_t ld, uint32_t flags);
+
+/* One static-HMC transition for all chains: refresh (src/sampler.jl:48-58, hamiltonian.jl:213-220) +
+ * `transition(rng, h, Trajectory{EndPointTS,...,FixedNSteps}, z)` (src/trajectory.jl:271-300,336-340)
+ * + `mh_accept_ratio` (:863-880) + `accept_phasepoint!` (:312-332) + momentum flip (:283). */
+int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                            double eps, const double* eps_chain, int32_t n_steps, const ahmc_rng* rng,
+                            const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, const ahmc_stats* stats,
+                            uint32_t flags);
+
+/* One NUTS transition per chain (MultinomialTS + GeneralisedNoUTurn = what `NUTS(delta)` builds,
+ * src/abstractmcmc.jl:415-419): src/trajectory.jl:626-742, run one chain per warp-group. */
+int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                             double eps, const double* eps_chain, int32_t max_depth, double delta_max,
+                             const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
+                             const ahmc_stats* stats, uint32_t flags);
+
+/* ---- adaptor statistics (src/adaptation) ------------------------------------------------------ */
+/* Pooled summary of one iteration over this GPU's N chains, written to a small device/host record that
+ * the host all-gathers across ranks (one NCCL all-gather) and merges in rank order:
+ *   out[0] = N, out[1] = sum_c min(1, alpha_c)                       (dual averaging, stepsize.jl:178-210)
+ *   out[2 .. 2+D)   = mean_c theta[:,c]        out[2+D .. 2+2D) = sum_c (theta[:,c]-mean)^2
+ * (the (n, mu, M2) Welford partial of massmatrix.jl:141-149 over the chain axis). */
+int ahmc_adapt_summary_f64(ahmc_ctx* ctx, int32_t D, int64_t N, const double* theta, int64_t ld,
+                           const double* acceptance_rate, double* out /* 2+2D */, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AHMC_B200_H */

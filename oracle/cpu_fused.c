@@ -16,9 +16,8 @@
 
 static void fused_separable_chain(const orc_model* m, const orc_metric* me, int D, int64_t c, double eps, int n_steps,
                                   const double* th0, const double* r0, const double* g0, double* th, double* r,
-                                  double* g, double* lp_out, double* lk_out) {
+                                  double* g, double* lp_out, double* lk_out, const double* wv) {
     const double* mu = m->kind == ORC_MODEL_DIAG_GAUSS ? m->p0 : NULL;
-    const double* s = m->kind == ORC_MODEL_DIAG_GAUSS ? m->p1 : NULL;
     const double* Mi = me->kind == ORC_METRIC_DIAG ? me->Minv + me->chain_stride * c : NULL;
     double he = eps / 2;
     double lp = 0, lk = 0;
@@ -35,7 +34,7 @@ static void fused_separable_chain(const orc_model* m, const orc_metric* me, int 
             double mi = Mi ? Mi[d] : 1.0;
             double t = th[d] + eps * (mi * rr);
             double diff = mu ? (mu[d] - t) : -t;
-            double w = s ? 1.0 / (s[d] * s[d]) : 1.0;
+            double w = wv[d];
             double gg = -(diff * w);
             lp += -(diff * diff * w) / 2;
             rr = rr - he * gg;
@@ -61,14 +60,17 @@ void orc_leapfrog_omp(const orc_model* m, const orc_metric* me, int32_t D, int64
     if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
     if (separable) {
+        double* wv = (double*)malloc(sizeof(double) * (size_t)D); /* 1/s^2 hoisted out of the step loop */
+        for (int d = 0; d < D; ++d) wv[d] = m->kind == ORC_MODEL_DIAG_GAUSS ? 1.0 / (m->p1[d] * m->p1[d]) : 1.0;
 #pragma omp parallel for schedule(static)
         for (int64_t c = 0; c < N; ++c) {
             double e = eps_chain ? eps_chain[c] : eps;
             fused_separable_chain(m, me, D, c, e, n_steps, z_in->theta + z_in->ld * c, z_in->r + z_in->ld * c,
                                   z_in->lp_gradient + z_in->ld * c, z_out->theta + z_out->ld * c,
                                   z_out->r + z_out->ld * c, z_out->lp_gradient + z_out->ld * c, &z_out->lp_value[c],
-                                  &z_out->lk_value[c]);
+                                  &z_out->lk_value[c], wv);
         }
+        free(wv);
         return;
     }
     /* generic: chunk chains over threads, each chunk through the scalar oracle */

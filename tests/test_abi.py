@@ -1,0 +1,84 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/ahmc_b200.h declares, and the
+host-side mirror of the reference's integrator interface behaves like test/integrator.jl:34-106."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import ahmc_b200 as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ahmc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ahmc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(os.path.join(ROOT, "advancedhmc.jl_b200", "libahmc_b200.so"))
+    names = _declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(A._lib.PROTOTYPES), set(names) ^ set(A._lib.PROTOTYPES)
+    lib.ahmc_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.ahmc_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        A.get_context(0)
+
+
+def test_product_package_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "advancedhmc.jl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "oracle_c" not in txt and "oracle_np" not in txt and "ahmc_oracle" not in txt, f
+
+
+def test_jitter_and_update_nom_step_size():
+    """test/integrator.jl:34-87."""
+    rng = np.random.default_rng(0)
+    lf = A.Leapfrog(0.1)
+    assert A.nom_step_size(lf) == 0.1 and A.step_size(lf) == 0.1
+    assert A.jitter(rng, lf) is lf
+    lj = A.JitteredLeapfrog(0.1, 0.5)
+    assert lj.eps0 == 0.1 and lj.eps == 0.1 and A.nom_step_size(lj) == 0.1
+    lj2 = A.jitter(rng, lj)
+    assert lj2.eps0 == 0.1 and lj2.eps != 0.1 and A.step_size(lj2) == lj2.eps
+    assert abs(lj2.eps - 0.1) <= 0.05 + 1e-15
+    lf2 = A.update_nom_step_size(lf, 0.5)
+    assert lf2 is not lf and A.nom_step_size(lf2) == 0.5 and A.step_size(lf2) == 0.5
+    lj3 = A.update_nom_step_size(lj, 0.2)
+    assert A.nom_step_size(lj3) == 0.2 and A.step_size(lj3) == 0.1
+    ljv = A.jitter(rng, A.JitteredLeapfrog(np.full(5, 0.1), 1.0))
+    assert ljv.eps.shape == (5,) and np.all(ljv.eps >= 0) and np.all(ljv.eps <= 0.2) and len(set(ljv.eps)) == 5
+
+
+def test_temper_schedule():
+    """test/integrator.jl:89-106."""
+    lf = A.TemperedLeapfrog(0.01, 4.0)
+    r = np.ones(5)
+    got = [A.temper(lf, r, (i, half), 3)[0] for i in (1, 2, 3) for half in (True, False)]
+    assert got == [2.0, 2.0, 2.0, 0.5, 0.5, 0.5]
+    with pytest.raises(IndexError):
+        A.temper(lf, r, (4, False), 3)
+
+
+def test_nsteps():
+    """trajectory.jl:240-243."""
+    assert A.nsteps(A.Trajectory(A.EndPointTS, A.Leapfrog(0.1), A.FixedNSteps(7))) == 7
+    assert A.nsteps(A.Trajectory(A.EndPointTS, A.Leapfrog(0.1), A.FixedIntegrationTime(1.0))) == 10
+    assert A.nsteps(A.Trajectory(A.EndPointTS, A.Leapfrog(3.0), A.FixedIntegrationTime(1.0))) == 1
+    with pytest.raises(ValueError):
+        A.nsteps(A.Trajectory(A.EndPointTS, A.Leapfrog(np.full(3, 0.1)), A.FixedIntegrationTime(1.0)))

@@ -1,0 +1,369 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against
+(i) the committed 50-digit known answers and (ii) the CPU oracle on the same seeded inputs.
+Tolerance: 1e-10 relative fp64 (BASELINE.json north_star), written out below as TOL."""
+import numpy as np
+import pytest
+import torch
+
+import ahmc_b200 as A
+from oracle import oracle_c as oc
+from tests.helpers import METRIC_KINDS, MODEL_KINDS, case_arrays, golden_cases, rel_err, synth_diag_gauss
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+GOLD = golden_cases()
+DEV = "cuda:0"
+
+
+def T(a):
+    """(D,N) Fortran numpy -> (N,D) contiguous cuda tensor (same bytes)."""
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a).T), dtype=torch.float64, device=DEV)
+
+
+def F(t):
+    """(N,D) tensor / ndarray -> (D,N) numpy view for comparison with the oracle."""
+    a = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    return a.T if a.ndim == 2 else a
+
+
+def make_target(kind, D, p0, p1, c0):
+    if kind == "std_normal":
+        return A.StdNormal(D, c0)
+    if kind == "diag_gauss":
+        t = A.DiagGaussian(p0, p1, normalised=False)
+        t.c0 = c0
+        return t
+    if kind == "dense_gauss":
+        return A.DenseGaussian(p0, p1, c0)
+    return A.Funnel(D, c0)
+
+
+def make_metric(kind, Minv, D):
+    if kind == "unit":
+        return A.UnitEuclideanMetric(D)
+    if kind == "diag":
+        Mi = np.asarray(Minv)
+        return A.DiagEuclideanMetric(np.ascontiguousarray(Mi.T) if Mi.ndim == 2 else Mi)
+    return A.DenseEuclideanMetric(np.asarray(Minv))
+
+
+def assert_pp_close(z, ref, tol=TOL, fields=("theta", "r", "lp_gradient", "lp_value", "lk_value")):
+    got = dict(theta=F(z.theta), r=F(z.r), lp_gradient=F(z.lp.gradient), lp_value=F(z.lp.value), lk_value=F(z.lk.value))
+    if z.lk.gradient is not None:
+        got["lk_gradient"] = F(z.lk.gradient)
+    for f in fields:
+        want = ref[f] if isinstance(ref, dict) else getattr(ref, f)
+        assert rel_err(got[f], want) < tol, (f, rel_err(got[f], want))
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+@pytest.mark.parametrize("exact", [False, True], ids=["auto", "exact_checks"])
+def test_leapfrog_matches_mp50_golden(case, exact):
+    a = case_arrays(case)
+    D = case["D"]
+    h = A.Hamiltonian(make_metric(case["metric"], a["Minv"], D), make_target(case["model"], D, a["p0"], a["p1"], case["c0"]))
+    z0 = A.phasepoint(h, T(a["theta0"]), T(a["r0"]))
+    eps = a["eps"] if np.ndim(a["eps"]) == 0 else torch.as_tensor(a["eps"], device=DEV)
+    lf = A.TemperedLeapfrog(eps, case["temper_alpha"]) if case["temper_alpha"] else A.Leapfrog(eps)
+    z1, info = A.step(lf, h, z0, case["n_steps"], flags=A.FLAG_EXACT_CHECKS if exact else 0, return_info=True)
+    assert (info.status == 0).all() and (info.steps_done == abs(case["n_steps"])).all()
+    assert_pp_close(z1, a)
+
+
+LAYOUT_DS = [1, 3, 4, 5, 8, 10, 16, 17, 32, 33, 64, 100, 128, 129, 200, 256, 300, 512]
+
+
+@pytest.mark.parametrize("D", LAYOUT_DS)
+def test_every_register_layout_diag(D):
+    """all (G,E) layouts, ragged N (not a multiple of chains-per-block), per-chain eps, fast path."""
+    rng = np.random.default_rng(D)
+    N = 37
+    s = np.exp(rng.uniform(-1, 1, D))
+    m = rng.normal(size=D)
+    Minv = np.exp(rng.uniform(-1, 1, D))
+    th, r = rng.normal(size=(D, N)), rng.normal(size=(D, N))
+    eps = 0.05 * np.exp(rng.uniform(-0.3, 0.3, N))
+    om, ome = oc.Model(oc.DIAG_GAUSS, D, m, s, 0.25), oc.Metric(oc.DIAG, Minv)
+    zo, _, _ = oc.leapfrog(om, ome, eps, oc.phasepoint(om, ome, th, r), 13)
+    tgt = A.DiagGaussian(m, s, normalised=False)
+    tgt.c0 = 0.25
+    h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), tgt)
+    z0 = A.phasepoint(h, T(th), T(r))
+    z1 = A.step(A.Leapfrog(torch.as_tensor(eps, device=DEV)), h, z0, 13)
+    assert_pp_close(z1, zo, fields=("theta", "r", "lp_gradient", "lp_value", "lk_value", "lk_gradient"))
+
+
+MODELS = ["std_normal", "diag_gauss", "dense_gauss", "funnel"]
+METRICS = ["unit", "diag", "diag_perchain", "dense"]
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("D,n_steps", [(6, 9), (40, -7), (130, 5)])
+def test_model_metric_matrix_vs_oracle(model, metric, D, n_steps):
+    rng = np.random.default_rng(abs(hash((model, metric, D))) % 2**31)
+    N = 11
+    p0 = p1 = None
+    if model == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.7, 0.7, D))
+    elif model == "dense_gauss":
+        B = rng.normal(size=(D, D))
+        p0, p1 = rng.normal(size=D), B @ B.T / D + np.eye(D)
+    Minv = None
+    mk = "diag" if metric == "diag_perchain" else metric
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.7, 0.7, D))
+    elif metric == "diag_perchain":
+        Minv = np.exp(rng.uniform(-0.7, 0.7, (D, N)))
+    elif metric == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+    scale = 0.3 if model == "funnel" else 1.0
+    th, r = rng.normal(size=(D, N)) * scale, rng.normal(size=(D, N))
+    eps = 0.04
+    om, ome = oc.Model(MODEL_KINDS[model], D, p0, p1, 0.5), oc.Metric(METRIC_KINDS[mk], Minv)
+    z0o = oc.phasepoint(om, ome, th, r)
+    zo, st_o, dn_o = oc.leapfrog(om, ome, eps, z0o, n_steps)
+    h = A.Hamiltonian(make_metric(mk, Minv, D), make_target(model, D, p0, p1, 0.5))
+    z0 = A.phasepoint(h, T(th), T(r))
+    assert_pp_close(z0, z0o, tol=1e-12, fields=("lp_gradient", "lp_value", "lk_value", "lk_gradient"))
+    z1, info = A.step(A.Leapfrog(eps), h, z0, n_steps, return_info=True)
+    assert (F(info.steps_done) == dn_o).all()
+    assert_pp_close(z1, zo, fields=("theta", "r", "lp_gradient", "lp_value", "lk_value", "lk_gradient"))
+
+
+def test_host_buffer_call_equals_device_call():
+    D, N = 128, 257
+    m, s, Minv, th, r = synth_diag_gauss(D, N, 7)
+    h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s))
+    zd = A.step(A.Leapfrog(0.1), h, A.phasepoint(h, T(th), T(r)), 32)
+    thh, rh = np.ascontiguousarray(th.T), np.ascontiguousarray(r.T)
+    zh = A.step(A.Leapfrog(0.1), h, A.phasepoint(h, thh, rh), 32)
+    assert isinstance(zh.theta, np.ndarray)
+    for a, b in [(zh.theta, zd.theta), (zh.r, zd.r), (zh.lp.value, zd.lp.value), (zh.lk.value, zd.lk.value),
+                 (zh.lp.gradient, zd.lp.gradient), (zh.lk.gradient, zd.lk.gradient)]:
+        assert np.array_equal(a, b.cpu().numpy())
+
+
+def test_fast_path_equals_exact_path_within_tol_and_headline_shape_vs_oracle():
+    """BASELINE headline shape: 4096 chains x D=128 diagonal Gaussian, Diag metric, eps=0.1, L=32."""
+    D, N = 128, 4096
+    m, s, Minv, th, r = synth_diag_gauss(D, N, 20260923)
+    h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s))
+    z0 = A.phasepoint(h, T(th), T(r))
+    zf = A.step(A.Leapfrog(0.1), h, z0, 32)
+    ze = A.step(A.Leapfrog(0.1), h, z0, 32, flags=A.FLAG_EXACT_CHECKS)
+    om, ome = oc.Model(oc.DIAG_GAUSS, D, m, s, h.target.c0), oc.Metric(oc.DIAG, Minv)
+    zo, _, _ = oc.leapfrog(om, ome, 0.1, oc.phasepoint(om, ome, th, r), 32)
+    assert_pp_close(zf, zo)
+    assert_pp_close(ze, zo)
+    assert rel_err(F(zf.theta), F(ze.theta)) < 1e-12
+
+
+def test_nonfinite_per_chain_freeze_and_compat_break_all():
+    """integrator.jl:252-258, hamiltonian.jl:95-104,141-142, quirk Q1."""
+    D, N = 3, 6
+    h = A.Hamiltonian(A.UnitEuclideanMetric(D), A.StdNormal(D))
+    th = np.ones((D, N))
+    th[:, 2] = 1e200
+    th[1, 4] = np.inf
+    r = np.ones((D, N))
+    om, ome = oc.Model(oc.STD_NORMAL, D), oc.Metric(oc.UNIT)
+    z0o = oc.phasepoint(om, ome, th, r)
+    z0 = A.phasepoint(h, T(th), T(r))
+    assert F(z0.lp.value)[2] == -np.inf and F(z0.lp.value)[4] == -np.inf
+    for compat in (False, True):
+        zo, st_o, dn_o = oc.leapfrog(om, ome, 0.1, z0o, 5, compat_break_all=compat)
+        z1, info = A.step(A.Leapfrog(0.1), h, z0, 5, flags=A.FLAG_COMPAT_BREAK_ALL if compat else 0, return_info=True)
+        assert (F(info.steps_done) == dn_o).all(), (compat, F(info.steps_done), dn_o)
+        assert (F(info.status) == st_o).all()
+        ok = [0, 1, 3, 5]
+        assert rel_err(F(z1.theta)[:, ok], zo.theta[:, ok]) < TOL
+        assert F(z1.lp.value)[2] == -np.inf and F(z1.lk.value)[2] == zo.lk_value[2]
+        assert np.array_equal(np.isnan(F(z1.theta)), np.isnan(zo.theta))
+
+
+def test_fast_path_falls_back_to_exact_on_huge_values():
+    """A chain that leaves the magnitude-proof range is re-run by the exact path in the same launch."""
+    D, N = 128, 9
+    m, s, Minv, th, r = synth_diag_gauss(D, N, 3)
+    th[5, 3] = 1e250  # finite, but its square overflows: non-finite energy at step 1
+    th[7, 6] = 1e120  # large but every energy stays finite: must complete all steps
+    om, ome = oc.Model(oc.DIAG_GAUSS, D, m, s), oc.Metric(oc.DIAG, Minv)
+    zo, st_o, dn_o = oc.leapfrog(om, ome, 0.1, oc.phasepoint(om, ome, th, r), 20)
+    h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s, normalised=False))
+    z1, info = A.step(A.Leapfrog(0.1), h, A.phasepoint(h, T(th), T(r)), 20, return_info=True)
+    assert list(dn_o) == list(F(info.steps_done)) and dn_o[3] == 1 and dn_o[6] == 20
+    assert (F(info.status) == st_o).all()
+    ok = [c for c in range(N) if c != 3]
+    assert rel_err(F(z1.theta)[:, ok], zo.theta[:, ok]) < TOL and rel_err(F(z1.r)[:, ok], zo.r[:, ok]) < TOL
+    assert rel_err(F(z1.lk.value)[ok], zo.lk_value[ok]) < TOL
+
+
+def test_in_place_and_zero_steps_and_empty():
+    D, N = 10, 64
+    rng = np.random.default_rng(0)
+    h = A.Hamiltonian(A.UnitEuclideanMetric(D), A.StdNormal(D))
+    z0 = A.phasepoint(h, T(rng.normal(size=(D, N))), T(rng.normal(size=(D, N))))
+    ref = A.step(A.Leapfrog(0.1), h, z0, 32)
+    same = A.step(A.Leapfrog(0.1), h, z0, 0)
+    assert torch.equal(same.theta, z0.theta) and torch.equal(same.lp.value, z0.lp.value)
+    # in place through the raw ABI: z_out == z_in
+    import ctypes as C
+
+    ctx = A.get_context(0)
+    zc = z0._c()
+    md, _ = h.metric._desc(D, N, z0.theta)
+    ctx.check(ctx.lib.ahmc_leapfrog_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, 0.1, None, 32, 0.0,
+                                        C.byref(zc), C.byref(zc), None, None, 0))
+    assert torch.equal(z0.theta, ref.theta) and torch.equal(z0.r, ref.r) and torch.equal(z0.lk.value, ref.lk.value)
+    # N = 0 is a no-op
+    e = torch.empty((0, D), dtype=torch.float64, device=DEV)
+    ze = A.phasepoint(h, e, e.clone())
+    assert A.step(A.Leapfrog(0.1), h, ze, 3).theta.shape == (0, D)
+
+
+def test_argument_errors_like_the_reference():
+    """ArgumentError analogues (hamiltonian.jl:53-57, :94)."""
+    D, N = 5, 4
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D + 1)), A.StdNormal(D))
+    th = torch.zeros((N, D), dtype=torch.float64, device=DEV)
+    with pytest.raises(ValueError, match="AxesMismatch"):
+        A.phasepoint(h, th, th.clone())
+    h2 = A.Hamiltonian(A.UnitEuclideanMetric(D), A.StdNormal(D + 2))
+    with pytest.raises(ValueError, match="AxesMismatch"):
+        A.phasepoint(h2, th, th.clone())
+    with pytest.raises(ValueError):
+        A.phasepoint(A.Hamiltonian(A.UnitEuclideanMetric(D), A.StdNormal(D)), th, torch.zeros((N, D + 1), dtype=torch.float64, device=DEV))
+    big = torch.zeros((2, 513), dtype=torch.float64, device=DEV)
+    with pytest.raises(A.AhmcError, match="register-resident"):
+        A.phasepoint(A.Hamiltonian(A.UnitEuclideanMetric(513), A.StdNormal(513)), big, big.clone())
+
+
+# ------------------------------------------------------------------------------------------------ properties at scale
+def test_full_size_properties():
+    """Size-independent properties at 2^17 chains x D=128 (no oracle run needed):
+    reversibility, chain independence / permutation equivariance, energy error O(eps^2)."""
+    D, N = 128, 1 << 17
+    g = torch.Generator(device=DEV).manual_seed(1)
+    s = torch.exp(torch.linspace(np.log(0.1), np.log(10.0), D, dtype=torch.float64, device=DEV))
+    h = A.Hamiltonian(A.DiagEuclideanMetric(s * s), A.DiagGaussian(np.zeros(D), s.cpu().numpy()))
+    th = torch.randn((N, D), generator=g, dtype=torch.float64, device=DEV) * s
+    r = torch.randn((N, D), generator=g, dtype=torch.float64, device=DEV) / s
+    z0 = A.phasepoint(h, th, r)
+    z1 = A.step(A.Leapfrog(0.1), h, z0, 32)
+    zb = A.step(A.Leapfrog(0.1), h, z1, -32)
+    assert ((zb.theta - th).abs().max() / th.abs().max()).item() < 1e-12
+    assert ((zb.r - r).abs().max() / r.abs().max()).item() < 1e-12
+    dH = (A.energy(z1) - A.energy(z0)).abs().max().item()
+    assert dH < 0.5 * D  # leapfrog at eps=0.1 on unit-frequency modes: bounded energy error
+    perm = torch.randperm(N, device=DEV, generator=g)
+    zp = A.step(A.Leapfrog(0.1), h, A.phasepoint(h, th[perm].contiguous(), r[perm].contiguous()), 32)
+    assert torch.equal(zp.theta, z1.theta[perm]) and torch.equal(zp.lk.value, z1.lk.value[perm])
+    # 32 x step(1) == step(32) within rounding (test/integrator.jl:17-32, there atol 5e-3)
+    zl = z0
+    for _ in range(4):
+        zl = A.step(A.Leapfrog(0.1), h, zl, 8)
+    assert ((zl.theta - z1.theta).abs().max() / z1.theta.abs().max()).item() < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ transitions
+@pytest.mark.parametrize("model,metric,D", [("diag_gauss", "diag", 128), ("std_normal", "unit", 10),
+                                            ("funnel", "diag", 20), ("dense_gauss", "dense", 12)])
+def test_hmc_transition_vs_oracle_with_tapes(model, metric, D):
+    rng = np.random.default_rng(D)
+    N = 301
+    p0 = p1 = Minv = None
+    if model == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.5, 0.5, D))
+    elif model == "dense_gauss":
+        B = rng.normal(size=(D, D))
+        p0, p1 = rng.normal(size=D), B @ B.T / D + np.eye(D)
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    elif metric == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+    th = rng.normal(size=(D, N)) * (0.3 if model == "funnel" else 1.0)
+    nt, et = rng.normal(size=(D, N)), rng.exponential(size=N) * 0.1
+    eps, L = (0.35, 10) if model != "funnel" else (0.1, 8)
+    om, ome = oc.Model(MODEL_KINDS[model], D, p0, p1, 0.0), oc.Metric(METRIC_KINDS[metric], Minv)
+    z0o = oc.phasepoint(om, ome, th, np.zeros((D, N)))
+    zo, so = oc.hmc_transition(om, ome, eps, L, z0o, nt, et)
+    h = A.Hamiltonian(make_metric(metric, Minv, D), make_target(model, D, p0, p1, 0.0))
+    z0 = A.phasepoint(h, T(th), T(np.zeros((D, N))))
+    tau = A.Trajectory(A.EndPointTS, A.Leapfrog(eps), A.FixedNSteps(L))
+    tr = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(et, device=DEV)), h, A.HMCKernel(tau), z0)
+    acc = F(tr.stat["is_accept"]).astype(bool)
+    assert 0 < acc.sum() < N
+    assert (acc == so.is_accept.astype(bool)).all()
+    assert_pp_close(tr.z, zo)
+    assert rel_err(F(tr.stat["acceptance_rate"]), so.acceptance_rate) < 1e-9
+    assert np.allclose(F(tr.stat["hamiltonian_energy_error"]), so.hamiltonian_energy_error, rtol=0, atol=1e-9 * D)
+    assert rel_err(F(tr.stat["hamiltonian_energy"]), so.hamiltonian_energy) < TOL
+    assert (F(tr.stat["n_steps"]) == L).all() and (F(tr.stat["numerical_error"]) == so.numerical_error).all()
+    assert tr.stat["step_size"] == eps and tr.stat["nom_step_size"] == eps
+
+
+def test_rand_momentum_tape_and_philox_moments():
+    D, N = 6, 50_000
+    rng = np.random.default_rng(0)
+    B = rng.normal(size=(D, D))
+    Minv = B @ B.T / D + 0.5 * np.eye(D)
+    nt = rng.normal(size=(D, 64))
+    for me_o, me in [(oc.Metric(oc.UNIT), A.UnitEuclideanMetric(D)), (oc.Metric(oc.DIAG, np.diag(Minv).copy()), A.DiagEuclideanMetric(np.diag(Minv).copy())),
+                     (oc.Metric(oc.DENSE, Minv), A.DenseEuclideanMetric(Minv))]:
+        got = F(A.rand_momentum(A.TapeRNG(normal=T(nt)), me, None, T(nt)))
+        want = np.stack([_orc_rand_momentum(me_o, nt[:, c]) for c in range(64)], axis=1)
+        assert rel_err(got, want) < 1e-12
+    # Philox: r ~ N(0, M) with M = inv(Minv)   (metric.jl:311-320 => cov(r) = M)
+    th = torch.zeros((N, D), dtype=torch.float64, device=DEV)
+    r = A.rand_momentum(A.PhiloxRNG(123), A.DenseEuclideanMetric(Minv), None, th).cpu().numpy()
+    M = np.linalg.inv(Minv)
+    assert np.abs(r.mean(axis=0)).max() < 5 * np.sqrt(np.diag(M).max() / N)
+    assert np.abs(np.cov(r.T) - M).max() < 0.05 * np.abs(M).max()
+    r2 = A.rand_momentum(A.PhiloxRNG(123), A.DenseEuclideanMetric(Minv), None, th).cpu().numpy()
+    assert np.array_equal(r, r2)  # counter-based: same (seed, offset) -> same draw
+    # identical per-chain generators are impossible by construction (chain index is in the counter):
+    assert len({tuple(x) for x in r[:100]}) == 100
+
+
+def _orc_rand_momentum(me, z):
+    import ctypes as C
+
+    r = np.zeros_like(z)
+    z = np.ascontiguousarray(z)
+    oc.lib().orc_rand_momentum(C.byref(me.c), C.c_int32(z.size), C.c_int64(0), z.ctypes.data_as(oc._dp), r.ctypes.data_as(oc._dp))
+    return r
+
+
+def test_hmc_sampling_moments_philox():
+    """test/sampler-vec.jl:43 analogue: many chains, Philox randomness, mean ~ target mean."""
+    D, N = 5, 4096
+    m, s = np.array([1.0, -2.0, 0.5, 0.0, 3.0]), np.array([1.0, 0.5, 2.0, 1.5, 0.7])
+    h = A.Hamiltonian(A.UnitEuclideanMetric(D), A.DiagGaussian(m, s))
+    z = A.phasepoint(h, torch.zeros((N, D), dtype=torch.float64, device=DEV), torch.zeros((N, D), dtype=torch.float64, device=DEV))
+    kern = A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.2), A.FixedNSteps(10)))
+    rng = A.PhiloxRNG(2026)
+    acc = 0.0
+    for _ in range(60):
+        tr = A.transition(rng, h, kern, z)
+        z = tr.z
+        acc += tr.stat["acceptance_rate"].mean().item()
+    th = z.theta.cpu().numpy()
+    assert np.abs(th.mean(axis=0) - m).max() < 0.15 and np.abs(th.std(axis=0) - s).max() < 0.15
+    assert 0.6 < acc / 60 <= 1.0
+
+
+def test_adapt_summary_matches_numpy():
+    D, N = 100, 4097
+    rng = np.random.default_rng(1)
+    th = rng.normal(size=(N, D)) * 3 + 1
+    al = rng.uniform(0, 1.4, N)
+    out = A.adapt_summary(torch.as_tensor(th, device=DEV), torch.as_tensor(al, device=DEV)).cpu().numpy()
+    assert out[0] == N and out[1] == pytest.approx(np.minimum(1, al).sum(), rel=1e-13)
+    assert np.allclose(out[2:2 + D], th.mean(axis=0), rtol=1e-12)
+    assert np.allclose(out[2 + D:], ((th - th.mean(axis=0)) ** 2).sum(axis=0), rtol=1e-12)
+    out2 = A.adapt_summary(torch.as_tensor(th, device=DEV), torch.as_tensor(al, device=DEV)).cpu().numpy()
+    assert np.array_equal(out, out2)  # deterministic reduction order
