@@ -522,6 +522,35 @@ def step(lf: AbstractLeapfrog, h: Hamiltonian, z: PhasePoint, n_steps: int = 1, 
     return (out, StepInfo(status, done)) if return_info else out
 
 
+class StepPlan:
+    """A prepared `step` call: buffers, descriptors and ctypes arguments are bound once, `plan()` then
+    costs one foreign call (a few microseconds of host time) -- use it when the same shapes are stepped
+    repeatedly (sampling loops, benchmarks).  `z` and `out` keep their identity; pass out=z for in place."""
+
+    def __init__(self, lf: AbstractLeapfrog, h: Hamiltonian, z: PhasePoint, n_steps: int, out: Optional[PhasePoint] = None,
+                 flags: int = 0, with_info: bool = False):
+        self.ctx = ctx = get_context(_device_of(z.theta))
+        N, D = z._nd()
+        self.z, self.out = z, (out if out is not None else _empty_pp(z.theta, with_lk_gradient=False))
+        self.status = _like(z.theta, (N,), np.uint32) if with_info else None
+        self.steps_done = _like(z.theta, (N,), np.int32) if with_info else None
+        self._md, self._keep = h.metric._desc(D, N, z.theta)
+        e, ep, self._keep2 = _eps_args(step_size(lf), z.theta, N)
+        alpha = lf.alpha if isinstance(lf, TemperedLeapfrog) else 0.0
+        self._zc, self._oc = z._c(), self.out._c(self.out.lk.gradient is not None)
+        fl = flags | (L.FLAG_HOST_BUFFERS if _is_host(z.theta) else 0)
+        self._args = (ctx.h, h.target.handle(ctx), C.byref(self._md), D, N, e, ep, int(n_steps), alpha,
+                      C.byref(self._zc), C.byref(self._oc), _ptr(self.status), _ptr(self.steps_done), fl)
+        self._fn = ctx.lib.ahmc_leapfrog_f64
+        self._h = h
+
+    def __call__(self) -> PhasePoint:
+        rc = self._fn(*self._args)
+        if rc != L.OK:
+            self.ctx.check(rc)
+        return self.out
+
+
 # ------------------------------------------------------------------------------------------------
 # trajectories / kernels (src/trajectory.jl)
 # ------------------------------------------------------------------------------------------------

@@ -158,8 +158,9 @@ int check_common(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metr
     return AHMC_OK;
 }
 
-int check_pp(ahmc_ctx* ctx, const ahmc_phasepoint* z, int32_t D, const char* name, bool need_cache) {
+int check_pp(ahmc_ctx* ctx, const ahmc_phasepoint* z, int32_t D, const char* name, bool need_cache, int64_t N) {
     if (!z) return fail(ctx, AHMC_ERR_INVALID, "%s is NULL", name);
+    if (N == 0) return AHMC_OK;  // empty batch: nothing is dereferenced
     if (!z->theta || !z->r) return fail(ctx, AHMC_ERR_INVALID, "%s.theta / %s.r is NULL", name, name);
     if (need_cache && (!z->lp_value || !z->lp_gradient || !z->lk_value))
         return fail(ctx, AHMC_ERR_INVALID, "%s.lp_value / lp_gradient / lk_value is NULL", name);
@@ -336,7 +337,7 @@ int ahmc_phasepoint_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metri
     if (!ctx || !model || !metric) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
-    if ((rc = check_pp(ctx, z, D, "z", true))) return rc;
+    if ((rc = check_pp(ctx, z, D, "z", true, N))) return rc;
     if (model->kind == AHMC_MODEL_CALLBACK)
         return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
     if (N == 0) return AHMC_OK;
@@ -393,8 +394,8 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
     if (!ctx || !model || !metric) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
-    if ((rc = check_pp(ctx, z_in, D, "z_in", true))) return rc;
-    if ((rc = check_pp(ctx, z_out, D, "z_out", true))) return rc;
+    if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
+    if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
     if (model->kind == AHMC_MODEL_CALLBACK)
         return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
     if (N == 0) return AHMC_OK;
@@ -544,8 +545,8 @@ int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_m
     if (!ctx || !model || !metric || !rng) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric/rng");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
-    if ((rc = check_pp(ctx, z_in, D, "z_in", true))) return rc;
-    if ((rc = check_pp(ctx, z_out, D, "z_out", true))) return rc;
+    if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
+    if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
     if (n_steps < 1) return fail(ctx, AHMC_ERR_INVALID, "n_steps must be >= 1 (nsteps(tau) = max(1, ...), trajectory.jl:240-243)");
     if (model->kind == AHMC_MODEL_CALLBACK)
         return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
@@ -605,8 +606,8 @@ int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_
     if (!ctx || !model || !metric || !rng) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric/rng");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
-    if ((rc = check_pp(ctx, z_in, D, "z_in", true))) return rc;
-    if ((rc = check_pp(ctx, z_out, D, "z_out", true))) return rc;
+    if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
+    if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
     if (max_depth < 0 || max_depth > 20) return fail(ctx, AHMC_ERR_INVALID, "max_depth must be in 0..20");
     if (model->kind == AHMC_MODEL_CALLBACK)
         return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");

@@ -1,6 +1,404 @@
-// ahmc_nuts.cu -- K3 placeholder (real kernel lands next); keeps the ABI symbol set complete.
+// ahmc_nuts.cu -- K3: one NUTS transition per chain (MultinomialTS + GeneralisedNoUTurn), the
+// reference's recursive doubling tree (src/trajectory.jl:626-742) run ITERATIVELY by one warp-group
+// per chain, so divergent U-turn termination stays inside the group.
+//
+// Recursion -> iteration.  `build_tree(depth j)` is a post-order walk over 2^j leaves; the only state
+// the recursion keeps alive is, per level k, the FIRST half-subtree waiting for its sibling.  We keep
+// exactly that ("pending[k]") in a per-chain workspace and drive the merges like a binary counter:
+// after leaf i, level k merges iff bit k of i is set.  Per pending level:
+//   rho      = sum of momenta over its leaves            (TurnStatistic, :462-467)
+//   rfirst   = momentum of its first-built leaf          (zleft or zright of the half tree)
+//   cand     = (theta, r, -grad lp, lp, lk) of its multinomial candidate  (:131-136)
+//   scalars  = lw (log weight), sum_alpha, n_alpha, dH_max               (:512-542)
+// Semantics preserved: leaf weights H0 - H' (:174-176); one randexp per internal
+// combine in post-order (:191-195, :667) and one for the top-level mh_accept only if the new subtree
+// did not terminate (:708-713); a terminated first half is returned without building/combining its
+// sibling (:652) -- the terminated node "floats" up through levels whose bit is 0 and is combined at
+// levels whose bit is 1, exactly as the unwinding recursion does; divergence iff
+// !(-H0 < delta_max - H') (:503-507); direction = sign of the step size (:640, integrator.jl:221-226).
+//
+// Control flow is warp-uniform (`__any_sync` guarded blocks, per-group predicates) so that groups of
+// G < 32 lanes sharing a warp can sit at different tree positions while shuffles stay convergent.
 #include "ahmc_kernels.cuh"
+
 namespace ahmc {
-long long nuts_scratch_doubles_per_chain(int D, int max_depth) { return (long long)(7 + 5 * (max_depth > 0 ? max_depth : 1)) * D; }
-cudaError_t launch_nuts(const NutsArgs&, cudaStream_t, int*) { return cudaErrorNotSupported; }
+
+// workspace layout per chain (doubles): LEFT edge (theta,r,g) | RIGHT edge | rho_tree | per level k:
+// rho, rfirst, cand theta, cand r, cand g
+long long nuts_scratch_doubles_per_chain(int D, int max_depth) {
+    return (long long)(7 + 5 * (max_depth > 0 ? max_depth : 1)) * D;
+}
+
+__device__ __forceinline__ double jl_min0(double x) {  // min(0, x), NaN-propagating like Julia
+    return (x != x) ? x : (x < 0.0 ? x : 0.0);
+}
+__device__ __forceinline__ double logaddexp(double a, double b) {  // LogExpFunctions.logaddexp
+    double delta = (a == b) ? 0.0 : fabs(a - b);
+    double mx = (a != a || b != b) ? CUDART_NAN : (a > b ? a : b);
+    return mx + log1p(exp(-delta));
+}
+__device__ __forceinline__ double maxabs(double a, double b) { return fabs(a) > fabs(b) ? a : b; }  // :526
+
+constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, cand lk
+
+template <int MODEL, int METRIC, int G, int E>
+__global__ void __launch_bounds__(kBlockThreads) nuts_kernel(const NutsArgs a) {
+    extern __shared__ double smem[];
+    const int l = threadIdx.x % G;
+    const int grp_in_block = threadIdx.x / G;
+    constexpr int kGroups = kBlockThreads / G;
+    const long long chain0 = (long long)blockIdx.x * kGroups + grp_in_block;
+    const bool valid = chain0 < a.N;
+    const long long chain = valid ? chain0 : a.N - 1;
+    const int D = a.D;
+    const bool dense = (MODEL == AHMC_MODEL_DENSE_GAUSS) || (METRIC == AHMC_METRIC_DENSE);
+    double* xs = smem + (size_t)grp_in_block * D;  // dense slab (unused otherwise)
+    const int maxd = a.max_depth > 0 ? a.max_depth : 1;
+    double* lv = smem + (dense ? (size_t)kGroups * D : 0) + (size_t)grp_in_block * maxd * kLevelScalars;
+    double* LW = lv;
+    double* SA = lv + maxd;
+    double* NA = lv + 2 * maxd;
+    double* DH = lv + 3 * maxd;
+    double* CLP = lv + 4 * maxd;
+    double* CLK = lv + 5 * maxd;
+
+    double* base = a.scratch + a.scratch_stride * chain;
+    double* LEFT = base;
+    double* RIGHT = base + 3 * (long long)D;
+    double* RHO = base + 6 * (long long)D;
+    auto level = [&](int k) { return base + (7 + 5 * (long long)k) * D; };
+
+    const double eps_c = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
+
+    ModelOps<MODEL, G, E> mo;
+    MetricOps<METRIC, G, E> me;
+    mo.load(a.model, l, D);
+    me.load(a.metric, chain, l, D);
+
+    int nexp = 0, ndir = 0;
+    auto next_exp = [&]() -> double {
+        int k = nexp++;
+        if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
+        return philox_exp(a.rng.seed, a.rng.offset, chain, k);
+    };
+    auto next_dir = [&]() -> bool {
+        int k = ndir++;
+        if (a.rng.dir_tape && k < a.rng.dir_stride) return a.rng.dir_tape[chain * a.rng.dir_stride + k] != 0;
+        return philox_bit(a.rng.seed, a.rng.offset, chain, k);
+    };
+
+    // ---- z0: refresh (sampler.jl:55; hamiltonian.jl:213-220), cached lp / gradient
+    ChainState<E> s;
+    double dr[E];
+    vload_nc<G, E>(s.th, a.th_in + a.ld_in * chain, l, D);
+    vload_nc<G, E>(s.g, a.g_in + a.ld_in * chain, l, D);
+    if (a.refresh) {
+        if (a.rng.normal_tape) {
+            vload_nc<G, E>(s.r, a.rng.normal_tape + (long long)D * chain, l, D);
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                int d = l + G * e;
+                s.r[e] = (d < D) ? philox_normal(a.rng.seed, a.rng.offset, chain, d) : 0.0;
+            }
+        }
+        me.rand_momentum(s.r, l);
+    } else {
+        vload_nc<G, E>(s.r, a.r_in + a.ld_in * chain, l, D);
+    }
+    s.lp = map_nonfinite(a.lp_in[chain]);
+    s.lk = map_nonfinite(kinetic<METRIC, G, E>(me, s.r, dr, xs, l));
+    const double H0 = -(s.lp + s.lk);  // energy(z0) (:682)
+
+    // tree = BinaryTree(z0, z0, rho = z0.r, 0, 0, 0); sampler = MultinomialTS(z0, lw = 0) (:683-688, :155)
+    double zc_lp = s.lp, zc_lk = s.lk;
+    if (valid) {
+        vstore<G, E>(LEFT, s.th, l, D);
+        vstore<G, E>(LEFT + D, s.r, l, D);
+        vstore<G, E>(LEFT + 2 * (long long)D, s.g, l, D);
+        vstore<G, E>(RIGHT, s.th, l, D);
+        vstore<G, E>(RIGHT + D, s.r, l, D);
+        vstore<G, E>(RIGHT + 2 * (long long)D, s.g, l, D);
+        vstore<G, E>(RHO, s.r, l, D);
+        vstore<G, E>(a.th_out + a.ld_out * chain, s.th, l, D);
+        vstore<G, E>(a.r_out + a.ld_out * chain, s.r, l, D);
+        vstore<G, E>(a.g_out + a.ld_out * chain, s.g, l, D);
+    }
+    double lw_tree = 0.0, sa_tree = 0.0, dh_tree = 0.0;
+    int na_tree = 0, j = 0;
+    bool term_dyn = false, term_num = false;
+    bool done = !valid || !(j < a.max_depth);
+    bool in_sub = false;
+    int i = 0, jsub = 0, v = 1;
+
+    while (true) {
+        // ---------------------------------------------------------------- (A) start a doubling (:691-706)
+        const bool start = !done && !in_sub;
+        if (__any_sync(FULL, start)) {
+            if (start) {
+                const bool vleft = next_dir();  // rand(rng, Bool) (:693)
+                v = vleft ? -1 : 1;
+                const double* edge = vleft ? LEFT : RIGHT;
+                vload_nc<G, E>(s.th, edge, l, D);
+                vload_nc<G, E>(s.r, edge + D, l, D);
+                vload_nc<G, E>(s.g, edge + 2 * (long long)D, l, D);
+                jsub = j;
+                i = 0;
+                in_sub = true;
+            }
+        }
+        if (!__any_sync(FULL, in_sub)) break;
+
+        // ---------------------------------------------------------------- (B) one leaf (:638-647)
+        leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, v > 0 ? eps_c : -eps_c, dr, xs, l);
+        const double nE = s.lp + s.lk;  // neg_energy(z')
+        const double H1 = -nE;
+        const double dH = H1 - H0;
+        double lw_c = H0 + nE;                               // MultinomialTS(s, H0, z') (:174-176)
+        double sa_c = exp(jl_min0(-dH));                     // alpha' = exp(min(0, -dH))
+        double na_c = 1.0, dh_c = dH;
+        bool tnum_c = !(-H0 < a.delta_max + -H1);            // Termination(...) (:503-507)
+        bool tdyn_c = false;
+        double rho_cur[E], rfirst_cur[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            rho_cur[e] = s.r[e];  // TurnStatistic(z.r)
+            rfirst_cur[e] = s.r[e];
+        }
+        int cand_cur = -1;  // -1: the leaf in registers; k >= 0: candidate stored in level slot k
+
+        // ---------------------------------------------------------------- (C) post-order merges (:649-673)
+        bool merging = in_sub;
+        bool complete = false;
+        int k = 0;
+        while (__any_sync(FULL, merging)) {
+            if (merging && k == jsub) {
+                complete = true;
+                merging = false;
+            }
+            const bool bit = merging && ((i >> k) & 1);
+            const bool term_c = tnum_c || tdyn_c;
+            const bool do_comb = merging && bit;
+            const bool do_store = merging && !bit && !term_c;
+            const bool do_float = merging && !bit && term_c;  // terminated first half: returned as is (:652)
+            if (__any_sync(FULL, do_comb)) {
+                double rho_p[E], rf_p[E], t1[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) rho_p[e] = rf_p[e] = 0.0;
+                if (do_comb) {
+                    double* L = level(k);
+                    if (k == 0) {
+                        vload_nc<G, E>(rho_p, L + 3 * (long long)D, l, D);  // level 0: rho = rfirst = cand r
+#pragma unroll
+                        for (int e = 0; e < E; ++e) rf_p[e] = rho_p[e];
+                    } else {
+                        vload_nc<G, E>(rho_p, L, l, D);
+                        vload_nc<G, E>(rf_p, L + D, l, D);
+                    }
+#pragma unroll
+                    for (int e = 0; e < E; ++e) rho_cur[e] += rho_p[e];  // combine(ts) (:467)
+                }
+                // isterminated(GeneralisedNoUTurn) on the merged node (:566-570, :615-617)
+                me.dHdr(rf_p, t1, xs, l);
+                double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    d1 = fma(rho_cur[e], t1[e], d1);
+                    d2 = fma(rho_cur[e], dr[e], d2);
+                }
+                d1 = Grp<G>::sum(d1);
+                d2 = Grp<G>::sum(d2);
+                if (do_comb) {
+                    const double lw_p = LW[k], sa_p = SA[k], na_p = NA[k], dh_p = DH[k];
+                    const bool uturn = (d1 <= 0.0) || (d2 <= 0.0);
+                    const double lw = logaddexp(lw_p, lw_c);  // combine(rng, s1, s2) (:191-195)
+                    const double ex = next_exp();
+                    if (lw < lw_p + ex) cand_cur = k;  // keep the first-built half's candidate
+                    lw_c = lw;
+                    sa_c = (v > 0) ? sa_p + sa_c : sa_c + sa_p;  // treeleft + treeright (:538)
+                    na_c += na_p;
+                    dh_c = (v > 0) ? maxabs(dh_p, dh_c) : maxabs(dh_c, dh_p);
+                    tdyn_c = tdyn_c || uturn;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) rfirst_cur[e] = rf_p[e];
+                }
+            }
+            if (__any_sync(FULL, do_store)) {
+                if (do_store) {
+                    double* L = level(k);
+                    if (k > 0) {
+                        vstore<G, E>(L, rho_cur, l, D);
+                        vstore<G, E>(L + D, rfirst_cur, l, D);
+                    }
+                    double clp, clk;
+                    if (cand_cur < 0) {
+                        vstore<G, E>(L + 2 * (long long)D, s.th, l, D);
+                        vstore<G, E>(L + 3 * (long long)D, s.r, l, D);
+                        vstore<G, E>(L + 4 * (long long)D, s.g, l, D);
+                        clp = s.lp;
+                        clk = s.lk;
+                    } else {
+                        const double* S = level(cand_cur);
+                        double t[E];
+                        vload_nc<G, E>(t, S + 2 * (long long)D, l, D);
+                        vstore<G, E>(L + 2 * (long long)D, t, l, D);
+                        vload_nc<G, E>(t, S + 3 * (long long)D, l, D);
+                        vstore<G, E>(L + 3 * (long long)D, t, l, D);
+                        vload_nc<G, E>(t, S + 4 * (long long)D, l, D);
+                        vstore<G, E>(L + 4 * (long long)D, t, l, D);
+                        clp = CLP[cand_cur];
+                        clk = CLK[cand_cur];
+                    }
+                    if (l == 0) {
+                        LW[k] = lw_c;
+                        SA[k] = sa_c;
+                        NA[k] = na_c;
+                        DH[k] = dh_c;
+                        CLP[k] = clp;
+                        CLK[k] = clk;
+                    }
+                    merging = false;
+                }
+                __syncwarp();
+            }
+            if (do_comb || do_float) ++k;
+        }
+
+        // ---------------------------------------------------------------- (D) subtree complete (:707-722)
+        if (__any_sync(FULL, complete)) {
+            const bool sub_term = tnum_c || tdyn_c;
+            bool accept = false;
+            if (complete && !sub_term) {
+                j = j + 1;
+                const double ex = next_exp();
+                accept = lw_tree < lw_c + ex;  // mh_accept (:204-206)
+            }
+            if (accept) {  // zcand = sampler'.zcand
+                if (cand_cur < 0) {
+                    vstore<G, E>(a.th_out + a.ld_out * chain, s.th, l, D);
+                    vstore<G, E>(a.r_out + a.ld_out * chain, s.r, l, D);
+                    vstore<G, E>(a.g_out + a.ld_out * chain, s.g, l, D);
+                    zc_lp = s.lp;
+                    zc_lk = s.lk;
+                } else {
+                    const double* S = level(cand_cur);
+                    double t[E];
+                    vload_nc<G, E>(t, S + 2 * (long long)D, l, D);
+                    vstore<G, E>(a.th_out + a.ld_out * chain, t, l, D);
+                    vload_nc<G, E>(t, S + 3 * (long long)D, l, D);
+                    vstore<G, E>(a.r_out + a.ld_out * chain, t, l, D);
+                    vload_nc<G, E>(t, S + 4 * (long long)D, l, D);
+                    vstore<G, E>(a.g_out + a.ld_out * chain, t, l, D);
+                    zc_lp = CLP[cand_cur];
+                    zc_lk = CLK[cand_cur];
+                }
+            }
+            // tree = combine(treeleft, treeright) (:715): rho, the moved edge, statistics
+            double rho_t[E], r_other[E], t1[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) rho_t[e] = r_other[e] = 0.0;
+            if (complete) {
+                vload_nc<G, E>(rho_t, RHO, l, D);
+#pragma unroll
+                for (int e = 0; e < E; ++e) rho_t[e] += rho_cur[e];
+                vstore<G, E>(RHO, rho_t, l, D);
+                double* edge = (v < 0) ? LEFT : RIGHT;
+                vstore<G, E>(edge, s.th, l, D);
+                vstore<G, E>(edge + D, s.r, l, D);
+                vstore<G, E>(edge + 2 * (long long)D, s.g, l, D);
+                const double* other = (v < 0) ? RIGHT : LEFT;
+                vload_nc<G, E>(r_other, other + D, l, D);
+            }
+            me.dHdr(r_other, t1, xs, l);
+            double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                d1 = fma(rho_t[e], t1[e], d1);
+                d2 = fma(rho_t[e], dr[e], d2);
+            }
+            d1 = Grp<G>::sum(d1);
+            d2 = Grp<G>::sum(d2);
+            if (complete) {
+                sa_tree = (v < 0) ? sa_c + sa_tree : sa_tree + sa_c;
+                na_tree += (int)na_c;
+                dh_tree = (v < 0) ? maxabs(dh_c, dh_tree) : maxabs(dh_tree, dh_c);
+                lw_tree = logaddexp(lw_tree, lw_c);  // combine(zcand, sampler, sampler') (:197-200, :717)
+                const bool uturn = (d1 <= 0.0) || (d2 <= 0.0);
+                term_dyn = term_dyn || tdyn_c || uturn;  // (:719-722)
+                term_num = term_num || tnum_c;
+                in_sub = false;
+                if (term_dyn || term_num || !(j < a.max_depth)) done = true;
+            }
+            __syncwarp();
+        }
+        if (in_sub) ++i;
+    }
+
+    // ---------------------------------------------------------------- stats (:725-739)
+    if (valid && l == 0) {
+        const double H = -(zc_lp + zc_lk);
+        a.lp_out[chain] = zc_lp;
+        a.lk_out[chain] = zc_lk;
+        const StatsDev& st = a.st;
+        if (st.n_steps) st.n_steps[chain] = na_tree;
+        if (st.is_accept) st.is_accept[chain] = 1;
+        if (st.acceptance_rate) st.acceptance_rate[chain] = sa_tree / (double)na_tree;
+        if (st.log_density) st.log_density[chain] = zc_lp;
+        if (st.hamiltonian_energy) st.hamiltonian_energy[chain] = H;
+        if (st.hamiltonian_energy_error) st.hamiltonian_energy_error[chain] = H - H0;
+        if (st.max_hamiltonian_energy_error) st.max_hamiltonian_energy_error[chain] = dh_tree;
+        if (st.tree_depth) st.tree_depth[chain] = j;
+        if (st.numerical_error) st.numerical_error[chain] = term_num ? 1 : 0;
+    }
+}
+
+template <int MODEL, int METRIC, int G, int E>
+static cudaError_t launch_nuts_t(const NutsArgs& a, cudaStream_t st) {
+    const int chains_per_block = kBlockThreads / G;
+    const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
+    const int maxd = a.max_depth > 0 ? a.max_depth : 1;
+    size_t sm = smem_bytes(MODEL, METRIC, a.D, G) + (size_t)chains_per_block * maxd * kLevelScalars * sizeof(double);
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+    }
+    nuts_kernel<MODEL, METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int MODEL, int METRIC>
+static cudaError_t nuts_layout(const NutsArgs& a, cudaStream_t st, int G, int E) {
+    if (G == 4 && E == 1) return launch_nuts_t<MODEL, METRIC, 4, 1>(a, st);
+    if (G == 8 && E == 1) return launch_nuts_t<MODEL, METRIC, 8, 1>(a, st);
+    if (G == 16 && E == 1) return launch_nuts_t<MODEL, METRIC, 16, 1>(a, st);
+    if (G == 32 && E == 1) return launch_nuts_t<MODEL, METRIC, 32, 1>(a, st);
+    if (G == 32 && E == 2) return launch_nuts_t<MODEL, METRIC, 32, 2>(a, st);
+    if (G == 32 && E == 4) return launch_nuts_t<MODEL, METRIC, 32, 4>(a, st);
+    if (G == 32 && E == 8) return launch_nuts_t<MODEL, METRIC, 32, 8>(a, st);
+    if (G == 32 && E == 16) return launch_nuts_t<MODEL, METRIC, 32, 16>(a, st);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_nuts(const NutsArgs& a, cudaStream_t st, int* n_launches) {
+    int G, E;
+    if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+    if (n_launches) *n_launches += 1;
+    switch (a.model.kind * 3 + a.metric.kind) {
+        case 0: return nuts_layout<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_UNIT>(a, st, G, E);
+        case 1: return nuts_layout<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_DIAG>(a, st, G, E);
+        case 2: return nuts_layout<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_DENSE>(a, st, G, E);
+        case 3: return nuts_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_UNIT>(a, st, G, E);
+        case 4: return nuts_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DIAG>(a, st, G, E);
+        case 5: return nuts_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DENSE>(a, st, G, E);
+        case 6: return nuts_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_UNIT>(a, st, G, E);
+        case 7: return nuts_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DIAG>(a, st, G, E);
+        case 8: return nuts_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DENSE>(a, st, G, E);
+        case 9: return nuts_layout<AHMC_MODEL_FUNNEL, AHMC_METRIC_UNIT>(a, st, G, E);
+        case 10: return nuts_layout<AHMC_MODEL_FUNNEL, AHMC_METRIC_DIAG>(a, st, G, E);
+        case 11: return nuts_layout<AHMC_MODEL_FUNNEL, AHMC_METRIC_DENSE>(a, st, G, E);
+    }
+    return cudaErrorInvalidValue;
+}
+
 }  // namespace ahmc

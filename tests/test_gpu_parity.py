@@ -367,3 +367,86 @@ def test_adapt_summary_matches_numpy():
     assert np.allclose(out[2 + D:], ((th - th.mean(axis=0)) ** 2).sum(axis=0), rtol=1e-12)
     out2 = A.adapt_summary(torch.as_tensor(th, device=DEV), torch.as_tensor(al, device=DEV)).cpu().numpy()
     assert np.array_equal(out, out2)  # deterministic reduction order
+
+
+# ------------------------------------------------------------------------------------------------ NUTS
+def _nuts_case(model, metric, D, N, eps, seed, max_depth=10, scale=1.0):
+    rng = np.random.default_rng(seed)
+    p0 = p1 = Minv = None
+    if model == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.5, 0.5, D))
+    elif model == "dense_gauss":
+        B = rng.normal(size=(D, D))
+        p0, p1 = rng.normal(size=D), B @ B.T / D + np.eye(D)
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    elif metric == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+    th = rng.normal(size=(D, N)) * scale
+    nt = rng.normal(size=(D, N))
+    dirs = rng.integers(0, 2, size=(N, max_depth + 1)).astype(np.uint8)
+    exps = rng.exponential(size=(N, 1 << max_depth))
+    om, ome = oc.Model(MODEL_KINDS[model], D, p0, p1, 0.0), oc.Metric(METRIC_KINDS[metric], Minv)
+    z0o = oc.phasepoint(om, ome, th, np.zeros((D, N)))
+    zo, so, used = oc.nuts_transition(om, ome, eps, z0o, nt, dirs, exps, max_depth=max_depth)
+    h = A.Hamiltonian(make_metric(metric, Minv, D), make_target(model, D, p0, p1, 0.0))
+    z0 = A.phasepoint(h, T(th), T(np.zeros((D, N))))
+    tau = A.Trajectory(A.MultinomialTS, A.Leapfrog(eps), A.GeneralisedNoUTurn(max_depth, 1000.0))
+    rngt = A.TapeRNG(normal=T(nt), exp=torch.as_tensor(exps, device=DEV), dirs=torch.as_tensor(dirs, device=DEV))
+    tr = A.transition(rngt, h, A.HMCKernel(tau), z0)
+    return tr, zo, so
+
+
+@pytest.mark.parametrize("model,metric,D,eps,scale", [
+    ("std_normal", "unit", 10, 0.3, 1.0), ("diag_gauss", "diag", 128, 0.15, 1.0), ("diag_gauss", "unit", 5, 0.4, 1.0),
+    ("funnel", "diag", 20, 0.12, 0.6), ("dense_gauss", "dense", 12, 0.25, 1.0), ("diag_gauss", "diag", 200, 0.1, 1.0),
+    ("funnel", "unit", 3, 0.9, 2.0),
+])
+def test_nuts_transition_vs_oracle_with_tapes(model, metric, D, eps, scale):
+    N = 203
+    tr, zo, so = _nuts_case(model, metric, D, N, eps, seed=D * 7 + 1, scale=scale)
+    st = tr.stat
+    assert (F(st["tree_depth"]) == so.tree_depth).all(), (F(st["tree_depth"])[:20], so.tree_depth[:20])
+    assert (F(st["n_steps"]) == so.n_steps).all()
+    assert (F(st["numerical_error"]) == so.numerical_error).all()
+    assert len(set(so.tree_depth)) > 1  # divergent tree sizes inside warps were exercised
+    assert_pp_close(tr.z, zo)
+    assert rel_err(F(st["acceptance_rate"]), so.acceptance_rate) < 1e-9
+    assert np.allclose(F(st["hamiltonian_energy_error"]), so.hamiltonian_energy_error, rtol=0, atol=1e-9 * D)
+    assert np.allclose(F(st["max_hamiltonian_energy_error"]), so.max_hamiltonian_energy_error, rtol=1e-6, atol=1e-9 * D)
+    assert (F(st["is_accept"]) == 1).all()
+
+
+def test_nuts_max_depth_and_divergence_flags():
+    # tiny step size -> every chain hits max_depth (:691); huge step size on the funnel -> divergences (:503-507)
+    tr, zo, so = _nuts_case("std_normal", "unit", 4, 64, 0.01, seed=5, max_depth=5)
+    assert (F(tr.stat["tree_depth"]) == 5).all() and (so.tree_depth == 5).all()
+    assert (F(tr.stat["n_steps"]) == 31).all()
+    assert_pp_close(tr.z, zo)
+    tr, zo, so = _nuts_case("funnel", "unit", 6, 128, 3.0, seed=6, max_depth=8, scale=3.0)
+    assert so.numerical_error.sum() > 0
+    assert (F(tr.stat["numerical_error"]) == so.numerical_error).all()
+    assert (F(tr.stat["n_steps"]) == so.n_steps).all()
+    ok = so.numerical_error == 0
+    assert rel_err(F(tr.z.theta)[:, ok], zo.theta[:, ok]) < TOL
+
+
+def test_nuts_sampling_moments_philox():
+    """many-chain NUTS with on-device Philox randomness recovers the target moments (test/sampler.jl style)."""
+    D, N = 6, 2048
+    m, s = np.linspace(-2, 2, D), np.exp(np.linspace(-1, 1, D))
+    h = A.Hamiltonian(A.DiagEuclideanMetric(s * s), A.DiagGaussian(m, s))
+    zero = lambda: torch.zeros((N, D), dtype=torch.float64, device=DEV)
+    z = A.phasepoint(h, zero(), zero())
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.6), A.GeneralisedNoUTurn()))
+    rng = A.PhiloxRNG(11)
+    depths = []
+    for _ in range(40):
+        tr = A.transition(rng, h, kern, z)
+        z = tr.z
+        depths.append(tr.stat["tree_depth"].double().mean().item())
+    th = z.theta.cpu().numpy()
+    assert np.abs((th.mean(axis=0) - m) / s).max() < 0.12 and np.abs(th.std(axis=0) / s - 1).max() < 0.1
+    assert 1.0 < np.mean(depths) < 5.0
+    assert tr.stat["acceptance_rate"].mean().item() > 0.6
