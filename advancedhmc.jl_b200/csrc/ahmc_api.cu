@@ -24,6 +24,8 @@ struct ahmc_ctx {
     size_t nuts_scratch_bytes = 0;
     double* adapt_scratch = nullptr;
     size_t adapt_scratch_bytes = 0;
+    cudaStream_t stream2 = nullptr;  // second stream of the host-buffer pipeline (H2D of chunk i+1 || D2H of chunk i)
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 };
 
 struct ahmc_model {
@@ -246,6 +248,9 @@ int ahmc_destroy(ahmc_ctx* ctx) {
     cudaFree(ctx->arena);
     cudaFree(ctx->nuts_scratch);
     cudaFree(ctx->adapt_scratch);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return AHMC_OK;
@@ -387,6 +392,118 @@ static int copy_pp_device(ahmc_ctx* ctx, int32_t D, int64_t N, const ahmc_phasep
     return AHMC_OK;
 }
 
+// HOST_BUFFERS fast lane for big batches: the chain axis is cut into chunks that alternate between two streams, so
+// the host->device copy of chunk i+1 overlaps the kernel and the device->host copy of chunk i (PCIe is full duplex;
+// chains are independent, so a chunk is a complete sub-problem).  Same kernels, same results as the one-shot path.
+static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D,
+                                   int64_t N, double eps, const double* eps_chain, int32_t n_steps,
+                                   double temper_alpha, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
+                                   uint32_t* status, int32_t* steps_done, uint32_t flags) {
+    if (!ctx->stream2) {
+        CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+    }
+    const int64_t ldi = z_in->ld, ldo = z_out->ld;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t nMinv = metric_minv_count(metric, D, N);
+    size_t need = al(nMinv * 8) + al((size_t)D * D * 8) + al((size_t)N * 8) + 3 * al((size_t)ldi * N * 8) +
+                  4 * al((size_t)ldo * N * 8) + 2 * al((size_t)N * 8) + 2 * al((size_t)N * 4);
+    if (need > ctx->arena_bytes) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream2));
+        cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+        size_t cap = need + need / 4;
+        if (cudaMalloc((void**)&ctx->arena, cap) != cudaSuccess)
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc(%zu) for staging failed", cap);
+        ctx->arena_bytes = cap;
+    }
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { char* p = ctx->arena + off; off += al(bytes); return p; };
+    double* dMinv = (double*)carve(nMinv * 8);
+    double* dU = (double*)carve((size_t)D * D * 8);
+    double* dEps = (double*)carve((size_t)N * 8);
+    double* dTh = (double*)carve((size_t)ldi * N * 8);
+    double* dR = (double*)carve((size_t)ldi * N * 8);
+    double* dG = (double*)carve((size_t)ldi * N * 8);
+    double* oTh = (double*)carve((size_t)ldo * N * 8);
+    double* oR = (double*)carve((size_t)ldo * N * 8);
+    double* oG = (double*)carve((size_t)ldo * N * 8);
+    double* oDr = (double*)carve((size_t)ldo * N * 8);
+    double* oLp = (double*)carve((size_t)N * 8);
+    double* oLk = (double*)carve((size_t)N * 8);
+    uint32_t* oSt = (uint32_t*)carve((size_t)N * 4);
+    int32_t* oSd = (int32_t*)carve((size_t)N * 4);
+
+    cudaStream_t ss[2] = {ctx->stream, ctx->stream2};
+    // shared parameters first (stream 0), stream 1 waits for them
+    const bool per_chain_minv = metric->kind == AHMC_METRIC_DIAG && metric->chain_stride != 0;
+    if (nMinv && !per_chain_minv) CU(cudaMemcpyAsync(dMinv, metric->Minv, nMinv * 8, cudaMemcpyHostToDevice, ss[0]));
+    if (metric->kind == AHMC_METRIC_DENSE && metric->cholU)
+        CU(cudaMemcpyAsync(dU, metric->cholU, (size_t)D * D * 8, cudaMemcpyHostToDevice, ss[0]));
+    CU(cudaEventRecord(ctx->ev_a, ss[0]));
+    CU(cudaStreamWaitEvent(ss[1], ctx->ev_a, 0));
+
+    const int n_abs = n_steps < 0 ? -n_steps : n_steps;
+    int64_t chunk = (N + 7) / 8;                 // 8 chunks, at least 512 chains each
+    if (chunk < 512) chunk = 512;
+    chunk = (chunk + 3) & ~(int64_t)3;
+    int nl = 0, k = 0;
+    for (int64_t c0 = 0; c0 < N; c0 += chunk, ++k) {
+        const int64_t n = (c0 + chunk <= N) ? chunk : N - c0;
+        cudaStream_t st = ss[k & 1];
+        CU(cudaMemcpyAsync(dTh + ldi * c0, z_in->theta + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dR + ldi * c0, z_in->r + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dG + ldi * c0, z_in->lp_gradient + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, st));
+        if (eps_chain) CU(cudaMemcpyAsync(dEps + c0, eps_chain + c0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        if (per_chain_minv)
+            CU(cudaMemcpyAsync(dMinv + metric->chain_stride * c0, metric->Minv + metric->chain_stride * c0,
+                               (size_t)metric->chain_stride * n * 8, cudaMemcpyHostToDevice, st));
+        LeapfrogArgs a{};
+        a.model = model_dev(model);
+        a.metric = MetricDev{metric->kind, per_chain_minv ? dMinv + metric->chain_stride * c0 : (nMinv ? dMinv : nullptr),
+                             per_chain_minv ? metric->chain_stride : 0, metric->kind == AHMC_METRIC_DENSE ? dU : nullptr};
+        a.D = D;
+        a.N = n;
+        a.eps = eps;
+        a.eps_chain = eps_chain ? dEps + c0 : nullptr;
+        a.n_steps = n_abs;
+        a.fwd = n_steps > 0;
+        a.temper_alpha = temper_alpha;
+        a.th_in = dTh + ldi * c0;
+        a.r_in = dR + ldi * c0;
+        a.g_in = dG + ldi * c0;
+        a.ld_in = ldi;
+        a.th_out = oTh + ldo * c0;
+        a.r_out = oR + ldo * c0;
+        a.g_out = oG + ldo * c0;
+        a.dr_out = z_out->lk_gradient ? oDr + ldo * c0 : nullptr;
+        a.lp_out = oLp + c0;
+        a.lk_out = oLk + c0;
+        a.ld_out = ldo;
+        a.status = status ? oSt + c0 : nullptr;
+        a.steps_done = steps_done ? oSd + c0 : nullptr;
+        a.flags = flags;
+        CU(launch_leapfrog(a, st, &nl));
+        CU(cudaMemcpyAsync(z_out->theta + ldo * c0, a.th_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(z_out->r + ldo * c0, a.r_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(z_out->lp_gradient + ldo * c0, a.g_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, st));
+        if (a.dr_out) CU(cudaMemcpyAsync(z_out->lk_gradient + ldo * c0, a.dr_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(z_out->lp_value + c0, a.lp_out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(z_out->lk_value + c0, a.lk_out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        if (status) CU(cudaMemcpyAsync(status + c0, a.status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (steps_done) CU(cudaMemcpyAsync(steps_done + c0, a.steps_done, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    ctx->launches += nl;
+    // join stream 1 into stream 0, then synchronise (host buffers are only valid after the copies land)
+    CU(cudaEventRecord(ctx->ev_b, ss[1]));
+    CU(cudaStreamWaitEvent(ss[0], ctx->ev_b, 0));
+    CU(cudaStreamSynchronize(ss[0]));
+    return AHMC_OK;
+}
+
 int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
                       double eps, const double* eps_chain, int32_t n_steps, double temper_alpha,
                       const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, uint32_t* status,
@@ -416,6 +533,9 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
         }
         return AHMC_OK;
     }
+    if (host && !(flags & AHMC_FLAG_COMPAT_BREAK_ALL) && N >= 1024)
+        return leapfrog_host_pipelined(ctx, model, metric, D, N, eps, eps_chain, n_steps, temper_alpha, z_in, z_out,
+                                       status, steps_done, flags);
     Stager st(ctx, host);
     const size_t cin = (size_t)z_in->ld * N, cout = (size_t)z_out->ld * N;
     reserve_metric(st, metric, D, N);

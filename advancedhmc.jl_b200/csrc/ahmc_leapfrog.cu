@@ -65,8 +65,17 @@ struct StepIO {
     }
 };
 
+// Occupancy: the headline batch (4096 chains x D=128 -> 4096 warps) fits the chip in ONE wave only if 7 blocks of
+// 4 warps are resident per SM (148 x 7 x 4 = 4144 warp slots), i.e. <= 72 registers per thread.  The fast path needs
+// ~50; the cap makes the (rarely taken) exact fallback of the separable kernels spill a little, which is the right
+// trade.  Wider layouts (E >= 8) and non-separable models keep the default budget.
+template <int MODEL, int METRIC, int E>
+constexpr int min_blocks_per_sm() {
+    return (FastCapable<MODEL, METRIC>::value && E <= 4) ? 7 : 1;
+}
+
 template <int MODEL, int METRIC, int G, int E>
-__global__ void __launch_bounds__(kBlockThreads) leapfrog_kernel(const LeapfrogArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC, E>()) leapfrog_kernel(const LeapfrogArgs a) {
     extern __shared__ double smem[];
     const int l = threadIdx.x % G;
     const int grp_in_block = threadIdx.x / G;
@@ -153,7 +162,7 @@ struct HmcIO {
 };
 
 template <int MODEL, int METRIC, int G, int E>
-__global__ void __launch_bounds__(kBlockThreads) hmc_kernel(const HmcArgs h) {
+__global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC, E>()) hmc_kernel(const HmcArgs h) {
     extern __shared__ double smem[];
     const LeapfrogArgs& a = h.lf;
     const int l = threadIdx.x % G;

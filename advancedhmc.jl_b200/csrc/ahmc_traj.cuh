@@ -44,41 +44,44 @@ __device__ __forceinline__ void run_trajectory(const ModelDev& model, const Metr
         const bool fast_on = !(flags & AHMC_FLAG_EXACT_CHECKS) && !(temper_alpha > 0.0);
         if (fast_on) {
             constexpr int T200 = expo_bits(200), T100 = expo_bits(100), T50 = expo_bits(50);
-            double x[E], r[E], ca[E], cb[E];
-            bool suspicious = big_d(eps, T50);
+            double x[E], r[E], ca[E], cb[E], mu[E];
+            // |eps| must be in [2^-100, 2^50] for the proof below and for the 1/eps rescaling of the last step
+            const double inv_eps = 1.0 / eps;
+            bool suspicious = big_d(eps, T50) | big_d(inv_eps, T100);
             double Amax = 0.0, Bmax = 0.0;
             const double he = 0.5 * eps;
             {
                 double g0[E];
                 f.init(x, r, g0);
+                const double* pMi = (METRIC == AHMC_METRIC_DIAG) ? metric.Minv + metric.chain_stride * chain + l : nullptr;
+                const double* pW = (MODEL == AHMC_MODEL_DIAG_GAUSS) ? model.p1 + l : nullptr;
+                const double* pMu = (MODEL == AHMC_MODEL_DIAG_GAUSS) ? model.p0 + l : nullptr;
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
-                    int d = l + G * e;
-                    double mi = 0.0, wi = 0.0, mu = 0.0;
-                    if (d < D) {
-                        mi = (METRIC == AHMC_METRIC_DIAG) ? __ldg(metric.Minv + metric.chain_stride * chain + d) : 1.0;
-                        wi = (MODEL == AHMC_MODEL_DIAG_GAUSS) ? __ldg(model.p1 + d) : 1.0;
-                        mu = (MODEL == AHMC_MODEL_DIAG_GAUSS) ? __ldg(model.p0 + d) : 0.0;
-                    }
-                    suspicious |= big_d(mi, T100) | big_d(wi, T100) | big_d(mu, T200) | big_d(x[e], T200) |
+                    const bool in = (l + G * e) < D;
+                    double mi = (METRIC == AHMC_METRIC_DIAG) ? (in ? __ldg(pMi + G * e) : 0.0) : (in ? 1.0 : 0.0);
+                    double wi = (MODEL == AHMC_MODEL_DIAG_GAUSS) ? (in ? __ldg(pW + G * e) : 0.0) : (in ? 1.0 : 0.0);
+                    mu[e] = (MODEL == AHMC_MODEL_DIAG_GAUSS) ? (in ? __ldg(pMu + G * e) : 0.0) : 0.0;
+                    suspicious |= big_d(mi, T100) | big_d(wi, T100) | big_d(mu[e], T200) | big_d(x[e], T200) |
                                   big_d(r[e], T200) | big_d(g0[e], T200);
                     ca[e] = eps * mi;
                     cb[e] = eps * wi;
                     Amax = fmax(Amax, fabs(ca[e]));
                     Bmax = fmax(Bmax, fabs(cb[e]));
-                    x[e] = x[e] - mu;              // shifted coordinate
+                    x[e] = x[e] - mu[e];           // shifted coordinate
                     r[e] = fma(-he, g0[e], r[e]);  // first half kick uses the CACHED gradient (integrator.jl:237)
                 }
             }
             Amax = Grp<G>::max(Amax);
             Bmax = Grp<G>::max(Bmax);
+            // K = (1+A)(1+B) bounds the per-step growth of max(|x|,|r|); log2(K) <= exponent(K) + 1
             const double K = (1.0 + Amax) * (1.0 + Bmax);
             int kcheck = n;
-            if (K > 1.0) {
-                double kk = 100.0 / log2(K);
-                if (!(kk >= 1.0)) suspicious = true;
-                kcheck = kk > 1.0e6 ? 1000000 : (int)kk;
-                if (kcheck < 1) kcheck = 1;
+            {
+                const int ek = ((__double2hiint(K) >> 20) & 0x7ff) - 1023 + 1;  // K >= 1: ek >= 1
+                if (ek > 100 || !(K >= 1.0)) suspicious = true;                // also catches NaN / Inf
+                const int kk = 100 / (ek < 1 ? 1 : ek);
+                kcheck = kk < 1 ? 1 : kk;
             }
             // n-1 x (drift + merged full kick), magnitude check every kcheck steps
             int remaining = n - 1;
@@ -95,26 +98,20 @@ __device__ __forceinline__ void run_trajectory(const ModelDev& model, const Metr
 #pragma unroll
                 for (int e = 0; e < E; ++e) suspicious |= big_d(x[e], T200) | big_d(r[e], T200);
             }
-            // last step: drift, gradient, half kick, energies
+            // last step: drift, gradient, half kick, energies.  g = x*w and dH/dr = Minv*r are recovered from the
+            // per-coordinate constants as (x*b)/eps and (r*a)/eps (one extra rounding, ~1e-16 relative)
             double g[E], dr[E];
             double lp_part = 0.0, lk_part = 0.0;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                int d = l + G * e;
-                double mi = 0.0, wi = 0.0, mu = 0.0;
-                if (d < D) {
-                    mi = (METRIC == AHMC_METRIC_DIAG) ? __ldg(metric.Minv + metric.chain_stride * chain + d) : 1.0;
-                    wi = (MODEL == AHMC_MODEL_DIAG_GAUSS) ? __ldg(model.p1 + d) : 1.0;
-                    mu = (MODEL == AHMC_MODEL_DIAG_GAUSS) ? __ldg(model.p0 + d) : 0.0;
-                }
                 x[e] = fma(ca[e], r[e], x[e]);
-                g[e] = x[e] * wi;
+                g[e] = (MODEL == AHMC_MODEL_DIAG_GAUSS) ? (x[e] * cb[e]) * inv_eps : ((l + G * e) < D ? x[e] : 0.0);
                 r[e] = fma(-he, g[e], r[e]);
                 suspicious |= big_d(x[e], T200) | big_d(r[e], T200);
                 lp_part = fma(x[e], g[e], lp_part);
-                dr[e] = mi * r[e];
-                lk_part = fma(r[e] * r[e], mi, lk_part);
-                x[e] = x[e] + mu;  // back to theta
+                dr[e] = (METRIC == AHMC_METRIC_DIAG) ? (r[e] * ca[e]) * inv_eps : r[e];
+                lk_part = fma(r[e], dr[e], lk_part);
+                x[e] = x[e] + mu[e];  // back to theta
             }
             suspicious = Grp<G>::any(suspicious);
             const double lp = fma(-0.5, Grp<G>::sum(lp_part), model.c0);

@@ -1,0 +1,36 @@
+"""Small driver for ncu: headline K1 launches (L2 cold), HBM-honest single-step launches, one K2 and one K3 launch."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import ahmc_b200 as A
+import bench
+
+dev = torch.device("cuda:0")
+m, s, Minv, th, r = bench.synth(4096, 128, 1)
+h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s))
+z0 = A.phasepoint(h, torch.as_tensor(th, device=dev), torch.as_tensor(r, device=dev))
+plan = A.StepPlan(A.Leapfrog(0.1), h, z0, 32)
+flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float64, device=dev)
+for _ in range(4):
+    flush.max(); torch.cuda.synchronize(); plan()
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "honest"):
+    Nh = 1 << 20
+    st = torch.as_tensor(s, device=dev)
+    zh = A.phasepoint(h, torch.randn((Nh, 128), dtype=torch.float64, device=dev) * st, torch.randn((Nh, 128), dtype=torch.float64, device=dev) / st)
+    p1 = A.StepPlan(A.Leapfrog(0.1), h, zh, 1, out=zh)
+    for _ in range(3):
+        p1()
+if which in ("all", "k2"):
+    kern = A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.1), A.FixedNSteps(32)))
+    rng = A.PhiloxRNG(1)
+    for _ in range(3):
+        A.transition(rng, h, kern, z0)
+if which in ("all", "k3"):
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
+    rng = A.PhiloxRNG(1)
+    for _ in range(3):
+        tr = A.transition(rng, h, kern, z0)
+    print("nuts depth mean", tr.stat["tree_depth"].double().mean().item(), "steps", tr.stat["n_steps"].double().mean().item())
+torch.cuda.synchronize()
+print("done")

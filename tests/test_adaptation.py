@@ -1,0 +1,134 @@
+"""CPU tests of the host-side pooled adaptation logic (advancedhmc.jl_b200/adaptation.py) against the oracle's
+restatement of src/adaptation/*.jl, plus the world_size-2 gloo path of the adaptor-record exchange."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import ahmc_b200 as A
+from ahmc_b200 import adaptation as ad
+from oracle import oracle_c as oc
+
+
+def _record(theta, alpha):
+    """what ahmc_adapt_summary_f64 produces for one rank: [N, sum min(1,a), mean, M2]."""
+    N, D = theta.shape
+    mu = theta.mean(axis=0)
+    return np.concatenate([[N, np.minimum(1, alpha).sum()], mu, ((theta - mu) ** 2).sum(axis=0)])
+
+
+def test_merge_records_equals_pooled_statistics():
+    rng = np.random.default_rng(0)
+    parts = [rng.normal(size=(n, 7)) * 2 + 1 for n in (5, 1, 64, 3)]
+    alphas = [rng.uniform(0, 1.5, size=p.shape[0]) for p in parts]
+    merged = ad.merge_records([_record(p, a) for p, a in zip(parts, alphas)])
+    allx, alla = np.concatenate(parts), np.concatenate(alphas)
+    want = _record(allx, alla)
+    assert np.allclose(merged, want, rtol=1e-12, atol=1e-12)
+
+
+def test_dual_averaging_one_chain_equals_reference_path():
+    """pooled DA with a single chain == stepsize.jl:178-210 (oracle)."""
+    rng = np.random.default_rng(1)
+    da, ref = ad.NesterovDualAveraging(0.8, 0.1), oc.DualAveraging([0.1], delta=0.8)
+    for _ in range(60):
+        a = rng.uniform(0, 1.4)
+        da.adapt(min(1.0, a))
+        ref.adapt([a])
+        assert da.eps == pytest.approx(ref.eps[0], rel=1e-14) and da.m == ref.m
+    da.reset(), ref.reset()
+    assert da.mu == pytest.approx(ref.mu[0], rel=1e-15) and da.m == 0
+    for _ in range(5):
+        da.adapt(0.5), ref.adapt([0.5])
+    da.finalize(), ref.finalize()
+    assert da.eps == pytest.approx(ref.eps[0], rel=1e-14)
+
+
+def test_pooled_welford_one_chain_equals_reference_and_many_chains_equal_pushing_each():
+    rng = np.random.default_rng(2)
+    D = 6
+    w, ref = ad.WelfordVar(D), oc.WelfordVar((D,))
+    for _ in range(30):  # one chain per iteration: Chan merge of (1, x, 0) == massmatrix.jl:141-149
+        x = rng.normal(size=D)
+        w.push_record(_record(x[None, :], np.ones(1)))
+        ref.push(x)
+    assert np.allclose(w.mu, ref.mu, rtol=1e-13) and np.allclose(w.M, ref.M, rtol=1e-12)
+    assert np.allclose(w.get_estimation(), ref.estimate(), rtol=1e-12)
+    # 16 chains per iteration == pushing the 16 positions one after another into the reference estimator
+    w2, ref2 = ad.WelfordVar(D), oc.WelfordVar((D,))
+    for _ in range(10):
+        X = rng.normal(size=(16, D)) * np.arange(1, D + 1)
+        w2.push_record(_record(X, np.ones(16)))
+        for x in X:
+            ref2.push(x)
+    assert w2.n == 160 and np.allclose(w2.get_estimation(), ref2.estimate(), rtol=1e-11)
+
+
+def test_stan_windows_pin_and_adaptor_schedule():
+    """test/adaptation.jl:131-151."""
+    assert ad.stan_windows(1000) == (76, 950, [100, 150, 250, 450, 950])
+    assert ad.stan_windows(1000) == oc.stan_windows(1000)
+    for n in (100, 150, 200, 537, 2000):
+        assert ad.stan_windows(n) == oc.stan_windows(n)
+    D = 3
+    rng = np.random.default_rng(3)
+    adp = ad.StanHMCAdaptor(ad.WelfordVar(D), ad.NesterovDualAveraging(0.8, 0.1))
+    adp.initialize(1000)
+    updates = []
+    for i in range(1, 1001):
+        before = adp.pc.var.copy()
+        adp.adapt(_record(rng.normal(size=(8, D)) * [1, 2, 3], rng.uniform(0.5, 1, 8)))
+        if not np.array_equal(before, adp.pc.var):
+            updates.append(i)
+        if i in (100, 150, 250, 450, 950):
+            assert adp.pc.n == 0 and adp.ssa.m == 0  # reset at window ends (stan_adaptor.jl:155-158)
+    adp.finalize()
+    assert updates == [100, 150, 250, 450, 950]
+    assert np.allclose(adp.Minv, [1, 4, 9], rtol=0.15)
+    assert adp.eps == pytest.approx(np.exp(adp.ssa.x_bar))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    theta, alpha = rng.normal(size=(5 + rank, 4)), rng.uniform(0, 1.2, 5 + rank)
+    rec = torch.as_tensor(_record(theta, alpha))
+    merged = ad.merge_records(ad.allgather_records(rec))
+    q.put((rank, merged))
+    dist.destroy_process_group()
+
+
+def test_adaptor_record_allgather_world_size_2_gloo():
+    """The path's only exchange: every rank ends with the same, rank-ordered merge."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in ps]
+    assert np.array_equal(res[0], res[1])  # bit-identical on every rank
+    parts = [(np.random.default_rng(100 + r).normal(size=(5 + r, 4)), None) for r in range(2)]
+    th = [np.random.default_rng(100 + r) for r in range(2)]
+    recs = []
+    for r in range(2):
+        g = np.random.default_rng(100 + r)
+        t, a = g.normal(size=(5 + r, 4)), g.uniform(0, 1.2, 5 + r)
+        recs.append(_record(t, a))
+    assert np.array_equal(res[0], ad.merge_records(recs))
+    assert res[0][0] == 11

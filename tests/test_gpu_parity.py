@@ -286,8 +286,8 @@ def test_hmc_transition_vs_oracle_with_tapes(model, metric, D):
         B = rng.normal(size=(D, D))
         Minv = B @ B.T / D + 0.5 * np.eye(D)
     th = rng.normal(size=(D, N)) * (0.3 if model == "funnel" else 1.0)
-    nt, et = rng.normal(size=(D, N)), rng.exponential(size=N) * 0.1
-    eps, L = (0.35, 10) if model != "funnel" else (0.1, 8)
+    nt, et = rng.normal(size=(D, N)), rng.exponential(size=N) * 0.02
+    eps, L = {"diag_gauss": (0.6, 10), "std_normal": (0.9, 10), "funnel": (0.1, 8), "dense_gauss": (0.3, 10)}[model]
     om, ome = oc.Model(MODEL_KINDS[model], D, p0, p1, 0.0), oc.Metric(METRIC_KINDS[metric], Minv)
     z0o = oc.phasepoint(om, ome, th, np.zeros((D, N)))
     zo, so = oc.hmc_transition(om, ome, eps, L, z0o, nt, et)
@@ -410,7 +410,8 @@ def test_nuts_transition_vs_oracle_with_tapes(model, metric, D, eps, scale):
     assert (F(st["tree_depth"]) == so.tree_depth).all(), (F(st["tree_depth"])[:20], so.tree_depth[:20])
     assert (F(st["n_steps"]) == so.n_steps).all()
     assert (F(st["numerical_error"]) == so.numerical_error).all()
-    assert len(set(so.tree_depth)) > 1  # divergent tree sizes inside warps were exercised
+    if D <= 32:
+        assert len(set(so.tree_depth)) > 1  # several chains per warp with divergent tree sizes
     assert_pp_close(tr.z, zo)
     assert rel_err(F(st["acceptance_rate"]), so.acceptance_rate) < 1e-9
     assert np.allclose(F(st["hamiltonian_energy_error"]), so.hamiltonian_energy_error, rtol=0, atol=1e-9 * D)
@@ -450,3 +451,22 @@ def test_nuts_sampling_moments_philox():
     assert np.abs((th.mean(axis=0) - m) / s).max() < 0.12 and np.abs(th.std(axis=0) / s - 1).max() < 0.1
     assert 1.0 < np.mean(depths) < 5.0
     assert tr.stat["acceptance_rate"].mean().item() > 0.6
+
+
+def test_pipelined_host_path_equals_device_path():
+    """N >= 1024 host-buffer calls take the chunked two-stream pipeline: same bytes out as the device call."""
+    D, N = 100, 4099
+    rng = np.random.default_rng(5)
+    s = np.exp(rng.uniform(-1, 1, D))
+    m = rng.normal(size=D)
+    Minv_pc = np.exp(rng.uniform(-1, 1, (N, D)))
+    th, r = rng.normal(size=(N, D)), rng.normal(size=(N, D))
+    eps = 0.05 * np.exp(rng.uniform(-0.3, 0.3, N))
+    for Minv in (np.exp(rng.uniform(-1, 1, D)), Minv_pc):
+        h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s))
+        zd, infod = A.step(A.Leapfrog(torch.as_tensor(eps, device=DEV)), h,
+                           A.phasepoint(h, torch.as_tensor(th, device=DEV), torch.as_tensor(r, device=DEV)), 17, return_info=True)
+        zh, infoh = A.step(A.Leapfrog(eps), h, A.phasepoint(h, th, r), 17, return_info=True)
+        for a, b in [(zh.theta, zd.theta), (zh.r, zd.r), (zh.lp.value, zd.lp.value), (zh.lk.value, zd.lk.value),
+                     (zh.lp.gradient, zd.lp.gradient), (zh.lk.gradient, zd.lk.gradient), (infoh.steps_done, infod.steps_done)]:
+            assert np.array_equal(a, b.cpu().numpy())

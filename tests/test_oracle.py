@@ -228,3 +228,75 @@ def test_cpu_fused_matches_oracle():
     b = oc.leapfrog_omp(model, metric, 0.1, z, 32, n_threads=2)
     for f in ("theta", "r", "lp_gradient", "lp_value", "lk_value"):
         assert rel_err(getattr(b, f), getattr(a, f)) < 1e-12, f
+
+
+# ------------------------------------------------------------------------------------------------ NUTS oracle
+def _nuts_run(D, N, eps, seed, model=None, metric=None, max_depth=10):
+    rng = np.random.default_rng(seed)
+    model = model or oc.Model(oc.STD_NORMAL, D)
+    metric = metric or oc.Metric(oc.UNIT)
+    th = rng.normal(size=(D, N))
+    z0 = oc.phasepoint(model, metric, th, np.zeros((D, N)))
+    nt = rng.normal(size=(D, N))
+    dirs = rng.integers(0, 2, size=(N, max_depth + 1)).astype(np.uint8)
+    exps = rng.exponential(size=(N, 1 << max_depth))
+    return oc.nuts_transition(model, metric, eps, z0, nt, dirs, exps, max_depth=max_depth), (th, nt, dirs, exps)
+
+
+def test_nuts_oracle_determinism_and_structure():
+    """test/trajectory.jl:125-141 (same randomness -> same transition) + tree bookkeeping invariants."""
+    (z1, s1, u1), _ = _nuts_run(5, 40, 0.3, 1)
+    (z2, s2, u2), _ = _nuts_run(5, 40, 0.3, 1)
+    assert (z1.theta == z2.theta).all() and (s1.tree_depth == s2.tree_depth).all() and (u1 == u2).all()
+    # a transition of depth j that ended by a U-turn of the whole tree has exactly 2^j - 1 leapfrog steps;
+    # early termination inside the last subtree gives fewer.  Always: 2^(j) - 1 <= n_steps <= 2^(j+1) - 1
+    j, n = s1.tree_depth, s1.n_steps
+    assert ((n >= (1 << j) - 1) & (n <= (1 << (j + 1)) - 1)).all()
+    # exponentials consumed: one per internal combine (post-order) + one per successful doubling
+    assert (u1 <= n).all() and (u1 >= j).all()
+    assert ((s1.acceptance_rate >= 0) & (s1.acceptance_rate <= 1)).all()
+    assert (s1.is_accept == 1).all()
+    assert np.allclose(s1.hamiltonian_energy, -(z1.lp_value + z1.lk_value))
+
+
+def test_nuts_oracle_uturn_criterion_hand_formula():
+    """test/trajectory.jl:249-325 analogue: for a depth-1 tree the generalised criterion is
+    dot(rho, Minv r_left) <= 0 || dot(rho, Minv r_right) <= 0 with rho = r_left + r_right."""
+    D = 4
+    rng = np.random.default_rng(3)
+    Minv = np.exp(rng.uniform(-1, 1, D))
+    model, metric = oc.Model(oc.STD_NORMAL, D), oc.Metric(oc.DIAG, Minv)
+    hits = 0
+    for trial in range(200):
+        th, r = rng.normal(size=(D, 1)), rng.normal(size=(D, 1))
+        z0 = oc.phasepoint(model, metric, th, r)
+        dirs = np.zeros((1, 3), dtype=np.uint8)  # always expand to the right
+        (z1, st, used) = oc.nuts_transition(model, metric, 1.2, z0, None, dirs, np.full((1, 8), 1e9), max_depth=2)
+        zr, _, _ = oc.leapfrog(model, metric, 1.2, z0, 1)
+        rho = z0.r[:, 0] + zr.r[:, 0]
+        turn = (rho @ (Minv * z0.r[:, 0]) <= 0) or (rho @ (Minv * zr.r[:, 0]) <= 0)
+        # a U-turn after the first doubling stops the loop with tree_depth 1 and n_steps 1
+        if turn:
+            hits += 1
+            assert st.tree_depth[0] == 1 and st.n_steps[0] == 1
+        else:
+            assert st.n_steps[0] > 1
+    assert 10 < hits < 190
+
+
+def test_nuts_oracle_samples_standard_normal():
+    """statistical pin of the whole NUTS restatement (test/sampler.jl style): 1 chain x 3000 transitions."""
+    D = 3
+    rng = np.random.default_rng(4)
+    model, metric = oc.Model(oc.STD_NORMAL, D), oc.Metric(oc.UNIT)
+    th = np.zeros((D, 1))
+    draws = []
+    z = oc.phasepoint(model, metric, th, np.zeros((D, 1)))
+    for it in range(3000):
+        nt = rng.normal(size=(D, 1))
+        dirs = rng.integers(0, 2, size=(1, 11)).astype(np.uint8)
+        exps = rng.exponential(size=(1, 1024))
+        z, st, _ = oc.nuts_transition(model, metric, 0.9, z, nt, dirs, exps)
+        draws.append(z.theta[:, 0].copy())
+    X = np.array(draws[200:])
+    assert np.abs(X.mean(axis=0)).max() < 0.12 and np.abs(X.var(axis=0) - 1).max() < 0.15
