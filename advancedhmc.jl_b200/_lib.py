@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libahmc_b200.so")
+LIB_PATH = os.environ.get("AHMC_B200_LIB", os.path.join(HERE, "libahmc_b200.so"))  # override: A/B builds
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_CALLBACK = 0, -1, -2, -3, -4, -5
 METRIC_UNIT, METRIC_DIAG, METRIC_DENSE = 0, 1, 2

@@ -182,6 +182,51 @@ class Funnel(_Target):
         super().__init__(L.MODEL_FUNNEL, D, c0=c0)
 
 
+class _RawCuda:
+    """zero-copy view of a raw device pointer for torch (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class CallbackTarget(_Target):
+    """An arbitrary user log-density: `fn(theta) -> (lp, grad)` on CUDA tensors, theta of shape (N, D), lp (N,),
+    grad (N, D) = PLUS gradient of log pi -- the role of the `lp` / `dlp/dtheta` closures of `Hamiltonian`
+    (src/hamiltonian.jl:1-6, 45-48).  The engine runs in split-step mode: per leapfrog step two small fused kernels
+    with `fn` evaluated in between on the context's stream (any torch code, autograd included).  Supported by
+    phasepoint / step / static-HMC transition; NUTS needs a device-resident (built-in) target."""
+
+    def __init__(self, D, fn):
+        self.kind, self.D, self.c0, self.p0, self.p1 = L.MODEL_CALLBACK, int(D), 0.0, None, None
+        self.fn = fn
+        self._handles = {}
+        self.error = None
+        self._cfn = L.LOGP_GRAD_FN(self._trampoline)
+
+    def _trampoline(self, user, theta, lp, grad, D, N, ld, stream):
+        try:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            view = lambda p, shape: torch.as_tensor(_RawCuda(p, shape), device=dev)
+            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+                th = view(theta, (N, ld))[:, :D]
+                v, g = self.fn(th)
+                view(lp, (N,)).copy_(v)
+                view(grad, (N, ld))[:, :D].copy_(g)
+            return 0
+        except Exception as e:  # never raise across the C ABI
+            self.error = e
+            return 1
+
+    def handle(self, ctx: Context):
+        h = self._handles.get(ctx.device)
+        if h is None:
+            h = C.c_void_p()
+            ctx.check(ctx.lib.ahmc_model_create_callback(ctx.h, self.D, self._cfn, None, C.byref(h)))
+            self._handles[ctx.device] = h
+        return h
+
+
 # ------------------------------------------------------------------------------------------------
 # metrics (src/metric.jl)
 # ------------------------------------------------------------------------------------------------

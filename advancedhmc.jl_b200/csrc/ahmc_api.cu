@@ -1,5 +1,6 @@
 // ahmc_api.cu -- the C ABI of libahmc_b200 (include/ahmc_b200.h): context, models, argument
 // validation, host-buffer staging and kernel dispatch.  No torch types, no exceptions across the ABI.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -24,6 +25,8 @@ struct ahmc_ctx {
     size_t nuts_scratch_bytes = 0;
     double* adapt_scratch = nullptr;
     size_t adapt_scratch_bytes = 0;
+    char* split_scratch = nullptr;   // callback (split-step) mode workspace
+    size_t split_scratch_bytes = 0;
     cudaStream_t stream2 = nullptr;  // second stream of the host-buffer pipeline (H2D of chunk i+1 || D2H of chunk i)
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 };
@@ -200,6 +203,87 @@ int finish_call(ahmc_ctx* ctx, Stager& st, uint32_t flags) {
     return AHMC_OK;
 }
 
+
+// ---- split-step (callback) mode --------------------------------------------------------------------------------
+struct SplitWork {
+    double* cb_lp;
+    double* cb_grad;
+    double* r0;
+    double* lk0;
+    uint32_t* status;
+    int32_t* steps;
+    int* flag;
+};
+
+int split_workspace(ahmc_ctx* ctx, int32_t D, int64_t N, int64_t ld, SplitWork* w) {
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t need = al((size_t)N * 8) + al((size_t)ld * N * 8) + al((size_t)D * N * 8) + al((size_t)N * 8) +
+                        al((size_t)N * 4) * 2 + 256;
+    if (need > ctx->split_scratch_bytes) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->split_scratch);
+        ctx->split_scratch = nullptr;
+        ctx->split_scratch_bytes = 0;
+        if (cudaMalloc((void**)&ctx->split_scratch, need) != cudaSuccess)
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc(%zu) for the split-step workspace failed", need);
+        ctx->split_scratch_bytes = need;
+    }
+    char* p = ctx->split_scratch;
+    w->cb_lp = (double*)p; p += al((size_t)N * 8);
+    w->cb_grad = (double*)p; p += al((size_t)ld * N * 8);
+    w->r0 = (double*)p; p += al((size_t)D * N * 8);
+    w->lk0 = (double*)p; p += al((size_t)N * 8);
+    w->status = (uint32_t*)p; p += al((size_t)N * 4);
+    w->steps = (int32_t*)p; p += al((size_t)N * 4);
+    w->flag = (int*)p;
+    return AHMC_OK;
+}
+
+// user closure on the context stream: lp[N], grad[D x N] <- theta
+int call_user(ahmc_ctx* ctx, const ahmc_model* model, const double* th, double* lp, double* grad, int32_t D, int64_t N,
+              int64_t ld) {
+    int rc = model->fn(model->user, th, lp, grad, D, N, ld, (void*)ctx->stream);
+    if (rc != 0) return fail(ctx, AHMC_ERR_CALLBACK, "user gradient callback returned %d", rc);
+    return AHMC_OK;
+}
+
+// n leapfrog steps in split mode on DEVICE work arrays (th, r, g, lp, lk[, dr]); status/steps are device arrays
+int split_trajectory(ahmc_ctx* ctx, const ahmc_model* model, const MetricDev& md, int32_t D, int64_t N, double eps,
+                     const double* eps_chain, int n_abs, int fwd, double temper_alpha, double* th, double* r, double* g,
+                     double* lp, double* lk, double* dr, int64_t ld, uint32_t* status, int32_t* steps, const SplitWork& w,
+                     bool compat, int* nl) {
+    CU(cudaMemsetAsync(status, 0, (size_t)N * 4, ctx->stream));
+    if (steps) CU(cudaMemsetAsync(steps, 0, (size_t)N * 4, ctx->stream));
+    CU(cudaMemsetAsync(w.flag, 0, sizeof(int), ctx->stream));
+    const double sa = temper_alpha > 0.0 ? sqrt(temper_alpha) : 1.0;
+    for (int i = 1; i <= n_abs; ++i) {
+        SplitArgs a{};
+        a.metric = md;
+        a.D = D;
+        a.N = N;
+        a.eps = eps;
+        a.eps_chain = eps_chain;
+        a.fwd = fwd;
+        a.mul = temper_alpha > 0.0 ? ((2 * (i - 1) + 1 <= n_abs) ? sa : 1.0 / sa) : 1.0;
+        a.step_index = i;
+        a.th = th; a.r = r; a.g = g; a.lp = lp; a.lk = lk; a.dr = dr;
+        a.cb_lp = w.cb_lp; a.cb_grad = w.cb_grad;
+        a.ld = ld;
+        a.status = status; a.steps_done = steps; a.any_nonfinite = w.flag;
+        CU(launch_kick_drift(a, ctx->stream, nl));
+        int rc = call_user(ctx, model, th, w.cb_lp, w.cb_grad, D, N, ld);
+        if (rc) return rc;
+        a.mul = temper_alpha > 0.0 ? ((2 * (i - 1) + 2 <= n_abs) ? sa : 1.0 / sa) : 1.0;
+        CU(launch_kick_energy(a, ctx->stream, nl));
+        if (compat) {  // reference quirk Q1: first non-finite chain stops everyone (hamiltonian.jl:141-142)
+            int f = 0;
+            CU(cudaMemcpyAsync(&f, w.flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (f) break;
+        }
+    }
+    return AHMC_OK;
+}
 }  // namespace
 
 // =================================================================================================
@@ -248,6 +332,7 @@ int ahmc_destroy(ahmc_ctx* ctx) {
     cudaFree(ctx->arena);
     cudaFree(ctx->nuts_scratch);
     cudaFree(ctx->adapt_scratch);
+    cudaFree(ctx->split_scratch);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -343,8 +428,6 @@ int ahmc_phasepoint_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metri
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
     if ((rc = check_pp(ctx, z, D, "z", true, N))) return rc;
-    if (model->kind == AHMC_MODEL_CALLBACK)
-        return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
     if (N == 0) return AHMC_OK;
     DeviceGuard g(ctx->device);
     Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
@@ -366,7 +449,18 @@ int ahmc_phasepoint_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metri
     if ((rc = st.out(z->lk_value, (size_t)N, &a.lk))) return rc;
     if ((rc = st.out(z->lk_gradient, (size_t)z->ld * N, &a.dr))) return rc;
     int nl = 0;
-    CU(launch_phasepoint(a, ctx->stream, &nl));
+    if (model->kind == AHMC_MODEL_CALLBACK) {  // user closure, then the metric half of phasepoint
+        SplitWork w;
+        if ((rc = split_workspace(ctx, D, N, z->ld, &w))) return rc;
+        if ((rc = call_user(ctx, model, a.th, w.cb_lp, w.cb_grad, D, N, z->ld))) return rc;
+        SplitArgs sa{};
+        sa.metric = a.metric; sa.D = D; sa.N = N; sa.fwd = 1; sa.mul = 1.0; sa.no_kick = 1;
+        sa.r = const_cast<double*>(a.r); sa.g = a.g; sa.lp = a.lp; sa.lk = a.lk; sa.dr = a.dr;
+        sa.cb_lp = w.cb_lp; sa.cb_grad = w.cb_grad; sa.ld = z->ld;
+        CU(launch_kick_energy(sa, ctx->stream, &nl));
+    } else {
+        CU(launch_phasepoint(a, ctx->stream, &nl));
+    }
     ctx->launches += nl;
     return finish_call(ctx, st, flags);
 }
@@ -513,8 +607,6 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
     if (rc) return rc;
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
     if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
-    if (model->kind == AHMC_MODEL_CALLBACK)
-        return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
     if (N == 0) return AHMC_OK;
     DeviceGuard g(ctx->device);
     const bool host = flags & AHMC_FLAG_HOST_BUFFERS;
@@ -533,7 +625,7 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
         }
         return AHMC_OK;
     }
-    if (host && !(flags & AHMC_FLAG_COMPAT_BREAK_ALL) && N >= 1024)
+    if (host && !(flags & AHMC_FLAG_COMPAT_BREAK_ALL) && N >= 1024 && model->kind != AHMC_MODEL_CALLBACK)
         return leapfrog_host_pipelined(ctx, model, metric, D, N, eps, eps_chain, n_steps, temper_alpha, z_in, z_out,
                                        status, steps_done, flags);
     Stager st(ctx, host);
@@ -571,6 +663,26 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
     a.flags = flags;
     const bool compat = flags & AHMC_FLAG_COMPAT_BREAK_ALL;
     a.min_break = nullptr;
+    if (model->kind == AHMC_MODEL_CALLBACK) {
+        // split-step mode: the work state is the OUTPUT phase point; two small kernels + the user closure per step
+        SplitWork w;
+        if ((rc = split_workspace(ctx, D, N, z_out->ld, &w))) return rc;
+        auto cp = [&](double* dst, const double* src) -> cudaError_t {
+            if (dst == src) return cudaSuccess;
+            return cudaMemcpy2DAsync(dst, (size_t)a.ld_out * 8, src, (size_t)a.ld_in * 8, (size_t)D * 8, (size_t)N,
+                                     cudaMemcpyDeviceToDevice, ctx->stream);
+        };
+        CU(cp(a.th_out, a.th_in));
+        CU(cp(a.r_out, a.r_in));
+        CU(cp(a.g_out, a.g_in));
+        int nl2 = 0;
+        rc = split_trajectory(ctx, model, a.metric, D, N, eps, a.eps_chain, n_abs, a.fwd, temper_alpha, a.th_out, a.r_out,
+                              a.g_out, a.lp_out, a.lk_out, a.dr_out, a.ld_out, a.status ? a.status : w.status,
+                              a.steps_done, w, compat, &nl2);
+        ctx->launches += nl2;
+        if (rc) return rc;
+        return finish_call(ctx, st, flags);
+    }
     if (compat) {
         const int big = 0x7fffffff;
         CU(cudaMemcpyAsync(ctx->d_min_break, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -668,8 +780,6 @@ int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_m
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
     if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
     if (n_steps < 1) return fail(ctx, AHMC_ERR_INVALID, "n_steps must be >= 1 (nsteps(tau) = max(1, ...), trajectory.jl:240-243)");
-    if (model->kind == AHMC_MODEL_CALLBACK)
-        return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
     if (flags & AHMC_FLAG_COMPAT_BREAK_ALL)
         return fail(ctx, AHMC_ERR_UNSUPPORTED, "COMPAT_BREAK_ALL is only available on ahmc_leapfrog_f64");
     if (metric->kind == AHMC_METRIC_DENSE && !metric->cholU && !(flags & AHMC_FLAG_NO_REFRESH))
@@ -714,6 +824,46 @@ int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_m
     if ((rc = stage_stats(st, stats, N, &h.st))) return rc;
     h.refresh = (flags & AHMC_FLAG_NO_REFRESH) ? 0 : 1;
     int nl = 0;
+    if (model->kind == AHMC_MODEL_CALLBACK) {
+        // refresh -> kinetic energy -> split-step trajectory -> MH select (same semantics as hmc_kernel, unfused)
+        SplitWork w;
+        if ((rc = split_workspace(ctx, D, N, z_out->ld, &w))) return rc;
+        if (h.refresh) {
+            MomentumArgs ma{};
+            ma.metric = a.metric; ma.D = D; ma.N = N; ma.seed = h.rng.seed; ma.offset = h.rng.offset;
+            ma.normal_tape = h.rng.normal_tape; ma.r = w.r0; ma.ld = D;
+            CU(launch_rand_momentum(ma, ctx->stream, &nl));
+        } else {
+            CU(cudaMemcpy2DAsync(w.r0, (size_t)D * 8, a.r_in, (size_t)a.ld_in * 8, (size_t)D * 8, (size_t)N,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        SplitArgs k0{};  // lk0 = neg kinetic energy of the refreshed momentum
+        k0.metric = a.metric; k0.D = D; k0.N = N; k0.fwd = 1; k0.mul = 1.0; k0.no_kick = 1;
+        k0.r = w.r0; k0.lk = w.lk0; k0.ld = D;
+        CU(launch_kick_energy(k0, ctx->stream, &nl));
+        auto cp = [&](double* dst, const double* src, int64_t lds) -> cudaError_t {
+            if (dst == src) return cudaSuccess;
+            return cudaMemcpy2DAsync(dst, (size_t)a.ld_out * 8, src, (size_t)lds * 8, (size_t)D * 8, (size_t)N,
+                                     cudaMemcpyDeviceToDevice, ctx->stream);
+        };
+        if (a.th_out == a.th_in)
+            return fail(ctx, AHMC_ERR_INVALID, "callback-mode transitions need z_out distinct from z_in (the start point is re-read on rejection)");
+        CU(cp(a.th_out, a.th_in, a.ld_in));
+        CU(cp(a.g_out, a.g_in, a.ld_in));
+        CU(cp(a.r_out, w.r0, D));
+        rc = split_trajectory(ctx, model, a.metric, D, N, eps, a.eps_chain, n_steps, 1, 0.0, a.th_out, a.r_out, a.g_out,
+                              a.lp_out, a.lk_out, nullptr, a.ld_out, w.status, w.steps, w, false, &nl);
+        if (rc) return rc;
+        MhArgs m{};
+        m.D = D; m.N = N; m.n_steps = n_steps;
+        m.th0 = a.th_in; m.g0 = a.g_in; m.lp0 = a.lp_in; m.ld0 = a.ld_in;
+        m.r0 = w.r0; m.lk0 = w.lk0;
+        m.th = a.th_out; m.r = a.r_out; m.g = a.g_out; m.lp = a.lp_out; m.lk = a.lk_out; m.ld = a.ld_out;
+        m.rng = h.rng; m.st = h.st;
+        CU(launch_mh_select(m, ctx->stream, &nl));
+        ctx->launches += nl;
+        return finish_call(ctx, st, flags);
+    }
     CU(launch_hmc(h, ctx->stream, &nl));
     ctx->launches += nl;
     return finish_call(ctx, st, flags);
@@ -730,7 +880,7 @@ int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_
     if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
     if (max_depth < 0 || max_depth > 20) return fail(ctx, AHMC_ERR_INVALID, "max_depth must be in 0..20");
     if (model->kind == AHMC_MODEL_CALLBACK)
-        return fail(ctx, AHMC_ERR_UNSUPPORTED, "callback models are not wired into this entry point yet");
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "NUTS needs a device-resident target: callback (split-step) models are supported by ahmc_leapfrog_f64 / ahmc_hmc_transition_f64 / ahmc_phasepoint_f64 only");
     if (metric->kind == AHMC_METRIC_DENSE && !metric->cholU && !(flags & AHMC_FLAG_NO_REFRESH))
         return fail(ctx, AHMC_ERR_INVALID, "Dense metric needs cholU for the momentum refresh (metric.jl:311-320)");
     if (z_out->lk_gradient)

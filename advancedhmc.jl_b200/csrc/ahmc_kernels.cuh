@@ -92,6 +92,41 @@ struct NutsArgs {
     long long scratch_stride; // doubles per chain
 };
 
+// split-step mode (user gradient callback between the two half kicks): one leapfrog step = kick_drift kernel,
+// the user's lp/grad evaluation on the same stream, kick_energy kernel.  State lives in the OUTPUT phase point.
+struct SplitArgs {
+    MetricDev metric;
+    int D;
+    long long N;
+    double eps;
+    const double* eps_chain;
+    int fwd;
+    double mul;                 // tempering multiplier for this half (1.0: none)
+    int step_index;             // 1-based step number (kick_energy records it in steps_done)
+    int no_kick;                // 1: phasepoint mode -- leave r alone, ignore status, only (g, lp, lk, dr)
+    double *th, *r, *g;         // work state (D x N, ld)
+    double *lp, *lk, *dr;       // energies (N) and optional dH/dr
+    const double* cb_lp;        // callback outputs: lp[N], grad[D x N] (PLUS gradient)
+    const double* cb_grad;
+    long long ld;
+    uint32_t* status;           // per-chain: non-zero = frozen (already non-finite)
+    int32_t* steps_done;
+    int* any_nonfinite;         // device flag, set when a chain turns non-finite in this step
+};
+
+struct MhArgs {  // accept / revert / flip + stats after a split-mode trajectory (trajectory.jl:271-300)
+    int D;
+    long long N;
+    int n_steps;
+    const double *th0, *g0, *lp0;  // start point (ld0)
+    long long ld0;
+    const double *r0, *lk0;        // refreshed momentum (ld = D) and its kinetic energy
+    double *th, *r, *g, *lp, *lk;  // in: proposal; out: new phase point (ld)
+    long long ld;
+    RngDev rng;
+    StatsDev st;
+};
+
 // choose (G, E) for a dimension: returns false if D is out of the register-resident range
 bool pick_layout(int D, int* G, int* E);
 
@@ -102,6 +137,9 @@ cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t stream, int
 cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_nuts(const NutsArgs& a, cudaStream_t stream, int* n_launches);
 long long nuts_scratch_doubles_per_chain(int D, int max_depth);
+cudaError_t launch_kick_drift(const SplitArgs& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_kick_energy(const SplitArgs& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_mh_select(const MhArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_adapt_summary(int D, long long N, const double* theta, long long ld, const double* alpha,
                                  double* out, double* partial, unsigned* counter, int blocks, cudaStream_t st,
                                  int* n_launches);

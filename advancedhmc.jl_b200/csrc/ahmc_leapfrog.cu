@@ -262,6 +262,145 @@ __global__ void __launch_bounds__(kBlockThreads) momentum_kernel(const MomentumA
 }
 
 // ---------------------------------------------------------------------------------------------
+// split-step kernels: the generic path for a user-supplied gradient (hamiltonian.jl:45-48 closure)
+// ---------------------------------------------------------------------------------------------
+// first half of integrator.jl:235-240: temper, r -= eps/2 g, theta += eps dH/dr(r)
+template <int METRIC, int G, int E>
+__global__ void __launch_bounds__(kBlockThreads) kick_drift_kernel(const SplitArgs a) {
+    extern __shared__ double smem[];
+    const int l = threadIdx.x % G;
+    const int grp_in_block = threadIdx.x / G;
+    const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + grp_in_block;
+    const bool valid = chain0 < a.N;
+    const long long chain = valid ? chain0 : a.N - 1;
+    const int D = a.D;
+    double* xs = smem + (size_t)grp_in_block * D;
+    const bool active = valid && a.status[chain] == 0u;
+    double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
+    eps = a.fwd ? eps : -eps;
+    MetricOps<METRIC, G, E> me;
+    me.load(a.metric, chain, l, D);
+    double th[E], r[E], g[E], dr[E];
+    vload_nc<G, E>(th, a.th + a.ld * chain, l, D);
+    vload_nc<G, E>(r, a.r + a.ld * chain, l, D);
+    vload_nc<G, E>(g, a.g + a.ld * chain, l, D);
+    const double he = 0.5 * eps;
+#pragma unroll
+    for (int e = 0; e < E; ++e) r[e] = fma(-he, g[e], r[e] * a.mul);
+    me.dHdr(r, dr, xs, l);
+#pragma unroll
+    for (int e = 0; e < E; ++e) th[e] = fma(eps, dr[e], th[e]);
+    if (active) {
+        vstore<G, E>(a.th + a.ld * chain, th, l, D);
+        vstore<G, E>(a.r + a.ld * chain, r, l, D);
+    }
+}
+
+// second half of integrator.jl:242-258: g = -grad, r -= eps/2 g, temper, energies, isfinite(z).
+// no_kick = 1 turns it into the tail of `phasepoint` (hamiltonian.jl:115-119): r untouched, status ignored,
+// cb_grad / cb_lp may be NULL (then only lk / dH/dr are produced).
+template <int METRIC, int G, int E>
+__global__ void __launch_bounds__(kBlockThreads) kick_energy_kernel(const SplitArgs a) {
+    extern __shared__ double smem[];
+    const int l = threadIdx.x % G;
+    const int grp_in_block = threadIdx.x / G;
+    const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + grp_in_block;
+    const bool valid = chain0 < a.N;
+    const long long chain = valid ? chain0 : a.N - 1;
+    const int D = a.D;
+    double* xs = smem + (size_t)grp_in_block * D;
+    const bool active = valid && (a.no_kick || a.status[chain] == 0u);
+    double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
+    eps = a.fwd ? eps : -eps;
+    MetricOps<METRIC, G, E> me;
+    me.load(a.metric, chain, l, D);
+    double r[E], g[E], dr[E];
+    vload_nc<G, E>(r, a.r + a.ld * chain, l, D);
+    if (a.cb_grad) {
+        vload_nc<G, E>(g, a.cb_grad + a.ld * chain, l, D);
+#pragma unroll
+        for (int e = 0; e < E; ++e) g[e] = -g[e];  // dH/dtheta = DualValue(lp, -grad) (hamiltonian.jl:47)
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) g[e] = 0.0;
+    }
+    if (!a.no_kick) {
+        const double he = 0.5 * eps;
+#pragma unroll
+        for (int e = 0; e < E; ++e) r[e] = fma(-he, g[e], r[e]) * a.mul;
+    }
+    const double lk = kinetic<METRIC, G, E>(me, r, dr, xs, l);
+    const double lp = a.cb_lp ? a.cb_lp[chain] : 0.0;
+    bool fin = true;
+#pragma unroll
+    for (int e = 0; e < E; ++e) fin = fin && finite_d(g[e]) && finite_d(dr[e]);
+    fin = Grp<G>::all(fin) && finite_d(lp) && finite_d(lk);
+    if (active) {
+        if (!a.no_kick) vstore<G, E>(a.r + a.ld * chain, r, l, D);
+        if (a.cb_grad) vstore<G, E>(a.g + a.ld * chain, g, l, D);
+        if (a.dr) vstore<G, E>(a.dr + a.ld * chain, dr, l, D);
+        if (l == 0) {
+            if (a.cb_lp) a.lp[chain] = map_nonfinite(lp);
+            a.lk[chain] = map_nonfinite(lk);
+            if (!a.no_kick) {
+                if (a.steps_done) a.steps_done[chain] = a.step_index;
+                if (!fin) {
+                    a.status[chain] = AHMC_STATUS_NONFINITE;
+                    if (a.any_nonfinite) *a.any_nonfinite = 1;
+                }
+            }
+        }
+    }
+}
+
+// mh_accept_ratio + accept_phasepoint! + flip + stats, element-parallel over the group (trajectory.jl:271-300)
+template <int G, int E>
+__global__ void __launch_bounds__(kBlockThreads) mh_select_kernel(const MhArgs a) {
+    const int l = threadIdx.x % G;
+    const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + threadIdx.x / G;
+    if (chain0 >= a.N) return;
+    const long long chain = chain0;
+    const int D = a.D;
+    const double lp0 = map_nonfinite(a.lp0[chain]), lk0 = a.lk0[chain];
+    const double lp1 = a.lp[chain], lk1 = a.lk[chain];
+    const double H0 = -(lp0 + lk0), H1 = -(lp1 + lk1);
+    const double ex = a.rng.exp_tape ? a.rng.exp_tape[chain] : philox_exp(a.rng.seed, a.rng.offset, chain, 0);
+    const bool accept = H1 < H0 + ex;
+    double alpha = exp(H0 - H1);
+    alpha = (alpha != alpha) ? alpha : (alpha < 1.0 ? alpha : 1.0);
+    double t[E];
+    if (accept) {
+        vload_nc<G, E>(t, a.r + a.ld * chain, l, D);
+#pragma unroll
+        for (int e = 0; e < E; ++e) t[e] = -t[e];
+        vstore<G, E>(a.r + a.ld * chain, t, l, D);
+    } else {
+        vload_nc<G, E>(t, a.th0 + a.ld0 * chain, l, D);
+        vstore<G, E>(a.th + a.ld * chain, t, l, D);
+        vload_nc<G, E>(t, a.g0 + a.ld0 * chain, l, D);
+        vstore<G, E>(a.g + a.ld * chain, t, l, D);
+        vload_nc<G, E>(t, a.r0 + (long long)D * chain, l, D);
+#pragma unroll
+        for (int e = 0; e < E; ++e) t[e] = -t[e];
+        vstore<G, E>(a.r + a.ld * chain, t, l, D);
+    }
+    if (l == 0) {
+        const double lpn = accept ? lp1 : lp0, lkn = accept ? lk1 : lk0;
+        const double H = -(lpn + lkn);
+        a.lp[chain] = lpn;
+        a.lk[chain] = lkn;
+        const StatsDev& st = a.st;
+        if (st.n_steps) st.n_steps[chain] = a.n_steps;
+        if (st.is_accept) st.is_accept[chain] = accept ? 1 : 0;
+        if (st.acceptance_rate) st.acceptance_rate[chain] = alpha;
+        if (st.log_density) st.log_density[chain] = lpn;
+        if (st.hamiltonian_energy) st.hamiltonian_energy[chain] = H;
+        if (st.hamiltonian_energy_error) st.hamiltonian_energy_error[chain] = H - H0;
+        if (st.numerical_error) st.numerical_error[chain] = finite_d(H1) ? 0 : 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------
 template <int MODEL, int METRIC, int G, int E>
@@ -304,6 +443,34 @@ static cudaError_t launch_hmc_t(const HmcArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 template <int METRIC, int G, int E>
+static cudaError_t launch_kd_t(const SplitArgs& a, cudaStream_t st) {
+    const long long blocks = (a.N + kBlockThreads / G - 1) / (kBlockThreads / G);
+    size_t sm = smem_bytes(AHMC_MODEL_STD_NORMAL, METRIC, a.D, G);
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kick_drift_kernel<METRIC, G, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+    }
+    kick_drift_kernel<METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    return cudaGetLastError();
+}
+template <int METRIC, int G, int E>
+static cudaError_t launch_ke_t(const SplitArgs& a, cudaStream_t st) {
+    const long long blocks = (a.N + kBlockThreads / G - 1) / (kBlockThreads / G);
+    size_t sm = smem_bytes(AHMC_MODEL_STD_NORMAL, METRIC, a.D, G);
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kick_energy_kernel<METRIC, G, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+    }
+    kick_energy_kernel<METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    return cudaGetLastError();
+}
+template <int DUMMY, int G, int E>
+static cudaError_t launch_mh_t(const MhArgs& a, cudaStream_t st) {
+    const long long blocks = (a.N + kBlockThreads / G - 1) / (kBlockThreads / G);
+    mh_select_kernel<G, E><<<(unsigned)blocks, kBlockThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+template <int METRIC, int G, int E>
 static cudaError_t launch_mom_t(const MomentumArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;
     const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
@@ -335,6 +502,18 @@ static cudaError_t pp_layout(const PhasepointArgs& a, cudaStream_t st, int G, in
 template <int MODEL, int METRIC>
 static cudaError_t hmc_layout(const HmcArgs& a, cudaStream_t st, int G, int E) {
     AHMC_DISPATCH_LAYOUT(launch_hmc_t, MODEL, METRIC);
+}
+template <int METRIC>
+static cudaError_t kd_layout(const SplitArgs& a, cudaStream_t st, int G, int E) {
+    AHMC_DISPATCH_LAYOUT(launch_kd_t, METRIC);
+}
+template <int METRIC>
+static cudaError_t ke_layout(const SplitArgs& a, cudaStream_t st, int G, int E) {
+    AHMC_DISPATCH_LAYOUT(launch_ke_t, METRIC);
+}
+template <int DUMMY>
+static cudaError_t mh_layout(const MhArgs& a, cudaStream_t st, int G, int E) {
+    AHMC_DISPATCH_LAYOUT(launch_mh_t, DUMMY);
 }
 template <int METRIC>
 static cudaError_t mom_layout(const MomentumArgs& a, cudaStream_t st, int G, int E) {
@@ -379,6 +558,35 @@ cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t st, int* n_launches) {
     if (!pick_layout(a.lf.D, &G, &E)) return cudaErrorInvalidValue;
     if (n_launches) *n_launches += 1;
     AHMC_DISPATCH_MM(hmc_layout, a.lf.model.kind, a.lf.metric.kind);
+}
+
+cudaError_t launch_kick_drift(const SplitArgs& a, cudaStream_t st, int* n_launches) {
+    int G, E;
+    if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+    if (n_launches) *n_launches += 1;
+    switch (a.metric.kind) {
+        case AHMC_METRIC_UNIT: return kd_layout<AHMC_METRIC_UNIT>(a, st, G, E);
+        case AHMC_METRIC_DIAG: return kd_layout<AHMC_METRIC_DIAG>(a, st, G, E);
+        case AHMC_METRIC_DENSE: return kd_layout<AHMC_METRIC_DENSE>(a, st, G, E);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_kick_energy(const SplitArgs& a, cudaStream_t st, int* n_launches) {
+    int G, E;
+    if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+    if (n_launches) *n_launches += 1;
+    switch (a.metric.kind) {
+        case AHMC_METRIC_UNIT: return ke_layout<AHMC_METRIC_UNIT>(a, st, G, E);
+        case AHMC_METRIC_DIAG: return ke_layout<AHMC_METRIC_DIAG>(a, st, G, E);
+        case AHMC_METRIC_DENSE: return ke_layout<AHMC_METRIC_DENSE>(a, st, G, E);
+    }
+    return cudaErrorInvalidValue;
+}
+cudaError_t launch_mh_select(const MhArgs& a, cudaStream_t st, int* n_launches) {
+    int G, E;
+    if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+    if (n_launches) *n_launches += 1;
+    return mh_layout<0>(a, st, G, E);
 }
 
 cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t st, int* n_launches) {

@@ -41,8 +41,16 @@ __device__ __forceinline__ double maxabs(double a, double b) { return fabs(a) > 
 
 constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, cand lk
 
+// Occupancy knob: the tree walk is a long chain of dependent, mostly fixed-latency instructions, so throughput
+// scales with resident warps per scheduler; cap registers so that this many 4-warp blocks fit per SM.
+#ifndef AHMC_NUTS_MINB
+#define AHMC_NUTS_MINB 3
+#endif
+template <int E>
+constexpr int nuts_min_blocks() { return E <= 4 ? AHMC_NUTS_MINB : (E <= 8 ? 2 : 1); }
+
 template <int MODEL, int METRIC, int G, int E>
-__global__ void __launch_bounds__(kBlockThreads) nuts_kernel(const NutsArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kernel(const NutsArgs a) {
     extern __shared__ double smem[];
     const int l = threadIdx.x % G;
     const int grp_in_block = threadIdx.x / G;
@@ -159,12 +167,9 @@ __global__ void __launch_bounds__(kBlockThreads) nuts_kernel(const NutsArgs a) {
         double na_c = 1.0, dh_c = dH;
         bool tnum_c = !(-H0 < a.delta_max + -H1);            // Termination(...) (:503-507)
         bool tdyn_c = false;
-        double rho_cur[E], rfirst_cur[E];
+        double rho_cur[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            rho_cur[e] = s.r[e];  // TurnStatistic(z.r)
-            rfirst_cur[e] = s.r[e];
-        }
+        for (int e = 0; e < E; ++e) rho_cur[e] = s.r[e];  // TurnStatistic(z.r)
         int cand_cur = -1;  // -1: the leaf in registers; k >= 0: candidate stored in level slot k
 
         // ---------------------------------------------------------------- (C) post-order merges (:649-673)
@@ -219,16 +224,19 @@ __global__ void __launch_bounds__(kBlockThreads) nuts_kernel(const NutsArgs a) {
                     na_c += na_p;
                     dh_c = (v > 0) ? maxabs(dh_p, dh_c) : maxabs(dh_c, dh_p);
                     tdyn_c = tdyn_c || uturn;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) rfirst_cur[e] = rf_p[e];
                 }
             }
             if (__any_sync(FULL, do_store)) {
                 if (do_store) {
                     double* L = level(k);
                     if (k > 0) {
+                        // first-built leaf of this node = first-built leaf of the half merged last (level k-1),
+                        // whose slot is still intact (level 0 keeps it as its candidate momentum)
+                        double t[E];
+                        const double* P = level(k - 1);
+                        vload_nc<G, E>(t, (k == 1) ? P + 3 * (long long)D : P + D, l, D);
+                        vstore<G, E>(L + D, t, l, D);
                         vstore<G, E>(L, rho_cur, l, D);
-                        vstore<G, E>(L + D, rfirst_cur, l, D);
                     }
                     double clp, clk;
                     if (cand_cur < 0) {

@@ -470,3 +470,75 @@ def test_pipelined_host_path_equals_device_path():
         for a, b in [(zh.theta, zd.theta), (zh.r, zd.r), (zh.lp.value, zd.lp.value), (zh.lk.value, zd.lk.value),
                      (zh.lp.gradient, zd.lp.gradient), (zh.lk.gradient, zd.lk.gradient), (infoh.steps_done, infod.steps_done)]:
             assert np.array_equal(a, b.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ user closure (split-step)
+def _torch_funnel(th):
+    """Neal's funnel written by a 'user' in plain torch, gradient by autograd."""
+    th = th.detach().clone().requires_grad_(True)
+    v, x = th[:, 0], th[:, 1:]
+    lp = -v * v / 18 - 0.5 * ((x * x) * torch.exp(-v)[:, None]).sum(dim=1) - 0.5 * (th.shape[1] - 1) * v
+    (g,) = torch.autograd.grad(lp.sum(), th)
+    return lp.detach(), g
+
+
+@pytest.mark.parametrize("metric,D", [("unit", 8), ("diag", 40), ("dense", 12)])
+def test_callback_target_matches_builtin_and_oracle(metric, D):
+    """`Hamiltonian(metric, user_lp, user_grad)`: an arbitrary closure in split-step mode gives the same trajectory."""
+    rng = np.random.default_rng(D)
+    N = 77
+    Minv = None
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    elif metric == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+    th, r = rng.normal(size=(D, N)) * 0.5, rng.normal(size=(D, N))
+    om, ome = oc.Model(oc.FUNNEL, D), oc.Metric(METRIC_KINDS[metric], Minv)
+    z0o = oc.phasepoint(om, ome, th, r)
+    zo, st_o, dn_o = oc.leapfrog(om, ome, 0.07, z0o, 9)
+    hc = A.Hamiltonian(make_metric(metric, Minv, D), A.CallbackTarget(D, _torch_funnel))
+    z0 = A.phasepoint(hc, T(th), T(r))
+    assert_pp_close(z0, z0o, tol=1e-12, fields=("lp_gradient", "lp_value", "lk_value", "lk_gradient"))
+    z1, info = A.step(A.Leapfrog(0.07), hc, z0, 9, return_info=True)
+    assert hc.target.error is None
+    assert (F(info.steps_done) == dn_o).all() and (F(info.status) == 0).all()
+    assert_pp_close(z1, zo, fields=("theta", "r", "lp_gradient", "lp_value", "lk_value", "lk_gradient"))
+    # tempered + backward through the same path
+    zo2, _, _ = oc.leapfrog(om, ome, 0.05, z0o, -6, temper_alpha=1.1)
+    z2 = A.step(A.TemperedLeapfrog(0.05, 1.1), hc, z0, -6)
+    assert_pp_close(z2, zo2)
+    # static HMC transition with tapes: same accept decisions and state as the oracle
+    nt, et = rng.normal(size=(D, N)), rng.exponential(size=N) * 0.02
+    zt, so = oc.hmc_transition(om, ome, 0.12, 7, z0o, nt, et)
+    tau = A.Trajectory(A.EndPointTS, A.Leapfrog(0.12), A.FixedNSteps(7))
+    tr = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(et, device=DEV)), hc, A.HMCKernel(tau), z0)
+    assert (F(tr.stat["is_accept"]).astype(bool) == so.is_accept.astype(bool)).all()
+    assert_pp_close(tr.z, zt)
+    assert rel_err(F(tr.stat["acceptance_rate"]), so.acceptance_rate) < 1e-9
+
+
+def test_callback_nonfinite_freeze_and_error_propagation():
+    D, N = 3, 5
+    def std_normal(th):
+        return -0.5 * (th * th).sum(dim=1), -th
+    h = A.Hamiltonian(A.UnitEuclideanMetric(D), A.CallbackTarget(D, std_normal))
+    th = np.ones((D, N)); th[:, 1] = 1e200
+    om, ome = oc.Model(oc.STD_NORMAL, D), oc.Metric(oc.UNIT)
+    z0o = oc.phasepoint(om, ome, th, np.ones((D, N)))
+    for compat in (False, True):
+        zo, st_o, dn_o = oc.leapfrog(om, ome, 0.1, z0o, 4, compat_break_all=compat)
+        z1, info = A.step(A.Leapfrog(0.1), h, A.phasepoint(h, T(th), T(np.ones((D, N)))), 4,
+                          flags=A.FLAG_COMPAT_BREAK_ALL if compat else 0, return_info=True)
+        assert (F(info.steps_done) == dn_o).all() and (F(info.status) == st_o).all()
+        ok = [0, 2, 3, 4]
+        assert rel_err(F(z1.theta)[:, ok], zo.theta[:, ok]) < TOL
+    def broken(th):
+        raise RuntimeError("user model failed")
+    hb = A.Hamiltonian(A.UnitEuclideanMetric(D), A.CallbackTarget(D, broken))
+    with pytest.raises(A.AhmcError, match="callback"):
+        A.phasepoint(hb, T(th), T(th))
+    assert isinstance(hb.target.error, RuntimeError)
+    with pytest.raises(A.AhmcError, match="NUTS"):
+        A.transition(A.PhiloxRNG(0), h, A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn())),
+                     A.phasepoint(h, T(np.ones((D, N))), T(np.ones((D, N)))))
