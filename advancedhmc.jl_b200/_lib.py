@@ -65,6 +65,12 @@ PROTOTYPES = {
     "ahmc_nuts_transition_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp,
                                            C.c_int32, C.c_double, C.POINTER(Rng), C.POINTER(PhasePoint),
                                            C.POINTER(PhasePoint), C.POINTER(Stats), C.c_uint32]),
+    "ahmc_hmc_sample_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp, C.c_int32,
+                                      C.c_int32, C.POINTER(Rng), C.POINTER(PhasePoint), C.POINTER(PhasePoint), _vp,
+                                      C.POINTER(Stats), C.c_uint32]),
+    "ahmc_nuts_sample_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp, C.c_int32,
+                                       C.c_double, C.c_int32, C.POINTER(Rng), C.POINTER(PhasePoint),
+                                       C.POINTER(PhasePoint), _vp, C.POINTER(Stats), C.c_uint32]),
     "ahmc_adapt_summary_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
 }
 

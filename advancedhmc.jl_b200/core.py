@@ -663,13 +663,14 @@ class Transition:
     stat: dict
 
 
-def _stats_buffers(like, N, nuts):
-    s = dict(n_steps=_like(like, (N,), np.int32), is_accept=_like(like, (N,), np.uint8),
-             acceptance_rate=_like(like, (N,)), log_density=_like(like, (N,)), hamiltonian_energy=_like(like, (N,)),
-             hamiltonian_energy_error=_like(like, (N,)), numerical_error=_like(like, (N,), np.uint8))
+def _stats_buffers(like, N, nuts, T=None):
+    shp = (N,) if T is None else (T, N)
+    s = dict(n_steps=_like(like, shp, np.int32), is_accept=_like(like, shp, np.uint8),
+             acceptance_rate=_like(like, shp), log_density=_like(like, shp), hamiltonian_energy=_like(like, shp),
+             hamiltonian_energy_error=_like(like, shp), numerical_error=_like(like, shp, np.uint8))
     if nuts:
-        s["max_hamiltonian_energy_error"] = _like(like, (N,))
-        s["tree_depth"] = _like(like, (N,), np.int32)
+        s["max_hamiltonian_energy_error"] = _like(like, shp)
+        s["tree_depth"] = _like(like, shp, np.int32)
     c = L.Stats(_ptr(s["n_steps"]), _ptr(s["is_accept"]), _ptr(s["acceptance_rate"]), _ptr(s["log_density"]),
                 _ptr(s["hamiltonian_energy"]), _ptr(s["hamiltonian_energy_error"]),
                 _ptr(s.get("max_hamiltonian_energy_error")), _ptr(s.get("tree_depth")), _ptr(s["numerical_error"]))
@@ -710,6 +711,42 @@ def transition(rng, h: Hamiltonian, kappa: Union[HMCKernel, Trajectory], z: Phas
                                                   C.byref(rc), C.byref(zc), C.byref(oc), C.byref(sc), fl))
     st.update(stat(lf))
     return Transition(out, st)
+
+
+def sample_transitions(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: PhasePoint, n_transitions: int,
+                       keep_draws: bool = True, flags: int = 0):
+    """`n_transitions` consecutive transitions per chain in ONE kernel launch -- the un-adapted body of
+    `sample` (src/sampler.jl:182-228): returns (z_last, draws (T, N, D) or None, stats dict of (T, N) arrays).
+    Chains advance at their own pace inside the launch (no barrier between transitions)."""
+    if not isinstance(rng, PhiloxRNG):
+        raise L.InvalidArgument(L.ERR_INVALID, "multi-transition sampling draws from the on-device Philox streams")
+    tau = kappa.tau
+    ctx = get_context(_device_of(z.theta))
+    N, D = z._nd()
+    host = _is_host(z.theta)
+    out = _empty_pp(z.theta, with_lk_gradient=False)
+    md, keep = h.metric._desc(D, N, z.theta)
+    lf = tau.integrator
+    e, ep, keep2 = _eps_args(step_size(lf), z.theta, N)
+    rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0)
+    rng.offset += n_transitions
+    tc = tau.termination_criterion
+    nuts = isinstance(tc, GeneralisedNoUTurn)
+    st, sc = _stats_buffers(z.theta, N, nuts, T=n_transitions)
+    draws = _like(z.theta, (n_transitions, N, D)) if keep_draws else None
+    fl = flags | (L.FLAG_HOST_BUFFERS if host else 0)
+    _sync_torch(z.theta)
+    zc, oc = z._c(False), out._c(False)
+    if nuts:
+        ctx.check(ctx.lib.ahmc_nuts_sample_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, e, ep, tc.max_depth,
+                                               tc.delta_max, n_transitions, C.byref(rc), C.byref(zc), C.byref(oc),
+                                               _ptr(draws), C.byref(sc), fl))
+    else:
+        ctx.check(ctx.lib.ahmc_hmc_sample_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, e, ep, nsteps(tau),
+                                              n_transitions, C.byref(rc), C.byref(zc), C.byref(oc), _ptr(draws),
+                                              C.byref(sc), fl))
+    st.update(stat(lf))
+    return out, draws, st
 
 
 # ------------------------------------------------------------------------------------------------

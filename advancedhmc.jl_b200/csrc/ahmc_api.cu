@@ -770,11 +770,16 @@ static int stage_rng(Stager& st, const ahmc_rng* r, int32_t D, int64_t N, bool n
     return AHMC_OK;
 }
 
-int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
-                            double eps, const double* eps_chain, int32_t n_steps, const ahmc_rng* rng,
-                            const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, const ahmc_stats* stats,
-                            uint32_t flags) {
+static int hmc_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                    double eps, const double* eps_chain, int32_t n_steps, int32_t n_transitions, const ahmc_rng* rng,
+                    const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, double* draws, const ahmc_stats* stats,
+                    uint32_t flags) {
     if (!ctx || !model || !metric || !rng) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric/rng");
+    if (n_transitions < 1) return fail(ctx, AHMC_ERR_INVALID, "n_transitions must be >= 1");
+    if (n_transitions > 1 && (rng->normal_tape || rng->exp_tape))
+        return fail(ctx, AHMC_ERR_INVALID, "random tapes describe ONE transition; multi-transition sampling uses the Philox streams");
+    if (n_transitions > 1 && model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "multi-transition sampling needs a device-resident target");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
@@ -794,7 +799,8 @@ int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_m
     st.reserve(cin * 8 * 3);
     st.reserve(cout * 8 * 3);
     st.reserve((size_t)D * N * 8);
-    st.reserve((size_t)N * 8 * 16);
+    st.reserve((size_t)N * 8 * 16 * n_transitions);
+    if (draws) st.reserve((size_t)D * N * n_transitions * 8);
     if ((rc = st.prepare())) return rc;
     HmcArgs h{};
     LeapfrogArgs& a = h.lf;
@@ -821,7 +827,9 @@ int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_m
     a.dr_out = nullptr;
     a.flags = flags;
     if ((rc = stage_rng(st, rng, D, N, false, &h.rng))) return rc;
-    if ((rc = stage_stats(st, stats, N, &h.st))) return rc;
+    if ((rc = stage_stats(st, stats, N * n_transitions, &h.st))) return rc;
+    if ((rc = st.out(draws, (size_t)D * N * n_transitions, &h.draws))) return rc;
+    h.n_transitions = n_transitions;
     h.refresh = (flags & AHMC_FLAG_NO_REFRESH) ? 0 : 1;
     int nl = 0;
     if (model->kind == AHMC_MODEL_CALLBACK) {
@@ -869,11 +877,14 @@ int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_m
     return finish_call(ctx, st, flags);
 }
 
-int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
-                             double eps, const double* eps_chain, int32_t max_depth, double delta_max,
-                             const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
-                             const ahmc_stats* stats, uint32_t flags) {
+static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                     double eps, const double* eps_chain, int32_t max_depth, double delta_max, int32_t n_transitions,
+                     const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, double* draws,
+                     const ahmc_stats* stats, uint32_t flags) {
     if (!ctx || !model || !metric || !rng) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric/rng");
+    if (n_transitions < 1) return fail(ctx, AHMC_ERR_INVALID, "n_transitions must be >= 1");
+    if (n_transitions > 1 && (rng->normal_tape || rng->exp_tape || rng->dir_tape))
+        return fail(ctx, AHMC_ERR_INVALID, "random tapes describe ONE transition; multi-transition sampling uses the Philox streams");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
@@ -895,7 +906,8 @@ int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_
     st.reserve(cin * 8 * 3);
     st.reserve(cout * 8 * 3);
     st.reserve((size_t)D * N * 8);
-    st.reserve((size_t)N * 8 * 16);
+    st.reserve((size_t)N * 8 * 16 * n_transitions);
+    if (draws) st.reserve((size_t)D * N * n_transitions * 8);
     if (rng->exp_tape) st.reserve((size_t)rng->exp_stride * N * 8);
     if (rng->dir_tape) st.reserve((size_t)rng->dir_stride * N);
     if ((rc = st.prepare())) return rc;
@@ -922,7 +934,9 @@ int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_
     if ((rc = st.out(z_out->lk_value, (size_t)N, &a.lk_out))) return rc;
     a.dr_out = nullptr;
     if ((rc = stage_rng(st, rng, D, N, true, &a.rng))) return rc;
-    if ((rc = stage_stats(st, stats, N, &a.st))) return rc;
+    if ((rc = stage_stats(st, stats, N * n_transitions, &a.st))) return rc;
+    if ((rc = st.out(draws, (size_t)D * N * n_transitions, &a.draws))) return rc;
+    a.n_transitions = n_transitions;
     // per-chain tree workspace
     a.scratch_stride = nuts_scratch_doubles_per_chain(D, max_depth);
     size_t need = (size_t)a.scratch_stride * (size_t)N * sizeof(double);
@@ -940,6 +954,36 @@ int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_
     CU(launch_nuts(a, ctx->stream, &nl));
     ctx->launches += nl;
     return finish_call(ctx, st, flags);
+}
+
+int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                            double eps, const double* eps_chain, int32_t n_steps, const ahmc_rng* rng,
+                            const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, const ahmc_stats* stats,
+                            uint32_t flags) {
+    return hmc_impl(ctx, model, metric, D, N, eps, eps_chain, n_steps, 1, rng, z_in, z_out, nullptr, stats, flags);
+}
+
+int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                             double eps, const double* eps_chain, int32_t max_depth, double delta_max,
+                             const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
+                             const ahmc_stats* stats, uint32_t flags) {
+    return nuts_impl(ctx, model, metric, D, N, eps, eps_chain, max_depth, delta_max, 1, rng, z_in, z_out, nullptr, stats,
+                     flags);
+}
+
+int ahmc_hmc_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                        double eps, const double* eps_chain, int32_t n_steps, int32_t n_transitions, const ahmc_rng* rng,
+                        const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, double* draws,
+                        const ahmc_stats* stats, uint32_t flags) {
+    return hmc_impl(ctx, model, metric, D, N, eps, eps_chain, n_steps, n_transitions, rng, z_in, z_out, draws, stats, flags);
+}
+
+int ahmc_nuts_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                         double eps, const double* eps_chain, int32_t max_depth, double delta_max, int32_t n_transitions,
+                         const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, double* draws,
+                         const ahmc_stats* stats, uint32_t flags) {
+    return nuts_impl(ctx, model, metric, D, N, eps, eps_chain, max_depth, delta_max, n_transitions, rng, z_in, z_out,
+                     draws, stats, flags);
 }
 
 // ---------------------------------------------------------------------------------------------- adaptor stats

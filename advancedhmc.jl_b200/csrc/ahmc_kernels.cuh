@@ -68,8 +68,10 @@ struct RngDev {
 struct HmcArgs {
     LeapfrogArgs lf;  // th_in/r_in/g_in/lp_in = current phase point; outputs = new phase point
     RngDev rng;
-    StatsDev st;
-    int refresh;  // 1: draw new momentum
+    StatsDev st;          // arrays of n_transitions x N entries (transition-major)
+    int refresh;          // 1: draw new momentum
+    int n_transitions;    // >= 1: persistent sampling loop inside the kernel (sampler.jl:182 `for i in 1:n_samples`)
+    double* draws;        // nullable: n_transitions x (D x N) positions, draw t of chain c at (t*N + c)*D
 };
 
 struct NutsArgs {
@@ -87,7 +89,9 @@ struct NutsArgs {
     long long ld_in;
     double *th_out, *r_out, *g_out, *lp_out, *lk_out, *dr_out;
     long long ld_out;
-    StatsDev st;
+    StatsDev st;              // arrays of n_transitions x N entries
+    int n_transitions;
+    double* draws;            // nullable: n_transitions x (D x N)
     double* scratch;          // per-chain tree workspace (see ahmc_nuts.cu)
     long long scratch_stride; // doubles per chain
 };

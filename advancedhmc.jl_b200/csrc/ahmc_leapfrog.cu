@@ -96,16 +96,17 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC
 template <int METRIC, int G, int E>
 struct HmcIO {
     const HmcArgs& h;
-    const MetricOps<METRIC, G, E>& me;
     long long chain;
     int l;
+    const double* src_th;  // start point of THIS transition (z_in for the first, z_out afterwards)
+    const double* src_g;
+    long long stat_idx;    // t*N + chain
     double H0, lp0, lk0, ex;
     double r0[E];
 
     __device__ __forceinline__ void init(double (&th)[E], double (&r)[E], double (&g)[E]) const {
-        const LeapfrogArgs& a = h.lf;
-        vload_nc<G, E>(th, a.th_in + a.ld_in * chain, l, a.D);
-        vload_nc<G, E>(g, a.g_in + a.ld_in * chain, l, a.D);
+        vload_nc<G, E>(th, src_th, l, h.lf.D);
+        vload_nc<G, E>(g, src_g, l, h.lf.D);
 #pragma unroll
         for (int e = 0; e < E; ++e) r[e] = r0[e];
     }
@@ -120,6 +121,7 @@ struct HmcIO {
         double* tho = a.th_out + a.ld_out * chain;
         double* ro = a.r_out + a.ld_out * chain;
         double* go = a.g_out + a.ld_out * chain;
+        double* dro = h.draws ? h.draws + stat_idx * a.D : nullptr;
         double lpn, lkn;
         if (accept) {
             double nr[E];
@@ -128,17 +130,19 @@ struct HmcIO {
             vstore<G, E>(tho, th, l, a.D);
             vstore<G, E>(ro, nr, l, a.D);
             vstore<G, E>(go, g, l, a.D);
+            if (dro) vstore<G, E>(dro, th, l, a.D);
             lpn = lp;
             lkn = lk;
         } else {  // revert (trajectory.jl:312-332)
             double t0[E], g0[E], nr[E];
-            vload_nc<G, E>(t0, a.th_in + a.ld_in * chain, l, a.D);
-            vload_nc<G, E>(g0, a.g_in + a.ld_in * chain, l, a.D);
+            vload_nc<G, E>(t0, src_th, l, a.D);
+            vload_nc<G, E>(g0, src_g, l, a.D);
 #pragma unroll
             for (int e = 0; e < E; ++e) nr[e] = -r0[e];
             vstore<G, E>(tho, t0, l, a.D);
             vstore<G, E>(ro, nr, l, a.D);
             vstore<G, E>(go, g0, l, a.D);
+            if (dro) vstore<G, E>(dro, t0, l, a.D);
             lpn = lp0;
             lkn = lk0;
         }
@@ -149,18 +153,20 @@ struct HmcIO {
             if (a.status) a.status[chain] = fin ? 0u : AHMC_STATUS_NONFINITE;
             if (a.steps_done) a.steps_done[chain] = steps;
             const StatsDev& st = h.st;
-            if (st.n_steps) st.n_steps[chain] = a.n_steps;  // nsteps(tau), nominal (trajectory.jl:288)
-            if (st.is_accept) st.is_accept[chain] = accept ? 1 : 0;
-            if (st.acceptance_rate) st.acceptance_rate[chain] = alpha;
-            if (st.log_density) st.log_density[chain] = lpn;
-            if (st.hamiltonian_energy) st.hamiltonian_energy[chain] = H;
-            if (st.hamiltonian_energy_error) st.hamiltonian_energy_error[chain] = H - H0;
-            if (st.numerical_error) st.numerical_error[chain] = finite_d(H1) ? 0 : 1;
+            if (st.n_steps) st.n_steps[stat_idx] = a.n_steps;  // nsteps(tau), nominal (trajectory.jl:288)
+            if (st.is_accept) st.is_accept[stat_idx] = accept ? 1 : 0;
+            if (st.acceptance_rate) st.acceptance_rate[stat_idx] = alpha;
+            if (st.log_density) st.log_density[stat_idx] = lpn;
+            if (st.hamiltonian_energy) st.hamiltonian_energy[stat_idx] = H;
+            if (st.hamiltonian_energy_error) st.hamiltonian_energy_error[stat_idx] = H - H0;
+            if (st.numerical_error) st.numerical_error[stat_idx] = finite_d(H1) ? 0 : 1;
         }
         (void)dr;
     }
 };
 
+// One launch = n_transitions static-HMC transitions per chain (the reference's `for i in 1:n_samples` loop,
+// sampler.jl:182, without adaptation): state is re-read from the output phase point, which stays L2-resident.
 template <int MODEL, int METRIC, int G, int E>
 __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC, E>()) hmc_kernel(const HmcArgs h) {
     extern __shared__ double smem[];
@@ -172,35 +178,43 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC
     const long long chain = valid ? chain0 : a.N - 1;
     const int D = a.D;
     double* xs = smem + (size_t)grp_in_block * D;
-    double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
+    const double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
 
     MetricOps<METRIC, G, E> me;
     me.load(a.metric, chain, l, D);
-    HmcIO<METRIC, G, E> io{h, me, chain, l};
-    // refresh (hamiltonian.jl:213-220): new momentum, kinetic energy; lp is the cached value (quirk Q2:
-    // the reference recomputes it from theta -- same number)
-    if (h.refresh) {
-        if (h.rng.normal_tape) {
-            vload_nc<G, E>(io.r0, h.rng.normal_tape + (long long)D * chain, l, D);
-        } else {
+    HmcIO<METRIC, G, E> io{h, chain, l};
+    for (int t = 0; t < h.n_transitions; ++t) {
+        const bool first = (t == 0);
+        io.src_th = first ? a.th_in + a.ld_in * chain : a.th_out + a.ld_out * chain;
+        io.src_g = first ? a.g_in + a.ld_in * chain : a.g_out + a.ld_out * chain;
+        io.stat_idx = (long long)t * a.N + chain;
+        const uint64_t off = h.rng.offset + (uint64_t)t;
+        // refresh (hamiltonian.jl:213-220): new momentum, kinetic energy; lp is the cached value (quirk Q2:
+        // the reference recomputes it from theta -- same number)
+        if (h.refresh) {
+            if (h.rng.normal_tape) {
+                vload_nc<G, E>(io.r0, h.rng.normal_tape + (long long)D * chain, l, D);
+            } else {
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                int d = l + G * e;
-                io.r0[e] = (d < D) ? philox_normal(h.rng.seed, h.rng.offset, chain, d) : 0.0;
+                for (int e = 0; e < E; ++e) {
+                    int d = l + G * e;
+                    io.r0[e] = (d < D) ? philox_normal(h.rng.seed, off, chain, d) : 0.0;
+                }
             }
+            me.rand_momentum(io.r0, l);
+        } else {
+            vload_nc<G, E>(io.r0, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
         }
-        me.rand_momentum(io.r0, l);
-    } else {
-        vload_nc<G, E>(io.r0, a.r_in + a.ld_in * chain, l, D);
+        {
+            double dr0[E];
+            io.lk0 = map_nonfinite(kinetic<METRIC, G, E>(me, io.r0, dr0, xs, l));
+        }
+        io.lp0 = map_nonfinite(first ? a.lp_in[chain] : a.lp_out[chain]);
+        io.H0 = -(io.lp0 + io.lk0);
+        io.ex = h.rng.exp_tape ? h.rng.exp_tape[chain] : philox_exp(h.rng.seed, off, chain, 0);
+        run_trajectory<MODEL, METRIC, G, E>(a.model, a.metric, D, chain, valid, l, xs, eps, a.n_steps, 0.0, a.flags, io);
+        __syncwarp();
     }
-    {
-        double dr0[E];
-        io.lk0 = map_nonfinite(kinetic<METRIC, G, E>(me, io.r0, dr0, xs, l));
-    }
-    io.lp0 = map_nonfinite(a.lp_in[chain]);
-    io.H0 = -(io.lp0 + io.lk0);
-    io.ex = h.rng.exp_tape ? h.rng.exp_tape[chain] : philox_exp(h.rng.seed, h.rng.offset, chain, 0);
-    run_trajectory<MODEL, METRIC, G, E>(a.model, a.metric, D, chain, valid, l, xs, eps, a.n_steps, 0.0, a.flags, io);
 }
 
 // ---------------------------------------------------------------------------------------------

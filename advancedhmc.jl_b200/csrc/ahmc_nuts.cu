@@ -84,64 +84,125 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     me.load(a.metric, chain, l, D);
 
     int nexp = 0, ndir = 0;
+    uint64_t off = a.rng.offset;  // Philox transition counter of the transition this group is working on
     auto next_exp = [&]() -> double {
         int k = nexp++;
         if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
-        return philox_exp(a.rng.seed, a.rng.offset, chain, k);
+        return philox_exp(a.rng.seed, off, chain, k);
     };
     auto next_dir = [&]() -> bool {
         int k = ndir++;
         if (a.rng.dir_tape && k < a.rng.dir_stride) return a.rng.dir_tape[chain * a.rng.dir_stride + k] != 0;
-        return philox_bit(a.rng.seed, a.rng.offset, chain, k);
+        return philox_bit(a.rng.seed, off, chain, k);
     };
 
-    // ---- z0: refresh (sampler.jl:55; hamiltonian.jl:213-220), cached lp / gradient
+    // ---- per-transition state (a launch runs n_transitions transitions per chain: the reference's
+    //      `for i in 1:n_samples` loop, sampler.jl:182, each chain advancing at its own pace)
     ChainState<E> s;
     double dr[E];
-    vload_nc<G, E>(s.th, a.th_in + a.ld_in * chain, l, D);
-    vload_nc<G, E>(s.g, a.g_in + a.ld_in * chain, l, D);
-    if (a.refresh) {
-        if (a.rng.normal_tape) {
-            vload_nc<G, E>(s.r, a.rng.normal_tape + (long long)D * chain, l, D);
-        } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                int d = l + G * e;
-                s.r[e] = (d < D) ? philox_normal(a.rng.seed, a.rng.offset, chain, d) : 0.0;
-            }
-        }
-        me.rand_momentum(s.r, l);
-    } else {
-        vload_nc<G, E>(s.r, a.r_in + a.ld_in * chain, l, D);
-    }
-    s.lp = map_nonfinite(a.lp_in[chain]);
-    s.lk = map_nonfinite(kinetic<METRIC, G, E>(me, s.r, dr, xs, l));
-    const double H0 = -(s.lp + s.lk);  // energy(z0) (:682)
-
-    // tree = BinaryTree(z0, z0, rho = z0.r, 0, 0, 0); sampler = MultinomialTS(z0, lw = 0) (:683-688, :155)
-    double zc_lp = s.lp, zc_lk = s.lk;
-    if (valid) {
-        vstore<G, E>(LEFT, s.th, l, D);
-        vstore<G, E>(LEFT + D, s.r, l, D);
-        vstore<G, E>(LEFT + 2 * (long long)D, s.g, l, D);
-        vstore<G, E>(RIGHT, s.th, l, D);
-        vstore<G, E>(RIGHT + D, s.r, l, D);
-        vstore<G, E>(RIGHT + 2 * (long long)D, s.g, l, D);
-        vstore<G, E>(RHO, s.r, l, D);
-        vstore<G, E>(a.th_out + a.ld_out * chain, s.th, l, D);
-        vstore<G, E>(a.r_out + a.ld_out * chain, s.r, l, D);
-        vstore<G, E>(a.g_out + a.ld_out * chain, s.g, l, D);
-    }
+    double H0 = 0.0, zc_lp = 0.0, zc_lk = 0.0;
     double lw_tree = 0.0, sa_tree = 0.0, dh_tree = 0.0;
     int na_tree = 0, j = 0;
     bool term_dyn = false, term_num = false;
-    bool done = !valid || !(j < a.max_depth);
-    bool in_sub = false;
+    bool done = true, in_sub = false;
     int i = 0, jsub = 0, v = 1;
+    int t = 0;
+    bool finished = !valid;
+    bool need_init = valid;
 
     while (true) {
+        // ---------------------------------------------------------------- (I) begin a transition:
+        // z0 = refresh (sampler.jl:55; hamiltonian.jl:213-220) with the cached lp / gradient;
+        // tree = BinaryTree(z0, z0, rho = z0.r, 0, 0, 0); sampler = MultinomialTS(z0, lw = 0) (:682-688, :155)
+        if (__any_sync(FULL, need_init)) {
+            const bool first = (t == 0);
+            double rn[E], drn[E];
+            if (need_init) {
+                off = a.rng.offset + (uint64_t)t;
+                nexp = 0;
+                ndir = 0;
+                vload_nc<G, E>(s.th, first ? a.th_in + a.ld_in * chain : a.th_out + a.ld_out * chain, l, D);
+                vload_nc<G, E>(s.g, first ? a.g_in + a.ld_in * chain : a.g_out + a.ld_out * chain, l, D);
+            }
+            if (a.refresh) {
+                if (a.rng.normal_tape) {
+                    vload_nc<G, E>(rn, a.rng.normal_tape + (long long)D * chain, l, D);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        int d = l + G * e;
+                        rn[e] = (d < D) ? philox_normal(a.rng.seed, off, chain, d) : 0.0;
+                    }
+                }
+                me.rand_momentum(rn, l);
+            } else {
+                vload_nc<G, E>(rn, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
+            }
+            const double lk0 = map_nonfinite(kinetic<METRIC, G, E>(me, rn, drn, xs, l));
+            if (need_init) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) s.r[e] = rn[e];
+                s.lp = first ? map_nonfinite(a.lp_in[chain]) : zc_lp;
+                s.lk = lk0;
+                H0 = -(s.lp + s.lk);  // energy(z0) (:682)
+                zc_lp = s.lp;
+                zc_lk = s.lk;
+                vstore<G, E>(LEFT, s.th, l, D);
+                vstore<G, E>(LEFT + D, s.r, l, D);
+                vstore<G, E>(LEFT + 2 * (long long)D, s.g, l, D);
+                vstore<G, E>(RIGHT, s.th, l, D);
+                vstore<G, E>(RIGHT + D, s.r, l, D);
+                vstore<G, E>(RIGHT + 2 * (long long)D, s.g, l, D);
+                vstore<G, E>(RHO, s.r, l, D);
+                vstore<G, E>(a.th_out + a.ld_out * chain, s.th, l, D);
+                vstore<G, E>(a.r_out + a.ld_out * chain, s.r, l, D);
+                vstore<G, E>(a.g_out + a.ld_out * chain, s.g, l, D);
+                lw_tree = 0.0;
+                sa_tree = 0.0;
+                dh_tree = 0.0;
+                na_tree = 0;
+                j = 0;
+                term_dyn = false;
+                term_num = false;
+                done = !(j < a.max_depth);
+                in_sub = false;
+                need_init = false;
+            }
+        }
+        // ---------------------------------------------------------------- (F) finish a transition: stats (:725-739), draw
+        {
+            const bool fin_now = !finished && done && !in_sub;
+            if (fin_now) {
+                const long long si = (long long)t * a.N + chain;
+                if (a.draws) {
+                    double tt[E];
+                    vload_nc<G, E>(tt, a.th_out + a.ld_out * chain, l, D);
+                    vstore<G, E>(a.draws + si * D, tt, l, D);
+                }
+                if (l == 0) {
+                    const double H = -(zc_lp + zc_lk);
+                    a.lp_out[chain] = zc_lp;
+                    a.lk_out[chain] = zc_lk;
+                    const StatsDev& st = a.st;
+                    if (st.n_steps) st.n_steps[si] = na_tree;
+                    if (st.is_accept) st.is_accept[si] = 1;
+                    if (st.acceptance_rate) st.acceptance_rate[si] = sa_tree / (double)na_tree;
+                    if (st.log_density) st.log_density[si] = zc_lp;
+                    if (st.hamiltonian_energy) st.hamiltonian_energy[si] = H;
+                    if (st.hamiltonian_energy_error) st.hamiltonian_energy_error[si] = H - H0;
+                    if (st.max_hamiltonian_energy_error) st.max_hamiltonian_energy_error[si] = dh_tree;
+                    if (st.tree_depth) st.tree_depth[si] = j;
+                    if (st.numerical_error) st.numerical_error[si] = term_num ? 1 : 0;
+                }
+                ++t;
+                if (t < a.n_transitions) need_init = true;
+                else finished = true;
+            }
+        }
+        if (__any_sync(FULL, need_init)) continue;
+
         // ---------------------------------------------------------------- (A) start a doubling (:691-706)
-        const bool start = !done && !in_sub;
+        const bool start = !finished && !done && !in_sub;
         if (__any_sync(FULL, start)) {
             if (start) {
                 const bool vleft = next_dir();  // rand(rng, Bool) (:693)
@@ -342,22 +403,6 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         if (in_sub) ++i;
     }
 
-    // ---------------------------------------------------------------- stats (:725-739)
-    if (valid && l == 0) {
-        const double H = -(zc_lp + zc_lk);
-        a.lp_out[chain] = zc_lp;
-        a.lk_out[chain] = zc_lk;
-        const StatsDev& st = a.st;
-        if (st.n_steps) st.n_steps[chain] = na_tree;
-        if (st.is_accept) st.is_accept[chain] = 1;
-        if (st.acceptance_rate) st.acceptance_rate[chain] = sa_tree / (double)na_tree;
-        if (st.log_density) st.log_density[chain] = zc_lp;
-        if (st.hamiltonian_energy) st.hamiltonian_energy[chain] = H;
-        if (st.hamiltonian_energy_error) st.hamiltonian_energy_error[chain] = H - H0;
-        if (st.max_hamiltonian_energy_error) st.max_hamiltonian_energy_error[chain] = dh_tree;
-        if (st.tree_depth) st.tree_depth[chain] = j;
-        if (st.numerical_error) st.numerical_error[chain] = term_num ? 1 : 0;
-    }
 }
 
 template <int MODEL, int METRIC, int G, int E>

@@ -173,6 +173,21 @@ int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_
                              const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
                              const ahmc_stats* stats, uint32_t flags);
 
+/* n_transitions transitions per chain in ONE launch: the body of `sample(rng, h, kappa, theta, n_samples)` without
+ * adaptation (`for i in 1:n_samples; t = transition(rng, h, kappa, t.z); thetas[i] = t.z.theta`, src/sampler.jl:182-228).
+ * Each chain advances at its own pace (no cross-chain barrier between transitions: divergent NUTS tree sizes do
+ * not idle the other chains).  Randomness: Philox streams (seed, offset + i); tapes are rejected for n_transitions > 1.
+ *   draws  : nullable, n_transitions x (D x N) doubles -- draw i of chain c at ((i*N + c)*D)
+ *   stats  : arrays of n_transitions x N entries (entry i*N + c); z_out = phase point after the last transition. */
+int ahmc_hmc_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                        double eps, const double* eps_chain, int32_t n_steps, int32_t n_transitions, const ahmc_rng* rng,
+                        const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, double* draws,
+                        const ahmc_stats* stats, uint32_t flags);
+int ahmc_nuts_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                         double eps, const double* eps_chain, int32_t max_depth, double delta_max, int32_t n_transitions,
+                         const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, double* draws,
+                         const ahmc_stats* stats, uint32_t flags);
+
 /* ---- adaptor statistics (src/adaptation) ------------------------------------------------------ */
 /* Pooled summary of one iteration over this GPU's N chains, written to a small device/host record that
  * the host all-gathers across ranks (one NCCL all-gather) and merges in rank order:

@@ -32,3 +32,18 @@ with torch.cuda.stream(stream):
         ms = e0.elapsed_time(e1) / reps
         print(json.dumps(dict(lib=os.environ.get("AHMC_B200_LIB", "default"), eps=eps, ms_per_transition=ms,
                               mean_steps=steps / reps / 4096, rate=steps * 128 / (e0.elapsed_time(e1) * 1e-3))))
+    # persistent launch: T transitions per launch, chains free-running
+    for eps in (0.1, 0.4):
+        kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(eps), A.GeneralisedNoUTurn()))
+        rng = A.PhiloxRNG(1)
+        T = 20
+        zl, _, st = A.sample_transitions(rng, h, kern, z0, T, keep_draws=False, flags=A.FLAG_ASYNC)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        zl, _, st = A.sample_transitions(rng, h, kern, zl, T, keep_draws=False, flags=A.FLAG_ASYNC)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        steps = int(st["n_steps"].sum().item())
+        print(json.dumps(dict(mode="persistent", eps=eps, ms_per_transition=e0.elapsed_time(e1) / T, mean_steps=steps / T / 4096,
+                              rate=steps * 128 / (e0.elapsed_time(e1) * 1e-3))))

@@ -542,3 +542,36 @@ def test_callback_nonfinite_freeze_and_error_propagation():
     with pytest.raises(A.AhmcError, match="NUTS"):
         A.transition(A.PhiloxRNG(0), h, A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn())),
                      A.phasepoint(h, T(np.ones((D, N))), T(np.ones((D, N)))))
+
+
+# ------------------------------------------------------------------------------------------------ persistent sampling
+@pytest.mark.parametrize("kind", ["hmc", "nuts"])
+@pytest.mark.parametrize("D", [5, 128])
+def test_multi_transition_launch_equals_sequential_transitions(kind, D):
+    """One launch of T transitions (chains free-running) == T single-transition launches with the same Philox
+    counters: the persistent loop changes scheduling, not results (sampler.jl:182-228)."""
+    N, T = 300, 6
+    rng0 = np.random.default_rng(D)
+    s = np.exp(rng0.uniform(-0.5, 0.5, D))
+    h = A.Hamiltonian(A.DiagEuclideanMetric(s * s), A.DiagGaussian(rng0.normal(size=D), s))
+    th = torch.as_tensor(rng0.normal(size=(N, D)), device=DEV)
+    z0 = A.phasepoint(h, th, torch.zeros_like(th))
+    if kind == "hmc":
+        kern = A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.5), A.FixedNSteps(7)))
+    else:
+        kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.35), A.GeneralisedNoUTurn(6, 1000.0)))
+    zl, draws, st = A.sample_transitions(A.PhiloxRNG(99), h, kern, z0, T)
+    rng = A.PhiloxRNG(99)
+    z = z0
+    for t in range(T):
+        tr = A.transition(rng, h, kern, z)
+        z = tr.z
+        assert torch.equal(draws[t], z.theta), t
+        for k in ("n_steps", "acceptance_rate", "hamiltonian_energy_error", "is_accept", "numerical_error"):
+            assert torch.equal(st[k][t], tr.stat[k]), (k, t)
+        if kind == "nuts":
+            assert torch.equal(st["tree_depth"][t], tr.stat["tree_depth"])
+    assert torch.equal(zl.theta, z.theta) and torch.equal(zl.r, z.r) and torch.equal(zl.lp.value, z.lp.value)
+    assert torch.equal(zl.lp.gradient, z.lp.gradient) and torch.equal(zl.lk.value, z.lk.value)
+    if kind == "nuts":
+        assert len(set(st["tree_depth"].flatten().tolist())) > 1
