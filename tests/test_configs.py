@@ -1,0 +1,98 @@
+"""GPU end-to-end checks of the five BASELINE.json configurations at reduced chain counts: the sampling loop
+(src/sampler.jl:159-248 mirror) with pooled adaptation on top of the fused transition kernels recovers the
+targets' moments.  (Trajectory-level parity with the oracle is in test_gpu_parity.py.)"""
+import numpy as np
+import pytest
+import torch
+
+import ahmc_b200 as A
+from ahmc_b200 import adaptation as ad
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _corr_gauss(D, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    Q, _ = np.linalg.qr(rng.normal(size=(D, D)))
+    lam = np.exp(np.linspace(np.log(0.1), np.log(10.0), D))
+    return (Q * lam) @ Q.T, (Q / lam) @ Q.T
+
+
+def test_c1_static_hmc_unit_metric_d10_64_chains():
+    """StaticTrajectory(Leapfrog(0.1), 32) + UnitEuclideanMetric, D=10 std-Normal, 64 chains (test/sampler-vec.jl path).
+    Integration time 3.2 ~ pi makes this config nearly anti-periodic (theta' ~ -0.998 theta - 0.058 r): the lag-1
+    autocorrelation must be ~ cos(3.2) and the stationary variance 1 is reached only over ~250 transitions, so the
+    check runs 6000 transitions in one persistent launch."""
+    D, N, T = 10, 64, 6000
+    h = A.Hamiltonian(A.UnitEuclideanMetric(D), A.StdNormal(D))
+    kern = A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.1), A.FixedNSteps(32)))
+    th0 = torch.rand((N, D), dtype=torch.float64, device=DEV)
+    zl, draws, st = A.sample_transitions(A.PhiloxRNG(1), h, kern, A.phasepoint(h, th0, torch.zeros_like(th0)), T)
+    X = draws[1000:].cpu().numpy()  # (T', N, D)
+    assert st["acceptance_rate"].mean().item() > 0.99
+    lag1 = np.mean(X[1:] * X[:-1]) / np.mean(X * X)
+    assert abs(lag1 - np.cos(3.2)) < 0.01
+    assert np.abs(X.reshape(-1, D).mean(axis=0)).max() < 0.05
+    assert abs(X.var() - 1) < 0.25  # RNDATOL-style tolerance (test/common.jl:12)
+
+
+def test_c2_hmcda_diag_metric_correlated_gaussian():
+    """HMCDA(0.8, lambda=1) + DiagEuclideanMetric on a D=128 correlated Gaussian; shared eps from pooled dual averaging."""
+    D, N = 128, 256
+    Sigma, P = _corr_gauss(D, 7)
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.diag(Sigma).copy()), A.DenseGaussian(np.zeros(D), P))
+    kern = A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.05), A.FixedIntegrationTime(1.0)))
+    adaptor = ad.NaiveHMCAdaptor(ad.UnitMassMatrix(), ad.NesterovDualAveraging(0.8, 0.05))
+    th0 = torch.as_tensor(np.random.default_rng(0).normal(size=(N, D)), device=DEV)
+    res = ad.sample(A.PhiloxRNG(2), h, kern, th0, 150, adaptor, 100, keep_draws=True, drop_warmup=True)
+    acc = np.mean([s["acceptance_rate"] for s in res.stats[100:]])
+    assert 0.6 < acc < 0.95, acc          # dual averaging steers the pooled acceptance towards delta = 0.8
+    assert 0.02 < res.eps < 1.0
+    X = torch.stack(res.draws).reshape(-1, D).cpu().numpy()
+    assert np.abs(X.mean(axis=0)).max() < 0.35
+    ratio = X.var(axis=0) / np.diag(Sigma)
+    assert 0.7 < ratio.min() and ratio.max() < 1.35
+
+
+def test_c3_nuts_diag_metric_d128():
+    D, N = 128, 512
+    s = np.exp(np.linspace(np.log(0.1), np.log(10.0), D))
+    h = A.Hamiltonian(A.DiagEuclideanMetric(s * s), A.DiagGaussian(np.zeros(D), s))
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.25), A.GeneralisedNoUTurn()))
+    z = A.phasepoint(h, torch.zeros((N, D), dtype=torch.float64, device=DEV), torch.zeros((N, D), dtype=torch.float64, device=DEV))
+    zl, draws, st = A.sample_transitions(A.PhiloxRNG(3), h, kern, z, 30)
+    X = draws[10:].reshape(-1, D).cpu().numpy() / s
+    assert np.abs(X.mean(axis=0)).max() < 0.08 and np.abs(X.var(axis=0) - 1).max() < 0.12
+    assert st["acceptance_rate"].mean().item() > 0.8 and int(st["numerical_error"].sum().item()) == 0
+
+
+def test_c4_funnel_nuts_stan_adaptor_pooled():
+    """NUTS + StanHMCAdaptor on Neal's funnel (D=100 in BASELINE; D=20 here), pooled windows: v ~ N(0, 3^2)."""
+    D, N = 20, 1024
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.Funnel(D))
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
+    adaptor = ad.StanHMCAdaptor(ad.WelfordVar(D), ad.NesterovDualAveraging(0.8, 0.1))
+    th0 = torch.as_tensor(np.random.default_rng(1).normal(size=(N, D)) * 0.1, device=DEV)
+    res = ad.sample(A.PhiloxRNG(4), h, kern, th0, 260, adaptor, 200, keep_draws=True, drop_warmup=True)
+    v = torch.stack(res.draws)[:, :, 0].reshape(-1).cpu().numpy()
+    # the funnel's neck is famously under-sampled by NUTS; the bulk of v ~ N(0, 9) must be there
+    assert abs(np.median(v)) < 1.0 and 1.5 < v.std() < 3.6
+    assert res.Minv is not None and res.Minv.shape == (D,) and res.Minv[0] > 1.0  # adapted: var(v) >> var at init
+    assert 0.01 < res.eps < 2.0
+
+
+def test_c5_nuts_dense_metric_d256():
+    """NUTS + DenseEuclideanMetric (Minv = Sigma) on a D=256 correlated Gaussian: with the exact metric the
+    sampler sees an isotropic problem."""
+    D, N = 256, 64
+    Sigma, P = _corr_gauss(D, 11)
+    h = A.Hamiltonian(A.DenseEuclideanMetric(Sigma), A.DenseGaussian(np.zeros(D), P))
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.4), A.GeneralisedNoUTurn()))
+    z = A.phasepoint(h, torch.zeros((N, D), dtype=torch.float64, device=DEV), torch.zeros((N, D), dtype=torch.float64, device=DEV))
+    zl, draws, st = A.sample_transitions(A.PhiloxRNG(5), h, kern, z, 25)
+    X = draws[5:].reshape(-1, D).cpu().numpy()
+    L = np.linalg.cholesky(Sigma)
+    W = np.linalg.solve(L, X.T).T  # whitened draws ~ N(0, I)
+    assert np.abs(W.mean(axis=0)).max() < 0.2 and abs(W.var(axis=0).mean() - 1) < 0.05
+    assert st["acceptance_rate"][5:].mean().item() > 0.6 and st["tree_depth"].double().mean().item() < 5
