@@ -37,7 +37,8 @@ class Stats(C.Structure):
 
 class Rng(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64), ("normal_tape", _vp), ("exp_tape", _vp),
-                ("exp_stride", C.c_int64), ("dir_tape", _vp), ("dir_stride", C.c_int64)]
+                ("exp_stride", C.c_int64), ("dir_tape", _vp), ("dir_stride", C.c_int64),
+                ("partial_refresh_alpha", C.c_double)]
 
 
 LOGP_GRAD_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _vp, _vp, C.c_int32, C.c_int64, C.c_int64, _vp)

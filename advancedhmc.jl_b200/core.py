@@ -413,7 +413,7 @@ class PhiloxRNG:
         self.seed, self.offset = int(seed) & (2**64 - 1), 0
 
     def _c(self, advance=True):
-        r = L.Rng(self.seed, self.offset, None, None, 0, None, 0)
+        r = L.Rng(self.seed, self.offset, None, None, 0, None, 0, 0.0)
         if advance:
             self.offset += 1
         return r, ()
@@ -429,7 +429,7 @@ class TapeRNG:
     def _c(self, advance=True):
         es = 1 if (self.exp is None or self.exp.ndim == 1) else self.exp.shape[1]
         ds = 0 if self.dirs is None else self.dirs.shape[1]
-        return L.Rng(0, 0, _ptr(self.normal), _ptr(self.exp), es, _ptr(self.dirs), ds), (self.normal, self.exp, self.dirs)
+        return L.Rng(0, 0, _ptr(self.normal), _ptr(self.exp), es, _ptr(self.dirs), ds, 0.0), (self.normal, self.exp, self.dirs)
 
 
 def rand_momentum(rng, metric: AbstractMetric, kinetic, theta):
@@ -644,7 +644,19 @@ def nsteps(tau: Trajectory) -> int:
 
 
 class FullMomentumRefreshment:
-    pass
+    """src/hamiltonian.jl:210-220."""
+
+
+@dataclass(frozen=True)
+class PartialMomentumRefreshment:
+    """src/hamiltonian.jl:222-254: r' = alpha*r + sqrt(1 - alpha^2)*G."""
+
+    alpha: float
+
+
+def _refresh_alpha(kappa) -> float:
+    r = getattr(kappa, "refreshment", None)
+    return float(r.alpha) if isinstance(r, PartialMomentumRefreshment) else 0.0
 
 
 @dataclass(frozen=True)
@@ -692,6 +704,7 @@ def transition(rng, h: Hamiltonian, kappa: Union[HMCKernel, Trajectory], z: Phas
     lf = tau.integrator
     e, ep, keep2 = _eps_args(step_size(lf), z.theta, N)
     rc, keep3 = rng._c()
+    rc.partial_refresh_alpha = _refresh_alpha(kappa)
     tc = tau.termination_criterion
     nuts = isinstance(tc, GeneralisedNoUTurn)
     st, sc = _stats_buffers(z.theta, N, nuts)
@@ -713,6 +726,46 @@ def transition(rng, h: Hamiltonian, kappa: Union[HMCKernel, Trajectory], z: Phas
     return Transition(out, st)
 
 
+def find_good_stepsize(rng, h: Hamiltonian, theta, initial_step_size: float = 0.1, max_n_iters: int = 100) -> float:
+    """`find_good_stepsize(rng, h, theta)` (src/trajectory.jl:768-837): doubling / halving until the one-step
+    acceptance ratio crosses 1/2, then bisection until it lies in (1/4, 3/4].  Host-side control flow exactly
+    as the reference (it runs once); every probe `A(h, z, eps)` (:753-757) is one call of the fused `step` kernel.
+    `theta`: one chain, shape (D,) (the reference accepts a vector only)."""
+    if theta.ndim != 1:
+        raise L.InvalidArgument(L.ERR_INVALID, "find_good_stepsize takes a single chain (vector theta), like the reference")
+    th = theta.reshape(1, -1)
+    r = rand_momentum(rng, h.metric, h.kinetic, th)
+    z = phasepoint(h, th, r)
+    H = float(energy(z)[0])
+
+    def A_(eps):  # trajectory.jl:753-757
+        z1 = step(Leapfrog(eps), h, z, 1, with_lk_gradient=False)
+        return float(energy(z1)[0])
+
+    eps = eps_prime = float(initial_step_size)
+    log_a_min, log_a_cross, log_a_max = 2 * math.log(0.5), math.log(0.5), math.log(0.75)
+    dH = H - A_(eps)
+    ratio_too_high = dH > log_a_cross
+    for _ in range(max_n_iters):  # crossing step (:796-810)
+        eps_prime = 2.0 * eps if ratio_too_high else 0.5 * eps
+        dH = H - A_(eps)
+        if ratio_too_high != (dH > log_a_cross):
+            break
+        eps = eps_prime
+    eps, eps_prime = min(eps, eps_prime), max(eps, eps_prime)
+    for _ in range(max_n_iters):  # bisection (:822-834)
+        mid = 0.5 * (eps + eps_prime)
+        dH = H - A_(mid)
+        if dH > log_a_max:
+            eps = mid
+        elif dH < log_a_min:
+            eps_prime = mid
+        else:
+            eps = mid
+            break
+    return eps
+
+
 def sample_transitions(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: PhasePoint, n_transitions: int,
                        keep_draws: bool = True, flags: int = 0):
     """`n_transitions` consecutive transitions per chain in ONE kernel launch -- the un-adapted body of
@@ -728,7 +781,7 @@ def sample_transitions(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: Phas
     md, keep = h.metric._desc(D, N, z.theta)
     lf = tau.integrator
     e, ep, keep2 = _eps_args(step_size(lf), z.theta, N)
-    rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0)
+    rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0, _refresh_alpha(kappa))
     rng.offset += n_transitions
     tc = tau.termination_criterion
     nuts = isinstance(tc, GeneralisedNoUTurn)

@@ -761,6 +761,7 @@ static int stage_stats(Stager& st, const ahmc_stats* s, int64_t N, StatsDev* d) 
 static int stage_rng(Stager& st, const ahmc_rng* r, int32_t D, int64_t N, bool nuts, RngDev* d) {
     d->seed = r->seed;
     d->offset = r->offset;
+    d->partial_alpha = r->partial_refresh_alpha;
     d->exp_stride = nuts ? r->exp_stride : 1;
     d->dir_stride = r->dir_stride;
     int rc;
@@ -780,6 +781,10 @@ static int hmc_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* m
         return fail(ctx, AHMC_ERR_INVALID, "random tapes describe ONE transition; multi-transition sampling uses the Philox streams");
     if (n_transitions > 1 && model->kind == AHMC_MODEL_CALLBACK)
         return fail(ctx, AHMC_ERR_UNSUPPORTED, "multi-transition sampling needs a device-resident target");
+    if (rng->partial_refresh_alpha != 0.0 && model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "partial momentum refreshment is not wired into the split-step path");
+    if (!(rng->partial_refresh_alpha > -1.0 && rng->partial_refresh_alpha < 1.0))
+        return fail(ctx, AHMC_ERR_INVALID, "partial_refresh_alpha must be in (-1, 1)");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
@@ -885,6 +890,8 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     if (n_transitions < 1) return fail(ctx, AHMC_ERR_INVALID, "n_transitions must be >= 1");
     if (n_transitions > 1 && (rng->normal_tape || rng->exp_tape || rng->dir_tape))
         return fail(ctx, AHMC_ERR_INVALID, "random tapes describe ONE transition; multi-transition sampling uses the Philox streams");
+    if (!(rng->partial_refresh_alpha > -1.0 && rng->partial_refresh_alpha < 1.0))
+        return fail(ctx, AHMC_ERR_INVALID, "partial_refresh_alpha must be in (-1, 1)");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;

@@ -374,6 +374,25 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t offset, 
     sincospi(2.0 * u2, &s, &c);
     return (d & 1) ? rad * s : rad * c;
 }
+// D standard normals of (chain, transition) as a group-distributed vector: coordinates e = 2q and e = 2q+1 of a lane
+// share ONE Philox block and ONE Box-Muller evaluation (block index = lane + G*q), so a lane with E coordinates
+// spends ceil(E/2) blocks.  The stream is a pure function of (seed, offset, chain, D) -- the layout (G) follows from D.
+template <int G, int E>
+__device__ __forceinline__ void philox_normals(uint64_t seed, uint64_t offset, long long chain, int l, int D,
+                                               double (&z)[E]) {
+#pragma unroll
+    for (int q = 0; q < (E + 1) / 2; ++q) {
+        uint32_t o[4];
+        Philox::gen(seed, (uint64_t)chain, (offset << 24) ^ (STREAM_NORMAL << 60) ^ (uint64_t)(l + G * q), o);
+        const double u1 = Philox::u01(o[0], o[1]), u2 = Philox::u01(o[2], o[3]);
+        const double rad = sqrt(-2.0 * log(u1));
+        double sn, cs;
+        sincospi(2.0 * u2, &sn, &cs);
+        z[2 * q] = (l + G * (2 * q) < D) ? rad * cs : 0.0;
+        if (2 * q + 1 < E) z[2 * q + 1] = (l + G * (2 * q + 1) < D) ? rad * sn : 0.0;
+    }
+}
+
 // standard exponential, k-th draw of (chain, transition)
 __device__ __forceinline__ double philox_exp(uint64_t seed, uint64_t offset, long long chain, int k) {
     uint32_t o[4];

@@ -63,6 +63,7 @@ struct RngDev {
     long long exp_stride;
     const uint8_t* dir_tape;
     long long dir_stride;
+    double partial_alpha;  // 0: full refresh; else r' = alpha r + sqrt(1-alpha^2) xi (hamiltonian.jl:243-254)
 };
 
 struct HmcArgs {

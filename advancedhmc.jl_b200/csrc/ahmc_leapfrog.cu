@@ -195,13 +195,16 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC
             if (h.rng.normal_tape) {
                 vload_nc<G, E>(io.r0, h.rng.normal_tape + (long long)D * chain, l, D);
             } else {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    int d = l + G * e;
-                    io.r0[e] = (d < D) ? philox_normal(h.rng.seed, off, chain, d) : 0.0;
-                }
+                philox_normals<G, E>(h.rng.seed, off, chain, l, D, io.r0);
             }
             me.rand_momentum(io.r0, l);
+            if (h.rng.partial_alpha != 0.0) {  // PartialMomentumRefreshment (hamiltonian.jl:243-254)
+                double rp[E];
+                vload_nc<G, E>(rp, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
+                const double al = h.rng.partial_alpha, be = sqrt(1.0 - al * al);
+#pragma unroll
+                for (int e = 0; e < E; ++e) io.r0[e] = al * rp[e] + be * io.r0[e];
+            }
         } else {
             vload_nc<G, E>(io.r0, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
         }
@@ -265,11 +268,7 @@ __global__ void __launch_bounds__(kBlockThreads) momentum_kernel(const MomentumA
     if (a.normal_tape) {
         vload_nc<G, E>(r, a.normal_tape + (long long)D * chain, l, D);
     } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            int d = l + G * e;
-            r[e] = (d < D) ? philox_normal(a.seed, a.offset, chain, d) : 0.0;
-        }
+        philox_normals<G, E>(a.seed, a.offset, chain, l, D, r);
     }
     me.rand_momentum(r, l);
     if (valid) vstore<G, E>(a.r + a.ld * chain, r, l, D);

@@ -128,13 +128,16 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 if (a.rng.normal_tape) {
                     vload_nc<G, E>(rn, a.rng.normal_tape + (long long)D * chain, l, D);
                 } else {
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        int d = l + G * e;
-                        rn[e] = (d < D) ? philox_normal(a.rng.seed, off, chain, d) : 0.0;
-                    }
+                    philox_normals<G, E>(a.rng.seed, off, chain, l, D, rn);
                 }
                 me.rand_momentum(rn, l);
+                if (a.rng.partial_alpha != 0.0) {  // PartialMomentumRefreshment (hamiltonian.jl:243-254)
+                    double rp[E];
+                    vload_nc<G, E>(rp, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
+                    const double al = a.rng.partial_alpha, be = sqrt(1.0 - al * al);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) rn[e] = al * rp[e] + be * rn[e];
+                }
             } else {
                 vload_nc<G, E>(rn, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
             }

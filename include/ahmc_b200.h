@@ -114,6 +114,8 @@ typedef struct ahmc_rng {
     int64_t exp_stride;
     const uint8_t* dir_tape;   /* NUTS: dir_stride x N direction bits (`rand(rng,Bool)`, trajectory.jl:693) */
     int64_t dir_stride;
+    double partial_refresh_alpha; /* 0: FullMomentumRefreshment; else PartialMomentumRefreshment(alpha):
+                                     r' = alpha*r + sqrt(1-alpha^2)*rand_momentum (hamiltonian.jl:222-254) */
 } ahmc_rng;
 
 /* User gradient callback for AHMC_MODEL_CALLBACK (replaces the Julia closure h.dlp/dth, hamiltonian.jl:45-48).

@@ -56,6 +56,7 @@ struct CRng
     exp_stride::Int64
     dir_tape::Ptr{UInt8}
     dir_stride::Int64
+    partial_refresh_alpha::Float64
 end
 
 const FLAG_ASYNC = 0x4 % UInt32
@@ -108,6 +109,9 @@ cmetric(m::DenseEuclideanMetric, N) = CMetric(2, pointer(m.M⁻¹), 0, pointer(C
 cpp(z::PhasePoint{<:CuMatrix}) = CPhasePoint(pointer(z.θ), pointer(z.r), pointer(z.ℓπ.value), pointer(z.ℓπ.gradient),
                                             pointer(z.ℓκ.value), pointer(z.ℓκ.gradient), size(z.θ, 1))
 
+refresh_alpha(::AdvancedHMC.FullMomentumRefreshment) = 0.0
+refresh_alpha(r::AdvancedHMC.PartialMomentumRefreshment) = Float64(r.α)
+
 eps_args(ϵ::AbstractFloat) = (Float64(ϵ), Ptr{Float64}(C_NULL))
 eps_args(ϵ::CuVector{Float64}) = (0.0, pointer(ϵ))
 
@@ -141,7 +145,7 @@ function AdvancedHMC.transition(rng, h::Hamiltonian, κ::AdvancedHMC.HMCKernel{R
     acc = CUDA.zeros(UInt8, N); α = CUDA.zeros(Float64, N); H = CUDA.zeros(Float64, N); dH = CUDA.zeros(Float64, N)
     nerr = CUDA.zeros(UInt8, N)
     st = Ref(CStats(C_NULL, pointer(acc), pointer(α), C_NULL, pointer(H), pointer(dH), C_NULL, C_NULL, pointer(nerr)))
-    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0))   # Philox key drawn from the Julia rng
+    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, refresh_alpha(κ.refreshment)))   # Philox key drawn from the Julia rng
     ϵ, ϵp = eps_args(step_size(lf))
     md = Ref(cmetric(h.metric, N)); zi = Ref(cpp(z)); zo = Ref(cpp(zout))
     zo[] = CPhasePoint(zo[].theta, zo[].r, zo[].lp_value, zo[].lp_gradient, zo[].lk_value, C_NULL, zo[].ld)
@@ -168,7 +172,7 @@ function AdvancedHMC.transition(rng, h::Hamiltonian,
     ns = CUDA.zeros(Int32, N); α = CUDA.zeros(Float64, N); H = CUDA.zeros(Float64, N); dH = CUDA.zeros(Float64, N)
     mx = CUDA.zeros(Float64, N); td = CUDA.zeros(Int32, N); nerr = CUDA.zeros(UInt8, N)
     st = Ref(CStats(pointer(ns), C_NULL, pointer(α), C_NULL, pointer(H), pointer(dH), pointer(mx), pointer(td), pointer(nerr)))
-    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0))
+    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, refresh_alpha(κ.refreshment)))
     ϵ, ϵp = eps_args(step_size(lf))
     md = Ref(cmetric(h.metric, N)); zi = Ref(cpp(z)); zo = Ref(cpp(zout))
     zo[] = CPhasePoint(zo[].theta, zo[].r, zo[].lp_value, zo[].lp_gradient, zo[].lk_value, C_NULL, zo[].ld)

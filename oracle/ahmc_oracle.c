@@ -320,6 +320,17 @@ void orc_leapfrog_trajectory(const orc_model* m, const orc_metric* me, int32_t D
                   steps_done, compat_break_all);
 }
 
+static double g_partial_alpha = 0.0;
+void orc_set_partial_refresh(double alpha) { g_partial_alpha = alpha; }
+/* refresh(rng, ref, h, z) (hamiltonian.jl:213-220 full, :243-254 partial) for chain c */
+static void refresh_momentum(const orc_metric* me, int D, int64_t c, const double* z_tape, const double* r_prev, double* r) {
+    orc_rand_momentum(me, D, c, z_tape, r);
+    if (g_partial_alpha != 0.0) {
+        double a = g_partial_alpha, b = sqrt(1 - a * a);
+        for (int d = 0; d < D; ++d) r[d] = a * r_prev[d] + b * r[d];
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* static HMC transition (sampler.jl:48-58; trajectory.jl:271-300, :312-340, :863-880)          */
 /* ------------------------------------------------------------------------------------------ */
@@ -336,7 +347,7 @@ void orc_hmc_transition(const orc_model* m, const orc_metric* me, int32_t D, int
     for (int64_t c = 0; c < N; ++c) {
         memcpy(z0.theta + D * c, z_in->theta + z_in->ld * c, sizeof(double) * (size_t)D);
         if (normal_tape)
-            orc_rand_momentum(me, D, c, normal_tape + (size_t)D * c, z0.r + D * c);
+            refresh_momentum(me, D, c, normal_tape + (size_t)D * c, z_in->r + z_in->ld * c, z0.r + D * c);
         else
             memcpy(z0.r + D * c, z_in->r + z_in->ld * c, sizeof(double) * (size_t)D);
     }
@@ -556,7 +567,7 @@ void orc_nuts_transition(const orc_model* m, const orc_metric* me, int32_t D, in
         pp_t* z0 = pp_alloc(&x);
         memcpy(z0->theta, z_in->theta + z_in->ld * c, sizeof(double) * (size_t)D);
         if (normal_tape)
-            orc_rand_momentum(me, D, c, normal_tape + (size_t)D * c, z0->r);
+            refresh_momentum(me, D, c, normal_tape + (size_t)D * c, z_in->r + z_in->ld * c, z0->r);
         else
             memcpy(z0->r, z_in->r + z_in->ld * c, sizeof(double) * (size_t)D);
         double lp;

@@ -113,6 +113,9 @@ void orc_hmc_transition(const orc_model* m, const orc_metric* me, int32_t D, int
                         const double* eps_chain, int32_t n_steps, const double* normal_tape,
                         const double* exp_tape, const orc_phasepoint* z_in, const orc_phasepoint* z_out,
                         const orc_stats* st, int compat_break_all);
+/* PartialMomentumRefreshment(alpha) (hamiltonian.jl:222-254) for the transitions below: when non-zero, the
+ * refreshed momentum is alpha*z_in.r + sqrt(1-alpha^2)*rand_momentum(tape).  Process-global test knob. */
+void orc_set_partial_refresh(double alpha);
 
 /* NUTS transition, MultinomialTS + GeneralisedNoUTurn (trajectory.jl:626-742), one chain at a time
  * (the reference has no vectorised NUTS).  Tapes per chain c: dir_tape[c*dir_stride + k] = k-th

@@ -296,6 +296,11 @@ class WelfordCov:
         return out
 
 
+def set_partial_refresh(alpha: float):
+    """PartialMomentumRefreshment(alpha) for subsequent hmc/nuts transitions (0 = full refresh)."""
+    lib().orc_set_partial_refresh(C.c_double(alpha))
+
+
 def stan_windows(n_adapts, init_buffer=75, term_buffer=50, window_size=25):
     ws, we = C.c_int32(0), C.c_int32(0)
     splits = (C.c_int32 * 64)()

@@ -575,3 +575,76 @@ def test_multi_transition_launch_equals_sequential_transitions(kind, D):
     assert torch.equal(zl.lp.gradient, z.lp.gradient) and torch.equal(zl.lk.value, z.lk.value)
     if kind == "nuts":
         assert len(set(st["tree_depth"].flatten().tolist())) > 1
+
+
+# ------------------------------------------------------------------------------------------------ refreshment / step-size search
+def test_partial_momentum_refreshment_vs_oracle():
+    """PartialMomentumRefreshment(alpha): r' = alpha r + sqrt(1-alpha^2) xi (hamiltonian.jl:222-254), HMC and NUTS."""
+    rng = np.random.default_rng(12)
+    D, N, alpha = 9, 150, 0.7
+    s = np.exp(rng.uniform(-0.5, 0.5, D))
+    m = rng.normal(size=D)
+    om, ome = oc.Model(oc.DIAG_GAUSS, D, m, s), oc.Metric(oc.DIAG, s * s)
+    th, r = rng.normal(size=(D, N)), rng.normal(size=(D, N)) / s[:, None]
+    z0o = oc.phasepoint(om, ome, th, r)
+    h = A.Hamiltonian(A.DiagEuclideanMetric(s * s), A.DiagGaussian(m, s, normalised=False))
+    z0 = A.phasepoint(h, T(th), T(r))
+    nt, et = rng.normal(size=(D, N)), rng.exponential(size=N) * 0.05
+    oc.set_partial_refresh(alpha)
+    try:
+        zo, so = oc.hmc_transition(om, ome, 0.5, 6, z0o, nt, et)
+        dirs = rng.integers(0, 2, size=(N, 11)).astype(np.uint8)
+        exps = rng.exponential(size=(N, 1024))
+        zn, sn, _ = oc.nuts_transition(om, ome, 0.4, z0o, nt, dirs, exps)
+    finally:
+        oc.set_partial_refresh(0.0)
+    ref = A.PartialMomentumRefreshment(alpha)
+    tr = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(et, device=DEV)), h,
+                      A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.5), A.FixedNSteps(6)), ref), z0)
+    assert (F(tr.stat["is_accept"]).astype(bool) == so.is_accept.astype(bool)).all()
+    assert_pp_close(tr.z, zo)
+    tn = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(exps, device=DEV), dirs=torch.as_tensor(dirs, device=DEV)), h,
+                      A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.4), A.GeneralisedNoUTurn()), ref), z0)
+    assert (F(tn.stat["n_steps"]) == sn.n_steps).all()
+    assert_pp_close(tn.z, zn)
+    # with alpha the refreshed momentum stays correlated with the old one
+    full = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(et, device=DEV)), h,
+                        A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.5), A.FixedNSteps(6))), z0)
+    assert not torch.equal(full.z.theta, tr.z.theta)
+
+
+def test_find_good_stepsize_matches_reference_logic():
+    """src/trajectory.jl:768-837 restated on the CPU oracle with the same momentum draw -> same eps."""
+    D = 12
+    rng = np.random.default_rng(3)
+    s = np.exp(rng.uniform(-1, 1, D))
+    m = rng.normal(size=D)
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.DiagGaussian(m, s, normalised=False))
+    th = rng.normal(size=D)
+    xi = rng.normal(size=(D, 1))
+    eps = A.find_good_stepsize(A.TapeRNG(normal=T(xi)), h, torch.as_tensor(th, device=DEV))
+    # oracle-side restatement
+    om, ome = oc.Model(oc.DIAG_GAUSS, D, m, s), oc.Metric(oc.DIAG, np.ones(D))
+    z = oc.phasepoint(om, ome, th[:, None], xi)
+    H = z.energy()[0]
+    Af = lambda e: oc.leapfrog(om, ome, e, z, 1)[0].energy()[0]
+    e = ep = 0.1
+    lo, cross, hi = 2 * np.log(0.5), np.log(0.5), np.log(0.75)
+    too_high = (H - Af(e)) > cross
+    for _ in range(100):
+        ep = 2 * e if too_high else 0.5 * e
+        if too_high != ((H - Af(e)) > cross):
+            break
+        e = ep
+    e, ep = min(e, ep), max(e, ep)
+    for _ in range(100):
+        mid = 0.5 * (e + ep)
+        dH = H - Af(mid)
+        if dH > hi:
+            e = mid
+        elif dH < lo:
+            ep = mid
+        else:
+            e = mid
+            break
+    assert eps == pytest.approx(e, rel=1e-12) and 0.01 < eps < 10
