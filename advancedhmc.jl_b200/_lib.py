@@ -58,6 +58,12 @@ PROTOTYPES = {
                                       C.c_uint32]),
     "ahmc_leapfrog_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp, C.c_int32,
                                     C.c_double, C.POINTER(PhasePoint), C.POINTER(PhasePoint), _vp, _vp, C.c_uint32]),
+    "ahmc_leapfrog_trajectory_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp,
+                                               C.c_int32, C.c_double, C.POINTER(PhasePoint), C.POINTER(PhasePoint),
+                                               C.c_int64, _vp, C.c_uint32]),
+    "ahmc_hmc_multinomial_transition_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp,
+                                                      C.c_int32, C.c_int32, C.POINTER(Rng), C.POINTER(PhasePoint),
+                                                      C.POINTER(PhasePoint), C.POINTER(Stats), C.c_uint32]),
     "ahmc_rand_momentum_f64": (C.c_int, [_vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.POINTER(Rng), _vp,
                                          C.c_int64, C.c_uint32]),
     "ahmc_hmc_transition_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp,

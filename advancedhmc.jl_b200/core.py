@@ -418,13 +418,22 @@ class PhiloxRNG:
             self.offset += 1
         return r, ()
 
+    def draw_n_fwd(self, n_steps: int) -> int:
+        """the coupled `rand(0:n_steps)` of the multinomial-static transition (host side, one value for all chains)."""
+        return int(np.random.Generator(np.random.Philox(key=self.seed, counter=[0, 0, 0, self.offset])).integers(0, n_steps + 1))
+
 
 class TapeRNG:
     """Explicit random tapes: makes a transition a pure function (how parity with the oracle is defined).
     normal: (N, D); exp: (N,) static HMC or (N, n_exp) NUTS; dirs: (N, n_dir) uint8."""
 
-    def __init__(self, normal=None, exp=None, dirs=None):
-        self.normal, self.exp, self.dirs = normal, exp, dirs
+    def __init__(self, normal=None, exp=None, dirs=None, n_fwd=None):
+        self.normal, self.exp, self.dirs, self.n_fwd = normal, exp, dirs, n_fwd
+
+    def draw_n_fwd(self, n_steps: int) -> int:
+        if self.n_fwd is None:
+            raise L.InvalidArgument(L.ERR_INVALID, "TapeRNG needs n_fwd for a MultinomialTS static transition")
+        return int(self.n_fwd)
 
     def _c(self, advance=True):
         es = 1 if (self.exp is None or self.exp.ndim == 1) else self.exp.shape[1]
@@ -540,13 +549,15 @@ class StepInfo:
 
 def step(lf: AbstractLeapfrog, h: Hamiltonian, z: PhasePoint, n_steps: int = 1, *, fwd: Optional[bool] = None,
          flags: int = 0, return_info: bool = False, with_lk_gradient: bool = True,
-         out: Optional[PhasePoint] = None):
+         out: Optional[PhasePoint] = None, full_trajectory: bool = False):
     """`step(lf, h, z, n_steps; fwd)` (integrator.jl:216-265) -> ahmc_leapfrog_f64.
     Functional like the reference: returns a fresh PhasePoint, z is untouched."""
     if fwd is not None:
         n_steps = abs(n_steps) if fwd else -abs(n_steps)
     for nm in ("theta", "r"):
         _check_arr(getattr(z, nm), nm)
+    if full_trajectory:
+        return _step_full_trajectory(lf, h, z, n_steps, flags)
     ctx = get_context(_device_of(z.theta))
     N, D = z._nd()
     if out is None:
@@ -594,6 +605,36 @@ class StepPlan:
         if rc != L.OK:
             self.ctx.check(rc)
         return self.out
+
+
+def _step_full_trajectory(lf, h, z, n_steps, flags):
+    """`step(...; full_trajectory = Val(true))` (integrator.jl:229,249-261): returns (list of PhasePoint views,
+    steps_done).  Like the reference's matrix mode the list has max(steps_done) entries; a chain that stopped
+    early (per-chain break) leaves its later entries untouched -- consult steps_done."""
+    ctx = get_context(_device_of(z.theta))
+    N, D = z._nd()
+    L_ = abs(n_steps)
+    like = z.theta
+    shp = (L_, N, D)
+    traj = dict(theta=_like(like, shp), r=_like(like, shp), g=_like(like, shp), dr=_like(like, shp),
+                lp=_like(like, (L_, N)), lk=_like(like, (L_, N)))
+    done = _like(like, (N,), np.int32)
+    if L_ == 0:
+        return [], done
+    md, keep = h.metric._desc(D, N, like)
+    e, ep, keep2 = _eps_args(step_size(lf), like, N)
+    alpha = lf.alpha if isinstance(lf, TemperedLeapfrog) else 0.0
+    tc = L.PhasePoint(_ptr(traj["theta"]), _ptr(traj["r"]), _ptr(traj["lp"]), _ptr(traj["g"]), _ptr(traj["lk"]),
+                      _ptr(traj["dr"]), D)
+    _sync_torch(like)
+    zc = z._c()
+    ctx.check(ctx.lib.ahmc_leapfrog_trajectory_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, e, ep, int(n_steps),
+                                                   alpha, C.byref(zc), C.byref(tc), N * D, _ptr(done),
+                                                   flags | (L.FLAG_HOST_BUFFERS if _is_host(like) else 0)))
+    nmax = int(done.max()) if N else 0
+    zs = [PhasePoint(traj["theta"][i], traj["r"][i], DualValue(traj["lp"][i], traj["g"][i]),
+                     DualValue(traj["lk"][i], traj["dr"][i])) for i in range(nmax)]
+    return zs, done
 
 
 # ------------------------------------------------------------------------------------------------
@@ -707,7 +748,7 @@ def transition(rng, h: Hamiltonian, kappa: Union[HMCKernel, Trajectory], z: Phas
     rc.partial_refresh_alpha = _refresh_alpha(kappa)
     tc = tau.termination_criterion
     nuts = isinstance(tc, GeneralisedNoUTurn)
-    st, sc = _stats_buffers(z.theta, N, nuts)
+    st, sc = _stats_buffers(z.theta, N, nuts or tau.sampler is MultinomialTS)
     fl = flags | (L.FLAG_HOST_BUFFERS if host else 0)
     _sync_torch(z.theta)
     zc, oc = z._c(False), out._c(False)
@@ -717,9 +758,17 @@ def transition(rng, h: Hamiltonian, kappa: Union[HMCKernel, Trajectory], z: Phas
         ctx.check(ctx.lib.ahmc_nuts_transition_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, e, ep,
                                                    tc.max_depth, tc.delta_max, C.byref(rc), C.byref(zc),
                                                    C.byref(oc), C.byref(sc), fl))
+    elif tau.sampler is MultinomialTS:
+        # the direction split is ONE draw shared by all chains, like `rand_coupled(rng, 0:n_steps)` (trajectory.jl:371-373)
+        n = nsteps(tau)
+        n_fwd = rng.draw_n_fwd(n)
+        ctx.check(ctx.lib.ahmc_hmc_multinomial_transition_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, e, ep, n,
+                                                              n_fwd, C.byref(rc), C.byref(zc), C.byref(oc),
+                                                              C.byref(sc), fl))
+        st["n_steps_fwd"] = n_fwd
     else:
         if tau.sampler is not EndPointTS:
-            raise L.AhmcError(L.ERR_UNSUPPORTED, "only EndPointTS is built for static trajectories")
+            raise L.AhmcError(L.ERR_UNSUPPORTED, "static trajectories: EndPointTS or MultinomialTS")
         ctx.check(ctx.lib.ahmc_hmc_transition_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, e, ep, nsteps(tau),
                                                   C.byref(rc), C.byref(zc), C.byref(oc), C.byref(sc), fl))
     st.update(stat(lf))

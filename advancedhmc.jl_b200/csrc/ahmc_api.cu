@@ -25,6 +25,8 @@ struct ahmc_ctx {
     size_t nuts_scratch_bytes = 0;
     double* adapt_scratch = nullptr;
     size_t adapt_scratch_bytes = 0;
+    double* mn_scratch = nullptr;  // multinomial-static per-chain energy tape
+    size_t mn_scratch_bytes = 0;
     char* split_scratch = nullptr;   // callback (split-step) mode workspace
     size_t split_scratch_bytes = 0;
     cudaStream_t stream2 = nullptr;  // second stream of the host-buffer pipeline (H2D of chunk i+1 || D2H of chunk i)
@@ -332,6 +334,7 @@ int ahmc_destroy(ahmc_ctx* ctx) {
     cudaFree(ctx->arena);
     cudaFree(ctx->nuts_scratch);
     cudaFree(ctx->adapt_scratch);
+    cudaFree(ctx->mn_scratch);
     cudaFree(ctx->split_scratch);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -959,6 +962,116 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     a.scratch = ctx->nuts_scratch;
     int nl = 0;
     CU(launch_nuts(a, ctx->stream, &nl));
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
+int ahmc_leapfrog_trajectory_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D,
+                                 int64_t N, double eps, const double* eps_chain, int32_t n_steps, double temper_alpha,
+                                 const ahmc_phasepoint* z_in, const ahmc_phasepoint* traj, int64_t step_stride,
+                                 int32_t* steps_done, uint32_t flags) {
+    if (!ctx || !model || !metric) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric");
+    int rc = check_common(ctx, model, metric, D, N);
+    if (rc) return rc;
+    if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
+    const int n_abs = n_steps < 0 ? -n_steps : n_steps;
+    if (n_abs == 0 || N == 0) return AHMC_OK;  // res = Vector{P}(undef, 0)
+    if ((rc = check_pp(ctx, traj, D, "traj", true, N))) return rc;
+    if (step_stride < traj->ld * N) return fail(ctx, AHMC_ERR_INVALID, "step_stride must be >= ld*N");
+    if (model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "full_trajectory needs a device-resident target");
+    DeviceGuard g(ctx->device);
+    Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
+    const size_t cin = (size_t)z_in->ld * N, ctraj = (size_t)step_stride * n_abs;
+    reserve_metric(st, metric, D, N);
+    st.reserve(cin * 8 * 3);
+    st.reserve(ctraj * 8 * 4);
+    st.reserve((size_t)N * n_abs * 8 * 2 + (size_t)N * 16);
+    if ((rc = st.prepare())) return rc;
+    TrajArgs a{};
+    a.model = model_dev(model);
+    if ((rc = stage_metric(st, metric, D, N, &a.metric))) return rc;
+    a.D = D; a.N = N; a.eps = eps;
+    if ((rc = st.in(eps_chain, (size_t)N, &a.eps_chain))) return rc;
+    a.n_steps = n_abs; a.fwd = n_steps > 0; a.temper_alpha = temper_alpha;
+    a.ld_in = z_in->ld; a.ld_out = traj->ld; a.step_stride = step_stride;
+    if ((rc = st.in((const double*)z_in->theta, cin, &a.th_in))) return rc;
+    if ((rc = st.in((const double*)z_in->r, cin, &a.r_in))) return rc;
+    if ((rc = st.in((const double*)z_in->lp_gradient, cin, &a.g_in))) return rc;
+    if ((rc = st.out(traj->theta, ctraj, &a.th_out))) return rc;
+    if ((rc = st.out(traj->r, ctraj, &a.r_out))) return rc;
+    if ((rc = st.out(traj->lp_gradient, ctraj, &a.g_out))) return rc;
+    if ((rc = st.out(traj->lk_gradient, ctraj, &a.dr_out))) return rc;
+    if ((rc = st.out(traj->lp_value, (size_t)N * n_abs, &a.lp_out))) return rc;
+    if ((rc = st.out(traj->lk_value, (size_t)N * n_abs, &a.lk_out))) return rc;
+    if ((rc = st.out(steps_done, (size_t)N, &a.steps_done))) return rc;
+    int nl = 0;
+    CU(launch_trajectory(a, ctx->stream, &nl));
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
+int ahmc_hmc_multinomial_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D,
+                                        int64_t N, double eps, const double* eps_chain, int32_t n_steps,
+                                        int32_t n_steps_fwd, const ahmc_rng* rng, const ahmc_phasepoint* z_in,
+                                        const ahmc_phasepoint* z_out, const ahmc_stats* stats, uint32_t flags) {
+    if (!ctx || !model || !metric || !rng) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric/rng");
+    int rc = check_common(ctx, model, metric, D, N);
+    if (rc) return rc;
+    if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
+    if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
+    if (n_steps < 1 || n_steps_fwd < 0 || n_steps_fwd > n_steps)
+        return fail(ctx, AHMC_ERR_INVALID, "need n_steps >= 1 and 0 <= n_steps_fwd <= n_steps (rand(0:n_steps), trajectory.jl:373)");
+    if (model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "MultinomialTS static transitions need a device-resident target");
+    if (metric->kind == AHMC_METRIC_DENSE && !metric->cholU && !(flags & AHMC_FLAG_NO_REFRESH))
+        return fail(ctx, AHMC_ERR_INVALID, "Dense metric needs cholU for the momentum refresh (metric.jl:311-320)");
+    if (z_out->lk_gradient)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "transition entry points do not emit lk_gradient; call ahmc_phasepoint_f64 if needed");
+    if (!(rng->partial_refresh_alpha > -1.0 && rng->partial_refresh_alpha < 1.0))
+        return fail(ctx, AHMC_ERR_INVALID, "partial_refresh_alpha must be in (-1, 1)");
+    if (N == 0) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
+    const size_t cin = (size_t)z_in->ld * N, cout = (size_t)z_out->ld * N;
+    reserve_metric(st, metric, D, N);
+    st.reserve(cin * 8 * 3);
+    st.reserve(cout * 8 * 3);
+    st.reserve((size_t)D * N * 8);
+    st.reserve((size_t)N * 8 * 16);
+    if ((rc = st.prepare())) return rc;
+    MultinomialArgs a{};
+    a.model = model_dev(model);
+    if ((rc = stage_metric(st, metric, D, N, &a.metric))) return rc;
+    a.D = D; a.N = N; a.eps = eps;
+    if ((rc = st.in(eps_chain, (size_t)N, &a.eps_chain))) return rc;
+    a.n_steps = n_steps; a.n_fwd = n_steps_fwd;
+    a.refresh = (flags & AHMC_FLAG_NO_REFRESH) ? 0 : 1;
+    a.ld_in = z_in->ld; a.ld_out = z_out->ld;
+    if ((rc = st.in((const double*)z_in->theta, cin, &a.th_in))) return rc;
+    if ((rc = st.in((const double*)z_in->r, cin, &a.r_in))) return rc;
+    if ((rc = st.in((const double*)z_in->lp_gradient, cin, &a.g_in))) return rc;
+    if ((rc = st.in((const double*)z_in->lp_value, (size_t)N, &a.lp_in))) return rc;
+    if ((rc = st.out(z_out->theta, cout, &a.th_out))) return rc;
+    if ((rc = st.out(z_out->r, cout, &a.r_out))) return rc;
+    if ((rc = st.out(z_out->lp_gradient, cout, &a.g_out))) return rc;
+    if ((rc = st.out(z_out->lp_value, (size_t)N, &a.lp_out))) return rc;
+    if ((rc = st.out(z_out->lk_value, (size_t)N, &a.lk_out))) return rc;
+    if ((rc = stage_rng(st, rng, D, N, false, &a.rng))) return rc;
+    if ((rc = stage_stats(st, stats, N, &a.st))) return rc;
+    const size_t need = (size_t)(n_steps + 1) * (size_t)N * sizeof(double);
+    if (need > ctx->mn_scratch_bytes) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->mn_scratch);
+        ctx->mn_scratch = nullptr;
+        ctx->mn_scratch_bytes = 0;
+        if (cudaMalloc((void**)&ctx->mn_scratch, need) != cudaSuccess)
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc(%zu) for the multinomial energy tape failed", need);
+        ctx->mn_scratch_bytes = need;
+    }
+    a.energies = ctx->mn_scratch;
+    int nl = 0;
+    CU(launch_multinomial(a, ctx->stream, &nl));
     ctx->launches += nl;
     return finish_call(ctx, st, flags);
 }

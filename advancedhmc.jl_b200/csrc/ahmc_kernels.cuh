@@ -132,6 +132,42 @@ struct MhArgs {  // accept / revert / flip + stats after a split-mode trajectory
     StatsDev st;
 };
 
+struct TrajArgs {  // step(...; full_trajectory = Val(true)) (integrator.jl:229,249-261)
+    ModelDev model;
+    MetricDev metric;
+    int D;
+    long long N;
+    double eps;
+    const double* eps_chain;
+    int n_steps;  // absolute
+    int fwd;
+    double temper_alpha;
+    const double *th_in, *r_in, *g_in;
+    long long ld_in;
+    double *th_out, *r_out, *g_out, *dr_out;  // point i (0-based) at i*step_stride + ld_out*chain
+    double *lp_out, *lk_out;                   // point i at i*N + chain
+    long long ld_out, step_stride;
+    int32_t* steps_done;
+};
+
+struct MultinomialArgs {  // static transition with MultinomialTS (trajectory.jl:344-390)
+    ModelDev model;
+    MetricDev metric;
+    int D;
+    long long N;
+    double eps;
+    const double* eps_chain;
+    int n_steps, n_fwd;
+    int refresh;
+    RngDev rng;  // exp_tape doubles as the per-chain UNIFORM tape of `randcat`
+    const double *th_in, *r_in, *g_in, *lp_in;
+    long long ld_in;
+    double *th_out, *r_out, *g_out, *lp_out, *lk_out;
+    long long ld_out;
+    StatsDev st;
+    double* energies;  // (n_steps + 1) doubles per chain
+};
+
 // choose (G, E) for a dimension: returns false if D is out of the register-resident range
 bool pick_layout(int D, int* G, int* E);
 
@@ -142,6 +178,8 @@ cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t stream, int
 cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_nuts(const NutsArgs& a, cudaStream_t stream, int* n_launches);
 long long nuts_scratch_doubles_per_chain(int D, int max_depth);
+cudaError_t launch_trajectory(const TrajArgs& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_multinomial(const MultinomialArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_kick_drift(const SplitArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_kick_energy(const SplitArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_mh_select(const MhArgs& a, cudaStream_t stream, int* n_launches);

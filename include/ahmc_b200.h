@@ -156,6 +156,15 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
                       const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, uint32_t* status,
                       int32_t* steps_done, uint32_t flags);
 
+/* step(lf, h, z, n_steps; full_trajectory = Val(true))  (src/integrator.jl:229,249-261): every intermediate phase
+ * point is returned.  `traj` arrays hold |n_steps| phase points: point i (0-based) of theta/r/lp_gradient/lk_gradient
+ * at `i*step_stride + ld*c`, of lp_value/lk_value at `i*N + c`.  A chain that turns non-finite at step k fills k
+ * points (the non-finite one included, like `resize!(res, i)`); steps_done[c] = k. */
+int ahmc_leapfrog_trajectory_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D,
+                                 int64_t N, double eps, const double* eps_chain, int32_t n_steps, double temper_alpha,
+                                 const ahmc_phasepoint* z_in, const ahmc_phasepoint* traj, int64_t step_stride,
+                                 int32_t* steps_done, uint32_t flags);
+
 /* rand_momentum(rng, metric, kinetic, theta)  (src/metric.jl:290-320): r[D x N] from normals (tape or Philox). */
 int ahmc_rand_momentum_f64(ahmc_ctx* ctx, const ahmc_metric* metric, int32_t D, int64_t N, const ahmc_rng* rng,
                            double* r, int64_t ld, uint32_t flags);
@@ -167,6 +176,17 @@ int ahmc_hmc_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_m
                             double eps, const double* eps_chain, int32_t n_steps, const ahmc_rng* rng,
                             const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, const ahmc_stats* stats,
                             uint32_t flags);
+
+/* Static transition with `MultinomialTS` (src/trajectory.jl:344-390): n_steps_fwd forward and
+ * n_steps - n_steps_fwd backward steps from z, new point ~ softmax(-H) over the whole trajectory by inverse CDF
+ * (`randcat`, src/utilities.jl:92-103), is_accept = true, acceptance_rate = mean_i min(1, exp(H0 - H_i)).
+ * The caller draws n_steps_fwd ~ U{0..n_steps} ONCE for all chains, as the reference does (`rand_coupled`,
+ * trajectory.jl:371-373).  rng->exp_tape (if given) is the per-chain UNIFORM tape u[N] of `randcat`.
+ * stats->tree_depth (if given) receives the signed offset of the drawn point from z. */
+int ahmc_hmc_multinomial_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D,
+                                        int64_t N, double eps, const double* eps_chain, int32_t n_steps,
+                                        int32_t n_steps_fwd, const ahmc_rng* rng, const ahmc_phasepoint* z_in,
+                                        const ahmc_phasepoint* z_out, const ahmc_stats* stats, uint32_t flags);
 
 /* One NUTS transition per chain (MultinomialTS + GeneralisedNoUTurn = what `NUTS(delta)` builds,
  * src/abstractmcmc.jl:415-419): src/trajectory.jl:626-742, run one chain per warp-group. */

@@ -386,6 +386,123 @@ void orc_hmc_transition(const orc_model* m, const orc_metric* me, int32_t D, int
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* static HMC transition, MultinomialTS (trajectory.jl:344-390)                                 */
+/* ------------------------------------------------------------------------------------------ */
+void orc_hmc_multinomial_transition(const orc_model* m, const orc_metric* me, int32_t D, int64_t N, double eps,
+                                    const double* eps_chain, int32_t n_steps, int32_t n_steps_fwd,
+                                    const double* normal_tape, const double* unif_tape, const orc_phasepoint* z_in,
+                                    const orc_phasepoint* z_out, const orc_stats* st) {
+    const int nf_req = n_steps_fwd, nb_req = n_steps - n_steps_fwd;
+    const int L = n_steps + 1;
+    /* one chain at a time (per-chain break = the reference applied to a single chain) */
+    double* buf = (double*)malloc(sizeof(double) * ((size_t)D * 3 * (size_t)(L + 1) + (size_t)L * 4 + 8));
+    double* TH = buf;                       /* (L) x D : trajectory order */
+    double* R = TH + (size_t)D * L;
+    double* G = R + (size_t)D * L;
+    double* LP = G + (size_t)D * L;
+    double* LK = LP + L;
+    double* W = LK + L;
+    double* scratch = W + L; /* unused tail */
+    (void)scratch;
+    double* th = (double*)malloc(sizeof(double) * (size_t)D * 5);
+    double *r = th + D, *g = th + 2 * D, *dr = th + 3 * D, *grad = th + 4 * D;
+    for (int64_t c = 0; c < N; ++c) {
+        double e = eps_chain ? eps_chain[c] : eps;
+        /* z = refresh(...) */
+        double th0[1024], r0[1024], g0[1024];
+        if (D > 1024) abort();
+        memcpy(th0, z_in->theta + z_in->ld * c, sizeof(double) * (size_t)D);
+        if (normal_tape) refresh_momentum(me, D, c, normal_tape + (size_t)D * c, z_in->r + z_in->ld * c, r0);
+        else memcpy(r0, z_in->r + z_in->ld * c, sizeof(double) * (size_t)D);
+        double lp0;
+        orc_logp_grad(m, th0, &lp0, grad);
+        for (int d = 0; d < D; ++d) g0[d] = -grad[d];
+        lp0 = map_nonfinite(lp0);
+        double lk0 = map_nonfinite(orc_neg_kinetic(me, D, c, r0));
+        /* backward sweep first so that the arrays end up in trajectory order: reverse(bwd)..., z, fwd... */
+        int nb = 0, nf = 0;
+        double tmpTH[1], *bTH = (double*)malloc(sizeof(double) * (size_t)D * 3 * (size_t)(nb_req + 1) + 16);
+        (void)tmpTH;
+        double *bR = bTH + (size_t)D * (nb_req + 1), *bG = bR + (size_t)D * (nb_req + 1);
+        double* bLP = (double*)malloc(sizeof(double) * 2 * (size_t)(nb_req + 1));
+        double* bLK = bLP + (nb_req + 1);
+        memcpy(th, th0, sizeof(double) * (size_t)D); memcpy(r, r0, sizeof(double) * (size_t)D); memcpy(g, g0, sizeof(double) * (size_t)D);
+        for (int i = 1; i <= nb_req; ++i) {
+            double lp, lk;
+            int fin = lf_one_step(m, me, D, c, -e, i, nb_req, 0.0, th, r, g, &lp, &lk, dr, grad);
+            memcpy(bTH + (size_t)D * nb, th, sizeof(double) * (size_t)D);
+            memcpy(bR + (size_t)D * nb, r, sizeof(double) * (size_t)D);
+            memcpy(bG + (size_t)D * nb, g, sizeof(double) * (size_t)D);
+            bLP[nb] = lp; bLK[nb] = lk;
+            nb++;
+            if (!fin) break;
+        }
+        int len = 0;
+        for (int i = nb - 1; i >= 0; --i, ++len) {
+            memcpy(TH + (size_t)D * len, bTH + (size_t)D * i, sizeof(double) * (size_t)D);
+            memcpy(R + (size_t)D * len, bR + (size_t)D * i, sizeof(double) * (size_t)D);
+            memcpy(G + (size_t)D * len, bG + (size_t)D * i, sizeof(double) * (size_t)D);
+            LP[len] = bLP[i]; LK[len] = bLK[i];
+        }
+        free(bTH); free(bLP);
+        memcpy(TH + (size_t)D * len, th0, sizeof(double) * (size_t)D);
+        memcpy(R + (size_t)D * len, r0, sizeof(double) * (size_t)D);
+        memcpy(G + (size_t)D * len, g0, sizeof(double) * (size_t)D);
+        LP[len] = lp0; LK[len] = lk0; len++;
+        memcpy(th, th0, sizeof(double) * (size_t)D); memcpy(r, r0, sizeof(double) * (size_t)D); memcpy(g, g0, sizeof(double) * (size_t)D);
+        for (int i = 1; i <= nf_req; ++i) {
+            double lp, lk;
+            int fin = lf_one_step(m, me, D, c, e, i, nf_req, 0.0, th, r, g, &lp, &lk, dr, grad);
+            memcpy(TH + (size_t)D * len, th, sizeof(double) * (size_t)D);
+            memcpy(R + (size_t)D * len, r, sizeof(double) * (size_t)D);
+            memcpy(G + (size_t)D * len, g, sizeof(double) * (size_t)D);
+            LP[len] = lp; LK[len] = lk; len++; nf++;
+            if (!fin) break;
+        }
+        /* weights = -energy.(zs); P = exp.(w .- logsumexp(w)); idx = count(cumsum(P) .< u) + 1 */
+        double H0 = -(lp0 + lk0);
+        double mx = NEG_INF;
+        for (int i = 0; i < len; ++i) { W[i] = LP[i] + LK[i]; if (W[i] > mx) mx = W[i]; }
+        double ssum = 0.0;
+        for (int i = 0; i < len; ++i) ssum += exp(W[i] - mx);
+        double lse = mx + log(ssum);
+        double u = unif_tape[c], C = 0.0, asum = 0.0;
+        int cnt = 0;
+        for (int i = 0; i < len; ++i) {
+            C += exp(W[i] - lse);
+            if (C < u) cnt++;
+            double dH = -W[i] - H0;
+            asum += exp(jl_min(0.0, -dH));
+        }
+        int idx = cnt; /* 0-based index of the (cnt+1)-th point */
+        if (idx > len - 1) idx = len - 1;
+        double alpha = asum / len;
+        for (int d = 0; d < D; ++d) {
+            z_out->theta[z_out->ld * c + d] = TH[(size_t)D * idx + d];
+            z_out->r[z_out->ld * c + d] = -R[(size_t)D * idx + d]; /* flip (trajectory.jl:283) */
+            z_out->lp_gradient[z_out->ld * c + d] = G[(size_t)D * idx + d];
+        }
+        z_out->lp_value[c] = LP[idx];
+        z_out->lk_value[c] = LK[idx];
+        if (z_out->lk_gradient) orc_dHdr(me, D, c, R + (size_t)D * idx, z_out->lk_gradient + z_out->ld * c);
+        double H = -(LP[idx] + LK[idx]);
+        if (st) {
+            if (st->n_steps) st->n_steps[c] = n_steps;
+            if (st->is_accept) st->is_accept[c] = 1;
+            if (st->acceptance_rate) st->acceptance_rate[c] = alpha;
+            if (st->log_density) st->log_density[c] = LP[idx];
+            if (st->hamiltonian_energy) st->hamiltonian_energy[c] = H;
+            if (st->hamiltonian_energy_error) st->hamiltonian_energy_error[c] = H - H0;
+            if (st->numerical_error) st->numerical_error[c] = (uint8_t)!isfinite(H);
+            if (st->tree_depth) st->tree_depth[c] = idx - nb; /* signed offset of the chosen point from z (test aid) */
+        }
+        (void)nf;
+    }
+    free(th);
+    free(buf);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* NUTS  (trajectory.jl:626-742), MultinomialTS + GeneralisedNoUTurn, recursive like the ref    */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {

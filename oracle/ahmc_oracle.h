@@ -113,6 +113,15 @@ void orc_hmc_transition(const orc_model* m, const orc_metric* me, int32_t D, int
                         const double* eps_chain, int32_t n_steps, const double* normal_tape,
                         const double* exp_tape, const orc_phasepoint* z_in, const orc_phasepoint* z_out,
                         const orc_stats* st, int compat_break_all);
+/* static HMC transition, MultinomialTS (trajectory.jl:344-390): n_steps_fwd forward + (n_steps - n_steps_fwd)
+ * backward steps from z (the reference draws n_steps_fwd ONCE for all chains: `rand_coupled`, :371-373), the new
+ * point is drawn from the whole trajectory with probabilities softmax(-H) by inverse-CDF on unif_tape[c]
+ * (`randcat`, utilities.jl:92-103); acceptance_rate = mean_i min(1, exp(H0 - H_i)); is_accept = true. */
+void orc_hmc_multinomial_transition(const orc_model* m, const orc_metric* me, int32_t D, int64_t N, double eps,
+                                    const double* eps_chain, int32_t n_steps, int32_t n_steps_fwd,
+                                    const double* normal_tape, const double* unif_tape, const orc_phasepoint* z_in,
+                                    const orc_phasepoint* z_out, const orc_stats* st);
+
 /* PartialMomentumRefreshment(alpha) (hamiltonian.jl:222-254) for the transitions below: when non-zero, the
  * refreshed momentum is alpha*z_in.r + sqrt(1-alpha^2)*rand_momentum(tape).  Process-global test knob. */
 void orc_set_partial_refresh(double alpha);

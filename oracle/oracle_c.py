@@ -219,6 +219,18 @@ def hmc_transition(model, metric, eps, n_steps, z, normal_tape, exp_tape, compat
     return out, st
 
 
+def hmc_multinomial_transition(model, metric, eps, n_steps, n_steps_fwd, z, normal_tape, unif_tape):
+    D, N = z.theta.shape
+    out, st = PhasePoint(D, N), Stats(N)
+    nt = None if normal_tape is None else _f(normal_tape)
+    ut = np.ascontiguousarray(unif_tape, dtype=np.float64)
+    e, ep, _keep = _eps_args(eps, N)
+    zc, oc, sc = z.c, out.c, st.c
+    lib().orc_hmc_multinomial_transition(C.byref(model.c), C.byref(metric.c), D, C.c_int64(N), e, ep, int(n_steps),
+                                         int(n_steps_fwd), _p(nt), _p(ut), C.byref(zc), C.byref(oc), C.byref(sc))
+    return out, st
+
+
 def nuts_transition(model, metric, eps, z, normal_tape, dir_tape, exp_tape, max_depth=10, delta_max=1000.0):
     """dir_tape: (N, n_dir) uint8 C-order; exp_tape: (N, n_exp) float64 C-order."""
     D, N = z.theta.shape

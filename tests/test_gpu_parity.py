@@ -648,3 +648,81 @@ def test_find_good_stepsize_matches_reference_logic():
             e = mid
             break
     assert eps == pytest.approx(e, rel=1e-12) and 0.01 < eps < 10
+
+
+# ------------------------------------------------------------------------------------------------ trajectory-sampling forms
+def test_full_trajectory_mode_vs_oracle():
+    """step(...; full_trajectory=Val(true)) (integrator.jl:229,249-261): every intermediate phase point, forward,
+    backward and with a chain that stops early."""
+    rng = np.random.default_rng(21)
+    D, N, L_ = 7, 45, 9
+    s = np.exp(rng.uniform(-0.5, 0.5, D))
+    om, ome = oc.Model(oc.FUNNEL, D), oc.Metric(oc.DIAG, s * s)
+    th, r = rng.normal(size=(D, N)) * 0.5, rng.normal(size=(D, N))
+    th[:, 4] = 1e160  # energies overflow at the first step: that chain returns exactly one point
+    z0o = oc.phasepoint(om, ome, th, r)
+    h = A.Hamiltonian(A.DiagEuclideanMetric(s * s), A.Funnel(D))
+    z0 = A.phasepoint(h, T(th), T(r))
+    for n in (L_, -L_):
+        traj, done_o = oc.leapfrog_trajectory(om, ome, 0.05, z0o, n)
+        zs, done = A.step(A.Leapfrog(0.05), h, z0, n, full_trajectory=True)
+        assert (F(done) == done_o).all() and done_o[4] == 1 and len(zs) == L_
+        ok = [c for c in range(N) if c != 4]
+        for i, z in enumerate(zs):
+            assert rel_err(F(z.theta)[:, ok], traj["theta"][:, ok, i]) < TOL
+            assert rel_err(F(z.r)[:, ok], traj["r"][:, ok, i]) < TOL
+            assert rel_err(F(z.lp.value)[ok], traj["lp_value"][ok, i]) < TOL
+            assert rel_err(F(z.lk.gradient)[:, ok], traj["lk_gradient"][:, ok, i]) < TOL
+        # the last point of the full trajectory is the ordinary step(n)
+        zl = A.step(A.Leapfrog(0.05), h, z0, n)
+        assert torch.equal(zs[-1].theta[ok], zl.theta[ok])
+    assert A.step(A.Leapfrog(0.05), h, z0, 0, full_trajectory=True)[0] == []
+
+
+@pytest.mark.parametrize("model,metric,D", [("diag_gauss", "diag", 128), ("std_normal", "unit", 5), ("funnel", "unit", 10)])
+@pytest.mark.parametrize("n_fwd", [0, 4, 11])
+def test_multinomial_static_transition_vs_oracle(model, metric, D, n_fwd):
+    """Trajectory{MultinomialTS}(lf, FixedNSteps(11)) (trajectory.jl:344-390) with tapes: same draw, same statistics."""
+    rng = np.random.default_rng(D + n_fwd)
+    N, L_ = 211, 11
+    p0 = p1 = Minv = None
+    if model == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.5, 0.5, D))
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    th = rng.normal(size=(D, N)) * (0.4 if model == "funnel" else 1.0)
+    nt, ut = rng.normal(size=(D, N)), rng.uniform(size=N)
+    eps = {"diag_gauss": 0.45, "std_normal": 0.6, "funnel": 0.15}[model]
+    om, ome = oc.Model(MODEL_KINDS[model], D, p0, p1, 0.0), oc.Metric(METRIC_KINDS[metric], Minv)
+    z0o = oc.phasepoint(om, ome, th, np.zeros((D, N)))
+    zo, so = oc.hmc_multinomial_transition(om, ome, eps, L_, n_fwd, z0o, nt, ut)
+    h = A.Hamiltonian(make_metric(metric, Minv, D), make_target(model, D, p0, p1, 0.0))
+    z0 = A.phasepoint(h, T(th), T(np.zeros((D, N))))
+    tau = A.Trajectory(A.MultinomialTS, A.Leapfrog(eps), A.FixedNSteps(L_))
+    tr = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(ut, device=DEV), n_fwd=n_fwd), h, A.HMCKernel(tau), z0)
+    off = F(tr.stat["tree_depth"])
+    assert (off == so.tree_depth).all() and off.min() >= -(L_ - n_fwd) and off.max() <= n_fwd
+    assert len(set(off.tolist())) > 3  # the draw really ranges over the trajectory
+    assert_pp_close(tr.z, zo)
+    assert rel_err(F(tr.stat["acceptance_rate"]), so.acceptance_rate) < 1e-9
+    assert (F(tr.stat["is_accept"]) == 1).all() and (F(tr.stat["n_steps"]) == L_).all()
+    assert np.allclose(F(tr.stat["hamiltonian_energy_error"]), so.hamiltonian_energy_error, rtol=0, atol=1e-9 * D)
+
+
+def test_multinomial_static_sampling_moments_philox():
+    """test/sampler-vec.jl:22-29 analogue: Trajectory{MultinomialTS}(lf, FixedNSteps(10)), many chains."""
+    D, N = 5, 4096
+    m, s = np.array([1.0, -2.0, 0.5, 0.0, 3.0]), np.array([1.0, 0.5, 2.0, 1.5, 0.7])
+    h = A.Hamiltonian(A.UnitEuclideanMetric(D), A.DiagGaussian(m, s))
+    zero = lambda: torch.zeros((N, D), dtype=torch.float64, device=DEV)
+    z = A.phasepoint(h, zero(), zero())
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.2), A.FixedNSteps(10)))
+    rng = A.PhiloxRNG(77)
+    nf = set()
+    for _ in range(60):
+        tr = A.transition(rng, h, kern, z)
+        z = tr.z
+        nf.add(tr.stat["n_steps_fwd"])
+    th = z.theta.cpu().numpy()
+    assert np.abs(th.mean(axis=0) - m).max() < 0.15 and np.abs(th.std(axis=0) - s).max() < 0.15
+    assert len(nf) > 5 and tr.stat["acceptance_rate"].mean().item() > 0.8
