@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libahmc_b200.so")
-SOURCES = ["ahmc_api.cu", "ahmc_leapfrog.cu", "ahmc_nuts.cu", "ahmc_adapt.cu", "ahmc_multinomial.cu"]
+SOURCES = ["ahmc_api.cu", "ahmc_leapfrog.cu", "ahmc_nuts.cu", "ahmc_adapt.cu", "ahmc_multinomial.cu", "ahmc_dense.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("AHMC_PTXAS_V") else "-O3"]
@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stderr)
         return obj
 
-    with cf.ThreadPoolExecutor(max_workers=5) as ex:
+    with cf.ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared"]
     r = subprocess.run(cmd, capture_output=True, text=True)

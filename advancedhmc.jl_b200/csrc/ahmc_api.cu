@@ -27,6 +27,8 @@ struct ahmc_ctx {
     size_t adapt_scratch_bytes = 0;
     double* mn_scratch = nullptr;  // multinomial-static per-chain energy tape
     size_t mn_scratch_bytes = 0;
+    char* dense_scratch = nullptr;  // K4: padded Minv, norms, per-chain fallback mask
+    size_t dense_scratch_bytes = 0;
     char* split_scratch = nullptr;   // callback (split-step) mode workspace
     size_t split_scratch_bytes = 0;
     cudaStream_t stream2 = nullptr;  // second stream of the host-buffer pipeline (H2D of chunk i+1 || D2H of chunk i)
@@ -38,6 +40,8 @@ struct ahmc_model {
     int D = 0;
     double* d_p0 = nullptr;
     double* d_p1 = nullptr;
+    double* d_p1_pad = nullptr;  // DENSE_GAUSS: precision zero-padded to Dp x Dp (K4), followed by |P|_inf
+    int Dp = 0;
     double c0 = 0.0;
     ahmc_logp_grad_fn fn = nullptr;
     void* user = nullptr;
@@ -286,6 +290,69 @@ int split_trajectory(ahmc_ctx* ctx, const ahmc_model* model, const MetricDev& md
     }
     return AHMC_OK;
 }
+
+// K4 dispatch: GEMM-shaped operators (dense metric and/or dense-Gaussian target) -> tiled DMMA kernel; chains of tiles it
+// declines (magnitude proof not met) are redone by the exact warp-per-chain kernel from the untouched inputs.
+// `a` holds DEVICE pointers.  Returns 1 if handled, 0 if the configuration is not eligible, < 0 on error.
+int try_dense_trajectory(ahmc_ctx* ctx, const ahmc_model* model, LeapfrogArgs& a, int n_abs, double eps, double temper_alpha,
+                         bool compat, int* nl) {
+    const int D = a.D;
+    const long long N = a.N;
+    const bool gauss = model->kind == AHMC_MODEL_STD_NORMAL || model->kind == AHMC_MODEL_DIAG_GAUSS ||
+                       model->kind == AHMC_MODEL_DENSE_GAUSS;
+    const bool metric_ok = a.metric.kind != AHMC_METRIC_DIAG || a.metric.chain_stride == 0;
+    const bool has_dense = model->kind == AHMC_MODEL_DENSE_GAUSS || a.metric.kind == AHMC_METRIC_DENSE;
+    int Dp, RB, CB;
+    if (!(gauss && metric_ok && has_dense && !compat && !(a.flags & AHMC_FLAG_EXACT_CHECKS) && !(temper_alpha > 0.0) &&
+          dense_tile_shape(D, &Dp, &RB, &CB) && (model->kind != AHMC_MODEL_DENSE_GAUSS || model->d_p1_pad)))
+        return 0;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t need = al((size_t)Dp * Dp * 8) + al(16) + al((size_t)N);
+    if (need > ctx->dense_scratch_bytes) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->dense_scratch);
+        ctx->dense_scratch = nullptr;
+        ctx->dense_scratch_bytes = 0;
+        if (cudaMalloc((void**)&ctx->dense_scratch, need) != cudaSuccess)
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc(%zu) for the dense workspace failed", need);
+        ctx->dense_scratch_bytes = need;
+    }
+    double* Mpad = (double*)ctx->dense_scratch;
+    double* norms = (double*)(ctx->dense_scratch + al((size_t)Dp * Dp * 8));
+    uint8_t* mask = (uint8_t*)(ctx->dense_scratch + al((size_t)Dp * Dp * 8) + al(16));
+    DenseTrajHost h{};
+    h.D = D; h.Dp = Dp; h.N = N; h.c0 = model->c0;
+    h.mu = (model->kind == AHMC_MODEL_STD_NORMAL) ? nullptr : model->d_p0;
+    if (model->kind == AHMC_MODEL_DENSE_GAUSS) {
+        h.P = model->d_p1_pad;
+        CU(cudaMemcpyAsync(norms + 1, model->d_p1_pad + (size_t)Dp * Dp, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        h.w = (model->kind == AHMC_MODEL_DIAG_GAUSS) ? model->d_p1 : nullptr;
+        CU(launch_vec_norm(h.w, D, norms + 1, ctx->stream));
+        *nl += 1;
+    }
+    if (a.metric.kind == AHMC_METRIC_DENSE) {
+        CU(launch_pad_norm(a.metric.Minv, D, Dp, Mpad, norms, ctx->stream));
+        h.Minv = Mpad;
+    } else {
+        h.Mdiag = (a.metric.kind == AHMC_METRIC_DIAG) ? a.metric.Minv : nullptr;
+        CU(launch_vec_norm(h.Mdiag, D, norms, ctx->stream));
+    }
+    *nl += 1;
+    h.norms = norms;
+    h.eps = eps; h.eps_chain = a.eps_chain; h.n_steps = n_abs; h.fwd = a.fwd;
+    h.th_in = a.th_in; h.r_in = a.r_in; h.g_in = a.g_in; h.ld_in = a.ld_in;
+    h.th_out = a.th_out; h.r_out = a.r_out; h.g_out = a.g_out; h.dr_out = a.dr_out;
+    h.lp_out = a.lp_out; h.lk_out = a.lk_out; h.ld_out = a.ld_out;
+    h.status = a.status; h.steps_done = a.steps_done; h.need_exact = mask;
+    CU(launch_dense_traj(h, ctx->stream, nl));
+    LeapfrogArgs b = a;
+    b.n_steps = n_abs;
+    b.only_mask = mask;
+    b.min_break = nullptr;
+    CU(launch_leapfrog(b, ctx->stream, nl));
+    return 1;
+}
 }  // namespace
 
 // =================================================================================================
@@ -335,6 +402,7 @@ int ahmc_destroy(ahmc_ctx* ctx) {
     cudaFree(ctx->nuts_scratch);
     cudaFree(ctx->adapt_scratch);
     cudaFree(ctx->mn_scratch);
+    cudaFree(ctx->dense_scratch);
     cudaFree(ctx->split_scratch);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -389,6 +457,15 @@ int ahmc_model_create(ahmc_ctx* ctx, int32_t kind, int32_t D, const double* p0, 
         }
         cudaMemcpy(m->d_p0, p0, sizeof(double) * D, cudaMemcpyHostToDevice);
         cudaMemcpy(m->d_p1, p1, sizeof(double) * (size_t)D * D, cudaMemcpyHostToDevice);
+        int RB, CB;
+        if (dense_tile_shape(D, &m->Dp, &RB, &CB)) {  // padded copy + infinity norm for the tiled DMMA kernel
+            if (cudaMalloc((void**)&m->d_p1_pad, sizeof(double) * ((size_t)m->Dp * m->Dp + 2)) != cudaSuccess) {
+                ahmc_model_destroy(ctx, m);
+                return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc for the padded precision failed");
+            }
+            launch_pad_norm(m->d_p1, D, m->Dp, m->d_p1_pad, m->d_p1_pad + (size_t)m->Dp * m->Dp, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -419,6 +496,7 @@ int ahmc_model_destroy(ahmc_ctx* ctx, ahmc_model* m) {
         DeviceGuard g(ctx->device);
         cudaFree(m->d_p0);
         cudaFree(m->d_p1);
+        cudaFree(m->d_p1_pad);
     }
     delete m;
     return AHMC_OK;
@@ -666,6 +744,16 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
     a.flags = flags;
     const bool compat = flags & AHMC_FLAG_COMPAT_BREAK_ALL;
     a.min_break = nullptr;
+    a.only_mask = nullptr;
+    {
+        int nl2 = 0;
+        rc = try_dense_trajectory(ctx, model, a, n_abs, eps, temper_alpha, compat, &nl2);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            ctx->launches += nl2;
+            return finish_call(ctx, st, flags);
+        }
+    }
     if (model->kind == AHMC_MODEL_CALLBACK) {
         // split-step mode: the work state is the OUTPUT phase point; two small kernels + the user closure per step
         SplitWork w;
@@ -880,6 +968,54 @@ static int hmc_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* m
         ctx->launches += nl;
         return finish_call(ctx, st, flags);
     }
+    if (n_transitions == 1 && a.th_out != a.th_in && h.rng.partial_alpha == 0.0 && !draws &&
+        (model->kind == AHMC_MODEL_DENSE_GAUSS || a.metric.kind == AHMC_METRIC_DENSE)) {
+        // GEMM-shaped operators: refresh -> tiled DMMA trajectory (in place on z_out) -> MH select; same semantics as
+        // hmc_kernel.  (Falls through to the fused generic kernel when the tile kernel is not eligible.)
+        SplitWork w;
+        if ((rc = split_workspace(ctx, D, N, z_out->ld, &w))) return rc;
+        LeapfrogArgs t = a;
+        t.th_in = a.th_out; t.r_in = a.r_out; t.g_in = a.g_out; t.ld_in = a.ld_out;
+        t.status = nullptr; t.steps_done = nullptr; t.only_mask = nullptr; t.min_break = nullptr;
+        const bool gauss = model->kind != AHMC_MODEL_FUNNEL && model->kind != AHMC_MODEL_CALLBACK;
+        const bool metric_ok = a.metric.kind != AHMC_METRIC_DIAG || a.metric.chain_stride == 0;
+        int Dp_, RB_, CB_;
+        if (gauss && metric_ok && !(flags & AHMC_FLAG_EXACT_CHECKS) && dense_tile_shape(D, &Dp_, &RB_, &CB_)) {
+            if (h.refresh) {
+                MomentumArgs ma{};
+                ma.metric = a.metric; ma.D = D; ma.N = N; ma.seed = h.rng.seed; ma.offset = h.rng.offset;
+                ma.normal_tape = h.rng.normal_tape; ma.r = w.r0; ma.ld = D;
+                CU(launch_rand_momentum(ma, ctx->stream, &nl));
+            } else {
+                CU(cudaMemcpy2DAsync(w.r0, (size_t)D * 8, a.r_in, (size_t)a.ld_in * 8, (size_t)D * 8, (size_t)N,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            SplitArgs k0{};
+            k0.metric = a.metric; k0.D = D; k0.N = N; k0.fwd = 1; k0.mul = 1.0; k0.no_kick = 1;
+            k0.r = w.r0; k0.lk = w.lk0; k0.ld = D;
+            CU(launch_kick_energy(k0, ctx->stream, &nl));
+            auto cp = [&](double* dst, const double* src, int64_t lds) -> cudaError_t {
+                return cudaMemcpy2DAsync(dst, (size_t)a.ld_out * 8, src, (size_t)lds * 8, (size_t)D * 8, (size_t)N,
+                                         cudaMemcpyDeviceToDevice, ctx->stream);
+            };
+            CU(cp(a.th_out, a.th_in, a.ld_in));
+            CU(cp(a.g_out, a.g_in, a.ld_in));
+            CU(cp(a.r_out, w.r0, D));
+            rc = try_dense_trajectory(ctx, model, t, n_steps, eps, 0.0, false, &nl);
+            if (rc < 0) return rc;
+            if (rc == 1) {
+                MhArgs m{};
+                m.D = D; m.N = N; m.n_steps = n_steps;
+                m.th0 = a.th_in; m.g0 = a.g_in; m.lp0 = a.lp_in; m.ld0 = a.ld_in;
+                m.r0 = w.r0; m.lk0 = w.lk0;
+                m.th = a.th_out; m.r = a.r_out; m.g = a.g_out; m.lp = a.lp_out; m.lk = a.lk_out; m.ld = a.ld_out;
+                m.rng = h.rng; m.st = h.st;
+                CU(launch_mh_select(m, ctx->stream, &nl));
+                ctx->launches += nl;
+                return finish_call(ctx, st, flags);
+            }
+        }
+    }
     CU(launch_hmc(h, ctx->stream, &nl));
     ctx->launches += nl;
     return finish_call(ctx, st, flags);
@@ -1063,6 +1199,7 @@ int ahmc_hmc_multinomial_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, 
     if (need > ctx->mn_scratch_bytes) {
         CU(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->mn_scratch);
+    cudaFree(ctx->dense_scratch);
         ctx->mn_scratch = nullptr;
         ctx->mn_scratch_bytes = 0;
         if (cudaMalloc((void**)&ctx->mn_scratch, need) != cudaSuccess)

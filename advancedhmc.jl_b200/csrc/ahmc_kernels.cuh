@@ -22,6 +22,7 @@ struct LeapfrogArgs {
     int32_t* steps_done;
     int* min_break;  // device int: atomicMin of the first non-finite step over all chains (COMPAT_BREAK_ALL)
     uint32_t flags;
+    const uint8_t* only_mask;  // nullable: process only chains whose mask byte is non-zero (K4 exact fallback)
 };
 
 struct PhasepointArgs {
@@ -167,6 +168,33 @@ struct MultinomialArgs {  // static transition with MultinomialTS (trajectory.jl
     StatsDev st;
     double* energies;  // (n_steps + 1) doubles per chain
 };
+
+// K4 (ahmc_dense.cu): tiled DMMA trajectory for dense metric / dense-Gaussian target
+struct DenseTrajHost {
+    int D, Dp;
+    long long N;
+    const double* P;      // padded Dp x Dp precision or nullptr
+    const double* w;      // 1/s^2 (DIAG_GAUSS) or nullptr
+    const double* mu;
+    double c0;
+    const double* Minv;   // padded Dp x Dp or nullptr
+    const double* Mdiag;  // D or nullptr
+    const double* norms;  // device: [|Minv|_inf, |P|_inf]
+    double eps;
+    const double* eps_chain;
+    int n_steps, fwd;
+    const double *th_in, *r_in, *g_in;
+    long long ld_in;
+    double *th_out, *r_out, *g_out, *dr_out, *lp_out, *lk_out;
+    long long ld_out;
+    uint32_t* status;
+    int32_t* steps_done;
+    uint8_t* need_exact;
+};
+bool dense_tile_shape(int D, int* Dp, int* RB, int* CB);
+cudaError_t launch_dense_traj(const DenseTrajHost& h, cudaStream_t stream, int* n_launches);
+cudaError_t launch_pad_norm(const double* A, int D, int Dp, double* Ap, double* norm, cudaStream_t st);
+cudaError_t launch_vec_norm(const double* v, int D, double* norm, cudaStream_t st);
 
 // choose (G, E) for a dimension: returns false if D is out of the register-resident range
 bool pick_layout(int D, int* G, int* E);

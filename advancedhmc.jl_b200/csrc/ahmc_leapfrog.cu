@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC
     const int l = threadIdx.x % G;
     const int grp_in_block = threadIdx.x / G;
     const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + grp_in_block;
-    const bool valid = chain0 < a.N;
-    const long long chain = valid ? chain0 : a.N - 1;  // tail groups shadow the last chain, never store
+    const long long chain = chain0 < a.N ? chain0 : a.N - 1;  // tail groups shadow the last chain, never store
+    const bool valid = chain0 < a.N && (!a.only_mask || a.only_mask[chain] != 0);
     double* xs = smem + (size_t)grp_in_block * a.D;
     double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
     eps = a.fwd ? eps : -eps;  // integrator.jl:226

@@ -726,3 +726,45 @@ def test_multinomial_static_sampling_moments_philox():
     th = z.theta.cpu().numpy()
     assert np.abs(th.mean(axis=0) - m).max() < 0.15 and np.abs(th.std(axis=0) - s).max() < 0.15
     assert len(nf) > 5 and tr.stat["acceptance_rate"].mean().item() > 0.8
+
+
+# ------------------------------------------------------------------------------------------------ K4 tiled DMMA path
+@pytest.mark.parametrize("model,metric", [("dense_gauss", "diag"), ("dense_gauss", "dense"), ("diag_gauss", "dense"),
+                                          ("std_normal", "dense"), ("dense_gauss", "unit")])
+@pytest.mark.parametrize("D,N", [(128, 333), (100, 70), (256, 40), (30, 517), (320, 19)])
+def test_dense_tile_kernel_vs_oracle(model, metric, D, N):
+    """GEMM-shaped operators run on the tiled fp64-MMA kernel (ahmc_dense.cu): ragged tiles, padded D, per-chain eps,
+    backward steps, and one chain that forces its tile back onto the exact path."""
+    rng = np.random.default_rng(D * 3 + N)
+    p0 = p1 = Minv = None
+    if model == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.5, 0.5, D))
+    elif model == "dense_gauss":
+        B = rng.normal(size=(D, D))
+        p0, p1 = rng.normal(size=D), B @ B.T / D + np.eye(D)
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    elif metric == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+    th, r = rng.normal(size=(D, N)), rng.normal(size=(D, N))
+    th[3 % D, N // 2] = 1e250  # energy overflow at step 1: that chain freezes, its tile goes to the exact kernel
+    eps = 0.03 * np.exp(rng.uniform(-0.3, 0.3, N))
+    om, ome = oc.Model(MODEL_KINDS[model], D, p0, p1, 0.3), oc.Metric(METRIC_KINDS[metric], Minv)
+    z0o = oc.phasepoint(om, ome, th, r)
+    h = A.Hamiltonian(make_metric(metric, Minv, D), make_target(model, D, p0, p1, 0.3))
+    z0 = A.phasepoint(h, T(th), T(r))
+    for n in (7, -4):
+        zo, st_o, dn_o = oc.leapfrog(om, ome, eps, z0o, n)
+        z1, info = A.step(A.Leapfrog(torch.as_tensor(eps, device=DEV)), h, z0, n, return_info=True)
+        assert (F(info.steps_done) == dn_o).all() and dn_o[N // 2] == 1
+        assert (F(info.status) == st_o).all()
+        ok = [c for c in range(N) if c != N // 2]
+        for f, got in [("theta", z1.theta), ("r", z1.r), ("lp_gradient", z1.lp.gradient), ("lk_gradient", z1.lk.gradient)]:
+            assert rel_err(F(got)[:, ok], getattr(zo, f)[:, ok]) < TOL, f
+        assert rel_err(F(z1.lp.value)[ok], zo.lp_value[ok]) < TOL and rel_err(F(z1.lk.value)[ok], zo.lk_value[ok]) < TOL
+    # the tile path and the exact path agree to rounding
+    ze = A.step(A.Leapfrog(torch.as_tensor(eps, device=DEV)), h, z0, 7, flags=A.FLAG_EXACT_CHECKS)
+    z1 = A.step(A.Leapfrog(torch.as_tensor(eps, device=DEV)), h, z0, 7)
+    ok = [c for c in range(N) if c != N // 2]
+    assert rel_err(F(z1.theta)[:, ok], F(ze.theta)[:, ok]) < 1e-12
