@@ -10,7 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_obj")
+OBJ = os.environ.get("AHMC_OBJ_DIR", "/tmp/ahmc_b200_obj")  # objects stay out of the repo snapshot
 LIB = os.path.join(HERE, "libahmc_b200.so")
 SOURCES = ["ahmc_api.cu", "ahmc_leapfrog.cu", "ahmc_nuts.cu", "ahmc_adapt.cu", "ahmc_multinomial.cu", "ahmc_dense.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -75,6 +75,7 @@ struct DeviceGuard {
         cudaGetDevice(&prev);
         if (prev != dev) cudaSetDevice(dev);
         else prev = -1;
+        cudaGetLastError();  // a stale error left by another library on this thread must not be blamed on our launches
     }
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);
@@ -1199,7 +1200,6 @@ int ahmc_hmc_multinomial_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, 
     if (need > ctx->mn_scratch_bytes) {
         CU(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->mn_scratch);
-    cudaFree(ctx->dense_scratch);
         ctx->mn_scratch = nullptr;
         ctx->mn_scratch_bytes = 0;
         if (cudaMalloc((void**)&ctx->mn_scratch, need) != cudaSuccess)

@@ -9,6 +9,8 @@
 //    z, zs_fwd...)`); here only the n+1 ENERGIES are kept (per-chain scratch), the index is selected, and the
 //    chosen point is re-materialised by re-running that many steps from z: same arithmetic, same bits, no
 //    O(n * D) trajectory storage.
+#include <cstdio>
+
 #include "ahmc_kernels.cuh"
 
 namespace ahmc {
@@ -233,7 +235,15 @@ static cudaError_t launch_mn_t(const MultinomialArgs& a, cudaStream_t st) {
         if (e != cudaSuccess) return e;
     }
     multinomial_kernel<MODEL, METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
-    return cudaGetLastError();
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        cudaFuncAttributes fa{};
+        cudaError_t ae = cudaFuncGetAttributes(&fa, multinomial_kernel<MODEL, METRIC, G, E>);
+        fprintf(stderr, "[ahmc] multinomial launch failed: %s | model=%d metric=%d G=%d E=%d blocks=%lld smem=%zu stream=%p | attr: %s regs=%d "
+                        "static_smem=%zu maxthreads=%d\n", cudaGetErrorString(le), MODEL, METRIC, G, E, blocks, sm, (void*)st,
+                cudaGetErrorString(ae), fa.numRegs, fa.sharedSizeBytes, fa.maxThreadsPerBlock);
+    }
+    return le;
 }
 
 #define AHMC_LAYOUTS(FN, ...)                                          \

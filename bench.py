@@ -313,6 +313,28 @@ def run_ours(args):
             k2 = {"workload": "HMC transition (Philox refresh + 32 fused steps + MH), 4096x128, L2-warm",
                   "ms": e0.elapsed_time(e1) / 10, "rate_steps_dims_per_s": units_per_step / (e0.elapsed_time(e1) / 10) * 1e3}
 
+        # ---- K4: correlated (dense-precision) Gaussian target, Diag metric, same batch: fp64 tensor-MMA trajectory
+        k4 = None
+        if rank == 0 and not args.no_extras:
+            rng4 = np.random.Generator(np.random.PCG64(SEED))
+            Q, _ = np.linalg.qr(rng4.normal(size=(DIM, DIM)))
+            lam = np.exp(np.linspace(np.log(0.1), np.log(10.0), DIM))
+            hd = A.Hamiltonian(A.DiagEuclideanMetric(np.diag((Q * lam) @ Q.T).copy()), A.DenseGaussian(np.zeros(DIM), (Q / lam) @ Q.T))
+            zd = A.phasepoint(hd, torch.as_tensor(th, device=dev), torch.as_tensor(r, device=dev))
+            pd = A.StepPlan(A.Leapfrog(0.02), hd, zd, L_STEPS, flags=A.FLAG_ASYNC)
+            for _ in range(3):
+                pd()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(10):
+                pd()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            flops = 2.0 * DIM * DIM * N_CHAINS * L_STEPS
+            k4 = {"workload": "C2-style: 4096 chains x D=128 correlated Gaussian (dense precision), Diag metric, L=32 fused, tiled DMMA kernel",
+                  "ms_per_launch": ms, "rate_steps_dims_per_s": units_per_step / ms * 1e3, "fp64_tflops_gemm": flops / ms / 1e9}
+
     # ---- e2e: the public call with HOST (pinned) buffers, copies inside the timed region
     thp = torch.as_tensor(th).pin_memory()
     rp = torch.as_tensor(r).pin_memory()
@@ -389,6 +411,8 @@ def run_ours(args):
         line["roofline_hbm_honest"] = honest
     if k2:
         line["hmc_transition"] = k2
+    if k4:
+        line["dense_target_trajectory"] = k4
     args.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -761,7 +761,7 @@ def test_dense_tile_kernel_vs_oracle(model, metric, D, N):
         assert (F(info.status) == st_o).all()
         ok = [c for c in range(N) if c != N // 2]
         for f, got in [("theta", z1.theta), ("r", z1.r), ("lp_gradient", z1.lp.gradient), ("lk_gradient", z1.lk.gradient)]:
-            assert rel_err(F(got)[:, ok], getattr(zo, f)[:, ok]) < TOL, f
+            assert rel_err(F(got)[:, ok], getattr(zo, f)[:, ok]) < TOL, (f, n)
         assert rel_err(F(z1.lp.value)[ok], zo.lp_value[ok]) < TOL and rel_err(F(z1.lk.value)[ok], zo.lk_value[ok]) < TOL
     # the tile path and the exact path agree to rounding
     ze = A.step(A.Leapfrog(torch.as_tensor(eps, device=DEV)), h, z0, 7, flags=A.FLAG_EXACT_CHECKS)
