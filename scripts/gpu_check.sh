@@ -18,3 +18,7 @@ if [ "${1:-}" = "prof" ]; then
   ncu -i /tmp/k1.ncu-rep --page details > gpurun_out/k1_headline_details.txt 2>> gpurun_out/prof.log
 fi
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+if [ "${2:-}" = "configs" ]; then
+  timeout 900 python scripts/run_configs.py c1 c2 c3 2>&1 | grep -v Warn > gpurun_out/configs_1gpu.log
+  cat gpurun_out/configs_1gpu.log
+fi
