@@ -6,6 +6,7 @@ Product path = libahmc_b200.so (CUDA kernels + C ABI) + this thin host mirror.  
 """
 from . import _lib
 from ._lib import (FLAG_ASYNC, FLAG_COMPAT_BREAK_ALL, FLAG_EXACT_CHECKS, FLAG_HOST_BUFFERS, FLAG_NO_REFRESH,
+                   FLAG_NUTS_CLASSIC, FLAG_NUTS_SLICE_TS, FLAG_NUTS_STRICT,
                    STATUS_NONFINITE, AhmcError, InvalidArgument)
 from .core import *  # noqa: F401,F403
 from .core import get_context

@@ -648,6 +648,10 @@ class MultinomialTS:
     pass
 
 
+class SliceTS:
+    """Slice trajectory sampler (trajectory.jl:102-109); dynamic trajectories only."""
+
+
 @dataclass(frozen=True)
 class FixedNSteps:
     L: int
@@ -662,6 +666,39 @@ class FixedIntegrationTime:
 class GeneralisedNoUTurn:
     max_depth: int = 10
     delta_max: float = 1000.0
+
+
+@dataclass(frozen=True)
+class ClassicNoUTurn:
+    """trajectory.jl:240-250, isterminated at :551-557."""
+    max_depth: int = 10
+    delta_max: float = 1000.0
+
+
+@dataclass(frozen=True)
+class StrictGeneralisedNoUTurn:
+    """trajectory.jl:272-282, isterminated at :579-613."""
+    max_depth: int = 10
+    delta_max: float = 1000.0
+
+
+_DYNAMIC = (GeneralisedNoUTurn, ClassicNoUTurn, StrictGeneralisedNoUTurn)
+
+
+def _nuts_flags(tau):
+    """Flag bits selecting the trajectory sampler / criterion of a dynamic trajectory."""
+    if tau.sampler is MultinomialTS:
+        fl = 0
+    elif tau.sampler is SliceTS:
+        fl = L.FLAG_NUTS_SLICE_TS
+    else:
+        raise L.AhmcError(L.ERR_UNSUPPORTED, "dynamic trajectories: MultinomialTS or SliceTS")
+    tc = tau.termination_criterion
+    if isinstance(tc, ClassicNoUTurn):
+        fl |= L.FLAG_NUTS_CLASSIC
+    elif isinstance(tc, StrictGeneralisedNoUTurn):
+        fl |= L.FLAG_NUTS_STRICT
+    return fl
 
 
 @dataclass(frozen=True)
@@ -747,14 +784,13 @@ def transition(rng, h: Hamiltonian, kappa: Union[HMCKernel, Trajectory], z: Phas
     rc, keep3 = rng._c()
     rc.partial_refresh_alpha = _refresh_alpha(kappa)
     tc = tau.termination_criterion
-    nuts = isinstance(tc, GeneralisedNoUTurn)
+    nuts = isinstance(tc, _DYNAMIC)
     st, sc = _stats_buffers(z.theta, N, nuts or tau.sampler is MultinomialTS)
     fl = flags | (L.FLAG_HOST_BUFFERS if host else 0)
     _sync_torch(z.theta)
     zc, oc = z._c(False), out._c(False)
     if nuts:
-        if tau.sampler is not MultinomialTS:
-            raise L.AhmcError(L.ERR_UNSUPPORTED, "only MultinomialTS is built for dynamic trajectories")
+        fl |= _nuts_flags(tau)
         ctx.check(ctx.lib.ahmc_nuts_transition_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, e, ep,
                                                    tc.max_depth, tc.delta_max, C.byref(rc), C.byref(zc),
                                                    C.byref(oc), C.byref(sc), fl))
@@ -833,13 +869,14 @@ def sample_transitions(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: Phas
     rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0, _refresh_alpha(kappa))
     rng.offset += n_transitions
     tc = tau.termination_criterion
-    nuts = isinstance(tc, GeneralisedNoUTurn)
+    nuts = isinstance(tc, _DYNAMIC)
     st, sc = _stats_buffers(z.theta, N, nuts, T=n_transitions)
     draws = _like(z.theta, (n_transitions, N, D)) if keep_draws else None
     fl = flags | (L.FLAG_HOST_BUFFERS if host else 0)
     _sync_torch(z.theta)
     zc, oc = z._c(False), out._c(False)
     if nuts:
+        fl |= _nuts_flags(tau)
         ctx.check(ctx.lib.ahmc_nuts_sample_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, e, ep, tc.max_depth,
                                                tc.delta_max, n_transitions, C.byref(rc), C.byref(zc), C.byref(oc),
                                                _ptr(draws), C.byref(sc), fl))

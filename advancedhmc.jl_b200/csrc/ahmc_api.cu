@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -623,7 +624,9 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
     CU(cudaStreamWaitEvent(ss[1], ctx->ev_a, 0));
 
     const int n_abs = n_steps < 0 ? -n_steps : n_steps;
-    int64_t chunk = (N + 7) / 8;                 // 8 chunks, at least 512 chains each
+    int nchunk = 4;                              // default 4 chunks (>= 512 chains each): host issue rate ~3-4 us per call
+    if (const char* e = getenv("AHMC_PIPE_CHUNKS")) nchunk = atoi(e) > 0 ? atoi(e) : nchunk;
+    int64_t chunk = (N + nchunk - 1) / nchunk;
     if (chunk < 512) chunk = 512;
     chunk = (chunk + 3) & ~(int64_t)3;
     int nl = 0, k = 0;
@@ -1037,6 +1040,8 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
     if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
     if (max_depth < 0 || max_depth > 20) return fail(ctx, AHMC_ERR_INVALID, "max_depth must be in 0..20");
+    if ((flags & AHMC_FLAG_NUTS_CLASSIC) && (flags & AHMC_FLAG_NUTS_STRICT))
+        return fail(ctx, AHMC_ERR_INVALID, "AHMC_FLAG_NUTS_CLASSIC and AHMC_FLAG_NUTS_STRICT are mutually exclusive");
     if (model->kind == AHMC_MODEL_CALLBACK)
         return fail(ctx, AHMC_ERR_UNSUPPORTED, "NUTS needs a device-resident target: callback (split-step) models are supported by ahmc_leapfrog_f64 / ahmc_hmc_transition_f64 / ahmc_phasepoint_f64 only");
     if (metric->kind == AHMC_METRIC_DENSE && !metric->cholU && !(flags & AHMC_FLAG_NO_REFRESH))
@@ -1067,6 +1072,8 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     if ((rc = st.in(eps_chain, (size_t)N, &a.eps_chain))) return rc;
     a.max_depth = max_depth;
     a.delta_max = delta_max;
+    a.sampler = (flags & AHMC_FLAG_NUTS_SLICE_TS) ? 1 : 0;
+    a.criterion = (flags & AHMC_FLAG_NUTS_STRICT) ? 2 : (flags & AHMC_FLAG_NUTS_CLASSIC) ? 1 : 0;
     a.refresh = (flags & AHMC_FLAG_NO_REFRESH) ? 0 : 1;
     a.ld_in = z_in->ld;
     a.ld_out = z_out->ld;

@@ -85,6 +85,8 @@ struct NutsArgs {
     const double* eps_chain;
     int max_depth;
     double delta_max;
+    int sampler;    // 0 MultinomialTS, 1 SliceTS
+    int criterion;  // 0 GeneralisedNoUTurn, 1 ClassicNoUTurn, 2 StrictGeneralisedNoUTurn
     RngDev rng;
     int refresh;
     const double *th_in, *r_in, *g_in, *lp_in;

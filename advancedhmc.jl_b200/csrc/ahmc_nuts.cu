@@ -23,10 +23,11 @@
 
 namespace ahmc {
 
-// workspace layout per chain (doubles): LEFT edge (theta,r,g) | RIGHT edge | rho_tree | per level k:
-// rho, rfirst, cand theta, cand r, cand g
+// workspace layout per chain (doubles): LEFT edge (theta,r,g) | RIGHT edge | rho_tree | per level k (7 vectors):
+// 0 rho, 1 rfirst, 2 cand theta, 3 cand r, 4 cand g, 5 rlast (Strict), 6 theta_first (Classic)
+constexpr int kLevelVecs = 7;
 long long nuts_scratch_doubles_per_chain(int D, int max_depth) {
-    return (long long)(7 + 5 * (max_depth > 0 ? max_depth : 1)) * D;
+    return (long long)(7 + kLevelVecs * (max_depth > 0 ? max_depth : 1)) * D;
 }
 
 __device__ __forceinline__ double jl_min0(double x) {  // min(0, x), NaN-propagating like Julia
@@ -49,8 +50,14 @@ constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, ca
 template <int E>
 constexpr int nuts_min_blocks() { return E <= 4 ? AHMC_NUTS_MINB : (E <= 8 ? 2 : 1); }
 
-template <int MODEL, int METRIC, int G, int E>
+// VAR = false: MultinomialTS + GeneralisedNoUTurn only (what `NUTS(delta)` builds); VAR = true additionally compiles
+// SliceTS (trajectory.jl:102-109,144-145,164-166,178-189,202,500-502) and the Classic / StrictGeneralised criteria
+// (trajectory.jl:551-557, 579-613), selected at run time by a.sampler / a.criterion.
+template <int MODEL, int METRIC, int G, int E, bool VAR>
 __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kernel(const NutsArgs a) {
+    const int samp = VAR ? a.sampler : 0;    // 0 MultinomialTS, 1 SliceTS
+    const int crit = VAR ? a.criterion : 0;  // 0 Generalised, 1 Classic, 2 StrictGeneralised
+    double lu = 0.0;                         // SliceTS slice variable (log space)
     extern __shared__ double smem[];
     const int l = threadIdx.x % G;
     const int grp_in_block = threadIdx.x / G;
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     double* LEFT = base;
     double* RIGHT = base + 3 * (long long)D;
     double* RHO = base + 6 * (long long)D;
-    auto level = [&](int k) { return base + (7 + 5 * (long long)k) * D; };
+    auto level = [&](int k) { return base + (7 + kLevelVecs * (long long)k) * D; };
 
     const double eps_c = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
 
@@ -89,6 +96,11 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         int k = nexp++;
         if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
         return philox_exp(a.rng.seed, off, chain, k);
+    };
+    auto next_unif = [&]() -> double {  // SliceTS draws rand(rng) where MultinomialTS draws randexp(rng); same counter
+        int k = nexp++;
+        if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
+        return exp(-philox_exp(a.rng.seed, off, chain, k));
     };
     auto next_dir = [&]() -> bool {
         int k = ndir++;
@@ -161,6 +173,10 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 vstore<G, E>(a.r_out + a.ld_out * chain, s.r, l, D);
                 vstore<G, E>(a.g_out + a.ld_out * chain, s.g, l, D);
                 lw_tree = 0.0;
+                if (VAR && samp == 1) {  // SliceTS(rng, z0) = SliceTS(z0, neg_energy(z0) - randexp(rng), 1) (:144-145)
+                    lu = (s.lp + s.lk) - next_exp();
+                    lw_tree = 1.0;  // n = 1
+                }
                 sa_tree = 0.0;
                 dh_tree = 0.0;
                 na_tree = 0;
@@ -230,6 +246,10 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         double sa_c = exp(jl_min0(-dH));                     // alpha' = exp(min(0, -dH))
         double na_c = 1.0, dh_c = dH;
         bool tnum_c = !(-H0 < a.delta_max + -H1);            // Termination(...) (:503-507)
+        if (VAR && samp == 1) {
+            lw_c = (lu <= nE) ? 1.0 : 0.0;                   // SliceTS(s, H0, z'): n = Int(lu <= neg_energy) (:164-166)
+            tnum_c = !(lu < a.delta_max + -H1);              // Termination(::SliceTS) (:500-502)
+        }
         bool tdyn_c = false;
         double rho_cur[E];
 #pragma unroll
@@ -254,36 +274,104 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 double rho_p[E], rf_p[E], t1[E];
 #pragma unroll
                 for (int e = 0; e < E; ++e) rho_p[e] = rf_p[e] = 0.0;
+                const double* L = level(k);
                 if (do_comb) {
-                    double* L = level(k);
                     if (k == 0) {
-                        vload_nc<G, E>(rho_p, L + 3 * (long long)D, l, D);  // level 0: rho = rfirst = cand r
+                        vload_nc<G, E>(rho_p, L + 3 * (long long)D, l, D);  // level 0: rho = rfirst = rlast = cand r
 #pragma unroll
                         for (int e = 0; e < E; ++e) rf_p[e] = rho_p[e];
                     } else {
                         vload_nc<G, E>(rho_p, L, l, D);
                         vload_nc<G, E>(rf_p, L + D, l, D);
                     }
+                }
+                bool uturn_extra = false;
+                if (VAR && crit == 2) {
+                    // StrictGeneralisedNoUTurn (:579-613).  F = first-built half (pending), S = second-built half (current).
+                    //   check A: rho = F.rho + S.rfirst, against dH/dr(F.rfirst), dH/dr(S.rfirst)
+                    //   check B: rho = S.rho + F.rlast,  against dH/dr(r_leaf),  dH/dr(F.rlast)
+                    // (v = +1: A = check_left_subtree, B = check_right_subtree; v = -1: the other way round)
+                    double rsf[E], rl_p[E], tA[E], tB[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) rsf[e] = rl_p[e] = 0.0;
+                    if (do_comb) {
+                        if (k == 0) {
+#pragma unroll
+                            for (int e = 0; e < E; ++e) {
+                                rsf[e] = s.r[e];      // S is the leaf itself
+                                rl_p[e] = rho_p[e];   // F is a single leaf
+                            }
+                        } else {
+                            const double* P = level(k - 1);
+                            vload_nc<G, E>(rsf, (k == 1) ? P + 3 * (long long)D : P + D, l, D);
+                            vload_nc<G, E>(rl_p, L + 5 * (long long)D, l, D);
+                        }
+                    }
+                    me.dHdr(rf_p, t1, xs, l);
+                    me.dHdr(rsf, tA, xs, l);
+                    me.dHdr(rl_p, tB, xs, l);
+                    double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const double ra = rho_p[e] + rsf[e];
+                        const double rb = rho_cur[e] + rl_p[e];
+                        a1 = fma(ra, t1[e], a1);
+                        a2 = fma(ra, tA[e], a2);
+                        b1 = fma(rb, dr[e], b1);
+                        b2 = fma(rb, tB[e], b2);
+                    }
+                    a1 = Grp<G>::sum(a1);
+                    a2 = Grp<G>::sum(a2);
+                    b1 = Grp<G>::sum(b1);
+                    b2 = Grp<G>::sum(b2);
+                    uturn_extra = (a1 <= 0.0) || (a2 <= 0.0) || (b1 <= 0.0) || (b2 <= 0.0);
+                }
+                if (do_comb) {
 #pragma unroll
                     for (int e = 0; e < E; ++e) rho_cur[e] += rho_p[e];  // combine(ts) (:467)
                 }
-                // isterminated(GeneralisedNoUTurn) on the merged node (:566-570, :615-617)
-                me.dHdr(rf_p, t1, xs, l);
                 double d1 = 0.0, d2 = 0.0;
+                bool uturn;
+                me.dHdr(rf_p, t1, xs, l);
+                if (VAR && crit == 1) {
+                    // ClassicNoUTurn (:551-557): s = dot(dtheta, dH/dr(-r_left)) >= 0 || dot(-dtheta, dH/dr(r_right)) >= 0
+                    // with dtheta = theta_right - theta_left; q = -dtheta
+                    double thf[E];
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    d1 = fma(rho_cur[e], t1[e], d1);
-                    d2 = fma(rho_cur[e], dr[e], d2);
+                    for (int e = 0; e < E; ++e) thf[e] = 0.0;
+                    if (do_comb) vload_nc<G, E>(thf, (k == 0) ? L + 2 * (long long)D : L + 6 * (long long)D, l, D);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const double q = (v > 0) ? (thf[e] - s.th[e]) : (s.th[e] - thf[e]);
+                        d1 = fma(q, t1[e], d1);
+                        d2 = fma(q, dr[e], d2);
+                    }
+                    d1 = Grp<G>::sum(d1);
+                    d2 = Grp<G>::sum(d2);
+                    uturn = (d1 >= 0.0) || (d2 >= 0.0);
+                } else {
+                    // isterminated(GeneralisedNoUTurn) on the merged node (:566-570, :615-617)
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        d1 = fma(rho_cur[e], t1[e], d1);
+                        d2 = fma(rho_cur[e], dr[e], d2);
+                    }
+                    d1 = Grp<G>::sum(d1);
+                    d2 = Grp<G>::sum(d2);
+                    uturn = (d1 <= 0.0) || (d2 <= 0.0) || uturn_extra;
                 }
-                d1 = Grp<G>::sum(d1);
-                d2 = Grp<G>::sum(d2);
                 if (do_comb) {
                     const double lw_p = LW[k], sa_p = SA[k], na_p = NA[k], dh_p = DH[k];
-                    const bool uturn = (d1 <= 0.0) || (d2 <= 0.0);
-                    const double lw = logaddexp(lw_p, lw_c);  // combine(rng, s1, s2) (:191-195)
-                    const double ex = next_exp();
-                    if (lw < lw_p + ex) cand_cur = k;  // keep the first-built half's candidate
-                    lw_c = lw;
+                    const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
+                    if (VAR && samp == 1) {  // combine(rng, s1::SliceTS, s2) (:178-183): n = n1 + n2; n*rand < n1 ? s1 : s2
+                        const double n = lw_p + lw_c;
+                        if (n * ex < lw_p) cand_cur = k;
+                        lw_c = n;
+                    } else {
+                        const double lw = logaddexp(lw_p, lw_c);  // combine(rng, s1, s2) (:191-195)
+                        if (lw < lw_p + ex) cand_cur = k;         // keep the first-built half's candidate
+                        lw_c = lw;
+                    }
                     sa_c = (v > 0) ? sa_p + sa_c : sa_c + sa_p;  // treeleft + treeright (:538)
                     na_c += na_p;
                     dh_c = (v > 0) ? maxabs(dh_p, dh_c) : maxabs(dh_c, dh_p);
@@ -301,6 +389,11 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                         vload_nc<G, E>(t, (k == 1) ? P + 3 * (long long)D : P + D, l, D);
                         vstore<G, E>(L + D, t, l, D);
                         vstore<G, E>(L, rho_cur, l, D);
+                        if (VAR && crit == 2) vstore<G, E>(L + 5 * (long long)D, s.r, l, D);  // rlast = the current leaf
+                        if (VAR && crit == 1) {                                                // theta of the first-built leaf
+                            vload_nc<G, E>(t, (k == 1) ? P + 2 * (long long)D : P + 6 * (long long)D, l, D);
+                            vstore<G, E>(L + 6 * (long long)D, t, l, D);
+                        }
                     }
                     double clp, clk;
                     if (cand_cur < 0) {
@@ -342,8 +435,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             bool accept = false;
             if (complete && !sub_term) {
                 j = j + 1;
-                const double ex = next_exp();
-                accept = lw_tree < lw_c + ex;  // mh_accept (:204-206)
+                const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
+                accept = (VAR && samp == 1) ? (lw_tree * ex < lw_c)   // mh_accept(::SliceTS): s.n * rand < s'.n (:202)
+                                            : (lw_tree < lw_c + ex);  // mh_accept (:204-206)
             }
             if (accept) {  // zcand = sampler'.zcand
                 if (cand_cur < 0) {
@@ -369,34 +463,93 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             double rho_t[E], r_other[E], t1[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) rho_t[e] = r_other[e] = 0.0;
+            double* edge = (v < 0) ? LEFT : RIGHT;        // the edge that moves
+            const double* other = (v < 0) ? RIGHT : LEFT;
+            bool uturn_extra = false;
+            if (VAR && crit == 2) {
+                // StrictGeneralisedNoUTurn at the top level (:579-613), T = old tree, S = new subtree:
+                //   X: rho = T.rho + S.rfirst, against dH/dr(r_far),  dH/dr(S.rfirst)
+                //   Y: rho = r_near + S.rho,   against dH/dr(r_near), dH/dr(r_leaf)      (r_near = the edge being replaced)
+                double rhoT[E], rsf[E], rnear[E], rfar[E], tA[E], tB[E], tC[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) rhoT[e] = rsf[e] = rnear[e] = rfar[e] = 0.0;
+                if (complete) {
+                    vload_nc<G, E>(rhoT, RHO, l, D);
+                    vload_nc<G, E>(rnear, edge + D, l, D);
+                    vload_nc<G, E>(rfar, other + D, l, D);
+                    if (jsub == 0) {
+#pragma unroll
+                        for (int e = 0; e < E; ++e) rsf[e] = s.r[e];
+                    } else {
+                        const double* P = level(jsub - 1);
+                        vload_nc<G, E>(rsf, (jsub == 1) ? P + 3 * (long long)D : P + D, l, D);
+                    }
+                }
+                me.dHdr(rfar, tA, xs, l);
+                me.dHdr(rsf, tB, xs, l);
+                me.dHdr(rnear, tC, xs, l);
+                double x1 = 0.0, x2 = 0.0, y1 = 0.0, y2 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double rx = rhoT[e] + rsf[e];
+                    const double ry = rnear[e] + rho_cur[e];
+                    x1 = fma(rx, tA[e], x1);
+                    x2 = fma(rx, tB[e], x2);
+                    y1 = fma(ry, tC[e], y1);
+                    y2 = fma(ry, dr[e], y2);
+                }
+                x1 = Grp<G>::sum(x1);
+                x2 = Grp<G>::sum(x2);
+                y1 = Grp<G>::sum(y1);
+                y2 = Grp<G>::sum(y2);
+                uturn_extra = (x1 <= 0.0) || (x2 <= 0.0) || (y1 <= 0.0) || (y2 <= 0.0);
+            }
+            double th_other[E];
+            if (VAR && crit == 1) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) th_other[e] = 0.0;
+                if (complete) vload_nc<G, E>(th_other, other, l, D);
+            }
             if (complete) {
                 vload_nc<G, E>(rho_t, RHO, l, D);
 #pragma unroll
                 for (int e = 0; e < E; ++e) rho_t[e] += rho_cur[e];
                 vstore<G, E>(RHO, rho_t, l, D);
-                double* edge = (v < 0) ? LEFT : RIGHT;
                 vstore<G, E>(edge, s.th, l, D);
                 vstore<G, E>(edge + D, s.r, l, D);
                 vstore<G, E>(edge + 2 * (long long)D, s.g, l, D);
-                const double* other = (v < 0) ? RIGHT : LEFT;
                 vload_nc<G, E>(r_other, other + D, l, D);
             }
             me.dHdr(r_other, t1, xs, l);
             double d1 = 0.0, d2 = 0.0;
+            bool uturn_top;
+            if (VAR && crit == 1) {  // ClassicNoUTurn on the whole tree: q = -(theta_right - theta_left)
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                d1 = fma(rho_t[e], t1[e], d1);
-                d2 = fma(rho_t[e], dr[e], d2);
+                for (int e = 0; e < E; ++e) {
+                    const double q = (v > 0) ? (th_other[e] - s.th[e]) : (s.th[e] - th_other[e]);
+                    d1 = fma(q, t1[e], d1);
+                    d2 = fma(q, dr[e], d2);
+                }
+                d1 = Grp<G>::sum(d1);
+                d2 = Grp<G>::sum(d2);
+                uturn_top = (d1 >= 0.0) || (d2 >= 0.0);
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    d1 = fma(rho_t[e], t1[e], d1);
+                    d2 = fma(rho_t[e], dr[e], d2);
+                }
+                d1 = Grp<G>::sum(d1);
+                d2 = Grp<G>::sum(d2);
+                uturn_top = (d1 <= 0.0) || (d2 <= 0.0) || uturn_extra;
             }
-            d1 = Grp<G>::sum(d1);
-            d2 = Grp<G>::sum(d2);
             if (complete) {
                 sa_tree = (v < 0) ? sa_c + sa_tree : sa_tree + sa_c;
                 na_tree += (int)na_c;
                 dh_tree = (v < 0) ? maxabs(dh_c, dh_tree) : maxabs(dh_tree, dh_c);
-                lw_tree = logaddexp(lw_tree, lw_c);  // combine(zcand, sampler, sampler') (:197-200, :717)
-                const bool uturn = (d1 <= 0.0) || (d2 <= 0.0);
-                term_dyn = term_dyn || tdyn_c || uturn;  // (:719-722)
+                lw_tree = (VAR && samp == 1) ? lw_tree + lw_c            // combine(zcand, s1::SliceTS, s2): n1 + n2 (:185-189)
+                                             : logaddexp(lw_tree, lw_c);  // combine(zcand, sampler, sampler') (:197-200, :717)
+                term_dyn = term_dyn || tdyn_c || uturn_top;  // (:719-722)
                 term_num = term_num || tnum_c;
                 in_sub = false;
                 if (term_dyn || term_num || !(j < a.max_depth)) done = true;
@@ -408,19 +561,24 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
 
 }
 
-template <int MODEL, int METRIC, int G, int E>
-static cudaError_t launch_nuts_t(const NutsArgs& a, cudaStream_t st) {
+template <int MODEL, int METRIC, int G, int E, bool VAR>
+static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;
     const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
     size_t sm = smem_bytes(MODEL, METRIC, a.D, G) + (size_t)chains_per_block * maxd * kLevelScalars * sizeof(double);
     if (sm > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E>,
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
     }
-    nuts_kernel<MODEL, METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    nuts_kernel<MODEL, METRIC, G, E, VAR><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
     return cudaGetLastError();
+}
+template <int MODEL, int METRIC, int G, int E>
+static cudaError_t launch_nuts_t(const NutsArgs& a, cudaStream_t st) {
+    if (a.sampler == 0 && a.criterion == 0) return launch_nuts_v<MODEL, METRIC, G, E, false>(a, st);
+    return launch_nuts_v<MODEL, METRIC, G, E, true>(a, st);
 }
 
 template <int MODEL, int METRIC>

@@ -380,7 +380,10 @@ def run_ours(args):
     fp64_ops = units_per_step * 2 * 2  # 2 DFMA per step*dim on the fast path
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "traffic": None, "peak_source": peak_src, "kernel": "leapfrog_kernel<DIAG_GAUSS,DIAG,G=32,E=4>",
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed `ncu --set full`
+        # capture (profiles/r01/k1_headline_details.txt): 12.61 MB read + 0 B written back by kernel end (outputs still
+        # dirty in L2) -- NOT re-measured inside this run
+        "traffic": 12607232, "peak_source": peak_src, "kernel": "leapfrog_kernel<DIAG_GAUSS,DIAG,G=32,E=4>",
         "kernel_ms": kernel_ms,
         "model": "SURVEY 8d streaming contract: (48+24/D) B per step*dim x N*D*L units per launch; the fused L-step "
                  "kernel keeps state in registers, so its COMPULSORY traffic is 1/L of that (next keys)",

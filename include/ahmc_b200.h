@@ -59,6 +59,10 @@ extern "C" {
 #define AHMC_FLAG_ASYNC 0x4u           /* do not synchronise the context stream before returning */
 #define AHMC_FLAG_EXACT_CHECKS 0x8u    /* force the per-step energy/finiteness path (disables the fused fast path) */
 #define AHMC_FLAG_NO_REFRESH 0x10u     /* transitions: keep z_in.r instead of drawing a new momentum */
+/* NUTS variants (ahmc_nuts_transition_f64 / ahmc_nuts_sample_f64 only; default = MultinomialTS + GeneralisedNoUTurn) */
+#define AHMC_FLAG_NUTS_SLICE_TS 0x20u  /* `SliceTS` trajectory sampler (src/trajectory.jl:102-109, 144-189, 202) */
+#define AHMC_FLAG_NUTS_CLASSIC 0x40u   /* `ClassicNoUTurn` criterion (src/trajectory.jl:551-557) */
+#define AHMC_FLAG_NUTS_STRICT 0x80u    /* `StrictGeneralisedNoUTurn` criterion (src/trajectory.jl:579-613) */
 
 /* per-chain status bits */
 #define AHMC_STATUS_NONFINITE 0x1u /* !isfinite(z) hit (integrator.jl:252-258) */
@@ -189,7 +193,10 @@ int ahmc_hmc_multinomial_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, 
                                         const ahmc_phasepoint* z_out, const ahmc_stats* stats, uint32_t flags);
 
 /* One NUTS transition per chain (MultinomialTS + GeneralisedNoUTurn = what `NUTS(delta)` builds,
- * src/abstractmcmc.jl:415-419): src/trajectory.jl:626-742, run one chain per warp-group. */
+ * src/abstractmcmc.jl:415-419): src/trajectory.jl:626-742, run one chain per warp-group.
+ * AHMC_FLAG_NUTS_SLICE_TS / _CLASSIC / _STRICT select the reference's other trajectory sampler and termination
+ * criteria (`HMCKernel(Trajectory{SliceTS}(integrator, ClassicNoUTurn()))` etc.).  With SliceTS the random tape
+ * rng->exp_tape holds, per chain, [randexp for the slice variable, then the rand() uniforms of each combine / mh_accept]. */
 int ahmc_nuts_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
                              double eps, const double* eps_chain, int32_t max_depth, double delta_max,
                              const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,

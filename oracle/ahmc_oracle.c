@@ -523,7 +523,7 @@ typedef struct {
 
 typedef struct {
     const pp_t* zcand;
-    double lw;
+    double lw; /* MultinomialTS: log weight; SliceTS: number of acceptable candidates n (as a double) */
 } sampler_t;
 
 typedef struct {
@@ -546,6 +546,9 @@ typedef struct {
     pp_t* pps;
     size_t pp_used, pp_cap;
     double* scratch; /* 2D */
+    int sampler;   /* 0 MultinomialTS, 1 SliceTS (trajectory.jl:102-136) */
+    int criterion; /* 0 GeneralisedNoUTurn, 1 ClassicNoUTurn, 2 StrictGeneralisedNoUTurn (trajectory.jl:414-452) */
+    double lu;     /* SliceTS slice variable */
 } nuts_ctx;
 
 static double* arena_alloc(nuts_ctx* x, size_t n) {
@@ -576,15 +579,43 @@ static term_t term_mul(term_t a, term_t b) { /* trajectory.jl:491-493 */
 }
 static int is_term(term_t t) { return t.dynamic || t.numerical; }
 
-/* isterminated(::GeneralisedNoUTurn, h, t) (trajectory.jl:566-570, 615-617) */
-static term_t uturn(nuts_ctx* x, const tree_t* t) {
+/* generalised_uturn_criterion(rho, p_sharp_minus, p_sharp_plus) (trajectory.jl:615-617) */
+static int gen_crit(nuts_ctx* x, const double* rho, const double* rminus, const double* rplus) {
     double* a = x->scratch;
     double dl = 0.0, dr_ = 0.0;
-    orc_dHdr(x->me, x->D, x->c, t->zleft->r, a);
-    for (int d = 0; d < x->D; ++d) dl += t->rho[d] * a[d];
-    orc_dHdr(x->me, x->D, x->c, t->zright->r, a);
-    for (int d = 0; d < x->D; ++d) dr_ += t->rho[d] * a[d];
-    term_t r = {(dl <= 0) || (dr_ <= 0), 0};
+    orc_dHdr(x->me, x->D, x->c, rminus, a);
+    for (int d = 0; d < x->D; ++d) dl += rho[d] * a[d];
+    orc_dHdr(x->me, x->D, x->c, rplus, a);
+    for (int d = 0; d < x->D; ++d) dr_ += rho[d] * a[d];
+    return (dl <= 0) || (dr_ <= 0);
+}
+
+/* isterminated(criterion, h, t, tleft, tright) (trajectory.jl:551-613) */
+static term_t uturn(nuts_ctx* x, const tree_t* t, const tree_t* tl, const tree_t* tr) {
+    term_t r = {0, 0};
+    const int D = x->D;
+    if (x->criterion == 1) { /* ClassicNoUTurn (trajectory.jl:551-557) */
+        double* a = x->scratch;
+        double* nr = x->scratch + D;
+        double s1 = 0.0, s2 = 0.0;
+        for (int d = 0; d < D; ++d) nr[d] = -t->zleft->r[d];
+        orc_dHdr(x->me, D, x->c, nr, a); /* dH/dr(h, -z0.r) */
+        for (int d = 0; d < D; ++d) s1 += (t->zright->theta[d] - t->zleft->theta[d]) * a[d];
+        orc_dHdr(x->me, D, x->c, t->zright->r, a);
+        for (int d = 0; d < D; ++d) s2 += (-(t->zright->theta[d] - t->zleft->theta[d])) * a[d];
+        r.dynamic = (s1 >= 0) || (s2 >= 0);
+        return r;
+    }
+    r.dynamic = gen_crit(x, t->rho, t->zleft->r, t->zright->r); /* :566-570 */
+    if (x->criterion == 2) { /* StrictGeneralisedNoUTurn (:579-613) */
+        double* rho = (double*)malloc(sizeof(double) * (size_t)D);
+        for (int d = 0; d < D; ++d) rho[d] = tl->rho[d] + tr->zleft->r[d]; /* check_left_subtree */
+        int s2 = gen_crit(x, rho, t->zleft->r, tr->zleft->r);
+        for (int d = 0; d < D; ++d) rho[d] = tl->zright->r[d] + tr->rho[d]; /* check_right_subtree */
+        int s3 = gen_crit(x, rho, tl->zright->r, t->zright->r);
+        free(rho);
+        r.dynamic = r.dynamic || s2 || s3;
+    }
     return r;
 }
 
@@ -610,9 +641,14 @@ static void build_tree(nuts_ctx* x, const pp_t* z, sampler_t sampler, int v, int
         tree_out->n_alpha = 1;
         tree_out->dH_max = dH;
         sampler_out->zcand = z1;
-        sampler_out->lw = H0 + (z1->lp + z1->lk); /* MultinomialTS(s,H0,zcand) :174-176 */
         term_out->dynamic = 0;
-        term_out->numerical = !(-H0 < x->delta_max + -H1); /* :503-507 */
+        if (x->sampler == 1) { /* SliceTS(s, H0, zcand) :164-166; Termination(::SliceTS) :500-502 */
+            sampler_out->lw = (x->lu <= (z1->lp + z1->lk)) ? 1.0 : 0.0;
+            term_out->numerical = !(x->lu < x->delta_max + -H1);
+        } else {
+            sampler_out->lw = H0 + (z1->lp + z1->lk); /* MultinomialTS(s,H0,zcand) :174-176 */
+            term_out->numerical = !(-H0 < x->delta_max + -H1); /* :503-507 */
+        }
         (void)sampler;
         return;
     }
@@ -642,11 +678,19 @@ static void build_tree(nuts_ctx* x, const pp_t* z, sampler_t sampler, int v, int
         t.sum_alpha = tl.sum_alpha + tr.sum_alpha;
         t.n_alpha = tl.n_alpha + tr.n_alpha;
         t.dH_max = maxabs(tl.dH_max, tr.dH_max);
-        /* combine(rng, sampler', sampler'') :191-195 */
-        double lw = logaddexp(s1.lw, s2.lw);
-        double ex = x->exps[x->n_exp++];
-        sampler_t s = {(lw < s1.lw + ex) ? s1.zcand : s2.zcand, lw};
-        e1 = term_mul(term_mul(e1, e2), uturn(x, &t)); /* :668-671 */
+        sampler_t s;
+        if (x->sampler == 1) { /* combine(rng, s1::SliceTS, s2) :178-183 */
+            double n = s1.lw + s2.lw;
+            double u = x->exps[x->n_exp++]; /* rand(rng) */
+            s.zcand = (n * u < s1.lw) ? s1.zcand : s2.zcand;
+            s.lw = n;
+        } else { /* combine(rng, sampler', sampler'') :191-195 */
+            double lw = logaddexp(s1.lw, s2.lw);
+            double ex = x->exps[x->n_exp++];
+            s.zcand = (lw < s1.lw + ex) ? s1.zcand : s2.zcand;
+            s.lw = lw;
+        }
+        e1 = term_mul(term_mul(e1, e2), uturn(x, &t, &tl, &tr)); /* :668-671 */
         t1 = t;
         s1 = s;
     }
@@ -660,8 +704,20 @@ void orc_nuts_transition(const orc_model* m, const orc_metric* me, int32_t D, in
                          const double* normal_tape, const uint8_t* dir_tape, int64_t dir_stride,
                          const double* exp_tape, int64_t exp_stride, const orc_phasepoint* z_in,
                          const orc_phasepoint* z_out, const orc_stats* st, int32_t* exp_used) {
+    orc_nuts_transition_ex(m, me, D, N, eps, eps_chain, max_depth, delta_max, 0, 0, normal_tape, dir_tape, dir_stride,
+                           exp_tape, exp_stride, z_in, z_out, st, exp_used);
+}
+
+void orc_nuts_transition_ex(const orc_model* m, const orc_metric* me, int32_t D, int64_t N, double eps,
+                            const double* eps_chain, int32_t max_depth, double delta_max, int32_t sampler_kind,
+                            int32_t criterion, const double* normal_tape, const uint8_t* dir_tape, int64_t dir_stride,
+                            const double* exp_tape, int64_t exp_stride, const orc_phasepoint* z_in,
+                            const orc_phasepoint* z_out, const orc_stats* st, int32_t* exp_used) {
     size_t max_leaves = ((size_t)1 << max_depth) + 4;
     nuts_ctx x;
+    x.sampler = sampler_kind;
+    x.criterion = criterion;
+    x.lu = 0.0;
     x.m = m;
     x.me = me;
     x.D = D;
@@ -703,6 +759,10 @@ void orc_nuts_transition(const orc_model* m, const orc_metric* me, int32_t D, in
         tree.n_alpha = 0;
         tree.dH_max = 0.0;
         sampler_t sampler = {z0, 0.0}; /* MultinomialTS(rng, z0) :155 */
+        if (x.sampler == 1) {          /* SliceTS(rng, z0) = SliceTS(z0, neg_energy(z0) - randexp(rng), 1) :144-145 */
+            x.lu = (z0->lp + z0->lk) - x.exps[x.n_exp++];
+            sampler.lw = 1.0;
+        }
         term_t term = {0, 0};
         const pp_t* zcand = z0;
         int j = 0, ndir = 0;
@@ -723,7 +783,9 @@ void orc_nuts_transition(const orc_model* m, const orc_metric* me, int32_t D, in
             if (!is_term(e1)) { /* :708-713 */
                 j = j + 1;
                 double ex = x.exps[x.n_exp++];
-                if (sampler.lw < s1.lw + ex) zcand = s1.zcand; /* mh_accept :204-206 */
+                if (x.sampler == 1) {
+                    if (sampler.lw * ex < s1.lw) zcand = s1.zcand; /* mh_accept(::SliceTS): s.n * rand < s'.n :202 */
+                } else if (sampler.lw < s1.lw + ex) zcand = s1.zcand; /* mh_accept :204-206 */
             }
             tree_t t; /* :715 */
             t.zleft = tl.zleft;
@@ -735,8 +797,8 @@ void orc_nuts_transition(const orc_model* m, const orc_metric* me, int32_t D, in
             t.dH_max = maxabs(tl.dH_max, tr.dH_max);
             tree = t;
             sampler.zcand = zcand; /* combine(zcand, sampler, sampler') :197-200, :717 */
-            sampler.lw = logaddexp(sampler.lw, s1.lw);
-            term = term_mul(term_mul(term, e1), uturn(&x, &tree)); /* :719-722 */
+            sampler.lw = (x.sampler == 1) ? sampler.lw + s1.lw : logaddexp(sampler.lw, s1.lw);
+            term = term_mul(term_mul(term, e1), uturn(&x, &tree, &tl, &tr)); /* :719-722 */
         }
         double H = -(zcand->lp + zcand->lk);
         for (int d = 0; d < D; ++d) {

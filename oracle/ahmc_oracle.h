@@ -137,6 +137,15 @@ void orc_nuts_transition(const orc_model* m, const orc_metric* me, int32_t D, in
                          const double* exp_tape, int64_t exp_stride, const orc_phasepoint* z_in,
                          const orc_phasepoint* z_out, const orc_stats* st, int32_t* exp_used);
 
+/* NUTS variants: sampler_kind 0 = MultinomialTS, 1 = SliceTS (trajectory.jl:102-206); criterion 0 = GeneralisedNoUTurn,
+ * 1 = ClassicNoUTurn, 2 = StrictGeneralisedNoUTurn (trajectory.jl:414-452, 551-613).  With SliceTS the tape entries
+ * are consumed as: [0] = the randexp of the slice variable (:144-145), then one UNIFORM per combine / mh_accept. */
+void orc_nuts_transition_ex(const orc_model* m, const orc_metric* me, int32_t D, int64_t N, double eps,
+                            const double* eps_chain, int32_t max_depth, double delta_max, int32_t sampler_kind,
+                            int32_t criterion, const double* normal_tape, const uint8_t* dir_tape, int64_t dir_stride,
+                            const double* exp_tape, int64_t exp_stride, const orc_phasepoint* z_in,
+                            const orc_phasepoint* z_out, const orc_stats* st, int32_t* exp_used);
+
 /* --- adaptation (src/adaptation) ----------------------------------------------------------- */
 /* NesterovDualAveraging state (stepsize.jl:13-62) for n independent entries (scalar: n=1) */
 typedef struct {

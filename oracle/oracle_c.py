@@ -231,7 +231,12 @@ def hmc_multinomial_transition(model, metric, eps, n_steps, n_steps_fwd, z, norm
     return out, st
 
 
-def nuts_transition(model, metric, eps, z, normal_tape, dir_tape, exp_tape, max_depth=10, delta_max=1000.0):
+SAMPLER = {"multinomial": 0, "slice": 1}
+CRITERION = {"generalised": 0, "classic": 1, "strict": 2}
+
+
+def nuts_transition(model, metric, eps, z, normal_tape, dir_tape, exp_tape, max_depth=10, delta_max=1000.0,
+                    sampler="multinomial", criterion="generalised"):
     """dir_tape: (N, n_dir) uint8 C-order; exp_tape: (N, n_exp) float64 C-order."""
     D, N = z.theta.shape
     out, st = PhasePoint(D, N), Stats(N)
@@ -241,8 +246,9 @@ def nuts_transition(model, metric, eps, z, normal_tape, dir_tape, exp_tape, max_
     used = np.zeros(N, dtype=np.int32)
     e, ep, _keep = _eps_args(eps, N)
     zc, oc, sc = z.c, out.c, st.c
-    lib().orc_nuts_transition(C.byref(model.c), C.byref(metric.c), D, C.c_int64(N), e, ep, int(max_depth),
-                              C.c_double(delta_max), _p(nt), dt.ctypes.data_as(C.POINTER(C.c_uint8)),
+    lib().orc_nuts_transition_ex(C.byref(model.c), C.byref(metric.c), D, C.c_int64(N), e, ep, int(max_depth),
+                              C.c_double(delta_max), SAMPLER[sampler], CRITERION[criterion], _p(nt),
+                              dt.ctypes.data_as(C.POINTER(C.c_uint8)),
                               C.c_int64(dt.shape[1]), _p(et), C.c_int64(et.shape[1]), C.byref(zc), C.byref(oc),
                               C.byref(sc), used.ctypes.data_as(C.POINTER(C.c_int32)))
     return out, st, used

@@ -370,7 +370,11 @@ def test_adapt_summary_matches_numpy():
 
 
 # ------------------------------------------------------------------------------------------------ NUTS
-def _nuts_case(model, metric, D, N, eps, seed, max_depth=10, scale=1.0):
+_SAMPLERS = {"multinomial": "MultinomialTS", "slice": "SliceTS"}
+_CRITERIA = {"generalised": "GeneralisedNoUTurn", "classic": "ClassicNoUTurn", "strict": "StrictGeneralisedNoUTurn"}
+
+
+def _nuts_case(model, metric, D, N, eps, seed, max_depth=10, scale=1.0, sampler="multinomial", criterion="generalised"):
     rng = np.random.default_rng(seed)
     p0 = p1 = Minv = None
     if model == "diag_gauss":
@@ -387,12 +391,15 @@ def _nuts_case(model, metric, D, N, eps, seed, max_depth=10, scale=1.0):
     nt = rng.normal(size=(D, N))
     dirs = rng.integers(0, 2, size=(N, max_depth + 1)).astype(np.uint8)
     exps = rng.exponential(size=(N, 1 << max_depth))
+    if sampler == "slice":  # SliceTS: one randexp for the slice variable, then rand() uniforms (trajectory.jl:144-145, 178-183, 202)
+        exps[:, 1:] = rng.uniform(size=(N, (1 << max_depth) - 1))
     om, ome = oc.Model(MODEL_KINDS[model], D, p0, p1, 0.0), oc.Metric(METRIC_KINDS[metric], Minv)
     z0o = oc.phasepoint(om, ome, th, np.zeros((D, N)))
-    zo, so, used = oc.nuts_transition(om, ome, eps, z0o, nt, dirs, exps, max_depth=max_depth)
+    zo, so, used = oc.nuts_transition(om, ome, eps, z0o, nt, dirs, exps, max_depth=max_depth, sampler=sampler,
+                                      criterion=criterion)
     h = A.Hamiltonian(make_metric(metric, Minv, D), make_target(model, D, p0, p1, 0.0))
     z0 = A.phasepoint(h, T(th), T(np.zeros((D, N))))
-    tau = A.Trajectory(A.MultinomialTS, A.Leapfrog(eps), A.GeneralisedNoUTurn(max_depth, 1000.0))
+    tau = A.Trajectory(getattr(A, _SAMPLERS[sampler]), A.Leapfrog(eps), getattr(A, _CRITERIA[criterion])(max_depth, 1000.0))
     rngt = A.TapeRNG(normal=T(nt), exp=torch.as_tensor(exps, device=DEV), dirs=torch.as_tensor(dirs, device=DEV))
     tr = A.transition(rngt, h, A.HMCKernel(tau), z0)
     return tr, zo, so
@@ -417,6 +424,49 @@ def test_nuts_transition_vs_oracle_with_tapes(model, metric, D, eps, scale):
     assert np.allclose(F(st["hamiltonian_energy_error"]), so.hamiltonian_energy_error, rtol=0, atol=1e-9 * D)
     assert np.allclose(F(st["max_hamiltonian_energy_error"]), so.max_hamiltonian_energy_error, rtol=1e-6, atol=1e-9 * D)
     assert (F(st["is_accept"]) == 1).all()
+
+
+@pytest.mark.parametrize("sampler,criterion", [
+    ("slice", "generalised"), ("multinomial", "classic"), ("multinomial", "strict"), ("slice", "classic"), ("slice", "strict"),
+])
+@pytest.mark.parametrize("model,metric,D,eps,scale", [
+    ("std_normal", "unit", 10, 0.3, 1.0), ("diag_gauss", "diag", 128, 0.15, 1.0), ("funnel", "diag", 20, 0.12, 0.6),
+    ("dense_gauss", "dense", 12, 0.25, 1.0), ("funnel", "unit", 3, 0.9, 2.0),
+])
+def test_nuts_variants_vs_oracle_with_tapes(sampler, criterion, model, metric, D, eps, scale):
+    """SliceTS / ClassicNoUTurn / StrictGeneralisedNoUTurn (trajectory.jl:102-109, 551-557, 579-613): same trees,
+    same draws and same statistics as the oracle, chain by chain, from shared random tapes."""
+    N = 203
+    tr, zo, so = _nuts_case(model, metric, D, N, eps, seed=D * 11 + 3, scale=scale, sampler=sampler, criterion=criterion)
+    st = tr.stat
+    assert (F(st["tree_depth"]) == so.tree_depth).all(), (F(st["tree_depth"])[:20], so.tree_depth[:20])
+    assert (F(st["n_steps"]) == so.n_steps).all()
+    assert (F(st["numerical_error"]) == so.numerical_error).all()
+    assert_pp_close(tr.z, zo)
+    assert rel_err(F(st["acceptance_rate"]), so.acceptance_rate) < 1e-9
+    assert np.allclose(F(st["hamiltonian_energy_error"]), so.hamiltonian_energy_error, rtol=0, atol=1e-9 * D)
+    assert np.allclose(F(st["max_hamiltonian_energy_error"]), so.max_hamiltonian_energy_error, rtol=1e-6, atol=1e-9 * D)
+
+
+def test_nuts_variants_differ_from_default_and_sample_the_target():
+    """the criteria are not aliases of each other (tree sizes differ on an anisotropic target), and SliceTS +
+    ClassicNoUTurn with Philox randomness still recovers the target moments."""
+    tr_g, _, so_g = _nuts_case("diag_gauss", "unit", 16, 256, 0.2, seed=77)
+    tr_c, _, so_c = _nuts_case("diag_gauss", "unit", 16, 256, 0.2, seed=77, criterion="classic")
+    tr_s, _, so_s = _nuts_case("diag_gauss", "unit", 16, 256, 0.2, seed=77, criterion="strict")
+    assert (F(tr_g.stat["n_steps"]) != F(tr_c.stat["n_steps"])).any()
+    assert (F(tr_s.stat["n_steps"]) <= F(tr_g.stat["n_steps"])).all()  # strict adds checks: never a larger tree
+    D, N = 6, 2048
+    m, s = np.linspace(-2, 2, D), np.exp(np.linspace(-1, 1, D))
+    h = A.Hamiltonian(A.DiagEuclideanMetric(s * s), A.DiagGaussian(m, s))
+    kern = A.HMCKernel(A.Trajectory(A.SliceTS, A.Leapfrog(0.5), A.ClassicNoUTurn()))
+    z = A.phasepoint(h, T(np.zeros((D, N))), T(np.zeros((D, N))))
+    zl, draws, st = A.sample_transitions(A.PhiloxRNG(11), h, kern, z, 60)
+    x = draws[20:].reshape(-1, D).cpu().numpy()
+    assert np.abs(x.mean(0) - m).max() < 0.05 * s.max()
+    assert np.abs(x.std(0) / s - 1).max() < 0.05
+    with pytest.raises(A.AhmcError):
+        A.transition(A.PhiloxRNG(0), h, A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.1), A.ClassicNoUTurn())), z)
 
 
 def test_nuts_max_depth_and_divergence_flags():

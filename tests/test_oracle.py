@@ -300,3 +300,56 @@ def test_nuts_oracle_samples_standard_normal():
         draws.append(z.theta[:, 0].copy())
     X = np.array(draws[200:])
     assert np.abs(X.mean(axis=0)).max() < 0.12 and np.abs(X.var(axis=0) - 1).max() < 0.15
+
+
+def test_nuts_oracle_classic_and_strict_hand_formulas():
+    """First doubling, expanding right from z0 to z1 (tleft = leaf z0, tright = leaf z1):
+    ClassicNoUTurn (trajectory.jl:551-557): dot(dth, Minv(-r0)) >= 0 || dot(-dth, Minv r1) >= 0, dth = th1 - th0.
+    StrictGeneralisedNoUTurn (:579-613) on two single leaves reduces to the generalised check on rho = r0 + r1
+    (both sub-tree checks use the same rho and the same two momenta)."""
+    D = 4
+    rng = np.random.default_rng(13)
+    Minv = np.exp(rng.uniform(-1, 1, D))
+    model, metric = oc.Model(oc.STD_NORMAL, D), oc.Metric(oc.DIAG, Minv)
+    hits = 0
+    for trial in range(200):
+        th, r = rng.normal(size=(D, 1)), rng.normal(size=(D, 1))
+        z0 = oc.phasepoint(model, metric, th, r)
+        dirs = np.zeros((1, 3), dtype=np.uint8)
+        big = np.full((1, 8), 1e9)
+        zr, _, _ = oc.leapfrog(model, metric, 1.2, z0, 1)
+        dth = zr.theta[:, 0] - z0.theta[:, 0]
+        turn_c = (dth @ (Minv * -z0.r[:, 0]) >= 0) or (-dth @ (Minv * zr.r[:, 0]) >= 0)
+        _, st, _ = oc.nuts_transition(model, metric, 1.2, z0, None, dirs, big, max_depth=2, criterion="classic")
+        assert (st.n_steps[0] == 1) == bool(turn_c)
+        hits += bool(turn_c)
+        _, sg, _ = oc.nuts_transition(model, metric, 1.2, z0, None, dirs, big, max_depth=1)
+        _, ss, _ = oc.nuts_transition(model, metric, 1.2, z0, None, dirs, big, max_depth=1, criterion="strict")
+        assert sg.n_steps[0] == ss.n_steps[0] == 1
+    assert 5 < hits < 195
+
+
+@pytest.mark.parametrize("sampler,criterion", [("slice", "generalised"), ("multinomial", "classic"),
+                                               ("multinomial", "strict"), ("slice", "strict")])
+def test_nuts_oracle_variants_sample_standard_normal(sampler, criterion):
+    """every (trajectory sampler, criterion) pair leaves N(0, I) invariant; strict never grows a larger tree than
+    generalised from the same randomness."""
+    D = 3
+    rng = np.random.default_rng(5)
+    model, metric = oc.Model(oc.STD_NORMAL, D), oc.Metric(oc.UNIT)
+    z = oc.phasepoint(model, metric, np.zeros((D, 1)), np.zeros((D, 1)))
+    draws = []
+    for it in range(2500):
+        nt = rng.normal(size=(D, 1))
+        dirs = rng.integers(0, 2, size=(1, 11)).astype(np.uint8)
+        exps = rng.exponential(size=(1, 1024))
+        if sampler == "slice":
+            exps[:, 1:] = rng.uniform(size=(1, 1023))
+        if criterion == "strict" and sampler == "multinomial":
+            _, sg, _ = oc.nuts_transition(model, metric, 0.9, z, nt, dirs, exps)
+        z, st, _ = oc.nuts_transition(model, metric, 0.9, z, nt, dirs, exps, sampler=sampler, criterion=criterion)
+        if criterion == "strict" and sampler == "multinomial":
+            assert st.n_steps[0] <= sg.n_steps[0]
+        draws.append(z.theta[:, 0].copy())
+    X = np.array(draws[200:])
+    assert np.abs(X.mean(axis=0)).max() < 0.15 and np.abs(X.var(axis=0) - 1).max() < 0.18
