@@ -9,6 +9,13 @@
 #include <string>
 #include <vector>
 
+// defaults of the host-buffer lane (see leapfrog_host_pipelined), chosen by measurement on B200 (profiles/README.md,
+// "host-buffer lane"): page-locked buffers are read and written by the kernel directly, in launches of >= 256 chains
+// alternating between two streams; pageable buffers go through the copy engines in two chunks.
+#define AHMC_PIPE_DIRECT_CHUNK_CHAINS 256
+#define AHMC_PIPE_DIRECT_MAX_CHUNKS 16
+#define AHMC_PIPE_CE_CHUNKS 2
+
 #include "ahmc_kernels.cuh"
 
 using namespace ahmc;
@@ -32,8 +39,11 @@ struct ahmc_ctx {
     size_t dense_scratch_bytes = 0;
     char* split_scratch = nullptr;   // callback (split-step) mode workspace
     size_t split_scratch_bytes = 0;
-    cudaStream_t stream2 = nullptr;  // second stream of the host-buffer pipeline (H2D of chunk i+1 || D2H of chunk i)
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // host-buffer pipeline: H2D stream, compute stream (= stream), D2H stream, one event pair per chunk
+    static constexpr int kMaxPipeChunks = 32, kPipeStreams = 5;  // 3 upload, 1 download, 1 second compute
+    cudaStream_t pipe[kPipeStreams] = {};
+    cudaEvent_t ev_a = nullptr, ev_join[kPipeStreams] = {};
+    cudaEvent_t ev_in[kMaxPipeChunks][3] = {}, ev_k[kMaxPipeChunks] = {};
 };
 
 struct ahmc_model {
@@ -406,9 +416,16 @@ int ahmc_destroy(ahmc_ctx* ctx) {
     cudaFree(ctx->mn_scratch);
     cudaFree(ctx->dense_scratch);
     cudaFree(ctx->split_scratch);
-    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int i = 0; i < ahmc_ctx::kPipeStreams; ++i) {
+        if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    for (int i = 0; i < ahmc_ctx::kMaxPipeChunks; ++i) {
+        for (int j = 0; j < 3; ++j)
+            if (ctx->ev_in[i][j]) cudaEventDestroy(ctx->ev_in[i][j]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+    }
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
-    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return AHMC_OK;
@@ -569,26 +586,106 @@ static int copy_pp_device(ahmc_ctx* ctx, int32_t D, int64_t N, const ahmc_phasep
     return AHMC_OK;
 }
 
-// HOST_BUFFERS fast lane for big batches: the chain axis is cut into chunks that alternate between two streams, so
-// the host->device copy of chunk i+1 overlaps the kernel and the device->host copy of chunk i (PCIe is full duplex;
-// chains are independent, so a chunk is a complete sub-problem).  Same kernels, same results as the one-shot path.
+// device alias of a page-locked, device-mapped host pointer (cudaHostAlloc / cudaHostRegister memory under unified
+// addressing), or nullptr for pageable memory
+static void* pinned_alias(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return at.devicePointer;
+}
+
+static int pipe_resources(ahmc_ctx* ctx) {
+    if (ctx->pipe[0]) return AHMC_OK;
+    for (int i = 0; i < ahmc_ctx::kPipeStreams; ++i) CU(cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
+    for (int i = 0; i < ahmc_ctx::kPipeStreams; ++i) CU(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    for (int i = 0; i < ahmc_ctx::kMaxPipeChunks; ++i) {
+        for (int j = 0; j < 3; ++j) CU(cudaEventCreateWithFlags(&ctx->ev_in[i][j], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+    }
+    return AHMC_OK;
+}
+
+// HOST_BUFFERS fast lane.  The chain axis is cut into chunks (chains are independent, so a chunk is a complete
+// sub-problem) that flow upload -> kernel -> download through separate streams linked chunk by chunk with events, so
+// the upload of chunk i+1 overlaps the kernel and the download of chunk i (PCIe is full duplex): the call costs about
+// max(H2D, D2H) + one chunk instead of their sum.  Same kernels, bit-identical results to the one-shot path.
+//   upload   : copy engines, theta / r / gradient on one stream or on one stream each (their fixed per-copy latencies
+//              overlap), or -- page-locked buffers only -- none at all: the kernel loads from host memory directly;
+//   download : copy engines on a third stream, or -- page-locked buffers only -- none: the kernel's stores go straight
+//              to host memory as posted PCIe writes.
+// Pageable buffers always take the copy-engine form.  Knobs for A/B measurements: AHMC_PIPE_CHUNKS (chunk count),
+// AHMC_PIPE_UP = ce1 | ce3 | direct, AHMC_PIPE_DOWN = ce | direct, AHMC_PIPE_TRACE=1 (event timeline on stderr).
 static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D,
                                    int64_t N, double eps, const double* eps_chain, int32_t n_steps,
                                    double temper_alpha, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
                                    uint32_t* status, int32_t* steps_done, uint32_t flags) {
-    if (!ctx->stream2) {
-        CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&ctx->ev_a, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming));
+    int rc = pipe_resources(ctx);
+    if (rc) return rc;
+    const char* ev;
+    const bool per_chain_minv = metric->kind == AHMC_METRIC_DIAG && metric->chain_stride != 0;
+
+    // which buffers can the device address directly?
+    bool in_pinned = true, out_pinned = true;
+    auto alias = [](const void* p, bool& all) -> void* {
+        if (!p) return nullptr;
+        void* d = pinned_alias(p);
+        if (!d) all = false;
+        return d;
+    };
+    const double* a_th = (const double*)alias(z_in->theta, in_pinned);
+    const double* a_r = (const double*)alias(z_in->r, in_pinned);
+    const double* a_g = (const double*)alias(z_in->lp_gradient, in_pinned);
+    const double* a_eps = (const double*)alias(eps_chain, in_pinned);
+    const double* a_minv = per_chain_minv ? (const double*)alias(metric->Minv, in_pinned) : nullptr;
+    double* b_th = (double*)alias(z_out->theta, out_pinned);
+    double* b_r = (double*)alias(z_out->r, out_pinned);
+    double* b_g = (double*)alias(z_out->lp_gradient, out_pinned);
+    double* b_dr = (double*)alias(z_out->lk_gradient, out_pinned);
+    double* b_lp = (double*)alias(z_out->lp_value, out_pinned);
+    double* b_lk = (double*)alias(z_out->lk_value, out_pinned);
+    uint32_t* b_st = (uint32_t*)alias(status, out_pinned);
+    int32_t* b_sd = (int32_t*)alias(steps_done, out_pinned);
+
+    enum { UP_CE1, UP_CE3, UP_DIRECT };
+    int up = in_pinned ? UP_DIRECT : UP_CE1;
+    bool down_direct = out_pinned;
+    if ((ev = getenv("AHMC_PIPE_UP"))) up = !strcmp(ev, "direct") ? UP_DIRECT : !strcmp(ev, "ce3") ? UP_CE3 : UP_CE1;
+    if ((ev = getenv("AHMC_PIPE_DOWN"))) down_direct = !strcmp(ev, "direct");
+    if (!in_pinned && up == UP_DIRECT) up = UP_CE3;
+    if (!out_pinned) down_direct = false;
+    const bool trace = (ev = getenv("AHMC_PIPE_TRACE")) && atoi(ev) != 0;
+    int nchunk = (ev = getenv("AHMC_PIPE_CHUNKS")) ? atoi(ev) : 0;
+    if (nchunk <= 0) {
+        if (up == UP_DIRECT) {
+            nchunk = (int)(N / AHMC_PIPE_DIRECT_CHUNK_CHAINS);
+            if (nchunk > AHMC_PIPE_DIRECT_MAX_CHUNKS) nchunk = AHMC_PIPE_DIRECT_MAX_CHUNKS;
+        } else {
+            nchunk = N >= 1024 ? AHMC_PIPE_CE_CHUNKS : 1;
+        }
+        if (nchunk < 1) nchunk = 1;
     }
+    if (nchunk > ahmc_ctx::kMaxPipeChunks) nchunk = ahmc_ctx::kMaxPipeChunks;
+    int64_t chunk = (N + nchunk - 1) / nchunk;
+    chunk = (chunk + 3) & ~(int64_t)3;
+
+    // device staging for whatever is not addressed directly
     const int64_t ldi = z_in->ld, ldo = z_out->ld;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t nMinv = metric_minv_count(metric, D, N);
-    size_t need = al(nMinv * 8) + al((size_t)D * D * 8) + al((size_t)N * 8) + 3 * al((size_t)ldi * N * 8) +
-                  4 * al((size_t)ldo * N * 8) + 2 * al((size_t)N * 8) + 2 * al((size_t)N * 4);
+    const bool stage_in = up != UP_DIRECT, stage_out = !down_direct;
+    const bool hasU = metric->kind == AHMC_METRIC_DENSE && metric->cholU;
+    size_t need = (per_chain_minv && !stage_in ? 0 : al(nMinv * 8)) + (hasU ? al((size_t)D * D * 8) : 0);
+    if (stage_in) need += al((size_t)N * 8) + 3 * al((size_t)ldi * N * 8);
+    if (stage_out) need += 4 * al((size_t)ldo * N * 8) + 2 * al((size_t)N * 8) + 2 * al((size_t)N * 4);
     if (need > ctx->arena_bytes) {
         CU(cudaStreamSynchronize(ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream2));
+        for (int i = 0; i < ahmc_ctx::kPipeStreams; ++i) CU(cudaStreamSynchronize(ctx->pipe[i]));
         cudaFree(ctx->arena);
         ctx->arena = nullptr;
         ctx->arena_bytes = 0;
@@ -598,88 +695,142 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
         ctx->arena_bytes = cap;
     }
     size_t off = 0;
-    auto carve = [&](size_t bytes) { char* p = ctx->arena + off; off += al(bytes); return p; };
-    double* dMinv = (double*)carve(nMinv * 8);
-    double* dU = (double*)carve((size_t)D * D * 8);
-    double* dEps = (double*)carve((size_t)N * 8);
-    double* dTh = (double*)carve((size_t)ldi * N * 8);
-    double* dR = (double*)carve((size_t)ldi * N * 8);
-    double* dG = (double*)carve((size_t)ldi * N * 8);
-    double* oTh = (double*)carve((size_t)ldo * N * 8);
-    double* oR = (double*)carve((size_t)ldo * N * 8);
-    double* oG = (double*)carve((size_t)ldo * N * 8);
-    double* oDr = (double*)carve((size_t)ldo * N * 8);
-    double* oLp = (double*)carve((size_t)N * 8);
-    double* oLk = (double*)carve((size_t)N * 8);
-    uint32_t* oSt = (uint32_t*)carve((size_t)N * 4);
-    int32_t* oSd = (int32_t*)carve((size_t)N * 4);
+    auto carve = [&](bool want, size_t bytes) -> char* {
+        if (!want || !bytes) return nullptr;
+        char* p = ctx->arena + off;
+        off += al(bytes);
+        return p;
+    };
+    double* dMinv = (double*)carve(!(per_chain_minv && !stage_in), nMinv * 8);
+    double* dU = (double*)carve(hasU, (size_t)D * D * 8);
+    double* dEps = (double*)carve(stage_in, (size_t)N * 8);
+    double* dTh = (double*)carve(stage_in, (size_t)ldi * N * 8);
+    double* dR = (double*)carve(stage_in, (size_t)ldi * N * 8);
+    double* dG = (double*)carve(stage_in, (size_t)ldi * N * 8);
+    double* oTh = (double*)carve(stage_out, (size_t)ldo * N * 8);
+    double* oR = (double*)carve(stage_out, (size_t)ldo * N * 8);
+    double* oG = (double*)carve(stage_out, (size_t)ldo * N * 8);
+    double* oDr = (double*)carve(stage_out, (size_t)ldo * N * 8);
+    double* oLp = (double*)carve(stage_out, (size_t)N * 8);
+    double* oLk = (double*)carve(stage_out, (size_t)N * 8);
+    uint32_t* oSt = (uint32_t*)carve(stage_out, (size_t)N * 4);
+    int32_t* oSd = (int32_t*)carve(stage_out, (size_t)N * 4);
 
-    cudaStream_t ss[2] = {ctx->stream, ctx->stream2};
-    // shared parameters first (stream 0), stream 1 waits for them
-    const bool per_chain_minv = metric->kind == AHMC_METRIC_DIAG && metric->chain_stride != 0;
-    if (nMinv && !per_chain_minv) CU(cudaMemcpyAsync(dMinv, metric->Minv, nMinv * 8, cudaMemcpyHostToDevice, ss[0]));
-    if (metric->kind == AHMC_METRIC_DENSE && metric->cholU)
-        CU(cudaMemcpyAsync(dU, metric->cholU, (size_t)D * D * 8, cudaMemcpyHostToDevice, ss[0]));
-    CU(cudaEventRecord(ctx->ev_a, ss[0]));
-    CU(cudaStreamWaitEvent(ss[1], ctx->ev_a, 0));
+    cudaStream_t s_cmp = ctx->stream;
+    cudaStream_t s_up[3] = {ctx->pipe[0], up == UP_CE3 ? ctx->pipe[1] : ctx->pipe[0], up == UP_CE3 ? ctx->pipe[2] : ctx->pipe[0]};
+    cudaStream_t s_down = ctx->pipe[3];
+    const int n_up = up == UP_CE3 ? 3 : 1;
+
+    // everything is ordered after earlier work on the context stream; shared parameters (re-read by every chain, so
+    // always staged) go first on the compute stream itself
+    CU(cudaEventRecord(ctx->ev_a, s_cmp));
+    if (stage_in)
+        for (int j = 0; j < n_up; ++j) CU(cudaStreamWaitEvent(s_up[j], ctx->ev_a, 0));
+    if (nMinv && !per_chain_minv) CU(cudaMemcpyAsync(dMinv, metric->Minv, nMinv * 8, cudaMemcpyHostToDevice, s_cmp));
+    if (hasU) CU(cudaMemcpyAsync(dU, metric->cholU, (size_t)D * D * 8, cudaMemcpyHostToDevice, s_cmp));
+    if (!stage_in) {  // the second compute stream starts after the shared parameters have landed
+        CU(cudaEventRecord(ctx->ev_join[0], s_cmp));
+        CU(cudaStreamWaitEvent(ctx->pipe[4], ctx->ev_join[0], 0));
+    }
+
+    std::vector<cudaEvent_t> tr;  // optional timeline (timing events are created only when tracing)
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tr.push_back(e);
+    };
+    mark(s_cmp);
 
     const int n_abs = n_steps < 0 ? -n_steps : n_steps;
-    int nchunk = 4;                              // default 4 chunks (>= 512 chains each): host issue rate ~3-4 us per call
-    if (const char* e = getenv("AHMC_PIPE_CHUNKS")) nchunk = atoi(e) > 0 ? atoi(e) : nchunk;
-    int64_t chunk = (N + nchunk - 1) / nchunk;
-    if (chunk < 512) chunk = 512;
-    chunk = (chunk + 3) & ~(int64_t)3;
     int nl = 0, k = 0;
     for (int64_t c0 = 0; c0 < N; c0 += chunk, ++k) {
         const int64_t n = (c0 + chunk <= N) ? chunk : N - c0;
-        cudaStream_t st = ss[k & 1];
-        CU(cudaMemcpyAsync(dTh + ldi * c0, z_in->theta + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(dR + ldi * c0, z_in->r + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(dG + ldi * c0, z_in->lp_gradient + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, st));
-        if (eps_chain) CU(cudaMemcpyAsync(dEps + c0, eps_chain + c0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        if (per_chain_minv)
-            CU(cudaMemcpyAsync(dMinv + metric->chain_stride * c0, metric->Minv + metric->chain_stride * c0,
-                               (size_t)metric->chain_stride * n * 8, cudaMemcpyHostToDevice, st));
+        if (stage_in) {
+            CU(cudaMemcpyAsync(dTh + ldi * c0, z_in->theta + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, s_up[0]));
+            if (eps_chain) CU(cudaMemcpyAsync(dEps + c0, eps_chain + c0, (size_t)n * 8, cudaMemcpyHostToDevice, s_up[0]));
+            CU(cudaMemcpyAsync(dR + ldi * c0, z_in->r + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, s_up[1]));
+            if (per_chain_minv)
+                CU(cudaMemcpyAsync(dMinv + metric->chain_stride * c0, metric->Minv + metric->chain_stride * c0,
+                                   (size_t)metric->chain_stride * n * 8, cudaMemcpyHostToDevice, s_up[1]));
+            CU(cudaMemcpyAsync(dG + ldi * c0, z_in->lp_gradient + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, s_up[2]));
+            for (int j = 0; j < n_up; ++j) {
+                CU(cudaEventRecord(ctx->ev_in[k][j], s_up[j]));
+                CU(cudaStreamWaitEvent(s_cmp, ctx->ev_in[k][j], 0));
+            }
+            mark(s_up[n_up - 1]);
+        }
         LeapfrogArgs a{};
         a.model = model_dev(model);
-        a.metric = MetricDev{metric->kind, per_chain_minv ? dMinv + metric->chain_stride * c0 : (nMinv ? dMinv : nullptr),
-                             per_chain_minv ? metric->chain_stride : 0, metric->kind == AHMC_METRIC_DENSE ? dU : nullptr};
+        const double* minv_k = !nMinv ? nullptr
+                               : !per_chain_minv ? dMinv
+                               : stage_in ? dMinv + metric->chain_stride * c0 : a_minv + metric->chain_stride * c0;
+        a.metric = MetricDev{metric->kind, minv_k, per_chain_minv ? metric->chain_stride : 0, hasU ? dU : nullptr};
         a.D = D;
         a.N = n;
         a.eps = eps;
-        a.eps_chain = eps_chain ? dEps + c0 : nullptr;
+        a.eps_chain = !eps_chain ? nullptr : stage_in ? dEps + c0 : a_eps + c0;
         a.n_steps = n_abs;
         a.fwd = n_steps > 0;
         a.temper_alpha = temper_alpha;
-        a.th_in = dTh + ldi * c0;
-        a.r_in = dR + ldi * c0;
-        a.g_in = dG + ldi * c0;
+        a.th_in = (stage_in ? dTh : a_th) + ldi * c0;
+        a.r_in = (stage_in ? dR : a_r) + ldi * c0;
+        a.g_in = (stage_in ? dG : a_g) + ldi * c0;
         a.ld_in = ldi;
-        a.th_out = oTh + ldo * c0;
-        a.r_out = oR + ldo * c0;
-        a.g_out = oG + ldo * c0;
-        a.dr_out = z_out->lk_gradient ? oDr + ldo * c0 : nullptr;
-        a.lp_out = oLp + c0;
-        a.lk_out = oLk + c0;
+        a.th_out = (stage_out ? oTh : b_th) + ldo * c0;
+        a.r_out = (stage_out ? oR : b_r) + ldo * c0;
+        a.g_out = (stage_out ? oG : b_g) + ldo * c0;
+        a.dr_out = !z_out->lk_gradient ? nullptr : (stage_out ? oDr : b_dr) + ldo * c0;
+        a.lp_out = (stage_out ? oLp : b_lp) + c0;
+        a.lk_out = (stage_out ? oLk : b_lk) + c0;
         a.ld_out = ldo;
-        a.status = status ? oSt + c0 : nullptr;
-        a.steps_done = steps_done ? oSd + c0 : nullptr;
+        a.status = !status ? nullptr : (stage_out ? oSt : b_st) + c0;
+        a.steps_done = !steps_done ? nullptr : (stage_out ? oSd : b_sd) + c0;
         a.flags = flags;
-        CU(launch_leapfrog(a, st, &nl));
-        CU(cudaMemcpyAsync(z_out->theta + ldo * c0, a.th_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(z_out->r + ldo * c0, a.r_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(z_out->lp_gradient + ldo * c0, a.g_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, st));
-        if (a.dr_out) CU(cudaMemcpyAsync(z_out->lk_gradient + ldo * c0, a.dr_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(z_out->lp_value + c0, a.lp_out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(z_out->lk_value + c0, a.lk_out, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        if (status) CU(cudaMemcpyAsync(status + c0, a.status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (steps_done) CU(cudaMemcpyAsync(steps_done + c0, a.steps_done, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        // with direct loads the kernels of different chunks may run side by side: alternate two streams
+        cudaStream_t s_k = (!stage_in && (k & 1)) ? ctx->pipe[4] : s_cmp;
+        CU(launch_leapfrog(a, s_k, &nl));
+        mark(s_k);
+        if (stage_out) {
+            CU(cudaEventRecord(ctx->ev_k[k], s_k));
+            CU(cudaStreamWaitEvent(s_down, ctx->ev_k[k], 0));
+            CU(cudaMemcpyAsync(z_out->theta + ldo * c0, a.th_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, s_down));
+            CU(cudaMemcpyAsync(z_out->r + ldo * c0, a.r_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, s_down));
+            CU(cudaMemcpyAsync(z_out->lp_gradient + ldo * c0, a.g_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, s_down));
+            if (a.dr_out) CU(cudaMemcpyAsync(z_out->lk_gradient + ldo * c0, a.dr_out, (size_t)ldo * n * 8, cudaMemcpyDeviceToHost, s_down));
+            mark(s_down);
+        }
     }
     ctx->launches += nl;
-    // join stream 1 into stream 0, then synchronise (host buffers are only valid after the copies land)
-    CU(cudaEventRecord(ctx->ev_b, ss[1]));
-    CU(cudaStreamWaitEvent(ss[0], ctx->ev_b, 0));
-    CU(cudaStreamSynchronize(ss[0]));
+    if (stage_out) {
+        // the per-chain scalars of all chunks go back in one copy each (stream order puts them after the last kernel)
+        CU(cudaMemcpyAsync(z_out->lp_value, oLp, (size_t)N * 8, cudaMemcpyDeviceToHost, s_down));
+        CU(cudaMemcpyAsync(z_out->lk_value, oLk, (size_t)N * 8, cudaMemcpyDeviceToHost, s_down));
+        if (status) CU(cudaMemcpyAsync(status, oSt, (size_t)N * 4, cudaMemcpyDeviceToHost, s_down));
+        if (steps_done) CU(cudaMemcpyAsync(steps_done, oSd, (size_t)N * 4, cudaMemcpyDeviceToHost, s_down));
+        mark(s_down);
+        CU(cudaEventRecord(ctx->ev_join[3], s_down));
+        CU(cudaStreamWaitEvent(s_cmp, ctx->ev_join[3], 0));
+    }
+    if (!stage_in && k > 1) {
+        CU(cudaEventRecord(ctx->ev_join[4], ctx->pipe[4]));
+        CU(cudaStreamWaitEvent(s_cmp, ctx->ev_join[4], 0));
+    }
+    // host buffers are valid once everything joined into the context stream has retired
+    CU(cudaStreamSynchronize(s_cmp));
+    if (trace && !tr.empty()) {
+        fprintf(stderr, "[ahmc pipe] up=%s down=%s chunks=%d x %lld chains; ms after the first mark, per chunk [upload] kernel [download]:\n ",
+                up == UP_DIRECT ? "direct" : up == UP_CE3 ? "ce3" : "ce1", down_direct ? "direct" : "ce", k, (long long)chunk);
+        const int per = 1 + (stage_in ? 1 : 0) + (stage_out ? 1 : 0);
+        for (size_t i = 1; i < tr.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, tr[0], tr[i]);
+            fprintf(stderr, "%s%.3f", (i - 1) % per == 0 ? " | " : " ", ms);
+        }
+        fprintf(stderr, "\n");
+        for (cudaEvent_t e : tr) cudaEventDestroy(e);
+    }
     return AHMC_OK;
 }
 
@@ -710,7 +861,10 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
         }
         return AHMC_OK;
     }
-    if (host && !(flags & AHMC_FLAG_COMPAT_BREAK_ALL) && N >= 1024 && model->kind != AHMC_MODEL_CALLBACK)
+    // dense targets / metrics go through the staged lane below, which can pick the tiled kernel
+    const bool host_fast = host && !(flags & AHMC_FLAG_COMPAT_BREAK_ALL) && model->kind != AHMC_MODEL_CALLBACK &&
+                           model->kind != AHMC_MODEL_DENSE_GAUSS && metric->kind != AHMC_METRIC_DENSE;
+    if (host_fast && N >= 256)
         return leapfrog_host_pipelined(ctx, model, metric, D, N, eps, eps_chain, n_steps, temper_alpha, z_in, z_out,
                                        status, steps_done, flags);
     Stager st(ctx, host);

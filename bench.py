@@ -353,10 +353,13 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    call_ms = []
     t0 = time.perf_counter()
     for _ in range(K):
+        tc = time.perf_counter()
         ze = e2e_step()
         _ = float(ze.lp.value[0])  # device->host read of the step's result
+        call_ms.append((time.perf_counter() - tc) * 1e3)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d = 3 * N_CHAINS * DIM * 8 + DIM * 8
@@ -401,7 +404,8 @@ def run_ours(args):
                    "l2": "flushed between timed iterations (512 MiB read-sweep outside the event pair)"},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "steps*dims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms_max / K, "path": "ahmc_leapfrog_f64(AHMC_FLAG_HOST_BUFFERS) via ahmc_b200.step on pinned host arrays"},
+                "ms_per_step": e2e_ms_max / K, "call_ms_min_med_max": [min(call_ms), sorted(call_ms)[len(call_ms) // 2], max(call_ms)],
+                "path": "ahmc_leapfrog_f64(AHMC_FLAG_HOST_BUFFERS) via ahmc_b200.step on pinned host arrays"},
         "gpu_launches": int(launches), "clocks": clocks,
         "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
     }

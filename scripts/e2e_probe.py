@@ -20,7 +20,6 @@ def both():
     with torch.cuda.stream(s2): h_a2.copy_(d_b, non_blocking=True)
 h_a2 = torch.empty(N * D * 3, dtype=torch.float64).pin_memory(); d_b = torch.empty(N * D * 3, dtype=torch.float64, device=dev)
 print("H2D || D2H 12.6MB each ms", t(both))
-chunks = os.environ.get("AHMC_PIPE_CHUNKS", "8")
 import ahmc_b200 as A
 m, s, Minv, th, r = bench.synth(N, D, 1)
 h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s))
@@ -32,4 +31,34 @@ z0.theta, z0.r, z0.lp.gradient = thp.numpy(), rp.numpy(), gp.numpy()
 outs = [torch.empty((N, D), dtype=torch.float64).pin_memory() for _ in range(3)] + [torch.empty((N,), dtype=torch.float64).pin_memory() for _ in range(2)]
 zout = A.PhasePoint(outs[0].numpy(), outs[1].numpy(), A.DualValue(outs[3].numpy(), outs[2].numpy()), A.DualValue(outs[4].numpy(), None))
 plan = A.StepPlan(A.Leapfrog(0.1), h, z0, 32, out=zout)
-print("chunks", chunks, "e2e call ms", t(plan, 30))
+zd = A.step(A.Leapfrog(0.1), h, A.phasepoint(h, torch.as_tensor(th, device=dev), torch.as_tensor(r, device=dev)), 32)
+def check(tag):
+    ok = all(np.array_equal(a, b.cpu().numpy()) for a, b in [(zout.theta, zd.theta), (zout.r, zd.r), (zout.lp.value, zd.lp.value),
+                                                             (zout.lk.value, zd.lk.value), (zout.lp.gradient, zd.lp.gradient)])
+    print(tag, "bit-identical to the device call:", ok, flush=True)
+best = None
+for up, down in (("ce1", "ce"), ("ce3", "ce"), ("ce1", "direct"), ("ce3", "direct"), ("direct", "direct"), ("direct", "ce")):
+    for chunks in ("1", "2", "3", "4", "6", "8", "16"):
+        os.environ["AHMC_PIPE_UP"], os.environ["AHMC_PIPE_DOWN"], os.environ["AHMC_PIPE_CHUNKS"] = up, down, chunks
+        for o in outs: o.zero_()
+        ms = min(t(plan, 30) for _ in range(2))
+        ok = all(np.array_equal(a, b.cpu().numpy()) for a, b in [(zout.theta, zd.theta), (zout.r, zd.r), (zout.lp.value, zd.lp.value),
+                                                                 (zout.lk.value, zd.lk.value), (zout.lp.gradient, zd.lp.gradient)])
+        print("up", up, "down", down, "chunks", chunks, "e2e call ms %.4f" % ms, "bit-identical" if ok else "MISMATCH", flush=True)
+        if best is None or ms < best[0]: best = (ms, up, down, chunks)
+print("best", best)
+for k in ("AHMC_PIPE_UP", "AHMC_PIPE_DOWN", "AHMC_PIPE_CHUNKS"): os.environ.pop(k)
+print("library defaults: e2e call ms %.4f" % t(plan, 40))
+os.environ["AHMC_PIPE_TRACE"] = "1"
+for up, down, chunks in (("ce3", "ce", "8"), ("ce3", "direct", "4"), ("ce1", "direct", "4"), ("direct", "direct", "4"), best[1:]):
+    os.environ["AHMC_PIPE_UP"], os.environ["AHMC_PIPE_DOWN"], os.environ["AHMC_PIPE_CHUNKS"] = up, down, chunks
+    plan(); plan()
+# small batches: latency of one call
+for n in (256, 1024):
+    for k in ("AHMC_PIPE_UP", "AHMC_PIPE_DOWN", "AHMC_PIPE_CHUNKS", "AHMC_PIPE_TRACE"): os.environ.pop(k, None)
+    zs = A.PhasePoint(thp.numpy()[:n], rp.numpy()[:n], A.DualValue(z0.lp.value[:n], gp.numpy()[:n]), A.DualValue(z0.lk.value[:n], None))
+    zo = A.PhasePoint(outs[0].numpy()[:n], outs[1].numpy()[:n], A.DualValue(outs[3].numpy()[:n], outs[2].numpy()[:n]), A.DualValue(outs[4].numpy()[:n], None))
+    pl = A.StepPlan(A.Leapfrog(0.1), h, zs, 32, out=zo)
+    print("N", n, "defaults: call ms %.4f" % t(pl, 50))
+    os.environ["AHMC_PIPE_UP"], os.environ["AHMC_PIPE_DOWN"] = "ce1", "ce"
+    print("N", n, "ce1/ce:   call ms %.4f" % t(pl, 50))

@@ -503,20 +503,45 @@ def test_nuts_sampling_moments_philox():
     assert tr.stat["acceptance_rate"].mean().item() > 0.6
 
 
-def test_pipelined_host_path_equals_device_path():
-    """N >= 1024 host-buffer calls take the chunked two-stream pipeline: same bytes out as the device call."""
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("up,down,chunks", [("ce1", "ce", "0"), ("ce3", "ce", "5"), ("ce3", "direct", "0"),
+                                            ("direct", "direct", "3"), ("direct", "ce", "2"), (None, None, None)])
+def test_pipelined_host_path_equals_device_path(up, down, chunks, pinned, monkeypatch):
+    """host-buffer calls with N >= 256 take the chunked upload / kernel / download lane: same bytes out as the device
+    call for every transport (copy engines on one or three streams, direct loads / stores on page-locked buffers,
+    ragged chunk counts, library defaults), with pageable and with page-locked arrays."""
+    if up is not None:
+        monkeypatch.setenv("AHMC_PIPE_UP", up)
+        monkeypatch.setenv("AHMC_PIPE_DOWN", down)
+        monkeypatch.setenv("AHMC_PIPE_CHUNKS", chunks)
     D, N = 100, 4099
     rng = np.random.default_rng(5)
     s = np.exp(rng.uniform(-1, 1, D))
     m = rng.normal(size=D)
+    hold = []
+
+    def buf(a):
+        if not pinned:
+            return np.ascontiguousarray(a)
+        t = torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+        hold.append(t)
+        return t.numpy()
+
     Minv_pc = np.exp(rng.uniform(-1, 1, (N, D)))
     th, r = rng.normal(size=(N, D)), rng.normal(size=(N, D))
     eps = 0.05 * np.exp(rng.uniform(-0.3, 0.3, N))
     for Minv in (np.exp(rng.uniform(-1, 1, D)), Minv_pc):
-        h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s))
-        zd, infod = A.step(A.Leapfrog(torch.as_tensor(eps, device=DEV)), h,
-                           A.phasepoint(h, torch.as_tensor(th, device=DEV), torch.as_tensor(r, device=DEV)), 17, return_info=True)
-        zh, infoh = A.step(A.Leapfrog(eps), h, A.phasepoint(h, th, r), 17, return_info=True)
+        hd = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s))
+        zd, infod = A.step(A.Leapfrog(torch.as_tensor(eps, device=DEV)), hd,
+                           A.phasepoint(hd, torch.as_tensor(th, device=DEV), torch.as_tensor(r, device=DEV)), 17, return_info=True)
+        hh = A.Hamiltonian(A.DiagEuclideanMetric(buf(Minv)), A.DiagGaussian(m, s))
+        z0 = A.phasepoint(hh, buf(th), buf(r))
+        z0.lp.gradient = buf(z0.lp.gradient)
+        out = None
+        if pinned:
+            out = A.PhasePoint(buf(np.zeros((N, D))), buf(np.zeros((N, D))), A.DualValue(buf(np.zeros(N)), buf(np.zeros((N, D)))),
+                               A.DualValue(buf(np.zeros(N)), buf(np.zeros((N, D)))))
+        zh, infoh = A.step(A.Leapfrog(buf(eps)), hh, z0, 17, return_info=True, out=out)
         for a, b in [(zh.theta, zd.theta), (zh.r, zd.r), (zh.lp.value, zd.lp.value), (zh.lk.value, zd.lk.value),
                      (zh.lp.gradient, zd.lp.gradient), (zh.lk.gradient, zd.lk.gradient), (infoh.steps_done, infod.steps_done)]:
             assert np.array_equal(a, b.cpu().numpy())
