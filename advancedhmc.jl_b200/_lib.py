@@ -80,6 +80,7 @@ PROTOTYPES = {
                                        C.c_double, C.c_int32, C.POINTER(Rng), C.POINTER(PhasePoint),
                                        C.POINTER(PhasePoint), _vp, C.POINTER(Stats), C.c_uint32]),
     "ahmc_adapt_summary_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
+    "ahmc_adapt_cov_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
 }
 
 _lib = None

@@ -21,16 +21,34 @@ from . import core as A
 
 
 # ------------------------------------------------------------------------------------------------ records
-def merge_records(records: List[np.ndarray]) -> np.ndarray:
-    """Chan merge of per-rank records [n, sum_alpha, mean[D], M2[D]] in list (= rank) order."""
+def merge_records(records: List[np.ndarray], kind: str = "diag") -> np.ndarray:
+    """Chan merge of per-rank records in list (= rank) order.  Layouts (D inferred from the size):
+       "diag"   [n, sum_alpha, mean[D], M2[D]]
+       "nutpie" [n, sum_alpha, mean[D], M2[D], mean_g[D], M2_g[D]]            (positions and gradients)
+       "cov"    [n, sum_alpha, mean[D], M2[D], M2full[D*D]]                    (dense second moment)"""
     out = np.array(records[0], dtype=np.float64, copy=True)
-    D = (out.size - 2) // 2
+    if kind == "diag":
+        D = (out.size - 2) // 2
+    elif kind == "nutpie":
+        D = (out.size - 2) // 4
+    elif kind == "cov":
+        D = int(round(-1 + math.sqrt(1 + (out.size - 2)))) if out.size > 2 else 0  # D^2 + 2D = size - 2
+        assert 2 + 2 * D + D * D == out.size, "bad cov record size"
+    else:
+        raise ValueError(kind)
     for rec in records[1:]:
         n_a, n_b = out[0], rec[0]
         n = n_a + n_b
+        w = n_a * n_b / n
         delta = rec[2:2 + D] - out[2:2 + D]
-        out[2 + D:] = out[2 + D:] + rec[2 + D:] + delta * delta * (n_a * n_b / n)
-        out[2:2 + D] = out[2:2 + D] + delta * (n_b / n)
+        out[2 + D:2 + 2 * D] += rec[2 + D:2 + 2 * D] + delta * delta * w
+        if kind == "cov":
+            out[2 + 2 * D:] += rec[2 + 2 * D:] + (np.outer(delta, delta) * w).ravel()
+        out[2:2 + D] += delta * (n_b / n)
+        if kind == "nutpie":
+            dg = rec[2 + 2 * D:2 + 3 * D] - out[2 + 2 * D:2 + 3 * D]
+            out[2 + 3 * D:] += rec[2 + 3 * D:] + dg * dg * w
+            out[2 + 2 * D:2 + 3 * D] += dg * (n_b / n)
         out[1] = out[1] + rec[1]
         out[0] = n
     return out
@@ -128,6 +146,84 @@ class WelfordVar:
             self.var = self.get_estimation()
 
 
+class NutpieVar:
+    """Pooled NutpieVar (src/adaptation/massmatrix.jl:172-250): WelfordVar of the positions and of the gradients,
+    estimate sqrt(var_theta / var_grad) from the two regularised Welford estimates."""
+    record_kind = "nutpie"
+
+    def __init__(self, D: int, n_min: int = 10):
+        self.D, self.n_min = D, n_min
+        self.pos, self.grad = WelfordVar(D, n_min), WelfordVar(D, n_min)
+        self.var = np.ones(D)
+        self.n = 0.0
+
+    def reset(self):
+        self.n = 0.0
+        self.pos.reset()
+        self.grad.reset()
+
+    def push_record(self, rec: np.ndarray):
+        D = self.D
+        self.pos.push_record(rec[:2 + 2 * D])
+        self.grad.push_record(np.concatenate([rec[:2], rec[2 + 2 * D:2 + 4 * D]]))
+        self.n = self.pos.n
+
+    def get_estimation(self):  # massmatrix.jl:244-248
+        return np.sqrt(self.pos.get_estimation() / self.grad.get_estimation())
+
+    def update(self):
+        if self.n >= self.n_min:
+            self.var = self.get_estimation()
+
+
+class WelfordCov:
+    """Pooled WelfordCov (src/adaptation/massmatrix.jl:286-340): (n, mean, M2 full) records, Chan-merged;
+    estimate n/((n+5)(n-1)) M + 1e-3 * 5/(n+5) I.  `var` holds the D x D covariance (-> DenseEuclideanMetric)."""
+    record_kind = "cov"
+
+    def __init__(self, D: int, n_min: int = 10):
+        self.D, self.n_min = D, n_min
+        self.var = np.eye(D)
+        self.reset()
+
+    def reset(self):
+        self.n, self.mu, self.M = 0.0, np.zeros(self.D), np.zeros((self.D, self.D))
+
+    def push_record(self, rec: np.ndarray):
+        D = self.D
+        n_b, mean_b, M2_b = rec[0], rec[2:2 + D], rec[2 + 2 * D:2 + 2 * D + D * D].reshape(D, D)
+        n = self.n + n_b
+        delta = mean_b - self.mu
+        self.M = self.M + M2_b + np.outer(delta, delta) * (self.n * n_b / n)
+        self.mu = self.mu + delta * (n_b / n)
+        self.n = n
+
+    def get_estimation(self):  # massmatrix.jl:335-340
+        n = self.n
+        return n / ((n + 5) * (n - 1)) * self.M + 1e-3 * (5 / (n + 5)) * np.eye(self.D)
+
+    def update(self):
+        if self.n >= self.n_min:
+            self.var = self.get_estimation()
+
+
+def iteration_record(z, acceptance_rate, kind: str = "diag"):
+    """This rank's adaptor record of one iteration, built on the device (K5 / K5b), ready for the all-gather."""
+    rec = A.adapt_summary(z.theta, acceptance_rate)
+    if kind == "diag":
+        return rec
+    D = z.theta.shape[1]
+    if kind == "nutpie":
+        extra = A.adapt_summary(z.lp.gradient, None)[2:]
+    else:
+        extra = A.adapt_cov(z.theta, rec[2:2 + D]).reshape(-1)
+    if hasattr(rec, "detach"):
+        import torch
+
+        return torch.cat([rec, extra])
+    return np.concatenate([rec, extra])
+
+
 class UnitMassMatrix:
     var = None
 
@@ -209,38 +305,107 @@ class SampleResult:
     eps: float
     Minv: Optional[np.ndarray]
     leapfrog_steps: int = 0
+    timing: dict = field(default_factory=dict)  # wall seconds: transition / adapt / sampling_launch / bookkeeping
+
+
+def _mean(x):
+    return x.double().mean() if hasattr(x, "double") else np.asarray(x, dtype=np.float64).mean()
+
+
+def _sum(x):
+    return x.sum() if hasattr(x, "detach") else np.asarray(x).sum()
 
 
 def sample(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_samples: int, adaptor=None, n_adapts: int = 0,
-           keep_draws: bool = False, drop_warmup: bool = False) -> SampleResult:
+           keep_draws: bool = False, drop_warmup: bool = False, fused_sampling: bool = True) -> SampleResult:
     """`sample(rng, h, kappa, theta, n_samples, adaptor, n_adapts)` (src/sampler.jl:159-248) for N chains on this
-    rank, pooled adaptation across chains and ranks.  Per iteration: one fused transition kernel (K2 / K3), and
-    during warm-up one K5 launch + one all-gather of the (2+2D)-double record."""
+    rank, pooled adaptation across chains and ranks.
+    Warm-up iterations (i <= n_adapts): one fused transition kernel (K2 / K3), one K5 launch and one all-gather of
+    the (2+2D)-double record each -- the adaptor must see iteration i before iteration i+1 starts.
+    Sampling iterations (i > n_adapts) have no such dependency: with a Philox RNG they run as ONE persistent launch
+    (`sample_transitions`), every chain advancing at its own pace (`fused_sampling=False` keeps the loop)."""
+    import time
+
     import torch
 
+    tm = dict(transition=0.0, adapt=0.0, sampling_launch=0.0, bookkeeping=0.0)
     z = A.phasepoint(h, theta, torch.zeros_like(theta))  # sample_init (sampler.jl:36-46); r is refreshed anyway
-    draws, stats, total_steps = [], [], 0
-    if adaptor is not None and n_adapts > 0:
+    draws, total_steps = [], 0
+    acc, nerr, nst, eps_used, is_adapt = [], [], [], [], []  # per-iteration pooled scalars, fetched once at the end
+    n_adapts = min(n_adapts, n_samples) if adaptor is not None else 0
+    if n_adapts > 0:
         adaptor.initialize(n_adapts)
-    for i in range(1, n_samples + 1):
+    minv_seen = None
+
+    def one(i, adapting):
+        nonlocal z, h, kappa, minv_seen
+        t0 = time.perf_counter()
         tr = A.transition(rng, h, kappa, z)
         z = tr.z
-        if adaptor is not None and i <= n_adapts:  # Adaptation.adapt! glue (sampler.jl:72-90)
-            rec = merge_records(allgather_records(A.adapt_summary(z.theta, tr.stat["acceptance_rate"])))
+        t1 = time.perf_counter()
+        eps_used.append(A.step_size(kappa.tau.integrator))
+        if adapting:  # Adaptation.adapt! glue (sampler.jl:72-90)
+            kind = getattr(getattr(adaptor, "pc", None), "record_kind", "diag")
+            rec = merge_records(allgather_records(iteration_record(z, tr.stat["acceptance_rate"], kind)), kind)
             adaptor.adapt(rec)
             if i == n_adapts:
                 adaptor.finalize()
-            if adaptor.Minv is not None:
-                h = A.Hamiltonian(A.renew(h.metric, np.array(adaptor.Minv)), h.target)  # update(h, adaptor)
+            if adaptor.Minv is not None and adaptor.Minv is not minv_seen:  # update(h, adaptor): only when it changed
+                minv_seen = adaptor.Minv
+                h = A.Hamiltonian(A.renew(h.metric, np.array(minv_seen)), h.target)
             tau = kappa.tau
             kappa = A.HMCKernel(A.Trajectory(tau.sampler, A.update_nom_step_size(tau.integrator, adaptor.eps),
                                              tau.termination_criterion), kappa.refreshment)
+        t2 = time.perf_counter()
+        acc.append(_mean(tr.stat["acceptance_rate"]))
+        nerr.append(_sum(tr.stat["numerical_error"]))
         ns = tr.stat["n_steps"]
-        total_steps += int(ns.sum().item()) if hasattr(ns, "sum") else int(ns) * theta.shape[0]
-        stats.append(dict(acceptance_rate=float(tr.stat["acceptance_rate"].mean().item()),
-                          step_size=A.step_size(kappa.tau.integrator),
-                          numerical_error=int(tr.stat["numerical_error"].sum().item()), is_adapt=i <= n_adapts))
-        if keep_draws and (not drop_warmup or i > n_adapts):
+        nst.append(_sum(ns) if hasattr(ns, "sum") else int(ns) * theta.shape[0])
+        is_adapt.append(adapting)
+        if keep_draws and (not drop_warmup or not adapting):
             draws.append(z.theta.clone())
+        t3 = time.perf_counter()
+        tm["transition"] += t1 - t0
+        tm["adapt"] += t2 - t1
+        tm["bookkeeping"] += t3 - t2
+
+    for i in range(1, n_adapts + 1):
+        one(i, True)
+    n_rest = n_samples - n_adapts
+    if n_rest > 0 and fused_sampling and isinstance(rng, A.PhiloxRNG) and type(kappa.tau.integrator) is A.Leapfrog:
+        t0 = time.perf_counter()
+        z, dr, st = A.sample_transitions(rng, h, kappa, z, n_rest, keep_draws=keep_draws)
+        if hasattr(z.theta, "is_cuda") and z.theta.is_cuda:
+            torch.cuda.synchronize(z.theta.device)
+        tm["sampling_launch"] += time.perf_counter() - t0
+        a, e, n = st["acceptance_rate"], st["numerical_error"], st["n_steps"]
+        if hasattr(a, "detach"):
+            acc.extend(a.double().mean(dim=1).unbind())
+            nerr.extend(e.sum(dim=1).unbind())
+            nst.extend(n.sum(dim=1).unbind())
+        else:
+            acc.extend(np.asarray(a, dtype=np.float64).mean(axis=1))
+            nerr.extend(np.asarray(e).sum(axis=1))
+            nst.extend(np.asarray(n).sum(axis=1))
+        eps_used.extend([A.step_size(kappa.tau.integrator)] * n_rest)
+        is_adapt.extend([False] * n_rest)
+        if keep_draws:
+            draws.extend(dr.unbind(0) if hasattr(dr, "unbind") else list(dr))
+    else:
+        for i in range(n_adapts + 1, n_samples + 1):
+            one(i, False)
+
+    t0 = time.perf_counter()
+
+    def fetch(xs):  # one device->host transfer for the whole run
+        if xs and hasattr(xs[0], "detach"):
+            return torch.stack([x.double() for x in xs]).cpu().numpy()
+        return np.asarray([float(x) for x in xs], dtype=np.float64)
+
+    acc_h, nerr_h, nst_h = fetch(acc), fetch(nerr), fetch(nst)
+    stats = [dict(acceptance_rate=float(acc_h[k]), step_size=eps_used[k], numerical_error=int(nerr_h[k]),
+                  n_steps=int(nst_h[k]), is_adapt=is_adapt[k]) for k in range(len(acc))]
+    total_steps = int(nst_h.sum())
+    tm["bookkeeping"] += time.perf_counter() - t0
     return SampleResult(z.theta, draws, stats, A.step_size(kappa.tau.integrator),
-                        None if adaptor is None else adaptor.Minv, total_steps)
+                        None if adaptor is None else adaptor.Minv, total_steps, tm)

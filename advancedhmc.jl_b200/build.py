@@ -13,6 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.environ.get("AHMC_OBJ_DIR", "/tmp/ahmc_b200_obj")  # objects stay out of the repo snapshot
 LIB = os.path.join(HERE, "libahmc_b200.so")
 SOURCES = ["ahmc_api.cu", "ahmc_leapfrog.cu", "ahmc_nuts.cu", "ahmc_adapt.cu", "ahmc_multinomial.cu", "ahmc_dense.cu"]
+MB_LIB = os.path.join(HERE, "libahmc_microbench.so")  # bench.py's measurement helpers; not part of the C ABI
+MB_SOURCE = "ahmc_microbench.cu"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v" if os.environ.get("AHMC_PTXAS_V") else "-O3"]
@@ -34,10 +36,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     stamp = LIB + ".digest"  # travels with the .so (the _obj/ directory is not shipped to the GPU box)
     dg = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dg:
+    if (not force and os.path.exists(LIB) and os.path.exists(MB_LIB) and os.path.exists(stamp)
+            and open(stamp).read() == dg):
         return LIB
     if not os.path.exists(NVCC):
         raise RuntimeError(f"nvcc not found at {NVCC}: cannot build libahmc_b200.so (no CPU fallback exists)")
+    r = subprocess.run([NVCC, *FLAGS, "-shared", os.path.join(CSRC, MB_SOURCE), "-o", MB_LIB, "-cudart", "shared"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {MB_SOURCE}:\n{r.stdout}\n{r.stderr}")
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))

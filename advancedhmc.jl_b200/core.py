@@ -900,3 +900,15 @@ def adapt_summary(theta, acceptance_rate):
     ctx.check(ctx.lib.ahmc_adapt_summary_f64(ctx.h, D, N, _ptr(theta), D, _ptr(acceptance_rate), _ptr(out),
                                              L.FLAG_HOST_BUFFERS if _is_host(theta) else 0))
     return out
+
+
+def adapt_cov(theta, mean):
+    """-> (D, D) float64 second-moment matrix sum_c (theta_c - mean)(theta_c - mean)' (ahmc_adapt_cov_f64);
+    `mean` = adapt_summary(theta, .)[2:2+D]."""
+    ctx = get_context(_device_of(theta))
+    N, D = tuple(theta.shape)
+    out = _like(theta, (D, D))
+    _sync_torch(theta)
+    ctx.check(ctx.lib.ahmc_adapt_cov_f64(ctx.h, D, N, _ptr(theta), D, _ptr(mean), _ptr(out),
+                                         L.FLAG_HOST_BUFFERS if _is_host(theta) else 0))
+    return out

@@ -77,4 +77,68 @@ cudaError_t launch_adapt_summary(int D, long long N, const double* theta, long l
     return cudaGetLastError();
 }
 
+// K5b: full second-moment matrix about a given mean, for the pooled WelfordCov (massmatrix.jl:286-340):
+//     out[i + D*j] = sum_c (theta[i, c] - mean[i]) * (theta[j, c] - mean[j])            (symmetric, D x D)
+// One CTA per 32x32 output tile of the upper triangle walks ALL chains in slabs of 32 (centred slabs staged in
+// shared memory, 2x2 outputs per thread), so every entry is one fixed-order sum: deterministic, no atomics; the
+// mirror entry is written by the same thread.
+constexpr int kCovTile = 32;
+
+__global__ void __launch_bounds__(256) adapt_cov_kernel(int D, long long N, const double* __restrict__ theta, long long ld,
+                                                         const double* __restrict__ mean, double* __restrict__ out) {
+    // tile index -> (ti, tj) with ti <= tj
+    const int T = (D + kCovTile - 1) / kCovTile;
+    int t = blockIdx.x, ti = 0;
+    while (t >= T - ti) {
+        t -= T - ti;
+        ++ti;
+    }
+    const int tj = ti + t;
+    __shared__ double A[kCovTile][kCovTile + 1];  // [chain in slab][coordinate i]
+    __shared__ double Bm[kCovTile][kCovTile + 1];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const int li = threadIdx.x % kCovTile, lc = threadIdx.x / kCovTile;  // loader mapping: 8 chains x 32 coordinates
+    const int gi = ti * kCovTile + li, gj = tj * kCovTile + li;
+    const double mi = gi < D ? mean[gi] : 0.0, mj = gj < D ? mean[gj] : 0.0;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (long long c0 = 0; c0 < N; c0 += kCovTile) {
+#pragma unroll
+        for (int k = 0; k < kCovTile / 8; ++k) {
+            const int cc = lc + 8 * k;
+            const long long c = c0 + cc;
+            const bool ok = c < N;
+            A[cc][li] = (ok && gi < D) ? theta[ld * c + gi] - mi : 0.0;
+            Bm[cc][li] = (ok && gj < D) ? theta[ld * c + gj] - mj : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int cc = 0; cc < kCovTile; ++cc) {
+            const double a0 = A[cc][ty], a1 = A[cc][ty + 16], b0 = Bm[cc][tx], b1 = Bm[cc][tx + 16];
+            acc[0][0] = fma(a0, b0, acc[0][0]);
+            acc[0][1] = fma(a0, b1, acc[0][1]);
+            acc[1][0] = fma(a1, b0, acc[1][0]);
+            acc[1][1] = fma(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int i = ti * kCovTile + ty + 16 * p, j = tj * kCovTile + tx + 16 * q;
+            if (i < D && j < D) {
+                out[(size_t)i + (size_t)D * j] = acc[p][q];
+                if (ti != tj) out[(size_t)j + (size_t)D * i] = acc[p][q];
+            }
+        }
+}
+
+cudaError_t launch_adapt_cov(int D, long long N, const double* theta, long long ld, const double* mean, double* out,
+                             cudaStream_t st, int* n_launches) {
+    const int T = (D + kCovTile - 1) / kCovTile;
+    adapt_cov_kernel<<<T * (T + 1) / 2, 256, 0, st>>>(D, N, theta, ld, mean, out);
+    if (n_launches) *n_launches += 1;
+    return cudaGetLastError();
+}
+
 }  // namespace ahmc

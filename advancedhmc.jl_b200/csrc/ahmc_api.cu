@@ -1442,4 +1442,26 @@ int ahmc_adapt_summary_f64(ahmc_ctx* ctx, int32_t D, int64_t N, const double* th
     return finish_call(ctx, st, flags);
 }
 
+int ahmc_adapt_cov_f64(ahmc_ctx* ctx, int32_t D, int64_t N, const double* theta, int64_t ld, const double* mean,
+                       double* out, uint32_t flags) {
+    if (!ctx || !theta || !mean || !out) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/theta/mean/out");
+    if (D < 1 || N < 1 || ld < D) return fail(ctx, AHMC_ERR_INVALID, "need D >= 1, N >= 1, ld >= D");
+    DeviceGuard g(ctx->device);
+    Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
+    st.reserve((size_t)ld * N * 8);
+    st.reserve((size_t)D * 8);
+    st.reserve((size_t)D * D * 8);
+    int rc = st.prepare();
+    if (rc) return rc;
+    const double *d_theta, *d_mean;
+    double* d_out;
+    if ((rc = st.in(theta, (size_t)ld * N, &d_theta))) return rc;
+    if ((rc = st.in(mean, (size_t)D, &d_mean))) return rc;
+    if ((rc = st.out(out, (size_t)D * D, &d_out))) return rc;
+    int nl = 0;
+    CU(launch_adapt_cov(D, N, d_theta, ld, d_mean, d_out, ctx->stream, &nl));
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
 }  // extern "C"

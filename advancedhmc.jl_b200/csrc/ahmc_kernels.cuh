@@ -216,6 +216,8 @@ cudaError_t launch_mh_select(const MhArgs& a, cudaStream_t stream, int* n_launch
 cudaError_t launch_adapt_summary(int D, long long N, const double* theta, long long ld, const double* alpha,
                                  double* out, double* partial, unsigned* counter, int blocks, cudaStream_t st,
                                  int* n_launches);
+cudaError_t launch_adapt_cov(int D, long long N, const double* theta, long long ld, const double* mean, double* out,
+                             cudaStream_t st, int* n_launches);
 
 constexpr int kBlockThreads = 128;
 

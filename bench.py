@@ -334,6 +334,41 @@ def run_ours(args):
             flops = 2.0 * DIM * DIM * N_CHAINS * L_STEPS
             k4 = {"workload": "C2-style: 4096 chains x D=128 correlated Gaussian (dense precision), Diag metric, L=32 fused, tiled DMMA kernel",
                   "ms_per_launch": ms, "rate_steps_dims_per_s": units_per_step / ms * 1e3, "fp64_tflops_gemm": flops / ms / 1e9}
+            # the same contraction through cuBLAS Dgemm: one [D x D] @ [D x N] product per step, 32 per
+            # trajectory, as a step-at-a-time implementation would issue them; and a large Dgemm for the DMMA peak
+            P64 = torch.as_tensor((Q / lam) @ Q.T, device=dev)
+            X64 = torch.as_tensor(th, device=dev).T.contiguous()
+            Y64 = torch.empty_like(X64)
+            for _ in range(3):
+                torch.matmul(P64, X64, out=Y64)
+            e0.record(stream)
+            for _ in range(10 * L_STEPS):
+                torch.matmul(P64, X64, out=Y64)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms_cb = e0.elapsed_time(e1) / 10
+            k4["cublas_dgemm_same_shape"] = {"what": "torch.matmul fp64 [128x128]@[128x4096], 32 calls = the gradient GEMMs of one trajectory (no leapfrog arithmetic)",
+                                             "ms_per_32": ms_cb, "tflops": flops / ms_cb / 1e9}
+            Ab = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+            Cb = torch.empty_like(Ab)
+            torch.matmul(Ab, Ab, out=Cb)
+            e0.record(stream)
+            for _ in range(3):
+                torch.matmul(Ab, Ab, out=Cb)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            k4["cublas_dgemm_4096_tflops"] = 2.0 * 4096 ** 3 * 3 / e0.elapsed_time(e1) / 1e9
+            del Ab, Cb
+
+        # ---- fp64 FMA-pipe peak (the bound of the fused fast path), measured by a DFMA microbenchmark
+        dfma = None
+        if rank == 0 and not args.no_extras:
+            import ctypes
+            mb = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "advancedhmc.jl_b200", "libahmc_microbench.so"))
+            tf, msb = ctypes.c_double(), ctypes.c_double()
+            rcmb = mb.ahmc_mb_dfma_peak(ctypes.c_int(local), ctypes.c_int(2048), ctypes.c_int(5), ctypes.byref(tf), ctypes.byref(msb))
+            if rcmb == 0:
+                dfma = {"tflops": tf.value, "ms": msb.value, "what": "148*8 blocks x 256 threads x 8 independent DFMA chains (libahmc_microbench.so)"}
 
     # ---- e2e: the public call with HOST (pinned) buffers, copies inside the timed region
     thp = torch.as_tensor(th).pin_memory()
@@ -420,6 +455,11 @@ def run_ours(args):
         line["hmc_transition"] = k2
     if k4:
         line["dense_target_trajectory"] = k4
+    if dfma:
+        line["fp64_fma_peak"] = dfma
+        roofline["frac_fp64_fma_pipe"] = roofline["fp64_tflops_fastpath"] / dfma["tflops"]
+        if honest and "fused_L32" in honest:
+            honest["fused_L32"]["frac_fp64_fma_pipe"] = honest["fused_L32"]["fp64_tflops"] / dfma["tflops"]
     args.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

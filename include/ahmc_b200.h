@@ -226,6 +226,13 @@ int ahmc_nuts_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metr
 int ahmc_adapt_summary_f64(ahmc_ctx* ctx, int32_t D, int64_t N, const double* theta, int64_t ld,
                            const double* acceptance_rate, double* out /* 2+2D */, uint32_t flags);
 
+/* Dense companion of the record above, for the pooled `WelfordCov` (src/adaptation/massmatrix.jl:286-340):
+ *   out[i + D*j] = sum_c (theta[i,c] - mean[i]) * (theta[j,c] - mean[j])      (D x D, symmetric)
+ * with `mean` = out[2 .. 2+D) of ahmc_adapt_summary_f64 on the same theta.  Records (n, mean, M2) of different
+ * ranks / iterations merge exactly (Chan): M2 = M2_a + M2_b + (n_a n_b / n) dd', d = mean_b - mean_a. */
+int ahmc_adapt_cov_f64(ahmc_ctx* ctx, int32_t D, int64_t N, const double* theta, int64_t ld, const double* mean,
+                       double* out /* D*D */, uint32_t flags);
+
 #ifdef __cplusplus
 }
 #endif

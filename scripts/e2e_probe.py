@@ -36,23 +36,29 @@ def check(tag):
     ok = all(np.array_equal(a, b.cpu().numpy()) for a, b in [(zout.theta, zd.theta), (zout.r, zd.r), (zout.lp.value, zd.lp.value),
                                                              (zout.lk.value, zd.lk.value), (zout.lp.gradient, zd.lp.gradient)])
     print(tag, "bit-identical to the device call:", ok, flush=True)
-best = None
-for up, down in (("ce1", "ce"), ("ce3", "ce"), ("ce1", "direct"), ("ce3", "direct"), ("direct", "direct"), ("direct", "ce")):
-    for chunks in ("1", "2", "3", "4", "6", "8", "16"):
-        os.environ["AHMC_PIPE_UP"], os.environ["AHMC_PIPE_DOWN"], os.environ["AHMC_PIPE_CHUNKS"] = up, down, chunks
-        for o in outs: o.zero_()
-        ms = min(t(plan, 30) for _ in range(2))
-        ok = all(np.array_equal(a, b.cpu().numpy()) for a, b in [(zout.theta, zd.theta), (zout.r, zd.r), (zout.lp.value, zd.lp.value),
-                                                                 (zout.lk.value, zd.lk.value), (zout.lp.gradient, zd.lp.gradient)])
-        print("up", up, "down", down, "chunks", chunks, "e2e call ms %.4f" % ms, "bit-identical" if ok else "MISMATCH", flush=True)
-        if best is None or ms < best[0]: best = (ms, up, down, chunks)
-print("best", best)
-for k in ("AHMC_PIPE_UP", "AHMC_PIPE_DOWN", "AHMC_PIPE_CHUNKS"): os.environ.pop(k)
-print("library defaults: e2e call ms %.4f" % t(plan, 40))
-os.environ["AHMC_PIPE_TRACE"] = "1"
-for up, down, chunks in (("ce3", "ce", "8"), ("ce3", "direct", "4"), ("ce1", "direct", "4"), ("direct", "direct", "4"), best[1:]):
+for up, down, chunks in (("ce1", "ce", "2"), ("ce1", "direct", "2"), ("direct", "direct", "1"), ("direct", "direct", "16")):
     os.environ["AHMC_PIPE_UP"], os.environ["AHMC_PIPE_DOWN"], os.environ["AHMC_PIPE_CHUNKS"] = up, down, chunks
-    plan(); plan()
+    print("up", up, "down", down, "chunks", chunks, "e2e call ms %.4f" % min(t(plan, 30) for _ in range(2)), flush=True)
+for k in ("AHMC_PIPE_UP", "AHMC_PIPE_DOWN", "AHMC_PIPE_CHUNKS"): os.environ.pop(k)
+print("library defaults: e2e call ms %.4f" % min(t(plan, 40) for _ in range(2)))
+check("library defaults")
+# how much of the bidirectional PCIe rate survives small copies?  n copies of `mb` MiB each way, two streams
+for mb in (0.5, 1, 2, 4, 12):
+    n = int(mb * 2 ** 20 // 8)
+    reps = max(1, int(24 / mb))
+    hs, ds = h_a[:n], d_a[:n]
+    hd, dd = h_a2[:n], d_b[:n]
+    def bid():
+        with torch.cuda.stream(s1):
+            for _ in range(reps): ds.copy_(hs, non_blocking=True)
+        with torch.cuda.stream(s2):
+            for _ in range(reps): hd.copy_(dd, non_blocking=True)
+    def uni():
+        with torch.cuda.stream(s1):
+            for _ in range(reps): ds.copy_(hs, non_blocking=True)
+    tb, tu = t(bid, 5), t(uni, 5)
+    gb = reps * n * 8 / 1e9
+    print("copies of %.1f MiB: H2D alone %.1f GB/s; H2D || D2H %.1f GB/s each way" % (mb, gb / (tu * 1e-3), gb / (tb * 1e-3)), flush=True)
 # small batches: latency of one call
 for n in (256, 1024):
     for k in ("AHMC_PIPE_UP", "AHMC_PIPE_DOWN", "AHMC_PIPE_CHUNKS", "AHMC_PIPE_TRACE"): os.environ.pop(k, None)

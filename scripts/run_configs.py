@@ -93,7 +93,8 @@ def run(name, world, rank, dev, scale, iters):
                mean_accept=float(np.mean([s["acceptance_rate"] for s in res.stats[n_adapts:]])),
                divergent=int(sum(s["numerical_error"] for s in res.stats[n_adapts:])),
                theta_mean_abs_max=float(th.mean(dim=0).abs().max().item()), theta_std_first=float(th[:, 0].std().item()),
-               timing="wall clock around the whole sample() loop (python host loop + kernels + adaptor exchange)")
+               timing="wall clock around the whole sample() loop (python host loop + kernels + adaptor exchange)",
+               breakdown_s={k: round(v, 4) for k, v in res.timing.items()})
     if rank == 0:
         print(json.dumps(out), flush=True)
 

@@ -132,3 +132,65 @@ def test_adaptor_record_allgather_world_size_2_gloo():
         recs.append(_record(t, a))
     assert np.array_equal(res[0], ad.merge_records(recs))
     assert res[0][0] == 11
+
+
+def _welford_cov_reference(xs):
+    """sequential restatement of `push!(::WelfordCov, s)` + `get_estimation` (src/adaptation/massmatrix.jl:324-340)."""
+    D = xs.shape[1]
+    n, mu, M = 0, np.zeros(D), np.zeros((D, D))
+    for s in xs:
+        n += 1
+        delta = s - mu
+        mu = mu + delta / n
+        M = M + np.outer(s - mu, delta)
+    return n, mu, M, n / ((n + 5) * (n - 1)) * M + 1e-3 * (5 / (n + 5)) * np.eye(D)
+
+
+def _record_cov(theta, alpha):
+    mu = theta.mean(axis=0)
+    c = theta - mu
+    return np.concatenate([_record(theta, alpha), (c.T @ c).ravel()])
+
+
+def _record_nutpie(theta, grad, alpha):
+    return np.concatenate([_record(theta, alpha), _record(grad, alpha)[2:]])
+
+
+def test_merge_records_cov_and_nutpie_layouts():
+    rng = np.random.default_rng(3)
+    D = 5
+    L = rng.normal(size=(D, D))
+    parts = [rng.normal(size=(n, D)) @ L + 0.5 for n in (4, 1, 33, 2)]
+    grads = [-(p - 0.5) @ np.linalg.inv(L @ L.T) for p in parts]
+    alphas = [rng.uniform(0, 1.5, size=p.shape[0]) for p in parts]
+    allx, allg, alla = np.concatenate(parts), np.concatenate(grads), np.concatenate(alphas)
+    got = ad.merge_records([_record_cov(p, a) for p, a in zip(parts, alphas)], "cov")
+    assert np.allclose(got, _record_cov(allx, alla), rtol=1e-12, atol=1e-12)
+    got = ad.merge_records([_record_nutpie(p, g, a) for p, g, a in zip(parts, grads, alphas)], "nutpie")
+    assert np.allclose(got, _record_nutpie(allx, allg, alla), rtol=1e-12, atol=1e-12)
+
+
+def test_pooled_welford_cov_and_nutpie_equal_the_sequential_reference_estimators():
+    rng = np.random.default_rng(4)
+    D = 4
+    L = rng.normal(size=(D, D))
+    xs = rng.normal(size=(48, D)) @ L
+    gs = -xs @ np.linalg.inv(L @ L.T)
+    n, mu, M, est = _welford_cov_reference(xs)
+    # one chain per record (the reference's own granularity) and 16 chains per record give the same estimator
+    for chunk in (1, 16):
+        wc, nv = ad.WelfordCov(D), ad.NutpieVar(D)
+        for k in range(0, len(xs), chunk):
+            a = np.ones(chunk)
+            wc.push_record(_record_cov(xs[k:k + chunk], a))
+            nv.push_record(_record_nutpie(xs[k:k + chunk], gs[k:k + chunk], a))
+        assert wc.n == n and np.allclose(wc.mu, mu, rtol=1e-12) and np.allclose(wc.M, M, rtol=1e-11, atol=1e-12)
+        assert np.allclose(wc.get_estimation(), est, rtol=1e-11, atol=1e-13)
+        wv_x, wv_g = oc.WelfordVar((D,)), oc.WelfordVar((D,))
+        for x, g in zip(xs, gs):
+            wv_x.push(x), wv_g.push(g)
+        assert np.allclose(nv.get_estimation(), np.sqrt(wv_x.estimate() / wv_g.estimate()), rtol=1e-11)
+    wc.update(), nv.update()
+    assert wc.var.shape == (D, D) and nv.var.shape == (D,)
+    # for a Gaussian the Nutpie estimate is sqrt(var_x * var of (Sigma^-1 x))^-1 ... -> positive, finite
+    assert np.all(np.isfinite(nv.var)) and np.all(nv.var > 0)

@@ -97,3 +97,40 @@ def test_c5_nuts_dense_metric_d256():
     assert np.abs(W.mean(axis=0)).max() < 0.2 and abs(W.var(axis=0).mean() - 1) < 0.05
     assert st["acceptance_rate"][5:].mean().item() > 0.6
     # (with the exact metric every mode has the same frequency: NUTS trees resonate and grow deep -- not asserted)
+
+
+def test_nuts_dense_metric_adapted_with_pooled_welford_cov():
+    """NUTS + DenseEuclideanMetric whose M^-1 is adapted by the pooled WelfordCov (K5 + K5b records): the adapted
+    metric approaches the target covariance and the draws recover it (8a a15, massmatrix.jl:286-340)."""
+    D, N = 16, 512
+    Sigma, P = _corr_gauss(D, 11)
+    h = A.Hamiltonian(A.DenseEuclideanMetric(np.eye(D)), A.DenseGaussian(np.zeros(D), P))
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
+    adaptor = ad.StanHMCAdaptor(ad.WelfordCov(D), ad.NesterovDualAveraging(0.8, 0.1))
+    th0 = torch.as_tensor(np.random.default_rng(1).normal(size=(N, D)), device=DEV)
+    res = ad.sample(A.PhiloxRNG(5), h, kern, th0, 200, adaptor, 150, keep_draws=True, drop_warmup=True)
+    assert res.Minv.shape == (D, D)
+    rel = np.linalg.norm(res.Minv - Sigma) / np.linalg.norm(Sigma)
+    assert rel < 0.15, rel
+    X = torch.stack(list(res.draws)).reshape(-1, D).cpu().numpy()
+    emp = np.cov(X.T)
+    assert np.linalg.norm(emp - Sigma) / np.linalg.norm(Sigma) < 0.15
+    acc = np.mean([s["acceptance_rate"] for s in res.stats[150:]])
+    assert 0.6 < acc < 0.97, acc
+    assert res.timing["sampling_launch"] > 0  # the 50 post-warm-up transitions ran as one persistent launch
+
+
+def test_nuts_diag_metric_adapted_with_pooled_nutpie_var():
+    """NutpieVar (positions + gradients, massmatrix.jl:172-250): for an independent Gaussian N(0, s^2) the gradient
+    is -x/s^2, so sqrt(var_x / var_g) = s^2 exactly: the adapted M^-1 recovers the target variances."""
+    D, N = 24, 512
+    sd = np.exp(np.linspace(np.log(0.2), np.log(5.0), D))
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.DiagGaussian(np.zeros(D), sd))
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
+    adaptor = ad.StanHMCAdaptor(ad.NutpieVar(D), ad.NesterovDualAveraging(0.8, 0.1))
+    th0 = torch.as_tensor(np.random.default_rng(2).normal(size=(N, D)), device=DEV)
+    res = ad.sample(A.PhiloxRNG(6), h, kern, th0, 160, adaptor, 130)
+    ratio = res.Minv / sd ** 2
+    assert 0.8 < ratio.min() and ratio.max() < 1.25, (ratio.min(), ratio.max())
+    acc = np.mean([s["acceptance_rate"] for s in res.stats[130:]])
+    assert 0.6 < acc < 0.97, acc

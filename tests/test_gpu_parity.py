@@ -369,6 +369,25 @@ def test_adapt_summary_matches_numpy():
     assert np.array_equal(out, out2)  # deterministic reduction order
 
 
+@pytest.mark.parametrize("D,N", [(7, 33), (100, 4097), (256, 1024), (33, 5)])
+def test_adapt_cov_matches_numpy(D, N):
+    """K5b (ahmc_adapt_cov_f64): full second-moment matrix about the K5 mean, symmetric, deterministic; host buffers too."""
+    rng = np.random.default_rng(D)
+    Lm = rng.normal(size=(D, D)) / np.sqrt(D)
+    th = rng.normal(size=(N, D)) @ Lm + rng.normal(size=D)
+    tht = torch.as_tensor(th, device=DEV)
+    rec = A.adapt_summary(tht, None)
+    out = A.adapt_cov(tht, rec[2:2 + D]).cpu().numpy()
+    c = th - th.mean(axis=0)
+    want = c.T @ c
+    assert np.allclose(out, want, rtol=1e-11, atol=1e-11 * np.abs(want).max())
+    assert np.array_equal(out, out.T)
+    assert np.array_equal(out, A.adapt_cov(tht, rec[2:2 + D]).cpu().numpy())
+    assert np.allclose(np.diag(out), rec[2 + D:].cpu().numpy(), rtol=1e-11)
+    outh = A.adapt_cov(th, th.mean(axis=0))
+    assert np.allclose(outh, want, rtol=1e-11, atol=1e-11 * np.abs(want).max())
+
+
 # ------------------------------------------------------------------------------------------------ NUTS
 _SAMPLERS = {"multinomial": "MultinomialTS", "slice": "SliceTS"}
 _CRITERIA = {"generalised": "GeneralisedNoUTurn", "classic": "ClassicNoUTurn", "strict": "StrictGeneralisedNoUTurn"}
