@@ -10,11 +10,13 @@
 #include <vector>
 
 // defaults of the host-buffer lane (see leapfrog_host_pipelined), chosen by measurement on B200 (profiles/README.md,
-// "host-buffer lane"): page-locked buffers are read and written by the kernel directly, in launches of >= 256 chains
-// alternating between two streams; pageable buffers go through the copy engines in two chunks.
-#define AHMC_PIPE_DIRECT_CHUNK_CHAINS 256
-#define AHMC_PIPE_DIRECT_MAX_CHUNKS 16
+// "host-buffer lane"): page-locked buffers are read and written by the kernel directly in ONE launch whose residency
+// is capped at one CTA per SM, so the grid runs in staggered waves and uploads overlap downloads (0.36 ms against
+// 0.48 ms uncapped and 0.45-0.50 ms for the best copy-engine pipeline at 4096 x 128); pageable buffers go through
+// the copy engines in two chunks.
+#define AHMC_PIPE_DIRECT_CHUNKS 1
 #define AHMC_PIPE_CE_CHUNKS 2
+#define AHMC_PIPE_DIRECT_OCC 1  // resident CTAs per SM of a direct-access launch (0 = no cap)
 
 #include "ahmc_kernels.cuh"
 
@@ -660,11 +662,11 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
     if (!in_pinned && up == UP_DIRECT) up = UP_CE3;
     if (!out_pinned) down_direct = false;
     const bool trace = (ev = getenv("AHMC_PIPE_TRACE")) && atoi(ev) != 0;
+    const int occ_cap = (ev = getenv("AHMC_PIPE_OCC")) ? atoi(ev) : AHMC_PIPE_DIRECT_OCC;
     int nchunk = (ev = getenv("AHMC_PIPE_CHUNKS")) ? atoi(ev) : 0;
     if (nchunk <= 0) {
         if (up == UP_DIRECT) {
-            nchunk = (int)(N / AHMC_PIPE_DIRECT_CHUNK_CHAINS);
-            if (nchunk > AHMC_PIPE_DIRECT_MAX_CHUNKS) nchunk = AHMC_PIPE_DIRECT_MAX_CHUNKS;
+            nchunk = AHMC_PIPE_DIRECT_CHUNKS;
         } else {
             nchunk = N >= 1024 ? AHMC_PIPE_CE_CHUNKS : 1;
         }
@@ -788,6 +790,7 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
         a.status = !status ? nullptr : (stage_out ? oSt : b_st) + c0;
         a.steps_done = !steps_done ? nullptr : (stage_out ? oSd : b_sd) + c0;
         a.flags = flags;
+        a.resident_blocks_per_sm = (!stage_in || !stage_out) ? occ_cap : 0;
         // with direct loads the kernels of different chunks may run side by side: alternate two streams
         cudaStream_t s_k = (!stage_in && (k & 1)) ? ctx->pipe[4] : s_cmp;
         CU(launch_leapfrog(a, s_k, &nl));

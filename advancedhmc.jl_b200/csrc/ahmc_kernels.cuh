@@ -23,6 +23,7 @@ struct LeapfrogArgs {
     int* min_break;  // device int: atomicMin of the first non-finite step over all chains (COMPAT_BREAK_ALL)
     uint32_t flags;
     const uint8_t* only_mask;  // nullable: process only chains whose mask byte is non-zero (K4 exact fallback)
+    int resident_blocks_per_sm;  // 0 = as many as fit; > 0 caps residency (the launch pads the dynamic shared memory)
 };
 
 struct PhasepointArgs {

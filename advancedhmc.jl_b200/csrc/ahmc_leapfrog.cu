@@ -421,6 +421,12 @@ static cudaError_t launch_lf_t(const LeapfrogArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;
     const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
     size_t sm = smem_bytes(MODEL, METRIC, a.D, G);
+    if (a.resident_blocks_per_sm > 0) {
+        // occupancy throttle (host-memory lanes): pad the dynamic shared memory so that only this many CTAs fit on
+        // an SM; the grid then runs in staggered waves, some CTAs storing while others are still loading
+        const size_t pad = (size_t)(227 * 1024) / (size_t)a.resident_blocks_per_sm - 1024;
+        if (pad > sm) sm = pad;
+    }
     if (sm > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(leapfrog_kernel<MODEL, METRIC, G, E>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

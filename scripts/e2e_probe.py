@@ -39,6 +39,12 @@ def check(tag):
 for up, down, chunks in (("ce1", "ce", "2"), ("ce1", "direct", "2"), ("direct", "direct", "1"), ("direct", "direct", "16")):
     os.environ["AHMC_PIPE_UP"], os.environ["AHMC_PIPE_DOWN"], os.environ["AHMC_PIPE_CHUNKS"] = up, down, chunks
     print("up", up, "down", down, "chunks", chunks, "e2e call ms %.4f" % min(t(plan, 30) for _ in range(2)), flush=True)
+for occ in ("0", "1", "2", "3", "4", "5"):
+    for chunks in ("1", "2"):
+        os.environ.update(AHMC_PIPE_UP="direct", AHMC_PIPE_DOWN="direct", AHMC_PIPE_CHUNKS=chunks, AHMC_PIPE_OCC=occ)
+        print("direct/direct occ", occ, "chunks", chunks, "e2e call ms %.4f" % min(t(plan, 30) for _ in range(3)), flush=True)
+        check("occ " + occ)
+os.environ.pop("AHMC_PIPE_OCC")
 for k in ("AHMC_PIPE_UP", "AHMC_PIPE_DOWN", "AHMC_PIPE_CHUNKS"): os.environ.pop(k)
 print("library defaults: e2e call ms %.4f" % min(t(plan, 40) for _ in range(2)))
 check("library defaults")

@@ -129,8 +129,8 @@ def test_nuts_diag_metric_adapted_with_pooled_nutpie_var():
     kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
     adaptor = ad.StanHMCAdaptor(ad.NutpieVar(D), ad.NesterovDualAveraging(0.8, 0.1))
     th0 = torch.as_tensor(np.random.default_rng(2).normal(size=(N, D)), device=DEV)
-    res = ad.sample(A.PhiloxRNG(6), h, kern, th0, 160, adaptor, 130)
+    res = ad.sample(A.PhiloxRNG(6), h, kern, th0, 180, adaptor, 150)  # 150 warm-ups: one metric window ending at 100
     ratio = res.Minv / sd ** 2
     assert 0.8 < ratio.min() and ratio.max() < 1.25, (ratio.min(), ratio.max())
-    acc = np.mean([s["acceptance_rate"] for s in res.stats[130:]])
+    acc = np.mean([s["acceptance_rate"] for s in res.stats[150:]])
     assert 0.6 < acc < 0.97, acc
