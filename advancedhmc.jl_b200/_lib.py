@@ -42,6 +42,13 @@ class Rng(C.Structure):
                 ("partial_refresh_alpha", C.c_double)]
 
 
+class AdaptCfg(C.Structure):
+    _fields_ = [("n_adapts", C.c_int32), ("init_buffer", C.c_int32), ("term_buffer", C.c_int32), ("window_size", C.c_int32),
+                ("delta", C.c_double), ("gamma", C.c_double), ("t0", C.c_double), ("kappa", C.c_double),
+                ("adapt_metric", C.c_int32), ("n_min", C.c_int32), ("eps_chain", _vp), ("Minv_chain", _vp),
+                ("eps_trace", _vp)]
+
+
 LOGP_GRAD_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _vp, _vp, C.c_int32, C.c_int64, C.c_int64, _vp)
 
 # name -> (restype, argtypes): exactly the entry points include/ahmc_b200.h declares
@@ -79,6 +86,9 @@ PROTOTYPES = {
     "ahmc_nuts_sample_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_double, _vp, C.c_int32,
                                        C.c_double, C.c_int32, C.POINTER(Rng), C.POINTER(PhasePoint),
                                        C.POINTER(PhasePoint), _vp, C.POINTER(Stats), C.c_uint32]),
+    "ahmc_nuts_adapt_sample_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.c_int32, C.c_double,
+                                             C.c_int32, C.POINTER(AdaptCfg), C.POINTER(Rng), C.POINTER(PhasePoint),
+                                             C.POINTER(PhasePoint), _vp, C.POINTER(Stats), C.c_uint32]),
     "ahmc_adapt_summary_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
     "ahmc_adapt_cov_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
 }

@@ -330,6 +330,26 @@ def sample(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_samples: int, ada
 
     tm = dict(transition=0.0, adapt=0.0, sampling_launch=0.0, bookkeeping=0.0)
     z = A.phasepoint(h, theta, torch.zeros_like(theta))  # sample_init (sampler.jl:36-46); r is refreshed anyway
+    if isinstance(adaptor, A.VectorisedStanAdaptor):
+        # the reference's vectorised adaptors (per-chain eps and M^-1): warm-up and sampling are ONE launch
+        t0 = time.perf_counter()
+        zl, dr, st, eps, minv, _ = A.nuts_adapt_sample(rng, h, kappa, z, n_samples, min(n_adapts, n_samples), adaptor,
+                                                       keep_draws=keep_draws)
+        if hasattr(zl.theta, "is_cuda") and zl.theta.is_cuda:
+            torch.cuda.synchronize(zl.theta.device)
+        tm["sampling_launch"] = time.perf_counter() - t0
+        a, e, n = st["acceptance_rate"], st["numerical_error"], st["n_steps"]
+        acc_h = (a.double().mean(dim=1).cpu().numpy() if hasattr(a, "detach") else np.asarray(a).mean(axis=1))
+        nerr_h = (e.sum(dim=1).cpu().numpy() if hasattr(e, "detach") else np.asarray(e).sum(axis=1))
+        nst_h = (n.sum(dim=1).cpu().numpy() if hasattr(n, "detach") else np.asarray(n).sum(axis=1))
+        stats = [dict(acceptance_rate=float(acc_h[k]), step_size=None, numerical_error=int(nerr_h[k]), n_steps=int(nst_h[k]),
+                      is_adapt=k < n_adapts) for k in range(n_samples)]
+        dl = []
+        if keep_draws:
+            dl = list(dr.unbind(0) if hasattr(dr, "unbind") else dr)
+            if drop_warmup:
+                dl = dl[n_adapts:]
+        return SampleResult(zl.theta, dl, stats, eps, minv, int(nst_h.sum()), tm)
     draws, total_steps = [], 0
     acc, nerr, nst, eps_used, is_adapt = [], [], [], [], []  # per-iteration pooled scalars, fetched once at the end
     n_adapts = min(n_adapts, n_samples) if adaptor is not None else 0

@@ -888,6 +888,65 @@ def sample_transitions(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: Phas
     return out, draws, st
 
 
+@dataclass
+class VectorisedStanAdaptor:
+    """`StanHMCAdaptor(WelfordVar((D, N)), NesterovDualAveraging(delta, eps::Vector))`: the reference's vectorised
+    adaptors -- one dual-averaging state and one windowed variance estimator PER CHAIN (stepsize.jl:178-210,
+    massmatrix.jl:141-157, stan_adaptor.jl:13-50, 137-159).  Runs inside the NUTS launch (ahmc_nuts_adapt_sample_f64)."""
+    delta: float = 0.8
+    adapt_metric: bool = True
+    init_buffer: int = 75
+    term_buffer: int = 50
+    window_size: int = 25
+    gamma: float = 0.05
+    t0: float = 10.0
+    kappa: float = 0.75
+    n_min: int = 10
+
+
+def nuts_adapt_sample(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: PhasePoint, n_transitions: int, n_adapts: int,
+                      adaptor: VectorisedStanAdaptor, keep_draws: bool = True, keep_eps_trace: bool = False, flags: int = 0):
+    """n_adapts adapting + (n_transitions - n_adapts) sampling NUTS transitions per chain in ONE launch, every chain
+    adapting its own step size (and diagonal metric).  -> (z_last, draws (T, N, D) | None, stats of (T, N) arrays,
+    eps (N,), Minv (N, D) | None, eps_trace (T, N) | None).  The initial step size is `step_size(kappa.tau.integrator)`
+    (scalar or per chain), the initial metric h.metric (DiagEuclideanMetric)."""
+    if not isinstance(rng, PhiloxRNG):
+        raise L.InvalidArgument(L.ERR_INVALID, "in-launch adaptation draws from the on-device Philox streams")
+    tau = kappa.tau
+    if tau.sampler is not MultinomialTS or not isinstance(tau.termination_criterion, GeneralisedNoUTurn):
+        raise L.AhmcError(L.ERR_UNSUPPORTED, "in-launch adaptation: MultinomialTS + GeneralisedNoUTurn")
+    ctx = get_context(_device_of(z.theta))
+    N, D = z._nd()
+    host = _is_host(z.theta)
+    out = _empty_pp(z.theta, with_lk_gradient=False)
+    md, keep = h.metric._desc(D, N, z.theta)
+    e0 = step_size(tau.integrator)
+    eps = _like(z.theta, (N,))
+    if np.ndim(e0) == 0:
+        eps[...] = float(e0)
+    elif host:
+        eps[...] = np.asarray(e0, dtype=np.float64)
+    else:
+        eps.copy_(e0 if hasattr(e0, "detach") else torch.as_tensor(np.asarray(e0, dtype=np.float64)))
+    minv = _like(z.theta, (N, D)) if adaptor.adapt_metric else None
+    trace = _like(z.theta, (n_transitions, N)) if keep_eps_trace else None
+    cfg = L.AdaptCfg(n_adapts, adaptor.init_buffer, adaptor.term_buffer, adaptor.window_size, adaptor.delta, adaptor.gamma,
+                     adaptor.t0, adaptor.kappa, 1 if adaptor.adapt_metric else 0, adaptor.n_min, _ptr(eps), _ptr(minv),
+                     _ptr(trace))
+    rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0, _refresh_alpha(kappa))
+    rng.offset += n_transitions
+    tc = tau.termination_criterion
+    st, sc = _stats_buffers(z.theta, N, True, T=n_transitions)
+    draws = _like(z.theta, (n_transitions, N, D)) if keep_draws else None
+    fl = flags | (L.FLAG_HOST_BUFFERS if host else 0)
+    _sync_torch(z.theta)
+    zc, oc = z._c(False), out._c(False)
+    ctx.check(ctx.lib.ahmc_nuts_adapt_sample_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, tc.max_depth, tc.delta_max,
+                                                 n_transitions, C.byref(cfg), C.byref(rc), C.byref(zc), C.byref(oc),
+                                                 _ptr(draws), C.byref(sc), fl))
+    return out, draws, st, eps, minv, trace
+
+
 # ------------------------------------------------------------------------------------------------
 # adaptor statistics (src/adaptation): pooled summary record of one iteration
 # ------------------------------------------------------------------------------------------------

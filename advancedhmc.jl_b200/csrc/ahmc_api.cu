@@ -140,6 +140,17 @@ public:
         *d = p;
         return AHMC_OK;
     }
+    template <class T>
+    int inout(T* h, size_t count, T** d) {  // copied in now, copied back at finish
+        if (!h) { *d = nullptr; return AHMC_OK; }
+        if (!host_) { *d = h; return AHMC_OK; }
+        ahmc_ctx* ctx = ctx_;
+        T* p = (T*)alloc(count * sizeof(T));
+        CU(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        outs_.push_back({(void*)h, (void*)p, count * sizeof(T)});
+        *d = p;
+        return AHMC_OK;
+    }
     int finish() {
         ahmc_ctx* ctx = ctx_;
         for (auto& o : outs_) CU(cudaMemcpyAsync(o.h, o.d, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1185,9 +1196,26 @@ static int hmc_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* m
 static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
                      double eps, const double* eps_chain, int32_t max_depth, double delta_max, int32_t n_transitions,
                      const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, double* draws,
-                     const ahmc_stats* stats, uint32_t flags) {
+                     const ahmc_stats* stats, uint32_t flags, const ahmc_adapt_cfg* cfg = nullptr) {
     if (!ctx || !model || !metric || !rng) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric/rng");
     if (n_transitions < 1) return fail(ctx, AHMC_ERR_INVALID, "n_transitions must be >= 1");
+    if (cfg) {
+        if (metric->kind != AHMC_METRIC_DIAG)
+            return fail(ctx, AHMC_ERR_UNSUPPORTED, "in-launch adaptation needs the Diag metric (per-chain diagonal M^-1)");
+        if (flags & (AHMC_FLAG_NUTS_SLICE_TS | AHMC_FLAG_NUTS_CLASSIC | AHMC_FLAG_NUTS_STRICT))
+            return fail(ctx, AHMC_ERR_UNSUPPORTED, "in-launch adaptation is built for MultinomialTS + GeneralisedNoUTurn");
+        if (rng->normal_tape || rng->exp_tape || rng->dir_tape)
+            return fail(ctx, AHMC_ERR_INVALID, "in-launch adaptation draws from the Philox streams (no tapes)");
+        if (cfg->n_adapts < 0 || cfg->n_adapts > n_transitions)
+            return fail(ctx, AHMC_ERR_INVALID, "need 0 <= n_adapts <= n_transitions");
+        if (!cfg->eps_chain) return fail(ctx, AHMC_ERR_INVALID, "cfg.eps_chain (N, in/out) is required");
+        if (cfg->adapt_metric && !cfg->Minv_chain)
+            return fail(ctx, AHMC_ERR_INVALID, "cfg.Minv_chain (N x D, out) is required with adapt_metric");
+        if (cfg->init_buffer < 0 || cfg->term_buffer < 0 || cfg->window_size < 1)
+            return fail(ctx, AHMC_ERR_INVALID, "need init_buffer >= 0, term_buffer >= 0, window_size >= 1");
+        if (!(cfg->gamma > 0.0) || !(cfg->t0 >= 0.0) || !(cfg->delta > 0.0 && cfg->delta < 1.0))
+            return fail(ctx, AHMC_ERR_INVALID, "need gamma > 0, t0 >= 0, 0 < delta < 1");
+    }
     if (n_transitions > 1 && (rng->normal_tape || rng->exp_tape || rng->dir_tape))
         return fail(ctx, AHMC_ERR_INVALID, "random tapes describe ONE transition; multi-transition sampling uses the Philox streams");
     if (!(rng->partial_refresh_alpha > -1.0 && rng->partial_refresh_alpha < 1.0))
@@ -1219,6 +1247,11 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     if (draws) st.reserve((size_t)D * N * n_transitions * 8);
     if (rng->exp_tape) st.reserve((size_t)rng->exp_stride * N * 8);
     if (rng->dir_tape) st.reserve((size_t)rng->dir_stride * N);
+    if (cfg) {
+        st.reserve((size_t)N * 8);
+        if (cfg->Minv_chain) st.reserve((size_t)N * D * 8);
+        if (cfg->eps_trace) st.reserve((size_t)N * n_transitions * 8);
+    }
     if ((rc = st.prepare())) return rc;
     NutsArgs a{};
     a.model = model_dev(model);
@@ -1226,7 +1259,35 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     a.D = D;
     a.N = N;
     a.eps = eps;
-    if ((rc = st.in(eps_chain, (size_t)N, &a.eps_chain))) return rc;
+    if (cfg) {
+        AdaptDev& ad = a.ad;
+        ad.enabled = 1;
+        ad.n_adapts = cfg->n_adapts;
+        ad.delta = cfg->delta;
+        ad.gamma = cfg->gamma;
+        ad.t0 = cfg->t0;
+        ad.kappa = cfg->kappa;
+        ad.adapt_metric = cfg->adapt_metric ? 1 : 0;
+        ad.n_min = cfg->n_min > 0 ? cfg->n_min : 10;
+        // initialize!(StanHMCAdaptorState, ...) (stan_adaptor.jl:13-50)
+        ad.window_start = cfg->init_buffer + 1;
+        ad.window_end = cfg->n_adapts - cfg->term_buffer;
+        ad.n_splits = 0;
+        long long wsz = cfg->window_size, next = (long long)cfg->init_buffer + wsz;
+        while (next <= ad.window_end && ad.n_splits < 12) {
+            if (next + 2 * wsz > ad.window_end) next = ad.window_end;
+            ad.splits[ad.n_splits++] = (int)next;
+            wsz *= 2;
+            next += wsz;
+        }
+        if (ad.n_splits > 0 && ad.splits[ad.n_splits - 1] == cfg->n_adapts) --ad.n_splits;
+        if ((rc = st.inout(cfg->eps_chain, (size_t)N, &ad.eps))) return rc;
+        a.eps_chain = ad.eps;
+        if ((rc = st.out(cfg->Minv_chain, (size_t)N * D, &ad.minv))) return rc;
+        if ((rc = st.out(cfg->eps_trace, (size_t)N * n_transitions, &ad.eps_trace))) return rc;
+    } else if ((rc = st.in(eps_chain, (size_t)N, &a.eps_chain))) {
+        return rc;
+    }
     a.max_depth = max_depth;
     a.delta_max = delta_max;
     a.sampler = (flags & AHMC_FLAG_NUTS_SLICE_TS) ? 1 : 0;
@@ -1249,7 +1310,7 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     if ((rc = st.out(draws, (size_t)D * N * n_transitions, &a.draws))) return rc;
     a.n_transitions = n_transitions;
     // per-chain tree workspace
-    a.scratch_stride = nuts_scratch_doubles_per_chain(D, max_depth);
+    a.scratch_stride = nuts_scratch_doubles_per_chain(D, max_depth, cfg != nullptr);
     size_t need = (size_t)a.scratch_stride * (size_t)N * sizeof(double);
     if (need > ctx->nuts_scratch_bytes) {
         CU(cudaStreamSynchronize(ctx->stream));
@@ -1405,6 +1466,15 @@ int ahmc_nuts_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metr
                          const ahmc_stats* stats, uint32_t flags) {
     return nuts_impl(ctx, model, metric, D, N, eps, eps_chain, max_depth, delta_max, n_transitions, rng, z_in, z_out,
                      draws, stats, flags);
+}
+
+int ahmc_nuts_adapt_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                               int32_t max_depth, double delta_max, int32_t n_transitions, const ahmc_adapt_cfg* cfg,
+                               const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
+                               double* draws, const ahmc_stats* stats, uint32_t flags) {
+    if (!cfg) return fail(ctx, AHMC_ERR_INVALID, "NULL cfg");
+    return nuts_impl(ctx, model, metric, D, N, 0.0, nullptr, max_depth, delta_max, n_transitions, rng, z_in, z_out, draws,
+                     stats, flags, cfg);
 }
 
 // ---------------------------------------------------------------------------------------------- adaptor stats

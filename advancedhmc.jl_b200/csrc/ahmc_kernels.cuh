@@ -77,6 +77,21 @@ struct HmcArgs {
     double* draws;        // nullable: n_transitions x (D x N) positions, draw t of chain c at (t*N + c)*D
 };
 
+// in-kernel per-chain adaptation (K3 adaptive family): NesterovDualAveraging + windowed WelfordVar per chain
+struct AdaptDev {
+    int enabled;
+    int n_adapts;                  // iterations 1..n_adapts adapt (sampler.jl:72-90)
+    int window_start, window_end;  // stan_adaptor.jl:13-50
+    int n_splits;
+    int splits[12];
+    double delta, gamma, t0, kappa;  // stepsize.jl:162-172
+    int adapt_metric;                // 0: step size only
+    int n_min;                       // massmatrix.jl:103-107
+    double* eps;                     // N, out: adapted step size per chain (in: a.eps_chain / a.eps)
+    double* minv;                    // N*D, out: adapted diagonal M^-1 per chain (nullable when !adapt_metric)
+    double* eps_trace;               // nullable, n_transitions x N: step size used by each transition
+};
+
 struct NutsArgs {
     ModelDev model;
     MetricDev metric;
@@ -88,6 +103,7 @@ struct NutsArgs {
     double delta_max;
     int sampler;    // 0 MultinomialTS, 1 SliceTS
     int criterion;  // 0 GeneralisedNoUTurn, 1 ClassicNoUTurn, 2 StrictGeneralisedNoUTurn
+    AdaptDev ad;
     RngDev rng;
     int refresh;
     const double *th_in, *r_in, *g_in, *lp_in;
@@ -208,7 +224,7 @@ cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t stream, int*
 cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_nuts(const NutsArgs& a, cudaStream_t stream, int* n_launches);
-long long nuts_scratch_doubles_per_chain(int D, int max_depth);
+long long nuts_scratch_doubles_per_chain(int D, int max_depth, bool adaptive);
 cudaError_t launch_trajectory(const TrajArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_multinomial(const MultinomialArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_kick_drift(const SplitArgs& a, cudaStream_t stream, int* n_launches);

@@ -1,0 +1,707 @@
+// ahmc_nuts_kernel.cuh -- K3: one NUTS transition per chain (MultinomialTS + GeneralisedNoUTurn), the
+// reference's recursive doubling tree (src/trajectory.jl:626-742) run ITERATIVELY by one warp-group
+// per chain, so divergent U-turn termination stays inside the group.
+//
+// Recursion -> iteration.  `build_tree(depth j)` is a post-order walk over 2^j leaves; the only state
+// the recursion keeps alive is, per level k, the FIRST half-subtree waiting for its sibling.  We keep
+// exactly that ("pending[k]") in a per-chain workspace and drive the merges like a binary counter:
+// after leaf i, level k merges iff bit k of i is set.  Per pending level:
+//   rho      = sum of momenta over its leaves            (TurnStatistic, :462-467)
+//   rfirst   = momentum of its first-built leaf          (zleft or zright of the half tree)
+//   cand     = (theta, r, -grad lp, lp, lk) of its multinomial candidate  (:131-136)
+//   scalars  = lw (log weight), sum_alpha, n_alpha, dH_max               (:512-542)
+// Semantics preserved: leaf weights H0 - H' (:174-176); one randexp per internal
+// combine in post-order (:191-195, :667) and one for the top-level mh_accept only if the new subtree
+// did not terminate (:708-713); a terminated first half is returned without building/combining its
+// sibling (:652) -- the terminated node "floats" up through levels whose bit is 0 and is combined at
+// levels whose bit is 1, exactly as the unwinding recursion does; divergence iff
+// !(-H0 < delta_max - H') (:503-507); direction = sign of the step size (:640, integrator.jl:221-226).
+//
+// Control flow is warp-uniform (`__any_sync` guarded blocks, per-group predicates) so that groups of
+// G < 32 lanes sharing a warp can sit at different tree positions while shuffles stay convergent.
+//
+// The kernel is compiled in three families, one translation unit each (build time): the default sampler/criterion
+// (ahmc_nuts.cu), the SliceTS / Classic / Strict variants (ahmc_nuts_var.cu), and the form that adapts step size and
+// diagonal metric per chain inside the launch (ahmc_nuts_adapt.cu).
+#pragma once
+#include "ahmc_kernels.cuh"
+
+namespace ahmc {
+
+// workspace layout per chain (doubles): LEFT edge (theta,r,g) | RIGHT edge | rho_tree | per level k (7 vectors):
+// 0 rho, 1 rfirst, 2 cand theta, 3 cand r, 4 cand g, 5 rlast (Strict), 6 theta_first (Classic)
+constexpr int kLevelVecs = 7;
+// (+ 2 vectors at the end for the in-kernel Welford state of the adaptive form: mean, M2)
+__host__ __device__ inline long long nuts_level_doubles(int D, int max_depth) {
+    return (long long)(7 + kLevelVecs * (max_depth > 0 ? max_depth : 1)) * D;
+}
+
+__device__ __forceinline__ double jl_min0(double x) {  // min(0, x), NaN-propagating like Julia
+    return (x != x) ? x : (x < 0.0 ? x : 0.0);
+}
+__device__ __forceinline__ double logaddexp(double a, double b) {  // LogExpFunctions.logaddexp
+    double delta = (a == b) ? 0.0 : fabs(a - b);
+    double mx = (a != a || b != b) ? CUDART_NAN : (a > b ? a : b);
+    return mx + log1p(exp(-delta));
+}
+__device__ __forceinline__ double maxabs(double a, double b) { return fabs(a) > fabs(b) ? a : b; }  // :526
+
+constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, cand lk
+
+// Occupancy knob: the tree walk is a long chain of dependent, mostly fixed-latency instructions, so throughput
+// scales with resident warps per scheduler; cap registers so that this many 4-warp blocks fit per SM.
+#ifndef AHMC_NUTS_MINB
+#define AHMC_NUTS_MINB 3
+#endif
+template <int E>
+constexpr int nuts_min_blocks() { return E <= 4 ? AHMC_NUTS_MINB : (E <= 8 ? 2 : 1); }
+
+// VAR = false: MultinomialTS + GeneralisedNoUTurn only (what `NUTS(delta)` builds); VAR = true additionally compiles
+// SliceTS (trajectory.jl:102-109,144-145,164-166,178-189,202,500-502) and the Classic / StrictGeneralised criteria
+// (trajectory.jl:551-557, 579-613), selected at run time by a.sampler / a.criterion.
+template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
+__global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kernel(const NutsArgs a) {
+    const int samp = VAR ? a.sampler : 0;    // 0 MultinomialTS, 1 SliceTS
+    const int crit = VAR ? a.criterion : 0;  // 0 Generalised, 1 Classic, 2 StrictGeneralised
+    double lu = 0.0;                         // SliceTS slice variable (log space)
+    extern __shared__ double smem[];
+    const int l = threadIdx.x % G;
+    const int grp_in_block = threadIdx.x / G;
+    constexpr int kGroups = kBlockThreads / G;
+    const long long chain0 = (long long)blockIdx.x * kGroups + grp_in_block;
+    const bool valid = chain0 < a.N;
+    const long long chain = valid ? chain0 : a.N - 1;
+    const int D = a.D;
+    const bool dense = (MODEL == AHMC_MODEL_DENSE_GAUSS) || (METRIC == AHMC_METRIC_DENSE);
+    double* xs = smem + (size_t)grp_in_block * D;  // dense slab (unused otherwise)
+    const int maxd = a.max_depth > 0 ? a.max_depth : 1;
+    double* lv = smem + (dense ? (size_t)kGroups * D : 0) + (size_t)grp_in_block * maxd * kLevelScalars;
+    double* LW = lv;
+    double* SA = lv + maxd;
+    double* NA = lv + 2 * maxd;
+    double* DH = lv + 3 * maxd;
+    double* CLP = lv + 4 * maxd;
+    double* CLK = lv + 5 * maxd;
+
+    double* base = a.scratch + a.scratch_stride * chain;
+    double* LEFT = base;
+    double* RIGHT = base + 3 * (long long)D;
+    double* RHO = base + 6 * (long long)D;
+    auto level = [&](int k) { return base + (7 + kLevelVecs * (long long)k) * D; };
+
+    double eps_c = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
+    // adaptive family: per-chain dual-averaging state (all lanes of the group hold the same values) and the chain's
+    // Welford accumulators (mean, M2 per coordinate, owned lane-wise) behind the tree workspace
+    double da_mu = 0.0, da_xbar = 0.0, da_Hbar = 0.0, da_m = 0.0, w_n = 0.0;
+    double* W_MU = base + nuts_level_doubles(D, a.max_depth);
+    double* W_M2 = W_MU + D;
+
+    ModelOps<MODEL, G, E> mo;
+    MetricOps<METRIC, G, E> me;
+    mo.load(a.model, l, D);
+    me.load(a.metric, chain, l, D);
+
+    int nexp = 0, ndir = 0;
+    uint64_t off = a.rng.offset;  // Philox transition counter of the transition this group is working on
+    auto next_exp = [&]() -> double {
+        int k = nexp++;
+        if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
+        return philox_exp(a.rng.seed, off, chain, k);
+    };
+    auto next_unif = [&]() -> double {  // SliceTS draws rand(rng) where MultinomialTS draws randexp(rng); same counter
+        int k = nexp++;
+        if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
+        return exp(-philox_exp(a.rng.seed, off, chain, k));
+    };
+    auto next_dir = [&]() -> bool {
+        int k = ndir++;
+        if (a.rng.dir_tape && k < a.rng.dir_stride) return a.rng.dir_tape[chain * a.rng.dir_stride + k] != 0;
+        return philox_bit(a.rng.seed, off, chain, k);
+    };
+
+    // ---- per-transition state (a launch runs n_transitions transitions per chain: the reference's
+    //      `for i in 1:n_samples` loop, sampler.jl:182, each chain advancing at its own pace)
+    ChainState<E> s;
+    double dr[E];
+    double H0 = 0.0, zc_lp = 0.0, zc_lk = 0.0;
+    double lw_tree = 0.0, sa_tree = 0.0, dh_tree = 0.0;
+    int na_tree = 0, j = 0;
+    bool term_dyn = false, term_num = false;
+    bool done = true, in_sub = false;
+    int i = 0, jsub = 0, v = 1;
+    int t = 0;
+    bool finished = !valid;
+    bool need_init = valid;
+
+    while (true) {
+        // ---------------------------------------------------------------- (I) begin a transition:
+        // z0 = refresh (sampler.jl:55; hamiltonian.jl:213-220) with the cached lp / gradient;
+        // tree = BinaryTree(z0, z0, rho = z0.r, 0, 0, 0); sampler = MultinomialTS(z0, lw = 0) (:682-688, :155)
+        if (__any_sync(FULL, need_init)) {
+            const bool first = (t == 0);
+            double rn[E], drn[E];
+            if (need_init) {
+                off = a.rng.offset + (uint64_t)t;
+                nexp = 0;
+                ndir = 0;
+                vload_nc<G, E>(s.th, first ? a.th_in + a.ld_in * chain : a.th_out + a.ld_out * chain, l, D);
+                vload_nc<G, E>(s.g, first ? a.g_in + a.ld_in * chain : a.g_out + a.ld_out * chain, l, D);
+            }
+            if (a.refresh) {
+                if (a.rng.normal_tape) {
+                    vload_nc<G, E>(rn, a.rng.normal_tape + (long long)D * chain, l, D);
+                } else {
+                    philox_normals<G, E>(a.rng.seed, off, chain, l, D, rn);
+                }
+                me.rand_momentum(rn, l);
+                if (a.rng.partial_alpha != 0.0) {  // PartialMomentumRefreshment (hamiltonian.jl:243-254)
+                    double rp[E];
+                    vload_nc<G, E>(rp, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
+                    const double al = a.rng.partial_alpha, be = sqrt(1.0 - al * al);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) rn[e] = al * rp[e] + be * rn[e];
+                }
+            } else {
+                vload_nc<G, E>(rn, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
+            }
+            const double lk0 = map_nonfinite(kinetic<METRIC, G, E>(me, rn, drn, xs, l));
+            if (need_init) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) s.r[e] = rn[e];
+                s.lp = first ? map_nonfinite(a.lp_in[chain]) : zc_lp;
+                s.lk = lk0;
+                H0 = -(s.lp + s.lk);  // energy(z0) (:682)
+                zc_lp = s.lp;
+                zc_lk = s.lk;
+                vstore<G, E>(LEFT, s.th, l, D);
+                vstore<G, E>(LEFT + D, s.r, l, D);
+                vstore<G, E>(LEFT + 2 * (long long)D, s.g, l, D);
+                vstore<G, E>(RIGHT, s.th, l, D);
+                vstore<G, E>(RIGHT + D, s.r, l, D);
+                vstore<G, E>(RIGHT + 2 * (long long)D, s.g, l, D);
+                vstore<G, E>(RHO, s.r, l, D);
+                vstore<G, E>(a.th_out + a.ld_out * chain, s.th, l, D);
+                vstore<G, E>(a.r_out + a.ld_out * chain, s.r, l, D);
+                vstore<G, E>(a.g_out + a.ld_out * chain, s.g, l, D);
+                if (ADAPT && first) {  // DAState(eps) (stepsize.jl:27-36); WelfordVar zeros (massmatrix.jl:109-118)
+                    da_mu = log(10.0 * eps_c);
+                    da_xbar = da_Hbar = da_m = w_n = 0.0;
+                    double zero[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) zero[e] = 0.0;
+                    vstore<G, E>(W_MU, zero, l, D);
+                    vstore<G, E>(W_M2, zero, l, D);
+                    if (a.ad.minv) vstore<G, E>(a.ad.minv + (long long)D * chain, me.Minv, l, D);
+                    if (l == 0) a.ad.eps[chain] = eps_c;
+                }
+                lw_tree = 0.0;
+                if (VAR && samp == 1) {  // SliceTS(rng, z0) = SliceTS(z0, neg_energy(z0) - randexp(rng), 1) (:144-145)
+                    lu = (s.lp + s.lk) - next_exp();
+                    lw_tree = 1.0;  // n = 1
+                }
+                sa_tree = 0.0;
+                dh_tree = 0.0;
+                na_tree = 0;
+                j = 0;
+                term_dyn = false;
+                term_num = false;
+                done = !(j < a.max_depth);
+                in_sub = false;
+                need_init = false;
+            }
+        }
+        // ---------------------------------------------------------------- (F) finish a transition: stats (:725-739), draw
+        {
+            const bool fin_now = !finished && done && !in_sub;
+            if (fin_now) {
+                const long long si = (long long)t * a.N + chain;
+                if (a.draws) {
+                    double tt[E];
+                    vload_nc<G, E>(tt, a.th_out + a.ld_out * chain, l, D);
+                    vstore<G, E>(a.draws + si * D, tt, l, D);
+                }
+                if (l == 0) {
+                    const double H = -(zc_lp + zc_lk);
+                    a.lp_out[chain] = zc_lp;
+                    a.lk_out[chain] = zc_lk;
+                    const StatsDev& st = a.st;
+                    if (st.n_steps) st.n_steps[si] = na_tree;
+                    if (st.is_accept) st.is_accept[si] = 1;
+                    if (st.acceptance_rate) st.acceptance_rate[si] = sa_tree / (double)na_tree;
+                    if (st.log_density) st.log_density[si] = zc_lp;
+                    if (st.hamiltonian_energy) st.hamiltonian_energy[si] = H;
+                    if (st.hamiltonian_energy_error) st.hamiltonian_energy_error[si] = H - H0;
+                    if (st.max_hamiltonian_energy_error) st.max_hamiltonian_energy_error[si] = dh_tree;
+                    if (st.tree_depth) st.tree_depth[si] = j;
+                    if (st.numerical_error) st.numerical_error[si] = term_num ? 1 : 0;
+                }
+                if (ADAPT) {
+                    const int it = t + 1;  // 1-based iteration of `sample` (sampler.jl:182)
+                    if (a.ad.eps_trace && l == 0) a.ad.eps_trace[si] = eps_c;
+                    if (it <= a.ad.n_adapts) {
+                        // adapt_stepsize! (stepsize.jl:178-210), one chain: alpha = this transition's acceptance rate
+                        const double alpha = sa_tree / (double)na_tree;
+                        const double amin = (alpha != alpha) ? alpha : (alpha < 1.0 ? alpha : 1.0);  // min(1, alpha)
+                        const double m1 = da_m + 1.0;
+                        const double eta_H = 1.0 / (m1 + a.ad.t0);
+                        const double Hn = (1.0 - eta_H) * da_Hbar + eta_H * (a.ad.delta - amin);
+                        const double x = da_mu - Hn * (sqrt(m1) / a.ad.gamma);
+                        const double eta_x = pow(m1, -a.ad.kappa);
+                        const double xn = (1.0 - eta_x) * da_xbar + eta_x * x;
+                        const double en = exp(x);
+                        if (finite_d(en)) {  // else the previous state stays (stepsize.jl:199-203, per chain)
+                            da_m = m1;
+                            da_Hbar = Hn;
+                            da_xbar = xn;
+                            eps_c = en;
+                        }
+                        bool split = false;  // is_window_end (stan_adaptor.jl:135)
+                        for (int q = 0; q < a.ad.n_splits; ++q) split = split || (a.ad.splits[q] == it);
+                        if (a.ad.adapt_metric && it >= a.ad.window_start && it <= a.ad.window_end) {
+                            // push!(::WelfordVar, theta) (massmatrix.jl:141-149) with the new draw
+                            double th_new[E], wmu[E], wm2[E];
+                            vload_nc<G, E>(th_new, a.th_out + a.ld_out * chain, l, D);
+                            vload_nc<G, E>(wmu, W_MU, l, D);
+                            vload_nc<G, E>(wm2, W_M2, l, D);
+                            w_n += 1.0;
+                            const double f = (w_n - 1.0) / w_n;
+#pragma unroll
+                            for (int e = 0; e < E; ++e) {
+                                const double dl = th_new[e] - wmu[e];
+                                wmu[e] = wmu[e] + dl / w_n;
+                                wm2[e] = wm2[e] + dl * dl * f;
+                            }
+                            if (split && w_n >= (double)a.ad.n_min) {  // update! + get_estimation (massmatrix.jl:60-62, 152-157)
+                                const double c1 = w_n / ((w_n + 5.0) * (w_n - 1.0)), c2 = 1e-3 * (5.0 / (w_n + 5.0));
+#pragma unroll
+                                for (int e = 0; e < E; ++e) me.Minv[e] = (l + G * e < D) ? c1 * wm2[e] + c2 : 0.0;
+                                vstore<G, E>(a.ad.minv + (long long)D * chain, me.Minv, l, D);
+                            }
+                            vstore<G, E>(W_MU, wmu, l, D);
+                            vstore<G, E>(W_M2, wm2, l, D);
+                        }
+                        if (split) {  // reset!(ssa); reset!(pc) (stan_adaptor.jl:155-158; stepsize.jl:38-52)
+                            da_m = 0.0;
+                            da_mu = log(10.0 * eps_c);
+                            da_xbar = da_Hbar = 0.0;
+                            w_n = 0.0;
+                            double zero[E];
+#pragma unroll
+                            for (int e = 0; e < E; ++e) zero[e] = 0.0;
+                            vstore<G, E>(W_MU, zero, l, D);
+                            vstore<G, E>(W_M2, zero, l, D);
+                        }
+                        if (it == a.ad.n_adapts) eps_c = exp(da_xbar);  // finalize! (stepsize.jl:54-62)
+                        if (l == 0) a.ad.eps[chain] = eps_c;
+                    }
+                }
+                ++t;
+                if (t < a.n_transitions) need_init = true;
+                else finished = true;
+            }
+        }
+        if (__any_sync(FULL, need_init)) continue;
+
+        // ---------------------------------------------------------------- (A) start a doubling (:691-706)
+        const bool start = !finished && !done && !in_sub;
+        if (__any_sync(FULL, start)) {
+            if (start) {
+                const bool vleft = next_dir();  // rand(rng, Bool) (:693)
+                v = vleft ? -1 : 1;
+                const double* edge = vleft ? LEFT : RIGHT;
+                vload_nc<G, E>(s.th, edge, l, D);
+                vload_nc<G, E>(s.r, edge + D, l, D);
+                vload_nc<G, E>(s.g, edge + 2 * (long long)D, l, D);
+                jsub = j;
+                i = 0;
+                in_sub = true;
+            }
+        }
+        if (!__any_sync(FULL, in_sub)) break;
+
+        // ---------------------------------------------------------------- (B) one leaf (:638-647)
+        leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, v > 0 ? eps_c : -eps_c, dr, xs, l);
+        const double nE = s.lp + s.lk;  // neg_energy(z')
+        const double H1 = -nE;
+        const double dH = H1 - H0;
+        double lw_c = H0 + nE;                               // MultinomialTS(s, H0, z') (:174-176)
+        double sa_c = exp(jl_min0(-dH));                     // alpha' = exp(min(0, -dH))
+        double na_c = 1.0, dh_c = dH;
+        bool tnum_c = !(-H0 < a.delta_max + -H1);            // Termination(...) (:503-507)
+        if (VAR && samp == 1) {
+            lw_c = (lu <= nE) ? 1.0 : 0.0;                   // SliceTS(s, H0, z'): n = Int(lu <= neg_energy) (:164-166)
+            tnum_c = !(lu < a.delta_max + -H1);              // Termination(::SliceTS) (:500-502)
+        }
+        bool tdyn_c = false;
+        double rho_cur[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) rho_cur[e] = s.r[e];  // TurnStatistic(z.r)
+        int cand_cur = -1;  // -1: the leaf in registers; k >= 0: candidate stored in level slot k
+
+        // ---------------------------------------------------------------- (C) post-order merges (:649-673)
+        bool merging = in_sub;
+        bool complete = false;
+        int k = 0;
+        while (__any_sync(FULL, merging)) {
+            if (merging && k == jsub) {
+                complete = true;
+                merging = false;
+            }
+            const bool bit = merging && ((i >> k) & 1);
+            const bool term_c = tnum_c || tdyn_c;
+            const bool do_comb = merging && bit;
+            const bool do_store = merging && !bit && !term_c;
+            const bool do_float = merging && !bit && term_c;  // terminated first half: returned as is (:652)
+            if (__any_sync(FULL, do_comb)) {
+                double rho_p[E], rf_p[E], t1[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) rho_p[e] = rf_p[e] = 0.0;
+                const double* L = level(k);
+                if (do_comb) {
+                    if (k == 0) {
+                        vload_nc<G, E>(rho_p, L + 3 * (long long)D, l, D);  // level 0: rho = rfirst = rlast = cand r
+#pragma unroll
+                        for (int e = 0; e < E; ++e) rf_p[e] = rho_p[e];
+                    } else {
+                        vload_nc<G, E>(rho_p, L, l, D);
+                        vload_nc<G, E>(rf_p, L + D, l, D);
+                    }
+                }
+                bool uturn_extra = false;
+                if (VAR && crit == 2) {
+                    // StrictGeneralisedNoUTurn (:579-613).  F = first-built half (pending), S = second-built half (current).
+                    //   check A: rho = F.rho + S.rfirst, against dH/dr(F.rfirst), dH/dr(S.rfirst)
+                    //   check B: rho = S.rho + F.rlast,  against dH/dr(r_leaf),  dH/dr(F.rlast)
+                    // (v = +1: A = check_left_subtree, B = check_right_subtree; v = -1: the other way round)
+                    double rsf[E], rl_p[E], tA[E], tB[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) rsf[e] = rl_p[e] = 0.0;
+                    if (do_comb) {
+                        if (k == 0) {
+#pragma unroll
+                            for (int e = 0; e < E; ++e) {
+                                rsf[e] = s.r[e];      // S is the leaf itself
+                                rl_p[e] = rho_p[e];   // F is a single leaf
+                            }
+                        } else {
+                            const double* P = level(k - 1);
+                            vload_nc<G, E>(rsf, (k == 1) ? P + 3 * (long long)D : P + D, l, D);
+                            vload_nc<G, E>(rl_p, L + 5 * (long long)D, l, D);
+                        }
+                    }
+                    me.dHdr(rf_p, t1, xs, l);
+                    me.dHdr(rsf, tA, xs, l);
+                    me.dHdr(rl_p, tB, xs, l);
+                    double a1 = 0.0, a2 = 0.0, b1 = 0.0, b2 = 0.0;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const double ra = rho_p[e] + rsf[e];
+                        const double rb = rho_cur[e] + rl_p[e];
+                        a1 = fma(ra, t1[e], a1);
+                        a2 = fma(ra, tA[e], a2);
+                        b1 = fma(rb, dr[e], b1);
+                        b2 = fma(rb, tB[e], b2);
+                    }
+                    a1 = Grp<G>::sum(a1);
+                    a2 = Grp<G>::sum(a2);
+                    b1 = Grp<G>::sum(b1);
+                    b2 = Grp<G>::sum(b2);
+                    uturn_extra = (a1 <= 0.0) || (a2 <= 0.0) || (b1 <= 0.0) || (b2 <= 0.0);
+                }
+                if (do_comb) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) rho_cur[e] += rho_p[e];  // combine(ts) (:467)
+                }
+                double d1 = 0.0, d2 = 0.0;
+                bool uturn;
+                me.dHdr(rf_p, t1, xs, l);
+                if (VAR && crit == 1) {
+                    // ClassicNoUTurn (:551-557): s = dot(dtheta, dH/dr(-r_left)) >= 0 || dot(-dtheta, dH/dr(r_right)) >= 0
+                    // with dtheta = theta_right - theta_left; q = -dtheta
+                    double thf[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) thf[e] = 0.0;
+                    if (do_comb) vload_nc<G, E>(thf, (k == 0) ? L + 2 * (long long)D : L + 6 * (long long)D, l, D);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const double q = (v > 0) ? (thf[e] - s.th[e]) : (s.th[e] - thf[e]);
+                        d1 = fma(q, t1[e], d1);
+                        d2 = fma(q, dr[e], d2);
+                    }
+                    d1 = Grp<G>::sum(d1);
+                    d2 = Grp<G>::sum(d2);
+                    uturn = (d1 >= 0.0) || (d2 >= 0.0);
+                } else {
+                    // isterminated(GeneralisedNoUTurn) on the merged node (:566-570, :615-617)
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        d1 = fma(rho_cur[e], t1[e], d1);
+                        d2 = fma(rho_cur[e], dr[e], d2);
+                    }
+                    d1 = Grp<G>::sum(d1);
+                    d2 = Grp<G>::sum(d2);
+                    uturn = (d1 <= 0.0) || (d2 <= 0.0) || uturn_extra;
+                }
+                if (do_comb) {
+                    const double lw_p = LW[k], sa_p = SA[k], na_p = NA[k], dh_p = DH[k];
+                    const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
+                    if (VAR && samp == 1) {  // combine(rng, s1::SliceTS, s2) (:178-183): n = n1 + n2; n*rand < n1 ? s1 : s2
+                        const double n = lw_p + lw_c;
+                        if (n * ex < lw_p) cand_cur = k;
+                        lw_c = n;
+                    } else {
+                        const double lw = logaddexp(lw_p, lw_c);  // combine(rng, s1, s2) (:191-195)
+                        if (lw < lw_p + ex) cand_cur = k;         // keep the first-built half's candidate
+                        lw_c = lw;
+                    }
+                    sa_c = (v > 0) ? sa_p + sa_c : sa_c + sa_p;  // treeleft + treeright (:538)
+                    na_c += na_p;
+                    dh_c = (v > 0) ? maxabs(dh_p, dh_c) : maxabs(dh_c, dh_p);
+                    tdyn_c = tdyn_c || uturn;
+                }
+            }
+            if (__any_sync(FULL, do_store)) {
+                if (do_store) {
+                    double* L = level(k);
+                    if (k > 0) {
+                        // first-built leaf of this node = first-built leaf of the half merged last (level k-1),
+                        // whose slot is still intact (level 0 keeps it as its candidate momentum)
+                        double t[E];
+                        const double* P = level(k - 1);
+                        vload_nc<G, E>(t, (k == 1) ? P + 3 * (long long)D : P + D, l, D);
+                        vstore<G, E>(L + D, t, l, D);
+                        vstore<G, E>(L, rho_cur, l, D);
+                        if (VAR && crit == 2) vstore<G, E>(L + 5 * (long long)D, s.r, l, D);  // rlast = the current leaf
+                        if (VAR && crit == 1) {                                                // theta of the first-built leaf
+                            vload_nc<G, E>(t, (k == 1) ? P + 2 * (long long)D : P + 6 * (long long)D, l, D);
+                            vstore<G, E>(L + 6 * (long long)D, t, l, D);
+                        }
+                    }
+                    double clp, clk;
+                    if (cand_cur < 0) {
+                        vstore<G, E>(L + 2 * (long long)D, s.th, l, D);
+                        vstore<G, E>(L + 3 * (long long)D, s.r, l, D);
+                        vstore<G, E>(L + 4 * (long long)D, s.g, l, D);
+                        clp = s.lp;
+                        clk = s.lk;
+                    } else {
+                        const double* S = level(cand_cur);
+                        double t[E];
+                        vload_nc<G, E>(t, S + 2 * (long long)D, l, D);
+                        vstore<G, E>(L + 2 * (long long)D, t, l, D);
+                        vload_nc<G, E>(t, S + 3 * (long long)D, l, D);
+                        vstore<G, E>(L + 3 * (long long)D, t, l, D);
+                        vload_nc<G, E>(t, S + 4 * (long long)D, l, D);
+                        vstore<G, E>(L + 4 * (long long)D, t, l, D);
+                        clp = CLP[cand_cur];
+                        clk = CLK[cand_cur];
+                    }
+                    if (l == 0) {
+                        LW[k] = lw_c;
+                        SA[k] = sa_c;
+                        NA[k] = na_c;
+                        DH[k] = dh_c;
+                        CLP[k] = clp;
+                        CLK[k] = clk;
+                    }
+                    merging = false;
+                }
+                __syncwarp();
+            }
+            if (do_comb || do_float) ++k;
+        }
+
+        // ---------------------------------------------------------------- (D) subtree complete (:707-722)
+        if (__any_sync(FULL, complete)) {
+            const bool sub_term = tnum_c || tdyn_c;
+            bool accept = false;
+            if (complete && !sub_term) {
+                j = j + 1;
+                const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
+                accept = (VAR && samp == 1) ? (lw_tree * ex < lw_c)   // mh_accept(::SliceTS): s.n * rand < s'.n (:202)
+                                            : (lw_tree < lw_c + ex);  // mh_accept (:204-206)
+            }
+            if (accept) {  // zcand = sampler'.zcand
+                if (cand_cur < 0) {
+                    vstore<G, E>(a.th_out + a.ld_out * chain, s.th, l, D);
+                    vstore<G, E>(a.r_out + a.ld_out * chain, s.r, l, D);
+                    vstore<G, E>(a.g_out + a.ld_out * chain, s.g, l, D);
+                    zc_lp = s.lp;
+                    zc_lk = s.lk;
+                } else {
+                    const double* S = level(cand_cur);
+                    double t[E];
+                    vload_nc<G, E>(t, S + 2 * (long long)D, l, D);
+                    vstore<G, E>(a.th_out + a.ld_out * chain, t, l, D);
+                    vload_nc<G, E>(t, S + 3 * (long long)D, l, D);
+                    vstore<G, E>(a.r_out + a.ld_out * chain, t, l, D);
+                    vload_nc<G, E>(t, S + 4 * (long long)D, l, D);
+                    vstore<G, E>(a.g_out + a.ld_out * chain, t, l, D);
+                    zc_lp = CLP[cand_cur];
+                    zc_lk = CLK[cand_cur];
+                }
+            }
+            // tree = combine(treeleft, treeright) (:715): rho, the moved edge, statistics
+            double rho_t[E], r_other[E], t1[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) rho_t[e] = r_other[e] = 0.0;
+            double* edge = (v < 0) ? LEFT : RIGHT;        // the edge that moves
+            const double* other = (v < 0) ? RIGHT : LEFT;
+            bool uturn_extra = false;
+            if (VAR && crit == 2) {
+                // StrictGeneralisedNoUTurn at the top level (:579-613), T = old tree, S = new subtree:
+                //   X: rho = T.rho + S.rfirst, against dH/dr(r_far),  dH/dr(S.rfirst)
+                //   Y: rho = r_near + S.rho,   against dH/dr(r_near), dH/dr(r_leaf)      (r_near = the edge being replaced)
+                double rhoT[E], rsf[E], rnear[E], rfar[E], tA[E], tB[E], tC[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) rhoT[e] = rsf[e] = rnear[e] = rfar[e] = 0.0;
+                if (complete) {
+                    vload_nc<G, E>(rhoT, RHO, l, D);
+                    vload_nc<G, E>(rnear, edge + D, l, D);
+                    vload_nc<G, E>(rfar, other + D, l, D);
+                    if (jsub == 0) {
+#pragma unroll
+                        for (int e = 0; e < E; ++e) rsf[e] = s.r[e];
+                    } else {
+                        const double* P = level(jsub - 1);
+                        vload_nc<G, E>(rsf, (jsub == 1) ? P + 3 * (long long)D : P + D, l, D);
+                    }
+                }
+                me.dHdr(rfar, tA, xs, l);
+                me.dHdr(rsf, tB, xs, l);
+                me.dHdr(rnear, tC, xs, l);
+                double x1 = 0.0, x2 = 0.0, y1 = 0.0, y2 = 0.0;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double rx = rhoT[e] + rsf[e];
+                    const double ry = rnear[e] + rho_cur[e];
+                    x1 = fma(rx, tA[e], x1);
+                    x2 = fma(rx, tB[e], x2);
+                    y1 = fma(ry, tC[e], y1);
+                    y2 = fma(ry, dr[e], y2);
+                }
+                x1 = Grp<G>::sum(x1);
+                x2 = Grp<G>::sum(x2);
+                y1 = Grp<G>::sum(y1);
+                y2 = Grp<G>::sum(y2);
+                uturn_extra = (x1 <= 0.0) || (x2 <= 0.0) || (y1 <= 0.0) || (y2 <= 0.0);
+            }
+            double th_other[E];
+            if (VAR && crit == 1) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) th_other[e] = 0.0;
+                if (complete) vload_nc<G, E>(th_other, other, l, D);
+            }
+            if (complete) {
+                vload_nc<G, E>(rho_t, RHO, l, D);
+#pragma unroll
+                for (int e = 0; e < E; ++e) rho_t[e] += rho_cur[e];
+                vstore<G, E>(RHO, rho_t, l, D);
+                vstore<G, E>(edge, s.th, l, D);
+                vstore<G, E>(edge + D, s.r, l, D);
+                vstore<G, E>(edge + 2 * (long long)D, s.g, l, D);
+                vload_nc<G, E>(r_other, other + D, l, D);
+            }
+            me.dHdr(r_other, t1, xs, l);
+            double d1 = 0.0, d2 = 0.0;
+            bool uturn_top;
+            if (VAR && crit == 1) {  // ClassicNoUTurn on the whole tree: q = -(theta_right - theta_left)
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const double q = (v > 0) ? (th_other[e] - s.th[e]) : (s.th[e] - th_other[e]);
+                    d1 = fma(q, t1[e], d1);
+                    d2 = fma(q, dr[e], d2);
+                }
+                d1 = Grp<G>::sum(d1);
+                d2 = Grp<G>::sum(d2);
+                uturn_top = (d1 >= 0.0) || (d2 >= 0.0);
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    d1 = fma(rho_t[e], t1[e], d1);
+                    d2 = fma(rho_t[e], dr[e], d2);
+                }
+                d1 = Grp<G>::sum(d1);
+                d2 = Grp<G>::sum(d2);
+                uturn_top = (d1 <= 0.0) || (d2 <= 0.0) || uturn_extra;
+            }
+            if (complete) {
+                sa_tree = (v < 0) ? sa_c + sa_tree : sa_tree + sa_c;
+                na_tree += (int)na_c;
+                dh_tree = (v < 0) ? maxabs(dh_c, dh_tree) : maxabs(dh_tree, dh_c);
+                lw_tree = (VAR && samp == 1) ? lw_tree + lw_c            // combine(zcand, s1::SliceTS, s2): n1 + n2 (:185-189)
+                                             : logaddexp(lw_tree, lw_c);  // combine(zcand, sampler, sampler') (:197-200, :717)
+                term_dyn = term_dyn || tdyn_c || uturn_top;  // (:719-722)
+                term_num = term_num || tnum_c;
+                in_sub = false;
+                if (term_dyn || term_num || !(j < a.max_depth)) done = true;
+            }
+            __syncwarp();
+        }
+        if (in_sub) ++i;
+    }
+
+}
+
+template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
+static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
+    const int chains_per_block = kBlockThreads / G;
+    const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
+    const int maxd = a.max_depth > 0 ? a.max_depth : 1;
+    size_t sm = smem_bytes(MODEL, METRIC, a.D, G) + (size_t)chains_per_block * maxd * kLevelScalars * sizeof(double);
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+    }
+    nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int MODEL, int METRIC, bool VAR, bool ADAPT>
+static cudaError_t nuts_layout(const NutsArgs& a, cudaStream_t st, int G, int E) {
+    if (G == 4 && E == 1) return launch_nuts_v<MODEL, METRIC, 4, 1, VAR, ADAPT>(a, st);
+    if (G == 8 && E == 1) return launch_nuts_v<MODEL, METRIC, 8, 1, VAR, ADAPT>(a, st);
+    if (G == 16 && E == 1) return launch_nuts_v<MODEL, METRIC, 16, 1, VAR, ADAPT>(a, st);
+    if (G == 32 && E == 1) return launch_nuts_v<MODEL, METRIC, 32, 1, VAR, ADAPT>(a, st);
+    if (G == 32 && E == 2) return launch_nuts_v<MODEL, METRIC, 32, 2, VAR, ADAPT>(a, st);
+    if (G == 32 && E == 4) return launch_nuts_v<MODEL, METRIC, 32, 4, VAR, ADAPT>(a, st);
+    if (G == 32 && E == 8) return launch_nuts_v<MODEL, METRIC, 32, 8, VAR, ADAPT>(a, st);
+    if (G == 32 && E == 16) return launch_nuts_v<MODEL, METRIC, 32, 16, VAR, ADAPT>(a, st);
+    return cudaErrorInvalidValue;
+}
+
+// model x metric dispatch of one (VAR, ADAPT) family; DIAG_ONLY restricts the family to the Diag metric
+template <bool VAR, bool ADAPT, bool DIAG_ONLY>
+static cudaError_t nuts_dispatch(const NutsArgs& a, cudaStream_t st) {
+    int G, E;
+    if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+    if (DIAG_ONLY) {
+        if (a.metric.kind != AHMC_METRIC_DIAG) return cudaErrorInvalidValue;
+        switch (a.model.kind) {
+            case AHMC_MODEL_STD_NORMAL: return nuts_layout<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_DIAG, VAR, ADAPT>(a, st, G, E);
+            case AHMC_MODEL_DIAG_GAUSS: return nuts_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DIAG, VAR, ADAPT>(a, st, G, E);
+            case AHMC_MODEL_DENSE_GAUSS: return nuts_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DIAG, VAR, ADAPT>(a, st, G, E);
+            case AHMC_MODEL_FUNNEL: return nuts_layout<AHMC_MODEL_FUNNEL, AHMC_METRIC_DIAG, VAR, ADAPT>(a, st, G, E);
+        }
+        return cudaErrorInvalidValue;
+    } else {
+        switch (a.model.kind * 3 + a.metric.kind) {
+            case 0: return nuts_layout<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_UNIT, VAR, ADAPT>(a, st, G, E);
+            case 1: return nuts_layout<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_DIAG, VAR, ADAPT>(a, st, G, E);
+            case 2: return nuts_layout<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_DENSE, VAR, ADAPT>(a, st, G, E);
+            case 3: return nuts_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_UNIT, VAR, ADAPT>(a, st, G, E);
+            case 4: return nuts_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DIAG, VAR, ADAPT>(a, st, G, E);
+            case 5: return nuts_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DENSE, VAR, ADAPT>(a, st, G, E);
+            case 6: return nuts_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_UNIT, VAR, ADAPT>(a, st, G, E);
+            case 7: return nuts_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DIAG, VAR, ADAPT>(a, st, G, E);
+            case 8: return nuts_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DENSE, VAR, ADAPT>(a, st, G, E);
+            case 9: return nuts_layout<AHMC_MODEL_FUNNEL, AHMC_METRIC_UNIT, VAR, ADAPT>(a, st, G, E);
+            case 10: return nuts_layout<AHMC_MODEL_FUNNEL, AHMC_METRIC_DIAG, VAR, ADAPT>(a, st, G, E);
+            case 11: return nuts_layout<AHMC_MODEL_FUNNEL, AHMC_METRIC_DENSE, VAR, ADAPT>(a, st, G, E);
+        }
+        return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace ahmc

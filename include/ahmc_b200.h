@@ -217,6 +217,30 @@ int ahmc_nuts_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metr
                          const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, double* draws,
                          const ahmc_stats* stats, uint32_t flags);
 
+/* Warm-up + sampling in ONE launch with the reference's VECTORISED adaptors: every chain owns a
+ * `NesterovDualAveraging` state (src/adaptation/stepsize.jl:178-210: eps is a length-N vector and adapts per chain) and,
+ * with adapt_metric, a windowed `WelfordVar` over its own draws (massmatrix.jl:141-157 with a D x N variance, i.e. a
+ * per-chain diagonal M^-1), scheduled like `StanHMCAdaptor` (stan_adaptor.jl:13-50, 137-159: windows, reset of both
+ * adaptors at each window end, `finalize!` eps = exp(x_bar) after iteration n_adapts).  Because nothing is pooled,
+ * chains never wait for each other: iterations 1..n_adapts adapt, n_adapts+1..n_transitions sample with the final
+ * eps / M^-1.  Requires the Diag metric (shared or per-chain M^-1 as the starting point), MultinomialTS +
+ * GeneralisedNoUTurn, Philox randomness (no tapes).  Deviation from the reference: a non-finite eps proposal reverts
+ * that chain only (the reference reverts every chain, "buggy for batch mode" by its own comment, stepsize.jl:199-203). */
+typedef struct ahmc_adapt_cfg {
+    int32_t n_adapts;                             /* 0 <= n_adapts <= n_transitions */
+    int32_t init_buffer, term_buffer, window_size; /* Stan defaults 75 / 50 / 25 */
+    double delta, gamma, t0, kappa;               /* 0.8, 0.05, 10, 0.75 (stepsize.jl:162-172) */
+    int32_t adapt_metric;                         /* 0: step size only; 1: + per-chain WelfordVar */
+    int32_t n_min;                                /* WelfordVar n_min, 10 (massmatrix.jl:103-107) */
+    double* eps_chain;  /* N, in: initial step size per chain; out: adapted step size per chain */
+    double* Minv_chain; /* N x D, out: adapted diagonal M^-1 per chain (required iff adapt_metric) */
+    double* eps_trace;  /* nullable, n_transitions x N: the step size each transition used (`step_size` stat) */
+} ahmc_adapt_cfg;
+int ahmc_nuts_adapt_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                               int32_t max_depth, double delta_max, int32_t n_transitions, const ahmc_adapt_cfg* cfg,
+                               const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
+                               double* draws, const ahmc_stats* stats, uint32_t flags);
+
 /* ---- adaptor statistics (src/adaptation) ------------------------------------------------------ */
 /* Pooled summary of one iteration over this GPU's N chains, written to a small device/host record that
  * the host all-gathers across ranks (one NCCL all-gather) and merges in rank order:

@@ -7,6 +7,7 @@ import torch
 
 import ahmc_b200 as A
 from ahmc_b200 import adaptation as ad
+from tests.helpers import rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -134,3 +135,78 @@ def test_nuts_diag_metric_adapted_with_pooled_nutpie_var():
     assert 0.8 < ratio.min() and ratio.max() < 1.25, (ratio.min(), ratio.max())
     acc = np.mean([s["acceptance_rate"] for s in res.stats[150:]])
     assert 0.6 < acc < 0.97, acc
+
+
+def test_in_launch_per_chain_adaptation_equals_host_loop_with_oracle_adaptors():
+    """ahmc_nuts_adapt_sample_f64 (per-chain NesterovDualAveraging + windowed WelfordVar inside the persistent NUTS
+    launch) against the same run done iteration by iteration: single-transition launches on the same Philox streams,
+    with the ORACLE's vectorised adaptors (stepsize.jl:178-210, massmatrix.jl:141-157) and the reference's window
+    schedule / reset / finalize order (stan_adaptor.jl:13-50, 137-159; sampler.jl:72-90) applied on the host."""
+    from oracle import oracle_c as oc
+
+    D, N, T, n_adapts = 8, 96, 60, 50
+    ib, tb, wsz = 10, 8, 6
+    ws, we, splits = oc.stan_windows(n_adapts, ib, tb, wsz)
+    assert (ws, we, list(splits)) == (11, 42, [16, 42])  # first window has 6 < n_min draws: reset without update
+    rng = np.random.default_rng(3)
+    sd = np.exp(rng.uniform(-1.0, 1.0, D))
+    target = A.DiagGaussian(rng.normal(size=D), sd)
+    th0 = torch.as_tensor(rng.normal(size=(N, D)), device=DEV)
+    eps0, seed = 0.3, 99
+
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), target)
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(eps0), A.GeneralisedNoUTurn(8, 1000.0)))
+    z0 = A.phasepoint(h, th0, torch.zeros_like(th0))
+    adaptor = A.VectorisedStanAdaptor(delta=0.8, init_buffer=ib, term_buffer=tb, window_size=wsz)
+    zl, draws, st, eps_f, minv_f, trace = A.nuts_adapt_sample(A.PhiloxRNG(seed), h, kern, z0, T, n_adapts, adaptor,
+                                                              keep_eps_trace=True)
+
+    # ---- the same thing, one launch per iteration, adaptors on the host (oracle)
+    prng = A.PhiloxRNG(seed)
+    da, wv = oc.DualAveraging(np.full(N, eps0), delta=0.8), oc.WelfordVar((D, N))
+    eps, Minv = np.full(N, eps0), np.ones((N, D))
+    z = z0
+    for i in range(1, T + 1):
+        assert np.allclose(trace[i - 1].cpu().numpy(), eps, rtol=1e-9, atol=0), i
+        hi = A.Hamiltonian(A.DiagEuclideanMetric(torch.as_tensor(Minv, device=DEV)), target)
+        ki = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(torch.as_tensor(eps, device=DEV)),
+                                      A.GeneralisedNoUTurn(8, 1000.0)))
+        tr = A.transition(prng, hi, ki, z)
+        z = tr.z
+        assert rel_err(draws[i - 1].cpu().numpy(), z.theta.cpu().numpy()) < 1e-7, i
+        assert (st["n_steps"][i - 1].cpu().numpy() == tr.stat["n_steps"].cpu().numpy()).all(), i
+        if i <= n_adapts:
+            da.adapt(tr.stat["acceptance_rate"].cpu().numpy())
+            if ws <= i <= we:
+                wv.push(z.theta.cpu().numpy().T)
+                if i in splits and wv.n.value >= 10:
+                    Minv = np.ascontiguousarray(wv.estimate().T)
+            if i in splits:
+                da.reset()
+                wv = oc.WelfordVar((D, N))
+            if i == n_adapts:
+                da.finalize()
+            eps = da.eps.copy()
+    assert np.allclose(eps_f.cpu().numpy(), eps, rtol=1e-9)
+    assert np.allclose(minv_f.cpu().numpy(), Minv, rtol=1e-8)
+    assert not np.allclose(Minv, 1.0)                       # the second window did update the metric
+    assert rel_err(zl.theta.cpu().numpy(), z.theta.cpu().numpy()) < 1e-7
+    # and it adapts: per-chain acceptance after warm-up is near delta, M^-1 tracks the target variances
+    acc = st["acceptance_rate"][n_adapts:].double().mean().item()
+    assert 0.6 < acc < 0.95, acc
+    ratio = np.median(minv_f.cpu().numpy(), axis=0) / sd ** 2
+    assert 0.4 < ratio.min() and ratio.max() < 2.5  # 26 draws per chain: a rough estimate, as in the reference
+
+
+def test_sample_with_vectorised_adaptor_runs_funnel_warmup_in_one_launch():
+    D, N = 20, 512
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.Funnel(D))
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
+    th0 = torch.as_tensor(np.random.default_rng(4).normal(size=(N, D)) * 0.1, device=DEV)
+    res = ad.sample(A.PhiloxRNG(8), h, kern, th0, 300, A.VectorisedStanAdaptor(delta=0.8), 250)
+    acc = np.mean([s["acceptance_rate"] for s in res.stats[250:]])
+    assert 0.65 < acc < 0.95, acc
+    assert res.eps.shape == (N,) and res.Minv.shape == (N, D)
+    assert float(res.eps.min()) > 1e-3 and float(res.eps.max()) < 2.0
+    v = res.theta[:, 0].cpu().numpy()
+    assert abs(v.std() - 3.0) < 1.0  # the funnel's neck variable ~ N(0, 3^2)
