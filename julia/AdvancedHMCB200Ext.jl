@@ -60,6 +60,9 @@ struct CRng
 end
 
 const FLAG_ASYNC = 0x4 % UInt32
+const FLAG_NUTS_SLICE_TS = 0x20 % UInt32
+const FLAG_NUTS_CLASSIC = 0x40 % UInt32
+const FLAG_NUTS_STRICT = 0x80 % UInt32
 
 # ---- context / models -------------------------------------------------------------------------------
 mutable struct B200Context
@@ -163,9 +166,13 @@ end
 
 "Many-chain NUTS (MultinomialTS + GeneralisedNoUTurn; the reference's src/trajectory.jl:677-742 is scalar-only)."
 function AdvancedHMC.transition(rng, h::Hamiltonian,
-                                κ::AdvancedHMC.HMCKernel{R,<:Trajectory{MultinomialTS,<:B200Leapfrog,<:GeneralisedNoUTurn}},
-                                z::PhasePoint{<:CuMatrix{Float64}}) where {R}
+                                κ::AdvancedHMC.HMCKernel{R,<:Trajectory{TS,<:B200Leapfrog,TC}},
+                                z::PhasePoint{<:CuMatrix{Float64}}) where {R,TS<:Union{MultinomialTS,SliceTS},
+                                                                          TC<:AdvancedHMC.DynamicTerminationCriterion}
     τ = κ.τ; lf = τ.integrator; tc = τ.termination_criterion
+    # sampler / criterion variants are flag bits of the same entry point (trajectory.jl:102-109, 551-557, 579-613)
+    flags = (TS <: SliceTS ? FLAG_NUTS_SLICE_TS : 0x0 % UInt32) |
+            (TC <: ClassicNoUTurn ? FLAG_NUTS_CLASSIC : TC <: StrictGeneralisedNoUTurn ? FLAG_NUTS_STRICT : 0x0 % UInt32)
     D, N = size(z.θ)
     zout = PhasePoint(similar(z.θ), similar(z.r), DualValue(similar(z.ℓπ.value), similar(z.ℓπ.gradient)),
                       DualValue(similar(z.ℓκ.value), similar(z.ℓκ.gradient)))
@@ -180,12 +187,51 @@ function AdvancedHMC.transition(rng, h::Hamiltonian,
         check(ccall((:ahmc_nuts_transition_f64, libahmc), Cint,
                     (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CMetric}, Int32, Int64, Float64, Ptr{Float64}, Int32, Float64, Ref{CRng},
                      Ref{CPhasePoint}, Ref{CPhasePoint}, Ref{CStats}, UInt32),
-                    context().h, lf.target.handle, md, D, N, ϵ, ϵp, tc.max_depth, tc.Δ_max, rg, zi, zo, st, 0))
+                    context().h, lf.target.handle, md, D, N, ϵ, ϵp, tc.max_depth, tc.Δ_max, rg, zi, zo, st, flags))
     end
     tstat = merge((n_steps=ns, is_accept=true, acceptance_rate=α, log_density=zout.ℓπ.value, hamiltonian_energy=H,
                    hamiltonian_energy_error=dH, max_hamiltonian_energy_error=mx, tree_depth=td, numerical_error=nerr .== 1),
                   AdvancedHMC.stat(lf))
     return Transition(zout, tstat)
+end
+
+struct CAdaptCfg
+    n_adapts::Int32; init_buffer::Int32; term_buffer::Int32; window_size::Int32
+    delta::Float64; gamma::Float64; t0::Float64; kappa::Float64
+    adapt_metric::Int32; n_min::Int32
+    eps_chain::Ptr{Float64}; Minv_chain::Ptr{Float64}; eps_trace::Ptr{Float64}
+end
+
+"""
+`sample(rng, h, κ, θ, n_samples, adaptor, n_adapts)` (src/sampler.jl:159-248) for many-chain NUTS with the reference's
+vectorised adaptors -- `StanHMCAdaptor(WelfordVar((D, N)), NesterovDualAveraging(δ, ϵ::Vector))` -- as ONE launch
+(ahmc_nuts_adapt_sample_f64): every chain adapts its own ϵ and diagonal M⁻¹ and never waits for another chain.
+Returns (θ draws D×N×n_samples, final per-chain ϵ, per-chain M⁻¹ D×N).
+"""
+function b200_sample_nuts(rng, h::Hamiltonian, lf::B200Leapfrog, tc::GeneralisedNoUTurn, θ::CuMatrix{Float64},
+                          n_samples::Int, n_adapts::Int; δ=0.8, adapt_metric=true, init_buffer=75, term_buffer=50,
+                          window_size=25)
+    D, N = size(θ)
+    z = b200_phasepoint(lf.target, h, θ, CUDA.zeros(Float64, D, N))
+    zout = PhasePoint(similar(z.θ), similar(z.r), DualValue(similar(z.ℓπ.value), similar(z.ℓπ.gradient)),
+                      DualValue(similar(z.ℓκ.value), similar(z.ℓκ.gradient)))
+    ϵ = CUDA.fill(Float64(first(step_size(lf))), N); Minv = CUDA.ones(Float64, D, N)
+    draws = CUDA.zeros(Float64, D, N, n_samples)
+    α = CUDA.zeros(Float64, N * n_samples)
+    st = Ref(CStats(C_NULL, C_NULL, pointer(α), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
+    cfg = Ref(CAdaptCfg(n_adapts, init_buffer, term_buffer, window_size, δ, 0.05, 10.0, 0.75, adapt_metric ? 1 : 0, 10,
+                        pointer(ϵ), pointer(Minv), C_NULL))
+    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, 0.0))
+    md = Ref(cmetric(h.metric, N)); zi = Ref(cpp(z)); zo = Ref(cpp(zout))
+    zo[] = CPhasePoint(zo[].theta, zo[].r, zo[].lp_value, zo[].lp_gradient, zo[].lk_value, C_NULL, zo[].ld)
+    GC.@preserve z zout ϵ Minv draws α begin
+        check(ccall((:ahmc_nuts_adapt_sample_f64, libahmc), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CMetric}, Int32, Int64, Int32, Float64, Int32, Ref{CAdaptCfg}, Ref{CRng},
+                     Ref{CPhasePoint}, Ref{CPhasePoint}, Ptr{Float64}, Ref{CStats}, UInt32),
+                    context().h, lf.target.handle, md, D, N, tc.max_depth, tc.Δ_max, n_samples, cfg, rg, zi, zo,
+                    pointer(draws), st, 0))
+    end
+    return draws, ϵ, Minv
 end
 
 "`phasepoint(h, θ, r)` (src/hamiltonian.jl:115-119) for a B200 target."

@@ -59,6 +59,13 @@ def run(name, world, rank, dev, scale, iters):
         adaptor = ad.StanHMCAdaptor(ad.WelfordVar(D), ad.NesterovDualAveraging(0.8, 0.1))
         n_samples = iters or 120
         n_adapts = int(n_samples * 0.8)
+    elif name == "c4v":  # C4 with the reference's vectorised (per-chain) adaptors: warm-up + sampling in ONE launch
+        D, N = 100, int(32768 * scale) // world
+        h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.Funnel(D))
+        kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
+        adaptor = A.VectorisedStanAdaptor(delta=0.8)
+        n_samples = iters or 120
+        n_adapts = int(n_samples * 0.8)
     elif name == "c5":  # NUTS + DenseEuclideanMetric, D=256 Gaussian, 8192 chains over the ranks
         D, N = 256, int(8192 * scale) // world
         Sigma, P = correlated_gaussian(D, SEED + 5)
@@ -89,7 +96,7 @@ def run(name, world, rank, dev, scale, iters):
     th = res.theta
     out = dict(config=name, n_gpus=world, chains=N * world, D=D, transitions=n_samples, n_adapts=n_adapts,
                seconds=dt, leapfrog_steps=steps, rate_steps_dims_per_s=steps * D / dt,
-               final_eps=float(res.eps) if np.ndim(res.eps) == 0 else None,
+               final_eps=float(res.eps) if np.ndim(res.eps) == 0 else float(res.eps.double().median().item()),
                mean_accept=float(np.mean([s["acceptance_rate"] for s in res.stats[n_adapts:]])),
                divergent=int(sum(s["numerical_error"] for s in res.stats[n_adapts:])),
                theta_mean_abs_max=float(th.mean(dim=0).abs().max().item()), theta_std_first=float(th[:, 0].std().item()),
