@@ -399,10 +399,10 @@ def sample(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_samples: int, ada
             torch.cuda.synchronize(z.theta.device)
         tm["sampling_launch"] += time.perf_counter() - t0
         a, e, n = st["acceptance_rate"], st["numerical_error"], st["n_steps"]
-        if hasattr(a, "detach"):
-            acc.extend(a.double().mean(dim=1).unbind())
-            nerr.extend(e.sum(dim=1).unbind())
-            nst.extend(n.sum(dim=1).unbind())
+        if hasattr(a, "detach"):  # (T,) device vectors: one chunk each, fetched once below
+            acc.append(a.double().mean(dim=1))
+            nerr.append(e.sum(dim=1))
+            nst.append(n.sum(dim=1))
         else:
             acc.extend(np.asarray(a, dtype=np.float64).mean(axis=1))
             nerr.extend(np.asarray(e).sum(axis=1))
@@ -417,14 +417,14 @@ def sample(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_samples: int, ada
 
     t0 = time.perf_counter()
 
-    def fetch(xs):  # one device->host transfer for the whole run
+    def fetch(xs):  # one device->host transfer for the whole run (entries: 0-d scalars or (T,) chunks)
         if xs and hasattr(xs[0], "detach"):
-            return torch.stack([x.double() for x in xs]).cpu().numpy()
+            return torch.cat([x.double().reshape(-1) for x in xs]).cpu().numpy()
         return np.asarray([float(x) for x in xs], dtype=np.float64)
 
     acc_h, nerr_h, nst_h = fetch(acc), fetch(nerr), fetch(nst)
     stats = [dict(acceptance_rate=float(acc_h[k]), step_size=eps_used[k], numerical_error=int(nerr_h[k]),
-                  n_steps=int(nst_h[k]), is_adapt=is_adapt[k]) for k in range(len(acc))]
+                  n_steps=int(nst_h[k]), is_adapt=is_adapt[k]) for k in range(len(acc_h))]
     total_steps = int(nst_h.sum())
     tm["bookkeeping"] += time.perf_counter() - t0
     return SampleResult(z.theta, draws, stats, A.step_size(kappa.tau.integrator),

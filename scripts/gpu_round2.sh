@@ -2,8 +2,12 @@
 set -u
 mkdir -p gpurun_out
 python advancedhmc.jl_b200/build.py > gpurun_out/build.log 2>&1
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
 echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
-timeout 600 python scripts/run_configs.py c4 c4v --scale 0.125 2>&1 | grep -v Warn > gpurun_out/configs_c4.log
-timeout 600 python scripts/run_configs.py c4 c4v --scale 0.125 --iters 1000 2>&1 | grep -v Warn >> gpurun_out/configs_c4.log
-tail -40 gpurun_out/pytest_gpu.log; cat gpurun_out/configs_c4.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 300 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+timeout 900 python scripts/run_configs.py c1 c2 c3 c4 c4v c5 2>&1 | grep -v Warn > gpurun_out/configs_1gpu.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 3 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
+tail -6 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -2 gpurun_out/bench.err; cat gpurun_out/bench_ref.json; cat gpurun_out/configs_1gpu.log
