@@ -32,5 +32,14 @@ if which in ("all", "k3"):
     for _ in range(3):
         tr = A.transition(rng, h, kern, z0)
     print("nuts depth mean", tr.stat["tree_depth"].double().mean().item(), "steps", tr.stat["n_steps"].double().mean().item())
+if which in ("all", "k4"):
+    rng4 = np.random.Generator(np.random.PCG64(bench.SEED))
+    Q, _ = np.linalg.qr(rng4.normal(size=(128, 128)))
+    lam = np.exp(np.linspace(np.log(0.1), np.log(10.0), 128))
+    hd = A.Hamiltonian(A.DiagEuclideanMetric(np.diag((Q * lam) @ Q.T).copy()), A.DenseGaussian(np.zeros(128), (Q / lam) @ Q.T))
+    zd = A.phasepoint(hd, torch.as_tensor(th, device=dev), torch.as_tensor(r, device=dev))
+    pd = A.StepPlan(A.Leapfrog(0.02), hd, zd, 32)
+    for _ in range(3):
+        pd()
 torch.cuda.synchronize()
 print("done")
