@@ -213,3 +213,45 @@ def test_sample_with_vectorised_adaptor_runs_funnel_warmup_in_one_launch():
     assert float(res.eps.min()) > 1e-3 and float(res.eps.max()) < 2.0
     v = res.theta[:, 0].cpu().numpy()
     assert abs(v.std() - 3.0) < 1.0  # the funnel's neck variable ~ N(0, 3^2)
+
+
+def test_in_launch_adaptation_degenerate_and_host_forms():
+    """n_adapts = 0 -> the adaptive family is bit-identical to the plain persistent launch (same arithmetic, same
+    Philox streams); host (numpy) buffers give the device result; unsupported combinations fail loudly."""
+    D, N, T = 12, 130, 15
+    rng = np.random.default_rng(9)
+    sd = np.exp(rng.uniform(-0.7, 0.7, D))
+    target = A.DiagGaussian(rng.normal(size=D), sd)
+    Minv = np.exp(rng.uniform(-0.3, 0.3, D))
+    h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), target)
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.25), A.GeneralisedNoUTurn(7, 1000.0)))
+    th = rng.normal(size=(N, D))
+    z0 = A.phasepoint(h, torch.as_tensor(th, device=DEV), torch.zeros((N, D), dtype=torch.float64, device=DEV))
+    ad0 = A.VectorisedStanAdaptor()
+    zl, dr, st, eps, minv, tr = A.nuts_adapt_sample(A.PhiloxRNG(3), h, kern, z0, T, 0, ad0, keep_eps_trace=True)
+    zl2, dr2, st2 = A.sample_transitions(A.PhiloxRNG(3), h, kern, z0, T)
+    assert torch.equal(dr, dr2) and torch.equal(zl.theta, zl2.theta) and torch.equal(st["n_steps"], st2["n_steps"])
+    assert torch.equal(eps, torch.full_like(eps, 0.25)) and torch.equal(tr, torch.full_like(tr, 0.25))
+    assert np.allclose(minv.cpu().numpy(), np.broadcast_to(Minv, (N, D)))
+    # adapting run: host buffers == device buffers
+    ad1 = A.VectorisedStanAdaptor(init_buffer=3, term_buffer=2, window_size=4, n_min=3)
+    zd, dd, sd_, ed, md, _ = A.nuts_adapt_sample(A.PhiloxRNG(4), h, kern, z0, T, 12, ad1)
+    zh0 = A.phasepoint(h, th, np.zeros((N, D)))
+    zh, dh, sh, eh, mh, _ = A.nuts_adapt_sample(A.PhiloxRNG(4), h, kern, zh0, T, 12, ad1)
+    assert np.array_equal(dh, dd.cpu().numpy()) and np.array_equal(eh, ed.cpu().numpy()) and np.array_equal(mh, md.cpu().numpy())
+    assert not np.allclose(mh, np.broadcast_to(Minv, (N, D)))  # the windows did update the metric
+    assert (eh != 0.25).all()
+    # per-chain initial step sizes are honoured
+    e0 = torch.as_tensor(rng.uniform(0.1, 0.4, N), device=DEV)
+    k2 = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(e0), A.GeneralisedNoUTurn(7, 1000.0)))
+    _, _, _, e2, _, t2 = A.nuts_adapt_sample(A.PhiloxRNG(5), h, k2, z0, 3, 0, ad0, keep_eps_trace=True)
+    assert torch.equal(t2[0], e0) and torch.equal(e2, e0)
+    # loud failures
+    hu = A.Hamiltonian(A.UnitEuclideanMetric(D), target)
+    with pytest.raises(A.AhmcError):
+        A.nuts_adapt_sample(A.PhiloxRNG(1), hu, kern, A.phasepoint(hu, z0.theta, z0.r), 4, 2, ad0)
+    ks = A.HMCKernel(A.Trajectory(A.SliceTS, A.Leapfrog(0.25), A.GeneralisedNoUTurn()))
+    with pytest.raises(A.AhmcError):
+        A.nuts_adapt_sample(A.PhiloxRNG(1), h, ks, z0, 4, 2, ad0)
+    with pytest.raises(A.AhmcError):
+        A.nuts_adapt_sample(A.PhiloxRNG(1), h, kern, z0, 4, 5, ad0)  # n_adapts > n_transitions
