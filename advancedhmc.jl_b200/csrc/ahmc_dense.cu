@@ -13,6 +13,9 @@
 // proof as the separable fast path applies with the induced infinity norms (K = (1+|eps| |Minv|_inf)(1+|eps| |P|_inf)),
 // energies are evaluated once at the end, and a tile that fails a magnitude check is handed, chain by chain, to
 // the exact warp-per-chain kernel (`only_mask`) inside the same stream -- no host round trip.
+#include <cstdlib>
+#include <cstring>
+
 #include "ahmc_kernels.cuh"
 
 namespace ahmc {
@@ -132,8 +135,8 @@ struct DenseArgs {
     uint8_t* need_exact;  // per chain: 1 -> the exact warp-per-chain kernel must redo this chain
 };
 
-template <int RB, int CB>
-__global__ void __launch_bounds__(kDenseThreads, 1) dense_traj_kernel(const DenseArgs a) {
+template <int RB, int CB, int MINB = 1>
+__global__ void __launch_bounds__(kDenseThreads, MINB) dense_traj_kernel(const DenseArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CT = 8 * CB;
     const int Dp = a.Dp, D = a.D, Dx = Dp + 4, Ds = Dp + 4;
@@ -406,15 +409,15 @@ bool dense_tile_shape(int D, int* Dp, int* RB, int* CB) {
     return true;
 }
 
-template <int RB, int CB>
+template <int RB, int CB, int MINB = 1>
 static cudaError_t launch_dense_t(const DenseArgs& a, cudaStream_t st) {
     constexpr int CT = 8 * CB;
     const int Ds = a.Dp + 4;
     const size_t sm = ((size_t)2 * kKC * Ds + (size_t)CT * Ds + 8 * CT * 2) * sizeof(double) + 64;
-    cudaError_t e = cudaFuncSetAttribute(dense_traj_kernel<RB, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaError_t e = cudaFuncSetAttribute(dense_traj_kernel<RB, CB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
     const long long blocks = (a.N + CT - 1) / CT;
-    dense_traj_kernel<RB, CB><<<(unsigned)blocks, kDenseThreads, sm, st>>>(a);
+    dense_traj_kernel<RB, CB, MINB><<<(unsigned)blocks, kDenseThreads, sm, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -429,7 +432,12 @@ cudaError_t launch_dense_traj(const DenseTrajHost& h, cudaStream_t st, int* n_la
     const int RB = h.Dp / 64;
     switch (RB) {
         case 1: return launch_dense_t<1, 4>(a, st);
-        case 2: return launch_dense_t<2, 4>(a, st);
+        case 2: {
+            // A/B knob: AHMC_DENSE_TILE=16x2 -> tiles of 16 chains, two CTAs per SM (barrier stalls of one hide behind the other)
+            const char* ev = getenv("AHMC_DENSE_TILE");
+            if (ev && !strcmp(ev, "16x2")) return launch_dense_t<2, 2, 2>(a, st);
+            return launch_dense_t<2, 4>(a, st);
+        }
         case 3: return launch_dense_t<3, 2>(a, st);
         case 4: return launch_dense_t<4, 2>(a, st);
         case 5: return launch_dense_t<5, 1>(a, st);

@@ -61,6 +61,9 @@ constexpr int nuts_min_blocks() { return E <= 4 ? AHMC_NUTS_MINB : (E <= 8 ? 2 :
 // (trajectory.jl:551-557, 579-613), selected at run time by a.sampler / a.criterion.
 template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
 __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kernel(const NutsArgs a) {
+    // Dense metric: a merge needs dH/dr = M^-1 r of the pending half's first leaf -- a D x D product.  The default family
+    // caches the vector (slot 1 of the level holds M^-1 r_first instead of r_first) so merges do no dense product at all.
+    constexpr bool STORE_DR = !VAR && METRIC == AHMC_METRIC_DENSE;
     const int samp = VAR ? a.sampler : 0;    // 0 MultinomialTS, 1 SliceTS
     const int crit = VAR ? a.criterion : 0;  // 0 Generalised, 1 Classic, 2 StrictGeneralised
     double lu = 0.0;                         // SliceTS slice variable (log space)
@@ -414,7 +417,13 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 }
                 double d1 = 0.0, d2 = 0.0;
                 bool uturn;
-                me.dHdr(rf_p, t1, xs, l);
+                if (STORE_DR) {  // dH/dr of the pending half's first leaf was cached when that leaf was stored
+#pragma unroll
+                    for (int e = 0; e < E; ++e) t1[e] = 0.0;
+                    if (do_comb) vload_nc<G, E>(t1, L + D, l, D);
+                } else {
+                    me.dHdr(rf_p, t1, xs, l);
+                }
                 if (VAR && crit == 1) {
                     // ClassicNoUTurn (:551-557): s = dot(dtheta, dH/dr(-r_left)) >= 0 || dot(-dtheta, dH/dr(r_right)) >= 0
                     // with dtheta = theta_right - theta_left; q = -dtheta
@@ -468,7 +477,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                         // whose slot is still intact (level 0 keeps it as its candidate momentum)
                         double t[E];
                         const double* P = level(k - 1);
-                        vload_nc<G, E>(t, (k == 1) ? P + 3 * (long long)D : P + D, l, D);
+                        vload_nc<G, E>(t, (k == 1 && !STORE_DR) ? P + 3 * (long long)D : P + D, l, D);
                         vstore<G, E>(L + D, t, l, D);
                         vstore<G, E>(L, rho_cur, l, D);
                         if (VAR && crit == 2) vstore<G, E>(L + 5 * (long long)D, s.r, l, D);  // rlast = the current leaf
@@ -477,6 +486,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                             vstore<G, E>(L + 6 * (long long)D, t, l, D);
                         }
                     }
+                    if (STORE_DR && k == 0) vstore<G, E>(L + D, dr, l, D);  // M^-1 r of this leaf, for the merge above
                     double clp, clk;
                     if (cand_cur < 0) {
                         vstore<G, E>(L + 2 * (long long)D, s.th, l, D);

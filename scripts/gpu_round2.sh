@@ -1,16 +1,10 @@
 #!/bin/bash
-# sanitizer over the code added this session + ncu capture of K4
 set -u
 mkdir -p gpurun_out
 python advancedhmc.jl_b200/build.py > gpurun_out/build.log 2>&1
-SEL="variants or in_launch or vectorised or pipelined or adapt_cov or nutpie or welford_cov or multinomial"
-timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -q -x -k "$SEL" > gpurun_out/sanitizer_memcheck_new.log 2>&1
-echo "memcheck exit: $?" | tee gpurun_out/sanitizer_new_summary.log
-grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_memcheck_new.log | tail -3 | tee -a gpurun_out/sanitizer_new_summary.log
-timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -q -x -k "adapt_cov or in_launch or variants_vs_oracle" > gpurun_out/sanitizer_racecheck_new.log 2>&1
-echo "racecheck exit: $?" | tee -a gpurun_out/sanitizer_new_summary.log
-grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_racecheck_new.log | tail -3 | tee -a gpurun_out/sanitizer_new_summary.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:dense_traj_kernel -s 1 -c 1 -f -o /tmp/k4 python scripts/profile_k1.py k4 > gpurun_out/prof_k4.log 2>&1
-ncu -i /tmp/k4.ncu-rep --page details > gpurun_out/k4_details.txt 2>> gpurun_out/prof_k4.log
-ncu -i /tmp/k4.ncu-rep --page source --csv > gpurun_out/k4_source.csv 2>> gpurun_out/prof_k4.log
-tail -3 gpurun_out/prof_k4.log
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -30 > gpurun_out/pytest_gpu.log
+echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
+timeout 300 python scripts/k4_ab.py > gpurun_out/k4_ab.log 2>&1
+timeout 600 python scripts/run_configs.py c5 c2 2>&1 | grep -v Warn > gpurun_out/configs_c5.log
+AHMC_DENSE_TILE=16x2 timeout 600 python scripts/run_configs.py c2 2>&1 | grep -v Warn >> gpurun_out/configs_c5.log
+tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/k4_ab.log; cat gpurun_out/configs_c5.log
