@@ -10,7 +10,10 @@
  * therefore pinned by (i) 50-digit closed-form linear-map known answers for Gaussian targets
  * (tests/golden/gen_closed_form.py), (ii) the algebraic identities the reference's own tests assert
  * (test/hamiltonian.jl:54-79, test/integrator.jl:17-32,108-153, test/adaptation.jl:131-151,
- * test/trajectory.jl:249-325) and (iii) an independent op-for-op numpy twin (oracle/oracle_np.py).
+ * test/trajectory.jl:249-325), (iii) an independent op-for-op numpy twin (oracle/oracle_np.py) and (iv) for the
+ * NUTS transitions (both trajectory samplers, all three termination criteria, numerical termination) a second,
+ * independently written recursive restatement of src/trajectory.jl:626-742 evaluated in 50-digit arithmetic
+ * (tests/golden/gen_nuts_mp.py -> tests/golden/nuts_mp50.json: identical trees, outputs to 1e-10).
  * It is NOT pinned against outputs of the reference itself: "parity unpinned" at that level.
  *
  * All `file:line` citations are relative to /root/reference/.

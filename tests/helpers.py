@@ -14,6 +14,12 @@ def golden_cases():
         return json.load(f)
 
 
+def nuts_golden_cases():
+    """tests/golden/nuts_mp50.json: NUTS transitions from the recursive 50-digit restatement (gen_nuts_mp.py)."""
+    with open(os.path.join(HERE, "golden", "nuts_mp50.json")) as f:
+        return json.load(f)["cases"]
+
+
 def case_arrays(case):
     """-> dict of numpy arrays in (D,N) Fortran layout."""
     D, N = case["D"], case["N"]

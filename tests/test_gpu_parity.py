@@ -7,7 +7,8 @@ import torch
 
 import ahmc_b200 as A
 from oracle import oracle_c as oc
-from tests.helpers import METRIC_KINDS, MODEL_KINDS, case_arrays, golden_cases, rel_err, synth_diag_gauss
+from tests.helpers import (METRIC_KINDS, MODEL_KINDS, case_arrays, golden_cases, nuts_golden_cases, rel_err,
+                           synth_diag_gauss)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -486,6 +487,38 @@ def test_nuts_variants_differ_from_default_and_sample_the_target():
     assert np.abs(x.std(0) / s - 1).max() < 0.05
     with pytest.raises(A.AhmcError):
         A.transition(A.PhiloxRNG(0), h, A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.1), A.ClassicNoUTurn())), z)
+
+
+_NUTS_GOLD = nuts_golden_cases()
+
+
+@pytest.mark.parametrize("case", _NUTS_GOLD, ids=[c["name"] for c in _NUTS_GOLD])
+def test_nuts_kernel_matches_mp50_recursive_restatement(case):
+    """K3 through the C ABI against tests/golden/nuts_mp50.json (recursive 50-digit restatement of
+    src/trajectory.jl:626-742, independent of the C oracle): identical trees and selections, outputs to 1e-10."""
+    D, N = case["D"], case["N"]
+    p0 = None if case["p0"] is None else np.array(case["p0"])
+    p1 = None if case["p1"] is None else np.array(case["p1"])
+    Minv = None if case["Minv"] is None else np.array(case["Minv"])
+    h = A.Hamiltonian(make_metric(case["metric"], Minv, D), make_target(case["model"], D, p0, p1, case["c0"]))
+    z0 = A.phasepoint(h, torch.as_tensor(np.array(case["theta0"]), device=DEV), torch.as_tensor(np.array(case["r0"]), device=DEV))
+    tau = A.Trajectory(getattr(A, _SAMPLERS[case["sampler"]]), A.Leapfrog(case["eps"]),
+                       getattr(A, _CRITERIA[case["criterion"]])(case["max_depth"], case["delta_max"]))
+    rngt = A.TapeRNG(exp=torch.as_tensor(np.array(case["variates"]), device=DEV),
+                     dirs=torch.as_tensor(np.array(case["dirs"], dtype=np.uint8), device=DEV))
+    tr = A.transition(rngt, h, tau, z0)  # a bare Trajectory: the given momentum is used (no refresh), like the fixture
+    e, st = case["expect"], tr.stat
+    assert (st["tree_depth"].cpu().numpy() == np.array(e["tree_depth"])).all()
+    assert (st["n_steps"].cpu().numpy() == np.array(e["n_steps"])).all()
+    assert (st["numerical_error"].cpu().numpy().astype(bool) == np.array(e["numerical_error"])).all()
+    z = tr.z
+    for got, want in ((z.theta, e["theta"]), (z.r, e["r"]), (z.lp.gradient, e["lp_gradient"])):
+        assert rel_err(got.cpu().numpy(), np.array(want)) < TOL
+    assert np.allclose(z.lp.value.cpu().numpy(), e["lp_value"], rtol=1e-10, atol=1e-10)
+    assert np.allclose(z.lk.value.cpu().numpy(), e["lk_value"], rtol=1e-10, atol=1e-10)
+    assert np.allclose(st["acceptance_rate"].cpu().numpy(), e["acceptance_rate"], rtol=1e-10)
+    assert np.allclose(st["hamiltonian_energy_error"].cpu().numpy(), e["hamiltonian_energy_error"], rtol=1e-9, atol=1e-10)
+    assert np.allclose(st["max_hamiltonian_energy_error"].cpu().numpy(), e["max_hamiltonian_energy_error"], rtol=1e-9, atol=1e-10)
 
 
 def test_nuts_max_depth_and_divergence_flags():

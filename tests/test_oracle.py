@@ -353,3 +353,40 @@ def test_nuts_oracle_variants_sample_standard_normal(sampler, criterion):
         draws.append(z.theta[:, 0].copy())
     X = np.array(draws[200:])
     assert np.abs(X.mean(axis=0)).max() < 0.15 and np.abs(X.var(axis=0) - 1).max() < 0.18
+
+
+# ------------------------------------------------------------------------------------------------ NUTS known answers
+from tests.helpers import nuts_golden_cases  # noqa: E402
+
+_NUTS_GOLD = nuts_golden_cases()
+
+
+@pytest.mark.parametrize("case", _NUTS_GOLD, ids=[c["name"] for c in _NUTS_GOLD])
+def test_nuts_oracle_matches_mp50_recursive_restatement(case):
+    """The C oracle's NUTS transition against tests/golden/nuts_mp50.json -- an independent recursive restatement of
+    src/trajectory.jl:626-742 evaluated in 50-digit arithmetic (tests/golden/gen_nuts_mp.py): same tree for every
+    chain (depth, leapfrog steps, divergence flag, number of random variates consumed), same selected candidate and
+    statistics to 1e-10, for both trajectory samplers and all three termination criteria."""
+    D, N = case["D"], case["N"]
+    kinds = dict(std_normal=oc.STD_NORMAL, diag_gauss=oc.DIAG_GAUSS, dense_gauss=oc.DENSE_GAUSS, funnel=oc.FUNNEL)
+    mkinds = dict(unit=oc.UNIT, diag=oc.DIAG, dense=oc.DENSE)
+    p0 = None if case["p0"] is None else np.array(case["p0"])
+    p1 = None if case["p1"] is None else np.asfortranarray(np.array(case["p1"]))
+    Minv = None if case["Minv"] is None else np.asfortranarray(np.array(case["Minv"]))
+    model, metric = oc.Model(kinds[case["model"]], D, p0, p1, case["c0"]), oc.Metric(mkinds[case["metric"]], Minv)
+    th, r = np.array(case["theta0"]).T, np.array(case["r0"]).T
+    z0 = oc.phasepoint(model, metric, th, r)
+    z, st, used = oc.nuts_transition(model, metric, case["eps"], z0, None, np.array(case["dirs"], dtype=np.uint8),
+                                     np.array(case["variates"]), max_depth=case["max_depth"], delta_max=case["delta_max"],
+                                     sampler=case["sampler"], criterion=case["criterion"])
+    e = case["expect"]
+    assert (st.tree_depth == np.array(e["tree_depth"])).all()
+    assert (st.n_steps == np.array(e["n_steps"])).all()
+    assert (st.numerical_error.astype(bool) == np.array(e["numerical_error"])).all()
+    assert (used == np.array(e["variates_used"])).all()
+    assert rel_err(z.theta, np.array(e["theta"]).T) < 1e-10 and rel_err(z.r, np.array(e["r"]).T) < 1e-10
+    assert rel_err(z.lp_gradient, np.array(e["lp_gradient"]).T) < 1e-10
+    assert np.allclose(z.lp_value, e["lp_value"], rtol=1e-10, atol=1e-10) and np.allclose(z.lk_value, e["lk_value"], rtol=1e-10, atol=1e-10)
+    assert np.allclose(st.acceptance_rate, e["acceptance_rate"], rtol=1e-10)
+    assert np.allclose(st.hamiltonian_energy_error, e["hamiltonian_energy_error"], rtol=1e-9, atol=1e-10)
+    assert np.allclose(st.max_hamiltonian_energy_error, e["max_hamiltonian_energy_error"], rtol=1e-9, atol=1e-10)
