@@ -13,7 +13,8 @@
  * test/trajectory.jl:249-325), (iii) an independent op-for-op numpy twin (oracle/oracle_np.py) and (iv) for the
  * NUTS transitions (both trajectory samplers, all three termination criteria, numerical termination) a second,
  * independently written recursive restatement of src/trajectory.jl:626-742 evaluated in 50-digit arithmetic
- * (tests/golden/gen_nuts_mp.py -> tests/golden/nuts_mp50.json: identical trees, outputs to 1e-10).
+ * (tests/golden/gen_nuts_mp.py -> tests/golden/nuts_mp50.json: identical trees, outputs to 1e-10), and likewise
+ * for the static transitions and the adaptors (gen_hmc_mp.py, gen_adapt_mp.py).
  * It is NOT pinned against outputs of the reference itself: "parity unpinned" at that level.
  *
  * All `file:line` citations are relative to /root/reference/.

@@ -20,6 +20,12 @@ def nuts_golden_cases():
         return json.load(f)["cases"]
 
 
+def hmc_golden_cases():
+    """tests/golden/hmc_mp50.json: static HMC transitions (refresh, EndPointTS / MultinomialTS) from gen_hmc_mp.py."""
+    with open(os.path.join(HERE, "golden", "hmc_mp50.json")) as f:
+        return json.load(f)["cases"]
+
+
 def case_arrays(case):
     """-> dict of numpy arrays in (D,N) Fortran layout."""
     D, N = case["D"], case["N"]

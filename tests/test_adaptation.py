@@ -194,3 +194,39 @@ def test_pooled_welford_cov_and_nutpie_equal_the_sequential_reference_estimators
     assert wc.var.shape == (D, D) and nv.var.shape == (D,)
     # for a Gaussian the Nutpie estimate is sqrt(var_x * var of (Sigma^-1 x))^-1 ... -> positive, finite
     assert np.all(np.isfinite(nv.var)) and np.all(nv.var > 0)
+
+
+def test_adaptors_match_mp50_known_answers():
+    """oracle AND host-mirror adaptors against tests/golden/adapt_mp50.json (50-digit restatement of stepsize.jl:25-62,
+    178-210 and massmatrix.jl:141-157, 244-248, 324-340; tests/golden/gen_adapt_mp.py)."""
+    import json
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "adapt_mp50.json")) as f:
+        g = json.load(f)
+    d = g["dual_averaging"]
+    da_o, da_h = oc.DualAveraging([d["eps0"]], delta=d["delta"]), ad.NesterovDualAveraging(d["delta"], d["eps0"])
+    for i, (a, want) in enumerate(zip(d["alphas"], d["eps_trace"]), 1):
+        da_o.adapt([a])
+        da_h.adapt(min(1.0, a))
+        assert da_o.eps[0] == pytest.approx(want, rel=1e-12) and da_h.eps == pytest.approx(want, rel=1e-12)
+        if i == d["reset_at"]:
+            da_o.reset(), da_h.reset()
+    da_o.finalize(), da_h.finalize()
+    assert da_o.eps[0] == pytest.approx(d["eps_final"], rel=1e-12) and da_h.eps == pytest.approx(d["eps_final"], rel=1e-12)
+    w = g["welford"]
+    xs, gs = np.array(w["xs"]), np.array(w["gs"])
+    D = xs.shape[1]
+    wo, co = oc.WelfordVar((D,)), oc.WelfordCov(D)
+    wh, ch, nh = ad.WelfordVar(D), ad.WelfordCov(D), ad.NutpieVar(D)
+    for x, gr in zip(xs, gs):
+        wo.push(x), co.push(x)
+        one = np.ones(1)
+        wh.push_record(_record(x[None, :], one))
+        ch.push_record(_record_cov(x[None, :], one))
+        nh.push_record(_record_nutpie(x[None, :], gr[None, :], one))
+    for est in (wo.estimate(), wh.get_estimation()):
+        assert np.allclose(est, w["var_estimate"], rtol=1e-11)
+    for est in (co.estimate(), ch.get_estimation()):
+        assert np.allclose(est, w["cov_estimate"], rtol=1e-10, atol=1e-13)
+    assert np.allclose(wh.mu, w["mu"], rtol=1e-12) and np.allclose(wh.M, w["M"], rtol=1e-11)
+    assert np.allclose(nh.get_estimation(), w["nutpie_estimate"], rtol=1e-10)

@@ -7,7 +7,7 @@ import torch
 
 import ahmc_b200 as A
 from oracle import oracle_c as oc
-from tests.helpers import (METRIC_KINDS, MODEL_KINDS, case_arrays, golden_cases, nuts_golden_cases, rel_err,
+from tests.helpers import (METRIC_KINDS, MODEL_KINDS, case_arrays, golden_cases, hmc_golden_cases, nuts_golden_cases, rel_err,
                            synth_diag_gauss)
 
 pytestmark = pytest.mark.gpu
@@ -487,6 +487,39 @@ def test_nuts_variants_differ_from_default_and_sample_the_target():
     assert np.abs(x.std(0) / s - 1).max() < 0.05
     with pytest.raises(A.AhmcError):
         A.transition(A.PhiloxRNG(0), h, A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.1), A.ClassicNoUTurn())), z)
+
+
+_HMC_GOLD = hmc_golden_cases()
+
+
+@pytest.mark.parametrize("case", _HMC_GOLD, ids=[c["name"] for c in _HMC_GOLD])
+def test_static_transitions_match_mp50_restatement(case):
+    """K2 (refresh + trajectory + Metropolis step + flip) and the MultinomialTS static kernel through the C ABI against
+    tests/golden/hmc_mp50.json (50-digit restatement of metric.jl:290-320 and trajectory.jl:271-390)."""
+    D, N = case["D"], case["N"]
+    p0 = None if case["p0"] is None else np.array(case["p0"])
+    p1 = None if case["p1"] is None else np.array(case["p1"])
+    Minv = None if case["Minv"] is None else np.array(case["Minv"])
+    h = A.Hamiltonian(make_metric(case["metric"], Minv, D), make_target(case["model"], D, p0, p1, case["c0"]))
+    th0 = torch.as_tensor(np.array(case["theta0"]), device=DEV)
+    z0 = A.phasepoint(h, th0, torch.zeros_like(th0))
+    normals = torch.as_tensor(np.array(case["normals"]), device=DEV)
+    var = torch.as_tensor(np.array(case["variates"]), device=DEV)
+    if case["sampler"] == "endpoint":
+        tau = A.Trajectory(A.EndPointTS, A.Leapfrog(case["eps"]), A.FixedNSteps(case["n_steps"]))
+        tr = A.transition(A.TapeRNG(normal=normals, exp=var), h, A.HMCKernel(tau), z0)
+    else:
+        tau = A.Trajectory(A.MultinomialTS, A.Leapfrog(case["eps"]), A.FixedNSteps(case["n_steps"]))
+        tr = A.transition(A.TapeRNG(normal=normals, exp=var, n_fwd=case["n_fwd"]), h, A.HMCKernel(tau), z0)
+        assert (tr.stat["tree_depth"].cpu().numpy() == np.array(case["expect"]["index"])).all()
+    e, st, z = case["expect"], tr.stat, tr.z
+    assert (st["is_accept"].cpu().numpy().astype(bool) == np.array(e["is_accept"])).all()
+    for got, want in ((z.theta, e["theta"]), (z.r, e["r"]), (z.lp.gradient, e["lp_gradient"])):
+        assert rel_err(got.cpu().numpy(), np.array(want)) < TOL
+    assert np.allclose(z.lp.value.cpu().numpy(), e["lp_value"], rtol=1e-10, atol=1e-10)
+    assert np.allclose(z.lk.value.cpu().numpy(), e["lk_value"], rtol=1e-10, atol=1e-10)
+    assert np.allclose(st["acceptance_rate"].cpu().numpy(), e["acceptance_rate"], rtol=1e-10)
+    assert np.allclose(st["hamiltonian_energy_error"].cpu().numpy(), e["hamiltonian_energy_error"], rtol=1e-9, atol=1e-10)
 
 
 _NUTS_GOLD = nuts_golden_cases()

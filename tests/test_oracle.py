@@ -390,3 +390,36 @@ def test_nuts_oracle_matches_mp50_recursive_restatement(case):
     assert np.allclose(st.acceptance_rate, e["acceptance_rate"], rtol=1e-10)
     assert np.allclose(st.hamiltonian_energy_error, e["hamiltonian_energy_error"], rtol=1e-9, atol=1e-10)
     assert np.allclose(st.max_hamiltonian_energy_error, e["max_hamiltonian_energy_error"], rtol=1e-9, atol=1e-10)
+
+
+from tests.helpers import hmc_golden_cases  # noqa: E402
+
+_HMC_GOLD = hmc_golden_cases()
+
+
+@pytest.mark.parametrize("case", _HMC_GOLD, ids=[c["name"] for c in _HMC_GOLD])
+def test_hmc_oracle_matches_mp50_restatement(case):
+    """The C oracle's static transitions (momentum refresh from normals, EndPointTS Metropolis step with momentum flip,
+    MultinomialTS trajectory sampling) against tests/golden/hmc_mp50.json (50-digit restatement, gen_hmc_mp.py)."""
+    D, N = case["D"], case["N"]
+    kinds = dict(std_normal=oc.STD_NORMAL, diag_gauss=oc.DIAG_GAUSS, dense_gauss=oc.DENSE_GAUSS, funnel=oc.FUNNEL)
+    mkinds = dict(unit=oc.UNIT, diag=oc.DIAG, dense=oc.DENSE)
+    p0 = None if case["p0"] is None else np.array(case["p0"])
+    p1 = None if case["p1"] is None else np.asfortranarray(np.array(case["p1"]))
+    Minv = None if case["Minv"] is None else np.asfortranarray(np.array(case["Minv"]))
+    model, metric = oc.Model(kinds[case["model"]], D, p0, p1, case["c0"]), oc.Metric(mkinds[case["metric"]], Minv)
+    th, nt = np.array(case["theta0"]).T, np.array(case["normals"]).T
+    z0 = oc.phasepoint(model, metric, th, np.zeros((D, N)))
+    if case["sampler"] == "endpoint":
+        z, st = oc.hmc_transition(model, metric, case["eps"], case["n_steps"], z0, nt, np.array(case["variates"]))
+    else:
+        z, st = oc.hmc_multinomial_transition(model, metric, case["eps"], case["n_steps"], case["n_fwd"], z0, nt,
+                                              np.array(case["variates"]))
+        assert (st.tree_depth == np.array(case["expect"]["index"])).all()
+    e = case["expect"]
+    assert (st.is_accept.astype(bool) == np.array(e["is_accept"])).all()
+    assert rel_err(z.theta, np.array(e["theta"]).T) < 1e-10 and rel_err(z.r, np.array(e["r"]).T) < 1e-10
+    assert rel_err(z.lp_gradient, np.array(e["lp_gradient"]).T) < 1e-10
+    assert np.allclose(z.lp_value, e["lp_value"], rtol=1e-10, atol=1e-10) and np.allclose(z.lk_value, e["lk_value"], rtol=1e-10, atol=1e-10)
+    assert np.allclose(st.acceptance_rate, e["acceptance_rate"], rtol=1e-10)
+    assert np.allclose(st.hamiltonian_energy_error, e["hamiltonian_energy_error"], rtol=1e-9, atol=1e-10)
