@@ -433,10 +433,12 @@ cudaError_t launch_dense_traj(const DenseTrajHost& h, cudaStream_t st, int* n_la
     switch (RB) {
         case 1: return launch_dense_t<1, 4>(a, st);
         case 2: {
-            // A/B knob: AHMC_DENSE_TILE=16x2 -> tiles of 16 chains, two CTAs per SM (barrier stalls of one hide behind the other)
+            // D <= 128: tiles of 16 chains, two CTAs per SM -- the barrier / copy waits of one hide behind the other
+            // (measured on B200, 4096 / 16384 chains x D=128, L=32: 0.286 / 1.07 ms against 0.294 / 1.91 ms for one
+            // 32-chain CTA per SM).  AHMC_DENSE_TILE=32x1 selects the single-CTA form for A/B runs.
             const char* ev = getenv("AHMC_DENSE_TILE");
-            if (ev && !strcmp(ev, "16x2")) return launch_dense_t<2, 2, 2>(a, st);
-            return launch_dense_t<2, 4>(a, st);
+            if (ev && !strcmp(ev, "32x1")) return launch_dense_t<2, 4>(a, st);
+            return launch_dense_t<2, 2, 2>(a, st);
         }
         case 3: return launch_dense_t<3, 2>(a, st);
         case 4: return launch_dense_t<4, 2>(a, st);

@@ -1,4 +1,4 @@
-"""K4 tile-shape A/B: 32-chain tiles, one CTA per SM (default) vs 16-chain tiles, two CTAs per SM (AHMC_DENSE_TILE=16x2)."""
+"""K4 tile-shape A/B: 16-chain tiles, two CTAs per SM (default) vs 32-chain tiles, one CTA per SM (AHMC_DENSE_TILE=32x1)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -15,7 +15,7 @@ for N in (4096, 16384):
     zd = A.phasepoint(hd, torch.as_tensor(th, device=dev), torch.as_tensor(r, device=dev))
     pd = A.StepPlan(A.Leapfrog(0.02), hd, zd, 32, flags=A.FLAG_ASYNC)
     ref = None
-    for tile in ("", "16x2"):
+    for tile in ("", "32x1"):
         if tile:
             os.environ["AHMC_DENSE_TILE"] = tile
         else:
@@ -31,5 +31,5 @@ for N in (4096, 16384):
         th_out = z.theta.clone()
         if ref is None:
             ref = th_out
-        print(f"N={N} tile={tile or '32x1'}: {ms:.4f} ms/trajectory, {2.0 * 128 * 128 * N * 32 / ms / 1e9:.2f} TFLOP/s, "
+        print(f"N={N} tile={tile or '16x2'}: {ms:.4f} ms/trajectory, {2.0 * 128 * 128 * N * 32 / ms / 1e9:.2f} TFLOP/s, "
               f"max |dtheta| vs default {float((th_out - ref).abs().max()):.3e}", flush=True)
