@@ -20,5 +20,10 @@ if [ "${1:-}" = "prof" ]; then
   ncu -i /tmp/k1.ncu-rep --page source --csv > gpurun_out/k1_headline_source.csv 2>> gpurun_out/prof.log
   ncu -i /tmp/k1.ncu-rep --page details > gpurun_out/k1_headline_details.txt 2>> gpurun_out/prof.log
 fi
+if [ "${1:-}" = "hostlane" ]; then  # the zero-copy host-buffer launch (reads / writes pinned host memory directly)
+  timeout 600 ncu --set full --clock-control none -k regex:leapfrog_kernel -s 6 -c 1 -f -o /tmp/k1h python scripts/profile_k1.py hostlane > gpurun_out/prof_hostlane.log 2>&1
+  ncu -i /tmp/k1h.ncu-rep --page details > gpurun_out/k1_hostlane_details.txt 2>> gpurun_out/prof_hostlane.log
+  ncu -i /tmp/k1h.ncu-rep --page raw --csv > gpurun_out/k1_hostlane_raw.csv 2>> gpurun_out/prof_hostlane.log
+fi
 tail -5 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -2 gpurun_out/bench.err
 cat gpurun_out/bench_ref.json; cat gpurun_out/configs_1gpu.log; cat gpurun_out/k4_ab.log

@@ -41,5 +41,16 @@ if which in ("all", "k4"):
     pd = A.StepPlan(A.Leapfrog(0.02), hd, zd, 32)
     for _ in range(3):
         pd()
+if which in ("all", "hostlane"):
+    pin = lambda a: torch.as_tensor(a).pin_memory()
+    thp, rp = pin(th), pin(r)
+    zh0 = A.phasepoint(h, thp.numpy(), rp.numpy())
+    gp = pin(zh0.lp.gradient)
+    zh0.theta, zh0.r, zh0.lp.gradient = thp.numpy(), rp.numpy(), gp.numpy()
+    outs = [torch.empty((4096, 128), dtype=torch.float64).pin_memory() for _ in range(3)] + [torch.empty((4096,), dtype=torch.float64).pin_memory() for _ in range(2)]
+    zout = A.PhasePoint(outs[0].numpy(), outs[1].numpy(), A.DualValue(outs[3].numpy(), outs[2].numpy()), A.DualValue(outs[4].numpy(), None))
+    ph = A.StepPlan(A.Leapfrog(0.1), h, zh0, 32, out=zout)
+    for _ in range(3):
+        ph()
 torch.cuda.synchronize()
 print("done")
