@@ -971,3 +971,31 @@ def adapt_cov(theta, mean):
     ctx.check(ctx.lib.ahmc_adapt_cov_f64(ctx.h, D, N, _ptr(theta), D, _ptr(mean), _ptr(out),
                                          L.FLAG_HOST_BUFFERS if _is_host(theta) else 0))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# deployment helper: host-buffer calls move every byte over PCIe, so the page-locked buffers should live on the NUMA
+# node the GPU hangs off (on a two-socket B200 box a remote node costs up to ~1.5x per call, profiles/README.md)
+# ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(device: int = 0):
+    """Pin the calling thread to the CPUs NVML reports as local to `device` (nvmlDeviceSetCpuAffinity) so that memory
+    it allocates and first-touches afterwards -- e.g. `torch.Tensor.pin_memory()` buffers handed to the
+    AHMC_FLAG_HOST_BUFFERS calls -- lands on the GPU's NUMA node.  Returns the previous affinity set (pass it to
+    `os.sched_setaffinity(0, prev)` to undo) or None when NVML / the cpuset does not allow it."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(device).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return prev
+    except Exception:
+        return None

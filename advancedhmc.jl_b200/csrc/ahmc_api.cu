@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -638,6 +639,8 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
                                    int64_t N, double eps, const double* eps_chain, int32_t n_steps,
                                    double temper_alpha, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
                                    uint32_t* status, int32_t* steps_done, uint32_t flags) {
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count(); };
     int rc = pipe_resources(ctx);
     if (rc) return rc;
     const char* ev;
@@ -665,6 +668,7 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
     uint32_t* b_st = (uint32_t*)alias(status, out_pinned);
     int32_t* b_sd = (int32_t*)alias(steps_done, out_pinned);
 
+    const double t_attr = since();
     enum { UP_CE1, UP_CE3, UP_DIRECT };
     int up = in_pinned ? UP_DIRECT : UP_CE1;
     bool down_direct = out_pinned;
@@ -832,7 +836,11 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
         CU(cudaStreamWaitEvent(s_cmp, ctx->ev_join[4], 0));
     }
     // host buffers are valid once everything joined into the context stream has retired
+    const double t_issued = since();
     CU(cudaStreamSynchronize(s_cmp));
+    if (trace)
+        fprintf(stderr, "[ahmc pipe] host ms: pointer queries %.3f, everything issued %.3f, synchronised %.3f\n", t_attr,
+                t_issued, since());
     if (trace && !tr.empty()) {
         fprintf(stderr, "[ahmc pipe] up=%s down=%s chunks=%d x %lld chains; ms after the first mark, per chunk [upload] kernel [download]:\n ",
                 up == UP_DIRECT ? "direct" : up == UP_CE3 ? "ce3" : "ce1", down_direct ? "direct" : "ce", k, (long long)chunk);

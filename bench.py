@@ -372,7 +372,9 @@ def run_ours(args):
             if rcmb == 0:
                 dfma = {"tflops": tf.value, "ms": msb.value, "what": "148*8 blocks x 256 threads x 8 independent DFMA chains (libahmc_microbench.so)"}
 
-    # ---- e2e: the public call with HOST (pinned) buffers, copies inside the timed region
+    # ---- e2e: the public call with HOST (pinned) buffers, copies inside the timed region.  The page-locked buffers are
+    # allocated with this thread bound to the GPU's NUMA node (every byte crosses PCIe; a remote node costs up to 1.5x)
+    prev_affinity = A.bind_to_gpu_numa(local)
     thp = torch.as_tensor(th).pin_memory()
     rp = torch.as_tensor(r).pin_memory()
     z0h = A.phasepoint(h, thp.numpy(), rp.numpy())
@@ -399,6 +401,8 @@ def run_ours(args):
         call_ms.append((time.perf_counter() - tc) * 1e3)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)  # the CPU arms below use every host thread again
     h2d = 3 * N_CHAINS * DIM * 8 + DIM * 8
     d2h = 3 * N_CHAINS * DIM * 8 + N_CHAINS * (8 + 8 + 4 + 4)
 
@@ -442,6 +446,7 @@ def run_ours(args):
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "steps*dims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_max / K, "call_ms_min_med_max": [min(call_ms), sorted(call_ms)[len(call_ms) // 2], max(call_ms)],
+                "numa_bound": prev_affinity is not None,
                 "path": "ahmc_leapfrog_f64(AHMC_FLAG_HOST_BUFFERS) via ahmc_b200.step on pinned host arrays"},
         "gpu_launches": int(launches), "clocks": clocks,
         "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],

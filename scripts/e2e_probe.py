@@ -48,6 +48,14 @@ os.environ.pop("AHMC_PIPE_OCC")
 for k in ("AHMC_PIPE_UP", "AHMC_PIPE_DOWN", "AHMC_PIPE_CHUNKS"): os.environ.pop(k)
 print("library defaults: e2e call ms %.4f" % min(t(plan, 40) for _ in range(2)))
 check("library defaults")
+import time as _t
+per = []
+for _ in range(40):
+    t0 = _t.perf_counter(); plan(); per.append((_t.perf_counter() - t0) * 1e3)
+print("per-call wall ms: min %.4f med %.4f max %.4f" % (min(per), sorted(per)[20], max(per)), flush=True)
+os.environ["AHMC_PIPE_TRACE"] = "1"
+for _ in range(4): plan()
+os.environ.pop("AHMC_PIPE_TRACE")
 # how much of the bidirectional PCIe rate survives small copies?  n copies of `mb` MiB each way, two streams
 for mb in (0.5, 1, 2, 4, 12):
     n = int(mb * 2 ** 20 // 8)
