@@ -851,6 +851,60 @@ def find_good_stepsize(rng, h: Hamiltonian, theta, initial_step_size: float = 0.
     return eps
 
 
+def find_good_stepsize_batched(rng, h: Hamiltonian, theta, initial_step_size: float = 0.1, max_n_iters: int = 100):
+    """N independent copies of `find_good_stepsize` (src/trajectory.jl:768-837), one per chain of `theta` (N, D), run in
+    lock-step: every probe `A(h, z, eps)` of all chains is ONE launch of the fused `step` kernel with a per-chain step
+    size; the per-chain search state (a few scalars per chain) is advanced on the host exactly as the reference's
+    control flow does for a single chain (finished chains keep probing with their final eps and ignore the result).
+    Returns eps (N,) -- the natural starting point for the vectorised adaptors (`VectorisedStanAdaptor`).
+    Chain c's result equals `find_good_stepsize` on that chain alone with the same momentum."""
+    if theta.ndim != 2:
+        raise L.InvalidArgument(L.ERR_INVALID, "find_good_stepsize_batched takes (N, D) positions")
+    N = theta.shape[0]
+    host = _is_host(theta)
+    r = rand_momentum(rng, h.metric, h.kinetic, theta)
+    z = phasepoint(h, theta, r)
+
+    def to_h(x):
+        return np.asarray(x, dtype=np.float64) if host else x.detach().cpu().numpy()
+
+    H = to_h(energy(z))
+
+    def A_(eps):  # trajectory.jl:753-757 for all chains
+        e = eps if host else torch.as_tensor(eps, device=theta.device)
+        return to_h(energy(step(Leapfrog(e), h, z, 1, with_lk_gradient=False)))
+
+    log_a_min, log_a_cross, log_a_max = 2 * math.log(0.5), math.log(0.5), math.log(0.75)
+    eps = np.full(N, float(initial_step_size))
+    eps_prime = eps.copy()
+    dH = H - A_(eps)
+    too_high = dH > log_a_cross
+    active = np.ones(N, dtype=bool)
+    for _ in range(max_n_iters):  # crossing step (:796-810)
+        if not active.any():
+            break
+        eps_prime = np.where(active, np.where(too_high, 2.0 * eps, 0.5 * eps), eps_prime)
+        dH = H - A_(eps)
+        crossed = too_high != (dH > log_a_cross)
+        stop = active & crossed
+        cont = active & ~crossed
+        eps = np.where(cont, eps_prime, eps)
+        active = active & ~stop
+    lo, hi = np.minimum(eps, eps_prime), np.maximum(eps, eps_prime)
+    active = np.ones(N, dtype=bool)
+    for _ in range(max_n_iters):  # bisection (:822-834)
+        if not active.any():
+            break
+        mid = 0.5 * (lo + hi)
+        dH = H - A_(np.where(active, mid, lo))
+        up, down = active & (dH > log_a_max), active & (dH < log_a_min)
+        done = active & ~(dH > log_a_max) & ~(dH < log_a_min)
+        lo = np.where(up | done, mid, lo)
+        hi = np.where(down, mid, hi)
+        active = active & ~done
+    return lo if host else torch.as_tensor(lo, device=theta.device)
+
+
 def sample_transitions(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: PhasePoint, n_transitions: int,
                        keep_draws: bool = True, flags: int = 0):
     """`n_transitions` consecutive transitions per chain in ONE kernel launch -- the un-adapted body of

@@ -773,6 +773,24 @@ def test_partial_momentum_refreshment_vs_oracle():
     assert not torch.equal(full.z.theta, tr.z.theta)
 
 
+def test_find_good_stepsize_batched_equals_per_chain_search():
+    """N lock-step copies of the reference's search == the single-chain search run chain by chain on the same momenta;
+    host (numpy) positions give the same step sizes as device positions."""
+    D, N = 10, 37
+    rng = np.random.default_rng(8)
+    s = np.exp(rng.uniform(-1.5, 1.5, D))
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.exp(rng.uniform(-0.5, 0.5, D))), A.DiagGaussian(rng.normal(size=D), s))
+    th = rng.normal(size=(N, D)) * np.exp(rng.uniform(-2, 2, (N, 1)))  # chains at very different energy scales
+    xi = rng.normal(size=(N, D))
+    eps_b = A.find_good_stepsize_batched(A.TapeRNG(normal=torch.as_tensor(xi, device=DEV)), h, torch.as_tensor(th, device=DEV))
+    eps_1 = [A.find_good_stepsize(A.TapeRNG(normal=torch.as_tensor(xi[c:c + 1], device=DEV)), h, torch.as_tensor(th[c], device=DEV))
+             for c in range(N)]
+    assert np.array_equal(eps_b.cpu().numpy(), np.array(eps_1))
+    assert len(set(eps_1)) > 3  # the chains really ended at different step sizes
+    eps_h = A.find_good_stepsize_batched(A.TapeRNG(normal=xi), h, th)
+    assert np.array_equal(eps_h, np.array(eps_1))
+
+
 def test_find_good_stepsize_matches_reference_logic():
     """src/trajectory.jl:768-837 restated on the CPU oracle with the same momentum draw -> same eps."""
     D = 12
