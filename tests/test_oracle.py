@@ -423,3 +423,81 @@ def test_hmc_oracle_matches_mp50_restatement(case):
     assert np.allclose(z.lp_value, e["lp_value"], rtol=1e-10, atol=1e-10) and np.allclose(z.lk_value, e["lk_value"], rtol=1e-10, atol=1e-10)
     assert np.allclose(st.acceptance_rate, e["acceptance_rate"], rtol=1e-10)
     assert np.allclose(st.hamiltonian_energy_error, e["hamiltonian_energy_error"], rtol=1e-9, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------ structural properties
+def _systems():
+    rng = np.random.default_rng(21)
+    D = 4
+    B = rng.normal(size=(D, D))
+    P = B @ B.T / D + np.eye(D)
+    C_ = rng.normal(size=(D, D))
+    Minv_dense = C_ @ C_.T / D + 0.5 * np.eye(D)
+    return [
+        ("diag_gauss/diag", oc.Model(oc.DIAG_GAUSS, D, rng.normal(size=D), np.exp(rng.uniform(-0.5, 0.5, D))), oc.Metric(oc.DIAG, np.exp(rng.uniform(-0.5, 0.5, D)))),
+        ("dense_gauss/dense", oc.Model(oc.DENSE_GAUSS, D, rng.normal(size=D), np.asfortranarray(P)), oc.Metric(oc.DENSE, np.asfortranarray(Minv_dense))),
+        ("funnel/unit", oc.Model(oc.FUNNEL, D), oc.Metric(oc.UNIT)),
+        ("funnel/dense", oc.Model(oc.FUNNEL, D), oc.Metric(oc.DENSE, np.asfortranarray(Minv_dense))),
+    ]
+
+
+@pytest.mark.parametrize("name,model,metric", _systems(), ids=[s[0] for s in _systems()])
+def test_leapfrog_map_is_symplectic_and_volume_preserving(name, model, metric):
+    """The leapfrog map is a composition of shears, hence symplectic for ANY target and metric: its Jacobian J satisfies
+    J' Omega J = Omega (and det J = 1).  Checked by central differences on the restated `step` -- an error in the
+    order / sign / scaling of a kick or drift breaks it at O(1), independently of any known answer."""
+    D = 4
+    rng = np.random.default_rng(5)
+    z0 = np.concatenate([rng.normal(size=D) * 0.5, rng.normal(size=D)])
+    eps, n = 0.13, 3
+
+    def f(v):
+        z = oc.phasepoint(model, metric, v[:D, None].copy(), v[D:, None].copy())
+        z1 = oc.leapfrog(model, metric, eps, z, n)[0]
+        return np.concatenate([z1.theta[:, 0], z1.r[:, 0]])
+
+    hstep = 1e-5
+    J = np.zeros((2 * D, 2 * D))
+    for k in range(2 * D):
+        e = np.zeros(2 * D)
+        e[k] = hstep
+        J[:, k] = (f(z0 + e) - f(z0 - e)) / (2 * hstep)
+    Om = np.block([[np.zeros((D, D)), np.eye(D)], [-np.eye(D), np.zeros((D, D))]])
+    assert np.abs(J.T @ Om @ J - Om).max() < 1e-7
+    assert abs(np.linalg.det(J) - 1.0) < 1e-7
+
+
+@pytest.mark.parametrize("name,model,metric", _systems(), ids=[s[0] for s in _systems()])
+def test_energy_error_is_second_order_in_the_step_size(name, model, metric):
+    """Over a fixed integration time the energy error of leapfrog scales like eps^2: halving eps divides it by ~4."""
+    D = 4
+    rng = np.random.default_rng(6)
+    th, r = rng.normal(size=(D, 6)) * 0.4, rng.normal(size=(D, 6))
+    z = oc.phasepoint(model, metric, th, r)
+    H0 = z.energy()
+    errs = []
+    for eps, n in ((0.04, 8), (0.02, 16), (0.01, 32)):
+        z1 = oc.leapfrog(model, metric, eps, z, n)[0]
+        errs.append(np.abs(z1.energy() - H0))
+    r1, r2 = errs[0] / errs[1], errs[1] / errs[2]
+    assert np.all((r1 > 2.5) & (r1 < 6.5)) and np.all((r2 > 3.0) & (r2 < 5.5)), (r1, r2)
+
+
+def test_gaussian_leapfrog_map_is_linear():
+    """Gaussian target (mean 0) + Euclidean metric: the n-step map is linear in (theta, r) -- the property the fused
+    fast path and the tiled DMMA kernel rely on (magnitude proof, energies evaluated once at the end)."""
+    rng = np.random.default_rng(7)
+    D = 5
+    B = rng.normal(size=(D, D))
+    model = oc.Model(oc.DENSE_GAUSS, D, np.zeros(D), np.asfortranarray(B @ B.T / D + np.eye(D)))
+    metric = oc.Metric(oc.DIAG, np.exp(rng.uniform(-0.5, 0.5, D)))
+
+    def f(th, r):
+        z1 = oc.leapfrog(model, metric, 0.11, oc.phasepoint(model, metric, th[:, None].copy(), r[:, None].copy()), 9)[0]
+        return z1.theta[:, 0], z1.r[:, 0]
+
+    a, b = 0.7, -1.9
+    t1, r1, t2, r2 = (rng.normal(size=D) for _ in range(4))
+    A1, A2, A3 = f(t1, r1), f(t2, r2), f(a * t1 + b * t2, a * r1 + b * r2)
+    assert np.allclose(A3[0], a * A1[0] + b * A2[0], rtol=1e-12, atol=1e-12)
+    assert np.allclose(A3[1], a * A1[1] + b * A2[1], rtol=1e-12, atol=1e-12)
