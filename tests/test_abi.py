@@ -82,3 +82,50 @@ def test_nsteps():
     assert A.nsteps(A.Trajectory(A.EndPointTS, A.Leapfrog(3.0), A.FixedIntegrationTime(1.0))) == 1
     with pytest.raises(ValueError):
         A.nsteps(A.Trajectory(A.EndPointTS, A.Leapfrog(np.full(3, 0.1)), A.FixedIntegrationTime(1.0)))
+
+
+def test_ctypes_mirror_matches_the_header(tmp_path):
+    """The Python binding restates the header's constants and struct layouts by hand: compile a tiny C program against
+    include/ahmc_b200.h (gcc, no CUDA needed) that prints every flag / kind value and sizeof / offsetof of every struct,
+    and compare with advancedhmc.jl_b200/_lib.py."""
+    import subprocess
+
+    from ahmc_b200 import _lib as L
+
+    src = tmp_path / "abi_probe.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "ahmc_b200.h"
+#define P(name, v) printf("%s %lld\n", name, (long long)(v))
+int main(void) {
+    P("FLAG_HOST_BUFFERS", AHMC_FLAG_HOST_BUFFERS); P("FLAG_COMPAT_BREAK_ALL", AHMC_FLAG_COMPAT_BREAK_ALL);
+    P("FLAG_ASYNC", AHMC_FLAG_ASYNC); P("FLAG_EXACT_CHECKS", AHMC_FLAG_EXACT_CHECKS); P("FLAG_NO_REFRESH", AHMC_FLAG_NO_REFRESH);
+    P("FLAG_NUTS_SLICE_TS", AHMC_FLAG_NUTS_SLICE_TS); P("FLAG_NUTS_CLASSIC", AHMC_FLAG_NUTS_CLASSIC);
+    P("FLAG_NUTS_STRICT", AHMC_FLAG_NUTS_STRICT); P("STATUS_NONFINITE", AHMC_STATUS_NONFINITE);
+    P("sizeof_metric", sizeof(ahmc_metric)); P("metric.Minv", offsetof(ahmc_metric, Minv));
+    P("metric.chain_stride", offsetof(ahmc_metric, chain_stride)); P("metric.cholU", offsetof(ahmc_metric, cholU));
+    P("sizeof_phasepoint", sizeof(ahmc_phasepoint)); P("phasepoint.lk_gradient", offsetof(ahmc_phasepoint, lk_gradient));
+    P("phasepoint.ld", offsetof(ahmc_phasepoint, ld));
+    P("sizeof_stats", sizeof(ahmc_stats)); P("stats.numerical_error", offsetof(ahmc_stats, numerical_error));
+    P("sizeof_rng", sizeof(ahmc_rng)); P("rng.exp_stride", offsetof(ahmc_rng, exp_stride));
+    P("rng.partial_refresh_alpha", offsetof(ahmc_rng, partial_refresh_alpha));
+    P("sizeof_adapt_cfg", sizeof(ahmc_adapt_cfg)); P("adapt_cfg.delta", offsetof(ahmc_adapt_cfg, delta));
+    P("adapt_cfg.adapt_metric", offsetof(ahmc_adapt_cfg, adapt_metric)); P("adapt_cfg.eps_chain", offsetof(ahmc_adapt_cfg, eps_chain));
+    P("adapt_cfg.eps_trace", offsetof(ahmc_adapt_cfg, eps_trace));
+    return 0;
+}
+''')
+    exe = tmp_path / "abi_probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    got = {k: int(v) for k, v in got.items()}
+    for name in ("FLAG_HOST_BUFFERS", "FLAG_COMPAT_BREAK_ALL", "FLAG_ASYNC", "FLAG_EXACT_CHECKS", "FLAG_NO_REFRESH",
+                 "FLAG_NUTS_SLICE_TS", "FLAG_NUTS_CLASSIC", "FLAG_NUTS_STRICT", "STATUS_NONFINITE"):
+        assert getattr(L, name) == got[name], name
+    for cname, cls in (("metric", L.Metric), ("phasepoint", L.PhasePoint), ("stats", L.Stats), ("rng", L.Rng),
+                       ("adapt_cfg", L.AdaptCfg)):
+        assert ctypes.sizeof(cls) == got["sizeof_" + cname], cname
+        for key, off in got.items():
+            if key.startswith(cname + "."):
+                assert getattr(cls, key.split(".")[1]).offset == off, key
