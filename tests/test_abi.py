@@ -129,3 +129,56 @@ int main(void) {
         for key, off in got.items():
             if key.startswith(cname + "."):
                 assert getattr(cls, key.split(".")[1]).offset == off, key
+
+
+def _split_top(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_shim_ccall_arity_matches_the_header():
+    """julia/AdvancedHMCB200Ext.jl cannot be executed here (no julia binary); at least every `ccall` in it must name an
+    exported entry point and pass exactly as many argument types -- and values -- as the C prototype has parameters."""
+    import re
+
+    hdr = open(os.path.join(ROOT, "include", "ahmc_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {m.group(1): len(_split_top(m.group(2))) for m in re.finditer(r"\b(ahmc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)}
+    jl = open(os.path.join(ROOT, "julia", "AdvancedHMCB200Ext.jl")).read()
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(ahmc_[a-z0-9_]+),\s*libahmc\),\s*(\w+),\s*\(", jl):
+        name = m.group(1)
+        assert name in protos, name
+        # the type tuple starts at m.end() - 1
+        i, depth = m.end() - 1, 0
+        j = i
+        while True:
+            depth += jl[j] == "("
+            depth -= jl[j] == ")"
+            if depth == 0:
+                break
+            j += 1
+        types = [t for t in _split_top(jl[i + 1:j]) if t]
+        # the values follow up to the ccall's closing parenthesis
+        k, depth = j + 1, 1
+        while depth:
+            depth += jl[k] == "("
+            depth -= jl[k] == ")"
+            k += 1
+        values = [v for v in _split_top(jl[j + 1:k - 1].lstrip(", \n")) if v]
+        assert len(types) == protos[name], (name, len(types), protos[name])
+        assert len(values) == protos[name], (name, len(values), protos[name])
+        seen += 1
+    assert seen >= 8
