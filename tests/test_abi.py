@@ -182,3 +182,17 @@ def test_julia_shim_ccall_arity_matches_the_header():
         assert len(values) == protos[name], (name, len(values), protos[name])
         seen += 1
     assert seen >= 8
+
+
+def test_julia_shim_struct_field_counts_match_the_c_structs():
+    import re
+
+    from ahmc_b200 import _lib as L
+
+    jl = open(os.path.join(ROOT, "julia", "AdvancedHMCB200Ext.jl")).read()
+    want = {"CMetric": L.Metric, "CPhasePoint": L.PhasePoint, "CStats": L.Stats, "CRng": L.Rng, "CAdaptCfg": L.AdaptCfg}
+    for name, cls in want.items():
+        m = re.search(r"struct " + name + r"\n(.*?)\nend", jl, flags=re.S)
+        assert m, name
+        fields = [f for line in m.group(1).splitlines() for f in line.split("#")[0].split(";") if "::" in f]
+        assert len(fields) == len(cls._fields_), (name, len(fields), len(cls._fields_))
