@@ -1,5 +1,7 @@
 """CPU tests: pin the oracle (C restatement + numpy twin) against the 50-digit known answers and the
 identities the reference's own tests assert.  No GPU, no reference at run time."""
+import math
+
 import numpy as np
 import pytest
 
@@ -501,3 +503,92 @@ def test_gaussian_leapfrog_map_is_linear():
     A1, A2, A3 = f(t1, r1), f(t2, r2), f(a * t1 + b * t2, a * r1 + b * r2)
     assert np.allclose(A3[0], a * A1[0] + b * A2[0], rtol=1e-12, atol=1e-12)
     assert np.allclose(A3[1], a * A1[1] + b * A2[1], rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ the kernel's iterative scheme
+def _np_system(kind, D, p0, p1, mkind, Minv, eps):
+    """numpy closures for oracle/nuts_iterative.py from fixture-style parameters."""
+    from oracle import nuts_iterative as ni
+
+    p0 = None if p0 is None else np.asarray(p0, dtype=np.float64)
+    p1 = None if p1 is None else np.asarray(p1, dtype=np.float64)
+    Minv = None if Minv is None else np.asarray(Minv, dtype=np.float64)
+
+    def logp_grad(th):
+        if kind == "std_normal":
+            return -0.5 * float(th @ th), th.copy()
+        if kind == "diag_gauss":
+            d = th - p0
+            return -0.5 * float(np.sum(d * d / (p1 * p1))), d / (p1 * p1)
+        if kind == "dense_gauss":
+            d = th - p0
+            Pd = p1 @ d
+            return -0.5 * float(d @ Pd), Pd
+        v, x = th[0], th[1:]
+        ev = math.exp(-v)
+        S = float(np.sum(x * x) * ev)
+        return -v * v / 18 - 0.5 * (S + (D - 1) * v), np.concatenate([[v / 9 - 0.5 * (S - (D - 1))], x * ev])
+
+    def dHdr(r):
+        if mkind == "unit":
+            return r
+        return Minv * r if mkind == "diag" else Minv @ r
+
+    return ni.System(logp_grad, dHdr, eps)
+
+
+@pytest.mark.parametrize("case", _NUTS_GOLD, ids=[c["name"] for c in _NUTS_GOLD])
+def test_iterative_nuts_scheme_matches_mp50_recursion(case):
+    """oracle/nuts_iterative.py -- the binary-counter / pending-level / float-up scheme the CUDA kernel runs, written out
+    in numpy -- reproduces the recursive 50-digit fixtures: the iterative algorithm is pinned on the CPU."""
+    from oracle import nuts_iterative as ni
+
+    S = _np_system(case["model"], case["D"], case["p0"], case["p1"], case["metric"], case["Minv"], case["eps"])
+    e = case["expect"]
+    for c in range(case["N"]):
+        z0 = S.point(np.array(case["theta0"][c]), np.array(case["r0"][c]))
+        zc, st, used = ni.transition(S, z0, case["dirs"][c], case["variates"][c], sampler=case["sampler"],
+                                     criterion=case["criterion"], max_depth=case["max_depth"], delta_max=case["delta_max"])
+        assert (st["tree_depth"], st["n_steps"], bool(st["numerical_error"]), used) == \
+               (e["tree_depth"][c], e["n_steps"][c], e["numerical_error"][c], e["variates_used"][c]), c
+        assert rel_err(zc["th"], e["theta"][c]) < 1e-10 and rel_err(zc["r"], e["r"][c]) < 1e-10
+        assert st["acceptance_rate"] == pytest.approx(e["acceptance_rate"][c], rel=1e-10)
+        assert st["max_hamiltonian_energy_error"] == pytest.approx(e["max_hamiltonian_energy_error"][c], rel=1e-9, abs=1e-10)
+
+
+@pytest.mark.parametrize("sampler,criterion", [("multinomial", "generalised"), ("slice", "generalised"),
+                                               ("multinomial", "classic"), ("multinomial", "strict"), ("slice", "strict")])
+@pytest.mark.parametrize("eps,delta_max", [(0.12, 6.0), (0.4, 0.3)], ids=["deep", "divergent"])
+def test_iterative_nuts_scheme_matches_recursive_c_oracle_on_deep_trees(sampler, criterion, eps, delta_max):
+    """Same check against the (recursive) C oracle on 120 random chains with trees up to depth 8, small step sizes and
+    a tight Delta_max so that max-depth exits, U-turns inside subtrees (float-up) and divergences all occur."""
+    from oracle import nuts_iterative as ni
+
+    rng = np.random.default_rng(31)
+    D, N, max_depth = 5, 120, 8
+    sd = np.exp(rng.uniform(-1.0, 1.0, D))
+    mu = rng.normal(size=D)
+    Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    model, metric = oc.Model(oc.DIAG_GAUSS, D, mu, sd, 0.0), oc.Metric(oc.DIAG, Minv)
+    S = _np_system("diag_gauss", D, mu, sd, "diag", Minv, eps)
+    th, r = rng.normal(size=(D, N)) * 2.0, rng.normal(size=(D, N))
+    dirs = rng.integers(0, 2, size=(N, max_depth + 1)).astype(np.uint8)
+    var = rng.exponential(size=(N, 1 << max_depth))
+    if sampler == "slice":
+        var[:, 1:] = rng.uniform(size=(N, (1 << max_depth) - 1))
+    z0 = oc.phasepoint(model, metric, th, r)
+    zo, so, used = oc.nuts_transition(model, metric, eps, z0, None, dirs, var, max_depth=max_depth, delta_max=delta_max,
+                                      sampler=sampler, criterion=criterion)
+    depths = set()
+    for c in range(N):
+        zc, st, nu = ni.transition(S, S.point(th[:, c].copy(), r[:, c].copy()), dirs[c], var[c], sampler=sampler,
+                                   criterion=criterion, max_depth=max_depth, delta_max=delta_max)
+        assert (st["tree_depth"], st["n_steps"], int(st["numerical_error"]), nu) == \
+               (so.tree_depth[c], so.n_steps[c], so.numerical_error[c], used[c]), c
+        assert rel_err(zc["th"], zo.theta[:, c]) < 1e-9
+        depths.add(st["tree_depth"])
+    if delta_max < 1.0:
+        assert so.numerical_error.sum() > 5       # numerical terminations inside and at the top of subtrees
+    else:
+        assert len(depths) >= 3                   # several tree sizes, partial subtrees (float-up) included
+        assert (((so.n_steps + 1) & so.n_steps) != 0).any()
