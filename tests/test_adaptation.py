@@ -107,7 +107,21 @@ def _worker(rank, world, port, q):
     theta, alpha = rng.normal(size=(5 + rank, 4)), rng.uniform(0, 1.2, 5 + rank)
     rec = torch.as_tensor(_record(theta, alpha))
     merged = ad.merge_records(ad.allgather_records(rec))
-    q.put((rank, merged))
+    # the dense and the position+gradient record layouts go through the same single all-gather
+    grad = -theta * 0.5
+    rec_cov = torch.as_tensor(_record_cov(theta, alpha))
+    rec_nut = torch.as_tensor(_record_nutpie(theta, grad, alpha))
+    merged_cov = ad.merge_records(ad.allgather_records(rec_cov), "cov")
+    merged_nut = ad.merge_records(ad.allgather_records(rec_nut), "nutpie")
+    # a short pooled Stan warm-up driven by exchanged records: every rank must end with the same eps and M^-1
+    adaptor = ad.StanHMCAdaptor(ad.WelfordVar(4), ad.NesterovDualAveraging(0.8, 0.1), init_buffer=3, term_buffer=2, window_size=4)
+    adaptor.initialize(20)
+    for it in range(20):
+        th_i = rng.normal(size=(6 + rank, 4)) * (1.0 + 0.1 * it)
+        al_i = rng.uniform(0.3, 1.1, 6 + rank)
+        adaptor.adapt(ad.merge_records(ad.allgather_records(torch.as_tensor(_record(th_i, al_i)))))
+    adaptor.finalize()
+    q.put((rank, merged, merged_cov, merged_nut, adaptor.eps, np.array(adaptor.Minv)))
     dist.destroy_process_group()
 
 
@@ -120,9 +134,15 @@ def test_adaptor_record_allgather_world_size_2_gloo():
     port = _free_port()
     ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in ps]
-    res = dict(q.get(timeout=120) for _ in range(2))
+    got = [q.get(timeout=120) for _ in range(2)]
     [p.join(timeout=60) for p in ps]
+    full = {g[0]: g[1:] for g in got}
+    res = {r: full[r][0] for r in full}
     assert np.array_equal(res[0], res[1])  # bit-identical on every rank
+    for k in (1, 2, 4):  # cov record, nutpie record, adapted M^-1: bit-identical across ranks too
+        assert np.array_equal(full[0][k], full[1][k])
+    assert full[0][3] == full[1][3] and 0.0 < full[0][3] < 10.0  # the pooled step size
+    assert not np.allclose(full[0][4], 1.0)  # the window did update the metric
     parts = [(np.random.default_rng(100 + r).normal(size=(5 + r, 4)), None) for r in range(2)]
     th = [np.random.default_rng(100 + r) for r in range(2)]
     recs = []
@@ -132,6 +152,9 @@ def test_adaptor_record_allgather_world_size_2_gloo():
         recs.append(_record(t, a))
     assert np.array_equal(res[0], ad.merge_records(recs))
     assert res[0][0] == 11
+    allx = np.concatenate([np.random.default_rng(100 + r).normal(size=(5 + r, 4)) for r in range(2)])
+    c = allx - allx.mean(axis=0)
+    assert np.allclose(full[0][1][2 + 8:].reshape(4, 4), c.T @ c, rtol=1e-12, atol=1e-12)
 
 
 def _welford_cov_reference(xs):
