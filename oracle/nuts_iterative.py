@@ -45,8 +45,13 @@ def maxabs(a, b):
     return a if abs(a) > abs(b) else b
 
 
-def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generalised", max_depth=10, delta_max=1000.0):
-    """-> (zcand, stats dict, number of variates used).  dirs: direction bits (1 = left), variates: the tape."""
+def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generalised", max_depth=10, delta_max=1000.0,
+               linear_accept=False):
+    """-> (zcand, stats dict, number of variates used).  dirs: direction bits (1 = left), variates: the tape.
+    linear_accept: take the multinomial decisions in the probability domain -- `u < w_p / (w_p + w_c)` with
+    u = exp(-randexp) -- instead of the reference's `lw < lw_p + randexp` (mathematically the same event; it would save
+    the kernel one log per combine because exp(-|lw_p - lw_c|) is already computed by logaddexp and the Philox stream
+    yields u directly).  tests/test_oracle.py checks that both forms decide identically on every test tree."""
     nvar = ndir = 0
 
     def draw():
@@ -111,7 +116,13 @@ def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generali
                         lw_c = n
                     else:  # :191-195
                         lw = logaddexp(F["lw"], lw_c)
-                        cand = F["cand"] if lw < F["lw"] + u else node["cand"]
+                        if linear_accept:
+                            t = math.exp(-abs(F["lw"] - lw_c))
+                            p_first = 1.0 / (1.0 + t) if F["lw"] >= lw_c else t / (1.0 + t)
+                            take = math.exp(-u) < p_first
+                        else:
+                            take = lw < F["lw"] + u
+                        cand = F["cand"] if take else node["cand"]
                         lw_c = lw
                     sa_c = F["sa"] + sa_c if v > 0 else sa_c + F["sa"]
                     na_c += F["na"]
@@ -132,7 +143,12 @@ def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generali
         if not sub_term:
             j += 1
             u = draw()
-            accept = (lw_tree * u < lw_c) if sampler == "slice" else (lw_tree < lw_c + u)
+            if sampler == "slice":
+                accept = lw_tree * u < lw_c
+            elif linear_accept:
+                accept = math.exp(-u) < math.exp(min(0.0, lw_c - lw_tree))
+            else:
+                accept = lw_tree < lw_c + u
             if accept:
                 zc = node["cand"]
         near, far = (LEFT, RIGHT) if v < 0 else (RIGHT, LEFT)

@@ -587,6 +587,11 @@ def test_iterative_nuts_scheme_matches_recursive_c_oracle_on_deep_trees(sampler,
                (so.tree_depth[c], so.n_steps[c], so.numerical_error[c], used[c]), c
         assert rel_err(zc["th"], zo.theta[:, c]) < 1e-9
         depths.add(st["tree_depth"])
+        if sampler == "multinomial":  # the probability-domain form of the same decisions (planned kernel optimisation)
+            zl, sl, nl = ni.transition(S, S.point(th[:, c].copy(), r[:, c].copy()), dirs[c], var[c], sampler=sampler,
+                                       criterion=criterion, max_depth=max_depth, delta_max=delta_max, linear_accept=True)
+            assert (sl["tree_depth"], sl["n_steps"], nl) == (st["tree_depth"], st["n_steps"], nu)
+            assert np.array_equal(zl["th"], zc["th"])
     if delta_max < 1.0:
         assert so.numerical_error.sum() > 5       # numerical terminations inside and at the top of subtrees
     else:
