@@ -1,6 +1,6 @@
 """Per-source-line dynamic instruction profile of the NUTS kernel from an `ncu --page source --csv` export (SASS view with
 executed counts) joined with `nvdisasm -c -gi` line / inline info of the SAME build.
-Usage: python scripts/k3_line_profile.py <source.csv> <nvdisasm -gi listing of the kernel> <kernel .cu> <device .cuh> <leaves> [inner]
+Usage: python scripts/ncu_line_profile.py <source.csv> <nvdisasm -gi listing of the kernel> <kernel .cu> <device .cuh> <leaves> [inner]
 ("inner": attribute to the INNERMOST frame inside the kernel's own file instead of the outermost -- for kernels whose
  body is one big inlined call, e.g. K4's tile product)
 (The r01 capture predates the template split: rebuild that commit's ahmc_nuts.cu to a cubin first; see profiles/README.md.)"""
@@ -13,9 +13,10 @@ csv.field_size_limit(10 ** 9)
 path_csv, path_sass, path_cu, path_dev, leaves = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4], float(sys.argv[5])
 inner_mode = len(sys.argv) > 6 and sys.argv[6] == "inner"
 rows = list(csv.reader(open(path_csv)))
-s = [i for i, r in enumerate(rows) if len(r) > 5 and r[0] == "Address" and "Source" in r][0]
+starts = [i for i, r in enumerate(rows) if len(r) > 5 and r[0] == "Address" and "Source" in r]
+s = starts[0]  # first table = first captured launch
 hdr = rows[s]
-body = [r for r in rows[s + 1:] if len(r) == len(hdr)]
+body = [r for r in rows[s + 1:(starts[1] if len(starts) > 1 else len(rows))] if len(r) == len(hdr)]
 ix = {n: i for i, n in enumerate(hdr)}
 ex = [float(r[ix["Instructions Executed"]] or 0) for r in body]
 samp = [float(r[ix["# Samples"]] or 0) for r in body]
