@@ -48,6 +48,20 @@ __device__ __forceinline__ double maxabs(double a, double b) { return fabs(a) > 
 
 constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, cand lk
 
+// AHMC_NUTS_FASTDRAW (default 0 = the build every test and measurement of round 1 ran): staged instruction-count cuts
+// the K3 line profile asks for (profiles/r01/k3_source_line_profile.txt: random draws 24 %, logaddexp 16 % of the
+// instructions).  With 1:
+//   * one Philox block serves two consecutive variates / 128 direction bits (cached in registers) instead of being
+//     regenerated for each;
+//   * the multinomial combine decides in the probability domain, u < w_p / (w_p + w_c) with exp(-|dlw|) shared with the
+//     log-sum-exp, instead of lw < lw_p - log(u): no log per combine (same event; oracle/nuts_iterative.py checks that
+//     the two forms decide identically on every test tree); SliceTS takes u directly instead of exp(-(-log u)).
+// Compiled and register-checked only; NOT yet run on a GPU -- build with -DAHMC_NUTS_FASTDRAW=1 (scripts/build_variants.sh)
+// and run the tape-parity tests before making it the default.
+#ifndef AHMC_NUTS_FASTDRAW
+#define AHMC_NUTS_FASTDRAW 0
+#endif
+
 // Occupancy knob: the tree walk is a long chain of dependent, mostly fixed-latency instructions, so throughput
 // scales with resident warps per scheduler; cap registers so that this many 4-warp blocks fit per SM.
 #ifndef AHMC_NUTS_MINB
@@ -106,6 +120,41 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
 
     int nexp = 0, ndir = 0;
     uint64_t off = a.rng.offset;  // Philox transition counter of the transition this group is working on
+#if AHMC_NUTS_FASTDRAW
+    uint32_t cexp[4] = {0u, 0u, 0u, 0u}, cdir[4] = {0u, 0u, 0u, 0u};
+    int cexp_blk = -1, cdir_blk = -1;  // cached Philox blocks (reset with the per-transition counters)
+    auto philox_u = [&](int k) -> double {  // k-th uniform of (chain, transition): two per block
+        if ((k >> 1) != cexp_blk) {
+            cexp_blk = k >> 1;
+            Philox::gen(a.rng.seed, (uint64_t)chain, (off << 24) ^ (STREAM_EXP << 60) ^ (uint64_t)cexp_blk, cexp);
+        }
+        return (k & 1) ? Philox::u01(cexp[2], cexp[3]) : Philox::u01(cexp[0], cexp[1]);
+    };
+    auto next_exp = [&]() -> double {
+        int k = nexp++;
+        if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
+        return -log(philox_u(k));
+    };
+    auto next_unif = [&]() -> double {  // SliceTS: rand(rng)
+        int k = nexp++;
+        if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
+        return philox_u(k);
+    };
+    auto next_u_of_exp = [&]() -> double {  // u = exp(-randexp): the uniform behind the k-th exponential
+        int k = nexp++;
+        if (a.rng.exp_tape && k < a.rng.exp_stride) return exp(-a.rng.exp_tape[chain * a.rng.exp_stride + k]);
+        return philox_u(k);
+    };
+    auto next_dir = [&]() -> bool {
+        int k = ndir++;
+        if (a.rng.dir_tape && k < a.rng.dir_stride) return a.rng.dir_tape[chain * a.rng.dir_stride + k] != 0;
+        if ((k >> 7) != cdir_blk) {
+            cdir_blk = k >> 7;
+            Philox::gen(a.rng.seed, (uint64_t)chain, (off << 24) ^ (STREAM_DIR << 60) ^ (uint64_t)cdir_blk, cdir);
+        }
+        return (cdir[(k >> 5) & 3] >> (k & 31)) & 1u;
+    };
+#else
     auto next_exp = [&]() -> double {
         int k = nexp++;
         if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
@@ -121,6 +170,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         if (a.rng.dir_tape && k < a.rng.dir_stride) return a.rng.dir_tape[chain * a.rng.dir_stride + k] != 0;
         return philox_bit(a.rng.seed, off, chain, k);
     };
+#endif
 
     // ---- per-transition state (a launch runs n_transitions transitions per chain: the reference's
     //      `for i in 1:n_samples` loop, sampler.jl:182, each chain advancing at its own pace)
@@ -147,6 +197,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 off = a.rng.offset + (uint64_t)t;
                 nexp = 0;
                 ndir = 0;
+#if AHMC_NUTS_FASTDRAW
+                cexp_blk = cdir_blk = -1;
+#endif
                 vload_nc<G, E>(s.th, first ? a.th_in + a.ld_in * chain : a.th_out + a.ld_out * chain, l, D);
                 vload_nc<G, E>(s.g, first ? a.g_in + a.ld_in * chain : a.g_out + a.ld_out * chain, l, D);
             }
@@ -453,6 +506,21 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 }
                 if (do_comb) {
                     const double lw_p = LW[k], sa_p = SA[k], na_p = NA[k], dh_p = DH[k];
+#if AHMC_NUTS_FASTDRAW
+                    if (VAR && samp == 1) {  // combine(rng, s1::SliceTS, s2) (:178-183)
+                        const double n = lw_p + lw_c;
+                        if (n * next_unif() < lw_p) cand_cur = k;
+                        lw_c = n;
+                    } else {  // combine(rng, s1, s2) (:191-195) decided in the probability domain (see the macro's comment)
+                        const double u = next_u_of_exp();
+                        const double dlw = lw_p - lw_c;
+                        const double tt = exp(-((lw_p == lw_c) ? 0.0 : fabs(dlw)));
+                        const double mx = (lw_p != lw_p || lw_c != lw_c) ? CUDART_NAN : (lw_p > lw_c ? lw_p : lw_c);
+                        const double p_first = (dlw >= 0.0) ? 1.0 / (1.0 + tt) : tt / (1.0 + tt);
+                        if ((dlw == dlw) && (u < p_first)) cand_cur = k;  // lw < lw_p + randexp  <=>  u < w_p / (w_p + w_c)
+                        lw_c = mx + log1p(tt);                            // == logaddexp(lw_p, lw_c)
+                    }
+#else
                     const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
                     if (VAR && samp == 1) {  // combine(rng, s1::SliceTS, s2) (:178-183): n = n1 + n2; n*rand < n1 ? s1 : s2
                         const double n = lw_p + lw_c;
@@ -463,6 +531,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                         if (lw < lw_p + ex) cand_cur = k;         // keep the first-built half's candidate
                         lw_c = lw;
                     }
+#endif
                     sa_c = (v > 0) ? sa_p + sa_c : sa_c + sa_p;  // treeleft + treeright (:538)
                     na_c += na_p;
                     dh_c = (v > 0) ? maxabs(dh_p, dh_c) : maxabs(dh_c, dh_p);

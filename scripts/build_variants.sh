@@ -1,14 +1,25 @@
 #!/bin/bash
-# A/B builds of the NUTS kernel occupancy knob: advancedhmc.jl_b200/_variants/libahmc_b200_minb{N}.so
+# A/B builds of the NUTS kernel: advancedhmc.jl_b200/_variants/libahmc_b200_<tag>.so, selected at run time with
+# AHMC_B200_LIB=<path>.  Usage: scripts/build_variants.sh minb4 fastdraw ...   (tags: minbN -> -DAHMC_NUTS_MINB=N,
+# fastdraw -> -DAHMC_NUTS_FASTDRAW=1).  The three NUTS translation units are recompiled, the rest is reused.
 set -e
 cd "$(dirname "$0")/.."
 python advancedhmc.jl_b200/build.py
 P=advancedhmc.jl_b200
+O=${AHMC_OBJ_DIR:-/tmp/ahmc_b200_obj}
 mkdir -p $P/_variants
-for m in "$@"; do
-  ( nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -DAHMC_NUTS_MINB=$m \
-      -c $P/csrc/ahmc_nuts.cu -o $P/_obj/ahmc_nuts_minb$m.o && \
-    nvcc -shared -o $P/_variants/libahmc_b200_minb$m.so $P/_obj/ahmc_api.o $P/_obj/ahmc_leapfrog.o $P/_obj/ahmc_adapt.o $P/_obj/ahmc_nuts_minb$m.o \
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -O3"
+for tag in "$@"; do
+  case $tag in
+    minb*) DEF="-DAHMC_NUTS_MINB=${tag#minb}" ;;
+    fastdraw) DEF="-DAHMC_NUTS_FASTDRAW=1" ;;
+    *) echo "unknown tag $tag"; exit 1 ;;
+  esac
+  ( for tu in ahmc_nuts ahmc_nuts_var ahmc_nuts_adapt; do
+      nvcc $FLAGS $DEF -c $P/csrc/$tu.cu -o $O/${tu}_$tag.o &
+    done; wait
+    nvcc -shared -o $P/_variants/libahmc_b200_$tag.so $O/ahmc_api.o $O/ahmc_leapfrog.o $O/ahmc_adapt.o $O/ahmc_multinomial.o \
+      $O/ahmc_dense.o $O/ahmc_nuts_$tag.o $O/ahmc_nuts_var_$tag.o $O/ahmc_nuts_adapt_$tag.o \
       -gencode arch=compute_100a,code=sm_100a -cudart shared ) &
 done
 wait
