@@ -597,3 +597,59 @@ def test_iterative_nuts_scheme_matches_recursive_c_oracle_on_deep_trees(sampler,
     else:
         assert len(depths) >= 3                   # several tree sizes, partial subtrees (float-up) included
         assert (((so.n_steps + 1) & so.n_steps) != 0).any()
+
+
+def test_iterative_scheme_vs_recursive_oracle_randomised_configurations():
+    """Differential test over random configurations (dimension, target, metric incl. dense, step size, depth limit,
+    divergence threshold, sampler, criterion): the iterative numpy scheme and the recursive C oracle must build the same
+    tree and select the same point for every chain."""
+    from oracle import nuts_iterative as ni
+
+    rng = np.random.default_rng(77)
+    n_cfg, checked = 60, 0
+    for cfg in range(n_cfg):
+        D = int(rng.integers(1, 9))
+        kind = ["std_normal", "diag_gauss", "dense_gauss", "funnel"][int(rng.integers(0, 4))]
+        if kind == "funnel" and D < 2:
+            D = 2
+        mkind = ["unit", "diag", "dense"][int(rng.integers(0, 3))]
+        eps = float(np.exp(rng.uniform(np.log(0.05), np.log(0.8))))
+        max_depth = int(rng.integers(1, 8))
+        delta_max = [1000.0, 2.0][int(rng.integers(0, 2))]
+        sampler = ["multinomial", "slice"][int(rng.integers(0, 2))]
+        criterion = ["generalised", "classic", "strict"][int(rng.integers(0, 3))]
+        p0 = p1 = Minv = None
+        if kind == "diag_gauss":
+            p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.7, 0.7, D))
+        elif kind == "dense_gauss":
+            B = rng.normal(size=(D, D))
+            p0, p1 = rng.normal(size=D), B @ B.T / D + np.eye(D)
+        if mkind == "diag":
+            Minv = np.exp(rng.uniform(-0.7, 0.7, D))
+        elif mkind == "dense":
+            B = rng.normal(size=(D, D))
+            Minv = B @ B.T / D + 0.5 * np.eye(D)
+        kinds = dict(std_normal=oc.STD_NORMAL, diag_gauss=oc.DIAG_GAUSS, dense_gauss=oc.DENSE_GAUSS, funnel=oc.FUNNEL)
+        mkinds = dict(unit=oc.UNIT, diag=oc.DIAG, dense=oc.DENSE)
+        model = oc.Model(kinds[kind], D, p0, None if p1 is None else np.asfortranarray(p1), 0.0)
+        metric = oc.Metric(mkinds[mkind], None if Minv is None else np.asfortranarray(Minv))
+        S = _np_system(kind, D, p0, p1, mkind, Minv, eps)
+        N = 12
+        th, r = rng.normal(size=(D, N)) * (0.6 if kind == "funnel" else 1.5), rng.normal(size=(D, N))
+        dirs = rng.integers(0, 2, size=(N, max_depth + 1)).astype(np.uint8)
+        var = rng.exponential(size=(N, 1 << max_depth))
+        if sampler == "slice":
+            var[:, 1:] = rng.uniform(size=(N, (1 << max_depth) - 1))
+        zo, so, used = oc.nuts_transition(model, metric, eps, oc.phasepoint(model, metric, th, r), None, dirs, var,
+                                          max_depth=max_depth, delta_max=delta_max, sampler=sampler, criterion=criterion)
+        for c in range(N):
+            zc, st, nu = ni.transition(S, S.point(th[:, c].copy(), r[:, c].copy()), dirs[c], var[c], sampler=sampler,
+                                       criterion=criterion, max_depth=max_depth, delta_max=delta_max)
+            key = (cfg, c, kind, mkind, sampler, criterion)
+            if not np.all(np.isfinite(zo.theta[:, c])):
+                continue  # a non-finite trajectory: covered by the -Inf mapping tests, not a tree-logic question
+            assert (st["tree_depth"], st["n_steps"], int(st["numerical_error"]), nu) == \
+                   (so.tree_depth[c], so.n_steps[c], so.numerical_error[c], used[c]), key
+            assert rel_err(zc["th"], zo.theta[:, c]) < 1e-8, key
+            checked += 1
+    assert checked > 0.9 * n_cfg * 12
