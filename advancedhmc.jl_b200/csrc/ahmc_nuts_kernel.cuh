@@ -722,6 +722,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
 
 }
 
+#ifndef AHMC_SIMT_EMULATION  // host launch code (not compiled by the CPU SIMT emulation harness, tests/simt_emu/)
 template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
 static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;
@@ -782,5 +783,7 @@ static cudaError_t nuts_dispatch(const NutsArgs& a, cudaStream_t st) {
         return cudaErrorInvalidValue;
     }
 }
+
+#endif  // AHMC_SIMT_EMULATION
 
 }  // namespace ahmc

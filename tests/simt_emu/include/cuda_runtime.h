@@ -1,0 +1,69 @@
+// Fake <cuda_runtime.h> for the CPU SIMT emulation harness (tests/simt_emu/): just enough host-side declarations for the
+// product's kernel headers to compile with g++.  TEST INFRASTRUCTURE ONLY.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __shared__
+#define __launch_bounds__(...)
+
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+constexpr cudaError_t cudaSuccess = 0, cudaErrorInvalidValue = 1;
+
+struct EmuUint3 {
+    unsigned x, y, z;
+};
+extern thread_local EmuUint3 threadIdx, blockIdx;
+extern EmuUint3 blockDim, gridDim;
+
+// ---- warp-synchronous primitives: 32 host threads per warp in lock-step (tests/simt_emu/simt_emu.cpp)
+unsigned emu_ballot(bool pred);
+uint64_t emu_shfl(uint64_t bits, int src_lane);
+void emu_syncwarp();
+inline unsigned __ballot_sync(unsigned, bool pred) { return emu_ballot(pred); }
+inline bool __any_sync(unsigned, bool pred) { return emu_ballot(pred) != 0u; }
+inline bool __all_sync(unsigned, bool pred) { return emu_ballot(pred) == 0xffffffffu; }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu_syncwarp(); }
+int emu_lane();
+template <class T>
+inline T emu_shfl_t(T v, int src) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    uint64_t b = 0;
+    std::memcpy(&b, &v, sizeof(T));
+    b = emu_shfl(b, src);
+    T out;
+    std::memcpy(&out, &b, sizeof(T));
+    return out;
+}
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int lanemask, int = 32) { return emu_shfl_t(v, emu_lane() ^ lanemask); }
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+    const int lane = emu_lane();
+    return emu_shfl_t(v, (lane & ~(width - 1)) | (src & (width - 1)));
+}
+
+// ---- scalar intrinsics
+template <class T>
+inline T __ldg(const T* p) { return *p; }
+inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32); }
+inline int __double2hiint(double x) {
+    uint64_t b;
+    std::memcpy(&b, &x, 8);
+    return (int)(b >> 32);
+}
+int atomicMin(int* addr, int v);
+using std::fabs;
+using std::fma;
+using std::fmax;
+using std::fmin;
+inline void sincospi(double x, double* s, double* c) {  // CUDA math API; only the Philox (non-tape) momentum draw uses it
+    *s = std::sin(M_PI * x);
+    *c = std::cos(M_PI * x);
+}

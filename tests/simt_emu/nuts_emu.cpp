@@ -1,0 +1,146 @@
+// nuts_emu.cpp -- runs the product's NUTS kernel source (ahmc_nuts_kernel.cuh) under the CPU SIMT emulator.
+// TEST INFRASTRUCTURE ONLY: built by tests/test_simt_emulation.py with g++; the kernel header is included unmodified
+// (its host launch code is skipped with AHMC_SIMT_EMULATION); optional -DAHMC_NUTS_FASTDRAW=1 builds the staged variant.
+#define AHMC_SIMT_EMULATION 1
+#include <cstdlib>
+#include <vector>
+
+#include "ahmc_nuts_kernel.cuh"
+
+namespace ahmc {
+double smem[1 << 16];  // the block's dynamic shared memory (`extern __shared__ double smem[]` in the kernel)
+}
+void emu_launch(void (*kernel)(const void*), const void* args, int blocks, int threads);
+
+using namespace ahmc;
+
+struct EmuNuts {
+    int32_t model_kind, metric_kind, D;
+    int64_t N;
+    const double *p0, *p1;
+    double c0;
+    const double* Minv;
+    int64_t minv_stride;
+    const double* cholU;
+    double eps;
+    const double* eps_chain;
+    int32_t max_depth;
+    double delta_max;
+    int32_t sampler, criterion;
+    uint64_t seed, offset;
+    const double *normal_tape, *exp_tape;
+    int64_t exp_stride;
+    const uint8_t* dir_tape;
+    int64_t dir_stride;
+    double partial_alpha;
+    int32_t refresh;
+    const double *th_in, *r_in, *g_in, *lp_in;
+    double *th_out, *r_out, *g_out, *lp_out, *lk_out;
+    int32_t *n_steps, *tree_depth;
+    uint8_t* numerical;
+    double *acc, *dH, *dHmax;
+    int32_t n_transitions;
+    double* draws;
+    int32_t adapt, n_adapts, init_buffer, term_buffer, window_size;
+    double delta, gamma, t0, kappa;
+    int32_t adapt_metric, n_min;
+    double *eps_rw, *minv_rw, *eps_trace;
+};
+
+template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
+static void thunk(const void* p) { nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT>(*static_cast<const NutsArgs*>(p)); }
+
+typedef void (*KernelFn)(const void*);
+
+template <int MODEL, int METRIC, bool VAR, bool ADAPT>
+static KernelFn by_layout(int G, int E) {
+    if (G == 4 && E == 1) return thunk<MODEL, METRIC, 4, 1, VAR, ADAPT>;
+    if (G == 8 && E == 1) return thunk<MODEL, METRIC, 8, 1, VAR, ADAPT>;
+    if (G == 32 && E == 2) return thunk<MODEL, METRIC, 32, 2, VAR, ADAPT>;
+    return nullptr;
+}
+
+template <bool VAR, bool ADAPT>
+static KernelFn by_model(int model, int metric, int G, int E) {
+    if (model == AHMC_MODEL_STD_NORMAL && metric == AHMC_METRIC_UNIT) return by_layout<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_UNIT, VAR, ADAPT>(G, E);
+    if (model == AHMC_MODEL_DIAG_GAUSS && metric == AHMC_METRIC_DIAG) return by_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DIAG, VAR, ADAPT>(G, E);
+    if (model == AHMC_MODEL_FUNNEL && metric == AHMC_METRIC_DIAG) return by_layout<AHMC_MODEL_FUNNEL, AHMC_METRIC_DIAG, VAR, ADAPT>(G, E);
+    if (!ADAPT) {
+        if (model == AHMC_MODEL_DENSE_GAUSS && metric == AHMC_METRIC_DENSE) return by_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DENSE, VAR, false>(G, E);
+        if (model == AHMC_MODEL_DIAG_GAUSS && metric == AHMC_METRIC_UNIT) return by_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_UNIT, VAR, false>(G, E);
+    }
+    return nullptr;
+}
+
+extern "C" int emu_fastdraw() { return AHMC_NUTS_FASTDRAW; }
+
+extern "C" int emu_nuts(const EmuNuts* q) {
+    int G, E;
+    const int D = q->D;
+    if (D <= 4) G = 4, E = 1;
+    else if (D <= 8) G = 8, E = 1;
+    else if (D > 32 && D <= 64) G = 32, E = 2;
+    else return -1;
+    NutsArgs a{};
+    a.model = ModelDev{q->model_kind, D, q->p0, q->p1, q->c0};
+    a.metric = MetricDev{q->metric_kind, q->Minv, q->minv_stride, q->cholU};
+    a.D = D;
+    a.N = q->N;
+    a.eps = q->eps;
+    a.eps_chain = q->eps_chain;
+    a.max_depth = q->max_depth;
+    a.delta_max = q->delta_max;
+    a.sampler = q->sampler;
+    a.criterion = q->criterion;
+    a.rng = RngDev{q->seed, q->offset, q->normal_tape, q->exp_tape, q->exp_stride, q->dir_tape, q->dir_stride, q->partial_alpha};
+    a.refresh = q->refresh;
+    a.th_in = q->th_in; a.r_in = q->r_in; a.g_in = q->g_in; a.lp_in = q->lp_in;
+    a.ld_in = D;
+    a.th_out = q->th_out; a.r_out = q->r_out; a.g_out = q->g_out; a.lp_out = q->lp_out; a.lk_out = q->lk_out;
+    a.ld_out = D;
+    a.st = StatsDev{};
+    a.st.n_steps = q->n_steps;
+    a.st.tree_depth = q->tree_depth;
+    a.st.numerical_error = q->numerical;
+    a.st.acceptance_rate = q->acc;
+    a.st.hamiltonian_energy_error = q->dH;
+    a.st.max_hamiltonian_energy_error = q->dHmax;
+    a.n_transitions = q->n_transitions;
+    a.draws = q->draws;
+    if (q->adapt) {
+        AdaptDev& ad = a.ad;
+        ad.enabled = 1;
+        ad.n_adapts = q->n_adapts;
+        ad.delta = q->delta; ad.gamma = q->gamma; ad.t0 = q->t0; ad.kappa = q->kappa;
+        ad.adapt_metric = q->adapt_metric;
+        ad.n_min = q->n_min;
+        ad.window_start = q->init_buffer + 1;  // same schedule code as nuts_impl (ahmc_api.cu)
+        ad.window_end = q->n_adapts - q->term_buffer;
+        ad.n_splits = 0;
+        long long wsz = q->window_size, next = (long long)q->init_buffer + wsz;
+        while (next <= ad.window_end && ad.n_splits < 12) {
+            if (next + 2 * wsz > ad.window_end) next = ad.window_end;
+            ad.splits[ad.n_splits++] = (int)next;
+            wsz *= 2;
+            next += wsz;
+        }
+        if (ad.n_splits > 0 && ad.splits[ad.n_splits - 1] == q->n_adapts) --ad.n_splits;
+        ad.eps = q->eps_rw;
+        a.eps_chain = q->eps_rw;
+        ad.minv = q->minv_rw;
+        ad.eps_trace = q->eps_trace;
+    }
+    const long long stride = nuts_level_doubles(D, q->max_depth) + (q->adapt ? 2LL * D : 0);
+    std::vector<double> scratch((size_t)stride * (size_t)q->N, 0.0);
+    a.scratch = scratch.data();
+    a.scratch_stride = stride;
+    const bool var = q->sampler != 0 || q->criterion != 0;
+    KernelFn fn = q->adapt ? by_model<false, true>(q->model_kind, q->metric_kind, G, E)
+                           : (var ? by_model<true, false>(q->model_kind, q->metric_kind, G, E)
+                                  : by_model<false, false>(q->model_kind, q->metric_kind, G, E));
+    if (!fn) return -2;
+    const int chains_per_block = kBlockThreads / G;
+    const int blocks = (int)((q->N + chains_per_block - 1) / chains_per_block);
+    emu_launch(fn, &a, blocks, kBlockThreads);
+    return 0;
+}

@@ -1,0 +1,223 @@
+"""The product's NUTS kernel SOURCE (advancedhmc.jl_b200/csrc/ahmc_nuts_kernel.cuh + ahmc_device.cuh, unmodified) executed
+on the CPU by a small SIMT emulator (tests/simt_emu/: one host thread per CUDA thread, the 32 threads of a warp meet at
+a barrier in every shuffle / vote) and compared with the recursive C oracle on shared random tapes.  This checks the
+kernel's actual code -- control flow, workspace addressing, warp-uniform predicates, every template family -- without a
+GPU; the GPU parity tests (-m gpu) remain the authority for the compiled binary."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_c as oc
+from tests.helpers import rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_vp = C.c_void_p
+
+
+class EmuNuts(C.Structure):
+    _fields_ = [("model_kind", C.c_int32), ("metric_kind", C.c_int32), ("D", C.c_int32), ("N", C.c_int64), ("p0", _vp), ("p1", _vp),
+                ("c0", C.c_double), ("Minv", _vp), ("minv_stride", C.c_int64), ("cholU", _vp), ("eps", C.c_double),
+                ("eps_chain", _vp), ("max_depth", C.c_int32), ("delta_max", C.c_double), ("sampler", C.c_int32),
+                ("criterion", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64), ("normal_tape", _vp), ("exp_tape", _vp),
+                ("exp_stride", C.c_int64), ("dir_tape", _vp), ("dir_stride", C.c_int64), ("partial_alpha", C.c_double),
+                ("refresh", C.c_int32), ("th_in", _vp), ("r_in", _vp), ("g_in", _vp), ("lp_in", _vp), ("th_out", _vp),
+                ("r_out", _vp), ("g_out", _vp), ("lp_out", _vp), ("lk_out", _vp), ("n_steps", _vp), ("tree_depth", _vp),
+                ("numerical", _vp), ("acc", _vp), ("dH", _vp), ("dHmax", _vp), ("n_transitions", C.c_int32), ("draws", _vp),
+                ("adapt", C.c_int32), ("n_adapts", C.c_int32), ("init_buffer", C.c_int32), ("term_buffer", C.c_int32),
+                ("window_size", C.c_int32), ("delta", C.c_double), ("gamma", C.c_double), ("t0", C.c_double), ("kappa", C.c_double),
+                ("adapt_metric", C.c_int32), ("n_min", C.c_int32), ("eps_rw", _vp), ("minv_rw", _vp), ("eps_trace", _vp)]
+
+
+def _build(tmp, fastdraw):
+    out = tmp / ("libnuts_emu_fast.so" if fastdraw else "libnuts_emu.so")
+    d = os.path.join(ROOT, "tests", "simt_emu")
+    cmd = ["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-I", os.path.join(d, "include"),
+           "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(d, "simt_emu.cpp"), os.path.join(d, "nuts_emu.cpp"), "-o", str(out)]
+    if fastdraw:
+        cmd.insert(1, "-DAHMC_NUTS_FASTDRAW=1")
+    subprocess.run(cmd, check=True)
+    lib = C.CDLL(str(out))
+    assert lib.emu_fastdraw() == (1 if fastdraw else 0)
+    return lib
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    return _build(tmp_path_factory.mktemp("simt"), False)
+
+
+@pytest.fixture(scope="module")
+def emu_fast(tmp_path_factory):
+    return _build(tmp_path_factory.mktemp("simt_fast"), True)
+
+
+P = lambda a: None if a is None else a.ctypes.data_as(_vp)
+KINDS = dict(std_normal=oc.STD_NORMAL, diag_gauss=oc.DIAG_GAUSS, dense_gauss=oc.DENSE_GAUSS, funnel=oc.FUNNEL)
+MKINDS = dict(unit=oc.UNIT, diag=oc.DIAG, dense=oc.DENSE)
+
+
+def _case(lib, kind, mkind, D, N, eps, sampler, criterion, seed, max_depth=6, delta_max=1000.0, scale=1.0):
+    rng = np.random.default_rng(seed)
+    p0 = p1 = Minv = cholU = None
+    if kind == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.5, 0.5, D))
+    elif kind == "dense_gauss":
+        B = rng.normal(size=(D, D))
+        p0, p1 = rng.normal(size=D), B @ B.T / D + np.eye(D)
+    if mkind == "diag":
+        Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    elif mkind == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+        cholU = np.ascontiguousarray(np.linalg.cholesky(Minv).T.T)  # U column-major == U' row-major
+    th, r = rng.normal(size=(N, D)) * scale, rng.normal(size=(N, D))
+    dirs = rng.integers(0, 2, size=(N, max_depth + 1)).astype(np.uint8)
+    var = rng.exponential(size=(N, 1 << max_depth))
+    if sampler == "slice":
+        var[:, 1:] = rng.uniform(size=(N, (1 << max_depth) - 1))
+    model = oc.Model(KINDS[kind], D, p0, None if kind != "dense_gauss" else np.asfortranarray(p1), 0.0) if kind != "diag_gauss" \
+        else oc.Model(oc.DIAG_GAUSS, D, p0, p1, 0.0)
+    metric = oc.Metric(MKINDS[mkind], None if Minv is None else np.asfortranarray(Minv))
+    z0 = oc.phasepoint(model, metric, th.T, r.T)
+    zo, so, used = oc.nuts_transition(model, metric, eps, z0, None, dirs, var, max_depth=max_depth, delta_max=delta_max,
+                                      sampler=sampler, criterion=criterion)
+    # what the device-side model holds: DIAG_GAUSS p1 = 1/s^2; DENSE_GAUSS p1 = precision (column-major == symmetric)
+    dp1 = None if p1 is None else (1.0 / (p1 * p1) if kind == "diag_gauss" else np.ascontiguousarray(p1))
+    g_in = np.ascontiguousarray(z0.lp_gradient.T)
+    lp_in = np.ascontiguousarray(z0.lp_value)
+    out = {k: np.zeros((N, D)) for k in ("th", "r", "g")}
+    lp_o, lk_o, acc, dH, dHm = (np.zeros(N) for _ in range(5))
+    ns, td = np.zeros(N, dtype=np.int32), np.zeros(N, dtype=np.int32)
+    ne = np.zeros(N, dtype=np.uint8)
+    q = EmuNuts(model_kind=KINDS[kind], metric_kind=MKINDS[mkind], D=D, N=N, p0=P(p0), p1=P(dp1), c0=0.0,
+                Minv=P(Minv), minv_stride=0, cholU=P(cholU), eps=eps, eps_chain=None, max_depth=max_depth, delta_max=delta_max,
+                sampler=oc.SAMPLER[sampler], criterion=oc.CRITERION[criterion], seed=1, offset=0, normal_tape=None,
+                exp_tape=P(var), exp_stride=var.shape[1], dir_tape=P(dirs), dir_stride=dirs.shape[1], partial_alpha=0.0,
+                refresh=0, th_in=P(th), r_in=P(r), g_in=P(g_in), lp_in=P(lp_in), th_out=P(out["th"]), r_out=P(out["r"]),
+                g_out=P(out["g"]), lp_out=P(lp_o), lk_out=P(lk_o), n_steps=P(ns), tree_depth=P(td), numerical=P(ne), acc=P(acc),
+                dH=P(dH), dHmax=P(dHm), n_transitions=1, draws=None, adapt=0)
+    assert lib.emu_nuts(C.byref(q)) == 0
+    assert (td == so.tree_depth).all() and (ns == so.n_steps).all() and (ne == so.numerical_error).all()
+    assert rel_err(out["th"].T, zo.theta) < 1e-10 and rel_err(out["r"].T, zo.r) < 1e-10
+    assert rel_err(out["g"].T, zo.lp_gradient) < 1e-10
+    assert np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10) and np.allclose(lk_o, zo.lk_value, rtol=1e-10, atol=1e-10)
+    assert np.allclose(acc, so.acceptance_rate, rtol=1e-10)
+    assert np.allclose(dHm, so.max_hamiltonian_energy_error, rtol=1e-9, atol=1e-12)
+    return so
+
+
+CASES = [
+    ("diag_gauss", "diag", 7, 9, 0.25, "multinomial", "generalised"),   # G=8: four chains per warp at different tree positions
+    ("std_normal", "unit", 3, 11, 0.35, "multinomial", "generalised"),  # G=4: eight chains per warp
+    ("funnel", "diag", 6, 6, 0.25, "multinomial", "generalised"),
+    ("diag_gauss", "diag", 40, 3, 0.2, "multinomial", "generalised"),   # G=32, E=2: one chain per warp
+    ("dense_gauss", "dense", 6, 5, 0.3, "multinomial", "generalised"),  # shared-memory slab, cached M^-1 r_first
+    ("diag_gauss", "diag", 7, 9, 0.25, "slice", "generalised"),
+    ("diag_gauss", "diag", 7, 9, 0.25, "multinomial", "classic"),
+    ("diag_gauss", "diag", 7, 9, 0.25, "multinomial", "strict"),
+    ("dense_gauss", "dense", 6, 5, 0.3, "slice", "strict"),
+    ("diag_gauss", "unit", 5, 7, 0.3, "slice", "classic"),
+]
+
+
+@pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion", CASES,
+                         ids=[f"{c[0]}-{c[1]}-D{c[2]}-{c[5]}-{c[6]}" for c in CASES])
+def test_kernel_source_under_cpu_simt_emulation_matches_oracle(emu, kind, mkind, D, N, eps, sampler, criterion):
+    so = _case(emu, kind, mkind, D, N, eps, sampler, criterion, seed=5 + D)
+    assert so.n_steps.max() >= 7
+
+
+def test_kernel_source_emulated_divergent_and_max_depth(emu):
+    so = _case(emu, "funnel", "diag", 4, 8, 1.5, "multinomial", "generalised", seed=3, delta_max=3.0, scale=1.5)
+    assert so.numerical_error.sum() > 0
+    so = _case(emu, "std_normal", "unit", 3, 6, 0.02, "multinomial", "generalised", seed=4, max_depth=4)
+    assert (so.tree_depth == 4).all()
+
+
+@pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion", CASES[:4] + CASES[5:6],
+                         ids=[f"{c[0]}-{c[1]}-D{c[2]}-{c[5]}-{c[6]}" for c in CASES[:4] + CASES[5:6]])
+def test_staged_fastdraw_variant_under_emulation_matches_oracle(emu_fast, kind, mkind, D, N, eps, sampler, criterion):
+    """-DAHMC_NUTS_FASTDRAW=1 (Philox block cache + probability-domain combine; off in the shipped build): same trees and
+    selections as the oracle from the same tapes."""
+    _case(emu_fast, kind, mkind, D, N, eps, sampler, criterion, seed=5 + D)
+
+
+def _philox_run(lib, N, D, T, seed, n_adapts=0, adapt=False, eps0=0.3, Minv0=None, sd=None, mu=None, windows=(3, 2, 4), n_min=3):
+    """Philox-mode run of the (adaptive or plain) persistent kernel: T transitions per chain from theta = 0."""
+    th = np.zeros((N, D))
+    th[:] = np.linspace(-1, 1, D)
+    r = np.zeros((N, D))
+    w = 1.0 / (sd * sd)
+    g_in = (th - mu) * w
+    lp_in = -0.5 * np.sum((th - mu) ** 2 * w, axis=1)
+    out = {k: np.zeros((N, D)) for k in ("th", "r", "g")}
+    lp_o, lk_o = np.zeros(N), np.zeros(N)
+    acc, dH, dHm = (np.zeros(T * N) for _ in range(3))
+    ns, td = np.zeros(T * N, dtype=np.int32), np.zeros(T * N, dtype=np.int32)
+    ne = np.zeros(T * N, dtype=np.uint8)
+    draws = np.zeros((T, N, D))
+    eps_rw, minv_rw, trace = np.full(N, eps0), np.zeros((N, D)), np.zeros((T, N))
+    Minv = np.ones(D) if Minv0 is None else Minv0
+    q = EmuNuts(model_kind=oc.DIAG_GAUSS, metric_kind=oc.DIAG, D=D, N=N, p0=P(mu), p1=P(w), c0=0.0, Minv=P(Minv),
+                minv_stride=0 if Minv.ndim == 1 else D, cholU=None, eps=eps0, eps_chain=None, max_depth=6, delta_max=1000.0,
+                sampler=0, criterion=0, seed=seed, offset=0, normal_tape=None, exp_tape=None, exp_stride=0, dir_tape=None,
+                dir_stride=0, partial_alpha=0.0, refresh=1, th_in=P(th), r_in=P(r), g_in=P(g_in), lp_in=P(lp_in),
+                th_out=P(out["th"]), r_out=P(out["r"]), g_out=P(out["g"]), lp_out=P(lp_o), lk_out=P(lk_o), n_steps=P(ns),
+                tree_depth=P(td), numerical=P(ne), acc=P(acc), dH=P(dH), dHmax=P(dHm), n_transitions=T, draws=P(draws),
+                adapt=1 if adapt else 0, n_adapts=n_adapts, init_buffer=windows[0], term_buffer=windows[1], window_size=windows[2],
+                delta=0.8, gamma=0.05, t0=10.0, kappa=0.75, adapt_metric=1, n_min=n_min, eps_rw=P(eps_rw), minv_rw=P(minv_rw),
+                eps_trace=P(trace))
+    assert lib.emu_nuts(C.byref(q)) == 0
+    return dict(draws=draws, acc=acc.reshape(T, N), n_steps=ns.reshape(T, N), eps=eps_rw, minv=minv_rw, trace=trace, theta=out["th"])
+
+
+def test_fastdraw_variant_equals_default_build_on_philox_streams(emu, emu_fast):
+    """Philox mode (no tapes): the staged variant consumes the same counter-based streams (cached blocks instead of
+    regenerated ones) and decides the same events, so whole multi-transition runs are bit-identical."""
+    rng = np.random.default_rng(2)
+    D, N, T = 6, 9, 12
+    sd, mu = np.exp(rng.uniform(-0.5, 0.5, D)), rng.normal(size=D)
+    a = _philox_run(emu, N, D, T, seed=77, sd=sd, mu=mu)
+    b = _philox_run(emu_fast, N, D, T, seed=77, sd=sd, mu=mu)
+    assert np.array_equal(a["draws"], b["draws"]) and np.array_equal(a["n_steps"], b["n_steps"])
+    assert np.array_equal(a["acc"], b["acc"])
+    assert a["n_steps"].max() >= 7 and len(np.unique(a["draws"][:, 0, 0])) > 6  # the chains really moved
+
+
+def test_in_launch_adaptation_under_emulation_equals_oracle_adaptors(emu):
+    """The adaptive kernel family (per-chain NesterovDualAveraging + windowed WelfordVar inside the persistent launch)
+    executed by the emulator, replayed iteration by iteration with the ORACLE's adaptors fed by the kernel's own
+    acceptance rates and draws: step-size trace, window update of M^-1, reset and finalize! must agree."""
+    rng = np.random.default_rng(3)
+    D, N, T, n_adapts = 5, 6, 24, 20
+    ib, tb, wsz = 3, 2, 4
+    ws, we, splits = oc.stan_windows(n_adapts, ib, tb, wsz)
+    sd, mu = np.exp(rng.uniform(-0.7, 0.7, D)), rng.normal(size=D)
+    run = _philox_run(emu, N, D, T, seed=5, n_adapts=n_adapts, adapt=True, sd=sd, mu=mu, windows=(ib, tb, wsz), n_min=3)
+    da, wv = oc.DualAveraging(np.full(N, 0.3), delta=0.8), oc.WelfordVar((D, N))
+    Minv = np.ones((N, D))
+    updates = 0
+    for i in range(1, T + 1):
+        assert np.allclose(run["trace"][i - 1], da.eps, rtol=1e-10), i
+        if i <= n_adapts:
+            da.adapt(run["acc"][i - 1])
+            if ws <= i <= we:
+                wv.push(run["draws"][i - 1].T)
+                if i in splits and wv.n.value >= 3:
+                    Minv = np.ascontiguousarray(wv.estimate().T)
+                    updates += 1
+            if i in splits:
+                da.reset()
+                wv = oc.WelfordVar((D, N))
+            if i == n_adapts:
+                da.finalize()
+    assert updates >= 1 and np.allclose(run["minv"], Minv, rtol=1e-9)
+    assert np.allclose(run["eps"], da.eps, rtol=1e-10)
+    # n_adapts = 0: the adaptive family is the plain persistent launch
+    p0 = _philox_run(emu, N, D, 6, seed=9, sd=sd, mu=mu)
+    p1 = _philox_run(emu, N, D, 6, seed=9, n_adapts=0, adapt=True, sd=sd, mu=mu)
+    assert np.array_equal(p0["draws"], p1["draws"]) and np.array_equal(p1["trace"], np.full((6, N), 0.3))
