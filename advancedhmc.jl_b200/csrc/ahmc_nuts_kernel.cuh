@@ -46,7 +46,7 @@ __device__ __forceinline__ double logaddexp(double a, double b) {  // LogExpFunc
 }
 __device__ __forceinline__ double maxabs(double a, double b) { return fabs(a) > fabs(b) ? a : b; }  // :526
 
-constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, cand lk
+constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, cand lk   (+ ww under AHMC_NUTS_FASTDRAW)
 
 // AHMC_NUTS_FASTDRAW (default 0 = the build every test and measurement of round 1 ran): staged instruction-count cuts
 // the K3 line profile asks for (profiles/r01/k3_source_line_profile.txt: random draws 24 %, logaddexp 16 % of the
@@ -56,6 +56,9 @@ constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, ca
 //   * the multinomial combine decides in the probability domain, u < w_p / (w_p + w_c) with exp(-|dlw|) shared with the
 //     log-sum-exp, instead of lw < lw_p - log(u): no log per combine (same event; oracle/nuts_iterative.py checks that
 //     the two forms decide identically on every test tree); SliceTS takes u directly instead of exp(-(-log u)).
+//   * multinomial weights are carried as (m, w) pairs -- log-weight = m + log(w), m = the largest leaf log-weight under
+//     the node, w in [1, #leaves] -- so combining two nodes costs one exp and NO log / log1p at all (same decisions:
+//     oracle/nuts_iterative.py max_weights, tests/test_oracle.py).
 // Compiled and register-checked only; NOT yet run on a GPU -- build with -DAHMC_NUTS_FASTDRAW=1 (scripts/build_variants.sh)
 // and run the tape-parity tests before making it the default.
 #ifndef AHMC_NUTS_FASTDRAW
@@ -92,13 +95,18 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     const bool dense = (MODEL == AHMC_MODEL_DENSE_GAUSS) || (METRIC == AHMC_METRIC_DENSE);
     double* xs = smem + (size_t)grp_in_block * D;  // dense slab (unused otherwise)
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
-    double* lv = smem + (dense ? (size_t)kGroups * D : 0) + (size_t)grp_in_block * maxd * kLevelScalars;
+    double* lv = smem + (dense ? (size_t)kGroups * D : 0) +
+                 (size_t)grp_in_block * maxd * (kLevelScalars + (AHMC_NUTS_FASTDRAW ? 1 : 0));
     double* LW = lv;
     double* SA = lv + maxd;
     double* NA = lv + 2 * maxd;
     double* DH = lv + 3 * maxd;
     double* CLP = lv + 4 * maxd;
     double* CLK = lv + 5 * maxd;
+#if AHMC_NUTS_FASTDRAW
+    double* WW = lv + 6 * maxd;  // (m, w) weights: LW holds m, WW holds w
+    double ww_tree = 1.0, ww_c = 1.0;
+#endif
 
     double* base = a.scratch + a.scratch_stride * chain;
     double* LEFT = base;
@@ -251,6 +259,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                     if (l == 0) a.ad.eps[chain] = eps_c;
                 }
                 lw_tree = 0.0;
+#if AHMC_NUTS_FASTDRAW
+                ww_tree = 1.0;
+#endif
                 if (VAR && samp == 1) {  // SliceTS(rng, z0) = SliceTS(z0, neg_energy(z0) - randexp(rng), 1) (:144-145)
                     lu = (s.lp + s.lk) - next_exp();
                     lw_tree = 1.0;  // n = 1
@@ -389,6 +400,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             tnum_c = !(lu < a.delta_max + -H1);              // Termination(::SliceTS) (:500-502)
         }
         bool tdyn_c = false;
+#if AHMC_NUTS_FASTDRAW
+        ww_c = 1.0;  // a leaf: (m, w) = (H0 - H', 1)
+#endif
         double rho_cur[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) rho_cur[e] = s.r[e];  // TurnStatistic(z.r)
@@ -511,14 +525,23 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                         const double n = lw_p + lw_c;
                         if (n * next_unif() < lw_p) cand_cur = k;
                         lw_c = n;
-                    } else {  // combine(rng, s1, s2) (:191-195) decided in the probability domain (see the macro's comment)
+                    } else {  // combine(rng, s1, s2) (:191-195) on (m, w) weights, decided in the probability domain
                         const double u = next_u_of_exp();
-                        const double dlw = lw_p - lw_c;
-                        const double tt = exp(-((lw_p == lw_c) ? 0.0 : fabs(dlw)));
-                        const double mx = (lw_p != lw_p || lw_c != lw_c) ? CUDART_NAN : (lw_p > lw_c ? lw_p : lw_c);
-                        const double p_first = (dlw >= 0.0) ? 1.0 / (1.0 + tt) : tt / (1.0 + tt);
+                        const double ww_p = WW[k];
+                        const double dlw = lw_p - lw_c;          // m_p - m_c
+                        const double tt = (lw_p == lw_c) ? 1.0 : exp(-fabs(dlw));  // like logaddexp: equal (even -Inf) -> 1; NaN in -> NaN
+                        double w_new, p_first;
+                        if (dlw >= 0.0) {
+                            w_new = fma(ww_c, tt, ww_p);
+                            p_first = ww_p / w_new;
+                            lw_c = lw_p;
+                        } else {  // m_c is the larger one, or dlw is NaN (both -Inf: m stays -Inf; a NaN weight: m becomes NaN)
+                            w_new = fma(ww_p, tt, ww_c);
+                            p_first = ww_p * tt / w_new;
+                            lw_c = (lw_p != lw_p) ? lw_p : lw_c;
+                        }
                         if ((dlw == dlw) && (u < p_first)) cand_cur = k;  // lw < lw_p + randexp  <=>  u < w_p / (w_p + w_c)
-                        lw_c = mx + log1p(tt);                            // == logaddexp(lw_p, lw_c)
+                        ww_c = w_new;
                     }
 #else
                     const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
@@ -576,6 +599,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                         clk = CLK[cand_cur];
                     }
                     if (l == 0) {
+#if AHMC_NUTS_FASTDRAW
+                        WW[k] = ww_c;
+#endif
                         LW[k] = lw_c;
                         SA[k] = sa_c;
                         NA[k] = na_c;
@@ -596,9 +622,14 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             bool accept = false;
             if (complete && !sub_term) {
                 j = j + 1;
+#if AHMC_NUTS_FASTDRAW
+                if (VAR && samp == 1) accept = lw_tree * next_unif() < lw_c;  // mh_accept(::SliceTS) (:202)
+                else accept = next_u_of_exp() < (ww_c / ww_tree) * exp(lw_c - lw_tree);  // lw_T < lw_c + randexp (:204-206)
+#else
                 const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
                 accept = (VAR && samp == 1) ? (lw_tree * ex < lw_c)   // mh_accept(::SliceTS): s.n * rand < s'.n (:202)
                                             : (lw_tree < lw_c + ex);  // mh_accept (:204-206)
+#endif
             }
             if (accept) {  // zcand = sampler'.zcand
                 if (cand_cur < 0) {
@@ -708,8 +739,23 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 sa_tree = (v < 0) ? sa_c + sa_tree : sa_tree + sa_c;
                 na_tree += (int)na_c;
                 dh_tree = (v < 0) ? maxabs(dh_c, dh_tree) : maxabs(dh_tree, dh_c);
+#if AHMC_NUTS_FASTDRAW
+                if (VAR && samp == 1) {
+                    lw_tree = lw_tree + lw_c;  // combine(zcand, s1::SliceTS, s2): n1 + n2 (:185-189)
+                } else {                       // combine(zcand, sampler, sampler') (:197-200, :717) on (m, w)
+                    const double dT = lw_tree - lw_c;
+                    const double tT = (lw_tree == lw_c) ? 1.0 : exp(-fabs(dT));
+                    if (dT >= 0.0) {
+                        ww_tree = fma(ww_c, tT, ww_tree);
+                    } else {
+                        ww_tree = fma(ww_tree, tT, ww_c);
+                        lw_tree = (lw_tree != lw_tree) ? lw_tree : lw_c;
+                    }
+                }
+#else
                 lw_tree = (VAR && samp == 1) ? lw_tree + lw_c            // combine(zcand, s1::SliceTS, s2): n1 + n2 (:185-189)
                                              : logaddexp(lw_tree, lw_c);  // combine(zcand, sampler, sampler') (:197-200, :717)
+#endif
                 term_dyn = term_dyn || tdyn_c || uturn_top;  // (:719-722)
                 term_num = term_num || tnum_c;
                 in_sub = false;
@@ -728,7 +774,8 @@ static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;
     const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
-    size_t sm = smem_bytes(MODEL, METRIC, a.D, G) + (size_t)chains_per_block * maxd * kLevelScalars * sizeof(double);
+    size_t sm = smem_bytes(MODEL, METRIC, a.D, G) +
+                (size_t)chains_per_block * maxd * (kLevelScalars + (AHMC_NUTS_FASTDRAW ? 1 : 0)) * sizeof(double);
     if (sm > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

@@ -46,12 +46,15 @@ def maxabs(a, b):
 
 
 def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generalised", max_depth=10, delta_max=1000.0,
-               linear_accept=False):
+               linear_accept=False, max_weights=False):
     """-> (zcand, stats dict, number of variates used).  dirs: direction bits (1 = left), variates: the tape.
     linear_accept: take the multinomial decisions in the probability domain -- `u < w_p / (w_p + w_c)` with
     u = exp(-randexp) -- instead of the reference's `lw < lw_p + randexp` (mathematically the same event; it would save
     the kernel one log per combine because exp(-|lw_p - lw_c|) is already computed by logaddexp and the Philox stream
-    yields u directly).  tests/test_oracle.py checks that both forms decide identically on every test tree."""
+    yields u directly).  tests/test_oracle.py checks that both forms decide identically on every test tree.
+    max_weights (implies the probability-domain decisions): carry every multinomial weight as (m, w) with
+    log-weight = m + log(w), m = the largest leaf log-weight under the node and w in [1, #leaves]; combining two nodes
+    costs one exp and no log at all -- the form staged in the kernel behind AHMC_NUTS_FASTDRAW."""
     nvar = ndir = 0
 
     def draw():
@@ -67,6 +70,7 @@ def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generali
     else:
         lu, lw_tree = None, 0.0
     sa_tree = dh_tree = 0.0
+    ww_tree = 1.0
     na_tree = j = 0
     term_dyn = term_num = False
     pending = {}  # level k -> dict(rho, rfirst, rlast, thfirst, cand, lw, sa, na, dh)
@@ -87,6 +91,7 @@ def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generali
             else:
                 lw_c, tnum_c = H0 + nE, not (-H0 < delta_max + -H1)
             sa_c, na_c, dh_c, tdyn_c = math.exp(min(0.0, -dH)), 1, dH, False
+            ww_c = 1.0  # max_weights: (lw_c, ww_c) = (m, w)
             node = dict(rho=s["r"].copy(), rfirst=s["r"], rlast=s["r"], thfirst=s["th"], cand=s)
             # ------------------------------------------------------------ (C) post-order merges, binary-counter style
             k, complete = 0, False
@@ -114,6 +119,18 @@ def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generali
                         n = F["lw"] + lw_c
                         cand = F["cand"] if n * u < F["lw"] else node["cand"]
                         lw_c = n
+                    elif max_weights:  # :191-195 on (m, w) pairs: one exp, no log
+                        d = F["lw"] - lw_c
+                        t = math.exp(-abs(d)) if d == d else float("nan")
+                        if d >= 0:
+                            w_new, p_first, m_new = F["ww"] + ww_c * t, None, F["lw"]
+                            p_first = F["ww"] / w_new
+                        else:
+                            w_new, m_new = F["ww"] * t + ww_c, lw_c
+                            p_first = F["ww"] * t / w_new
+                        take = (d == d) and (math.exp(-u) < p_first)
+                        cand = F["cand"] if take else node["cand"]
+                        lw_c, ww_c = m_new, w_new
                     else:  # :191-195
                         lw = logaddexp(F["lw"], lw_c)
                         if linear_accept:
@@ -133,7 +150,7 @@ def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generali
                 elif tnum_c or tdyn_c:  # a terminated first half is returned as is (:652): it "floats" up a level
                     k += 1
                 else:  # first half of level k: park it and go build its sibling
-                    pending[k] = dict(node, lw=lw_c, sa=sa_c, na=na_c, dh=dh_c)
+                    pending[k] = dict(node, lw=lw_c, ww=ww_c, sa=sa_c, na=na_c, dh=dh_c)
                     break
             if complete:
                 break
@@ -145,6 +162,8 @@ def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generali
             u = draw()
             if sampler == "slice":
                 accept = lw_tree * u < lw_c
+            elif max_weights:  # lw_tree < lw_c + randexp  <=>  u < (w_c / w_T) exp(m_c - m_T)
+                accept = math.exp(-u) < (ww_c / ww_tree) * math.exp(lw_c - lw_tree)
             elif linear_accept:
                 accept = math.exp(-u) < math.exp(min(0.0, lw_c - lw_tree))
             else:
@@ -171,7 +190,17 @@ def transition(S, z0, dirs, variates, sampler="multinomial", criterion="generali
         sa_tree = sa_c + sa_tree if v < 0 else sa_tree + sa_c
         na_tree += na_c
         dh_tree = maxabs(dh_c, dh_tree) if v < 0 else maxabs(dh_tree, dh_c)
-        lw_tree = lw_tree + lw_c if sampler == "slice" else logaddexp(lw_tree, lw_c)
+        if sampler == "slice":
+            lw_tree = lw_tree + lw_c
+        elif max_weights:
+            d = lw_tree - lw_c
+            t = math.exp(-abs(d)) if d == d else float("nan")
+            if d >= 0:
+                ww_tree = ww_tree + ww_c * t
+            else:
+                lw_tree, ww_tree = lw_c, ww_tree * t + ww_c
+        else:
+            lw_tree = logaddexp(lw_tree, lw_c)
         term_dyn = term_dyn or tdyn_c or uturn
         term_num = term_num or tnum_c
         pending.clear()

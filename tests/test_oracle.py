@@ -554,6 +554,12 @@ def test_iterative_nuts_scheme_matches_mp50_recursion(case):
         assert rel_err(zc["th"], e["theta"][c]) < 1e-10 and rel_err(zc["r"], e["r"][c]) < 1e-10
         assert st["acceptance_rate"] == pytest.approx(e["acceptance_rate"][c], rel=1e-10)
         assert st["max_hamiltonian_energy_error"] == pytest.approx(e["max_hamiltonian_energy_error"][c], rel=1e-9, abs=1e-10)
+        if case["sampler"] == "multinomial":  # the log-free (m, w) weight form staged for the kernel decides the same
+            zm, sm, um = ni.transition(S, z0, case["dirs"][c], case["variates"][c], sampler="multinomial",
+                                       criterion=case["criterion"], max_depth=case["max_depth"], delta_max=case["delta_max"],
+                                       max_weights=True)
+            assert (sm["tree_depth"], sm["n_steps"], um) == (e["tree_depth"][c], e["n_steps"][c], e["variates_used"][c])
+            assert np.array_equal(zm["th"], zc["th"])
 
 
 @pytest.mark.parametrize("sampler,criterion", [("multinomial", "generalised"), ("slice", "generalised"),
@@ -592,6 +598,10 @@ def test_iterative_nuts_scheme_matches_recursive_c_oracle_on_deep_trees(sampler,
                                        criterion=criterion, max_depth=max_depth, delta_max=delta_max, linear_accept=True)
             assert (sl["tree_depth"], sl["n_steps"], nl) == (st["tree_depth"], st["n_steps"], nu)
             assert np.array_equal(zl["th"], zc["th"])
+            zm, sm, nm = ni.transition(S, S.point(th[:, c].copy(), r[:, c].copy()), dirs[c], var[c], sampler=sampler,
+                                       criterion=criterion, max_depth=max_depth, delta_max=delta_max, max_weights=True)
+            assert (sm["tree_depth"], sm["n_steps"], nm) == (st["tree_depth"], st["n_steps"], nu)
+            assert np.array_equal(zm["th"], zc["th"])  # (m, w) weights: same decisions, no log
     if delta_max < 1.0:
         assert so.numerical_error.sum() > 5       # numerical terminations inside and at the top of subtrees
     else:

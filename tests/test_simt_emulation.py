@@ -146,6 +146,13 @@ def test_staged_fastdraw_variant_under_emulation_matches_oracle(emu_fast, kind, 
     _case(emu_fast, kind, mkind, D, N, eps, sampler, criterion, seed=5 + D)
 
 
+def test_staged_fastdraw_variant_divergent_and_max_depth(emu_fast):
+    so = _case(emu_fast, "funnel", "diag", 4, 8, 1.5, "multinomial", "generalised", seed=3, delta_max=3.0, scale=1.5)
+    assert so.numerical_error.sum() > 0
+    so = _case(emu_fast, "funnel", "diag", 4, 8, 2.5, "multinomial", "generalised", seed=6, delta_max=1000.0, scale=3.0)
+    _case(emu_fast, "std_normal", "unit", 3, 6, 0.02, "multinomial", "generalised", seed=4, max_depth=4)
+
+
 def _philox_run(lib, N, D, T, seed, n_adapts=0, adapt=False, eps0=0.3, Minv0=None, sd=None, mu=None, windows=(3, 2, 4), n_min=3):
     """Philox-mode run of the (adaptive or plain) persistent kernel: T transitions per chain from theta = 0."""
     th = np.zeros((N, D))
