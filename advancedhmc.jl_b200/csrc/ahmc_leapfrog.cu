@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(kBlockThreads) mh_select_kernel(const MhArgs a
     }
 }
 
+#ifndef AHMC_SIMT_EMULATION  // host launch code (skipped by the CPU SIMT emulation harness, tests/simt_emu/)
 // ---------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------
@@ -619,5 +620,7 @@ cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t st, int* n_
     }
     return cudaErrorInvalidValue;
 }
+
+#endif  // AHMC_SIMT_EMULATION
 
 }  // namespace ahmc

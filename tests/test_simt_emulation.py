@@ -228,3 +228,102 @@ def test_in_launch_adaptation_under_emulation_equals_oracle_adaptors(emu):
     p0 = _philox_run(emu, N, D, 6, seed=9, sd=sd, mu=mu)
     p1 = _philox_run(emu, N, D, 6, seed=9, n_adapts=0, adapt=True, sd=sd, mu=mu)
     assert np.array_equal(p0["draws"], p1["draws"]) and np.array_equal(p1["trace"], np.full((6, N), 0.3))
+
+
+# ------------------------------------------------------------------------------------------------ K1 / K2 under emulation
+class EmuLf(C.Structure):
+    _fields_ = [("model_kind", C.c_int32), ("metric_kind", C.c_int32), ("D", C.c_int32), ("N", C.c_int64), ("p0", _vp), ("p1", _vp),
+                ("c0", C.c_double), ("Minv", _vp), ("minv_stride", C.c_int64), ("cholU", _vp), ("eps", C.c_double),
+                ("eps_chain", _vp), ("n_steps", C.c_int32), ("fwd", C.c_int32), ("temper_alpha", C.c_double), ("th_in", _vp),
+                ("r_in", _vp), ("g_in", _vp), ("lp_in", _vp), ("th_out", _vp), ("r_out", _vp), ("g_out", _vp), ("lp_out", _vp),
+                ("lk_out", _vp), ("dr_out", _vp), ("status", _vp), ("steps_done", _vp), ("flags", C.c_uint32), ("hmc", C.c_int32),
+                ("refresh", C.c_int32), ("n_transitions", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("normal_tape", _vp), ("exp_tape", _vp), ("is_accept", _vp), ("acc", _vp), ("dH", _vp), ("draws", _vp)]
+
+
+@pytest.fixture(scope="module")
+def emu_lf(tmp_path_factory):
+    out = tmp_path_factory.mktemp("simt_lf") / "liblf_emu.so"
+    d = os.path.join(ROOT, "tests", "simt_emu")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-x", "c++",
+                    "-I", os.path.join(d, "include"), "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"),
+                    "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"), os.path.join(d, "lf_emu.cpp"),
+                    "-o", str(out)], check=True)
+    return C.CDLL(str(out))
+
+
+def _lf_system(kind, mkind, D, rng):
+    p0 = p1 = Minv = cholU = None
+    if kind == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.5, 0.5, D))
+    elif kind == "dense_gauss":
+        B = rng.normal(size=(D, D))
+        p0, p1 = rng.normal(size=D), B @ B.T / D + np.eye(D)
+    if mkind == "diag":
+        Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    elif mkind == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+        cholU = np.ascontiguousarray(np.linalg.cholesky(Minv))  # U column-major == (U')' = L row-major
+    model = oc.Model(KINDS[kind], D, p0, p1 if kind != "dense_gauss" else np.asfortranarray(p1), 0.0)
+    metric = oc.Metric(MKINDS[mkind], None if Minv is None else np.asfortranarray(Minv))
+    dp1 = None if p1 is None else (1.0 / (p1 * p1) if kind == "diag_gauss" else np.ascontiguousarray(p1))
+    return model, metric, p0, dp1, Minv, cholU
+
+
+LF_CASES = [("diag_gauss", "diag", 7, 9, 0.1, 20, 1),    # fused fast path, 4 chains per warp
+            ("std_normal", "unit", 3, 13, 0.2, 11, 1),   # fast path, 8 chains per warp
+            ("funnel", "diag", 6, 7, 0.05, 12, 1),       # exact per-step path
+            ("dense_gauss", "dense", 6, 5, 0.1, 9, 1),   # exact path with the shared-memory slab matvec
+            ("diag_gauss", "diag", 40, 3, 0.1, 16, 0)]   # backward, one chain per warp (E = 2)
+
+
+@pytest.mark.parametrize("kind,mkind,D,N,eps,n,fwd", LF_CASES, ids=[f"{c[0]}-{c[1]}-D{c[2]}" for c in LF_CASES])
+def test_trajectory_kernel_source_under_emulation_matches_oracle(emu_lf, kind, mkind, D, N, eps, n, fwd):
+    """K1 (`leapfrog_kernel`, fast and exact paths of ahmc_traj.cuh) executed by the emulator vs the oracle's `step`."""
+    rng = np.random.default_rng(11 + D)
+    model, metric, p0, dp1, Minv, cholU = _lf_system(kind, mkind, D, rng)
+    th, r = rng.normal(size=(N, D)) * (0.5 if kind == "funnel" else 1.0), rng.normal(size=(N, D))
+    eps_chain = eps * np.exp(rng.uniform(-0.3, 0.3, N))
+    z0 = oc.phasepoint(model, metric, th.T, r.T)
+    zo = oc.leapfrog(model, metric, eps_chain, z0, n if fwd else -n)[0]
+    g_in, lp_in = np.ascontiguousarray(z0.lp_gradient.T), np.ascontiguousarray(z0.lp_value)
+    o = {k: np.zeros((N, D)) for k in ("th", "r", "g", "dr")}
+    lp_o, lk_o = np.zeros(N), np.zeros(N)
+    status, done = np.zeros(N, dtype=np.uint32), np.zeros(N, dtype=np.int32)
+    q = EmuLf(model_kind=KINDS[kind], metric_kind=MKINDS[mkind], D=D, N=N, p0=P(p0), p1=P(dp1), c0=0.0, Minv=P(Minv),
+              minv_stride=0, cholU=P(cholU), eps=eps, eps_chain=P(eps_chain), n_steps=n, fwd=fwd, temper_alpha=0.0,
+              th_in=P(th), r_in=P(r), g_in=P(g_in), lp_in=P(lp_in), th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]),
+              lp_out=P(lp_o), lk_out=P(lk_o), dr_out=P(o["dr"]), status=P(status), steps_done=P(done), flags=0, hmc=0)
+    assert emu_lf.emu_leapfrog(C.byref(q)) == 0
+    assert (done == n).all() and (status == 0).all()
+    assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10 and rel_err(o["g"].T, zo.lp_gradient) < 1e-10
+    assert np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10) and np.allclose(lk_o, zo.lk_value, rtol=1e-10, atol=1e-10)
+    assert rel_err(o["dr"].T, zo.lk_gradient) < 1e-10
+
+
+@pytest.mark.parametrize("kind,mkind,D,N,eps,n", [("diag_gauss", "diag", 7, 9, 0.6, 6), ("funnel", "diag", 5, 10, 0.45, 6),
+                                                  ("dense_gauss", "dense", 6, 6, 0.7, 5)],
+                         ids=["diag-fast", "funnel-exact", "dense"])
+def test_hmc_transition_kernel_source_under_emulation_matches_oracle(emu_lf, kind, mkind, D, N, eps, n):
+    """K2 (`hmc_kernel`: momentum refresh from a normal tape, trajectory, Metropolis step, revert, flip) vs the oracle."""
+    rng = np.random.default_rng(21 + D)
+    model, metric, p0, dp1, Minv, cholU = _lf_system(kind, mkind, D, rng)
+    th = rng.normal(size=(N, D)) * (1.5 if kind == "funnel" else 1.0)
+    nt, et = rng.normal(size=(N, D)), rng.exponential(size=N)
+    z0 = oc.phasepoint(model, metric, th.T, np.zeros((D, N)))
+    zo, so = oc.hmc_transition(model, metric, eps, n, z0, nt.T, et)
+    g_in, lp_in = np.ascontiguousarray(z0.lp_gradient.T), np.ascontiguousarray(z0.lp_value)
+    o = {k: np.zeros((N, D)) for k in ("th", "r", "g")}
+    lp_o, lk_o, acc, dH = (np.zeros(N) for _ in range(4))
+    isacc = np.zeros(N, dtype=np.uint8)
+    r0 = np.zeros((N, D))
+    q = EmuLf(model_kind=KINDS[kind], metric_kind=MKINDS[mkind], D=D, N=N, p0=P(p0), p1=P(dp1), c0=0.0, Minv=P(Minv),
+              minv_stride=0, cholU=P(cholU), eps=eps, eps_chain=None, n_steps=n, fwd=1, temper_alpha=0.0, th_in=P(th), r_in=P(r0),
+              g_in=P(g_in), lp_in=P(lp_in), th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]), lp_out=P(lp_o), lk_out=P(lk_o),
+              dr_out=None, status=None, steps_done=None, flags=0, hmc=1, refresh=1, n_transitions=1, seed=1, offset=0,
+              normal_tape=P(nt), exp_tape=P(et), is_accept=P(isacc), acc=P(acc), dH=P(dH), draws=None)
+    assert emu_lf.emu_leapfrog(C.byref(q)) == 0
+    assert (isacc == so.is_accept).all()
+    assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10
+    assert np.allclose(acc, so.acceptance_rate, rtol=1e-10) and np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10)
