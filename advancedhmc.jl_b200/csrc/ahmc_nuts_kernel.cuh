@@ -49,18 +49,19 @@ __device__ __forceinline__ double maxabs(double a, double b) { return fabs(a) > 
 constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, cand lk   (+ ww under AHMC_NUTS_FASTDRAW)
 
 // AHMC_NUTS_FASTDRAW (default 0 = the build every test and measurement of round 1 ran): staged instruction-count cuts
-// the K3 line profile asks for (profiles/r01/k3_source_line_profile.txt: random draws 24 %, logaddexp 16 % of the
-// instructions).  With 1:
-//   * one Philox block serves two consecutive variates / 128 direction bits (cached in registers) instead of being
-//     regenerated for each;
-//   * the multinomial combine decides in the probability domain, u < w_p / (w_p + w_c) with exp(-|dlw|) shared with the
-//     log-sum-exp, instead of lw < lw_p - log(u): no log per combine (same event; oracle/nuts_iterative.py checks that
-//     the two forms decide identically on every test tree); SliceTS takes u directly instead of exp(-(-log u)).
+// the K3 line profile asks for (profiles/r01/k3_source_line_profile.txt: of 882 warp-instructions per leaf, random draws
+// 24 %, logaddexp 16 %, the leaf's exp 6 %).  With 1:
+//   * variates are prefetched lane-parallel: lane l of the chain's group generates uniform #(base + l) of the Philox
+//     stream (one block per LANE instead of one per DRAW), a draw is then a group broadcast of one register; direction
+//     bits come from a cached block (128 doublings each);
 //   * multinomial weights are carried as (m, w) pairs -- log-weight = m + log(w), m = the largest leaf log-weight under
-//     the node, w in [1, #leaves] -- so combining two nodes costs one exp and NO log / log1p at all (same decisions:
-//     oracle/nuts_iterative.py max_weights, tests/test_oracle.py).
-// Compiled and register-checked only; NOT yet run on a GPU -- build with -DAHMC_NUTS_FASTDRAW=1 (scripts/build_variants.sh)
-// and run the tape-parity tests before making it the default.
+//     the node, w in [1, #leaves] -- and the combine decides in the probability domain, u < w_p / (w_p + w_c): one exp per
+//     combine, NO log / log1p anywhere in the tree walk (same events; oracle/nuts_iterative.py max_weights);
+//   * the acceptance statistic sum_alpha = sum over leaves of exp(min(0, -dH)) is order-free: a leaf parks dH in one
+//     lane's register and the exponentials are taken G at a time, one per lane.
+// Status: compiles for sm_100a (168 registers); its SOURCE passes the oracle comparisons, the in-launch adaptation check
+// and a draw-for-draw identity check against the default build on Philox streams under the CPU SIMT emulator
+// (tests/test_simt_emulation.py).  NOT yet run on a GPU: scripts/build_variants.sh fastdraw + scripts/gpu_fastdraw_ab.sh.
 #ifndef AHMC_NUTS_FASTDRAW
 #define AHMC_NUTS_FASTDRAW 0
 #endif
@@ -129,30 +130,43 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     int nexp = 0, ndir = 0;
     uint64_t off = a.rng.offset;  // Philox transition counter of the transition this group is working on
 #if AHMC_NUTS_FASTDRAW
-    uint32_t cexp[4] = {0u, 0u, 0u, 0u}, cdir[4] = {0u, 0u, 0u, 0u};
-    int cexp_blk = -1, cdir_blk = -1;  // cached Philox blocks (reset with the per-transition counters)
-    auto philox_u = [&](int k) -> double {  // k-th uniform of (chain, transition): two per block
-        if ((k >> 1) != cexp_blk) {
-            cexp_blk = k >> 1;
-            Philox::gen(a.rng.seed, (uint64_t)chain, (off << 24) ^ (STREAM_EXP << 60) ^ (uint64_t)cexp_blk, cexp);
+    // Lane-parallel variate prefetch: lane l of the chain's group holds uniform #(vbase + l) of the (chain, transition)
+    // stream -- one Philox block per LANE instead of one per DRAW -- and a draw is a group broadcast of one register.
+    // peek_u() must be called by every lane of the warp at a warp-uniform point (it shuffles); the take_*() below then
+    // consume the peeked value inside the per-chain (divergent) bookkeeping.  Same stream, same values as philox_exp().
+    double vbuf = 0.0;
+    int vbase = -(1 << 30);
+    auto peek_u = [&]() -> double {
+        const bool tape = a.rng.exp_tape && nexp < a.rng.exp_stride;
+        const bool need = !tape && (nexp < vbase || nexp >= vbase + G);
+        if (__any_sync(FULL, need)) {
+            if (need) {
+                vbase = (nexp / G) * G;
+                const int kk = vbase + l;
+                uint32_t o[4];
+                Philox::gen(a.rng.seed, (uint64_t)chain, (off << 24) ^ (STREAM_EXP << 60) ^ (uint64_t)(kk >> 1), o);
+                vbuf = (kk & 1) ? Philox::u01(o[2], o[3]) : Philox::u01(o[0], o[1]);
+            }
         }
-        return (k & 1) ? Philox::u01(cexp[2], cexp[3]) : Philox::u01(cexp[0], cexp[1]);
+        return Grp<G>::bcast(vbuf, (nexp - vbase) & (G - 1));
     };
-    auto next_exp = [&]() -> double {
+    auto take_exp = [&](double u_pk) -> double {  // randexp
         int k = nexp++;
         if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
-        return -log(philox_u(k));
+        return -log(u_pk);
     };
-    auto next_unif = [&]() -> double {  // SliceTS: rand(rng)
+    auto take_unif = [&](double u_pk) -> double {  // SliceTS: rand(rng)
         int k = nexp++;
         if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
-        return philox_u(k);
+        return u_pk;
     };
-    auto next_u_of_exp = [&]() -> double {  // u = exp(-randexp): the uniform behind the k-th exponential
+    auto take_u_of_exp = [&](double u_pk) -> double {  // u = exp(-randexp): the uniform behind the exponential
         int k = nexp++;
         if (a.rng.exp_tape && k < a.rng.exp_stride) return exp(-a.rng.exp_tape[chain * a.rng.exp_stride + k]);
-        return philox_u(k);
+        return u_pk;
     };
+    uint32_t cdir[4] = {0u, 0u, 0u, 0u};
+    int cdir_blk = -1;  // cached Philox block of direction bits (128 doublings per block)
     auto next_dir = [&]() -> bool {
         int k = ndir++;
         if (a.rng.dir_tape && k < a.rng.dir_stride) return a.rng.dir_tape[chain * a.rng.dir_stride + k] != 0;
@@ -161,6 +175,18 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             Philox::gen(a.rng.seed, (uint64_t)chain, (off << 24) ^ (STREAM_DIR << 60) ^ (uint64_t)cdir_blk, cdir);
         }
         return (cdir[(k >> 5) & 3] >> (k & 31)) & 1u;
+    };
+    // Deferred acceptance statistic: sum_alpha = sum over the leaves built of exp(min(0, -dH)) is order-free, so the leaf
+    // only parks its dH in one lane's register and the exponentials are taken G at a time, one per lane.
+    double abuf = 0.0, sa_acc = 0.0;
+    int acnt = 0;
+    auto alpha_flush = [&](bool mine) {  // warp-uniform call; `mine`: this group flushes now
+        double v = (mine && l < acnt) ? exp(jl_min0(-abuf)) : 0.0;
+        v = Grp<G>::sum(v);
+        if (mine) {
+            sa_acc += v;
+            acnt = 0;
+        }
     };
 #else
     auto next_exp = [&]() -> double {
@@ -206,7 +232,10 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 nexp = 0;
                 ndir = 0;
 #if AHMC_NUTS_FASTDRAW
-                cexp_blk = cdir_blk = -1;
+                vbase = -(1 << 30);
+                cdir_blk = -1;
+                sa_acc = 0.0;
+                acnt = 0;
 #endif
                 vload_nc<G, E>(s.th, first ? a.th_in + a.ld_in * chain : a.th_out + a.ld_out * chain, l, D);
                 vload_nc<G, E>(s.g, first ? a.g_in + a.ld_in * chain : a.g_out + a.ld_out * chain, l, D);
@@ -229,6 +258,10 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 vload_nc<G, E>(rn, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
             }
             const double lk0 = map_nonfinite(kinetic<METRIC, G, E>(me, rn, drn, xs, l));
+#if AHMC_NUTS_FASTDRAW
+            double u_init = 0.0;
+            if (VAR && samp == 1) u_init = peek_u();  // the slice variable's randexp (variate #0 of the transition)
+#endif
             if (need_init) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) s.r[e] = rn[e];
@@ -263,7 +296,11 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 ww_tree = 1.0;
 #endif
                 if (VAR && samp == 1) {  // SliceTS(rng, z0) = SliceTS(z0, neg_energy(z0) - randexp(rng), 1) (:144-145)
+#if AHMC_NUTS_FASTDRAW
+                    lu = (s.lp + s.lk) - take_exp(u_init);
+#else
                     lu = (s.lp + s.lk) - next_exp();
+#endif
                     lw_tree = 1.0;  // n = 1
                 }
                 sa_tree = 0.0;
@@ -278,8 +315,17 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             }
         }
         // ---------------------------------------------------------------- (F) finish a transition: stats (:725-739), draw
+#if AHMC_NUTS_FASTDRAW
+        {
+            const bool fl = !finished && done && !in_sub && acnt > 0;
+            if (__any_sync(FULL, fl)) alpha_flush(fl);
+        }
+#endif
         {
             const bool fin_now = !finished && done && !in_sub;
+#if AHMC_NUTS_FASTDRAW
+            if (fin_now) sa_tree = sa_acc;
+#endif
             if (fin_now) {
                 const long long si = (long long)t * a.N + chain;
                 if (a.draws) {
@@ -392,7 +438,19 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         const double H1 = -nE;
         const double dH = H1 - H0;
         double lw_c = H0 + nE;                               // MultinomialTS(s, H0, z') (:174-176)
+#if AHMC_NUTS_FASTDRAW
+        double sa_c = 0.0;  // (deferred: see alpha_flush)
+        if (in_sub) {
+            if (l == acnt) abuf = dH;
+            ++acnt;
+        }
+        {
+            const bool fl = in_sub && acnt == G;
+            if (__any_sync(FULL, fl)) alpha_flush(fl);
+        }
+#else
         double sa_c = exp(jl_min0(-dH));                     // alpha' = exp(min(0, -dH))
+#endif
         double na_c = 1.0, dh_c = dH;
         bool tnum_c = !(-H0 < a.delta_max + -H1);            // Termination(...) (:503-507)
         if (VAR && samp == 1) {
@@ -518,15 +576,18 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                     d2 = Grp<G>::sum(d2);
                     uturn = (d1 <= 0.0) || (d2 <= 0.0) || uturn_extra;
                 }
+#if AHMC_NUTS_FASTDRAW
+                const double u_comb = peek_u();
+#endif
                 if (do_comb) {
                     const double lw_p = LW[k], sa_p = SA[k], na_p = NA[k], dh_p = DH[k];
 #if AHMC_NUTS_FASTDRAW
                     if (VAR && samp == 1) {  // combine(rng, s1::SliceTS, s2) (:178-183)
                         const double n = lw_p + lw_c;
-                        if (n * next_unif() < lw_p) cand_cur = k;
+                        if (n * take_unif(u_comb) < lw_p) cand_cur = k;
                         lw_c = n;
                     } else {  // combine(rng, s1, s2) (:191-195) on (m, w) weights, decided in the probability domain
-                        const double u = next_u_of_exp();
+                        const double u = take_u_of_exp(u_comb);
                         const double ww_p = WW[k];
                         const double dlw = lw_p - lw_c;          // m_p - m_c
                         const double tt = (lw_p == lw_c) ? 1.0 : exp(-fabs(dlw));  // like logaddexp: equal (even -Inf) -> 1; NaN in -> NaN
@@ -620,11 +681,14 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         if (__any_sync(FULL, complete)) {
             const bool sub_term = tnum_c || tdyn_c;
             bool accept = false;
+#if AHMC_NUTS_FASTDRAW
+            const double u_top = peek_u();
+#endif
             if (complete && !sub_term) {
                 j = j + 1;
 #if AHMC_NUTS_FASTDRAW
-                if (VAR && samp == 1) accept = lw_tree * next_unif() < lw_c;  // mh_accept(::SliceTS) (:202)
-                else accept = next_u_of_exp() < (ww_c / ww_tree) * exp(lw_c - lw_tree);  // lw_T < lw_c + randexp (:204-206)
+                if (VAR && samp == 1) accept = lw_tree * take_unif(u_top) < lw_c;  // mh_accept(::SliceTS) (:202)
+                else accept = take_u_of_exp(u_top) < (ww_c / ww_tree) * exp(lw_c - lw_tree);  // lw_T < lw_c + randexp (:204-206)
 #else
                 const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
                 accept = (VAR && samp == 1) ? (lw_tree * ex < lw_c)   // mh_accept(::SliceTS): s.n * rand < s'.n (:202)

@@ -184,21 +184,24 @@ def _philox_run(lib, N, D, T, seed, n_adapts=0, adapt=False, eps0=0.3, Minv0=Non
 
 def test_fastdraw_variant_equals_default_build_on_philox_streams(emu, emu_fast):
     """Philox mode (no tapes): the staged variant consumes the same counter-based streams (cached blocks instead of
-    regenerated ones) and decides the same events, so whole multi-transition runs are bit-identical."""
+    regenerated ones, prefetched one per lane) and decides the same events, so whole multi-transition runs give
+    bit-identical draws and trees (the acceptance statistic, summed in a different order, to 1e-13)."""
     rng = np.random.default_rng(2)
     D, N, T = 6, 9, 12
     sd, mu = np.exp(rng.uniform(-0.5, 0.5, D)), rng.normal(size=D)
     a = _philox_run(emu, N, D, T, seed=77, sd=sd, mu=mu)
     b = _philox_run(emu_fast, N, D, T, seed=77, sd=sd, mu=mu)
     assert np.array_equal(a["draws"], b["draws"]) and np.array_equal(a["n_steps"], b["n_steps"])
-    assert np.array_equal(a["acc"], b["acc"])
+    assert np.allclose(a["acc"], b["acc"], rtol=1e-13, atol=0)  # sum_alpha is accumulated in a different (lane-parallel) order
     assert a["n_steps"].max() >= 7 and len(np.unique(a["draws"][:, 0, 0])) > 6  # the chains really moved
 
 
-def test_in_launch_adaptation_under_emulation_equals_oracle_adaptors(emu):
+@pytest.mark.parametrize("which", ["default", "fastdraw"])
+def test_in_launch_adaptation_under_emulation_equals_oracle_adaptors(emu, emu_fast, which):
     """The adaptive kernel family (per-chain NesterovDualAveraging + windowed WelfordVar inside the persistent launch)
     executed by the emulator, replayed iteration by iteration with the ORACLE's adaptors fed by the kernel's own
     acceptance rates and draws: step-size trace, window update of M^-1, reset and finalize! must agree."""
+    emu = emu if which == "default" else emu_fast
     rng = np.random.default_rng(3)
     D, N, T, n_adapts = 5, 6, 24, 20
     ib, tb, wsz = 3, 2, 4
