@@ -65,6 +65,9 @@ constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, ca
 #ifndef AHMC_NUTS_FASTDRAW
 #define AHMC_NUTS_FASTDRAW 0
 #endif
+#ifndef AHMC_NUTS_ALT_LAYOUT
+#define AHMC_NUTS_ALT_LAYOUT 0  // 1: (G, E) = (16, 4) / (16, 8) for 32 < D <= 128 -- staged, see nuts_dispatch
+#endif
 
 // Occupancy knob: the tree walk is a long chain of dependent, mostly fixed-latency instructions, so throughput
 // scales with resident warps per scheduler; cap registers so that this many 4-warp blocks fit per SM.
@@ -859,6 +862,10 @@ static cudaError_t nuts_layout(const NutsArgs& a, cudaStream_t st, int G, int E)
     if (G == 32 && E == 4) return launch_nuts_v<MODEL, METRIC, 32, 4, VAR, ADAPT>(a, st);
     if (G == 32 && E == 8) return launch_nuts_v<MODEL, METRIC, 32, 8, VAR, ADAPT>(a, st);
     if (G == 32 && E == 16) return launch_nuts_v<MODEL, METRIC, 32, 16, VAR, ADAPT>(a, st);
+#if AHMC_NUTS_ALT_LAYOUT
+    if (G == 16 && E == 4) return launch_nuts_v<MODEL, METRIC, 16, 4, VAR, ADAPT>(a, st);
+    if (G == 16 && E == 8) return launch_nuts_v<MODEL, METRIC, 16, 8, VAR, ADAPT>(a, st);
+#endif
     return cudaErrorInvalidValue;
 }
 
@@ -867,6 +874,12 @@ template <bool VAR, bool ADAPT, bool DIAG_ONLY>
 static cudaError_t nuts_dispatch(const NutsArgs& a, cudaStream_t st) {
     int G, E;
     if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+#if AHMC_NUTS_ALT_LAYOUT
+    // staged A/B knob (scripts/build_variants.sh altlayout): two chains per warp for 32 < D <= 128 (16 lanes x 4 or 8
+    // coordinates), so that the per-chain scalar bookkeeping -- ~2/3 of K3's instructions -- is issued once per TWO chains
+    if (a.D > 32 && a.D <= 64) G = 16, E = 4;
+    else if (a.D > 64 && a.D <= 128) G = 16, E = 8;
+#endif
     if (DIAG_ONLY) {
         if (a.metric.kind != AHMC_METRIC_DIAG) return cudaErrorInvalidValue;
         switch (a.model.kind) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B builds of the NUTS kernel: advancedhmc.jl_b200/_variants/libahmc_b200_<tag>.so, selected at run time with
 # AHMC_B200_LIB=<path>.  Usage: scripts/build_variants.sh minb4 fastdraw ...   (tags: minbN -> -DAHMC_NUTS_MINB=N,
-# fastdraw -> -DAHMC_NUTS_FASTDRAW=1).  The three NUTS translation units are recompiled, the rest is reused.
+# fastdraw -> -DAHMC_NUTS_FASTDRAW=1, altlayout -> -DAHMC_NUTS_ALT_LAYOUT=1, fastdraw_altlayout -> both).  The three NUTS translation units are recompiled, the rest is reused.
 set -e
 cd "$(dirname "$0")/.."
 python advancedhmc.jl_b200/build.py
@@ -13,6 +13,8 @@ for tag in "$@"; do
   case $tag in
     minb*) DEF="-DAHMC_NUTS_MINB=${tag#minb}" ;;
     fastdraw) DEF="-DAHMC_NUTS_FASTDRAW=1" ;;
+    altlayout) DEF="-DAHMC_NUTS_ALT_LAYOUT=1" ;;
+    fastdraw_altlayout) DEF="-DAHMC_NUTS_FASTDRAW=1 -DAHMC_NUTS_ALT_LAYOUT=1" ;;
     *) echo "unknown tag $tag"; exit 1 ;;
   esac
   ( for tu in ahmc_nuts ahmc_nuts_var ahmc_nuts_adapt; do

@@ -57,6 +57,10 @@ static KernelFn by_layout(int G, int E) {
     if (G == 4 && E == 1) return thunk<MODEL, METRIC, 4, 1, VAR, ADAPT>;
     if (G == 8 && E == 1) return thunk<MODEL, METRIC, 8, 1, VAR, ADAPT>;
     if (G == 32 && E == 2) return thunk<MODEL, METRIC, 32, 2, VAR, ADAPT>;
+#if AHMC_NUTS_ALT_LAYOUT
+    if (G == 16 && E == 4) return thunk<MODEL, METRIC, 16, 4, VAR, ADAPT>;
+    if (G == 16 && E == 8) return thunk<MODEL, METRIC, 16, 8, VAR, ADAPT>;
+#endif
     return nullptr;
 }
 
@@ -73,6 +77,7 @@ static KernelFn by_model(int model, int metric, int G, int E) {
 }
 
 extern "C" int emu_fastdraw() { return AHMC_NUTS_FASTDRAW; }
+extern "C" int emu_altlayout() { return AHMC_NUTS_ALT_LAYOUT; }
 
 extern "C" int emu_nuts(const EmuNuts* q) {
     int G, E;
@@ -80,7 +85,13 @@ extern "C" int emu_nuts(const EmuNuts* q) {
     if (D <= 4) G = 4, E = 1;
     else if (D <= 8) G = 8, E = 1;
     else if (D > 32 && D <= 64) G = 32, E = 2;
+#if AHMC_NUTS_ALT_LAYOUT
+    else if (D > 64 && D <= 128) G = 16, E = 8;
+#endif
     else return -1;
+#if AHMC_NUTS_ALT_LAYOUT
+    if (D > 32 && D <= 64) G = 16, E = 4;
+#endif
     NutsArgs a{};
     a.model = ModelDev{q->model_kind, D, q->p0, q->p1, q->c0};
     a.metric = MetricDev{q->metric_kind, q->Minv, q->minv_stride, q->cholU};

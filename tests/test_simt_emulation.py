@@ -31,7 +31,7 @@ class EmuNuts(C.Structure):
                 ("adapt_metric", C.c_int32), ("n_min", C.c_int32), ("eps_rw", _vp), ("minv_rw", _vp), ("eps_trace", _vp)]
 
 
-def _build(tmp, fastdraw):
+def _build(tmp, fastdraw, altlayout=False):
     out = tmp / ("libnuts_emu_fast.so" if fastdraw else "libnuts_emu.so")
     d = os.path.join(ROOT, "tests", "simt_emu")
     cmd = ["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-I", os.path.join(d, "include"),
@@ -39,9 +39,11 @@ def _build(tmp, fastdraw):
            os.path.join(d, "simt_emu.cpp"), os.path.join(d, "nuts_emu.cpp"), "-o", str(out)]
     if fastdraw:
         cmd.insert(1, "-DAHMC_NUTS_FASTDRAW=1")
+    if altlayout:
+        cmd.insert(1, "-DAHMC_NUTS_ALT_LAYOUT=1")
     subprocess.run(cmd, check=True)
     lib = C.CDLL(str(out))
-    assert lib.emu_fastdraw() == (1 if fastdraw else 0)
+    assert lib.emu_fastdraw() == (1 if fastdraw else 0) and lib.emu_altlayout() == (1 if altlayout else 0)
     return lib
 
 
@@ -53,6 +55,11 @@ def emu(tmp_path_factory):
 @pytest.fixture(scope="module")
 def emu_fast(tmp_path_factory):
     return _build(tmp_path_factory.mktemp("simt_fast"), True)
+
+
+@pytest.fixture(scope="module")
+def emu_alt(tmp_path_factory):
+    return _build(tmp_path_factory.mktemp("simt_alt"), True, altlayout=True)
 
 
 P = lambda a: None if a is None else a.ctypes.data_as(_vp)
@@ -144,6 +151,15 @@ def test_staged_fastdraw_variant_under_emulation_matches_oracle(emu_fast, kind, 
     """-DAHMC_NUTS_FASTDRAW=1 (Philox block cache + probability-domain combine; off in the shipped build): same trees and
     selections as the oracle from the same tapes."""
     _case(emu_fast, kind, mkind, D, N, eps, sampler, criterion, seed=5 + D)
+
+
+@pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion", [
+    ("diag_gauss", "diag", 100, 5, 0.15, "multinomial", "generalised"), ("diag_gauss", "diag", 40, 5, 0.2, "multinomial", "strict"),
+    ("funnel", "diag", 70, 3, 0.1, "slice", "generalised")], ids=["D100-16x8", "D40-16x4-strict", "funnel-D70-slice"])
+def test_staged_alt_layout_two_chains_per_warp_matches_oracle(emu_alt, kind, mkind, D, N, eps, sampler, criterion):
+    """-DAHMC_NUTS_ALT_LAYOUT=1 (+ FASTDRAW): 16 lanes x 4 / 8 coordinates per chain, i.e. two chains per warp for
+    32 < D <= 128 -- staged for the round-2 A/B; an odd chain count leaves half a warp idle."""
+    _case(emu_alt, kind, mkind, D, N, eps, sampler, criterion, seed=9 + D, scale=0.5 if kind == "funnel" else 1.0)
 
 
 def test_staged_fastdraw_variant_divergent_and_max_depth(emu_fast):
