@@ -57,6 +57,8 @@ static KernelFn by_layout(int G, int E) {
     if (G == 4 && E == 1) return thunk<MODEL, METRIC, 4, 1, VAR, ADAPT>;
     if (G == 8 && E == 1) return thunk<MODEL, METRIC, 8, 1, VAR, ADAPT>;
     if (G == 32 && E == 2) return thunk<MODEL, METRIC, 32, 2, VAR, ADAPT>;
+    if (G == 16 && E == 1) return thunk<MODEL, METRIC, 16, 1, VAR, ADAPT>;
+    if (G == 32 && E == 4) return thunk<MODEL, METRIC, 32, 4, VAR, ADAPT>;
 #if AHMC_NUTS_ALT_LAYOUT
     if (G == 16 && E == 4) return thunk<MODEL, METRIC, 16, 4, VAR, ADAPT>;
     if (G == 16 && E == 8) return thunk<MODEL, METRIC, 16, 8, VAR, ADAPT>;
@@ -84,11 +86,13 @@ extern "C" int emu_nuts(const EmuNuts* q) {
     const int D = q->D;
     if (D <= 4) G = 4, E = 1;
     else if (D <= 8) G = 8, E = 1;
+    else if (D <= 16) G = 16, E = 1;
     else if (D > 32 && D <= 64) G = 32, E = 2;
-#if AHMC_NUTS_ALT_LAYOUT
-    else if (D > 64 && D <= 128) G = 16, E = 8;
-#endif
+    else if (D > 64 && D <= 128) G = 32, E = 4;  // the headline layout
     else return -1;
+#if AHMC_NUTS_ALT_LAYOUT
+    if (D > 64 && D <= 128) G = 16, E = 8;
+#endif
 #if AHMC_NUTS_ALT_LAYOUT
     if (D > 32 && D <= 64) G = 16, E = 4;
 #endif

@@ -128,6 +128,8 @@ CASES = [
     ("diag_gauss", "diag", 7, 9, 0.25, "multinomial", "strict"),
     ("dense_gauss", "dense", 6, 5, 0.3, "slice", "strict"),
     ("diag_gauss", "unit", 5, 7, 0.3, "slice", "classic"),
+    ("diag_gauss", "diag", 13, 5, 0.25, "multinomial", "generalised"),  # G=16: two chains per warp
+    ("diag_gauss", "diag", 128, 2, 0.12, "multinomial", "generalised"),  # G=32, E=4: the headline layout
 ]
 
 
@@ -346,3 +348,21 @@ def test_hmc_transition_kernel_source_under_emulation_matches_oracle(emu_lf, kin
     assert (isacc == so.is_accept).all()
     assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10
     assert np.allclose(acc, so.acceptance_rate, rtol=1e-10) and np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10)
+
+
+def test_kernel_source_emulated_randomised_configurations(emu):
+    """A small fuzz over (target, metric, dimension / layout, chains per warp, step size, depth limit, divergence threshold,
+    sampler, criterion) of the emulated kernel source against the recursive oracle."""
+    rng = np.random.default_rng(123)
+    combos = [("std_normal", "unit"), ("diag_gauss", "diag"), ("funnel", "diag"), ("dense_gauss", "dense"), ("diag_gauss", "unit")]
+    for cfg in range(12):
+        kind, mkind = combos[int(rng.integers(0, len(combos)))]
+        D = int([3, 4, 6, 8, 11, 16, 40][int(rng.integers(0, 7))])
+        if kind == "funnel":
+            D = max(D, 2)
+        N = int(rng.integers(1, 10))
+        eps = float(np.exp(rng.uniform(np.log(0.08), np.log(0.6))))
+        sampler = ["multinomial", "slice"][int(rng.integers(0, 2))]
+        criterion = ["generalised", "classic", "strict"][int(rng.integers(0, 3))]
+        _case(emu, kind, mkind, D, N, eps, sampler, criterion, seed=1000 + cfg, max_depth=int(rng.integers(2, 7)),
+              delta_max=[1000.0, 2.5][int(rng.integers(0, 2))], scale=0.6 if kind == "funnel" else 1.3)
