@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(kBlockThreads) multinomial_kernel(const Multin
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
+#ifndef AHMC_SIMT_EMULATION  // host launch code (skipped by the CPU SIMT emulation harness, tests/simt_emu/)
 template <int MODEL, int METRIC, int G, int E>
 static cudaError_t launch_traj_t(const TrajArgs& a, cudaStream_t st) {
     const long long blocks = (a.N + kBlockThreads / G - 1) / (kBlockThreads / G);
@@ -295,5 +296,7 @@ cudaError_t launch_multinomial(const MultinomialArgs& a, cudaStream_t st, int* n
     if (n_launches) *n_launches += 1;
     AHMC_MM(mn_layout, a.model.kind, a.metric.kind);
 }
+
+#endif  // AHMC_SIMT_EMULATION
 
 }  // namespace ahmc

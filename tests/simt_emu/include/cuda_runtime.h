@@ -67,3 +67,7 @@ inline void sincospi(double x, double* s, double* c) {  // CUDA math API; only t
     *s = std::sin(M_PI * x);
     *c = std::cos(M_PI * x);
 }
+// warp reduction over the lanes named in `mask` (sm_80+ __reduce_max_sync): every lane of the warp participates here
+unsigned emu_reduce_max(unsigned mask, unsigned v);
+inline int __reduce_max_sync(unsigned mask, int v) { return (int)(emu_reduce_max(mask, (unsigned)v ^ 0x80000000u) ^ 0x80000000u); }
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return emu_reduce_max(mask, v); }

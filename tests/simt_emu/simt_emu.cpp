@@ -44,6 +44,16 @@ uint64_t emu_shfl(uint64_t bits, int src_lane) {
     pthread_barrier_wait(&w->bar);
     return out;
 }
+unsigned emu_reduce_max(unsigned mask, unsigned v) {
+    Warp* w = tls_warp;
+    w->slot[tls_lane] = v;
+    pthread_barrier_wait(&w->bar);
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i)
+        if ((mask >> i) & 1u) m = w->slot[i] > m ? (unsigned)w->slot[i] : m;
+    pthread_barrier_wait(&w->bar);
+    return m;
+}
 int atomicMin(int* addr, int v) {
     std::atomic_ref<int> a(*addr);
     int old = a.load();

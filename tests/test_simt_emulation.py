@@ -366,3 +366,61 @@ def test_kernel_source_emulated_randomised_configurations(emu):
         criterion = ["generalised", "classic", "strict"][int(rng.integers(0, 3))]
         _case(emu, kind, mkind, D, N, eps, sampler, criterion, seed=1000 + cfg, max_depth=int(rng.integers(2, 7)),
               delta_max=[1000.0, 2.5][int(rng.integers(0, 2))], scale=0.6 if kind == "funnel" else 1.3)
+
+
+# ------------------------------------------------------------------------------------------------ MultinomialTS static kernel
+class EmuMn(C.Structure):
+    _fields_ = [("model_kind", C.c_int32), ("metric_kind", C.c_int32), ("D", C.c_int32), ("N", C.c_int64), ("p0", _vp), ("p1", _vp),
+                ("Minv", _vp), ("cholU", _vp), ("eps", C.c_double), ("n_steps", C.c_int32), ("n_fwd", C.c_int32),
+                ("normal_tape", _vp), ("unif_tape", _vp), ("th_in", _vp), ("g_in", _vp), ("lp_in", _vp), ("th_out", _vp),
+                ("r_out", _vp), ("g_out", _vp), ("lp_out", _vp), ("lk_out", _vp), ("acc", _vp), ("index", _vp)]
+
+
+@pytest.fixture(scope="module")
+def emu_mn(tmp_path_factory):
+    out = tmp_path_factory.mktemp("simt_mn") / "libmn_emu.so"
+    d = os.path.join(ROOT, "tests", "simt_emu")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-x", "c++",
+                    "-I", os.path.join(d, "include"), "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"),
+                    "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"), os.path.join(d, "mn_emu.cpp"),
+                    "-o", str(out)], check=True)
+    return C.CDLL(str(out))
+
+
+def test_multinomial_static_kernel_source_under_emulation_matches_mp50_fixtures(emu_mn):
+    """`multinomial_kernel` (energy pass, inverse-CDF draw, re-materialisation of the drawn point) executed by the emulator
+    on the 50-digit MultinomialTS fixtures of tests/golden/hmc_mp50.json (mixed, all-forward and all-backward splits)."""
+    from tests.helpers import hmc_golden_cases
+
+    done = 0
+    for case in hmc_golden_cases():
+        if case["sampler"] != "multinomial":
+            continue
+        D, N = case["D"], case["N"]
+        kind, mkind = case["model"], case["metric"]
+        p0 = None if case["p0"] is None else np.array(case["p0"])
+        p1 = None if case["p1"] is None else np.array(case["p1"])
+        Minv = None if case["Minv"] is None else np.array(case["Minv"])
+        cholU = None if mkind != "dense" else np.ascontiguousarray(np.linalg.cholesky(Minv))
+        dp1 = None if p1 is None else (1.0 / (p1 * p1) if kind == "diag_gauss" else np.ascontiguousarray(p1))
+        model = oc.Model(KINDS[kind], D, p0, p1 if kind != "dense_gauss" else np.asfortranarray(p1), 0.0)
+        metric = oc.Metric(MKINDS[mkind], None if Minv is None else np.asfortranarray(Minv))
+        th = np.array(case["theta0"])
+        z0 = oc.phasepoint(model, metric, th.T, np.zeros((D, N)))
+        g_in, lp_in = np.ascontiguousarray(z0.lp_gradient.T), np.ascontiguousarray(z0.lp_value)
+        nt, ut = np.array(case["normals"]), np.array(case["variates"])
+        o = {k: np.zeros((N, D)) for k in ("th", "r", "g")}
+        lp_o, lk_o, acc = np.zeros(N), np.zeros(N), np.zeros(N)
+        idx = np.zeros(N, dtype=np.int32)
+        q = EmuMn(model_kind=KINDS[kind], metric_kind=MKINDS[mkind], D=D, N=N, p0=P(p0), p1=P(dp1), Minv=P(Minv), cholU=P(cholU),
+                  eps=case["eps"], n_steps=case["n_steps"], n_fwd=case["n_fwd"], normal_tape=P(nt), unif_tape=P(ut), th_in=P(th),
+                  g_in=P(g_in), lp_in=P(lp_in), th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]), lp_out=P(lp_o), lk_out=P(lk_o),
+                  acc=P(acc), index=P(idx))
+        assert emu_mn.emu_multinomial(C.byref(q)) == 0, case["name"]
+        e = case["expect"]
+        assert (idx == np.array(e["index"])).all(), case["name"]
+        assert rel_err(o["th"], np.array(e["theta"])) < 1e-10 and rel_err(o["r"], np.array(e["r"])) < 1e-10
+        assert np.allclose(acc, e["acceptance_rate"], rtol=1e-10)
+        assert np.allclose(lp_o, e["lp_value"], rtol=1e-10, atol=1e-10) and np.allclose(lk_o, e["lk_value"], rtol=1e-10, atol=1e-10)
+        done += 1
+    assert done == 3
