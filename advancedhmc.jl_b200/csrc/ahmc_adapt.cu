@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kAdaptThreads) adapt_kernel(int D, long long N
     if (threadIdx.x == 0) *counter = 0u;  // re-arm for the next launch
 }
 
+#ifndef AHMC_SIMT_EMULATION  // host launch code (skipped by the CPU SIMT emulation harness, tests/simt_emu/)
 cudaError_t launch_adapt_summary(int D, long long N, const double* theta, long long ld, const double* alpha,
                                  double* out, double* partial, unsigned* counter, int blocks, cudaStream_t st,
                                  int* n_launches) {
@@ -76,6 +77,8 @@ cudaError_t launch_adapt_summary(int D, long long N, const double* theta, long l
     if (n_launches) *n_launches += 2;
     return cudaGetLastError();
 }
+
+#endif  // AHMC_SIMT_EMULATION
 
 // K5b: full second-moment matrix about a given mean, for the pooled WelfordCov (massmatrix.jl:286-340):
 //     out[i + D*j] = sum_c (theta[i, c] - mean[i]) * (theta[j, c] - mean[j])            (symmetric, D x D)
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(256) adapt_cov_kernel(int D, long long N, cons
         }
 }
 
+#ifndef AHMC_SIMT_EMULATION
 cudaError_t launch_adapt_cov(int D, long long N, const double* theta, long long ld, const double* mean, double* out,
                              cudaStream_t st, int* n_launches) {
     const int T = (D + kCovTile - 1) / kCovTile;
@@ -140,5 +144,7 @@ cudaError_t launch_adapt_cov(int D, long long N, const double* theta, long long 
     if (n_launches) *n_launches += 1;
     return cudaGetLastError();
 }
+
+#endif  // AHMC_SIMT_EMULATION
 
 }  // namespace ahmc

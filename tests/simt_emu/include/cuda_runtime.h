@@ -9,7 +9,9 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
-#define __shared__
+#ifndef __shared__
+#define __shared__  // kernels that only use `extern __shared__` arrays; a harness for kernels with STATIC shared
+#endif              // variables defines it as `static` before including this header (blocks run one at a time)
 #define __launch_bounds__(...)
 
 typedef int cudaError_t;
@@ -71,3 +73,8 @@ inline void sincospi(double x, double* s, double* c) {  // CUDA math API; only t
 unsigned emu_reduce_max(unsigned mask, unsigned v);
 inline int __reduce_max_sync(unsigned mask, int v) { return (int)(emu_reduce_max(mask, (unsigned)v ^ 0x80000000u) ^ 0x80000000u); }
 inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return emu_reduce_max(mask, v); }
+
+// ---- block-level primitives
+void __syncthreads();
+inline void __threadfence() {}
+unsigned atomicAdd(unsigned* addr, unsigned v);

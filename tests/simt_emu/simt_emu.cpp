@@ -23,7 +23,11 @@ struct Warp {
 };
 thread_local Warp* tls_warp = nullptr;
 thread_local int tls_lane = 0;
+thread_local pthread_barrier_t* tls_block_bar = nullptr;
 }  // namespace
+
+void __syncthreads() { pthread_barrier_wait(tls_block_bar); }
+unsigned atomicAdd(unsigned* addr, unsigned v) { return std::atomic_ref<unsigned>(*addr).fetch_add(v); }
 
 int emu_lane() { return tls_lane; }
 void emu_syncwarp() { pthread_barrier_wait(&tls_warp->bar); }
@@ -70,6 +74,8 @@ void emu_launch(void (*kernel)(const void*), const void* args, int blocks, int t
     for (int b = 0; b < blocks; ++b) {
         std::vector<Warp> warps(nwarps);
         for (auto& w : warps) pthread_barrier_init(&w.bar, nullptr, 32);
+        pthread_barrier_t block_bar;
+        pthread_barrier_init(&block_bar, nullptr, threads);
         std::vector<std::thread> ts;
         ts.reserve(threads);
         for (int t = 0; t < threads; ++t)
@@ -78,9 +84,11 @@ void emu_launch(void (*kernel)(const void*), const void* args, int blocks, int t
                 blockIdx = {(unsigned)b, 0, 0};
                 tls_warp = &warps[t / 32];
                 tls_lane = t % 32;
+                tls_block_bar = &block_bar;
                 kernel(args);
             });
         for (auto& th : ts) th.join();
         for (auto& w : warps) pthread_barrier_destroy(&w.bar);
+        pthread_barrier_destroy(&block_bar);
     }
 }

@@ -424,3 +424,28 @@ def test_multinomial_static_kernel_source_under_emulation_matches_mp50_fixtures(
         assert np.allclose(lp_o, e["lp_value"], rtol=1e-10, atol=1e-10) and np.allclose(lk_o, e["lk_value"], rtol=1e-10, atol=1e-10)
         done += 1
     assert done == 3
+
+
+def test_adaptor_statistics_kernel_sources_under_emulation(tmp_path):
+    """K5 (`adapt_kernel`: per-block partials, last-block reduction through a device counter) and K5b (`adapt_cov_kernel`:
+    tiled second moment) executed by the emulator (block barriers, static shared variables) vs numpy."""
+    out = tmp_path / "libadapt_emu.so"
+    d = os.path.join(ROOT, "tests", "simt_emu")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-x", "c++",
+                    "-I", os.path.join(d, "include"), "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"),
+                    "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"), os.path.join(d, "adapt_emu.cpp"),
+                    "-o", str(out)], check=True)
+    lib = C.CDLL(str(out))
+    rng = np.random.default_rng(8)
+    for D, N in ((7, 33), (40, 13), (33, 3)):
+        Lm = rng.normal(size=(D, D)) / np.sqrt(D)
+        th = rng.normal(size=(N, D)) @ Lm + rng.normal(size=D)
+        al = rng.uniform(0, 1.4, N)
+        rec, cov = np.zeros(2 + 2 * D), np.zeros((D, D))
+        assert lib.emu_adapt(D, C.c_longlong(N), P(th), P(al), P(rec), P(cov)) == 0
+        mu = th.mean(axis=0)
+        c = th - mu
+        assert rec[0] == N and rec[1] == pytest.approx(np.minimum(1, al).sum(), rel=1e-13)
+        assert np.allclose(rec[2:2 + D], mu, rtol=1e-12) and np.allclose(rec[2 + D:], (c ** 2).sum(axis=0), rtol=1e-11)
+        want = c.T @ c
+        assert np.allclose(cov, want, rtol=1e-11, atol=1e-11 * np.abs(want).max()) and np.array_equal(cov, cov.T)
