@@ -59,6 +59,7 @@ static KernelFn by_layout(int G, int E) {
     if (G == 32 && E == 2) return thunk<MODEL, METRIC, 32, 2, VAR, ADAPT>;
     if (G == 16 && E == 1) return thunk<MODEL, METRIC, 16, 1, VAR, ADAPT>;
     if (G == 32 && E == 4) return thunk<MODEL, METRIC, 32, 4, VAR, ADAPT>;
+    if (G == 32 && E == 8) return thunk<MODEL, METRIC, 32, 8, VAR, ADAPT>;
 #if AHMC_NUTS_ALT_LAYOUT
     if (G == 16 && E == 4) return thunk<MODEL, METRIC, 16, 4, VAR, ADAPT>;
     if (G == 16 && E == 8) return thunk<MODEL, METRIC, 16, 8, VAR, ADAPT>;
@@ -89,6 +90,7 @@ extern "C" int emu_nuts(const EmuNuts* q) {
     else if (D <= 16) G = 16, E = 1;
     else if (D > 32 && D <= 64) G = 32, E = 2;
     else if (D > 64 && D <= 128) G = 32, E = 4;  // the headline layout
+    else if (D > 128 && D <= 256) G = 32, E = 8;  // C5's layout
     else return -1;
 #if AHMC_NUTS_ALT_LAYOUT
     if (D > 64 && D <= 128) G = 16, E = 8;

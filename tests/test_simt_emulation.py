@@ -130,6 +130,7 @@ CASES = [
     ("diag_gauss", "unit", 5, 7, 0.3, "slice", "classic"),
     ("diag_gauss", "diag", 13, 5, 0.25, "multinomial", "generalised"),  # G=16: two chains per warp
     ("diag_gauss", "diag", 128, 2, 0.12, "multinomial", "generalised"),  # G=32, E=4: the headline layout
+    ("dense_gauss", "dense", 200, 1, 0.25, "multinomial", "generalised"),  # G=32, E=8 + dense slab: C5's layout
 ]
 
 
