@@ -66,7 +66,7 @@ constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, ca
 #define AHMC_NUTS_FASTDRAW 0
 #endif
 #ifndef AHMC_NUTS_ALT_LAYOUT
-#define AHMC_NUTS_ALT_LAYOUT 0  // 1: (G, E) = (16, 4) / (16, 8) for 32 < D <= 128 -- staged, see nuts_dispatch
+#define AHMC_NUTS_ALT_LAYOUT 0  // 1: (G, E) = (16, 4) / (16, 8), 2: (8, 8) / (8, 16) for 32 < D <= 128 -- staged, see nuts_dispatch
 #endif
 
 // Occupancy knob: the tree walk is a long chain of dependent, mostly fixed-latency instructions, so throughput
@@ -862,9 +862,12 @@ static cudaError_t nuts_layout(const NutsArgs& a, cudaStream_t st, int G, int E)
     if (G == 32 && E == 4) return launch_nuts_v<MODEL, METRIC, 32, 4, VAR, ADAPT>(a, st);
     if (G == 32 && E == 8) return launch_nuts_v<MODEL, METRIC, 32, 8, VAR, ADAPT>(a, st);
     if (G == 32 && E == 16) return launch_nuts_v<MODEL, METRIC, 32, 16, VAR, ADAPT>(a, st);
-#if AHMC_NUTS_ALT_LAYOUT
+#if AHMC_NUTS_ALT_LAYOUT == 1
     if (G == 16 && E == 4) return launch_nuts_v<MODEL, METRIC, 16, 4, VAR, ADAPT>(a, st);
     if (G == 16 && E == 8) return launch_nuts_v<MODEL, METRIC, 16, 8, VAR, ADAPT>(a, st);
+#elif AHMC_NUTS_ALT_LAYOUT == 2
+    if (G == 8 && E == 8) return launch_nuts_v<MODEL, METRIC, 8, 8, VAR, ADAPT>(a, st);
+    if (G == 8 && E == 16) return launch_nuts_v<MODEL, METRIC, 8, 16, VAR, ADAPT>(a, st);
 #endif
     return cudaErrorInvalidValue;
 }
@@ -877,8 +880,14 @@ static cudaError_t nuts_dispatch(const NutsArgs& a, cudaStream_t st) {
 #if AHMC_NUTS_ALT_LAYOUT
     // staged A/B knob (scripts/build_variants.sh altlayout): two chains per warp for 32 < D <= 128 (16 lanes x 4 or 8
     // coordinates), so that the per-chain scalar bookkeeping -- ~2/3 of K3's instructions -- is issued once per TWO chains
+#if AHMC_NUTS_ALT_LAYOUT == 1
     if (a.D > 32 && a.D <= 64) G = 16, E = 4;
     else if (a.D > 64 && a.D <= 128) G = 16, E = 8;
+#else  // 2: FOUR chains per warp (8 lanes x 8 / 16 coordinates); the vectors no longer fit the register file and the
+       // compiler keeps part of them in (L1-resident) local memory -- an experiment in trading that for 4x fewer scalar issues
+    if (a.D > 32 && a.D <= 64) G = 8, E = 8;
+    else if (a.D > 64 && a.D <= 128) G = 8, E = 16;
+#endif
 #endif
     if (DIAG_ONLY) {
         if (a.metric.kind != AHMC_METRIC_DIAG) return cudaErrorInvalidValue;

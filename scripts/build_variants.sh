@@ -15,6 +15,7 @@ for tag in "$@"; do
     fastdraw) DEF="-DAHMC_NUTS_FASTDRAW=1" ;;
     altlayout) DEF="-DAHMC_NUTS_ALT_LAYOUT=1" ;;
     fastdraw_altlayout) DEF="-DAHMC_NUTS_FASTDRAW=1 -DAHMC_NUTS_ALT_LAYOUT=1" ;;
+    fastdraw_altlayout2) DEF="-DAHMC_NUTS_FASTDRAW=1 -DAHMC_NUTS_ALT_LAYOUT=2" ;;
     *) echo "unknown tag $tag"; exit 1 ;;
   esac
   ( for tu in ahmc_nuts ahmc_nuts_var ahmc_nuts_adapt; do

@@ -14,7 +14,7 @@ echo "variant pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/fastdraw_pytest.log
 timeout 300 python scripts/nuts_ab.py > gpurun_out/fastdraw_ab_default.jsonl 2>&1
 AHMC_B200_LIB=$PWD/$V timeout 300 python scripts/nuts_ab.py > gpurun_out/fastdraw_ab_variant.jsonl 2>&1
 tail -4 gpurun_out/fastdraw_pytest.log; echo "--- default"; grep '^{' gpurun_out/fastdraw_ab_default.jsonl; echo "--- fastdraw"; grep '^{' gpurun_out/fastdraw_ab_variant.jsonl
-for tag in altlayout fastdraw_altlayout; do   # optional: two chains per warp for 32 < D <= 128
+for tag in altlayout fastdraw_altlayout fastdraw_altlayout2; do   # optional: two chains per warp for 32 < D <= 128
   W=advancedhmc.jl_b200/_variants/libahmc_b200_$tag.so
   [ -f "$W" ] || continue
   AHMC_B200_LIB=$PWD/$W timeout 900 python -m pytest tests -m gpu -q -k "nuts or in_launch or mp50 or c3 or c4" 2>&1 | tail -3 > gpurun_out/${tag}_pytest.log

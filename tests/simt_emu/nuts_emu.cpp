@@ -60,9 +60,12 @@ static KernelFn by_layout(int G, int E) {
     if (G == 16 && E == 1) return thunk<MODEL, METRIC, 16, 1, VAR, ADAPT>;
     if (G == 32 && E == 4) return thunk<MODEL, METRIC, 32, 4, VAR, ADAPT>;
     if (G == 32 && E == 8) return thunk<MODEL, METRIC, 32, 8, VAR, ADAPT>;
-#if AHMC_NUTS_ALT_LAYOUT
+#if AHMC_NUTS_ALT_LAYOUT == 1
     if (G == 16 && E == 4) return thunk<MODEL, METRIC, 16, 4, VAR, ADAPT>;
     if (G == 16 && E == 8) return thunk<MODEL, METRIC, 16, 8, VAR, ADAPT>;
+#elif AHMC_NUTS_ALT_LAYOUT == 2
+    if (G == 8 && E == 8) return thunk<MODEL, METRIC, 8, 8, VAR, ADAPT>;
+    if (G == 8 && E == 16) return thunk<MODEL, METRIC, 8, 16, VAR, ADAPT>;
 #endif
     return nullptr;
 }
@@ -92,11 +95,15 @@ extern "C" int emu_nuts(const EmuNuts* q) {
     else if (D > 64 && D <= 128) G = 32, E = 4;  // the headline layout
     else if (D > 128 && D <= 256) G = 32, E = 8;  // C5's layout
     else return -1;
-#if AHMC_NUTS_ALT_LAYOUT
+#if AHMC_NUTS_ALT_LAYOUT == 1
     if (D > 64 && D <= 128) G = 16, E = 8;
+#elif AHMC_NUTS_ALT_LAYOUT == 2
+    if (D > 64 && D <= 128) G = 8, E = 16;
 #endif
-#if AHMC_NUTS_ALT_LAYOUT
+#if AHMC_NUTS_ALT_LAYOUT == 1
     if (D > 32 && D <= 64) G = 16, E = 4;
+#elif AHMC_NUTS_ALT_LAYOUT == 2
+    if (D > 32 && D <= 64) G = 8, E = 8;
 #endif
     NutsArgs a{};
     a.model = ModelDev{q->model_kind, D, q->p0, q->p1, q->c0};

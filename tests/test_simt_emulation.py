@@ -40,10 +40,10 @@ def _build(tmp, fastdraw, altlayout=False):
     if fastdraw:
         cmd.insert(1, "-DAHMC_NUTS_FASTDRAW=1")
     if altlayout:
-        cmd.insert(1, "-DAHMC_NUTS_ALT_LAYOUT=1")
+        cmd.insert(1, f"-DAHMC_NUTS_ALT_LAYOUT={int(altlayout)}")
     subprocess.run(cmd, check=True)
     lib = C.CDLL(str(out))
-    assert lib.emu_fastdraw() == (1 if fastdraw else 0) and lib.emu_altlayout() == (1 if altlayout else 0)
+    assert lib.emu_fastdraw() == (1 if fastdraw else 0) and lib.emu_altlayout() == int(altlayout)
     return lib
 
 
@@ -59,7 +59,12 @@ def emu_fast(tmp_path_factory):
 
 @pytest.fixture(scope="module")
 def emu_alt(tmp_path_factory):
-    return _build(tmp_path_factory.mktemp("simt_alt"), True, altlayout=True)
+    return _build(tmp_path_factory.mktemp("simt_alt"), True, altlayout=1)
+
+
+@pytest.fixture(scope="module")
+def emu_alt2(tmp_path_factory):
+    return _build(tmp_path_factory.mktemp("simt_alt2"), True, altlayout=2)
 
 
 P = lambda a: None if a is None else a.ctypes.data_as(_vp)
@@ -163,6 +168,14 @@ def test_staged_alt_layout_two_chains_per_warp_matches_oracle(emu_alt, kind, mki
     """-DAHMC_NUTS_ALT_LAYOUT=1 (+ FASTDRAW): 16 lanes x 4 / 8 coordinates per chain, i.e. two chains per warp for
     32 < D <= 128 -- staged for the round-2 A/B; an odd chain count leaves half a warp idle."""
     _case(emu_alt, kind, mkind, D, N, eps, sampler, criterion, seed=9 + D, scale=0.5 if kind == "funnel" else 1.0)
+
+
+@pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion", [
+    ("diag_gauss", "diag", 100, 7, 0.15, "multinomial", "generalised"), ("funnel", "diag", 50, 6, 0.1, "multinomial", "generalised")],
+    ids=["D100-8x16", "funnel-D50-8x8"])
+def test_staged_alt_layout_four_chains_per_warp_matches_oracle(emu_alt2, kind, mkind, D, N, eps, sampler, criterion):
+    """-DAHMC_NUTS_ALT_LAYOUT=2: 8 lanes x 8 / 16 coordinates per chain (four chains per warp for 32 < D <= 128)."""
+    _case(emu_alt2, kind, mkind, D, N, eps, sampler, criterion, seed=19 + D, scale=0.5 if kind == "funnel" else 1.0)
 
 
 def test_staged_fastdraw_variant_divergent_and_max_depth(emu_fast):
