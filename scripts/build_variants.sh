@@ -1,7 +1,12 @@
 #!/bin/bash
 # A/B builds of the NUTS kernel: advancedhmc.jl_b200/_variants/libahmc_b200_<tag>.so, selected at run time with
-# AHMC_B200_LIB=<path>.  Usage: scripts/build_variants.sh minb4 fastdraw ...   (tags: minbN -> -DAHMC_NUTS_MINB=N,
-# fastdraw -> -DAHMC_NUTS_FASTDRAW=1, altlayout -> -DAHMC_NUTS_ALT_LAYOUT=1, fastdraw_altlayout -> both).  The three NUTS translation units are recompiled, the rest is reused.
+# AHMC_B200_LIB=<path>.  A tag is a '+'-joined list of knobs:
+#   minbN      -DAHMC_NUTS_MINB=N          resident 4-warp CTAs per SM the register cap aims at (default 3)
+#   fastdraw   -DAHMC_NUTS_FASTDRAW=1      lane-parallel variates, log-free (m, w) weights, deferred sum_alpha
+#   altlayout1 -DAHMC_NUTS_ALT_LAYOUT=1    two chains per warp for 32 < D <= 128
+#   altlayout2 -DAHMC_NUTS_ALT_LAYOUT=2    four chains per warp for 32 < D <= 128
+# e.g.  scripts/build_variants.sh fastdraw fastdraw+altlayout1 fastdraw+minb4
+# The three NUTS translation units are recompiled, everything else is reused from the default build.
 set -e
 cd "$(dirname "$0")/.."
 python advancedhmc.jl_b200/build.py
@@ -10,14 +15,16 @@ O=${AHMC_OBJ_DIR:-/tmp/ahmc_b200_obj}
 mkdir -p $P/_variants
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -O3"
 for tag in "$@"; do
-  case $tag in
-    minb*) DEF="-DAHMC_NUTS_MINB=${tag#minb}" ;;
-    fastdraw) DEF="-DAHMC_NUTS_FASTDRAW=1" ;;
-    altlayout) DEF="-DAHMC_NUTS_ALT_LAYOUT=1" ;;
-    fastdraw_altlayout) DEF="-DAHMC_NUTS_FASTDRAW=1 -DAHMC_NUTS_ALT_LAYOUT=1" ;;
-    fastdraw_altlayout2) DEF="-DAHMC_NUTS_FASTDRAW=1 -DAHMC_NUTS_ALT_LAYOUT=2" ;;
-    *) echo "unknown tag $tag"; exit 1 ;;
-  esac
+  DEF=""
+  for knob in ${tag//+/ }; do
+    case $knob in
+      minb*) DEF="$DEF -DAHMC_NUTS_MINB=${knob#minb}" ;;
+      fastdraw) DEF="$DEF -DAHMC_NUTS_FASTDRAW=1" ;;
+      altlayout1|altlayout) DEF="$DEF -DAHMC_NUTS_ALT_LAYOUT=1" ;;
+      altlayout2) DEF="$DEF -DAHMC_NUTS_ALT_LAYOUT=2" ;;
+      *) echo "unknown knob $knob"; exit 1 ;;
+    esac
+  done
   ( for tu in ahmc_nuts ahmc_nuts_var ahmc_nuts_adapt; do
       nvcc $FLAGS $DEF -c $P/csrc/$tu.cu -o $O/${tu}_$tag.o &
     done; wait
