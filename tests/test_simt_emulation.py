@@ -463,3 +463,47 @@ def test_adaptor_statistics_kernel_sources_under_emulation(tmp_path):
         assert np.allclose(rec[2:2 + D], mu, rtol=1e-12) and np.allclose(rec[2 + D:], (c ** 2).sum(axis=0), rtol=1e-11)
         want = c.T @ c
         assert np.allclose(cov, want, rtol=1e-11, atol=1e-11 * np.abs(want).max()) and np.array_equal(cov, cov.T)
+
+
+def test_trajectory_kernel_emulated_nonfinite_freeze_tempering_and_fast_path_fallback(emu_lf):
+    """K1 under emulation on the awkward inputs: a chain that overflows freezes on its own at the break step with -Inf
+    energies while its warp-mates finish (integrator.jl:252-258, hamiltonian.jl:95-104); tempering (exact path,
+    integrator.jl:198-209); a chain whose magnitude defeats the fast path's proof is redone by the exact path in-launch."""
+    rng = np.random.default_rng(31)
+    # (a) per-chain freeze, std-normal / unit (fast-path kernel with in-launch exact fallback)
+    D, N, n = 3, 6, 5
+    model, metric = oc.Model(oc.STD_NORMAL, D), oc.Metric(oc.UNIT)
+    th, r = np.ones((N, D)), np.ones((N, D))
+    th[2] = 1e200
+    th[4] = 1e120  # large but finite throughout: defeats the magnitude proof, must equal the exact result
+    z0 = oc.phasepoint(model, metric, th.T, r.T)
+    zo, so, do = oc.leapfrog(model, metric, 0.1, z0, n)
+    o = {k: np.zeros((N, D)) for k in ("th", "r", "g", "dr")}
+    lp_o, lk_o = np.zeros(N), np.zeros(N)
+    status, done = np.zeros(N, dtype=np.uint32), np.zeros(N, dtype=np.int32)
+    g_in, lp_in = np.ascontiguousarray(z0.lp_gradient.T), np.ascontiguousarray(z0.lp_value)
+    q = EmuLf(model_kind=oc.STD_NORMAL, metric_kind=oc.UNIT, D=D, N=N, p0=None, p1=None, c0=0.0, Minv=None, minv_stride=0, cholU=None,
+              eps=0.1, eps_chain=None, n_steps=n, fwd=1, temper_alpha=0.0, th_in=P(th), r_in=P(r), g_in=P(g_in), lp_in=P(lp_in),
+              th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]), lp_out=P(lp_o), lk_out=P(lk_o), dr_out=P(o["dr"]),
+              status=P(status), steps_done=P(done), flags=0, hmc=0)
+    assert emu_lf.emu_leapfrog(C.byref(q)) == 0
+    assert list(status) == list(so) and list(done) == list(do) and done[2] == 1 and status[2] == 1
+    ok = status == 0
+    assert rel_err(o["th"][ok].T, zo.theta[:, ok]) < 1e-10 and np.allclose(lp_o[ok], zo.lp_value[ok], rtol=1e-10)
+    assert lp_o[2] == -np.inf and zo.lp_value[2] == -np.inf
+    # (b) tempering on a diagonal Gaussian (exact path)
+    D, N, n = 6, 5, 8
+    model, metric, p0, dp1, Minv, cholU = _lf_system("diag_gauss", "diag", D, rng)
+    th, r = rng.normal(size=(N, D)), rng.normal(size=(N, D))
+    z0 = oc.phasepoint(model, metric, th.T, r.T)
+    zo, so, do = oc.leapfrog(model, metric, 0.1, z0, n, temper_alpha=1.05)
+    o = {k: np.zeros((N, D)) for k in ("th", "r", "g", "dr")}
+    lp_o, lk_o = np.zeros(N), np.zeros(N)
+    g_in, lp_in = np.ascontiguousarray(z0.lp_gradient.T), np.ascontiguousarray(z0.lp_value)
+    q = EmuLf(model_kind=oc.DIAG_GAUSS, metric_kind=oc.DIAG, D=D, N=N, p0=P(p0), p1=P(dp1), c0=0.0, Minv=P(Minv), minv_stride=0,
+              cholU=None, eps=0.1, eps_chain=None, n_steps=n, fwd=1, temper_alpha=1.05, th_in=P(th), r_in=P(r), g_in=P(g_in),
+              lp_in=P(lp_in), th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]), lp_out=P(lp_o), lk_out=P(lk_o), dr_out=P(o["dr"]),
+              status=None, steps_done=None, flags=0, hmc=0)
+    assert emu_lf.emu_leapfrog(C.byref(q)) == 0
+    assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10
+    assert np.allclose(lk_o, zo.lk_value, rtol=1e-10, atol=1e-10)
