@@ -65,6 +65,19 @@ constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, ca
 #ifndef AHMC_NUTS_FASTDRAW
 #define AHMC_NUTS_FASTDRAW 0
 #endif
+// AHMC_NUTS_FULLTILE (default 0, staged like the knobs above): an extra instantiation for D == G * E (e.g. 128 = 32 x 4)
+// in which D is a compile-time constant -- the `d < D` guard of every vector load / store and most of the workspace
+// address arithmetic fold away.
+#ifndef AHMC_NUTS_FULLTILE
+#define AHMC_NUTS_FULLTILE 0
+#endif
+#if AHMC_NUTS_FULLTILE
+#define AHMC_FULL_TPARAM , bool FULL
+#define AHMC_FULL_TARG(x) , x
+#else
+#define AHMC_FULL_TPARAM
+#define AHMC_FULL_TARG(x)
+#endif
 #ifndef AHMC_NUTS_ALT_LAYOUT
 #define AHMC_NUTS_ALT_LAYOUT 0  // 1: (G, E) = (16, 4) / (16, 8), 2: (8, 8) / (8, 16) for 32 < D <= 128 -- staged, see nuts_dispatch
 #endif
@@ -80,7 +93,7 @@ constexpr int nuts_min_blocks() { return E <= 4 ? AHMC_NUTS_MINB : (E <= 8 ? 2 :
 // VAR = false: MultinomialTS + GeneralisedNoUTurn only (what `NUTS(delta)` builds); VAR = true additionally compiles
 // SliceTS (trajectory.jl:102-109,144-145,164-166,178-189,202,500-502) and the Classic / StrictGeneralised criteria
 // (trajectory.jl:551-557, 579-613), selected at run time by a.sampler / a.criterion.
-template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
+template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT AHMC_FULL_TPARAM>
 __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kernel(const NutsArgs a) {
     // Dense metric: a merge needs dH/dr = M^-1 r of the pending half's first leaf -- a D x D product.  The default family
     // caches the vector (slot 1 of the level holds M^-1 r_first instead of r_first) so merges do no dense product at all.
@@ -95,7 +108,11 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     const long long chain0 = (long long)blockIdx.x * kGroups + grp_in_block;
     const bool valid = chain0 < a.N;
     const long long chain = valid ? chain0 : a.N - 1;
+#if AHMC_NUTS_FULLTILE
+    const int D = FULL ? G * E : a.D;
+#else
     const int D = a.D;
+#endif
     const bool dense = (MODEL == AHMC_MODEL_DENSE_GAUSS) || (METRIC == AHMC_METRIC_DENSE);
     double* xs = smem + (size_t)grp_in_block * D;  // dense slab (unused otherwise)
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
@@ -843,12 +860,23 @@ static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
     size_t sm = smem_bytes(MODEL, METRIC, a.D, G) +
                 (size_t)chains_per_block * maxd * (kLevelScalars + (AHMC_NUTS_FASTDRAW ? 1 : 0)) * sizeof(double);
+#if AHMC_NUTS_FULLTILE
+    if (a.D == G * E) {
+        if (sm > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (e != cudaSuccess) return e;
+        }
+        nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+        return cudaGetLastError();
+    }
+#endif
     if (sm > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT>,
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT AHMC_FULL_TARG(false)>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
     }
-    nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT AHMC_FULL_TARG(false)><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 #   fastdraw   -DAHMC_NUTS_FASTDRAW=1      lane-parallel variates, log-free (m, w) weights, deferred sum_alpha
 #   altlayout1 -DAHMC_NUTS_ALT_LAYOUT=1    two chains per warp for 32 < D <= 128
 #   altlayout2 -DAHMC_NUTS_ALT_LAYOUT=2    four chains per warp for 32 < D <= 128
+#   fulltile   -DAHMC_NUTS_FULLTILE=1      extra instantiation with a compile-time D for D == G * E
 # e.g.  scripts/build_variants.sh fastdraw fastdraw+altlayout1 fastdraw+minb4
 # The three NUTS translation units are recompiled, everything else is reused from the default build.
 set -e
@@ -22,6 +23,7 @@ for tag in "$@"; do
       fastdraw) DEF="$DEF -DAHMC_NUTS_FASTDRAW=1" ;;
       altlayout1|altlayout) DEF="$DEF -DAHMC_NUTS_ALT_LAYOUT=1" ;;
       altlayout2) DEF="$DEF -DAHMC_NUTS_ALT_LAYOUT=2" ;;
+      fulltile) DEF="$DEF -DAHMC_NUTS_FULLTILE=1" ;;
       *) echo "unknown knob $knob"; exit 1 ;;
     esac
   done

@@ -48,7 +48,16 @@ struct EmuNuts {
 };
 
 template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
-static void thunk(const void* p) { nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT>(*static_cast<const NutsArgs*>(p)); }
+static void thunk(const void* p) {
+    const NutsArgs& a = *static_cast<const NutsArgs*>(p);
+#if AHMC_NUTS_FULLTILE
+    if (a.D == G * E) {  // the full-tile instantiation (D a compile-time constant), like launch_nuts_v
+        nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true>(a);
+        return;
+    }
+#endif
+    nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT AHMC_FULL_TARG(false)>(a);
+}
 
 typedef void (*KernelFn)(const void*);
 
@@ -84,6 +93,7 @@ static KernelFn by_model(int model, int metric, int G, int E) {
 
 extern "C" int emu_fastdraw() { return AHMC_NUTS_FASTDRAW; }
 extern "C" int emu_altlayout() { return AHMC_NUTS_ALT_LAYOUT; }
+extern "C" int emu_fulltile() { return AHMC_NUTS_FULLTILE; }
 
 extern "C" int emu_nuts(const EmuNuts* q) {
     int G, E;

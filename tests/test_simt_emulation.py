@@ -31,7 +31,7 @@ class EmuNuts(C.Structure):
                 ("adapt_metric", C.c_int32), ("n_min", C.c_int32), ("eps_rw", _vp), ("minv_rw", _vp), ("eps_trace", _vp)]
 
 
-def _build(tmp, fastdraw, altlayout=False):
+def _build(tmp, fastdraw, altlayout=False, fulltile=False):
     out = tmp / ("libnuts_emu_fast.so" if fastdraw else "libnuts_emu.so")
     d = os.path.join(ROOT, "tests", "simt_emu")
     cmd = ["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-I", os.path.join(d, "include"),
@@ -41,6 +41,8 @@ def _build(tmp, fastdraw, altlayout=False):
         cmd.insert(1, "-DAHMC_NUTS_FASTDRAW=1")
     if altlayout:
         cmd.insert(1, f"-DAHMC_NUTS_ALT_LAYOUT={int(altlayout)}")
+    if fulltile:
+        cmd.insert(1, "-DAHMC_NUTS_FULLTILE=1")
     subprocess.run(cmd, check=True)
     lib = C.CDLL(str(out))
     assert lib.emu_fastdraw() == (1 if fastdraw else 0) and lib.emu_altlayout() == int(altlayout)
@@ -60,6 +62,13 @@ def emu_fast(tmp_path_factory):
 @pytest.fixture(scope="module")
 def emu_alt(tmp_path_factory):
     return _build(tmp_path_factory.mktemp("simt_alt"), True, altlayout=1)
+
+
+@pytest.fixture(scope="module")
+def emu_full(tmp_path_factory):
+    lib = _build(tmp_path_factory.mktemp("simt_full"), True, fulltile=True)
+    assert lib.emu_fulltile() == 1
+    return lib
 
 
 @pytest.fixture(scope="module")
@@ -176,6 +185,17 @@ def test_staged_alt_layout_two_chains_per_warp_matches_oracle(emu_alt, kind, mki
 def test_staged_alt_layout_four_chains_per_warp_matches_oracle(emu_alt2, kind, mkind, D, N, eps, sampler, criterion):
     """-DAHMC_NUTS_ALT_LAYOUT=2: 8 lanes x 8 / 16 coordinates per chain (four chains per warp for 32 < D <= 128)."""
     _case(emu_alt2, kind, mkind, D, N, eps, sampler, criterion, seed=19 + D, scale=0.5 if kind == "funnel" else 1.0)
+
+
+@pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion", [
+    ("diag_gauss", "diag", 128, 3, 0.12, "multinomial", "generalised"), ("diag_gauss", "diag", 8, 9, 0.25, "multinomial", "strict"),
+    ("funnel", "diag", 4, 10, 0.3, "slice", "generalised"), ("dense_gauss", "dense", 8, 5, 0.3, "multinomial", "generalised"),
+    ("diag_gauss", "diag", 7, 9, 0.25, "multinomial", "generalised")],
+    ids=["D128-full", "D8-full-strict", "D4-full-slice", "D8-full-dense", "D7-ragged"])
+def test_staged_full_tile_instantiation_matches_oracle(emu_full, kind, mkind, D, N, eps, sampler, criterion):
+    """-DAHMC_NUTS_FULLTILE=1 (+ FASTDRAW): D == G * E takes the instantiation with a compile-time D (no `d < D` guards);
+    ragged D still takes the general one."""
+    _case(emu_full, kind, mkind, D, N, eps, sampler, criterion, seed=29 + D, scale=0.5 if kind == "funnel" else 1.0)
 
 
 def test_staged_fastdraw_variant_divergent_and_max_depth(emu_fast):
