@@ -31,49 +31,56 @@ class EmuNuts(C.Structure):
                 ("adapt_metric", C.c_int32), ("n_min", C.c_int32), ("eps_rw", _vp), ("minv_rw", _vp), ("eps_trace", _vp)]
 
 
-def _build(tmp, fastdraw, altlayout=False, fulltile=False):
-    out = tmp / ("libnuts_emu_fast.so" if fastdraw else "libnuts_emu.so")
+_NUTS_VARIANTS = {  # name -> compile-time knobs of the NUTS harness
+    "default": [], "fast": ["-DAHMC_NUTS_FASTDRAW=1"], "alt": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=1"],
+    "alt2": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=2"], "full": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_FULLTILE=1"]}
+
+
+@pytest.fixture(scope="module")
+def _nuts_libs(tmp_path_factory):
+    """all NUTS harness variants, compiled concurrently once per test module"""
+    tmp = tmp_path_factory.mktemp("simt_nuts")
     d = os.path.join(ROOT, "tests", "simt_emu")
-    cmd = ["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-I", os.path.join(d, "include"),
-           "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
-           os.path.join(d, "simt_emu.cpp"), os.path.join(d, "nuts_emu.cpp"), "-o", str(out)]
-    if fastdraw:
-        cmd.insert(1, "-DAHMC_NUTS_FASTDRAW=1")
-    if altlayout:
-        cmd.insert(1, f"-DAHMC_NUTS_ALT_LAYOUT={int(altlayout)}")
-    if fulltile:
-        cmd.insert(1, "-DAHMC_NUTS_FULLTILE=1")
-    subprocess.run(cmd, check=True)
-    lib = C.CDLL(str(out))
-    assert lib.emu_fastdraw() == (1 if fastdraw else 0) and lib.emu_altlayout() == int(altlayout)
-    return lib
+    procs = {}
+    for name, defs in _NUTS_VARIANTS.items():
+        out = tmp / f"libnuts_emu_{name}.so"
+        cmd = ["g++", *defs, "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-I", os.path.join(d, "include"),
+               "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+               os.path.join(d, "simt_emu.cpp"), os.path.join(d, "nuts_emu.cpp"), "-o", str(out)]
+        procs[name] = (subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True), out)
+    libs = {}
+    for name, (pr, out) in procs.items():
+        _, err = pr.communicate()
+        assert pr.returncode == 0, err[-2000:]
+        libs[name] = C.CDLL(str(out))
+    assert libs["default"].emu_fastdraw() == 0 and libs["fast"].emu_fastdraw() == 1
+    assert libs["alt"].emu_altlayout() == 1 and libs["alt2"].emu_altlayout() == 2 and libs["full"].emu_fulltile() == 1
+    return libs
 
 
 @pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    return _build(tmp_path_factory.mktemp("simt"), False)
+def emu(_nuts_libs):
+    return _nuts_libs["default"]
 
 
 @pytest.fixture(scope="module")
-def emu_fast(tmp_path_factory):
-    return _build(tmp_path_factory.mktemp("simt_fast"), True)
+def emu_fast(_nuts_libs):
+    return _nuts_libs["fast"]
 
 
 @pytest.fixture(scope="module")
-def emu_alt(tmp_path_factory):
-    return _build(tmp_path_factory.mktemp("simt_alt"), True, altlayout=1)
+def emu_alt(_nuts_libs):
+    return _nuts_libs["alt"]
 
 
 @pytest.fixture(scope="module")
-def emu_full(tmp_path_factory):
-    lib = _build(tmp_path_factory.mktemp("simt_full"), True, fulltile=True)
-    assert lib.emu_fulltile() == 1
-    return lib
+def emu_full(_nuts_libs):
+    return _nuts_libs["full"]
 
 
 @pytest.fixture(scope="module")
-def emu_alt2(tmp_path_factory):
-    return _build(tmp_path_factory.mktemp("simt_alt2"), True, altlayout=2)
+def emu_alt2(_nuts_libs):
+    return _nuts_libs["alt2"]
 
 
 P = lambda a: None if a is None else a.ctypes.data_as(_vp)
