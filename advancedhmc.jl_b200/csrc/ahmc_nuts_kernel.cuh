@@ -78,6 +78,12 @@ constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, ca
 #define AHMC_FULL_TPARAM
 #define AHMC_FULL_TARG(x)
 #endif
+// AHMC_NUTS_RELOAD_COEF (default 0, staged): the model / metric coefficient vectors (mean, 1/s^2, M^-1: up to 3E doubles
+// per lane) are re-read from L1/L2 where they are used instead of living in registers for the whole kernel -- the register
+// diet that occupancy 4 (AHMC_NUTS_MINB=4, 128 registers) needs.
+#ifndef AHMC_NUTS_RELOAD_COEF
+#define AHMC_NUTS_RELOAD_COEF 0
+#endif
 #ifndef AHMC_NUTS_ALT_LAYOUT
 #define AHMC_NUTS_ALT_LAYOUT 0  // 1: (G, E) = (16, 4) / (16, 8), 2: (8, 8) / (8, 16) for 32 < D <= 128 -- staged, see nuts_dispatch
 #endif
@@ -146,6 +152,21 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     MetricOps<METRIC, G, E> me;
     mo.load(a.model, l, D);
     me.load(a.metric, chain, l, D);
+#if AHMC_NUTS_RELOAD_COEF
+    // re-materialise the coefficient registers from memory; the pointers are laundered through an empty asm so that
+    // the compiler can neither hoist the loads out of the leaf loop nor keep the values alive across it
+    auto reload_model = [&]() {
+        ModelDev md = a.model;
+        asm volatile("" : "+l"(md.p0), "+l"(md.p1));
+        mo.load(md, l, D);
+    };
+    auto reload_metric = [&]() {
+        if (ADAPT) return;  // the adaptive family's M^-1 is per-chain state owned by the registers
+        MetricDev mt = a.metric;
+        asm volatile("" : "+l"(mt.Minv));
+        me.load(mt, chain, l, D);
+    };
+#endif
 
     int nexp = 0, ndir = 0;
     uint64_t off = a.rng.offset;  // Philox transition counter of the transition this group is working on
@@ -266,6 +287,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 } else {
                     philox_normals<G, E>(a.rng.seed, off, chain, l, D, rn);
                 }
+#if AHMC_NUTS_RELOAD_COEF
+                reload_metric();
+#endif
                 me.rand_momentum(rn, l);
                 if (a.rng.partial_alpha != 0.0) {  // PartialMomentumRefreshment (hamiltonian.jl:243-254)
                     double rp[E];
@@ -453,6 +477,10 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         if (!__any_sync(FULL, in_sub)) break;
 
         // ---------------------------------------------------------------- (B) one leaf (:638-647)
+#if AHMC_NUTS_RELOAD_COEF
+        reload_model();
+        reload_metric();
+#endif
         leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, v > 0 ? eps_c : -eps_c, dr, xs, l);
         const double nE = s.lp + s.lk;  // neg_energy(z')
         const double H1 = -nE;
@@ -567,6 +595,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                     for (int e = 0; e < E; ++e) t1[e] = 0.0;
                     if (do_comb) vload_nc<G, E>(t1, L + D, l, D);
                 } else {
+#if AHMC_NUTS_RELOAD_COEF
+                    reload_metric();
+#endif
                     me.dHdr(rf_p, t1, xs, l);
                 }
                 if (VAR && crit == 1) {
@@ -796,6 +827,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 vstore<G, E>(edge + 2 * (long long)D, s.g, l, D);
                 vload_nc<G, E>(r_other, other + D, l, D);
             }
+#if AHMC_NUTS_RELOAD_COEF
+            reload_metric();
+#endif
             me.dHdr(r_other, t1, xs, l);
             double d1 = 0.0, d2 = 0.0;
             bool uturn_top;

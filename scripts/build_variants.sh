@@ -6,6 +6,7 @@
 #   altlayout1 -DAHMC_NUTS_ALT_LAYOUT=1    two chains per warp for 32 < D <= 128
 #   altlayout2 -DAHMC_NUTS_ALT_LAYOUT=2    four chains per warp for 32 < D <= 128
 #   fulltile   -DAHMC_NUTS_FULLTILE=1      extra instantiation with a compile-time D for D == G * E
+#   reloadcoef -DAHMC_NUTS_RELOAD_COEF=1   model / metric coefficients re-read where used instead of held in registers
 # e.g.  scripts/build_variants.sh fastdraw fastdraw+altlayout1 fastdraw+minb4
 # The three NUTS translation units are recompiled, everything else is reused from the default build.
 set -e
@@ -24,6 +25,7 @@ for tag in "$@"; do
       altlayout1|altlayout) DEF="$DEF -DAHMC_NUTS_ALT_LAYOUT=1" ;;
       altlayout2) DEF="$DEF -DAHMC_NUTS_ALT_LAYOUT=2" ;;
       fulltile) DEF="$DEF -DAHMC_NUTS_FULLTILE=1" ;;
+      reloadcoef) DEF="$DEF -DAHMC_NUTS_RELOAD_COEF=1" ;;
       *) echo "unknown knob $knob"; exit 1 ;;
     esac
   done

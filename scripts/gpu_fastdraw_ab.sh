@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round-2 starter: validate and time the staged NUTS variants against the default build.
 #   1. HERE, before gpurun (the variant .so files travel with the snapshot, ~50 MB of push each):
-#        scripts/build_variants.sh fastdraw fastdraw+fulltile fastdraw+fulltile+altlayout1 fastdraw+altlayout2 fastdraw+fulltile+minb4
+#        scripts/build_variants.sh fastdraw fastdraw+fulltile fastdraw+fulltile+altlayout1 fastdraw+altlayout2 \
+#            fastdraw+fulltile+reloadcoef+minb4
 #   2. gpurun --timeout 2400 -- 'bash scripts/gpu_fastdraw_ab.sh'
 # For every variant found: the GPU parity tests that touch NUTS run with AHMC_B200_LIB pointing at it, then
 # scripts/nuts_ab.py times it.  Outputs -> gpurun_out/ab_<tag>_*.  Make a knob the default (flip the macro in

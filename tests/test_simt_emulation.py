@@ -33,7 +33,8 @@ class EmuNuts(C.Structure):
 
 _NUTS_VARIANTS = {  # name -> compile-time knobs of the NUTS harness
     "default": [], "fast": ["-DAHMC_NUTS_FASTDRAW=1"], "alt": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=1"],
-    "alt2": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=2"], "full": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_FULLTILE=1"]}
+    "alt2": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=2"],
+    "full": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_FULLTILE=1", "-DAHMC_NUTS_RELOAD_COEF=1"]}
 
 
 @pytest.fixture(scope="module")
@@ -200,8 +201,8 @@ def test_staged_alt_layout_four_chains_per_warp_matches_oracle(emu_alt2, kind, m
     ("diag_gauss", "diag", 7, 9, 0.25, "multinomial", "generalised")],
     ids=["D128-full", "D8-full-strict", "D4-full-slice", "D8-full-dense", "D7-ragged"])
 def test_staged_full_tile_instantiation_matches_oracle(emu_full, kind, mkind, D, N, eps, sampler, criterion):
-    """-DAHMC_NUTS_FULLTILE=1 (+ FASTDRAW): D == G * E takes the instantiation with a compile-time D (no `d < D` guards);
-    ragged D still takes the general one."""
+    """-DAHMC_NUTS_FULLTILE=1 (+ FASTDRAW + RELOAD_COEF): D == G * E takes the instantiation with a compile-time D (no
+    `d < D` guards), ragged D the general one; model / metric coefficients are re-read where they are used."""
     _case(emu_full, kind, mkind, D, N, eps, sampler, criterion, seed=29 + D, scale=0.5 if kind == "funnel" else 1.0)
 
 
@@ -255,12 +256,12 @@ def test_fastdraw_variant_equals_default_build_on_philox_streams(emu, emu_fast):
     assert a["n_steps"].max() >= 7 and len(np.unique(a["draws"][:, 0, 0])) > 6  # the chains really moved
 
 
-@pytest.mark.parametrize("which", ["default", "fastdraw"])
-def test_in_launch_adaptation_under_emulation_equals_oracle_adaptors(emu, emu_fast, which):
+@pytest.mark.parametrize("which", ["default", "fastdraw", "fastdraw+reloadcoef"])
+def test_in_launch_adaptation_under_emulation_equals_oracle_adaptors(emu, emu_fast, emu_full, which):
     """The adaptive kernel family (per-chain NesterovDualAveraging + windowed WelfordVar inside the persistent launch)
     executed by the emulator, replayed iteration by iteration with the ORACLE's adaptors fed by the kernel's own
     acceptance rates and draws: step-size trace, window update of M^-1, reset and finalize! must agree."""
-    emu = emu if which == "default" else emu_fast
+    emu = {"default": emu, "fastdraw": emu_fast, "fastdraw+reloadcoef": emu_full}[which]
     rng = np.random.default_rng(3)
     D, N, T, n_adapts = 5, 6, 24, 20
     ib, tb, wsz = 3, 2, 4
