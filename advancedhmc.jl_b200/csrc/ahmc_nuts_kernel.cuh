@@ -631,7 +631,11 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 const double u_comb = peek_u();
 #endif
                 if (do_comb) {
+#if AHMC_NUTS_FASTDRAW
+                    const double lw_p = LW[k], sa_p = 0.0, na_p = NA[k], dh_p = DH[k];  // sum(alpha): see alpha_flush
+#else
                     const double lw_p = LW[k], sa_p = SA[k], na_p = NA[k], dh_p = DH[k];
+#endif
 #if AHMC_NUTS_FASTDRAW
                     if (VAR && samp == 1) {  // combine(rng, s1::SliceTS, s2) (:178-183)
                         const double n = lw_p + lw_c;
@@ -715,7 +719,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                         WW[k] = ww_c;
 #endif
                         LW[k] = lw_c;
+#if !AHMC_NUTS_FASTDRAW
                         SA[k] = sa_c;
+#endif
                         NA[k] = na_c;
                         DH[k] = dh_c;
                         CLP[k] = clp;
