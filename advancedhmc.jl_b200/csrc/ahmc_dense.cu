@@ -22,11 +22,25 @@ namespace ahmc {
 
 constexpr int kDenseThreads = 256;  // 8 warps
 constexpr int kKC = 16;             // columns of A per pipeline stage
+#ifdef AHMC_SIMT_EMULATION
+extern unsigned char* emu_dynamic_smem;  // the block's dynamic shared memory (blocks run one at a time)
+#endif
 
+#ifdef AHMC_SIMT_EMULATION
+// CPU SIMT emulation (tests/simt_emu/dense_emu.cpp): the five PTX wrappers below are provided by the harness with the
+// same contracts -- an mbarrier as (completed phases, pending bytes), a synchronous bulk copy, the m8n8k4 fragment map.
+void mbar_init(uint64_t* bar, int count);
+void mbar_fence_init();
+void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
+void mbar_wait(uint64_t* bar, uint32_t parity);
+void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
+void dmma(double& d0, double& d1, double a, double b);
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -53,6 +67,7 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
+#endif  // AHMC_SIMT_EMULATION
 
 // Y += A * X for the CTA's tile.  A: Dp x Dp column-major (padded, zero-filled) in global memory.
 // Xs: CT x Dx doubles in shared memory (chain-major, Dx = Dp + 4).  acc[rb][cb][2]: this thread's accumulators:
@@ -137,7 +152,11 @@ struct DenseArgs {
 
 template <int RB, int CB, int MINB = 1>
 __global__ void __launch_bounds__(kDenseThreads, MINB) dense_traj_kernel(const DenseArgs a) {
+#ifdef AHMC_SIMT_EMULATION
+    unsigned char* smem_raw = emu_dynamic_smem;
+#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
     constexpr int CT = 8 * CB;
     const int Dp = a.Dp, D = a.D, Dx = Dp + 4, Ds = Dp + 4;
     double* As = reinterpret_cast<double*>(smem_raw);
@@ -150,7 +169,7 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) dense_traj_kernel(const D
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         s_flag = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
     uint32_t phase[2] = {0u, 0u};
@@ -392,6 +411,15 @@ __global__ void vec_norm_kernel(const double* __restrict__ v, int D, double* nor
     }
 }
 
+bool dense_tile_shape(int D, int* Dp, int* RB, int* CB) {
+    if (D < 1 || D > 512) return false;
+    *Dp = ((D + 63) / 64) * 64;
+    *RB = *Dp / 64;
+    *CB = (*RB <= 2) ? 4 : (*RB <= 4 ? 2 : 1);
+    return true;
+}
+
+#ifndef AHMC_SIMT_EMULATION
 cudaError_t launch_pad_norm(const double* A, int D, int Dp, double* Ap, double* norm, cudaStream_t st) {
     pad_norm_kernel<<<1, 256, 0, st>>>(A, D, Dp, Ap, norm);
     return cudaGetLastError();
@@ -401,13 +429,6 @@ cudaError_t launch_vec_norm(const double* v, int D, double* norm, cudaStream_t s
     return cudaGetLastError();
 }
 
-bool dense_tile_shape(int D, int* Dp, int* RB, int* CB) {
-    if (D < 1 || D > 512) return false;
-    *Dp = ((D + 63) / 64) * 64;
-    *RB = *Dp / 64;
-    *CB = (*RB <= 2) ? 4 : (*RB <= 4 ? 2 : 1);
-    return true;
-}
 
 template <int RB, int CB, int MINB = 1>
 static cudaError_t launch_dense_t(const DenseArgs& a, cudaStream_t st) {
@@ -449,5 +470,6 @@ cudaError_t launch_dense_traj(const DenseTrajHost& h, cudaStream_t st, int* n_la
     }
     return cudaErrorInvalidValue;
 }
+#endif  // AHMC_SIMT_EMULATION
 
 }  // namespace ahmc

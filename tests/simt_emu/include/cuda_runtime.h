@@ -61,6 +61,9 @@ inline int __double2hiint(double x) {
     return (int)(b >> 32);
 }
 int atomicMin(int* addr, int v);
+int atomicOr(int* addr, int v);
+// every lane contributes (a, b); every lane receives all 32 of each (one exchange instead of 12 shuffles: emulated DMMA)
+void emu_gather2(double a, double b, double* a32, double* b32);
 using std::fabs;
 using std::fma;
 using std::fmax;

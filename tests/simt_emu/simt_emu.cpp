@@ -19,6 +19,7 @@ namespace {
 struct Warp {
     pthread_barrier_t bar;
     uint64_t slot[32];
+    double slot_b[32];
     unsigned pred[32];
 };
 thread_local Warp* tls_warp = nullptr;
@@ -57,6 +58,16 @@ unsigned emu_reduce_max(unsigned mask, unsigned v) {
         if ((mask >> i) & 1u) m = w->slot[i] > m ? (unsigned)w->slot[i] : m;
     pthread_barrier_wait(&w->bar);
     return m;
+}
+int atomicOr(int* addr, int v) { return std::atomic_ref<int>(*addr).fetch_or(v); }
+void emu_gather2(double a, double b, double* a32, double* b32) {
+    Warp* w = tls_warp;
+    std::memcpy(&w->slot[tls_lane], &a, 8);
+    w->slot_b[tls_lane] = b;
+    pthread_barrier_wait(&w->bar);
+    std::memcpy(a32, w->slot, 32 * 8);
+    std::memcpy(b32, w->slot_b, 32 * 8);
+    pthread_barrier_wait(&w->bar);
 }
 int atomicMin(int* addr, int v) {
     std::atomic_ref<int> a(*addr);

@@ -535,3 +535,81 @@ def test_trajectory_kernel_emulated_nonfinite_freeze_tempering_and_fast_path_fal
     assert emu_lf.emu_leapfrog(C.byref(q)) == 0
     assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10
     assert np.allclose(lk_o, zo.lk_value, rtol=1e-10, atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------------------------- K4
+class EmuDense(C.Structure):
+    _fields_ = [("D", C.c_int32), ("N", C.c_int64), ("P", _vp), ("w", _vp), ("mu", _vp), ("c0", C.c_double), ("Minv", _vp),
+                ("Mdiag", _vp), ("eps", C.c_double), ("eps_chain", _vp), ("n_steps", C.c_int32), ("fwd", C.c_int32),
+                ("th_in", _vp), ("r_in", _vp), ("g_in", _vp), ("th_out", _vp), ("r_out", _vp), ("g_out", _vp), ("dr_out", _vp),
+                ("lp_out", _vp), ("lk_out", _vp), ("status", _vp), ("steps_done", _vp), ("need_exact", _vp),
+                ("wide_tile", C.c_int32), ("norms_out", C.c_double * 2)]
+
+
+@pytest.fixture(scope="module")
+def emu_dense(tmp_path_factory):
+    out = tmp_path_factory.mktemp("simt_dense") / "libdense_emu.so"
+    d = os.path.join(ROOT, "tests", "simt_emu")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-x", "c++",
+                    "-I", os.path.join(d, "include"), "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"),
+                    "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"), os.path.join(d, "dense_emu.cpp"),
+                    "-o", str(out)], check=True)
+    return C.CDLL(str(out))
+
+
+def _dense_run(lib, kind, mkind, D, N, eps, n, fwd, seed, per_chain_eps=True, wide=0, poison=None):
+    rng = np.random.default_rng(seed)
+    model, metric, p0, dp1, Minv, _ = _lf_system(kind, mkind, D, rng)
+    th, r = rng.normal(size=(N, D)), rng.normal(size=(N, D))
+    eps_chain = eps * np.exp(rng.uniform(-0.3, 0.3, N)) if per_chain_eps else None
+    z0 = oc.phasepoint(model, metric, th.T, r.T)
+    zo = oc.leapfrog(model, metric, eps_chain if per_chain_eps else eps, z0, n if fwd else -n)[0]
+    g_in = np.ascontiguousarray(z0.lp_gradient.T)
+    if poison is not None:
+        th[poison, 0] = 1e250  # beyond the magnitude proof: the whole tile must be handed to the exact kernel
+    o = {k: np.full((N, D), np.nan) for k in ("th", "r", "g", "dr")}
+    lp_o, lk_o = np.full(N, np.nan), np.full(N, np.nan)
+    status, done, need = np.full(N, 7, dtype=np.uint32), np.zeros(N, dtype=np.int32), np.full(N, 9, dtype=np.uint8)
+    Pm = np.asfortranarray(dp1) if kind == "dense_gauss" else None
+    w = dp1 if kind == "diag_gauss" else None
+    Mm = np.asfortranarray(Minv) if mkind == "dense" else None
+    Md = Minv if mkind == "diag" else None
+    q = EmuDense(D=D, N=N, P=None if Pm is None else Pm.ctypes.data_as(_vp), w=P(w), mu=P(p0), c0=0.0,
+                 Minv=None if Mm is None else Mm.ctypes.data_as(_vp), Mdiag=P(Md), eps=eps, eps_chain=P(eps_chain), n_steps=n,
+                 fwd=fwd, th_in=P(th), r_in=P(r), g_in=P(g_in), th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]),
+                 dr_out=P(o["dr"]), lp_out=P(lp_o), lk_out=P(lk_o), status=P(status), steps_done=P(done), need_exact=P(need),
+                 wide_tile=wide)
+    assert lib.emu_dense(C.byref(q)) == 0
+    nM = np.abs(Minv).sum(axis=1).max() if mkind == "dense" else (np.abs(Minv).max() if mkind == "diag" else 1.0)
+    nP = np.abs(dp1).sum(axis=1).max() if kind == "dense_gauss" else (np.abs(dp1).max() if kind == "diag_gauss" else 1.0)
+    assert np.isclose(q.norms_out[0], nM, rtol=1e-13) and np.isclose(q.norms_out[1], nP, rtol=1e-13)
+    return zo, o, lp_o, lk_o, status, done, need
+
+
+DENSE_CASES = [("dense_gauss", "dense", 40, 37, 0.1, 5, 1, True, 0),    # Dp = 64: <1,4>, two ragged 32-chain tiles
+               ("dense_gauss", "diag", 100, 20, 0.08, 4, 0, True, 0),   # Dp = 128: default <2,2,2>, backward
+               ("diag_gauss", "dense", 70, 33, 0.12, 3, 1, False, 1),   # Dp = 128: the 32-chain form, shared eps
+               ("dense_gauss", "dense", 130, 17, 0.05, 2, 1, True, 0),  # Dp = 192: <3,2>
+               ("dense_gauss", "unit", 64, 8, 0.1, 1, 1, False, 0)]     # D == Dp, a single step (half kicks only)
+
+
+@pytest.mark.parametrize("kind,mkind,D,N,eps,n,fwd,pce,wide", DENSE_CASES, ids=[f"{c[0]}-{c[1]}-D{c[2]}" for c in DENSE_CASES])
+def test_dense_tile_kernel_source_under_emulation_matches_oracle(emu_dense, kind, mkind, D, N, eps, n, fwd, pce, wide):
+    """K4 (`dense_traj_kernel`: bulk-copy pipeline on mbarriers, DMMA fragment layout, tile staging, padding, ragged tiles,
+    energy reduction) executed by the emulator vs the oracle's `step`; `pad_norm_kernel` / `vec_norm_kernel` too."""
+    zo, o, lp_o, lk_o, status, done, need = _dense_run(emu_dense, kind, mkind, D, N, eps, n, fwd, seed=100 + D, per_chain_eps=pce,
+                                                       wide=wide)
+    assert (need == 0).all() and (done == n).all() and (status == 0).all()
+    assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10 and rel_err(o["g"].T, zo.lp_gradient) < 1e-10
+    assert np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10) and np.allclose(lk_o, zo.lk_value, rtol=1e-10, atol=1e-10)
+    assert rel_err(o["dr"].T, zo.lk_gradient) < 1e-10
+
+
+def test_dense_tile_kernel_emulated_hands_a_suspect_tile_to_the_exact_kernel(emu_dense):
+    """a magnitude beyond the linear-dynamics proof flags the WHOLE tile (`need_exact`), writes nothing for it, and leaves
+    the other tile's results intact"""
+    N, D = 37, 40
+    zo, o, lp_o, lk_o, status, done, need = _dense_run(emu_dense, "dense_gauss", "dense", D, N, 0.1, 3, 1, seed=5, poison=34)
+    assert (need[:32] == 0).all() and (need[32:] == 1).all()
+    assert np.isnan(o["th"][32:]).all() and np.isnan(lp_o[32:]).all() and (status[32:] == 7).all()
+    assert rel_err(o["th"][:32].T, zo.theta[:, :32]) < 1e-10 and np.allclose(lk_o[:32], zo.lk_value[:32], rtol=1e-10)
