@@ -333,7 +333,7 @@ int try_dense_trajectory(ahmc_ctx* ctx, const ahmc_model* model, LeapfrogArgs& a
           dense_tile_shape(D, &Dp, &RB, &CB) && (model->kind != AHMC_MODEL_DENSE_GAUSS || model->d_p1_pad)))
         return 0;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t need = al((size_t)Dp * Dp * 8) + al(16) + al((size_t)N);
+    const size_t need = al(dense_mat_doubles(Dp) * 8) + al(16) + al((size_t)N);
     if (need > ctx->dense_scratch_bytes) {
         CU(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->dense_scratch);
@@ -344,14 +344,14 @@ int try_dense_trajectory(ahmc_ctx* ctx, const ahmc_model* model, LeapfrogArgs& a
         ctx->dense_scratch_bytes = need;
     }
     double* Mpad = (double*)ctx->dense_scratch;
-    double* norms = (double*)(ctx->dense_scratch + al((size_t)Dp * Dp * 8));
-    uint8_t* mask = (uint8_t*)(ctx->dense_scratch + al((size_t)Dp * Dp * 8) + al(16));
+    double* norms = (double*)(ctx->dense_scratch + al(dense_mat_doubles(Dp) * 8));
+    uint8_t* mask = (uint8_t*)(ctx->dense_scratch + al(dense_mat_doubles(Dp) * 8) + al(16));
     DenseTrajHost h{};
     h.D = D; h.Dp = Dp; h.N = N; h.c0 = model->c0;
     h.mu = (model->kind == AHMC_MODEL_STD_NORMAL) ? nullptr : model->d_p0;
     if (model->kind == AHMC_MODEL_DENSE_GAUSS) {
         h.P = model->d_p1_pad;
-        CU(cudaMemcpyAsync(norms + 1, model->d_p1_pad + (size_t)Dp * Dp, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(norms + 1, model->d_p1_pad + dense_mat_doubles(Dp), 8, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
         h.w = (model->kind == AHMC_MODEL_DIAG_GAUSS) ? model->d_p1 : nullptr;
         CU(launch_vec_norm(h.w, D, norms + 1, ctx->stream));
@@ -492,11 +492,11 @@ int ahmc_model_create(ahmc_ctx* ctx, int32_t kind, int32_t D, const double* p0, 
         cudaMemcpy(m->d_p1, p1, sizeof(double) * (size_t)D * D, cudaMemcpyHostToDevice);
         int RB, CB;
         if (dense_tile_shape(D, &m->Dp, &RB, &CB)) {  // padded copy + infinity norm for the tiled DMMA kernel
-            if (cudaMalloc((void**)&m->d_p1_pad, sizeof(double) * ((size_t)m->Dp * m->Dp + 2)) != cudaSuccess) {
+            if (cudaMalloc((void**)&m->d_p1_pad, sizeof(double) * (dense_mat_doubles(m->Dp) + 2)) != cudaSuccess) {
                 ahmc_model_destroy(ctx, m);
                 return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc for the padded precision failed");
             }
-            launch_pad_norm(m->d_p1, D, m->Dp, m->d_p1_pad, m->d_p1_pad + (size_t)m->Dp * m->Dp, ctx->stream);
+            launch_pad_norm(m->d_p1, D, m->Dp, m->d_p1_pad, m->d_p1_pad + dense_mat_doubles(m->Dp), ctx->stream);
             cudaStreamSynchronize(ctx->stream);
         }
     }

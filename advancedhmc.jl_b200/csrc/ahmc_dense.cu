@@ -22,6 +22,21 @@ namespace ahmc {
 
 constexpr int kDenseThreads = 256;  // 8 warps
 constexpr int kKC = 16;             // columns of A per pipeline stage
+// Staged pipeline knobs (all OFF in the shipped build; each verified under the CPU SIMT emulator, tests/simt_emu/dense_emu.cpp):
+//   AHMC_DENSE_PADDED_A (ahmc_kernels.cuh)  the padded matrix is stored with the shared-memory stage's leading dimension
+//                             (Dp + 4), so a 16-column chunk is ONE contiguous bulk copy instead of sixteen;
+//   AHMC_DENSE_MBAR_RELEASE   consumers release a stage through an "empty" mbarrier (one arrival per warp) and only the
+//                             producer thread waits on it, instead of a CTA-wide __syncthreads per chunk;
+//   AHMC_DENSE_STAGES         depth of the A pipeline (2; 3 needs AHMC_DENSE_MBAR_RELEASE).
+#ifndef AHMC_DENSE_MBAR_RELEASE
+#define AHMC_DENSE_MBAR_RELEASE 0
+#endif
+#ifndef AHMC_DENSE_STAGES
+#define AHMC_DENSE_STAGES 2
+#endif
+constexpr int kStages = AHMC_DENSE_STAGES;
+static_assert(kStages == 2 || (kStages == 3 && AHMC_DENSE_MBAR_RELEASE), "AHMC_DENSE_STAGES: 2, or 3 with AHMC_DENSE_MBAR_RELEASE");
+constexpr int kBars = AHMC_DENSE_MBAR_RELEASE ? 2 * kStages : kStages;  // full[kStages] (+ empty[kStages])
 #ifdef AHMC_SIMT_EMULATION
 extern unsigned char* emu_dynamic_smem;  // the block's dynamic shared memory (blocks run one at a time)
 #endif
@@ -32,6 +47,7 @@ extern unsigned char* emu_dynamic_smem;  // the block's dynamic shared memory (b
 void mbar_init(uint64_t* bar, int count);
 void mbar_fence_init();
 void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
+void mbar_arrive(uint64_t* bar);
 void mbar_wait(uint64_t* bar, uint32_t parity);
 void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
 void dmma(double& d0, double& d1, double a, double b);
@@ -43,6 +59,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -73,11 +92,18 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // Xs: CT x Dx doubles in shared memory (chain-major, Dx = Dp + 4).  acc[rb][cb][2]: this thread's accumulators:
 // rows 8*(RB*warp + rb) + lane/4, columns 8*cb + 2*(lane%4) + {0,1}.
 template <int RB, int CB>
-__device__ __forceinline__ void tile_gemm(const double* __restrict__ A, int Dp, const double* Xs, double* As /* 2 stages */,
-                                          uint64_t* bars, uint32_t (&phase)[2], double (&acc)[RB][CB][2]) {
+__device__ __forceinline__ void tile_gemm(const double* __restrict__ A, int Dp, const double* Xs, double* As /* kStages stages */,
+                                          uint64_t* bars, uint32_t (&phase)[kBars], double (&acc)[RB][CB][2]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Ds = Dp + 4, Dx = Dp + 4;
     const int nchunks = Dp / kKC;
+#if AHMC_DENSE_PADDED_A
+    const uint32_t chunk_bytes = (uint32_t)(kKC * Ds * sizeof(double));
+    auto issue = [&](int c, int stage) {  // global leading dimension == stage leading dimension: one contiguous copy
+        mbar_expect_tx(&bars[stage], chunk_bytes);
+        bulk_g2s(As + (size_t)stage * kKC * Ds, A + (size_t)c * kKC * Ds, chunk_bytes, &bars[stage]);
+    };
+#else
     const uint32_t chunk_bytes = (uint32_t)(kKC * Dp * sizeof(double));
     auto issue = [&](int c, int stage) {
         mbar_expect_tx(&bars[stage], chunk_bytes);
@@ -86,6 +112,50 @@ __device__ __forceinline__ void tile_gemm(const double* __restrict__ A, int Dp, 
 #pragma unroll 4
         for (int k = 0; k < kKC; ++k) bulk_g2s(dst + (size_t)k * Ds, src + (size_t)k * Dp, (uint32_t)(Dp * sizeof(double)), &bars[stage]);
     };
+#endif
+#if AHMC_DENSE_MBAR_RELEASE
+    // Bit s of phase[0]: parity of the next "full" phase of stage s (every thread).  Producer thread only -- bit s of
+    // phase[1]: parity of the number of fills f of stage s so far; of phase[2]: f > 0.  Fill f >= 1 of a stage waits for
+    // the stage's (f-1)-th release: bars[kStages + s] completes one phase per consumption (8 warp arrivals), and at that
+    // point it has completed f-1 or f of them, so the parity wait is unambiguous.
+    auto refill = [&](int c, int stage) {
+        const uint32_t bit = 1u << stage;
+        if (phase[2] & bit) mbar_wait(&bars[kStages + stage], ((phase[1] >> stage) & 1u) ^ 1u);
+        phase[2] |= bit;
+        phase[1] ^= bit;
+        issue(c, stage);
+    };
+    if (tid == 0)
+        for (int c = 0; c < kStages && c < nchunks; ++c) refill(c, c);
+    const int arow = 8 * RB * warp + (lane >> 2);
+    int stage = 0, prev = kStages - 1;
+    for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&bars[stage], (phase[0] >> stage) & 1u);
+        phase[0] ^= 1u << stage;
+        const double* as = As + (size_t)stage * kKC * Ds;
+#pragma unroll
+        for (int ks = 0; ks < kKC / 4; ++ks) {
+            double a[RB], b[CB];
+            const int kl = 4 * ks + (lane & 3);
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) a[rb] = as[(size_t)kl * Ds + arow + 8 * rb];
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb) b[cb] = Xs[(size_t)(8 * cb + (lane >> 2)) * Dx + c * kKC + kl];
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) dmma(acc[rb][cb][0], acc[rb][cb][1], a[rb], b[cb]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[kStages + stage]);  // this warp is done with the stage
+        // the producer refills the stage of the PREVIOUS chunk: its last readers are at most one chunk behind
+        if (tid == 0 && c >= 1 && c - 1 + kStages < nchunks) refill(c - 1 + kStages, prev);
+        prev = stage;
+        stage = (stage + 1 == kStages) ? 0 : stage + 1;
+    }
+    __syncthreads();  // every warp is done with Xs; every release of this product has arrived
+}
+#else
     if (tid == 0) {
         issue(0, 0);
         if (nchunks > 1) issue(1, 1);
@@ -113,6 +183,7 @@ __device__ __forceinline__ void tile_gemm(const double* __restrict__ A, int Dp, 
         if (tid == 0 && c + 2 < nchunks) issue(c + 2, stage);
     }
 }
+#endif
 
 template <int RB, int CB>
 __device__ __forceinline__ void tile_to_smem(double* Xs, int Dp, const double (&v)[RB][CB][2]) {
@@ -160,19 +231,30 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) dense_traj_kernel(const D
     constexpr int CT = 8 * CB;
     const int Dp = a.Dp, D = a.D, Dx = Dp + 4, Ds = Dp + 4;
     double* As = reinterpret_cast<double*>(smem_raw);
-    double* Xs = As + (size_t)2 * kKC * Ds;
+    double* Xs = As + (size_t)kStages * kKC * Ds;
     double* red = Xs + (size_t)CT * Dx;                        // [8 warps][CT][2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * CT * 2);
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
+#if AHMC_DENSE_MBAR_RELEASE
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&bars[i], 1);
+            mbar_init(&bars[kStages + i], kDenseThreads / 32);
+        }
+#else
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
+#endif
         s_flag = 0;
         mbar_fence_init();
     }
     __syncthreads();
+#if AHMC_DENSE_MBAR_RELEASE
+    uint32_t phase[kBars] = {};
+#else
     uint32_t phase[2] = {0u, 0u};
+#endif
     const long long tile0 = (long long)blockIdx.x * CT;
     constexpr int T200 = expo_bits(200), T100 = expo_bits(100), T50 = expo_bits(50);
 
@@ -386,11 +468,15 @@ __global__ void pad_norm_kernel(const double* __restrict__ A, int D, int Dp, dou
         double s = 0.0;
         for (int k = 0; k < Dp; ++k) {
             double v = (rowi < D && k < D) ? A[(size_t)k * D + rowi] : 0.0;
-            if (Ap) Ap[(size_t)k * Dp + rowi] = v;
+            if (Ap) Ap[(size_t)k * dense_lda(Dp) + rowi] = v;
             s += fabs(v);
         }
         best = (s > best || s != s) ? s : best;
     }
+#if AHMC_DENSE_PADDED_A
+    if (Ap)  // the 4 padding rows of every column travel with the chunk copy: keep them defined
+        for (int i = threadIdx.x; i < 4 * Dp; i += blockDim.x) Ap[(size_t)(i >> 2) * dense_lda(Dp) + Dp + (i & 3)] = 0.0;
+#endif
     smax[threadIdx.x] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -434,7 +520,7 @@ template <int RB, int CB, int MINB = 1>
 static cudaError_t launch_dense_t(const DenseArgs& a, cudaStream_t st) {
     constexpr int CT = 8 * CB;
     const int Ds = a.Dp + 4;
-    const size_t sm = ((size_t)2 * kKC * Ds + (size_t)CT * Ds + 8 * CT * 2) * sizeof(double) + 64;
+    const size_t sm = ((size_t)kStages * kKC * Ds + (size_t)CT * Ds + 8 * CT * 2) * sizeof(double) + 64;
     cudaError_t e = cudaFuncSetAttribute(dense_traj_kernel<RB, CB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
     const long long blocks = (a.N + CT - 1) / CT;

@@ -1,8 +1,8 @@
 // dense_emu.cpp -- K4, the tile-per-CTA trajectory kernel for GEMM-shaped operators (advancedhmc.jl_b200/csrc/
 // ahmc_dense.cu: `dense_traj_kernel`, `pad_norm_kernel`, `vec_norm_kernel`, unmodified) under the CPU SIMT emulator.
 // The kernel's five PTX wrappers are restated here with the same contracts:
-//   * an mbarrier is (number of completed phases, pending transaction bytes); `mbar_wait(parity)` returns once the phase
-//     of that parity has completed;
+//   * an mbarrier is (completed phases, pending arrivals, pending transaction bytes); `mbar_wait(parity)` returns once
+//     the phase of that parity has completed;
 //   * `bulk_g2s` copies synchronously and completes its bytes on the barrier;
 //   * `dmma` is `mma.sync.aligned.m8n8k4.row.col.f64`: lane l holds A[l/4][l%4], B[l%4][l/4] and C[l/4][2(l%4)+{0,1}].
 // TEST INFRASTRUCTURE ONLY (tests/test_simt_emulation.py).
@@ -18,17 +18,55 @@ void emu_launch(void (*kernel)(const void*), const void* args, int blocks, int t
 
 namespace ahmc {
 unsigned char* emu_dynamic_smem = nullptr;
-void mbar_init(uint64_t* bar, int) { std::atomic_ref<uint64_t>(*bar).store(0); }
+// An mbarrier lives in the kernel's shared memory as one 64-bit word; here: bits 0..19 completed phases, 20..31 pending
+// arrivals of the current phase, 32..63 pending transaction bytes (biased by 2^31: complete_tx may precede expect_tx).
+// The expected arrival count of each barrier is kept beside it (indexed by its address: at most 8 barriers per block).
+namespace {
+constexpr uint64_t kTxBias = 1ull << 31;
+struct BarInfo {
+    uint64_t* bar;
+    uint32_t count;
+};
+BarInfo bar_info[8];
+std::atomic<int> n_bar_info{0};
+uint32_t expected_arrivals(uint64_t* bar) {
+    for (int i = 0; i < n_bar_info.load(); ++i)
+        if (bar_info[i].bar == bar) return bar_info[i].count;
+    return 0;  // unreachable for an initialised barrier
+}
+// apply (arrivals, +/- bytes) atomically; complete the phase when both reach zero
+void bar_update(uint64_t* bar, uint32_t arrivals, int64_t tx) {
+    std::atomic_ref<uint64_t> b(*bar);
+    uint64_t old = b.load(), neu;
+    do {
+        uint64_t phases = old & 0xfffffu, pend = (old >> 20) & 0xfffu;
+        int64_t bytes = (int64_t)(old >> 32) - (int64_t)kTxBias + tx;
+        pend -= arrivals;
+        if (pend == 0 && bytes == 0) {
+            phases = (phases + 1) & 0xfffffu;
+            pend = expected_arrivals(bar);
+        }
+        neu = phases | (pend << 20) | ((uint64_t)(bytes + (int64_t)kTxBias) << 32);
+    } while (!b.compare_exchange_weak(old, neu));
+}
+}  // namespace
+void mbar_init(uint64_t* bar, int count) {  // thread 0 only, before the block barrier
+    int i = 0;
+    for (; i < n_bar_info.load(); ++i)
+        if (bar_info[i].bar == bar) break;
+    if (i == n_bar_info.load()) n_bar_info.store(i + 1);
+    bar_info[i] = BarInfo{bar, (uint32_t)count};
+    std::atomic_ref<uint64_t>(*bar).store(((uint64_t)count << 20) | (kTxBias << 32));
+}
 void mbar_fence_init() {}
-void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { std::atomic_ref<uint64_t>(*bar).fetch_add((uint64_t)bytes << 32); }
+void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { bar_update(bar, 1, (int64_t)bytes); }
+void mbar_arrive(uint64_t* bar) { bar_update(bar, 1, 0); }
 void mbar_wait(uint64_t* bar, uint32_t parity) {
     while ((uint32_t)(std::atomic_ref<uint64_t>(*bar).load() & 1u) == parity) std::this_thread::yield();
 }
 void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     std::memcpy(dst, src, bytes);
-    std::atomic_ref<uint64_t> b(*bar);
-    const uint64_t before = b.fetch_sub((uint64_t)bytes << 32);
-    if ((before >> 32) == bytes) b.fetch_add(1);  // last byte of the phase: the single arrival (expect_tx) is already in
+    bar_update(bar, 0, -(int64_t)bytes);
 }
 void dmma(double& d0, double& d1, double a, double b) {
     double A[32], B[32];
@@ -77,14 +115,16 @@ struct EmuDense {
     double norms_out[2];
 };
 
+extern "C" int emu_dense_knobs() { return AHMC_DENSE_PADDED_A | (AHMC_DENSE_MBAR_RELEASE << 1) | (kStages << 2); }
 extern "C" int emu_dense(EmuDense* q) {
+    n_bar_info.store(0);
     int Dp, RB, CB;
     if (!dense_tile_shape(q->D, &Dp, &RB, &CB)) return -1;
     std::vector<double> Pp, Mp;
     double norms[2] = {0.0, 0.0};
     PadArgs pa{};
     if (q->Minv) {
-        Mp.assign((size_t)Dp * Dp, -1.0);
+        Mp.assign(dense_mat_doubles(Dp), -1.0);
         pa = PadArgs{q->Minv, q->D, Dp, Mp.data(), &norms[0]};
         emu_launch(pad_thunk, &pa, 1, 256);
     } else {
@@ -92,7 +132,7 @@ extern "C" int emu_dense(EmuDense* q) {
         emu_launch(vec_thunk, &pa, 1, 32);
     }
     if (q->P) {
-        Pp.assign((size_t)Dp * Dp, -1.0);
+        Pp.assign(dense_mat_doubles(Dp), -1.0);
         pa = PadArgs{q->P, q->D, Dp, Pp.data(), &norms[1]};
         emu_launch(pad_thunk, &pa, 1, 256);
     } else {
@@ -115,7 +155,7 @@ extern "C" int emu_dense(EmuDense* q) {
     else if (RB == 3) fn = dense_thunk<3, 2, 1>, CT = 16;
     else return -2;
     const int Ds = Dp + 4;
-    const size_t sm = ((size_t)2 * kKC * Ds + (size_t)CT * Ds + 8 * CT * 2) * sizeof(double) + 64;  // as launch_dense_t
+    const size_t sm = ((size_t)kStages * kKC * Ds + (size_t)CT * Ds + 8 * CT * 2) * sizeof(double) + 64;  // as launch_dense_t
     std::vector<double> smem(sm / sizeof(double) + 2, 0.0);
     emu_dynamic_smem = reinterpret_cast<unsigned char*>(smem.data());
     emu_launch(fn, &a, (int)((q->N + CT - 1) / CT), kDenseThreads);

@@ -546,15 +546,36 @@ class EmuDense(C.Structure):
                 ("wide_tile", C.c_int32), ("norms_out", C.c_double * 2)]
 
 
+_DENSE_VARIANTS = {  # name -> (compile-time knobs of ahmc_dense.cu, emu_dense_knobs() = padded | release << 1 | stages << 2)
+    "default": ([], 0 | 0 | 2 << 2),
+    "padded": (["-DAHMC_DENSE_PADDED_A=1"], 1 | 2 << 2),
+    "release": (["-DAHMC_DENSE_MBAR_RELEASE=1"], 2 | 2 << 2),
+    "padded+release+3stages": (["-DAHMC_DENSE_PADDED_A=1", "-DAHMC_DENSE_MBAR_RELEASE=1", "-DAHMC_DENSE_STAGES=3"], 1 | 2 | 3 << 2)}
+
+
 @pytest.fixture(scope="module")
-def emu_dense(tmp_path_factory):
-    out = tmp_path_factory.mktemp("simt_dense") / "libdense_emu.so"
+def _dense_libs(tmp_path_factory):
+    tmp = tmp_path_factory.mktemp("simt_dense")
     d = os.path.join(ROOT, "tests", "simt_emu")
-    subprocess.run(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-x", "c++",
-                    "-I", os.path.join(d, "include"), "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"),
-                    "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"), os.path.join(d, "dense_emu.cpp"),
-                    "-o", str(out)], check=True)
-    return C.CDLL(str(out))
+    procs = {}
+    for name, (defs, _) in _DENSE_VARIANTS.items():
+        out = tmp / f"libdense_emu_{len(procs)}.so"
+        cmd = ["g++", *defs, "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-x", "c++",
+               "-I", os.path.join(d, "include"), "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"),
+               "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"), os.path.join(d, "dense_emu.cpp"), "-o", str(out)]
+        procs[name] = (subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True), out)
+    libs = {}
+    for name, (pr, out) in procs.items():
+        _, err = pr.communicate()
+        assert pr.returncode == 0, err[-2000:]
+        libs[name] = C.CDLL(str(out))
+        assert libs[name].emu_dense_knobs() == _DENSE_VARIANTS[name][1]
+    return libs
+
+
+@pytest.fixture(scope="module")
+def emu_dense(_dense_libs):
+    return _dense_libs["default"]
 
 
 def _dense_run(lib, kind, mkind, D, N, eps, n, fwd, seed, per_chain_eps=True, wide=0, poison=None):
@@ -613,3 +634,16 @@ def test_dense_tile_kernel_emulated_hands_a_suspect_tile_to_the_exact_kernel(emu
     assert (need[:32] == 0).all() and (need[32:] == 1).all()
     assert np.isnan(o["th"][32:]).all() and np.isnan(lp_o[32:]).all() and (status[32:] == 7).all()
     assert rel_err(o["th"][:32].T, zo.theta[:, :32]) < 1e-10 and np.allclose(lk_o[:32], zo.lk_value[:32], rtol=1e-10)
+
+
+@pytest.mark.parametrize("variant", [v for v in _DENSE_VARIANTS if v != "default"])
+@pytest.mark.parametrize("kind,mkind,D,N,eps,n,fwd,pce,wide", DENSE_CASES[:4], ids=[f"{c[0]}-{c[1]}-D{c[2]}" for c in DENSE_CASES[:4]])
+def test_staged_dense_pipeline_variants_under_emulation_match_oracle(_dense_libs, variant, kind, mkind, D, N, eps, n, fwd, pce, wide):
+    """the staged K4 pipeline knobs (single contiguous chunk copy from a padded matrix; stage release through mbarriers
+    instead of a CTA barrier per chunk; a third stage): same oracle comparison as the shipped form"""
+    zo, o, lp_o, lk_o, status, done, need = _dense_run(_dense_libs[variant], kind, mkind, D, N, eps, n, fwd, seed=100 + D,
+                                                       per_chain_eps=pce, wide=wide)
+    assert (need == 0).all() and (done == n).all() and (status == 0).all()
+    assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10 and rel_err(o["g"].T, zo.lp_gradient) < 1e-10
+    assert np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10) and np.allclose(lk_o, zo.lk_value, rtol=1e-10, atol=1e-10)
+    assert rel_err(o["dr"].T, zo.lk_gradient) < 1e-10
