@@ -647,3 +647,58 @@ def test_staged_dense_pipeline_variants_under_emulation_match_oracle(_dense_libs
     assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10 and rel_err(o["g"].T, zo.lp_gradient) < 1e-10
     assert np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10) and np.allclose(lk_o, zo.lk_value, rtol=1e-10, atol=1e-10)
     assert rel_err(o["dr"].T, zo.lk_gradient) < 1e-10
+
+
+# ------------------------------------------------------------------------------- data-race check of the kernel sources
+_RACE_BUILDS = {  # name -> compile-time definitions for tests/simt_emu/race_main.cpp
+    "nuts": ["-DRACE_NUTS"],
+    "nuts-staged": ["-DRACE_NUTS", "-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_FULLTILE=1", "-DAHMC_NUTS_RELOAD_COEF=1"],
+    "nuts-staged-two-chains-per-warp": ["-DRACE_NUTS", "-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=1"],
+    "dense": ["-DRACE_DENSE"],
+    "dense-staged": ["-DRACE_DENSE", "-DAHMC_DENSE_PADDED_A=1", "-DAHMC_DENSE_MBAR_RELEASE=1", "-DAHMC_DENSE_STAGES=3"],
+    "dense-mutant": ["-DRACE_DENSE"]}  # a copy of ahmc_dense.cu with one barrier removed: the detector must fire
+
+
+@pytest.fixture(scope="module")
+def _race_bins(tmp_path_factory):
+    tmp = tmp_path_factory.mktemp("simt_race")
+    d = os.path.join(ROOT, "tests", "simt_emu")
+    csrc = os.path.join(ROOT, "advancedhmc.jl_b200", "csrc")
+    src = open(os.path.join(csrc, "ahmc_dense.cu")).read()
+    barrier = "= v[rb][cb][j];\n    __syncthreads();"  # tile_to_smem: publish the staged vectors to the other warps
+    assert src.count(barrier) == 1
+    mut = tmp / "mutant"
+    mut.mkdir()
+    (mut / "ahmc_dense.cu").write_text(src.replace(barrier, "= v[rb][cb][j];"))
+    procs = {}
+    for name, defs in _RACE_BUILDS.items():
+        out = tmp / f"race_{name}"
+        inc = ["-I", str(mut)] if name == "dense-mutant" else []
+        cmd = ["g++", *defs, "-w", "-O1", "-g", "-std=c++20", "-pthread", "-fsanitize=thread", "-ffp-contract=off", "-x", "c++", *inc,
+               "-I", os.path.join(d, "include"), "-I", csrc, "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"),
+               os.path.join(d, "race_main.cpp"), "-o", str(out)]
+        procs[name] = (subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True), out)
+    bins = {}
+    for name, (pr, out) in procs.items():
+        _, err = pr.communicate()
+        if pr.returncode != 0 and ("tsan" in err.lower() or "sanitize" in err.lower()):
+            pytest.skip("ThreadSanitizer runtime not available to g++ here")
+        assert pr.returncode == 0, err[-2000:]
+        bins[name] = str(out)
+    return bins
+
+
+@pytest.mark.parametrize("name", list(_RACE_BUILDS))
+def test_kernel_sources_are_data_race_free_under_thread_sanitizer(_race_bins, name):
+    """Every CUDA thread is a host thread whose only synchronisation is what the kernel asks for, so ThreadSanitizer sees a
+    missing __syncwarp / __syncthreads / mbarrier wait as a data race: the shipped NUTS and dense-tile sources and their
+    staged variants must be clean, and a copy of the dense kernel with one barrier removed must be reported."""
+    r = subprocess.run([_race_bins[name]], capture_output=True, text=True, timeout=600)
+    if "FATAL: ThreadSanitizer" in r.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this environment: " + r.stderr.strip().splitlines()[0])
+    races = r.stderr.count("WARNING: ThreadSanitizer: data race")
+    if name == "dense-mutant":
+        assert races > 0 and "dense_traj_kernel" in r.stderr
+    else:
+        assert races == 0 and r.returncode == 0, r.stderr[-3000:] + r.stdout[-500:]
+        assert r.stdout.count("rc 0") == (7 if name.startswith("nuts") else 4)
