@@ -1277,18 +1277,9 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
         ad.kappa = cfg->kappa;
         ad.adapt_metric = cfg->adapt_metric ? 1 : 0;
         ad.n_min = cfg->n_min > 0 ? cfg->n_min : 10;
-        // initialize!(StanHMCAdaptorState, ...) (stan_adaptor.jl:13-50)
-        ad.window_start = cfg->init_buffer + 1;
-        ad.window_end = cfg->n_adapts - cfg->term_buffer;
-        ad.n_splits = 0;
-        long long wsz = cfg->window_size, next = (long long)cfg->init_buffer + wsz;
-        while (next <= ad.window_end && ad.n_splits < 12) {
-            if (next + 2 * wsz > ad.window_end) next = ad.window_end;
-            ad.splits[ad.n_splits++] = (int)next;
-            wsz *= 2;
-            next += wsz;
-        }
-        if (ad.n_splits > 0 && ad.splits[ad.n_splits - 1] == cfg->n_adapts) --ad.n_splits;
+        if (!stan_window_schedule(ad, cfg->init_buffer, cfg->term_buffer, cfg->window_size, cfg->n_adapts))
+            return fail(ctx, AHMC_ERR_UNSUPPORTED, "the window schedule (stan_adaptor.jl:13-50) needs more than %d splits",
+                        (int)(sizeof(ad.splits) / sizeof(ad.splits[0])));
         if ((rc = st.inout(cfg->eps_chain, (size_t)N, &ad.eps))) return rc;
         a.eps_chain = ad.eps;
         if ((rc = st.out(cfg->Minv_chain, (size_t)N * D, &ad.minv))) return rc;

@@ -91,6 +91,24 @@ struct AdaptDev {
     double* minv;                    // N*D, out: adapted diagonal M^-1 per chain (nullable when !adapt_metric)
     double* eps_trace;               // nullable, n_transitions x N: step size used by each transition
 };
+// initialize!(StanHMCAdaptorState, init_buffer, term_buffer, window_size, n_adapts) (stan_adaptor.jl:13-50): the
+// host side of the in-launch adaptation.  false: the schedule needs more window splits than AdaptDev holds.
+inline bool stan_window_schedule(AdaptDev& ad, int init_buffer, int term_buffer, int window_size, int n_adapts) {
+    constexpr int kMaxSplits = (int)(sizeof(ad.splits) / sizeof(ad.splits[0]));
+    ad.window_start = init_buffer + 1;
+    ad.window_end = n_adapts - term_buffer;
+    ad.n_splits = 0;
+    long long wsz = window_size, next = (long long)init_buffer + wsz;
+    while (next <= ad.window_end) {
+        if (next + 2 * wsz > ad.window_end) next = ad.window_end;  // the last window runs to the end of the slow phase
+        if (ad.n_splits == kMaxSplits) return false;
+        ad.splits[ad.n_splits++] = (int)next;
+        wsz *= 2;
+        next += wsz;
+    }
+    if (ad.n_splits > 0 && ad.splits[ad.n_splits - 1] == n_adapts) --ad.n_splits;  // "avoid updating in the end"
+    return true;
+}
 
 struct NutsArgs {
     ModelDev model;

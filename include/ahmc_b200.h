@@ -228,7 +228,8 @@ int ahmc_nuts_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metr
  * that chain only (the reference reverts every chain, "buggy for batch mode" by its own comment, stepsize.jl:199-203). */
 typedef struct ahmc_adapt_cfg {
     int32_t n_adapts;                             /* 0 <= n_adapts <= n_transitions */
-    int32_t init_buffer, term_buffer, window_size; /* Stan defaults 75 / 50 / 25 */
+    int32_t init_buffer, term_buffer, window_size; /* Stan defaults 75 / 50 / 25; a schedule with more than 12 window
+                                                      ends (tiny window_size, huge n_adapts) -> AHMC_ERR_UNSUPPORTED */
     double delta, gamma, t0, kappa;               /* 0.8, 0.05, 10, 0.75 (stepsize.jl:162-172) */
     int32_t adapt_metric;                         /* 0: step size only; 1: + per-chain WelfordVar */
     int32_t n_min;                                /* WelfordVar n_min, 10 (massmatrix.jl:103-107) */

@@ -91,6 +91,15 @@ static KernelFn by_model(int model, int metric, int G, int E) {
     return nullptr;
 }
 
+// the product's host-side window schedule (ahmc_kernels.cuh), for the comparison with the oracle's
+extern "C" int emu_window_schedule(int init_buffer, int term_buffer, int window_size, int n_adapts, int* ws, int* we, int* splits) {
+    AdaptDev ad{};
+    if (!stan_window_schedule(ad, init_buffer, term_buffer, window_size, n_adapts)) return -1;
+    *ws = ad.window_start;
+    *we = ad.window_end;
+    for (int i = 0; i < ad.n_splits; ++i) splits[i] = ad.splits[i];
+    return ad.n_splits;
+}
 extern "C" int emu_fastdraw() { return AHMC_NUTS_FASTDRAW; }
 extern "C" int emu_altlayout() { return AHMC_NUTS_ALT_LAYOUT; }
 extern "C" int emu_fulltile() { return AHMC_NUTS_FULLTILE; }
@@ -148,17 +157,7 @@ extern "C" int emu_nuts(const EmuNuts* q) {
         ad.delta = q->delta; ad.gamma = q->gamma; ad.t0 = q->t0; ad.kappa = q->kappa;
         ad.adapt_metric = q->adapt_metric;
         ad.n_min = q->n_min;
-        ad.window_start = q->init_buffer + 1;  // same schedule code as nuts_impl (ahmc_api.cu)
-        ad.window_end = q->n_adapts - q->term_buffer;
-        ad.n_splits = 0;
-        long long wsz = q->window_size, next = (long long)q->init_buffer + wsz;
-        while (next <= ad.window_end && ad.n_splits < 12) {
-            if (next + 2 * wsz > ad.window_end) next = ad.window_end;
-            ad.splits[ad.n_splits++] = (int)next;
-            wsz *= 2;
-            next += wsz;
-        }
-        if (ad.n_splits > 0 && ad.splits[ad.n_splits - 1] == q->n_adapts) --ad.n_splits;
+        if (!stan_window_schedule(ad, q->init_buffer, q->term_buffer, q->window_size, q->n_adapts)) return -3;  // as nuts_impl
         ad.eps = q->eps_rw;
         a.eps_chain = q->eps_rw;
         ad.minv = q->minv_rw;

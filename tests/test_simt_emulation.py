@@ -703,3 +703,21 @@ def test_kernel_sources_are_data_race_free_under_thread_sanitizer(_race_bins, na
     else:
         assert races == 0 and r.returncode == 0, r.stderr[-3000:] + r.stdout[-500:]
         assert r.stdout.count("rc 0") == (7 if name.startswith("nuts") else 5 if name == "lf" else 4)
+
+
+def test_host_window_schedule_of_the_in_launch_adaptation_equals_the_oracle(emu):
+    """`stan_window_schedule` (ahmc_kernels.cuh: the host code `ahmc_nuts_adapt_sample_f64` runs before the launch) against
+    the oracle's `initialize!` restatement for every n_adapts up to 1300 and several buffer settings; the reference's own
+    expectation for n_adapts = 1000 (test/adaptation.jl:131-151); more splits than the device struct holds is refused."""
+    ws, we, sp = C.c_int(), C.c_int(), (C.c_int * 16)()
+    n = emu.emu_window_schedule(75, 50, 25, 1000, C.byref(ws), C.byref(we), sp)
+    assert (ws.value, we.value, list(sp[:n])) == (76, 950, [100, 150, 250, 450, 950])
+    for ib, tb, wsz in ((75, 50, 25), (3, 2, 4), (0, 0, 1), (10, 0, 7), (100, 100, 50)):
+        for n_adapts in range(0, 1301):
+            n = emu.emu_window_schedule(ib, tb, wsz, n_adapts, C.byref(ws), C.byref(we), sp)
+            ows, owe, osp = oc.stan_windows(n_adapts, ib, tb, wsz)
+            if len(osp) > 12:
+                assert n == -1
+                continue
+            assert (ws.value, we.value, list(sp[:n])) == (ows, owe, osp), (ib, tb, wsz, n_adapts)
+    assert emu.emu_window_schedule(0, 0, 1, 100000, C.byref(ws), C.byref(we), sp) == -1
