@@ -655,6 +655,8 @@ _RACE_BUILDS = {  # name -> compile-time definitions for tests/simt_emu/race_mai
     "nuts-staged": ["-DRACE_NUTS", "-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_FULLTILE=1", "-DAHMC_NUTS_RELOAD_COEF=1"],
     "nuts-staged-two-chains-per-warp": ["-DRACE_NUTS", "-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=1"],
     "lf": ["-DRACE_LF"],
+    "multinomial": ["-DRACE_MN"],
+    "adapt": ["-DRACE_ADAPT"],
     "dense": ["-DRACE_DENSE"],
     "dense-staged": ["-DRACE_DENSE", "-DAHMC_DENSE_PADDED_A=1", "-DAHMC_DENSE_MBAR_RELEASE=1", "-DAHMC_DENSE_STAGES=3"],
     "dense-mutant": ["-DRACE_DENSE"]}  # a copy of ahmc_dense.cu with one barrier removed: the detector must fire
@@ -692,8 +694,8 @@ def _race_bins(tmp_path_factory):
 @pytest.mark.parametrize("name", list(_RACE_BUILDS))
 def test_kernel_sources_are_data_race_free_under_thread_sanitizer(_race_bins, name):
     """Every CUDA thread is a host thread whose only synchronisation is what the kernel asks for, so ThreadSanitizer sees a
-    missing __syncwarp / __syncthreads / mbarrier wait as a data race: the shipped NUTS, trajectory / HMC and dense-tile sources and
-    their staged variants must be clean, and a copy of the dense kernel with one barrier removed must be reported."""
+    missing __syncwarp / __syncthreads / mbarrier wait as a data race: the shipped NUTS, trajectory / HMC, MultinomialTS, adaptor-statistics
+    and dense-tile sources and their staged variants must be clean, and a copy of the dense kernel with one barrier removed must be reported."""
     r = subprocess.run([_race_bins[name]], capture_output=True, text=True, timeout=600)
     if "FATAL: ThreadSanitizer" in r.stderr:
         pytest.skip("ThreadSanitizer cannot run in this environment: " + r.stderr.strip().splitlines()[0])
@@ -702,7 +704,7 @@ def test_kernel_sources_are_data_race_free_under_thread_sanitizer(_race_bins, na
         assert races > 0 and "dense_traj_kernel" in r.stderr
     else:
         assert races == 0 and r.returncode == 0, r.stderr[-3000:] + r.stdout[-500:]
-        assert r.stdout.count("rc 0") == (7 if name.startswith("nuts") else 5 if name == "lf" else 4)
+        assert r.stdout.count("rc 0") == {"nuts": 7, "lf": 5, "dense": 4, "multinomial": 3, "adapt": 1}[name.split("-")[0]]
 
 
 def test_host_window_schedule_of_the_in_launch_adaptation_equals_the_oracle(emu):
