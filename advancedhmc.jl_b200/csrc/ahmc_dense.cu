@@ -27,7 +27,9 @@ constexpr int kKC = 16;             // columns of A per pipeline stage
 //                             (Dp + 4), so a 16-column chunk is ONE contiguous bulk copy instead of sixteen;
 //   AHMC_DENSE_MBAR_RELEASE   consumers release a stage through an "empty" mbarrier (one arrival per warp) and only the
 //                             producer thread waits on it, instead of a CTA-wide __syncthreads per chunk;
-//   AHMC_DENSE_STAGES         depth of the A pipeline (2; 3 needs AHMC_DENSE_MBAR_RELEASE).
+//   AHMC_DENSE_STAGES         depth of the A pipeline (2; 3 needs AHMC_DENSE_MBAR_RELEASE).  Shared memory with 3 stages:
+//                             68 KB per CTA at Dp = 128 (two CTAs per SM still fit), 232,272 of the 232,448 bytes a CTA
+//                             may have at Dp = 512.
 #ifndef AHMC_DENSE_MBAR_RELEASE
 #define AHMC_DENSE_MBAR_RELEASE 0
 #endif
