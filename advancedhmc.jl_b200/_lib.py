@@ -59,6 +59,7 @@ PROTOTYPES = {
     "ahmc_last_error": (C.c_char_p, [_vp]),
     "ahmc_synchronize": (C.c_int, [_vp]),
     "ahmc_launch_count": (C.c_int64, [_vp]),
+    "ahmc_last_transport": (C.c_char_p, [_vp]),
     "ahmc_model_create": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp, _dp, C.c_double, C.POINTER(_vp)]),
     "ahmc_model_create_callback": (C.c_int, [_vp, C.c_int32, LOGP_GRAD_FN, _vp, C.POINTER(_vp)]),
     "ahmc_model_destroy": (C.c_int, [_vp, _vp]),

@@ -66,6 +66,10 @@ class Context:
     def synchronize(self):
         self.check(self.lib.ahmc_synchronize(self.h))
 
+    def last_transport(self) -> str:
+        """how the last host-buffer `step` moved its buffers (ahmc_last_transport)"""
+        return self.lib.ahmc_last_transport(self.h).decode()
+
 
 def get_context(device: int = 0, stream: Optional[int] = None) -> Context:
     """The process-wide context of `device`.  Pass `stream` (a raw cudaStream_t, e.g.

@@ -47,6 +47,17 @@ struct ahmc_ctx {
     cudaStream_t pipe[kPipeStreams] = {};
     cudaEvent_t ev_a = nullptr, ev_join[kPipeStreams] = {};
     cudaEvent_t ev_in[kMaxPipeChunks][3] = {}, ev_k[kMaxPipeChunks] = {};
+    // transport choice of the host-buffer lane, measured per problem shape on its first calls (leapfrog_host_pipelined)
+    struct PipeTune {
+        int64_t N;
+        int32_t D;
+        int key;       // has_g | has_dr << 1 | per-chain eps << 2 | per-chain Minv << 3
+        int calls;     // trial calls made so far
+        int chosen;    // -1 while measuring
+        double best_ms[8];
+    };
+    std::vector<PipeTune> tune;
+    std::string transport = "none";  // what the last host-buffer call used (ahmc_last_transport)
 };
 
 struct ahmc_model {
@@ -103,10 +114,14 @@ public:
     Stager(ahmc_ctx* c, bool host) : ctx_(c), host_(host) {}
     // first pass: reserve; second pass: bind.  (two passes so the arena is sized before any copy)
     size_t need = 0;
+    // `bytes` may cover several arrays that are later carved one by one (each rounded up to 256 B on its own):
+    // kSlack pays for those roundings (every call site stages fewer than kSlack / 256 arrays)
+    static constexpr size_t kSlack = 64 * 256;
     void reserve(size_t bytes) { need += (bytes + 255) & ~(size_t)255; }
     int prepare() {
         if (!host_) return AHMC_OK;
         ahmc_ctx* ctx = ctx_;
+        need += kSlack;
         if (need > ctx->arena_bytes) {
             if (ctx->arena) {
                 CU(cudaStreamSynchronize(ctx->stream));
@@ -128,6 +143,7 @@ public:
         if (!host_) { *d = h; return AHMC_OK; }
         ahmc_ctx* ctx = ctx_;
         T* p = (T*)alloc(count * sizeof(T));
+        if (!p) return overflow();
         CU(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
         *d = p;
         return AHMC_OK;
@@ -137,6 +153,7 @@ public:
         if (!h) { *d = nullptr; return AHMC_OK; }
         if (!host_) { *d = h; return AHMC_OK; }
         T* p = (T*)alloc(count * sizeof(T));
+        if (!p) return overflow();
         outs_.push_back({(void*)h, (void*)p, count * sizeof(T)});
         *d = p;
         return AHMC_OK;
@@ -147,6 +164,7 @@ public:
         if (!host_) { *d = h; return AHMC_OK; }
         ahmc_ctx* ctx = ctx_;
         T* p = (T*)alloc(count * sizeof(T));
+        if (!p) return overflow();
         CU(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
         outs_.push_back({(void*)h, (void*)p, count * sizeof(T)});
         *d = p;
@@ -161,11 +179,14 @@ public:
 
 private:
     struct Out { void* h; void* d; size_t bytes; };
-    void* alloc(size_t bytes) {
+    void* alloc(size_t bytes) {  // nullptr when the reservation pass undercounted: never hand out memory past the arena
+        const size_t b = (bytes + 255) & ~(size_t)255;
+        if (off_ + b > ctx_->arena_bytes) return nullptr;
         void* p = ctx_->arena + off_;
-        off_ += (bytes + 255) & ~(size_t)255;
+        off_ += b;
         return p;
     }
+    int overflow() { return fail(ctx_, AHMC_ERR_NOMEM, "internal: host-buffer staging arena undersized (%zu of %zu bytes used)", off_, ctx_->arena_bytes); }
     ahmc_ctx* ctx_;
     bool host_;
     size_t off_ = 0;
@@ -329,7 +350,7 @@ int try_dense_trajectory(ahmc_ctx* ctx, const ahmc_model* model, LeapfrogArgs& a
     const bool metric_ok = a.metric.kind != AHMC_METRIC_DIAG || a.metric.chain_stride == 0;
     const bool has_dense = model->kind == AHMC_MODEL_DENSE_GAUSS || a.metric.kind == AHMC_METRIC_DENSE;
     int Dp, RB, CB;
-    if (!(gauss && metric_ok && has_dense && !compat && !(a.flags & AHMC_FLAG_EXACT_CHECKS) && !(temper_alpha > 0.0) &&
+    if (!(gauss && metric_ok && has_dense && !compat && a.g_in && !(a.flags & AHMC_FLAG_EXACT_CHECKS) && !(temper_alpha > 0.0) &&
           dense_tile_shape(D, &Dp, &RB, &CB) && (model->kind != AHMC_MODEL_DENSE_GAUSS || model->d_p1_pad)))
         return 0;
     auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -455,6 +476,7 @@ int ahmc_synchronize(ahmc_ctx* ctx) {
 }
 
 int64_t ahmc_launch_count(const ahmc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* ahmc_last_transport(const ahmc_ctx* ctx) { return ctx ? ctx->transport.c_str() : "none"; }
 
 // ---------------------------------------------------------------------------------------------- models
 int ahmc_model_create(ahmc_ctx* ctx, int32_t kind, int32_t D, const double* p0, const double* p1, double c0,
@@ -670,15 +692,49 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
 
     const double t_attr = since();
     enum { UP_CE1, UP_CE3, UP_DIRECT };
+    const bool has_g = z_in->lp_gradient != nullptr;
     int up = in_pinned ? UP_DIRECT : UP_CE1;
     bool down_direct = out_pinned;
+    int occ_cap = AHMC_PIPE_DIRECT_OCC;
+    int nchunk = 0;
+    // ---- transport choice.  Page-locked buffers can be moved in several ways whose ranking depends on the HOST (the
+    // zero-copy lane measured 0.36 ms on one box and 3.8 ms on another: SM-issued reads of system memory are at the mercy
+    // of the platform's read-completion latency, copy engines are not), so the first calls of a given shape try each
+    // candidate in turn -- results are bit-identical in every mode, nothing extra is executed -- and the fastest is kept
+    // for the life of the context.  Candidates: {direct loads + direct stores, 1 CTA/SM}, {copy engines, 2 / 4 chunks},
+    // {copy-engine upload, direct stores, 4 chunks}.  The AHMC_PIPE_* variables pin the choice (A/B runs).
+    struct Cand { int up; bool down_direct; int chunks; int occ; };
+    static const Cand kCands[] = {{UP_DIRECT, true, 1, 1}, {UP_CE1, false, 2, 0}, {UP_CE1, false, 4, 0}, {UP_CE1, true, 4, 1}};
+    constexpr int kNCand = 4, kRounds = 3;  // round 0 warms every candidate up (arena growth, first-touch), rounds 1.. are timed
+    const bool pinned_env = getenv("AHMC_PIPE_UP") || getenv("AHMC_PIPE_DOWN") || getenv("AHMC_PIPE_CHUNKS") || getenv("AHMC_PIPE_OCC");
+    const bool tunable = in_pinned && out_pinned && !pinned_env && N >= 1024 && !((ev = getenv("AHMC_PIPE_AUTOTUNE")) && atoi(ev) == 0);
+    ahmc_ctx::PipeTune* tune = nullptr;
+    int trial = -1;
+    if (tunable) {
+        const int key = (has_g ? 1 : 0) | (z_out->lk_gradient ? 2 : 0) | (eps_chain ? 4 : 0) | (per_chain_minv ? 8 : 0);
+        for (auto& t : ctx->tune)
+            if (t.N == N && t.D == D && t.key == key) tune = &t;
+        if (!tune) {
+            ahmc_ctx::PipeTune t{};
+            t.N = N; t.D = D; t.key = key; t.calls = 0; t.chosen = -1;
+            for (double& b : t.best_ms) b = 1e30;
+            ctx->tune.push_back(t);
+            tune = &ctx->tune.back();
+        }
+        int c = tune->chosen;
+        if (c < 0) {
+            trial = tune->calls % kNCand;
+            c = trial;
+        }
+        up = kCands[c].up; down_direct = kCands[c].down_direct; nchunk = kCands[c].chunks; occ_cap = kCands[c].occ;
+    }
     if ((ev = getenv("AHMC_PIPE_UP"))) up = !strcmp(ev, "direct") ? UP_DIRECT : !strcmp(ev, "ce3") ? UP_CE3 : UP_CE1;
     if ((ev = getenv("AHMC_PIPE_DOWN"))) down_direct = !strcmp(ev, "direct");
     if (!in_pinned && up == UP_DIRECT) up = UP_CE3;
     if (!out_pinned) down_direct = false;
     const bool trace = (ev = getenv("AHMC_PIPE_TRACE")) && atoi(ev) != 0;
-    const int occ_cap = (ev = getenv("AHMC_PIPE_OCC")) ? atoi(ev) : AHMC_PIPE_DIRECT_OCC;
-    int nchunk = (ev = getenv("AHMC_PIPE_CHUNKS")) ? atoi(ev) : 0;
+    if ((ev = getenv("AHMC_PIPE_OCC"))) occ_cap = atoi(ev);
+    if ((ev = getenv("AHMC_PIPE_CHUNKS"))) nchunk = atoi(ev);
     if (nchunk <= 0) {
         if (up == UP_DIRECT) {
             nchunk = AHMC_PIPE_DIRECT_CHUNKS;
@@ -698,7 +754,7 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
     const bool stage_in = up != UP_DIRECT, stage_out = !down_direct;
     const bool hasU = metric->kind == AHMC_METRIC_DENSE && metric->cholU;
     size_t need = (per_chain_minv && !stage_in ? 0 : al(nMinv * 8)) + (hasU ? al((size_t)D * D * 8) : 0);
-    if (stage_in) need += al((size_t)N * 8) + 3 * al((size_t)ldi * N * 8);
+    if (stage_in) need += al((size_t)N * 8) + (has_g ? 3 : 2) * al((size_t)ldi * N * 8);
     if (stage_out) need += 4 * al((size_t)ldo * N * 8) + 2 * al((size_t)N * 8) + 2 * al((size_t)N * 4);
     if (need > ctx->arena_bytes) {
         CU(cudaStreamSynchronize(ctx->stream));
@@ -723,7 +779,7 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
     double* dEps = (double*)carve(stage_in, (size_t)N * 8);
     double* dTh = (double*)carve(stage_in, (size_t)ldi * N * 8);
     double* dR = (double*)carve(stage_in, (size_t)ldi * N * 8);
-    double* dG = (double*)carve(stage_in, (size_t)ldi * N * 8);
+    double* dG = (double*)carve(stage_in && has_g, (size_t)ldi * N * 8);
     double* oTh = (double*)carve(stage_out, (size_t)ldo * N * 8);
     double* oR = (double*)carve(stage_out, (size_t)ldo * N * 8);
     double* oG = (double*)carve(stage_out, (size_t)ldo * N * 8);
@@ -771,7 +827,7 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
             if (per_chain_minv)
                 CU(cudaMemcpyAsync(dMinv + metric->chain_stride * c0, metric->Minv + metric->chain_stride * c0,
                                    (size_t)metric->chain_stride * n * 8, cudaMemcpyHostToDevice, s_up[1]));
-            CU(cudaMemcpyAsync(dG + ldi * c0, z_in->lp_gradient + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, s_up[2]));
+            if (has_g) CU(cudaMemcpyAsync(dG + ldi * c0, z_in->lp_gradient + ldi * c0, (size_t)ldi * n * 8, cudaMemcpyHostToDevice, s_up[2]));
             for (int j = 0; j < n_up; ++j) {
                 CU(cudaEventRecord(ctx->ev_in[k][j], s_up[j]));
                 CU(cudaStreamWaitEvent(s_cmp, ctx->ev_in[k][j], 0));
@@ -793,7 +849,7 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
         a.temper_alpha = temper_alpha;
         a.th_in = (stage_in ? dTh : a_th) + ldi * c0;
         a.r_in = (stage_in ? dR : a_r) + ldi * c0;
-        a.g_in = (stage_in ? dG : a_g) + ldi * c0;
+        a.g_in = !has_g ? nullptr : (stage_in ? dG : a_g) + ldi * c0;
         a.ld_in = ldi;
         a.th_out = (stage_out ? oTh : b_th) + ldo * c0;
         a.r_out = (stage_out ? oR : b_r) + ldo * c0;
@@ -838,6 +894,26 @@ static int leapfrog_host_pipelined(ahmc_ctx* ctx, const ahmc_model* model, const
     // host buffers are valid once everything joined into the context stream has retired
     const double t_issued = since();
     CU(cudaStreamSynchronize(s_cmp));
+    {
+        char buf[96];
+        snprintf(buf, sizeof buf, "up=%s down=%s chunks=%d%s%s", up == UP_DIRECT ? "direct" : up == UP_CE3 ? "ce3" : "ce1",
+                 down_direct ? "direct" : "ce", k, (!stage_in || !stage_out) && occ_cap > 0 ? " occ=1" : "",
+                 tune ? (tune->chosen >= 0 ? " (autotuned)" : " (autotune trial)") : "");
+        ctx->transport = buf;
+    }
+    if (tune && trial >= 0) {
+        const double ms = since();
+        if (tune->calls >= kNCand && ms < tune->best_ms[trial]) tune->best_ms[trial] = ms;
+        if (++tune->calls >= kNCand * kRounds) {
+            int best = 0;
+            for (int c = 1; c < kNCand; ++c)
+                if (tune->best_ms[c] < tune->best_ms[best]) best = c;
+            tune->chosen = best;
+            if (trace)
+                fprintf(stderr, "[ahmc pipe] autotune N=%lld D=%d: %.3f %.3f %.3f %.3f ms -> candidate %d\n", (long long)N, D,
+                        tune->best_ms[0], tune->best_ms[1], tune->best_ms[2], tune->best_ms[3], best);
+        }
+    }
     if (trace)
         fprintf(stderr, "[ahmc pipe] host ms: pointer queries %.3f, everything issued %.3f, synchronised %.3f\n", t_attr,
                 t_issued, since());
@@ -863,12 +939,19 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
     if (!ctx || !model || !metric) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
-    if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
+    // z_in: only theta and r are required.  The cached energies are not read, and a NULL z_in->lp_gradient means "not
+    // cached": built-in targets recompute dH/dtheta at the start point on the device (bit-identical to the value
+    // phasepoint / a previous step produced), which saves a third of the upload of a host-buffer call.
+    if ((rc = check_pp(ctx, z_in, D, "z_in", false, N))) return rc;
     if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
     if (N == 0) return AHMC_OK;
+    if (!z_in->lp_gradient && model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_INVALID, "z_in.lp_gradient is NULL: a callback target needs the cached gradient (call ahmc_phasepoint_f64 first)");
     DeviceGuard g(ctx->device);
     const bool host = flags & AHMC_FLAG_HOST_BUFFERS;
     const int n_abs = n_steps < 0 ? -n_steps : n_steps;
+    if (n_abs == 0 && !z_in->lp_gradient)
+        return fail(ctx, AHMC_ERR_INVALID, "n_steps == 0 returns z unchanged and needs z_in.lp_gradient");
     if (n_abs == 0) {  // the loop body never runs: z is returned unchanged (integrator.jl:233)
         rc = copy_pp_device(ctx, D, N, z_in, z_out, host ? cudaMemcpyHostToHost : cudaMemcpyDeviceToDevice);
         if (rc) return rc;

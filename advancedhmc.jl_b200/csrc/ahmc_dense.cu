@@ -22,23 +22,15 @@ namespace ahmc {
 
 constexpr int kDenseThreads = 256;  // 8 warps
 constexpr int kKC = 16;             // columns of A per pipeline stage
-// Staged pipeline knobs (all OFF in the shipped build; each verified under the CPU SIMT emulator, tests/simt_emu/dense_emu.cpp):
-//   AHMC_DENSE_PADDED_A (ahmc_kernels.cuh)  the padded matrix is stored with the shared-memory stage's leading dimension
-//                             (Dp + 4), so a 16-column chunk is ONE contiguous bulk copy instead of sixteen;
-//   AHMC_DENSE_MBAR_RELEASE   consumers release a stage through an "empty" mbarrier (one arrival per warp) and only the
-//                             producer thread waits on it, instead of a CTA-wide __syncthreads per chunk;
-//   AHMC_DENSE_STAGES         depth of the A pipeline (2; 3 needs AHMC_DENSE_MBAR_RELEASE).  Shared memory with 3 stages:
-//                             68 KB per CTA at Dp = 128 (two CTAs per SM still fit), 232,272 of the 232,448 bytes a CTA
-//                             may have at Dp = 512.
-#ifndef AHMC_DENSE_MBAR_RELEASE
-#define AHMC_DENSE_MBAR_RELEASE 0
-#endif
-#ifndef AHMC_DENSE_STAGES
-#define AHMC_DENSE_STAGES 2
-#endif
-constexpr int kStages = AHMC_DENSE_STAGES;
-static_assert(kStages == 2 || (kStages == 3 && AHMC_DENSE_MBAR_RELEASE), "AHMC_DENSE_STAGES: 2, or 3 with AHMC_DENSE_MBAR_RELEASE");
-constexpr int kBars = AHMC_DENSE_MBAR_RELEASE ? 2 * kStages : kStages;  // full[kStages] (+ empty[kStages])
+// A pipeline (measured on B200 in round 2, profiles/r02/k4_ab.md: 15.0 -> 20.2 TFLOP/s at 4096 x 128, 16.0 -> 24.7 at 16384):
+//   * the padded matrix is stored with the shared-memory stage's leading dimension (Dp + 4, ahmc_kernels.cuh dense_lda), so a
+//     16-column chunk is ONE contiguous bulk copy instead of sixteen;
+//   * consumers release a stage through an "empty" mbarrier (one arrival per warp) and only the producer thread waits on it,
+//     instead of a CTA-wide __syncthreads per chunk;
+//   * three stages.  Shared memory: 68 KB per CTA at Dp = 128 (two CTAs per SM still fit), 232,272 of the 232,448 bytes a CTA
+//     may have at Dp = 512.
+constexpr int kStages = 3;
+constexpr int kBars = 2 * kStages;  // full[kStages] + empty[kStages]
 #ifdef AHMC_SIMT_EMULATION
 extern unsigned char* emu_dynamic_smem;  // the block's dynamic shared memory (blocks run one at a time)
 #endif
@@ -99,23 +91,11 @@ __device__ __forceinline__ void tile_gemm(const double* __restrict__ A, int Dp, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Ds = Dp + 4, Dx = Dp + 4;
     const int nchunks = Dp / kKC;
-#if AHMC_DENSE_PADDED_A
     const uint32_t chunk_bytes = (uint32_t)(kKC * Ds * sizeof(double));
     auto issue = [&](int c, int stage) {  // global leading dimension == stage leading dimension: one contiguous copy
         mbar_expect_tx(&bars[stage], chunk_bytes);
         bulk_g2s(As + (size_t)stage * kKC * Ds, A + (size_t)c * kKC * Ds, chunk_bytes, &bars[stage]);
     };
-#else
-    const uint32_t chunk_bytes = (uint32_t)(kKC * Dp * sizeof(double));
-    auto issue = [&](int c, int stage) {
-        mbar_expect_tx(&bars[stage], chunk_bytes);
-        const double* src = A + (size_t)c * kKC * Dp;
-        double* dst = As + (size_t)stage * kKC * Ds;
-#pragma unroll 4
-        for (int k = 0; k < kKC; ++k) bulk_g2s(dst + (size_t)k * Ds, src + (size_t)k * Dp, (uint32_t)(Dp * sizeof(double)), &bars[stage]);
-    };
-#endif
-#if AHMC_DENSE_MBAR_RELEASE
     // Bit s of phase[0]: parity of the next "full" phase of stage s (every thread).  Producer thread only -- bit s of
     // phase[1]: parity of the number of fills f of stage s so far; of phase[2]: f > 0.  Fill f >= 1 of a stage waits for
     // the stage's (f-1)-th release: bars[kStages + s] completes one phase per consumption (8 warp arrivals), and at that
@@ -157,35 +137,6 @@ __device__ __forceinline__ void tile_gemm(const double* __restrict__ A, int Dp, 
     }
     __syncthreads();  // every warp is done with Xs; every release of this product has arrived
 }
-#else
-    if (tid == 0) {
-        issue(0, 0);
-        if (nchunks > 1) issue(1, 1);
-    }
-    const int arow = 8 * RB * warp + (lane >> 2);
-    for (int c = 0; c < nchunks; ++c) {
-        const int stage = c & 1;
-        mbar_wait(&bars[stage], phase[stage]);
-        phase[stage] ^= 1u;
-        const double* as = As + (size_t)stage * kKC * Ds;
-#pragma unroll
-        for (int ks = 0; ks < kKC / 4; ++ks) {
-            double a[RB], b[CB];
-            const int kl = 4 * ks + (lane & 3);
-#pragma unroll
-            for (int rb = 0; rb < RB; ++rb) a[rb] = as[(size_t)kl * Ds + arow + 8 * rb];
-#pragma unroll
-            for (int cb = 0; cb < CB; ++cb) b[cb] = Xs[(size_t)(8 * cb + (lane >> 2)) * Dx + c * kKC + kl];
-#pragma unroll
-            for (int rb = 0; rb < RB; ++rb)
-#pragma unroll
-                for (int cb = 0; cb < CB; ++cb) dmma(acc[rb][cb][0], acc[rb][cb][1], a[rb], b[cb]);
-        }
-        __syncthreads();  // every warp is done with this stage (and, on the last chunk, with Xs)
-        if (tid == 0 && c + 2 < nchunks) issue(c + 2, stage);
-    }
-}
-#endif
 
 template <int RB, int CB>
 __device__ __forceinline__ void tile_to_smem(double* Xs, int Dp, const double (&v)[RB][CB][2]) {
@@ -239,24 +190,15 @@ __global__ void __launch_bounds__(kDenseThreads, MINB) dense_traj_kernel(const D
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-#if AHMC_DENSE_MBAR_RELEASE
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&bars[i], 1);
             mbar_init(&bars[kStages + i], kDenseThreads / 32);
         }
-#else
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-#endif
         s_flag = 0;
         mbar_fence_init();
     }
     __syncthreads();
-#if AHMC_DENSE_MBAR_RELEASE
     uint32_t phase[kBars] = {};
-#else
-    uint32_t phase[2] = {0u, 0u};
-#endif
     const long long tile0 = (long long)blockIdx.x * CT;
     constexpr int T200 = expo_bits(200), T100 = expo_bits(100), T50 = expo_bits(50);
 
@@ -475,10 +417,8 @@ __global__ void pad_norm_kernel(const double* __restrict__ A, int D, int Dp, dou
         }
         best = (s > best || s != s) ? s : best;
     }
-#if AHMC_DENSE_PADDED_A
     if (Ap)  // the 4 padding rows of every column travel with the chunk copy: keep them defined
         for (int i = threadIdx.x; i < 4 * Dp; i += blockDim.x) Ap[(size_t)(i >> 2) * dense_lda(Dp) + Dp + (i & 3)] = 0.0;
-#endif
     smax[threadIdx.x] = best;
     __syncthreads();
     if (threadIdx.x == 0) {

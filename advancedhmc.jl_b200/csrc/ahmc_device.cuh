@@ -105,6 +105,84 @@ __device__ __forceinline__ void vstore(double* base, const double (&x)[E], int l
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// lane-contiguous vector I/O (K1 fast path, G = 32): lane l owns V = min(E, 4) CONSECUTIVE doubles of every
+// 32*V-wide block, element e  <->  d = 32*V*(e / V) + V*l + (e % V).  One 128-bit (V = 2) or 256-bit (V = 4,
+// LDG.E.256 / STG.E.256 on sm_100) access per lane per block instead of V scalar ones; a warp instruction still
+// covers one contiguous run of 32*V doubles.  Used for FULL tiles only (D == 32*E, 8*V-byte aligned rows; the host
+// checks): no bounds predicate, no zero fill.
+// ------------------------------------------------------------------------------------------------
+template <int E>
+struct Contig {
+    static constexpr int V = E >= 4 ? 4 : E;
+    static __device__ __forceinline__ int dim(int l, int e) { return 32 * V * (e / V) + V * l + (e % V); }
+};
+template <int E>
+__device__ __forceinline__ void cload(double (&x)[E], const double* base, int l, int D) {
+    constexpr int V = Contig<E>::V;
+#pragma unroll
+    for (int b = 0; b < E / V; ++b) {
+        const int d0 = 32 * V * b + V * l;
+        if constexpr (V == 4) {
+#if defined(AHMC_SIMT_EMULATION)
+            for (int j = 0; j < 4; ++j) x[4 * b + j] = base[d0 + j];
+#else
+            asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(x[4 * b]), "=d"(x[4 * b + 1]), "=d"(x[4 * b + 2]), "=d"(x[4 * b + 3])
+                         : "l"(base + d0));
+#endif
+        } else if constexpr (V == 2) {
+            double2 v = *reinterpret_cast<const double2*>(base + d0);
+            x[2 * b] = v.x; x[2 * b + 1] = v.y;
+        } else {
+            x[b] = base[d0];
+        }
+    }
+}
+template <int E>
+__device__ __forceinline__ void cstore(double* base, const double (&x)[E], int l, int D) {
+    constexpr int V = Contig<E>::V;
+#pragma unroll
+    for (int b = 0; b < E / V; ++b) {
+        const int d0 = 32 * V * b + V * l;
+        if constexpr (V == 4) {
+#if defined(AHMC_SIMT_EMULATION)
+            for (int j = 0; j < 4; ++j) base[d0 + j] = x[4 * b + j];
+#else
+            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(base + d0), "d"(x[4 * b]), "d"(x[4 * b + 1]),
+                         "d"(x[4 * b + 2]), "d"(x[4 * b + 3]) : "memory");
+#endif
+        } else if constexpr (V == 2) {
+            *reinterpret_cast<double2*>(base + d0) = make_double2(x[2 * b], x[2 * b + 1]);
+        } else {
+            base[d0] = x[b];
+        }
+    }
+}
+// vector load in the layout a trajectory functor asks for (coefficients follow the state's layout)
+template <bool CONTIG, int G, int E>
+__device__ __forceinline__ void lload(double (&x)[E], const double* base, int l, int D) {
+    if constexpr (CONTIG) cload<E>(x, base, l, D);
+    else vload<G, E>(x, base, l, D);
+}
+template <bool CONTIG, int G, int E>
+__device__ __forceinline__ bool lin(int l, int e, int D) { return CONTIG ? true : (l + G * e) < D; }
+
+// max over the group of a 32-bit unsigned (one REDUX for a full warp)
+template <int G>
+__device__ __forceinline__ unsigned grp_umax(unsigned v) {
+    if constexpr (G == 32) {
+        return __reduce_max_sync(FULL, v);
+    } else {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const unsigned w = __shfl_xor_sync(FULL, v, o);
+            v = w > v ? w : v;
+        }
+        return v;
+    }
+}
+
 // y = A x for a D x D column-major matrix in global memory, x/y group-distributed.
 // xs: this group's private slab of >= D doubles in shared memory.  (Dense metric / dense Gaussian
 // target; the register-tiled CTA kernel for these shapes is a separate code path.)

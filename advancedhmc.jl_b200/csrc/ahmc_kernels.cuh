@@ -229,10 +229,8 @@ struct DenseTrajHost {
     uint8_t* need_exact;
 };
 bool dense_tile_shape(int D, int* Dp, int* RB, int* CB);
-#ifndef AHMC_DENSE_PADDED_A
-#define AHMC_DENSE_PADDED_A 0  // staged (ahmc_dense.cu): store padded matrices with leading dimension Dp + 4
-#endif
-__host__ __device__ constexpr int dense_lda(int Dp) { return AHMC_DENSE_PADDED_A ? Dp + 4 : Dp; }
+// padded matrices (K4) are stored with the shared-memory stage's leading dimension: a 16-column chunk is one bulk copy
+__host__ __device__ constexpr int dense_lda(int Dp) { return Dp + 4; }
 __host__ __device__ constexpr size_t dense_mat_doubles(int Dp) { return (size_t)Dp * (size_t)dense_lda(Dp); }
 cudaError_t launch_dense_traj(const DenseTrajHost& h, cudaStream_t stream, int* n_launches);
 cudaError_t launch_pad_norm(const double* A, int D, int Dp, double* Ap, double* norm, cudaStream_t st);

@@ -38,23 +38,28 @@ bool pick_layout(int D, int* G, int* E) {
     return false;
 }
 
-// K1 functor: start state = z_in, end state -> z_out (+ status / steps_done / min_break)
-template <int G, int E>
+// K1 functor: start state = z_in, end state -> z_out (+ status / steps_done / min_break).  CONTIG: the fast path moves
+// the state with lane-contiguous 128/256-bit accesses (init_c / done_c); the exact path always uses the interleaved form.
+template <int G, int E, bool CONTIG = false>
 struct StepIO {
+    static constexpr bool kContig = CONTIG;
     const LeapfrogArgs& a;
     long long chain;
     int l;
+    __device__ __forceinline__ bool has_g() const { return a.g_in != nullptr; }
     __device__ __forceinline__ void init(double (&th)[E], double (&r)[E], double (&g)[E]) const {
         vload_nc<G, E>(th, a.th_in + a.ld_in * chain, l, a.D);
         vload_nc<G, E>(r, a.r_in + a.ld_in * chain, l, a.D);
-        vload_nc<G, E>(g, a.g_in + a.ld_in * chain, l, a.D);
+        if (a.g_in) vload_nc<G, E>(g, a.g_in + a.ld_in * chain, l, a.D);
     }
-    __device__ __forceinline__ void done(const double (&th)[E], const double (&r)[E], const double (&g)[E],
-                                         const double (&dr)[E], double lp, double lk, bool fin, int steps) const {
-        vstore<G, E>(a.th_out + a.ld_out * chain, th, l, a.D);
-        vstore<G, E>(a.r_out + a.ld_out * chain, r, l, a.D);
-        vstore<G, E>(a.g_out + a.ld_out * chain, g, l, a.D);
-        if (a.dr_out) vstore<G, E>(a.dr_out + a.ld_out * chain, dr, l, a.D);
+    __device__ __forceinline__ void init_c(double (&th)[E], double (&r)[E], double (&g)[E]) const {
+        cload<E>(th, a.th_in + a.ld_in * chain, l, a.D);
+        cload<E>(r, a.r_in + a.ld_in * chain, l, a.D);
+        // issued unconditionally so that all three loads are in flight together (without a cached gradient theta is
+        // read a second time and the value ignored)
+        cload<E>(g, (a.g_in ? a.g_in : a.th_in) + a.ld_in * chain, l, a.D);
+    }
+    __device__ __forceinline__ void scalars(double lp, double lk, bool fin, int steps) const {
         if (l == 0) {
             a.lp_out[chain] = lp;
             a.lk_out[chain] = lk;
@@ -62,6 +67,22 @@ struct StepIO {
             if (a.steps_done) a.steps_done[chain] = steps;
             if (!fin && a.min_break) atomicMin(a.min_break, steps);
         }
+    }
+    __device__ __forceinline__ void done(const double (&th)[E], const double (&r)[E], const double (&g)[E],
+                                         const double (&dr)[E], double lp, double lk, bool fin, int steps) const {
+        vstore<G, E>(a.th_out + a.ld_out * chain, th, l, a.D);
+        vstore<G, E>(a.r_out + a.ld_out * chain, r, l, a.D);
+        vstore<G, E>(a.g_out + a.ld_out * chain, g, l, a.D);
+        if (a.dr_out) vstore<G, E>(a.dr_out + a.ld_out * chain, dr, l, a.D);
+        scalars(lp, lk, fin, steps);
+    }
+    __device__ __forceinline__ void done_c(const double (&th)[E], const double (&r)[E], const double (&g)[E],
+                                           const double (&dr)[E], double lp, double lk, bool fin, int steps) const {
+        cstore<E>(a.th_out + a.ld_out * chain, th, l, a.D);
+        cstore<E>(a.r_out + a.ld_out * chain, r, l, a.D);
+        cstore<E>(a.g_out + a.ld_out * chain, g, l, a.D);
+        if (a.dr_out) cstore<E>(a.dr_out + a.ld_out * chain, dr, l, a.D);
+        scalars(lp, lk, fin, steps);
     }
 };
 
@@ -74,7 +95,7 @@ constexpr int min_blocks_per_sm() {
     return (FastCapable<MODEL, METRIC>::value && E <= 4) ? 7 : 1;
 }
 
-template <int MODEL, int METRIC, int G, int E>
+template <int MODEL, int METRIC, int G, int E, bool CONTIG = false>
 __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC, E>()) leapfrog_kernel(const LeapfrogArgs a) {
     extern __shared__ double smem[];
     const int l = threadIdx.x % G;
@@ -85,7 +106,7 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC
     double* xs = smem + (size_t)grp_in_block * a.D;
     double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
     eps = a.fwd ? eps : -eps;  // integrator.jl:226
-    StepIO<G, E> io{a, chain, l};
+    StepIO<G, E, CONTIG> io{a, chain, l};
     run_trajectory<MODEL, METRIC, G, E>(a.model, a.metric, a.D, chain, valid, l, xs, eps, a.n_steps, a.temper_alpha,
                                         a.flags, io);
 }
@@ -104,6 +125,8 @@ struct HmcIO {
     double H0, lp0, lk0, ex;
     double r0[E];
 
+    static constexpr bool kContig = false;
+    __device__ __forceinline__ bool has_g() const { return true; }
     __device__ __forceinline__ void init(double (&th)[E], double (&r)[E], double (&g)[E]) const {
         vload_nc<G, E>(th, src_th, l, h.lf.D);
         vload_nc<G, E>(g, src_g, l, h.lf.D);
@@ -417,8 +440,22 @@ __global__ void __launch_bounds__(kBlockThreads) mh_select_kernel(const MhArgs a
 // ---------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------
-template <int MODEL, int METRIC, int G, int E>
-static cudaError_t launch_lf_t(const LeapfrogArgs& a, cudaStream_t st) {
+// can the fast path of this launch use the lane-contiguous vector layout?  (full tile D == 32*E, rows and coefficient
+// vectors aligned to the vector width)
+template <int E>
+static bool contig_ok(const LeapfrogArgs& a) {
+    constexpr int V = E >= 4 ? 4 : E;
+    const uintptr_t m = (uintptr_t)(8 * V - 1);
+    auto al = [&](const void* p) { return ((uintptr_t)p & m) == 0; };
+    if (a.D != 32 * E || a.ld_in % V || a.ld_out % V) return false;  // full tiles only: no bounds predicate in the kernel
+    if (!al(a.th_in) || !al(a.r_in) || !al(a.g_in) || !al(a.th_out) || !al(a.r_out) || !al(a.g_out) || !al(a.dr_out)) return false;
+    if (a.metric.kind == AHMC_METRIC_DIAG && (!al(a.metric.Minv) || a.metric.chain_stride % V)) return false;
+    if (a.model.kind == AHMC_MODEL_DIAG_GAUSS && (!al(a.model.p0) || !al(a.model.p1))) return false;
+    return true;
+}
+
+template <int MODEL, int METRIC, int G, int E, bool CONTIG>
+static cudaError_t launch_lf_c(const LeapfrogArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;
     const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
     size_t sm = smem_bytes(MODEL, METRIC, a.D, G);
@@ -429,12 +466,20 @@ static cudaError_t launch_lf_t(const LeapfrogArgs& a, cudaStream_t st) {
         if (pad > sm) sm = pad;
     }
     if (sm > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(leapfrog_kernel<MODEL, METRIC, G, E>,
+        cudaError_t e = cudaFuncSetAttribute(leapfrog_kernel<MODEL, METRIC, G, E, CONTIG>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
     }
-    leapfrog_kernel<MODEL, METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    leapfrog_kernel<MODEL, METRIC, G, E, CONTIG><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
     return cudaGetLastError();
+}
+template <int MODEL, int METRIC, int G, int E>
+static cudaError_t launch_lf_t(const LeapfrogArgs& a, cudaStream_t st) {
+    if constexpr (FastCapable<MODEL, METRIC>::value && G == 32 && E >= 2) {
+        if (!(a.flags & AHMC_FLAG_EXACT_CHECKS) && !(a.temper_alpha > 0.0) && contig_ok<E>(a))
+            return launch_lf_c<MODEL, METRIC, G, E, true>(a, st);
+    }
+    return launch_lf_c<MODEL, METRIC, G, E, false>(a, st);
 }
 template <int MODEL, int METRIC, int G, int E>
 static cudaError_t launch_pp_t(const PhasepointArgs& a, cudaStream_t st) {

@@ -46,11 +46,11 @@ __device__ __forceinline__ double logaddexp(double a, double b) {  // LogExpFunc
 }
 __device__ __forceinline__ double maxabs(double a, double b) { return fabs(a) > fabs(b) ? a : b; }  // :526
 
-constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, cand lk   (+ ww under AHMC_NUTS_FASTDRAW)
+constexpr int kLevelScalars = 7;  // lw (m), sum_alpha, n_alpha, dH_max, cand lp, cand lk, ww (w)
 
-// AHMC_NUTS_FASTDRAW (default 0 = the build every test and measurement of round 1 ran): staged instruction-count cuts
-// the K3 line profile asks for (profiles/r01/k3_source_line_profile.txt: of 882 warp-instructions per leaf, random draws
-// 24 %, logaddexp 16 %, the leaf's exp 6 %).  With 1:
+// Instruction-count cuts taken from the K3 line profile (profiles/r01/k3_source_line_profile.txt: of 882 warp-instructions
+// per leaf, random draws 24 %, logaddexp 16 %, the leaf's exp 6 %), measured on B200 in round 2 (profiles/r02/k3_ab.md:
+// +44 % / +33 % on the C3 shape at eps = 0.1 / 0.4) and tape-identical to the recursive oracle:
 //   * variates are prefetched lane-parallel: lane l of the chain's group generates uniform #(base + l) of the Philox
 //     stream (one block per LANE instead of one per DRAW), a draw is then a group broadcast of one register; direction
 //     bits come from a cached block (128 doublings each);
@@ -58,48 +58,19 @@ constexpr int kLevelScalars = 6;  // lw, sum_alpha, n_alpha, dH_max, cand lp, ca
 //     the node, w in [1, #leaves] -- and the combine decides in the probability domain, u < w_p / (w_p + w_c): one exp per
 //     combine, NO log / log1p anywhere in the tree walk (same events; oracle/nuts_iterative.py max_weights);
 //   * the acceptance statistic sum_alpha = sum over leaves of exp(min(0, -dH)) is order-free: a leaf parks dH in one
-//     lane's register and the exponentials are taken G at a time, one per lane.
-// Status: compiles for sm_100a (168 registers); its SOURCE passes the oracle comparisons, the in-launch adaptation check
-// and a draw-for-draw identity check against the default build on Philox streams under the CPU SIMT emulator
-// (tests/test_simt_emulation.py).  NOT yet run on a GPU: scripts/build_variants.sh fastdraw + scripts/gpu_fastdraw_ab.sh.
-#ifndef AHMC_NUTS_FASTDRAW
-#define AHMC_NUTS_FASTDRAW 0
-#endif
-// AHMC_NUTS_FULLTILE (default 0, staged like the knobs above): an extra instantiation for D == G * E (e.g. 128 = 32 x 4)
-// in which D is a compile-time constant -- the `d < D` guard of every vector load / store and most of the workspace
-// address arithmetic fold away.
-#ifndef AHMC_NUTS_FULLTILE
-#define AHMC_NUTS_FULLTILE 0
-#endif
-#if AHMC_NUTS_FULLTILE
-#define AHMC_FULL_TPARAM , bool FULL
-#define AHMC_FULL_TARG(x) , x
-#else
-#define AHMC_FULL_TPARAM
-#define AHMC_FULL_TARG(x)
-#endif
-// AHMC_NUTS_RELOAD_COEF (default 0, staged): the model / metric coefficient vectors (mean, 1/s^2, M^-1: up to 3E doubles
-// per lane) are re-read from L1/L2 where they are used instead of living in registers for the whole kernel -- the register
-// diet that occupancy 4 (AHMC_NUTS_MINB=4, 128 registers) needs.
-#ifndef AHMC_NUTS_RELOAD_COEF
-#define AHMC_NUTS_RELOAD_COEF 0
-#endif
-#ifndef AHMC_NUTS_ALT_LAYOUT
-#define AHMC_NUTS_ALT_LAYOUT 0  // 1: (G, E) = (16, 4) / (16, 8), 2: (8, 8) / (8, 16) for 32 < D <= 128 -- staged, see nuts_dispatch
-#endif
+//     lane's register and the exponentials are taken G at a time, one per lane;
+//   * FULL = true: the instantiation for D == G * E (64, 128, 256) in which D is a compile-time constant -- the `d < D`
+//     guard of every vector load / store and most of the workspace address arithmetic fold away.
 
-// Occupancy knob: the tree walk is a long chain of dependent, mostly fixed-latency instructions, so throughput
-// scales with resident warps per scheduler; cap registers so that this many 4-warp blocks fit per SM.
-#ifndef AHMC_NUTS_MINB
-#define AHMC_NUTS_MINB 3
-#endif
+// Occupancy: the tree walk is a long chain of dependent, mostly fixed-latency instructions, so throughput scales with
+// resident warps per scheduler; cap registers so that this many 4-warp blocks fit per SM (4 was measured slower: spills).
 template <int E>
-constexpr int nuts_min_blocks() { return E <= 4 ? AHMC_NUTS_MINB : (E <= 8 ? 2 : 1); }
+constexpr int nuts_min_blocks() { return E <= 4 ? 3 : (E <= 8 ? 2 : 1); }
 
 // VAR = false: MultinomialTS + GeneralisedNoUTurn only (what `NUTS(delta)` builds); VAR = true additionally compiles
 // SliceTS (trajectory.jl:102-109,144-145,164-166,178-189,202,500-502) and the Classic / StrictGeneralised criteria
 // (trajectory.jl:551-557, 579-613), selected at run time by a.sampler / a.criterion.
-template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT AHMC_FULL_TPARAM>
+template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT, bool FULL>
 __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kernel(const NutsArgs a) {
     // Dense metric: a merge needs dH/dr = M^-1 r of the pending half's first leaf -- a D x D product.  The default family
     // caches the vector (slot 1 of the level holds M^-1 r_first instead of r_first) so merges do no dense product at all.
@@ -114,26 +85,20 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     const long long chain0 = (long long)blockIdx.x * kGroups + grp_in_block;
     const bool valid = chain0 < a.N;
     const long long chain = valid ? chain0 : a.N - 1;
-#if AHMC_NUTS_FULLTILE
     const int D = FULL ? G * E : a.D;
-#else
-    const int D = a.D;
-#endif
     const bool dense = (MODEL == AHMC_MODEL_DENSE_GAUSS) || (METRIC == AHMC_METRIC_DENSE);
     double* xs = smem + (size_t)grp_in_block * D;  // dense slab (unused otherwise)
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
     double* lv = smem + (dense ? (size_t)kGroups * D : 0) +
-                 (size_t)grp_in_block * maxd * (kLevelScalars + (AHMC_NUTS_FASTDRAW ? 1 : 0));
+                 (size_t)grp_in_block * maxd * kLevelScalars;
     double* LW = lv;
     double* SA = lv + maxd;
     double* NA = lv + 2 * maxd;
     double* DH = lv + 3 * maxd;
     double* CLP = lv + 4 * maxd;
     double* CLK = lv + 5 * maxd;
-#if AHMC_NUTS_FASTDRAW
     double* WW = lv + 6 * maxd;  // (m, w) weights: LW holds m, WW holds w
     double ww_tree = 1.0, ww_c = 1.0;
-#endif
 
     double* base = a.scratch + a.scratch_stride * chain;
     double* LEFT = base;
@@ -152,25 +117,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     MetricOps<METRIC, G, E> me;
     mo.load(a.model, l, D);
     me.load(a.metric, chain, l, D);
-#if AHMC_NUTS_RELOAD_COEF
-    // re-materialise the coefficient registers from memory; the pointers are laundered through an empty asm so that
-    // the compiler can neither hoist the loads out of the leaf loop nor keep the values alive across it
-    auto reload_model = [&]() {
-        ModelDev md = a.model;
-        asm volatile("" : "+l"(md.p0), "+l"(md.p1));
-        mo.load(md, l, D);
-    };
-    auto reload_metric = [&]() {
-        if (ADAPT) return;  // the adaptive family's M^-1 is per-chain state owned by the registers
-        MetricDev mt = a.metric;
-        asm volatile("" : "+l"(mt.Minv));
-        me.load(mt, chain, l, D);
-    };
-#endif
 
     int nexp = 0, ndir = 0;
     uint64_t off = a.rng.offset;  // Philox transition counter of the transition this group is working on
-#if AHMC_NUTS_FASTDRAW
     // Lane-parallel variate prefetch: lane l of the chain's group holds uniform #(vbase + l) of the (chain, transition)
     // stream -- one Philox block per LANE instead of one per DRAW -- and a draw is a group broadcast of one register.
     // peek_u() must be called by every lane of the warp at a warp-uniform point (it shuffles); the take_*() below then
@@ -229,23 +178,6 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             acnt = 0;
         }
     };
-#else
-    auto next_exp = [&]() -> double {
-        int k = nexp++;
-        if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
-        return philox_exp(a.rng.seed, off, chain, k);
-    };
-    auto next_unif = [&]() -> double {  // SliceTS draws rand(rng) where MultinomialTS draws randexp(rng); same counter
-        int k = nexp++;
-        if (a.rng.exp_tape && k < a.rng.exp_stride) return a.rng.exp_tape[chain * a.rng.exp_stride + k];
-        return exp(-philox_exp(a.rng.seed, off, chain, k));
-    };
-    auto next_dir = [&]() -> bool {
-        int k = ndir++;
-        if (a.rng.dir_tape && k < a.rng.dir_stride) return a.rng.dir_tape[chain * a.rng.dir_stride + k] != 0;
-        return philox_bit(a.rng.seed, off, chain, k);
-    };
-#endif
 
     // ---- per-transition state (a launch runs n_transitions transitions per chain: the reference's
     //      `for i in 1:n_samples` loop, sampler.jl:182, each chain advancing at its own pace)
@@ -272,12 +204,10 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 off = a.rng.offset + (uint64_t)t;
                 nexp = 0;
                 ndir = 0;
-#if AHMC_NUTS_FASTDRAW
                 vbase = -(1 << 30);
                 cdir_blk = -1;
                 sa_acc = 0.0;
                 acnt = 0;
-#endif
                 vload_nc<G, E>(s.th, first ? a.th_in + a.ld_in * chain : a.th_out + a.ld_out * chain, l, D);
                 vload_nc<G, E>(s.g, first ? a.g_in + a.ld_in * chain : a.g_out + a.ld_out * chain, l, D);
             }
@@ -287,9 +217,6 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 } else {
                     philox_normals<G, E>(a.rng.seed, off, chain, l, D, rn);
                 }
-#if AHMC_NUTS_RELOAD_COEF
-                reload_metric();
-#endif
                 me.rand_momentum(rn, l);
                 if (a.rng.partial_alpha != 0.0) {  // PartialMomentumRefreshment (hamiltonian.jl:243-254)
                     double rp[E];
@@ -302,10 +229,8 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 vload_nc<G, E>(rn, first ? a.r_in + a.ld_in * chain : a.r_out + a.ld_out * chain, l, D);
             }
             const double lk0 = map_nonfinite(kinetic<METRIC, G, E>(me, rn, drn, xs, l));
-#if AHMC_NUTS_FASTDRAW
             double u_init = 0.0;
             if (VAR && samp == 1) u_init = peek_u();  // the slice variable's randexp (variate #0 of the transition)
-#endif
             if (need_init) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) s.r[e] = rn[e];
@@ -336,15 +261,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                     if (l == 0) a.ad.eps[chain] = eps_c;
                 }
                 lw_tree = 0.0;
-#if AHMC_NUTS_FASTDRAW
                 ww_tree = 1.0;
-#endif
                 if (VAR && samp == 1) {  // SliceTS(rng, z0) = SliceTS(z0, neg_energy(z0) - randexp(rng), 1) (:144-145)
-#if AHMC_NUTS_FASTDRAW
                     lu = (s.lp + s.lk) - take_exp(u_init);
-#else
-                    lu = (s.lp + s.lk) - next_exp();
-#endif
                     lw_tree = 1.0;  // n = 1
                 }
                 sa_tree = 0.0;
@@ -359,17 +278,13 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             }
         }
         // ---------------------------------------------------------------- (F) finish a transition: stats (:725-739), draw
-#if AHMC_NUTS_FASTDRAW
         {
             const bool fl = !finished && done && !in_sub && acnt > 0;
             if (__any_sync(FULL, fl)) alpha_flush(fl);
         }
-#endif
         {
             const bool fin_now = !finished && done && !in_sub;
-#if AHMC_NUTS_FASTDRAW
             if (fin_now) sa_tree = sa_acc;
-#endif
             if (fin_now) {
                 const long long si = (long long)t * a.N + chain;
                 if (a.draws) {
@@ -477,16 +392,11 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         if (!__any_sync(FULL, in_sub)) break;
 
         // ---------------------------------------------------------------- (B) one leaf (:638-647)
-#if AHMC_NUTS_RELOAD_COEF
-        reload_model();
-        reload_metric();
-#endif
         leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, v > 0 ? eps_c : -eps_c, dr, xs, l);
         const double nE = s.lp + s.lk;  // neg_energy(z')
         const double H1 = -nE;
         const double dH = H1 - H0;
         double lw_c = H0 + nE;                               // MultinomialTS(s, H0, z') (:174-176)
-#if AHMC_NUTS_FASTDRAW
         double sa_c = 0.0;  // (deferred: see alpha_flush)
         if (in_sub) {
             if (l == acnt) abuf = dH;
@@ -496,9 +406,6 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             const bool fl = in_sub && acnt == G;
             if (__any_sync(FULL, fl)) alpha_flush(fl);
         }
-#else
-        double sa_c = exp(jl_min0(-dH));                     // alpha' = exp(min(0, -dH))
-#endif
         double na_c = 1.0, dh_c = dH;
         bool tnum_c = !(-H0 < a.delta_max + -H1);            // Termination(...) (:503-507)
         if (VAR && samp == 1) {
@@ -506,9 +413,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
             tnum_c = !(lu < a.delta_max + -H1);              // Termination(::SliceTS) (:500-502)
         }
         bool tdyn_c = false;
-#if AHMC_NUTS_FASTDRAW
         ww_c = 1.0;  // a leaf: (m, w) = (H0 - H', 1)
-#endif
         double rho_cur[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) rho_cur[e] = s.r[e];  // TurnStatistic(z.r)
@@ -595,9 +500,6 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                     for (int e = 0; e < E; ++e) t1[e] = 0.0;
                     if (do_comb) vload_nc<G, E>(t1, L + D, l, D);
                 } else {
-#if AHMC_NUTS_RELOAD_COEF
-                    reload_metric();
-#endif
                     me.dHdr(rf_p, t1, xs, l);
                 }
                 if (VAR && crit == 1) {
@@ -627,16 +529,9 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                     d2 = Grp<G>::sum(d2);
                     uturn = (d1 <= 0.0) || (d2 <= 0.0) || uturn_extra;
                 }
-#if AHMC_NUTS_FASTDRAW
                 const double u_comb = peek_u();
-#endif
                 if (do_comb) {
-#if AHMC_NUTS_FASTDRAW
                     const double lw_p = LW[k], sa_p = 0.0, na_p = NA[k], dh_p = DH[k];  // sum(alpha): see alpha_flush
-#else
-                    const double lw_p = LW[k], sa_p = SA[k], na_p = NA[k], dh_p = DH[k];
-#endif
-#if AHMC_NUTS_FASTDRAW
                     if (VAR && samp == 1) {  // combine(rng, s1::SliceTS, s2) (:178-183)
                         const double n = lw_p + lw_c;
                         if (n * take_unif(u_comb) < lw_p) cand_cur = k;
@@ -659,18 +554,6 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                         if ((dlw == dlw) && (u < p_first)) cand_cur = k;  // lw < lw_p + randexp  <=>  u < w_p / (w_p + w_c)
                         ww_c = w_new;
                     }
-#else
-                    const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
-                    if (VAR && samp == 1) {  // combine(rng, s1::SliceTS, s2) (:178-183): n = n1 + n2; n*rand < n1 ? s1 : s2
-                        const double n = lw_p + lw_c;
-                        if (n * ex < lw_p) cand_cur = k;
-                        lw_c = n;
-                    } else {
-                        const double lw = logaddexp(lw_p, lw_c);  // combine(rng, s1, s2) (:191-195)
-                        if (lw < lw_p + ex) cand_cur = k;         // keep the first-built half's candidate
-                        lw_c = lw;
-                    }
-#endif
                     sa_c = (v > 0) ? sa_p + sa_c : sa_c + sa_p;  // treeleft + treeright (:538)
                     na_c += na_p;
                     dh_c = (v > 0) ? maxabs(dh_p, dh_c) : maxabs(dh_c, dh_p);
@@ -715,13 +598,8 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                         clk = CLK[cand_cur];
                     }
                     if (l == 0) {
-#if AHMC_NUTS_FASTDRAW
                         WW[k] = ww_c;
-#endif
                         LW[k] = lw_c;
-#if !AHMC_NUTS_FASTDRAW
-                        SA[k] = sa_c;
-#endif
                         NA[k] = na_c;
                         DH[k] = dh_c;
                         CLP[k] = clp;
@@ -738,19 +616,11 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         if (__any_sync(FULL, complete)) {
             const bool sub_term = tnum_c || tdyn_c;
             bool accept = false;
-#if AHMC_NUTS_FASTDRAW
             const double u_top = peek_u();
-#endif
             if (complete && !sub_term) {
                 j = j + 1;
-#if AHMC_NUTS_FASTDRAW
                 if (VAR && samp == 1) accept = lw_tree * take_unif(u_top) < lw_c;  // mh_accept(::SliceTS) (:202)
                 else accept = take_u_of_exp(u_top) < (ww_c / ww_tree) * exp(lw_c - lw_tree);  // lw_T < lw_c + randexp (:204-206)
-#else
-                const double ex = (VAR && samp == 1) ? next_unif() : next_exp();
-                accept = (VAR && samp == 1) ? (lw_tree * ex < lw_c)   // mh_accept(::SliceTS): s.n * rand < s'.n (:202)
-                                            : (lw_tree < lw_c + ex);  // mh_accept (:204-206)
-#endif
             }
             if (accept) {  // zcand = sampler'.zcand
                 if (cand_cur < 0) {
@@ -833,9 +703,6 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 vstore<G, E>(edge + 2 * (long long)D, s.g, l, D);
                 vload_nc<G, E>(r_other, other + D, l, D);
             }
-#if AHMC_NUTS_RELOAD_COEF
-            reload_metric();
-#endif
             me.dHdr(r_other, t1, xs, l);
             double d1 = 0.0, d2 = 0.0;
             bool uturn_top;
@@ -863,7 +730,6 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 sa_tree = (v < 0) ? sa_c + sa_tree : sa_tree + sa_c;
                 na_tree += (int)na_c;
                 dh_tree = (v < 0) ? maxabs(dh_c, dh_tree) : maxabs(dh_tree, dh_c);
-#if AHMC_NUTS_FASTDRAW
                 if (VAR && samp == 1) {
                     lw_tree = lw_tree + lw_c;  // combine(zcand, s1::SliceTS, s2): n1 + n2 (:185-189)
                 } else {                       // combine(zcand, sampler, sampler') (:197-200, :717) on (m, w)
@@ -876,10 +742,6 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                         lw_tree = (lw_tree != lw_tree) ? lw_tree : lw_c;
                     }
                 }
-#else
-                lw_tree = (VAR && samp == 1) ? lw_tree + lw_c            // combine(zcand, s1::SliceTS, s2): n1 + n2 (:185-189)
-                                             : logaddexp(lw_tree, lw_c);  // combine(zcand, sampler, sampler') (:197-200, :717)
-#endif
                 term_dyn = term_dyn || tdyn_c || uturn_top;  // (:719-722)
                 term_num = term_num || tnum_c;
                 in_sub = false;
@@ -899,9 +761,9 @@ static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
     const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
     size_t sm = smem_bytes(MODEL, METRIC, a.D, G) +
-                (size_t)chains_per_block * maxd * (kLevelScalars + (AHMC_NUTS_FASTDRAW ? 1 : 0)) * sizeof(double);
-#if AHMC_NUTS_FULLTILE
-    if (a.D == G * E) {
+                (size_t)chains_per_block * maxd * kLevelScalars * sizeof(double);
+    if constexpr (G == 32 && E >= 2 && E <= 8) {
+      if (a.D == G * E) {  // full tile: compile-time D
         if (sm > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -909,14 +771,14 @@ static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
         }
         nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
         return cudaGetLastError();
+      }
     }
-#endif
     if (sm > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT AHMC_FULL_TARG(false)>,
+        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
     }
-    nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT AHMC_FULL_TARG(false)><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, false><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -930,13 +792,6 @@ static cudaError_t nuts_layout(const NutsArgs& a, cudaStream_t st, int G, int E)
     if (G == 32 && E == 4) return launch_nuts_v<MODEL, METRIC, 32, 4, VAR, ADAPT>(a, st);
     if (G == 32 && E == 8) return launch_nuts_v<MODEL, METRIC, 32, 8, VAR, ADAPT>(a, st);
     if (G == 32 && E == 16) return launch_nuts_v<MODEL, METRIC, 32, 16, VAR, ADAPT>(a, st);
-#if AHMC_NUTS_ALT_LAYOUT == 1
-    if (G == 16 && E == 4) return launch_nuts_v<MODEL, METRIC, 16, 4, VAR, ADAPT>(a, st);
-    if (G == 16 && E == 8) return launch_nuts_v<MODEL, METRIC, 16, 8, VAR, ADAPT>(a, st);
-#elif AHMC_NUTS_ALT_LAYOUT == 2
-    if (G == 8 && E == 8) return launch_nuts_v<MODEL, METRIC, 8, 8, VAR, ADAPT>(a, st);
-    if (G == 8 && E == 16) return launch_nuts_v<MODEL, METRIC, 8, 16, VAR, ADAPT>(a, st);
-#endif
     return cudaErrorInvalidValue;
 }
 
@@ -945,18 +800,6 @@ template <bool VAR, bool ADAPT, bool DIAG_ONLY>
 static cudaError_t nuts_dispatch(const NutsArgs& a, cudaStream_t st) {
     int G, E;
     if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
-#if AHMC_NUTS_ALT_LAYOUT
-    // staged A/B knob (scripts/build_variants.sh altlayout): two chains per warp for 32 < D <= 128 (16 lanes x 4 or 8
-    // coordinates), so that the per-chain scalar bookkeeping -- ~2/3 of K3's instructions -- is issued once per TWO chains
-#if AHMC_NUTS_ALT_LAYOUT == 1
-    if (a.D > 32 && a.D <= 64) G = 16, E = 4;
-    else if (a.D > 64 && a.D <= 128) G = 16, E = 8;
-#else  // 2: FOUR chains per warp (8 lanes x 8 / 16 coordinates); the vectors no longer fit the register file and the
-       // compiler keeps part of them in (L1-resident) local memory -- an experiment in trading that for 4x fewer scalar issues
-    if (a.D > 32 && a.D <= 64) G = 8, E = 8;
-    else if (a.D > 64 && a.D <= 128) G = 8, E = 16;
-#endif
-#endif
     if (DIAG_ONLY) {
         if (a.metric.kind != AHMC_METRIC_DIAG) return cudaErrorInvalidValue;
         switch (a.model.kind) {

@@ -30,6 +30,13 @@ WORKLOAD = "north-star headline: 4096 chains x D=128 diag-Gaussian (s log-spaced
 SEED = 20260923
 
 
+def config_dict(world):
+    """the SAME keys and values in both arms (the driver compares the two `config` objects)"""
+    return {"workload": WORKLOAD, "chains_per_gpu": N_CHAINS, "D": DIM, "L": L_STEPS, "eps": EPS,
+            "parallelism": f"chains sharded x{world}, no data-path collective",
+            "l2": "flushed between timed iterations (512 MiB read-sweep outside the event pair)"}
+
+
 def synth(N, D, seed):
     rng = np.random.Generator(np.random.PCG64(seed))
     s = np.exp(np.linspace(np.log(0.1), np.log(10.0), D))
@@ -46,6 +53,15 @@ def peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02", "k1_headline_dram.json")) as f:
+            d = json.load(f)
+        return int(d["dram_bytes_read"] + d["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -174,7 +190,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC_NAME, "value": value, "unit": "steps*dims/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "chains": N_CHAINS, "D": DIM, "L": L_STEPS, "eps": EPS},
+        "config": config_dict(args.gpus),
         "cpu_baseline": {"value": value, "unit": "steps*dims/s", "cores": cores, "kind": "port",
                          "sample": "full workload per step (4096x128x32), fused C/OpenMP oracle port, all host threads; "
                                    "the Julia reference itself cannot run here (no julia binary)",
@@ -315,6 +331,61 @@ def run_ours(args):
             k2 = {"workload": "static HMC transitions (Philox refresh + 32 fused steps + MH), 4096x128, 100 transitions per chain in one launch",
                   "ms_per_transition": ms_k2, "rate_steps_dims_per_s": units_per_step / ms_k2 * 1e3}
 
+        # ---- the GENERAL path on the same shape: per-step reference op sequence with energies and isfinite tests (what every
+        # non-Gaussian user model runs), the funnel target, and NUTS on the C3 shape (persistent launch, 20 transitions)
+        general = None
+        if rank == 0 and not args.no_extras:
+            general = {}
+            B = 48.0 + 24.0 / DIM
+
+            def timed(fn, reps):
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(reps):
+                    fn()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+
+            ex = A.StepPlan(lf, h, z0, L_STEPS, flags=A.FLAG_ASYNC | A.FLAG_EXACT_CHECKS)
+            ms = timed(ex, 20)
+            rate = units_per_step / ms * 1e3
+            general["exact_path"] = {"workload": "headline shape, AHMC_FLAG_EXACT_CHECKS: per-step energies + isfinite, no linear shortcut",
+                                     "ms_per_launch": ms, "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * B / 1e9 / hbm_peak,
+                                     "roofline_frac_compulsory": (N_CHAINS * DIM * 48 + N_CHAINS * 24) / ms / 1e6 / hbm_peak}
+            Df = 100
+            hf = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(Df)), A.Funnel(Df))
+            gf = torch.Generator(device=dev).manual_seed(3)
+            zf = A.phasepoint(hf, 0.5 * torch.randn((N_CHAINS, Df), generator=gf, dtype=torch.float64, device=dev),
+                              torch.randn((N_CHAINS, Df), generator=gf, dtype=torch.float64, device=dev))
+            fp = A.StepPlan(A.Leapfrog(0.05), hf, zf, L_STEPS, flags=A.FLAG_ASYNC)
+            ms = timed(fp, 20)
+            rate = N_CHAINS * Df * L_STEPS / ms * 1e3
+            Bf = 48.0 + 24.0 / Df
+            general["funnel_trajectory"] = {"workload": "Neal's funnel D=100 (SURVEY 8c), 4096 chains, Diag metric, Leapfrog(0.05), L=32 fused",
+                                            "ms_per_launch": ms, "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * Bf / 1e9 / hbm_peak,
+                                            "roofline_frac_compulsory": (N_CHAINS * Df * 48 + N_CHAINS * 24) / ms / 1e6 / hbm_peak}
+            kn = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.4), A.GeneralisedNoUTurn()))
+            prn = A.PhiloxRNG(11)
+            zs = A.phasepoint(h, torch.as_tensor(th * s, device=dev), torch.as_tensor(r, device=dev))  # theta ~ target
+            TN = 20
+            zl, _, stn = A.sample_transitions(prn, h, kn, zs, TN, keep_draws=False, flags=A.FLAG_ASYNC)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            zl, _, stn = A.sample_transitions(prn, h, kn, zl, TN, keep_draws=False, flags=A.FLAG_ASYNC)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            nsteps = int(stn["n_steps"].sum().item())
+            msn = e0.elapsed_time(e1)
+            rate = nsteps * DIM / msn * 1e3
+            general["nuts_c3"] = {"workload": "C3: NUTS(MultinomialTS, GeneralisedNoUTurn) + DiagEuclidean, D=128 Gaussian, 4096 chains, eps=0.4, "
+                                              "20 transitions per chain in one persistent launch",
+                                  "ms_per_transition": msn / TN, "mean_leapfrog_steps_per_transition": nsteps / TN / N_CHAINS,
+                                  "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * B / 1e9 / hbm_peak}
+
         # ---- K4: correlated (dense-precision) Gaussian target, Diag metric, same batch: fp64 tensor-MMA trajectory
         k4 = None
         if rank == 0 and not args.no_extras:
@@ -372,14 +443,14 @@ def run_ours(args):
             if rcmb == 0:
                 dfma = {"tflops": tf.value, "ms": msb.value, "what": "148*8 blocks x 256 threads x 8 independent DFMA chains (libahmc_microbench.so)"}
 
-    # ---- e2e: the public call with HOST (pinned) buffers, copies inside the timed region.  The page-locked buffers are
-    # allocated with this thread bound to the GPU's NUMA node (every byte crosses PCIe; a remote node costs up to 1.5x)
+    # ---- e2e: the public call with HOST (pinned) buffers, copies inside the timed region.  Contract of
+    # src/integrator.jl:216-265: host arrays in (theta, r -- the cached gradient of a built-in target is recomputed on the
+    # device, so it is not uploaded), a fresh phase point out (theta', r', -grad', lp', lk').  The page-locked buffers are
+    # allocated with this thread bound to the GPU's NUMA node (every byte crosses PCIe; a remote node costs up to 1.5x).
     prev_affinity = A.bind_to_gpu_numa(local)
     thp = torch.as_tensor(th).pin_memory()
     rp = torch.as_tensor(r).pin_memory()
-    z0h = A.phasepoint(h, thp.numpy(), rp.numpy())
-    gp = torch.as_tensor(z0h.lp.gradient).pin_memory()
-    z0h.theta, z0h.r, z0h.lp.gradient = thp.numpy(), rp.numpy(), gp.numpy()
+    z0h = A.PhasePoint(thp.numpy(), rp.numpy(), A.DualValue(None, None), A.DualValue(None, None))
     pin = lambda shape: torch.empty(shape, dtype=torch.float64).pin_memory()
     outs = [pin((N_CHAINS, DIM)) for _ in range(3)] + [pin((N_CHAINS,)) for _ in range(2)]
     zout = A.PhasePoint(outs[0].numpy(), outs[1].numpy(), A.DualValue(outs[3].numpy(), outs[2].numpy()),
@@ -387,8 +458,11 @@ def run_ours(args):
 
     e2e_step = A.StepPlan(lf, h, z0h, L_STEPS, out=zout)
 
-    for _ in range(3):
+    # warm-up: the library measures its transports (zero-copy kernel loads/stores vs copy-engine pipelines of 2 / 4 chunks)
+    # on the first 12 calls of a shape and keeps the fastest -- every call returns the same bytes
+    for _ in range(14):
         e2e_step()
+    transport = ctx.last_transport()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -403,8 +477,8 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     if prev_affinity is not None:
         os.sched_setaffinity(0, prev_affinity)  # the CPU arms below use every host thread again
-    h2d = 3 * N_CHAINS * DIM * 8 + DIM * 8
-    d2h = 3 * N_CHAINS * DIM * 8 + N_CHAINS * (8 + 8 + 4 + 4)
+    h2d = 2 * N_CHAINS * DIM * 8 + DIM * 8
+    d2h = 3 * N_CHAINS * DIM * 8 + N_CHAINS * (8 + 8)
 
     # ---- reduce over ranks (max time)
     tt = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -424,10 +498,9 @@ def run_ours(args):
     fp64_ops = units_per_step * 2 * 2  # 2 DFMA per step*dim on the fast path
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed `ncu --set full`
-        # capture (profiles/r01/k1_headline_details.txt): 12.61 MB read + 0 B written back by kernel end (outputs still
-        # dirty in L2) -- NOT re-measured inside this run
-        "traffic": 12607232, "peak_source": peak_src, "kernel": "leapfrog_kernel<DIAG_GAUSS,DIAG,G=32,E=4>",
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, per launch, from the committed
+        # `ncu --set full` capture of this round (profiles/r02/k1_headline_dram.json; null when no capture is committed)
+        "traffic": measured_traffic(), "peak_source": peak_src, "kernel": "leapfrog_kernel<DIAG_GAUSS,DIAG,G=32,E=4>",
         "kernel_ms": kernel_ms,
         "model": "SURVEY 8d streaming contract: (48+24/D) B per step*dim x N*D*L units per launch; the fused L-step "
                  "kernel keeps state in registers, so its COMPULSORY traffic is 1/L of that (next keys)",
@@ -440,14 +513,13 @@ def run_ours(args):
         "metric": METRIC_NAME, "value": value, "unit": "steps*dims/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "chains_per_gpu": N_CHAINS, "D": DIM, "L": L_STEPS, "eps": EPS,
-                   "parallelism": f"chains sharded x{world}, no data-path collective",
-                   "l2": "flushed between timed iterations (512 MiB read-sweep outside the event pair)"},
+        "config": config_dict(world),
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "steps*dims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms_max / K, "call_ms_min_med_max": [min(call_ms), sorted(call_ms)[len(call_ms) // 2], max(call_ms)],
-                "numa_bound": prev_affinity is not None,
-                "path": "ahmc_leapfrog_f64(AHMC_FLAG_HOST_BUFFERS) via ahmc_b200.step on pinned host arrays"},
+                "ms_per_step": e2e_ms_max / K, "call_ms_min": min(call_ms), "call_ms_med": sorted(call_ms)[len(call_ms) // 2],
+                "call_ms_max": max(call_ms), "transport": transport, "numa_bound": prev_affinity is not None,
+                "path": "ahmc_leapfrog_f64(AHMC_FLAG_HOST_BUFFERS) via ahmc_b200.step on pinned host arrays: theta, r in; "
+                        "theta', r', -grad', lp', lk' out (the cached input gradient is recomputed on the device)"},
         "gpu_launches": int(launches), "clocks": clocks,
         "step_ms_min_med_max": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))],
     }
@@ -460,6 +532,8 @@ def run_ours(args):
         line["roofline_hbm_honest"] = honest
     if k2:
         line["hmc_transition"] = k2
+    if general:
+        line.update(general)
     if k4:
         line["dense_target_trajectory"] = k4
     if dfma:

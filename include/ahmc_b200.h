@@ -136,6 +136,10 @@ const char* ahmc_last_error(const ahmc_ctx* ctx);
 int ahmc_synchronize(ahmc_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches evidence) */
 int64_t ahmc_launch_count(const ahmc_ctx* ctx);
+/* how the last AHMC_FLAG_HOST_BUFFERS call of ahmc_leapfrog_f64 moved its buffers, e.g. "up=direct down=direct chunks=1
+ * occ=1 (autotuned)": page-locked buffers are moved by whichever of {kernel loads/stores of host memory, copy-engine
+ * pipelines of 2 / 4 chunks} measured fastest on the first calls of that shape (results are bit-identical in every mode) */
+const char* ahmc_last_transport(const ahmc_ctx* ctx);
 
 /* ---- models ---------------------------------------------------------------------------------- */
 /* p0/p1 are HOST pointers (copied to the device at creation); meaning per AHMC_MODEL_*. */

@@ -115,7 +115,7 @@ struct EmuDense {
     double norms_out[2];
 };
 
-extern "C" int emu_dense_knobs() { return AHMC_DENSE_PADDED_A | (AHMC_DENSE_MBAR_RELEASE << 1) | (kStages << 2); }
+extern "C" int emu_dense_stages() { return kStages; }
 extern "C" int emu_dense(EmuDense* q) {
     n_bar_info.store(0);
     int Dp, RB, CB;

@@ -60,6 +60,16 @@ inline int __double2hiint(double x) {
     std::memcpy(&b, &x, 8);
     return (int)(b >> 32);
 }
+inline double __hiloint2double(int hi, int lo) {
+    uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x;
+    std::memcpy(&x, &b, 8);
+    return x;
+}
+struct double2 {
+    double x, y;
+};
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 int atomicMin(int* addr, int v);
 int atomicOr(int* addr, int v);
 // every lane contributes (a, b); every lane receives all 32 of each (one exchange instead of 12 shuffles: emulated DMMA)

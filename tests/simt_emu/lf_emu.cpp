@@ -41,11 +41,16 @@ struct EmuLf {
 template <int MODEL, int METRIC, int G, int E>
 static void lf_thunk(const void* p) { leapfrog_kernel<MODEL, METRIC, G, E>(*static_cast<const LeapfrogArgs*>(p)); }
 template <int MODEL, int METRIC, int G, int E>
+static void lfc_thunk(const void* p) { leapfrog_kernel<MODEL, METRIC, G, E, true>(*static_cast<const LeapfrogArgs*>(p)); }
+template <int MODEL, int METRIC, int G, int E>
 static void hmc_thunk(const void* p) { hmc_kernel<MODEL, METRIC, G, E>(*static_cast<const HmcArgs*>(p)); }
 typedef void (*KernelFn)(const void*);
 
 template <int MODEL, int METRIC>
-static KernelFn pick(int G, int E, bool hmc) {
+static KernelFn pick(int G, int E, bool hmc, bool contig) {
+    // full tile D == 64: the lane-contiguous instantiation the product's launcher picks (launch_lf_t)
+    if constexpr (FastCapable<MODEL, METRIC>::value)
+        if (contig && !hmc && G == 32 && E == 2) return lfc_thunk<MODEL, METRIC, 32, 2>;
     if (G == 4 && E == 1) return hmc ? hmc_thunk<MODEL, METRIC, 4, 1> : lf_thunk<MODEL, METRIC, 4, 1>;
     if (G == 8 && E == 1) return hmc ? hmc_thunk<MODEL, METRIC, 8, 1> : lf_thunk<MODEL, METRIC, 8, 1>;
     if (G == 32 && E == 2) return hmc ? hmc_thunk<MODEL, METRIC, 32, 2> : lf_thunk<MODEL, METRIC, 32, 2>;
@@ -88,10 +93,11 @@ extern "C" int emu_leapfrog(const EmuLf* q) {
     KernelFn fn = nullptr;
     const int m = q->model_kind, me = q->metric_kind;
     const bool hm = q->hmc != 0;
-    if (m == AHMC_MODEL_STD_NORMAL && me == AHMC_METRIC_UNIT) fn = pick<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_UNIT>(G, E, hm);
-    else if (m == AHMC_MODEL_DIAG_GAUSS && me == AHMC_METRIC_DIAG) fn = pick<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DIAG>(G, E, hm);
-    else if (m == AHMC_MODEL_FUNNEL && me == AHMC_METRIC_DIAG) fn = pick<AHMC_MODEL_FUNNEL, AHMC_METRIC_DIAG>(G, E, hm);
-    else if (m == AHMC_MODEL_DENSE_GAUSS && me == AHMC_METRIC_DENSE) fn = pick<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DENSE>(G, E, hm);
+    const bool contig = D == 64 && !(q->flags & AHMC_FLAG_EXACT_CHECKS) && !(q->temper_alpha > 0.0);
+    if (m == AHMC_MODEL_STD_NORMAL && me == AHMC_METRIC_UNIT) fn = pick<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_UNIT>(G, E, hm, contig);
+    else if (m == AHMC_MODEL_DIAG_GAUSS && me == AHMC_METRIC_DIAG) fn = pick<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DIAG>(G, E, hm, contig);
+    else if (m == AHMC_MODEL_FUNNEL && me == AHMC_METRIC_DIAG) fn = pick<AHMC_MODEL_FUNNEL, AHMC_METRIC_DIAG>(G, E, hm, contig);
+    else if (m == AHMC_MODEL_DENSE_GAUSS && me == AHMC_METRIC_DENSE) fn = pick<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DENSE>(G, E, hm, contig);
     if (!fn) return -2;
     const int chains_per_block = kBlockThreads / G;
     const int blocks = (int)((q->N + chains_per_block - 1) / chains_per_block);

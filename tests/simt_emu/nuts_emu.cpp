@@ -1,6 +1,6 @@
 // nuts_emu.cpp -- runs the product's NUTS kernel source (ahmc_nuts_kernel.cuh) under the CPU SIMT emulator.
 // TEST INFRASTRUCTURE ONLY: built by tests/test_simt_emulation.py with g++; the kernel header is included unmodified
-// (its host launch code is skipped with AHMC_SIMT_EMULATION); optional -DAHMC_NUTS_FASTDRAW=1 builds the staged variant.
+// (its host launch code is skipped with AHMC_SIMT_EMULATION).
 #define AHMC_SIMT_EMULATION 1
 #include <cstdlib>
 #include <vector>
@@ -50,13 +50,11 @@ struct EmuNuts {
 template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
 static void thunk(const void* p) {
     const NutsArgs& a = *static_cast<const NutsArgs*>(p);
-#if AHMC_NUTS_FULLTILE
-    if (a.D == G * E) {  // the full-tile instantiation (D a compile-time constant), like launch_nuts_v
+    if (G == 32 && E >= 2 && E <= 8 && a.D == G * E) {  // the full-tile instantiation (D a compile-time constant), like launch_nuts_v
         nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true>(a);
         return;
     }
-#endif
-    nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT AHMC_FULL_TARG(false)>(a);
+    nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, false>(a);
 }
 
 typedef void (*KernelFn)(const void*);
@@ -69,13 +67,6 @@ static KernelFn by_layout(int G, int E) {
     if (G == 16 && E == 1) return thunk<MODEL, METRIC, 16, 1, VAR, ADAPT>;
     if (G == 32 && E == 4) return thunk<MODEL, METRIC, 32, 4, VAR, ADAPT>;
     if (G == 32 && E == 8) return thunk<MODEL, METRIC, 32, 8, VAR, ADAPT>;
-#if AHMC_NUTS_ALT_LAYOUT == 1
-    if (G == 16 && E == 4) return thunk<MODEL, METRIC, 16, 4, VAR, ADAPT>;
-    if (G == 16 && E == 8) return thunk<MODEL, METRIC, 16, 8, VAR, ADAPT>;
-#elif AHMC_NUTS_ALT_LAYOUT == 2
-    if (G == 8 && E == 8) return thunk<MODEL, METRIC, 8, 8, VAR, ADAPT>;
-    if (G == 8 && E == 16) return thunk<MODEL, METRIC, 8, 16, VAR, ADAPT>;
-#endif
     return nullptr;
 }
 
@@ -100,9 +91,6 @@ extern "C" int emu_window_schedule(int init_buffer, int term_buffer, int window_
     for (int i = 0; i < ad.n_splits; ++i) splits[i] = ad.splits[i];
     return ad.n_splits;
 }
-extern "C" int emu_fastdraw() { return AHMC_NUTS_FASTDRAW; }
-extern "C" int emu_altlayout() { return AHMC_NUTS_ALT_LAYOUT; }
-extern "C" int emu_fulltile() { return AHMC_NUTS_FULLTILE; }
 
 extern "C" int emu_nuts(const EmuNuts* q) {
     int G, E;
@@ -114,16 +102,6 @@ extern "C" int emu_nuts(const EmuNuts* q) {
     else if (D > 64 && D <= 128) G = 32, E = 4;  // the headline layout
     else if (D > 128 && D <= 256) G = 32, E = 8;  // C5's layout
     else return -1;
-#if AHMC_NUTS_ALT_LAYOUT == 1
-    if (D > 64 && D <= 128) G = 16, E = 8;
-#elif AHMC_NUTS_ALT_LAYOUT == 2
-    if (D > 64 && D <= 128) G = 8, E = 16;
-#endif
-#if AHMC_NUTS_ALT_LAYOUT == 1
-    if (D > 32 && D <= 64) G = 16, E = 4;
-#elif AHMC_NUTS_ALT_LAYOUT == 2
-    if (D > 32 && D <= 64) G = 8, E = 8;
-#endif
     NutsArgs a{};
     a.model = ModelDev{q->model_kind, D, q->p0, q->p1, q->c0};
     a.metric = MetricDev{q->metric_kind, q->Minv, q->minv_stride, q->cholU};

@@ -632,6 +632,96 @@ def test_pipelined_host_path_equals_device_path(up, down, chunks, pinned, monkey
             assert np.array_equal(a, b.cpu().numpy())
 
 
+@pytest.mark.parametrize("model,metric,D,N", [("diag_gauss", "diag", 128, 300), ("diag_gauss", "diag", 100, 300), ("std_normal", "unit", 64, 77),
+                                              ("funnel", "diag", 20, 130), ("dense_gauss", "dense", 12, 50), ("diag_gauss", "unit", 7, 19)])
+def test_step_without_cached_gradient_equals_step_with_it(model, metric, D, N):
+    """z_in.lp_gradient == NULL (a third less upload for host callers): the device recomputes dH/dtheta at the start point,
+    so the result is bit-identical to the call that was handed the cached gradient -- fast path (interleaved and
+    lane-contiguous layouts), exact path, dense fallback; device and host buffers."""
+    rng = np.random.default_rng(40 + D)
+    p0 = p1 = Minv = None
+    if model == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.7, 0.7, D))
+    elif model == "dense_gauss":
+        B = rng.normal(size=(D, D))
+        p0, p1 = rng.normal(size=D), B @ B.T / D + np.eye(D)
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.7, 0.7, D))
+    elif metric == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+    th, r = rng.normal(size=(D, N)) * (0.3 if model == "funnel" else 1.0), rng.normal(size=(D, N))
+    h = A.Hamiltonian(make_metric(metric, Minv, D), make_target(model, D, p0, p1, 0.5))
+    z0 = A.phasepoint(h, T(th), T(r))
+    zg = A.step(A.Leapfrog(0.07), h, z0, 9)
+    zn = A.step(A.Leapfrog(0.07), h, A.PhasePoint(z0.theta, z0.r, A.DualValue(None, None), A.DualValue(None, None)), 9)
+    for a, b in [(zg.theta, zn.theta), (zg.r, zn.r), (zg.lp.gradient, zn.lp.gradient), (zg.lp.value, zn.lp.value), (zg.lk.value, zn.lk.value)]:
+        assert torch.equal(a, b)
+    thh, rh = np.ascontiguousarray(np.asarray(th).T), np.ascontiguousarray(np.asarray(r).T)
+    zh = A.step(A.Leapfrog(0.07), h, A.PhasePoint(thh, rh, A.DualValue(None, None), A.DualValue(None, None)), 9)
+    assert np.array_equal(zh.theta, zg.theta.cpu().numpy()) and np.array_equal(zh.lp.gradient, zg.lp.gradient.cpu().numpy())
+    with pytest.raises(A.InvalidArgument):  # zero steps hands z back unchanged and needs the gradient to do so
+        A.step(A.Leapfrog(0.07), h, A.PhasePoint(z0.theta, z0.r, A.DualValue(None, None), A.DualValue(None, None)), 0)
+
+
+def test_host_lane_autotune_tries_every_transport_and_stays_bit_identical(monkeypatch):
+    """page-locked buffers: the first 12 calls of a shape walk through the four transports (3 rounds), then the fastest is
+    kept; every call returns the same bytes as the device call; ahmc_last_transport names what was used."""
+    for k in ("AHMC_PIPE_UP", "AHMC_PIPE_DOWN", "AHMC_PIPE_CHUNKS", "AHMC_PIPE_OCC", "AHMC_PIPE_AUTOTUNE"):
+        monkeypatch.delenv(k, raising=False)
+    D, N = 128, 2051
+    m, s, Minv, th, r = synth_diag_gauss(D, N, seed=9)
+    h = A.Hamiltonian(A.DiagEuclideanMetric(Minv), A.DiagGaussian(m, s))
+    zd = A.step(A.Leapfrog(0.1), h, A.phasepoint(h, T(th), T(r)), 32)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+    hold = [pin(th.T), pin(r.T)] + [pin(np.zeros((N, D))) for _ in range(3)] + [pin(np.zeros(N)) for _ in range(2)]
+    zin = A.PhasePoint(hold[0].numpy(), hold[1].numpy(), A.DualValue(None, None), A.DualValue(None, None))
+    zout = A.PhasePoint(hold[2].numpy(), hold[3].numpy(), A.DualValue(hold[5].numpy(), hold[4].numpy()), A.DualValue(hold[6].numpy(), None))
+    plan = A.StepPlan(A.Leapfrog(0.1), h, zin, 32, out=zout)
+    ctx = A.get_context(0)
+    seen = []
+    for i in range(16):
+        for t in hold[2:]:
+            t.zero_()
+        plan()
+        seen.append(ctx.last_transport())
+        for a, b in [(zout.theta, zd.theta), (zout.r, zd.r), (zout.lp.gradient, zd.lp.gradient), (zout.lp.value, zd.lp.value),
+                     (zout.lk.value, zd.lk.value)]:
+            assert np.array_equal(a, b.cpu().numpy()), (i, seen[-1])
+    assert len(set(seen[:4])) == 4 and all("trial" in t for t in seen[:12])
+    assert all("(autotuned)" in t for t in seen[12:]) and len(set(seen[12:])) == 1
+
+
+def test_small_host_buffer_calls_first_on_a_fresh_context_stay_inside_the_staging_arena():
+    """the staging arena was sized from grouped reservations while every staged array is rounded up to
+    256 B on its own, so N = 1 / small-D host calls made FIRST in a process wrote past the arena.  A fresh interpreter makes
+    them first (phasepoint, step, static transition, NUTS) under compute-sanitizer-free conditions by checking results
+    against device calls; the arena now carries slack for the roundings and alloc() fails instead of overrunning."""
+    import subprocess, sys, os
+    code = r'''
+import numpy as np, torch, ahmc_b200 as A
+rng = np.random.default_rng(0)
+D, N = 10, 1
+h = A.Hamiltonian(A.DiagEuclideanMetric(np.exp(rng.uniform(-1, 1, D))), A.DiagGaussian(rng.normal(size=D), np.exp(rng.uniform(-1, 1, D))))
+th, r = rng.normal(size=(N, D)), rng.normal(size=(N, D))
+zh = A.phasepoint(h, th, r)                                            # FIRST call of the process: host mode, 7 tiny arrays
+zd = A.phasepoint(h, torch.as_tensor(th, device="cuda"), torch.as_tensor(r, device="cuda"))
+assert np.array_equal(zh.lp.gradient, zd.lp.gradient.cpu().numpy()) and np.array_equal(zh.lk.value, zd.lk.value.cpu().numpy())
+z1h, z1d = A.step(A.Leapfrog(0.1), h, zh, 5), A.step(A.Leapfrog(0.1), h, zd, 5)
+assert np.array_equal(z1h.theta, z1d.theta.cpu().numpy()) and np.array_equal(z1h.lk.gradient, z1d.lk.gradient.cpu().numpy())
+k = A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.1), A.FixedNSteps(4)))
+th_, td_ = A.transition(A.PhiloxRNG(3), h, k, zh), A.transition(A.PhiloxRNG(3), h, k, zd)
+assert np.array_equal(th_.z.theta, td_.z.theta.cpu().numpy())
+kn = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.2), A.GeneralisedNoUTurn()))
+nh, nd = A.transition(A.PhiloxRNG(5), h, kn, zh), A.transition(A.PhiloxRNG(5), h, kn, zd)
+assert np.array_equal(nh.z.theta, nd.z.theta.cpu().numpy()) and int(nh.stat["n_steps"][0]) == int(nd.stat["n_steps"][0])
+print("ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pr = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
+    assert pr.returncode == 0 and "ok" in pr.stdout, pr.stderr[-2000:]
+
+
 # ------------------------------------------------------------------------------------------------ user closure (split-step)
 def _torch_funnel(th):
     """Neal's funnel written by a 'user' in plain torch, gradient by autograd."""

@@ -31,57 +31,19 @@ class EmuNuts(C.Structure):
                 ("adapt_metric", C.c_int32), ("n_min", C.c_int32), ("eps_rw", _vp), ("minv_rw", _vp), ("eps_trace", _vp)]
 
 
-_NUTS_VARIANTS = {  # name -> compile-time knobs of the NUTS harness
-    "default": [], "fast": ["-DAHMC_NUTS_FASTDRAW=1"], "alt": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=1"],
-    "alt2": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=2"],
-    "full": ["-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_FULLTILE=1", "-DAHMC_NUTS_RELOAD_COEF=1"]}
-
-
 @pytest.fixture(scope="module")
-def _nuts_libs(tmp_path_factory):
-    """all NUTS harness variants, compiled concurrently once per test module"""
+def emu(tmp_path_factory):
+    """the NUTS harness (kernel source + emulator), compiled once per test module"""
     tmp = tmp_path_factory.mktemp("simt_nuts")
     d = os.path.join(ROOT, "tests", "simt_emu")
-    procs = {}
-    for name, defs in _NUTS_VARIANTS.items():
-        out = tmp / f"libnuts_emu_{name}.so"
-        cmd = ["g++", *defs, "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-I", os.path.join(d, "include"),
-               "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
-               os.path.join(d, "simt_emu.cpp"), os.path.join(d, "nuts_emu.cpp"), "-o", str(out)]
-        procs[name] = (subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True), out)
-    libs = {}
-    for name, (pr, out) in procs.items():
-        _, err = pr.communicate()
-        assert pr.returncode == 0, err[-2000:]
-        libs[name] = C.CDLL(str(out))
-    assert libs["default"].emu_fastdraw() == 0 and libs["fast"].emu_fastdraw() == 1
-    assert libs["alt"].emu_altlayout() == 1 and libs["alt2"].emu_altlayout() == 2 and libs["full"].emu_fulltile() == 1
-    return libs
+    out = tmp / "libnuts_emu.so"
+    cmd = ["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-I", os.path.join(d, "include"),
+           "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(d, "simt_emu.cpp"), os.path.join(d, "nuts_emu.cpp"), "-o", str(out)]
+    pr = subprocess.run(cmd, capture_output=True, text=True)
+    assert pr.returncode == 0, pr.stderr[-2000:]
+    return C.CDLL(str(out))
 
-
-@pytest.fixture(scope="module")
-def emu(_nuts_libs):
-    return _nuts_libs["default"]
-
-
-@pytest.fixture(scope="module")
-def emu_fast(_nuts_libs):
-    return _nuts_libs["fast"]
-
-
-@pytest.fixture(scope="module")
-def emu_alt(_nuts_libs):
-    return _nuts_libs["alt"]
-
-
-@pytest.fixture(scope="module")
-def emu_full(_nuts_libs):
-    return _nuts_libs["full"]
-
-
-@pytest.fixture(scope="module")
-def emu_alt2(_nuts_libs):
-    return _nuts_libs["alt2"]
 
 
 P = lambda a: None if a is None else a.ctypes.data_as(_vp)
@@ -170,47 +132,19 @@ def test_kernel_source_emulated_divergent_and_max_depth(emu):
     assert (so.tree_depth == 4).all()
 
 
-@pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion", CASES[:4] + CASES[5:6],
-                         ids=[f"{c[0]}-{c[1]}-D{c[2]}-{c[5]}-{c[6]}" for c in CASES[:4] + CASES[5:6]])
-def test_staged_fastdraw_variant_under_emulation_matches_oracle(emu_fast, kind, mkind, D, N, eps, sampler, criterion):
-    """-DAHMC_NUTS_FASTDRAW=1 (Philox block cache + probability-domain combine; off in the shipped build): same trees and
-    selections as the oracle from the same tapes."""
-    _case(emu_fast, kind, mkind, D, N, eps, sampler, criterion, seed=5 + D)
-
-
 @pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion", [
-    ("diag_gauss", "diag", 100, 5, 0.15, "multinomial", "generalised"), ("diag_gauss", "diag", 40, 5, 0.2, "multinomial", "strict"),
-    ("funnel", "diag", 70, 3, 0.1, "slice", "generalised")], ids=["D100-16x8", "D40-16x4-strict", "funnel-D70-slice"])
-def test_staged_alt_layout_two_chains_per_warp_matches_oracle(emu_alt, kind, mkind, D, N, eps, sampler, criterion):
-    """-DAHMC_NUTS_ALT_LAYOUT=1 (+ FASTDRAW): 16 lanes x 4 / 8 coordinates per chain, i.e. two chains per warp for
-    32 < D <= 128 -- staged for the round-2 A/B; an odd chain count leaves half a warp idle."""
-    _case(emu_alt, kind, mkind, D, N, eps, sampler, criterion, seed=9 + D, scale=0.5 if kind == "funnel" else 1.0)
-
-
-@pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion", [
-    ("diag_gauss", "diag", 100, 7, 0.15, "multinomial", "generalised"), ("funnel", "diag", 50, 6, 0.1, "multinomial", "generalised")],
-    ids=["D100-8x16", "funnel-D50-8x8"])
-def test_staged_alt_layout_four_chains_per_warp_matches_oracle(emu_alt2, kind, mkind, D, N, eps, sampler, criterion):
-    """-DAHMC_NUTS_ALT_LAYOUT=2: 8 lanes x 8 / 16 coordinates per chain (four chains per warp for 32 < D <= 128)."""
-    _case(emu_alt2, kind, mkind, D, N, eps, sampler, criterion, seed=19 + D, scale=0.5 if kind == "funnel" else 1.0)
-
-
-@pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion", [
-    ("diag_gauss", "diag", 128, 3, 0.12, "multinomial", "generalised"), ("diag_gauss", "diag", 8, 9, 0.25, "multinomial", "strict"),
+    ("diag_gauss", "diag", 128, 3, 0.12, "multinomial", "generalised"), ("diag_gauss", "diag", 64, 4, 0.25, "multinomial", "strict"),
     ("funnel", "diag", 4, 10, 0.3, "slice", "generalised"), ("dense_gauss", "dense", 8, 5, 0.3, "multinomial", "generalised"),
     ("diag_gauss", "diag", 7, 9, 0.25, "multinomial", "generalised")],
-    ids=["D128-full", "D8-full-strict", "D4-full-slice", "D8-full-dense", "D7-ragged"])
-def test_staged_full_tile_instantiation_matches_oracle(emu_full, kind, mkind, D, N, eps, sampler, criterion):
-    """-DAHMC_NUTS_FULLTILE=1 (+ FASTDRAW + RELOAD_COEF): D == G * E takes the instantiation with a compile-time D (no
-    `d < D` guards), ragged D the general one; model / metric coefficients are re-read where they are used."""
-    _case(emu_full, kind, mkind, D, N, eps, sampler, criterion, seed=29 + D, scale=0.5 if kind == "funnel" else 1.0)
+    ids=["D128-full", "D64-full-strict", "D4-slice", "D8-dense", "D7-ragged"])
+def test_full_tile_instantiation_matches_oracle(emu, kind, mkind, D, N, eps, sampler, criterion):
+    """D == G * E (G = 32, E in 2..8) takes the instantiation with a compile-time D (no `d < D` guards), every other D the
+    general one."""
+    _case(emu, kind, mkind, D, N, eps, sampler, criterion, seed=29 + D, scale=0.5 if kind == "funnel" else 1.0)
 
 
-def test_staged_fastdraw_variant_divergent_and_max_depth(emu_fast):
-    so = _case(emu_fast, "funnel", "diag", 4, 8, 1.5, "multinomial", "generalised", seed=3, delta_max=3.0, scale=1.5)
-    assert so.numerical_error.sum() > 0
-    so = _case(emu_fast, "funnel", "diag", 4, 8, 2.5, "multinomial", "generalised", seed=6, delta_max=1000.0, scale=3.0)
-    _case(emu_fast, "std_normal", "unit", 3, 6, 0.02, "multinomial", "generalised", seed=4, max_depth=4)
+def test_kernel_source_emulated_wild_funnel_start(emu):
+    _case(emu, "funnel", "diag", 4, 8, 2.5, "multinomial", "generalised", seed=6, delta_max=1000.0, scale=3.0)
 
 
 def _philox_run(lib, N, D, T, seed, n_adapts=0, adapt=False, eps0=0.3, Minv0=None, sd=None, mu=None, windows=(3, 2, 4), n_min=3):
@@ -242,26 +176,10 @@ def _philox_run(lib, N, D, T, seed, n_adapts=0, adapt=False, eps0=0.3, Minv0=Non
     return dict(draws=draws, acc=acc.reshape(T, N), n_steps=ns.reshape(T, N), eps=eps_rw, minv=minv_rw, trace=trace, theta=out["th"])
 
 
-def test_fastdraw_variant_equals_default_build_on_philox_streams(emu, emu_fast):
-    """Philox mode (no tapes): the staged variant consumes the same counter-based streams (cached blocks instead of
-    regenerated ones, prefetched one per lane) and decides the same events, so whole multi-transition runs give
-    bit-identical draws and trees (the acceptance statistic, summed in a different order, to 1e-13)."""
-    rng = np.random.default_rng(2)
-    D, N, T = 6, 9, 12
-    sd, mu = np.exp(rng.uniform(-0.5, 0.5, D)), rng.normal(size=D)
-    a = _philox_run(emu, N, D, T, seed=77, sd=sd, mu=mu)
-    b = _philox_run(emu_fast, N, D, T, seed=77, sd=sd, mu=mu)
-    assert np.array_equal(a["draws"], b["draws"]) and np.array_equal(a["n_steps"], b["n_steps"])
-    assert np.allclose(a["acc"], b["acc"], rtol=1e-13, atol=0)  # sum_alpha is accumulated in a different (lane-parallel) order
-    assert a["n_steps"].max() >= 7 and len(np.unique(a["draws"][:, 0, 0])) > 6  # the chains really moved
-
-
-@pytest.mark.parametrize("which", ["default", "fastdraw", "fastdraw+reloadcoef"])
-def test_in_launch_adaptation_under_emulation_equals_oracle_adaptors(emu, emu_fast, emu_full, which):
+def test_in_launch_adaptation_under_emulation_equals_oracle_adaptors(emu):
     """The adaptive kernel family (per-chain NesterovDualAveraging + windowed WelfordVar inside the persistent launch)
     executed by the emulator, replayed iteration by iteration with the ORACLE's adaptors fed by the kernel's own
     acceptance rates and draws: step-size trace, window update of M^-1, reset and finalize! must agree."""
-    emu = {"default": emu, "fastdraw": emu_fast, "fastdraw+reloadcoef": emu_full}[which]
     rng = np.random.default_rng(3)
     D, N, T, n_adapts = 5, 6, 24, 20
     ib, tb, wsz = 3, 2, 4
@@ -338,12 +256,17 @@ LF_CASES = [("diag_gauss", "diag", 7, 9, 0.1, 20, 1),    # fused fast path, 4 ch
             ("std_normal", "unit", 3, 13, 0.2, 11, 1),   # fast path, 8 chains per warp
             ("funnel", "diag", 6, 7, 0.05, 12, 1),       # exact per-step path
             ("dense_gauss", "dense", 6, 5, 0.1, 9, 1),   # exact path with the shared-memory slab matvec
-            ("diag_gauss", "diag", 40, 3, 0.1, 16, 0)]   # backward, one chain per warp (E = 2)
+            ("diag_gauss", "diag", 40, 3, 0.1, 16, 0),   # backward, one chain per warp (E = 2)
+            ("diag_gauss", "diag", 64, 3, 0.1, 32, 1),   # full tile: lane-contiguous 128-bit layout of the fast path
+            ("std_normal", "unit", 64, 2, 0.2, 7, 0),    # same, unit coefficients, backward
+            ("diag_gauss", "diag", 5, 9, 0.1, 300, 1)]   # n * log2(K) > 240: periodic magnitude tests instead of one
 
 
-@pytest.mark.parametrize("kind,mkind,D,N,eps,n,fwd", LF_CASES, ids=[f"{c[0]}-{c[1]}-D{c[2]}" for c in LF_CASES])
-def test_trajectory_kernel_source_under_emulation_matches_oracle(emu_lf, kind, mkind, D, N, eps, n, fwd):
-    """K1 (`leapfrog_kernel`, fast and exact paths of ahmc_traj.cuh) executed by the emulator vs the oracle's `step`."""
+@pytest.mark.parametrize("with_g", [True, False], ids=["cached-grad", "no-grad"])
+@pytest.mark.parametrize("kind,mkind,D,N,eps,n,fwd", LF_CASES, ids=[f"{c[0]}-{c[1]}-D{c[2]}-n{c[5]}" for c in LF_CASES])
+def test_trajectory_kernel_source_under_emulation_matches_oracle(emu_lf, kind, mkind, D, N, eps, n, fwd, with_g):
+    """K1 (`leapfrog_kernel`, fast and exact paths of ahmc_traj.cuh) executed by the emulator vs the oracle's `step`;
+    `no-grad`: z_in.lp_gradient == NULL, the kernel recomputes dH/dtheta at the start point."""
     rng = np.random.default_rng(11 + D)
     model, metric, p0, dp1, Minv, cholU = _lf_system(kind, mkind, D, rng)
     th, r = rng.normal(size=(N, D)) * (0.5 if kind == "funnel" else 1.0), rng.normal(size=(N, D))
@@ -356,8 +279,9 @@ def test_trajectory_kernel_source_under_emulation_matches_oracle(emu_lf, kind, m
     status, done = np.zeros(N, dtype=np.uint32), np.zeros(N, dtype=np.int32)
     q = EmuLf(model_kind=KINDS[kind], metric_kind=MKINDS[mkind], D=D, N=N, p0=P(p0), p1=P(dp1), c0=0.0, Minv=P(Minv),
               minv_stride=0, cholU=P(cholU), eps=eps, eps_chain=P(eps_chain), n_steps=n, fwd=fwd, temper_alpha=0.0,
-              th_in=P(th), r_in=P(r), g_in=P(g_in), lp_in=P(lp_in), th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]),
-              lp_out=P(lp_o), lk_out=P(lk_o), dr_out=P(o["dr"]), status=P(status), steps_done=P(done), flags=0, hmc=0)
+              th_in=P(th), r_in=P(r), g_in=P(g_in) if with_g else None, lp_in=P(lp_in), th_out=P(o["th"]), r_out=P(o["r"]),
+              g_out=P(o["g"]), lp_out=P(lp_o), lk_out=P(lk_o), dr_out=P(o["dr"]), status=P(status), steps_done=P(done), flags=0,
+              hmc=0)
     assert emu_lf.emu_leapfrog(C.byref(q)) == 0
     assert (done == n).all() and (status == 0).all()
     assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10 and rel_err(o["g"].T, zo.lp_gradient) < 1e-10
@@ -546,36 +470,19 @@ class EmuDense(C.Structure):
                 ("wide_tile", C.c_int32), ("norms_out", C.c_double * 2)]
 
 
-_DENSE_VARIANTS = {  # name -> (compile-time knobs of ahmc_dense.cu, emu_dense_knobs() = padded | release << 1 | stages << 2)
-    "default": ([], 0 | 0 | 2 << 2),
-    "padded": (["-DAHMC_DENSE_PADDED_A=1"], 1 | 2 << 2),
-    "release": (["-DAHMC_DENSE_MBAR_RELEASE=1"], 2 | 2 << 2),
-    "padded+release+3stages": (["-DAHMC_DENSE_PADDED_A=1", "-DAHMC_DENSE_MBAR_RELEASE=1", "-DAHMC_DENSE_STAGES=3"], 1 | 2 | 3 << 2)}
-
-
 @pytest.fixture(scope="module")
-def _dense_libs(tmp_path_factory):
+def emu_dense(tmp_path_factory):
     tmp = tmp_path_factory.mktemp("simt_dense")
     d = os.path.join(ROOT, "tests", "simt_emu")
-    procs = {}
-    for name, (defs, _) in _DENSE_VARIANTS.items():
-        out = tmp / f"libdense_emu_{len(procs)}.so"
-        cmd = ["g++", *defs, "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-x", "c++",
-               "-I", os.path.join(d, "include"), "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"),
-               "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"), os.path.join(d, "dense_emu.cpp"), "-o", str(out)]
-        procs[name] = (subprocess.Popen(cmd, stderr=subprocess.PIPE, text=True), out)
-    libs = {}
-    for name, (pr, out) in procs.items():
-        _, err = pr.communicate()
-        assert pr.returncode == 0, err[-2000:]
-        libs[name] = C.CDLL(str(out))
-        assert libs[name].emu_dense_knobs() == _DENSE_VARIANTS[name][1]
-    return libs
-
-
-@pytest.fixture(scope="module")
-def emu_dense(_dense_libs):
-    return _dense_libs["default"]
+    out = tmp / "libdense_emu.so"
+    cmd = ["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-x", "c++",
+           "-I", os.path.join(d, "include"), "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"),
+           "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"), os.path.join(d, "dense_emu.cpp"), "-o", str(out)]
+    pr = subprocess.run(cmd, capture_output=True, text=True)
+    assert pr.returncode == 0, pr.stderr[-2000:]
+    lib = C.CDLL(str(out))
+    assert lib.emu_dense_stages() == 3
+    return lib
 
 
 def _dense_run(lib, kind, mkind, D, N, eps, n, fwd, seed, per_chain_eps=True, wide=0, poison=None):
@@ -636,29 +543,13 @@ def test_dense_tile_kernel_emulated_hands_a_suspect_tile_to_the_exact_kernel(emu
     assert rel_err(o["th"][:32].T, zo.theta[:, :32]) < 1e-10 and np.allclose(lk_o[:32], zo.lk_value[:32], rtol=1e-10)
 
 
-@pytest.mark.parametrize("variant", [v for v in _DENSE_VARIANTS if v != "default"])
-@pytest.mark.parametrize("kind,mkind,D,N,eps,n,fwd,pce,wide", DENSE_CASES[:4], ids=[f"{c[0]}-{c[1]}-D{c[2]}" for c in DENSE_CASES[:4]])
-def test_staged_dense_pipeline_variants_under_emulation_match_oracle(_dense_libs, variant, kind, mkind, D, N, eps, n, fwd, pce, wide):
-    """the staged K4 pipeline knobs (single contiguous chunk copy from a padded matrix; stage release through mbarriers
-    instead of a CTA barrier per chunk; a third stage): same oracle comparison as the shipped form"""
-    zo, o, lp_o, lk_o, status, done, need = _dense_run(_dense_libs[variant], kind, mkind, D, N, eps, n, fwd, seed=100 + D,
-                                                       per_chain_eps=pce, wide=wide)
-    assert (need == 0).all() and (done == n).all() and (status == 0).all()
-    assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10 and rel_err(o["g"].T, zo.lp_gradient) < 1e-10
-    assert np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10) and np.allclose(lk_o, zo.lk_value, rtol=1e-10, atol=1e-10)
-    assert rel_err(o["dr"].T, zo.lk_gradient) < 1e-10
-
-
 # ------------------------------------------------------------------------------- data-race check of the kernel sources
 _RACE_BUILDS = {  # name -> compile-time definitions for tests/simt_emu/race_main.cpp
     "nuts": ["-DRACE_NUTS"],
-    "nuts-staged": ["-DRACE_NUTS", "-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_FULLTILE=1", "-DAHMC_NUTS_RELOAD_COEF=1"],
-    "nuts-staged-two-chains-per-warp": ["-DRACE_NUTS", "-DAHMC_NUTS_FASTDRAW=1", "-DAHMC_NUTS_ALT_LAYOUT=1"],
     "lf": ["-DRACE_LF"],
     "multinomial": ["-DRACE_MN"],
     "adapt": ["-DRACE_ADAPT"],
     "dense": ["-DRACE_DENSE"],
-    "dense-staged": ["-DRACE_DENSE", "-DAHMC_DENSE_PADDED_A=1", "-DAHMC_DENSE_MBAR_RELEASE=1", "-DAHMC_DENSE_STAGES=3"],
     "dense-mutant": ["-DRACE_DENSE"]}  # a copy of ahmc_dense.cu with one barrier removed: the detector must fire
 
 
@@ -695,7 +586,7 @@ def _race_bins(tmp_path_factory):
 def test_kernel_sources_are_data_race_free_under_thread_sanitizer(_race_bins, name):
     """Every CUDA thread is a host thread whose only synchronisation is what the kernel asks for, so ThreadSanitizer sees a
     missing __syncwarp / __syncthreads / mbarrier wait as a data race: the shipped NUTS, trajectory / HMC, MultinomialTS, adaptor-statistics
-    and dense-tile sources and their staged variants must be clean, and a copy of the dense kernel with one barrier removed must be reported."""
+    and dense-tile sources must be clean, and a copy of the dense kernel with one barrier removed must be reported."""
     r = subprocess.run([_race_bins[name]], capture_output=True, text=True, timeout=600)
     if "FATAL: ThreadSanitizer" in r.stderr:
         pytest.skip("ThreadSanitizer cannot run in this environment: " + r.stderr.strip().splitlines()[0])
