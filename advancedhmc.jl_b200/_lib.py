@@ -49,6 +49,12 @@ class AdaptCfg(C.Structure):
                 ("eps_trace", _vp)]
 
 
+class PooledCfg(C.Structure):
+    _fields_ = [("n_adapts", C.c_int32), ("init_buffer", C.c_int32), ("term_buffer", C.c_int32), ("window_size", C.c_int32),
+                ("delta", C.c_double), ("gamma", C.c_double), ("t0", C.c_double), ("kappa", C.c_double), ("eps0", C.c_double),
+                ("adapt_metric", C.c_int32), ("n_min", C.c_int32)]
+
+
 LOGP_GRAD_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _vp, _vp, C.c_int32, C.c_int64, C.c_int64, _vp)
 
 # name -> (restype, argtypes): exactly the entry points include/ahmc_b200.h declares
@@ -92,6 +98,17 @@ PROTOTYPES = {
                                              C.POINTER(PhasePoint), _vp, C.POINTER(Stats), C.c_uint32]),
     "ahmc_adapt_summary_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
     "ahmc_adapt_cov_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
+    "ahmc_comm_unique_id": (C.c_int, [_vp, _vp]),
+    "ahmc_comm_create": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "ahmc_comm_from_nccl": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(_vp)]),
+    "ahmc_comm_destroy": (C.c_int, [_vp, _vp]),
+    "ahmc_adapt_allgather_f64": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, C.c_uint32]),
+    "ahmc_pooled_create": (C.c_int, [_vp, C.c_int32, C.c_int64, C.POINTER(PooledCfg), _dp, C.POINTER(_vp)]),
+    "ahmc_pooled_destroy": (C.c_int, [_vp, _vp]),
+    "ahmc_pooled_eps": (_vp, [_vp]),
+    "ahmc_pooled_minv": (_vp, [_vp]),
+    "ahmc_adapt_exchange_f64": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
+    "ahmc_pooled_state": (C.c_int, [_vp, _vp, _dp, _dp, C.POINTER(C.c_int32), _dp]),
 }
 
 _lib = None

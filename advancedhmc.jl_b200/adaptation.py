@@ -429,3 +429,158 @@ def sample(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_samples: int, ada
     tm["bookkeeping"] += time.perf_counter() - t0
     return SampleResult(z.theta, draws, stats, A.step_size(kappa.tau.integrator),
                         None if adaptor is None else adaptor.Minv, total_steps, tm)
+
+
+# ------------------------------------------------------------------------------------------------ device-side pooling
+class Comm:
+    """`ahmc_comm`: the NCCL communicator of the ranks that share one adaptation.  `from_torch_distributed` creates it from
+    the default process group (rank 0 draws the unique id, `broadcast_object_list` ships the 128 bytes)."""
+
+    def __init__(self, ctx, handle, nranks, rank):
+        self.ctx, self.h, self.nranks, self.rank = ctx, handle, nranks, rank
+
+    @staticmethod
+    def from_torch_distributed(device: int = 0) -> Optional["Comm"]:
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return None
+        ctx = A.get_context(device)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            ctx.check(ctx.lib.ahmc_comm_unique_id(ctx.h, C.cast(buf, C.c_void_p)))
+        box = [bytes(buf)]
+        dist.broadcast_object_list(box, src=0)
+        idb = C.create_string_buffer(box[0], 128)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.ahmc_comm_create(ctx.h, C.cast(idb, C.c_void_p), world, rank, C.byref(h)))
+        return Comm(ctx, h, world, rank)
+
+    def allgather(self, record, flags: int = 0):
+        """`ahmc_adapt_allgather_f64`: (n,) device tensor -> (nranks, n) device tensor, on the context stream."""
+        import torch
+
+        out = torch.empty((self.nranks, record.numel()), dtype=torch.float64, device=record.device)
+        self.ctx.check(self.ctx.lib.ahmc_adapt_allgather_f64(self.ctx.h, self.h, record.data_ptr(), record.numel(),
+                                                              out.data_ptr(), flags))
+        return out
+
+    def destroy(self):
+        if self.h is not None:
+            self.ctx.lib.ahmc_comm_destroy(self.ctx.h, self.h)
+            self.h = None
+
+
+class PooledDeviceAdaptor:
+    """`ahmc_pooled`: StanHMCAdaptor(WelfordVar, NesterovDualAveraging) pooled over all chains of all ranks, resident on
+    the device.  `eps` (N,) and `Minv` (D,) are torch views of the buffers the library updates in place -- hand them to
+    `Leapfrog` / `DiagEuclideanMetric` once; `exchange` then needs no host work beyond one foreign call."""
+
+    def __init__(self, device: int, D: int, N: int, n_adapts: int, eps0: float, delta: float = 0.8, adapt_metric: bool = True,
+                 init_buffer: int = 75, term_buffer: int = 50, window_size: int = 25, gamma: float = 0.05, t0: float = 10.0,
+                 kappa: float = 0.75, n_min: int = 10, Minv0=None):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib as L
+
+        self.ctx = ctx = A.get_context(device)
+        self.D, self.N, self.n_adapts = D, N, n_adapts
+        cfg = L.PooledCfg(n_adapts, init_buffer, term_buffer, window_size, delta, gamma, t0, kappa, float(eps0),
+                          1 if adapt_metric else 0, n_min)
+        m0 = None if Minv0 is None else np.ascontiguousarray(Minv0, dtype=np.float64)
+        self.h = C.c_void_p()
+        ctx.check(ctx.lib.ahmc_pooled_create(ctx.h, D, N, C.byref(cfg), None if m0 is None else m0.ctypes.data_as(L._dp),
+                                             C.byref(self.h)))
+        dev = torch.device("cuda", device)
+        self.eps = torch.as_tensor(A._RawCuda(ctx.lib.ahmc_pooled_eps(self.h), (N,)), device=dev)
+        self.Minv = torch.as_tensor(A._RawCuda(ctx.lib.ahmc_pooled_minv(self.h), (D,)), device=dev)
+
+    def exchange(self, theta, acceptance_rate, comm: Optional[Comm] = None, eps_trace=None, flags: int = A.L.FLAG_ASYNC):
+        """`adapt!` of the next iteration (ahmc_adapt_exchange_f64): K5 -> all-gather -> merge + adaptor update, on the stream"""
+        self.ctx.check(self.ctx.lib.ahmc_adapt_exchange_f64(self.ctx.h, None if comm is None else comm.h, self.h, self.D, self.N,
+                                                             theta.data_ptr(), self.D, acceptance_rate.data_ptr(),
+                                                             None if eps_trace is None else eps_trace.data_ptr(), flags))
+
+    def state(self):
+        """synchronising read-back -> dict(eps, Minv, iteration, merged_record)"""
+        import ctypes as C
+
+        from . import _lib as L
+
+        eps, it = C.c_double(), C.c_int32()
+        minv, rec = np.empty(self.D), np.empty(2 + 2 * self.D)
+        self.ctx.check(self.ctx.lib.ahmc_pooled_state(self.ctx.h, self.h, C.byref(eps), minv.ctypes.data_as(L._dp), C.byref(it),
+                                                       rec.ctypes.data_as(L._dp)))
+        return dict(eps=eps.value, Minv=minv, iteration=it.value, merged_record=rec)
+
+    def destroy(self):
+        if self.h is not None:
+            self.ctx.lib.ahmc_pooled_destroy(self.ctx.h, self.h)
+            self.h = None
+
+
+def sample_pooled_device(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_samples: int, n_adapts: int, eps0: float,
+                         delta: float = 0.8, adapt_metric: bool = True, comm: Optional[Comm] = None, windows=(75, 50, 25),
+                         keep_eps_trace: bool = False) -> SampleResult:
+    """`sample` with the pooled StanHMCAdaptor on the DEVICE: every warm-up iteration is [transition kernel, K5, all-gather,
+    adaptor-update kernel] enqueued on one stream -- no device->host copy, no synchronisation, no new Hamiltonian / kernel
+    objects; the sampling phase is the persistent launch.  Dynamic (NUTS) and fixed-n static trajectories (a
+    FixedIntegrationTime trajectory needs eps on the host to size the trajectory: use `sample`)."""
+    import time
+
+    import torch
+
+    if not isinstance(h.metric, A.DiagEuclideanMetric):
+        raise A.L.AhmcError(A.L.ERR_UNSUPPORTED, "pooled device adaptation: DiagEuclideanMetric (WelfordVar)")
+    tau = kappa.tau
+    if isinstance(tau.termination_criterion, A.FixedIntegrationTime):
+        raise A.L.AhmcError(A.L.ERR_UNSUPPORTED, "FixedIntegrationTime needs eps on the host; use sample()")
+    N, D = theta.shape
+    dev = theta.device
+    tm = dict(transition=0.0, adapt=0.0, sampling_launch=0.0, bookkeeping=0.0)
+    n_adapts = min(n_adapts, n_samples)
+    Minv0 = h.metric.Minv if A._is_host(h.metric.Minv) else h.metric.Minv.detach().cpu().numpy()
+    ad = PooledDeviceAdaptor(dev.index or 0, D, N, n_adapts, eps0, delta, adapt_metric, *windows, Minv0=Minv0)
+    hd = A.Hamiltonian(A.DiagEuclideanMetric(ad.Minv), h.target)
+    kd = A.HMCKernel(A.Trajectory(tau.sampler, A.Leapfrog(ad.eps), tau.termination_criterion), kappa.refreshment)
+    z = A.phasepoint(hd, theta, torch.zeros_like(theta))
+    trace = torch.zeros(max(n_adapts, 1), dtype=torch.float64, device=dev) if keep_eps_trace else None
+    acc, nerr, nst = [], [], []
+    t0 = time.perf_counter()
+    for _ in range(n_adapts):
+        tr = A.transition(rng, hd, kd, z, flags=A.L.FLAG_ASYNC)
+        z = tr.z
+        ad.exchange(z.theta, tr.stat["acceptance_rate"], comm, trace)
+        acc.append(tr.stat["acceptance_rate"].mean())
+        nerr.append(tr.stat["numerical_error"].sum())
+        nst.append(tr.stat["n_steps"].sum())
+    tm["issue_warmup"] = time.perf_counter() - t0
+    torch.cuda.synchronize(dev)
+    tm["transition"] = time.perf_counter() - t0  # warm-up wall time: transitions and exchanges share one stream
+    n_rest = n_samples - n_adapts
+    draws = []
+    if n_rest > 0:
+        t1 = time.perf_counter()
+        z, dr, st = A.sample_transitions(rng, hd, kd, z, n_rest, keep_draws=False)
+        torch.cuda.synchronize(dev)
+        tm["sampling_launch"] = time.perf_counter() - t1
+        acc.append(st["acceptance_rate"].double().mean(dim=1))
+        nerr.append(st["numerical_error"].sum(dim=1))
+        nst.append(st["n_steps"].sum(dim=1))
+    cat = lambda xs: torch.cat([x.double().reshape(-1) for x in xs]).cpu().numpy() if xs else np.zeros(0)
+    acc_h, nerr_h, nst_h = cat(acc), cat(nerr), cat(nst)
+    s = ad.state()
+    stats = [dict(acceptance_rate=float(acc_h[k]), step_size=None, numerical_error=int(nerr_h[k]), n_steps=int(nst_h[k]),
+                  is_adapt=k < n_adapts) for k in range(len(acc_h))]
+    if keep_eps_trace:
+        tr_h = trace.cpu().numpy()
+        for k in range(n_adapts):
+            stats[k]["step_size_after"] = float(tr_h[k])
+    res = SampleResult(z.theta, draws, stats, s["eps"], s["Minv"], int(nst_h.sum()), tm)
+    ad.destroy()
+    return res

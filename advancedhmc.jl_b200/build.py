@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.environ.get("AHMC_OBJ_DIR", "/tmp/ahmc_b200_obj")  # objects stay out of the repo snapshot
 LIB = os.path.join(HERE, "libahmc_b200.so")
-SOURCES = ["ahmc_api.cu", "ahmc_leapfrog.cu", "ahmc_nuts.cu", "ahmc_nuts_var.cu", "ahmc_nuts_adapt.cu", "ahmc_adapt.cu", "ahmc_multinomial.cu", "ahmc_dense.cu"]
+SOURCES = ["ahmc_api.cu", "ahmc_leapfrog.cu", "ahmc_nuts.cu", "ahmc_nuts_var.cu", "ahmc_nuts_adapt.cu", "ahmc_adapt.cu", "ahmc_multinomial.cu", "ahmc_dense.cu", "ahmc_pooled.cu"]
 MB_LIB = os.path.join(HERE, "libahmc_microbench.so")  # bench.py's measurement helpers; not part of the C ABI
 MB_SOURCE = "ahmc_microbench.cu"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared"]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

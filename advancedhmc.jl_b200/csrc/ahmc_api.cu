@@ -1619,4 +1619,188 @@ int ahmc_adapt_cov_f64(ahmc_ctx* ctx, int32_t D, int64_t N, const double* theta,
     return finish_call(ctx, st, flags);
 }
 
+// ------------------------------------------------------------------------------------------ comm + pooled adaptor
+struct ahmc_comm {
+    void* nccl = nullptr;
+    int nranks = 1, rank = 0;
+    bool owned = false;
+};
+struct ahmc_pooled {
+    int D = 0;
+    int64_t N = 0;
+    char* dev = nullptr;  // one allocation: state | record | gathered (grown on demand) ...
+    void* state = nullptr;
+    double *eps_chain = nullptr, *minv = nullptr, *w_mu = nullptr, *w_M2 = nullptr, *record = nullptr, *merged = nullptr;
+    double* gathered = nullptr;
+    int gathered_ranks = 0;
+};
+
+int ahmc_comm_unique_id(ahmc_ctx* ctx, void* id128_out) {
+    if (!ctx || !id128_out) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/id");
+    if (const char* why = nccl_bind()) return fail(ctx, AHMC_ERR_UNSUPPORTED, "NCCL unavailable: %s", why);
+    int rc = nccl_unique_id(id128_out);
+    if (rc) return fail(ctx, AHMC_ERR_CUDA, "ncclGetUniqueId: %s", nccl_err(rc));
+    return AHMC_OK;
+}
+int ahmc_comm_create(ahmc_ctx* ctx, const void* id128, int32_t nranks, int32_t rank, ahmc_comm** out) {
+    if (!ctx || !id128 || !out) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/id/out");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, AHMC_ERR_INVALID, "need 0 <= rank < nranks");
+    if (const char* why = nccl_bind()) return fail(ctx, AHMC_ERR_UNSUPPORTED, "NCCL unavailable: %s", why);
+    DeviceGuard g(ctx->device);
+    void* c = nullptr;
+    int rc = nccl_comm_init(&c, nranks, id128, rank);
+    if (rc) return fail(ctx, AHMC_ERR_CUDA, "ncclCommInitRank: %s", nccl_err(rc));
+    ahmc_comm* m = new (std::nothrow) ahmc_comm;
+    if (!m) return fail(ctx, AHMC_ERR_NOMEM, "out of host memory");
+    m->nccl = c; m->nranks = nranks; m->rank = rank; m->owned = true;
+    *out = m;
+    return AHMC_OK;
+}
+int ahmc_comm_from_nccl(ahmc_ctx* ctx, void* nccl_comm, int32_t nranks, int32_t rank, ahmc_comm** out) {
+    if (!ctx || !nccl_comm || !out) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/comm/out");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, AHMC_ERR_INVALID, "need 0 <= rank < nranks");
+    if (const char* why = nccl_bind()) return fail(ctx, AHMC_ERR_UNSUPPORTED, "NCCL unavailable: %s", why);
+    ahmc_comm* m = new (std::nothrow) ahmc_comm;
+    if (!m) return fail(ctx, AHMC_ERR_NOMEM, "out of host memory");
+    m->nccl = nccl_comm; m->nranks = nranks; m->rank = rank; m->owned = false;
+    *out = m;
+    return AHMC_OK;
+}
+int ahmc_comm_destroy(ahmc_ctx* ctx, ahmc_comm* comm) {
+    if (!ctx) return AHMC_ERR_INVALID;
+    if (!comm) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (comm->owned && comm->nccl) nccl_comm_destroy(comm->nccl);
+    delete comm;
+    return AHMC_OK;
+}
+
+int ahmc_adapt_allgather_f64(ahmc_ctx* ctx, ahmc_comm* comm, const double* record, int64_t n, double* out, uint32_t flags) {
+    if (!ctx || !record || !out || n < 1) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/record/out or n < 1");
+    if (flags & AHMC_FLAG_HOST_BUFFERS) return fail(ctx, AHMC_ERR_UNSUPPORTED, "the exchange takes device pointers");
+    DeviceGuard g(ctx->device);
+    if (!comm || comm->nranks == 1) {
+        if (out != record) CU(cudaMemcpyAsync(out, record, (size_t)n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        int rc = nccl_allgather_f64(record, out, (size_t)n, comm->nccl, ctx->stream);
+        if (rc) return fail(ctx, AHMC_ERR_CUDA, "ncclAllGather: %s", nccl_err(rc));
+    }
+    if (!(flags & AHMC_FLAG_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+    return AHMC_OK;
+}
+
+int ahmc_pooled_create(ahmc_ctx* ctx, int32_t D, int64_t N, const ahmc_pooled_cfg* cfg, const double* Minv0, ahmc_pooled** out) {
+    if (!ctx || !cfg || !out) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/cfg/out");
+    if (D < 1 || N < 1) return fail(ctx, AHMC_ERR_INVALID, "need D >= 1, N >= 1");
+    if (cfg->n_adapts < 0 || !(cfg->eps0 > 0.0)) return fail(ctx, AHMC_ERR_INVALID, "need n_adapts >= 0 and eps0 > 0");
+    AdaptDev sched{};
+    if (!stan_window_schedule(sched, cfg->init_buffer, cfg->term_buffer, cfg->window_size, cfg->n_adapts))
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "the window schedule has more than 12 window ends");
+    DeviceGuard g(ctx->device);
+    ahmc_pooled* a = new (std::nothrow) ahmc_pooled;
+    if (!a) return fail(ctx, AHMC_ERR_NOMEM, "out of host memory");
+    a->D = D;
+    a->N = N;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t rec = (size_t)(2 + 2 * D) * 8;
+    const size_t total = al(pooled_state_bytes()) + al((size_t)N * 8) + 3 * al((size_t)D * 8) + 2 * al(rec);
+    if (cudaMalloc((void**)&a->dev, total) != cudaSuccess) {
+        delete a;
+        return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc(%zu) for the pooled adaptor failed", total);
+    }
+    char* p = a->dev;
+    a->state = p; p += al(pooled_state_bytes());
+    a->eps_chain = (double*)p; p += al((size_t)N * 8);
+    a->minv = (double*)p; p += al((size_t)D * 8);
+    a->w_mu = (double*)p; p += al((size_t)D * 8);
+    a->w_M2 = (double*)p; p += al((size_t)D * 8);
+    a->record = (double*)p; p += al(rec);
+    a->merged = (double*)p;
+    std::vector<char> img(pooled_state_bytes());
+    pooled_state_init(img.data(), cfg->eps0, sched, cfg->delta, cfg->gamma, cfg->t0, cfg->kappa, cfg->n_adapts,
+                      cfg->adapt_metric, cfg->n_min);
+    CU(cudaMemcpyAsync(a->state, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(a->w_mu, 0, (size_t)D * 8, ctx->stream));
+    CU(cudaMemsetAsync(a->w_M2, 0, (size_t)D * 8, ctx->stream));
+    CU(cudaMemsetAsync(a->merged, 0, rec, ctx->stream));
+    if (Minv0) CU(cudaMemcpyAsync(a->minv, Minv0, (size_t)D * 8, cudaMemcpyHostToDevice, ctx->stream));
+    else CU(launch_fill(a->minv, D, 1.0, ctx->stream));
+    CU(launch_fill(a->eps_chain, N, cfg->eps0, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // img / Minv0 are host memory of this frame
+    *out = a;
+    return AHMC_OK;
+}
+int ahmc_pooled_destroy(ahmc_ctx* ctx, ahmc_pooled* a) {
+    if (!ctx) return AHMC_ERR_INVALID;
+    if (!a) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(a->dev);
+    cudaFree(a->gathered);
+    delete a;
+    return AHMC_OK;
+}
+double* ahmc_pooled_eps(ahmc_pooled* a) { return a ? a->eps_chain : nullptr; }
+double* ahmc_pooled_minv(ahmc_pooled* a) { return a ? a->minv : nullptr; }
+
+int ahmc_adapt_exchange_f64(ahmc_ctx* ctx, ahmc_comm* comm, ahmc_pooled* a, int32_t D, int64_t N, const double* theta,
+                            int64_t ld, const double* acceptance_rate, double* eps_trace, uint32_t flags) {
+    if (!ctx || !a || !theta || !acceptance_rate) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/adaptor/theta/acceptance_rate");
+    if (flags & AHMC_FLAG_HOST_BUFFERS) return fail(ctx, AHMC_ERR_UNSUPPORTED, "the exchange takes device pointers");
+    if (D != a->D || N != a->N || ld < D) return fail(ctx, AHMC_ERR_INVALID, "D / N differ from the adaptor's, or ld < D");
+    DeviceGuard g(ctx->device);
+    const int R = comm ? comm->nranks : 1;
+    const size_t rec = (size_t)(2 + 2 * D);
+    if (R > 1 && a->gathered_ranks < R) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(a->gathered);
+        a->gathered = nullptr;
+        if (cudaMalloc((void**)&a->gathered, rec * 8 * (size_t)R) != cudaSuccess)
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc for the gathered records failed");
+        a->gathered_ranks = R;
+    }
+    // K5: this rank's record (same workspace discipline as ahmc_adapt_summary_f64)
+    const int blocks = (int)(N < 148 ? N : 148);
+    const size_t need = ((size_t)blocks * (D + 1) + 2) * sizeof(double);
+    if (need > ctx->adapt_scratch_bytes) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->adapt_scratch);
+        ctx->adapt_scratch = nullptr;
+        ctx->adapt_scratch_bytes = 0;
+        if (cudaMalloc((void**)&ctx->adapt_scratch, need) != cudaSuccess)
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc(%zu) for the adaptor workspace failed", need);
+        ctx->adapt_scratch_bytes = need;
+        CU(cudaMemsetAsync(ctx->adapt_scratch, 0, need, ctx->stream));
+    }
+    int nl = 0;
+    CU(launch_adapt_summary(D, N, theta, ld, acceptance_rate, a->record, ctx->adapt_scratch + 2, (unsigned*)ctx->adapt_scratch,
+                            blocks, ctx->stream, &nl));
+    const double* gathered = a->record;
+    if (R > 1) {
+        int rc = nccl_allgather_f64(a->record, a->gathered, rec, comm->nccl, ctx->stream);
+        if (rc) return fail(ctx, AHMC_ERR_CUDA, "ncclAllGather: %s", nccl_err(rc));
+        gathered = a->gathered;
+    }
+    CU(launch_pooled_update(a->state, gathered, R, D, a->w_mu, a->w_M2, a->minv, a->eps_chain, N, eps_trace, a->merged,
+                            ctx->stream, &nl));
+    ctx->launches += nl;
+    if (!(flags & AHMC_FLAG_ASYNC)) CU(cudaStreamSynchronize(ctx->stream));
+    return AHMC_OK;
+}
+
+int ahmc_pooled_state(ahmc_ctx* ctx, ahmc_pooled* a, double* eps, double* Minv, int32_t* iteration, double* merged_record) {
+    if (!ctx || !a) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/adaptor");
+    DeviceGuard g(ctx->device);
+    std::vector<char> img(pooled_state_bytes());
+    CU(cudaMemcpyAsync(img.data(), a->state, img.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Minv) CU(cudaMemcpyAsync(Minv, a->minv, (size_t)a->D * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (merged_record) CU(cudaMemcpyAsync(merged_record, a->merged, (size_t)(2 + 2 * a->D) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int it = 0;
+    pooled_state_read(img.data(), eps, &it, nullptr, nullptr);
+    if (iteration) *iteration = it;
+    return AHMC_OK;
+}
+
 }  // extern "C"

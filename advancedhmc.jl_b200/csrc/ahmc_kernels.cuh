@@ -257,6 +257,25 @@ cudaError_t launch_adapt_summary(int D, long long N, const double* theta, long l
 cudaError_t launch_adapt_cov(int D, long long N, const double* theta, long long ld, const double* mean, double* out,
                              cudaStream_t st, int* n_launches);
 
+// pooled adaptation on the device + NCCL bound at run time (ahmc_pooled.cu)
+struct NcclId {
+    char internal[128];
+};
+cudaError_t launch_pooled_update(void* state, const double* gathered, int R, int D, double* w_mu, double* w_M2, double* Minv,
+                                 double* eps_chain, long long N, double* eps_trace, double* merged_out, cudaStream_t st,
+                                 int* n_launches);
+cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t st);
+size_t pooled_state_bytes();
+void pooled_state_init(void* host_image, double eps0, const AdaptDev& sched, double delta, double gamma, double t0, double kappa,
+                       int n_adapts, int adapt_metric, int n_min);
+void pooled_state_read(const void* host_image, double* eps, int* iteration, int* m, double* n_window);
+const char* nccl_bind();
+const char* nccl_err(int rc);
+int nccl_unique_id(void* out128);
+int nccl_comm_init(void** comm, int nranks, const void* id128, int rank);
+int nccl_comm_destroy(void* comm);
+int nccl_allgather_f64(const double* send, double* recv, size_t count, void* comm, cudaStream_t st);
+
 constexpr int kBlockThreads = 128;
 
 // dynamic shared memory needed by the dense paths: one D-double slab per group

@@ -246,6 +246,57 @@ int ahmc_nuts_adapt_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahm
                                const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
                                double* draws, const ahmc_stats* stats, uint32_t flags);
 
+/* ---- the one exchange: pooled adaptation across ranks, on the device ------------------ */
+/* Communicator over the GPUs that share one adaptation (one rank per GPU).  NCCL is bound at run time (dlopen of
+ * libnccl.so.2, override with AHMC_NCCL_LIB); without it these calls return AHMC_ERR_UNSUPPORTED and single-rank use
+ * (comm == NULL) still works.
+ *   ahmc_comm_unique_id : rank 0 fills 128 bytes, the host broadcasts them (MPI.jl / Distributed / torch.distributed ...)
+ *   ahmc_comm_create    : collective over all ranks -> ncclCommInitRank
+ *   ahmc_comm_from_nccl : wrap a communicator the host already owns (NCCL.jl's `Communicator` handle); not destroyed by us */
+typedef struct ahmc_comm ahmc_comm;
+int ahmc_comm_unique_id(ahmc_ctx* ctx, void* id128_out);
+int ahmc_comm_create(ahmc_ctx* ctx, const void* id128, int32_t nranks, int32_t rank, ahmc_comm** out);
+int ahmc_comm_from_nccl(ahmc_ctx* ctx, void* nccl_comm /* ncclComm_t */, int32_t nranks, int32_t rank, ahmc_comm** out);
+int ahmc_comm_destroy(ahmc_ctx* ctx, ahmc_comm* comm);
+
+/* All-gather of a small per-rank record of n doubles on the context stream (ncclAllGather; comm == NULL: one rank, a
+ * device copy).  record / out are device pointers (out: nranks * n doubles, rank order).  No host synchronisation with
+ * AHMC_FLAG_ASYNC. */
+int ahmc_adapt_allgather_f64(ahmc_ctx* ctx, ahmc_comm* comm, const double* record, int64_t n, double* out, uint32_t flags);
+
+/* Pooled Stan-style adaptor living on the device: one shared step size (dual averaging on the mean of min(1, alpha)
+ * over ALL chains of ALL ranks, src/adaptation/stepsize.jl:178-210) and one shared diagonal M^-1 (`WelfordVar` over
+ * chains x iterations of a window, massmatrix.jl:141-157), scheduled by `StanHMCAdaptor` (stan_adaptor.jl:13-50,
+ * 137-159).  The reference never pools (`Adaptation.jl:52` TODO); with one chain on one rank this is its scalar path.
+ * The adaptor owns two device buffers the transition calls read directly:
+ *   ahmc_pooled_eps(a)  : eps_chain[N] (every entry the shared step size)  -> pass as `eps_chain`
+ *   ahmc_pooled_minv(a) : Minv[D]                                          -> pass as ahmc_metric.Minv (Diag, stride 0) */
+typedef struct ahmc_pooled_cfg {
+    int32_t n_adapts;
+    int32_t init_buffer, term_buffer, window_size; /* 75 / 50 / 25 */
+    double delta, gamma, t0, kappa;               /* 0.8, 0.05, 10, 0.75 */
+    double eps0;                                  /* initial step size */
+    int32_t adapt_metric;                         /* 0: step size only; 1: + pooled WelfordVar */
+    int32_t n_min;                                /* 10 */
+} ahmc_pooled_cfg;
+typedef struct ahmc_pooled ahmc_pooled;
+int ahmc_pooled_create(ahmc_ctx* ctx, int32_t D, int64_t N, const ahmc_pooled_cfg* cfg,
+                       const double* Minv0 /* host, D doubles, NULL = ones */, ahmc_pooled** out);
+int ahmc_pooled_destroy(ahmc_ctx* ctx, ahmc_pooled* a);
+double* ahmc_pooled_eps(ahmc_pooled* a);
+double* ahmc_pooled_minv(ahmc_pooled* a);
+/* `adapt!(adaptor, theta, alpha)` of iteration i = (calls so far) + 1 (sampler.jl:72-90 glue), entirely on the context
+ * stream: K5 record of this rank's N chains -> all-gather over `comm` (NULL: single rank) -> rank-ordered Chan merge,
+ * dual averaging, window logic, `finalize!` at i == n_adapts; eps / M^-1 land in the buffers above before the next
+ * transition (same stream) starts.  theta[D x N] (ld), acceptance_rate[N]: device pointers.  Nothing is copied to the
+ * host and, with AHMC_FLAG_ASYNC, nothing is waited for.  eps_trace (nullable, device, n_adapts doubles) receives the
+ * step size after each iteration. */
+int ahmc_adapt_exchange_f64(ahmc_ctx* ctx, ahmc_comm* comm, ahmc_pooled* a, int32_t D, int64_t N, const double* theta,
+                            int64_t ld, const double* acceptance_rate, double* eps_trace, uint32_t flags);
+/* synchronising read-back of the adaptor (host outputs, each nullable): current eps, Minv[D], iterations done,
+ * the merged record [n, sum alpha, mean[D], M2[D]] of the last exchange */
+int ahmc_pooled_state(ahmc_ctx* ctx, ahmc_pooled* a, double* eps, double* Minv, int32_t* iteration, double* merged_record);
+
 /* ---- adaptor statistics (src/adaptation) ------------------------------------------------------ */
 /* Pooled summary of one iteration over this GPU's N chains, written to a small device/host record that
  * the host all-gathers across ranks (one NCCL all-gather) and merges in rank order:

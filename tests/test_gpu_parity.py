@@ -1035,3 +1035,66 @@ def test_dense_tile_kernel_vs_oracle(model, metric, D, N):
     z1 = A.step(A.Leapfrog(torch.as_tensor(eps, device=DEV)), h, z0, 7)
     ok = [c for c in range(N) if c != N // 2]
     assert rel_err(F(z1.theta)[:, ok], F(ze.theta)[:, ok]) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ pooled adaptor on the device
+@pytest.mark.parametrize("adapt_metric", [True, False], ids=["eps+Minv", "eps-only"])
+def test_device_pooled_adaptor_equals_host_adaptors_iteration_by_iteration(adapt_metric):
+    """ahmc_adapt_exchange_f64 (K5 -> [all-gather] -> device merge + dual averaging + WelfordVar + Stan windows) fed with the
+    same (theta, alpha) per iteration as the host-side pooled adaptors (adaptation.py: the restatement of stepsize.jl:178-210,
+    massmatrix.jl:141-157, stan_adaptor.jl:137-159 that tests/test_adaptation.py checks against the oracle): step size after
+    every iteration, M^-1 after every window end, reset and finalize! agree to 1e-12."""
+    from ahmc_b200 import adaptation as ad
+
+    D, N, n_adapts = 37, 300, 46
+    windows = (5, 4, 6)
+    rng = np.random.default_rng(8)
+    dev_ad = ad.PooledDeviceAdaptor(0, D, N, n_adapts, eps0=0.13, delta=0.8, adapt_metric=adapt_metric, init_buffer=windows[0],
+                                    term_buffer=windows[1], window_size=windows[2], n_min=3)
+    pc = ad.WelfordVar(D, n_min=3) if adapt_metric else ad.UnitMassMatrix()
+    host = ad.StanHMCAdaptor(pc, ad.NesterovDualAveraging(0.8, 0.13), *windows)
+    host.initialize(n_adapts)
+    assert len(host.window_splits) >= 2
+    trace = torch.zeros(n_adapts, dtype=torch.float64, device=DEV)
+    scale = np.exp(rng.uniform(-1, 1, D))
+    for i in range(1, n_adapts + 1):
+        th = torch.as_tensor(rng.normal(size=(N, D)) * scale + 0.3, device=DEV)
+        al = torch.as_tensor(np.clip(rng.uniform(0.3, 1.4, N), 0, None), device=DEV)
+        dev_ad.exchange(th, al, None, trace, flags=0)
+        rec = A.adapt_summary(th, al).cpu().numpy()
+        host.adapt(rec)
+        if i == n_adapts:
+            host.finalize()
+        s = dev_ad.state()
+        assert s["iteration"] == i
+        assert np.allclose(s["merged_record"], rec, rtol=1e-13, atol=0)
+        assert abs(s["eps"] - host.eps) <= 1e-12 * host.eps, (i, s["eps"], host.eps)
+        assert float(dev_ad.eps[0]) == s["eps"] and float(dev_ad.eps[N - 1]) == s["eps"]
+        if adapt_metric:
+            assert np.allclose(s["Minv"], host.Minv, rtol=1e-12, atol=0), i
+            assert np.array_equal(dev_ad.Minv.cpu().numpy(), s["Minv"])
+    assert np.allclose(trace.cpu().numpy()[-1], host.eps, rtol=1e-12)
+    dev_ad.destroy()
+
+
+def test_device_pooled_warmup_runs_without_host_syncs_and_adapts_like_the_host_loop():
+    """sample_pooled_device (transition, K5, merge + adaptor update per iteration, all on one stream) against sample() with
+    the host-side pooled StanHMCAdaptor on the same Philox streams: same step-size trajectory and final M^-1."""
+    from ahmc_b200 import adaptation as ad
+
+    D, N, n_adapts, n_samples = 24, 512, 60, 70
+    rng = np.random.default_rng(3)
+    s = np.exp(rng.uniform(-1, 1, D))
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.DiagGaussian(np.zeros(D), s))
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.2), A.GeneralisedNoUTurn(max_depth=6)))
+    th0 = torch.as_tensor(rng.normal(size=(N, D)), device=DEV)
+    windows = (10, 8, 6)
+    rd = ad.sample_pooled_device(A.PhiloxRNG(5), h, kern, th0, n_samples, n_adapts, eps0=0.2, windows=windows, keep_eps_trace=True)
+    host = ad.StanHMCAdaptor(ad.WelfordVar(D), ad.NesterovDualAveraging(0.8, 0.2), *windows)
+    rh = ad.sample(A.PhiloxRNG(5), h, kern, th0, n_samples, adaptor=host, n_adapts=n_adapts)
+    eps_dev = np.array([st["step_size_after"] for st in rd.stats[:n_adapts]])
+    eps_host = np.array([rh.stats[k + 1]["step_size"] for k in range(n_adapts - 1)] + [rh.eps])
+    assert np.allclose(eps_dev[:-1], eps_host[:-1], rtol=1e-9) and abs(rd.eps - rh.eps) < 1e-9 * rh.eps
+    assert np.allclose(rd.Minv, rh.Minv, rtol=1e-9)
+    assert np.allclose(rd.Minv, s * s, rtol=0.35)  # and it learned the target's scales
+    assert rd.leapfrog_steps == rh.leapfrog_steps
