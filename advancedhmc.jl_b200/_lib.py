@@ -64,6 +64,7 @@ PROTOTYPES = {
     "ahmc_destroy": (C.c_int, [_vp]),
     "ahmc_last_error": (C.c_char_p, [_vp]),
     "ahmc_synchronize": (C.c_int, [_vp]),
+    "ahmc_stream": (_vp, [_vp]),
     "ahmc_launch_count": (C.c_int64, [_vp]),
     "ahmc_last_transport": (C.c_char_p, [_vp]),
     "ahmc_model_create": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp, _dp, C.c_double, C.POINTER(_vp)]),
@@ -98,6 +99,8 @@ PROTOTYPES = {
                                              C.POINTER(PhasePoint), _vp, C.POINTER(Stats), C.c_uint32]),
     "ahmc_adapt_summary_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
     "ahmc_adapt_cov_f64": (C.c_int, [_vp, C.c_int32, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint32]),
+    "ahmc_find_good_stepsize_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.POINTER(PhasePoint),
+                                                C.POINTER(Rng), C.c_double, C.c_int32, _vp, _vp, C.c_uint32]),
     "ahmc_comm_unique_id": (C.c_int, [_vp, _vp]),
     "ahmc_comm_create": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(_vp)]),
     "ahmc_comm_from_nccl": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(_vp)]),

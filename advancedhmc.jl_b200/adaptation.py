@@ -332,9 +332,12 @@ def sample(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_samples: int, ada
     z = A.phasepoint(h, theta, torch.zeros_like(theta))  # sample_init (sampler.jl:36-46); r is refreshed anyway
     if isinstance(adaptor, A.VectorisedStanAdaptor):
         # the reference's vectorised adaptors (per-chain eps and M^-1): warm-up and sampling are ONE launch
+        if not isinstance(h.metric, A.DiagEuclideanMetric):
+            raise A.L.AhmcError(A.L.ERR_UNSUPPORTED, "VectorisedStanAdaptor adapts a per-chain diagonal M^-1: DiagEuclideanMetric")
+        n_adapts = min(n_adapts, n_samples)
         t0 = time.perf_counter()
-        zl, dr, st, eps, minv, _ = A.nuts_adapt_sample(rng, h, kappa, z, n_samples, min(n_adapts, n_samples), adaptor,
-                                                       keep_draws=keep_draws)
+        zl, dr, st, eps, minv, trace = A.nuts_adapt_sample(rng, h, kappa, z, n_samples, n_adapts, adaptor,
+                                                           keep_draws=keep_draws, keep_eps_trace=True)
         if hasattr(zl.theta, "is_cuda") and zl.theta.is_cuda:
             torch.cuda.synchronize(zl.theta.device)
         tm["sampling_launch"] = time.perf_counter() - t0
@@ -342,8 +345,9 @@ def sample(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_samples: int, ada
         acc_h = (a.double().mean(dim=1).cpu().numpy() if hasattr(a, "detach") else np.asarray(a).mean(axis=1))
         nerr_h = (e.sum(dim=1).cpu().numpy() if hasattr(e, "detach") else np.asarray(e).sum(axis=1))
         nst_h = (n.sum(dim=1).cpu().numpy() if hasattr(n, "detach") else np.asarray(n).sum(axis=1))
-        stats = [dict(acceptance_rate=float(acc_h[k]), step_size=None, numerical_error=int(nerr_h[k]), n_steps=int(nst_h[k]),
-                      is_adapt=k < n_adapts) for k in range(n_samples)]
+        eps_h = (trace.double().mean(dim=1).cpu().numpy() if hasattr(trace, "detach") else np.asarray(trace).mean(axis=1))
+        stats = [dict(acceptance_rate=float(acc_h[k]), step_size=float(eps_h[k]), numerical_error=int(nerr_h[k]),
+                      n_steps=int(nst_h[k]), is_adapt=k < n_adapts) for k in range(n_samples)]  # step_size: mean over chains
         dl = []
         if keep_draws:
             dl = list(dr.unbind(0) if hasattr(dr, "unbind") else dr)
@@ -392,7 +396,9 @@ def sample(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_samples: int, ada
     for i in range(1, n_adapts + 1):
         one(i, True)
     n_rest = n_samples - n_adapts
-    if n_rest > 0 and fused_sampling and isinstance(rng, A.PhiloxRNG) and type(kappa.tau.integrator) is A.Leapfrog:
+    fusable = (type(kappa.tau.integrator) is A.Leapfrog and
+               (isinstance(kappa.tau.termination_criterion, A._DYNAMIC) or kappa.tau.sampler is A.EndPointTS))
+    if n_rest > 0 and fused_sampling and isinstance(rng, A.PhiloxRNG) and fusable:
         t0 = time.perf_counter()
         z, dr, st = A.sample_transitions(rng, h, kappa, z, n_rest, keep_draws=keep_draws)
         if hasattr(z.theta, "is_cuda") and z.theta.is_cuda:
@@ -549,18 +555,22 @@ def sample_pooled_device(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_sam
     hd = A.Hamiltonian(A.DiagEuclideanMetric(ad.Minv), h.target)
     kd = A.HMCKernel(A.Trajectory(tau.sampler, A.Leapfrog(ad.eps), tau.termination_criterion), kappa.refreshment)
     z = A.phasepoint(hd, theta, torch.zeros_like(theta))
-    trace = torch.zeros(max(n_adapts, 1), dtype=torch.float64, device=dev) if keep_eps_trace else None
     acc, nerr, nst = [], [], []
     t0 = time.perf_counter()
-    for _ in range(n_adapts):
-        tr = A.transition(rng, hd, kd, z, flags=A.L.FLAG_ASYNC)
-        z = tr.z
-        ad.exchange(z.theta, tr.stat["acceptance_rate"], comm, trace)
-        acc.append(tr.stat["acceptance_rate"].mean())
-        nerr.append(tr.stat["numerical_error"].sum())
-        nst.append(tr.stat["n_steps"].sum())
-    tm["issue_warmup"] = time.perf_counter() - t0
-    torch.cuda.synchronize(dev)
+    # torch work (allocation / release of the per-iteration buffers, the scalar reductions) runs on the CONTEXT's stream:
+    # the transition and exchange calls are asynchronous, so everything that touches their buffers must be ordered with them
+    torch.cuda.current_stream(dev).synchronize()
+    with torch.cuda.stream(ad.ctx.torch_stream()):
+        trace = torch.zeros(max(n_adapts, 1), dtype=torch.float64, device=dev) if keep_eps_trace else None
+        for _ in range(n_adapts):
+            tr = A.transition(rng, hd, kd, z, flags=A.L.FLAG_ASYNC)
+            z = tr.z
+            ad.exchange(z.theta, tr.stat["acceptance_rate"], comm, trace)
+            acc.append(tr.stat["acceptance_rate"].mean())
+            nerr.append(tr.stat["numerical_error"].sum())
+            nst.append(tr.stat["n_steps"].sum())
+        tm["issue_warmup"] = time.perf_counter() - t0
+        torch.cuda.synchronize(dev)
     tm["transition"] = time.perf_counter() - t0  # warm-up wall time: transitions and exchanges share one stream
     n_rest = n_samples - n_adapts
     draws = []

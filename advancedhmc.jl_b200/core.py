@@ -66,6 +66,11 @@ class Context:
     def synchronize(self):
         self.check(self.lib.ahmc_synchronize(self.h))
 
+    def torch_stream(self):
+        """the context's stream as a torch stream: run torch work that feeds / consumes FLAG_ASYNC calls under
+        `with torch.cuda.stream(ctx.torch_stream())` so that torch's allocator and kernels are ordered with ours"""
+        return torch.cuda.ExternalStream(int(self.lib.ahmc_stream(self.h)), device=torch.device("cuda", self.device))
+
     def last_transport(self) -> str:
         """how the last host-buffer `step` moved its buffers (ahmc_last_transport)"""
         return self.lib.ahmc_last_transport(self.h).decode()
@@ -345,7 +350,9 @@ class PhasePoint:
 
     def __init__(self, theta, r, lp: DualValue, lk: DualValue):
         n = tuple(theta.shape)
-        if tuple(r.shape) != n or tuple(lp.gradient.shape) != n or (lk.gradient is not None and tuple(lk.gradient.shape) != n):
+        # lp.gradient may be None: "not cached" -- `step` then recomputes it on the device for built-in targets
+        if (tuple(r.shape) != n or (lp.gradient is not None and tuple(lp.gradient.shape) != n)
+                or (lk.gradient is not None and tuple(lk.gradient.shape) != n)):
             raise L.InvalidArgument(L.ERR_INVALID, "length(theta) == length(r) == length(lp.gradient) == length(lk.gradient) violated")
         self.theta, self.r, self.lp, self.lk = theta, r, lp, lk
 
@@ -771,6 +778,22 @@ def _stats_buffers(like, N, nuts, T=None):
     return s, c
 
 
+def _jitter_generator(rng) -> np.random.Generator:
+    """host uniforms for `jitter` (integrator.jl:140-156), reproducible from the transition's rng"""
+    if isinstance(rng, PhiloxRNG):
+        return np.random.Generator(np.random.Philox(key=rng.seed, counter=[1, 0, 0, rng.offset]))
+    if isinstance(rng, np.random.Generator):
+        return rng
+    g = getattr(rng, "_jitter_gen", None)
+    if g is None:
+        g = np.random.default_rng(0)
+        try:
+            rng._jitter_gen = g
+        except Exception:
+            pass
+    return g
+
+
 def transition(rng, h: Hamiltonian, kappa: Union[HMCKernel, Trajectory], z: PhasePoint, flags: int = 0) -> Transition:
     """`transition(rng, h, kappa, z)` (sampler.jl:48-58 -> trajectory.jl:271-300 static / :677-742 NUTS).
     With an HMCKernel the momentum is refreshed first; with a bare Trajectory z.r is used as is."""
@@ -784,6 +807,14 @@ def transition(rng, h: Hamiltonian, kappa: Union[HMCKernel, Trajectory], z: Phas
     out = _empty_pp(z.theta, with_lk_gradient=False)
     md, keep = h.metric._desc(D, N, z.theta)
     lf = tau.integrator
+    if isinstance(lf, JitteredLeapfrog):
+        # `@set! tau.integrator = jitter(rng, tau.integrator)` (src/sampler.jl, transition): a fresh jittered step size per
+        # transition, derived from the nominal one (so a dual-averaging update of eps0 takes effect).  The jitter uniforms
+        # come from a host generator keyed by the transition's own rng state.
+        lf = jitter(_jitter_generator(rng), lf)
+    if isinstance(lf, TemperedLeapfrog):
+        raise L.AhmcError(L.ERR_UNSUPPORTED, "TemperedLeapfrog inside a fused transition is not built (the transition kernels "
+                                              "run plain leapfrog); use step() for tempered trajectories")
     e, ep, keep2 = _eps_args(step_size(lf), z.theta, N)
     rc, keep3 = rng._c()
     rc.partial_refresh_alpha = _refresh_alpha(kappa)
@@ -855,58 +886,28 @@ def find_good_stepsize(rng, h: Hamiltonian, theta, initial_step_size: float = 0.
     return eps
 
 
-def find_good_stepsize_batched(rng, h: Hamiltonian, theta, initial_step_size: float = 0.1, max_n_iters: int = 100):
-    """N independent copies of `find_good_stepsize` (src/trajectory.jl:768-837), one per chain of `theta` (N, D), run in
-    lock-step: every probe `A(h, z, eps)` of all chains is ONE launch of the fused `step` kernel with a per-chain step
-    size; the per-chain search state (a few scalars per chain) is advanced on the host exactly as the reference's
-    control flow does for a single chain (finished chains keep probing with their final eps and ignore the result).
-    Returns eps (N,) -- the natural starting point for the vectorised adaptors (`VectorisedStanAdaptor`).
-    Chain c's result equals `find_good_stepsize` on that chain alone with the same momentum."""
+def find_good_stepsize_batched(rng, h: Hamiltonian, theta, initial_step_size: float = 0.1, max_n_iters: int = 100,
+                               return_momentum: bool = False):
+    """N independent copies of `find_good_stepsize` (src/trajectory.jl:768-837), one per chain of `theta` (N, D), in ONE
+    kernel launch (ahmc_find_good_stepsize_f64): momentum draw, direction probe, crossing loop and bisection all run on the
+    device, each chain at its own pace -- no host round trip.  Returns eps (N,) -- the natural starting point for the
+    vectorised adaptors (`VectorisedStanAdaptor`).  Chain c's result equals `find_good_stepsize` on that chain alone with
+    the same momentum."""
     if theta.ndim != 2:
         raise L.InvalidArgument(L.ERR_INVALID, "find_good_stepsize_batched takes (N, D) positions")
-    N = theta.shape[0]
-    host = _is_host(theta)
-    r = rand_momentum(rng, h.metric, h.kinetic, theta)
-    z = phasepoint(h, theta, r)
-
-    def to_h(x):
-        return np.asarray(x, dtype=np.float64) if host else x.detach().cpu().numpy()
-
-    H = to_h(energy(z))
-
-    def A_(eps):  # trajectory.jl:753-757 for all chains
-        e = eps if host else torch.as_tensor(eps, device=theta.device)
-        return to_h(energy(step(Leapfrog(e), h, z, 1, with_lk_gradient=False)))
-
-    log_a_min, log_a_cross, log_a_max = 2 * math.log(0.5), math.log(0.5), math.log(0.75)
-    eps = np.full(N, float(initial_step_size))
-    eps_prime = eps.copy()
-    dH = H - A_(eps)
-    too_high = dH > log_a_cross
-    active = np.ones(N, dtype=bool)
-    for _ in range(max_n_iters):  # crossing step (:796-810)
-        if not active.any():
-            break
-        eps_prime = np.where(active, np.where(too_high, 2.0 * eps, 0.5 * eps), eps_prime)
-        dH = H - A_(eps)
-        crossed = too_high != (dH > log_a_cross)
-        stop = active & crossed
-        cont = active & ~crossed
-        eps = np.where(cont, eps_prime, eps)
-        active = active & ~stop
-    lo, hi = np.minimum(eps, eps_prime), np.maximum(eps, eps_prime)
-    active = np.ones(N, dtype=bool)
-    for _ in range(max_n_iters):  # bisection (:822-834)
-        if not active.any():
-            break
-        mid = 0.5 * (lo + hi)
-        dH = H - A_(np.where(active, mid, lo))
-        up, down = active & (dH > log_a_max), active & (dH < log_a_min)
-        done = active & ~(dH > log_a_max) & ~(dH < log_a_min)
-        lo = np.where(up | done, mid, lo)
-        hi = np.where(down, mid, hi)
-        active = active & ~done
-    return lo if host else torch.as_tensor(lo, device=theta.device)
+    N, D = theta.shape
+    ctx = get_context(_device_of(theta))
+    z = phasepoint(h, theta, _like(theta, (N, D)) * 0 if _is_host(theta) else torch.zeros_like(theta))
+    md, keep = h.metric._desc(D, N, theta)
+    rc, keep2 = rng._c()
+    eps = _like(theta, (N,))
+    r = _like(theta, (N, D)) if return_momentum else None
+    _sync_torch(theta)
+    zc = z._c(False)
+    ctx.check(ctx.lib.ahmc_find_good_stepsize_f64(ctx.h, h.target.handle(ctx), C.byref(md), D, N, C.byref(zc), C.byref(rc),
+                                                  float(initial_step_size), int(max_n_iters), _ptr(eps), _ptr(r),
+                                                  L.FLAG_HOST_BUFFERS if _is_host(theta) else 0))
+    return (eps, r) if return_momentum else eps
 
 
 def sample_transitions(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: PhasePoint, n_transitions: int,
@@ -923,11 +924,17 @@ def sample_transitions(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: Phas
     out = _empty_pp(z.theta, with_lk_gradient=False)
     md, keep = h.metric._desc(D, N, z.theta)
     lf = tau.integrator
+    if type(lf) is not Leapfrog:
+        raise L.AhmcError(L.ERR_UNSUPPORTED, "multi-transition launches run plain Leapfrog (a JitteredLeapfrog draws a new step "
+                                              "size per transition on the host, a TemperedLeapfrog is not fused): loop over transition()")
+    tc = tau.termination_criterion
+    nuts = isinstance(tc, _DYNAMIC)
+    if not nuts and tau.sampler is not EndPointTS:
+        raise L.AhmcError(L.ERR_UNSUPPORTED, "multi-transition static launches implement EndPointTS (Metropolis end point); a static "
+                                              "MultinomialTS trajectory needs one shared direction draw per transition: loop over transition()")
     e, ep, keep2 = _eps_args(step_size(lf), z.theta, N)
     rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0, _refresh_alpha(kappa))
     rng.offset += n_transitions
-    tc = tau.termination_criterion
-    nuts = isinstance(tc, _DYNAMIC)
     st, sc = _stats_buffers(z.theta, N, nuts, T=n_transitions)
     draws = _like(z.theta, (n_transitions, N, D)) if keep_draws else None
     fl = flags | (L.FLAG_HOST_BUFFERS if host else 0)

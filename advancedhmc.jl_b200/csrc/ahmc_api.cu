@@ -475,6 +475,7 @@ int ahmc_synchronize(ahmc_ctx* ctx) {
     return AHMC_OK;
 }
 
+void* ahmc_stream(const ahmc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int64_t ahmc_launch_count(const ahmc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 const char* ahmc_last_transport(const ahmc_ctx* ctx) { return ctx ? ctx->transport.c_str() : "none"; }
 
@@ -1615,6 +1616,48 @@ int ahmc_adapt_cov_f64(ahmc_ctx* ctx, int32_t D, int64_t N, const double* theta,
     if ((rc = st.out(out, (size_t)D * D, &d_out))) return rc;
     int nl = 0;
     CU(launch_adapt_cov(D, N, d_theta, ld, d_mean, d_out, ctx->stream, &nl));
+    ctx->launches += nl;
+    return finish_call(ctx, st, flags);
+}
+
+int ahmc_find_good_stepsize_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                                const ahmc_phasepoint* z, const ahmc_rng* rng, double initial_step_size, int32_t max_n_iters,
+                                double* eps_out, double* r_out, uint32_t flags) {
+    if (!ctx || !model || !metric || !rng || !eps_out) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric/rng/eps_out");
+    int rc = check_common(ctx, model, metric, D, N);
+    if (rc) return rc;
+    if (!z || (N > 0 && (!z->theta || !z->lp_value || !z->lp_gradient)))
+        return fail(ctx, AHMC_ERR_INVALID, "z.theta / lp_value / lp_gradient is NULL (call ahmc_phasepoint_f64 first)");
+    if (N > 0 && z->ld < D) return fail(ctx, AHMC_ERR_INVALID, "z.ld < D");
+    if (!(initial_step_size > 0.0) || max_n_iters < 0) return fail(ctx, AHMC_ERR_INVALID, "need initial_step_size > 0, max_n_iters >= 0");
+    if (model->kind == AHMC_MODEL_CALLBACK)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "find_good_stepsize in one launch needs the gradient inside the kernel (built-in targets)");
+    if (N == 0) return AHMC_OK;
+    DeviceGuard g(ctx->device);
+    Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
+    const size_t cin = (size_t)z->ld * N;
+    reserve_metric(st, metric, D, N);
+    st.reserve(cin * 8); st.reserve(cin * 8); st.reserve(cin * 8); st.reserve((size_t)D * N * 8);
+    st.reserve((size_t)N * 8); st.reserve((size_t)N * 8);
+    if ((rc = st.prepare())) return rc;
+    FindEpsArgs a{};
+    a.model = model_dev(model);
+    if ((rc = stage_metric(st, metric, D, N, &a.metric))) return rc;
+    a.D = D;
+    a.N = N;
+    a.ld = z->ld;
+    if ((rc = st.in((const double*)z->theta, cin, &a.th))) return rc;
+    if ((rc = st.in((const double*)z->lp_gradient, cin, &a.g))) return rc;
+    if ((rc = st.in((const double*)z->lp_value, (size_t)N, &a.lp))) return rc;
+    if ((rc = st.in(rng->normal_tape, (size_t)D * N, &a.normal_tape))) return rc;
+    a.seed = rng->seed;
+    a.offset = rng->offset;
+    a.eps0 = initial_step_size;
+    a.max_iters = max_n_iters;
+    if ((rc = st.out(eps_out, (size_t)N, &a.eps_out))) return rc;
+    if ((rc = st.out(r_out, cin, &a.r_out))) return rc;
+    int nl = 0;
+    CU(launch_find_eps(a, ctx->stream, &nl));
     ctx->launches += nl;
     return finish_call(ctx, st, flags);
 }

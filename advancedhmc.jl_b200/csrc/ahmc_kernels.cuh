@@ -46,6 +46,22 @@ struct MomentumArgs {
     long long ld;
 };
 
+// find_good_stepsize for every chain in ONE launch (trajectory.jl:753-837)
+struct FindEpsArgs {
+    ModelDev model;
+    MetricDev metric;
+    int D;
+    long long N;
+    const double *th, *g, *lp;  // positions and the cached (lp, -grad) of phasepoint
+    long long ld;
+    uint64_t seed, offset;
+    const double* normal_tape;  // D x N standard normals or nullptr (Philox)
+    double eps0;
+    int max_iters;
+    double* eps_out;            // N
+    double* r_out;              // nullable, D x N (ld): the momentum each search used
+};
+
 struct StatsDev {
     int32_t* n_steps;
     uint8_t* is_accept;
@@ -244,6 +260,7 @@ cudaError_t launch_leapfrog(const LeapfrogArgs& a, cudaStream_t stream, int* n_l
 cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t stream, int* n_launches);
+cudaError_t launch_find_eps(const FindEpsArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_nuts(const NutsArgs& a, cudaStream_t stream, int* n_launches);
 long long nuts_scratch_doubles_per_chain(int D, int max_depth, bool adaptive);
 cudaError_t launch_trajectory(const TrajArgs& a, cudaStream_t stream, int* n_launches);

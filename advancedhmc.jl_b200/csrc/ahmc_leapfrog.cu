@@ -244,6 +244,75 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC
 }
 
 // ---------------------------------------------------------------------------------------------
+// find_good_stepsize (trajectory.jl:768-837), one independent search per chain, the WHOLE search in one launch:
+// momentum draw, H, the direction probe, the crossing loop (doubling / halving until the one-step acceptance ratio
+// crosses 1/2) and the bisection (until it lies in (1/4, 3/4]).  Every probe A(h, z, eps) (:753-757) is one exact
+// leapfrog step from the chain's start point held in registers.  Loops are warp-uniform (groups that finished keep
+// stepping with their final eps and ignore the result), so shuffles stay convergent when several chains share a warp.
+// Mirrors the reference's control flow literally, including its quirk of probing with eps (not eps') in the crossing loop.
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int METRIC, int G, int E>
+__global__ void __launch_bounds__(kBlockThreads) find_eps_kernel(const FindEpsArgs a) {
+    extern __shared__ double smem[];
+    const int l = threadIdx.x % G;
+    const int grp_in_block = threadIdx.x / G;
+    const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + grp_in_block;
+    const bool valid = chain0 < a.N;
+    const long long chain = valid ? chain0 : a.N - 1;
+    const int D = a.D;
+    double* xs = smem + (size_t)grp_in_block * D;
+    ModelOps<MODEL, G, E> mo;
+    MetricOps<METRIC, G, E> me;
+    mo.load(a.model, l, D);
+    me.load(a.metric, chain, l, D);
+    ChainState<E> z0;
+    vload_nc<G, E>(z0.th, a.th + a.ld * chain, l, D);
+    vload_nc<G, E>(z0.g, a.g + a.ld * chain, l, D);
+    if (a.normal_tape) vload_nc<G, E>(z0.r, a.normal_tape + (long long)D * chain, l, D);
+    else philox_normals<G, E>(a.seed, a.offset, chain, l, D, z0.r);
+    me.rand_momentum(z0.r, l);
+    if (a.r_out && valid) vstore<G, E>(a.r_out + a.ld * chain, z0.r, l, D);
+    double dr[E];
+    const double lk0 = map_nonfinite(kinetic<METRIC, G, E>(me, z0.r, dr, xs, l));
+    const double H = -(map_nonfinite(a.lp[chain]) + lk0);  // energy(z) (hamiltonian.jl:149,194)
+    auto probe = [&](double eps) -> double {                // H' of A(h, z, eps) (trajectory.jl:753-757)
+        ChainState<E> s = z0;
+        leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, eps, dr, xs, l);
+        return -(s.lp + s.lk);
+    };
+    const double log_a_min = 2.0 * -0.6931471805599453, log_a_cross = -0.6931471805599453, log_a_max = log(0.75);
+    double eps = a.eps0, eps_p = a.eps0;
+    double dH = H - probe(eps);
+    const bool too_high = dH > log_a_cross;
+    bool active = true;
+    for (int it = 0; it < a.max_iters; ++it) {  // crossing step (:796-810)
+        if (!__any_sync(FULL, active)) break;
+        if (active) eps_p = too_high ? 2.0 * eps : 0.5 * eps;
+        dH = H - probe(eps);
+        if (active) {
+            if (too_high != (dH > log_a_cross)) active = false;
+            else eps = eps_p;
+        }
+    }
+    double lo = fmin(eps, eps_p), hi = fmax(eps, eps_p);  // minmax (:818)
+    active = true;
+    for (int it = 0; it < a.max_iters; ++it) {  // bisection (:822-834)
+        if (!__any_sync(FULL, active)) break;
+        const double mid = 0.5 * (lo + hi);
+        dH = H - probe(active ? mid : lo);
+        if (active) {
+            if (dH > log_a_max) lo = mid;
+            else if (dH < log_a_min) hi = mid;
+            else {
+                lo = mid;
+                active = false;
+            }
+        }
+    }
+    if (valid && l == 0) a.eps_out[chain] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------
 // phasepoint(h, theta, r)  (hamiltonian.jl:115-119)
 // ---------------------------------------------------------------------------------------------
 template <int MODEL, int METRIC, int G, int E>
@@ -482,6 +551,18 @@ static cudaError_t launch_lf_t(const LeapfrogArgs& a, cudaStream_t st) {
     return launch_lf_c<MODEL, METRIC, G, E, false>(a, st);
 }
 template <int MODEL, int METRIC, int G, int E>
+static cudaError_t launch_fe_t(const FindEpsArgs& a, cudaStream_t st) {
+    const int chains_per_block = kBlockThreads / G;
+    const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
+    size_t sm = smem_bytes(MODEL, METRIC, a.D, G);
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(find_eps_kernel<MODEL, METRIC, G, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+    }
+    find_eps_kernel<MODEL, METRIC, G, E><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+    return cudaGetLastError();
+}
+template <int MODEL, int METRIC, int G, int E>
 static cudaError_t launch_pp_t(const PhasepointArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;
     const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
@@ -561,6 +642,10 @@ static cudaError_t lf_layout(const LeapfrogArgs& a, cudaStream_t st, int G, int 
     AHMC_DISPATCH_LAYOUT(launch_lf_t, MODEL, METRIC);
 }
 template <int MODEL, int METRIC>
+static cudaError_t fe_layout(const FindEpsArgs& a, cudaStream_t st, int G, int E) {
+    AHMC_DISPATCH_LAYOUT(launch_fe_t, MODEL, METRIC);
+}
+template <int MODEL, int METRIC>
 static cudaError_t pp_layout(const PhasepointArgs& a, cudaStream_t st, int G, int E) {
     AHMC_DISPATCH_LAYOUT(launch_pp_t, MODEL, METRIC);
 }
@@ -609,6 +694,13 @@ cudaError_t launch_leapfrog(const LeapfrogArgs& a, cudaStream_t st, int* n_launc
     if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
     if (n_launches) *n_launches += 1;
     AHMC_DISPATCH_MM(lf_layout, a.model.kind, a.metric.kind);
+}
+
+cudaError_t launch_find_eps(const FindEpsArgs& a, cudaStream_t st, int* n_launches) {
+    int G, E;
+    if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
+    if (n_launches) *n_launches += 1;
+    AHMC_DISPATCH_MM(fe_layout, a.model.kind, a.metric.kind);
 }
 
 cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t st, int* n_launches) {

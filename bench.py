@@ -443,6 +443,67 @@ def run_ours(args):
             if rcmb == 0:
                 dfma = {"tflops": tf.value, "ms": msb.value, "what": "148*8 blocks x 256 threads x 8 independent DFMA chains (libahmc_microbench.so)"}
 
+    # ---- the path's one exchange, inside the driver-run line: pooled warm-up on the C4 shape (funnel D=100,
+    # 4096 chains per GPU, NUTS).  Per iteration, on ONE stream and with no host synchronisation: NUTS transition (K3) ->
+    # K5 record -> ncclAllGather of (2+2D) doubles per rank -> merge + dual averaging + WelfordVar + window logic in one
+    # kernel that writes eps / M^-1 where the next transition reads them (ahmc_adapt_exchange_f64).  All ranks take part.
+    exchange = None
+    if not args.no_extras:
+        from ahmc_b200 import adaptation as adp
+
+        with torch.cuda.stream(stream):
+            comm = adp.Comm.from_torch_distributed(local) if world > 1 else None
+            Df, n_it = 100, 40
+            hf = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(Df)), A.Funnel(Df))
+            gf = torch.Generator(device=dev).manual_seed(100 + rank)
+            thf = 0.5 * torch.randn((N_CHAINS, Df), generator=gf, dtype=torch.float64, device=dev)
+            pad = adp.PooledDeviceAdaptor(local, Df, N_CHAINS, n_adapts=n_it + 10, eps0=0.1, init_buffer=10, term_buffer=5, window_size=8)
+            hdv = A.Hamiltonian(A.DiagEuclideanMetric(pad.Minv), hf.target)
+            kdv = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(pad.eps), A.GeneralisedNoUTurn()))
+            prf = A.PhiloxRNG(21 + rank)
+            zf = A.phasepoint(hdv, thf, torch.zeros_like(thf))
+            for _ in range(5):  # warm-up (also the first NCCL call)
+                trf = A.transition(prf, hdv, kdv, zf, flags=A.FLAG_ASYNC)
+                zf = trf.z
+                pad.exchange(zf.theta, trf.stat["acceptance_rate"], comm)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nsteps_dev = torch.zeros((), dtype=torch.int64, device=dev)
+            e0.record(stream)
+            for _ in range(n_it):
+                trf = A.transition(prf, hdv, kdv, zf, flags=A.FLAG_ASYNC)
+                zf = trf.z
+                pad.exchange(zf.theta, trf.stat["acceptance_rate"], comm)
+                nsteps_dev += trf.stat["n_steps"].sum()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms_iter = e0.elapsed_time(e1) / n_it
+            e0.record(stream)
+            for _ in range(200):  # the exchange alone, back to back on fixed inputs
+                pad.exchange(zf.theta, trf.stat["acceptance_rate"], comm)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            us_x = e0.elapsed_time(e1) / 200 * 1e3
+            tx = torch.tensor([ms_iter, us_x], dtype=torch.float64, device=dev)
+            ns_all = nsteps_dev.clone()
+            if world > 1:
+                dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ns_all)
+            ms_iter_max, us_x_max = tx.tolist()
+            stt = pad.state()
+            exchange = {"workload": "C4 shape: Neal's funnel D=100, 4096 chains per GPU, NUTS(max_depth 10), pooled StanHMCAdaptor on the device, "
+                                    f"{n_it} warm-up iterations after 5 untimed",
+                        "ranks": world, "record_bytes_per_rank": (2 + 2 * Df) * 8,
+                        "warmup_iteration_ms": ms_iter_max, "exchange_us": us_x_max, "exchange_share": us_x_max * 1e-3 / ms_iter_max,
+                        "rate_steps_dims_per_s": float(ns_all.item()) * Df / (ms_iter_max * n_it) * 1e3,
+                        "host_syncs_per_iteration": 0, "eps_after": stt["eps"],
+                        "what": "exchange = K5 record + ncclAllGather + merge/adaptor kernel (ahmc_adapt_exchange_f64), max over ranks"}
+            pad.destroy()
+            if comm is not None:
+                comm.destroy()
+
     # ---- e2e: the public call with HOST (pinned) buffers, copies inside the timed region.  Contract of
     # src/integrator.jl:216-265: host arrays in (theta, r -- the cached gradient of a built-in target is recomputed on the
     # device, so it is not uploaded), a fresh phase point out (theta', r', -grad', lp', lk').  The page-locked buffers are
@@ -532,6 +593,8 @@ def run_ours(args):
         line["roofline_hbm_honest"] = honest
     if k2:
         line["hmc_transition"] = k2
+    if exchange:
+        line["adapt_exchange"] = exchange
     if general:
         line.update(general)
     if k4:

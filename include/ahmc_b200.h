@@ -134,6 +134,9 @@ int ahmc_create(ahmc_ctx** out, int32_t device, void* cuda_stream /* cudaStream_
 int ahmc_destroy(ahmc_ctx* ctx);
 const char* ahmc_last_error(const ahmc_ctx* ctx);
 int ahmc_synchronize(ahmc_ctx* ctx);
+/* the cudaStream_t every call of this context enqueues on (the one given to ahmc_create, or the context's own).  A host
+ * that passes AHMC_FLAG_ASYNC must order its own work -- and the lifetime of the buffers it hands over -- on this stream. */
+void* ahmc_stream(const ahmc_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches evidence) */
 int64_t ahmc_launch_count(const ahmc_ctx* ctx);
 /* how the last AHMC_FLAG_HOST_BUFFERS call of ahmc_leapfrog_f64 moved its buffers, e.g. "up=direct down=direct chunks=1
@@ -245,6 +248,14 @@ int ahmc_nuts_adapt_sample_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahm
                                int32_t max_depth, double delta_max, int32_t n_transitions, const ahmc_adapt_cfg* cfg,
                                const ahmc_rng* rng, const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out,
                                double* draws, const ahmc_stats* stats, uint32_t flags);
+
+/* `find_good_stepsize(rng, h, theta)` (src/trajectory.jl:768-837) for N chains at once, each running its own search, in
+ * ONE launch: momentum draw (rng->normal_tape or Philox), the direction probe, the crossing loop and the bisection, every
+ * probe `A(h, z, eps)` (:753-757) one leapfrog step.  z: theta + the cached lp_value / lp_gradient (ahmc_phasepoint_f64);
+ * eps_out[N]; r_out (nullable, D x N with z->ld) receives the momenta used.  No host round trip. */
+int ahmc_find_good_stepsize_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
+                                const ahmc_phasepoint* z, const ahmc_rng* rng, double initial_step_size, int32_t max_n_iters,
+                                double* eps_out, double* r_out, uint32_t flags);
 
 /* ---- the one exchange: pooled adaptation across ranks, on the device ------------------ */
 /* Communicator over the GPUs that share one adaptation (one rank per GPU).  NCCL is bound at run time (dlopen of

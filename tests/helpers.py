@@ -9,21 +9,40 @@ MODEL_KINDS = {"std_normal": 0, "diag_gauss": 1, "dense_gauss": 2, "funnel": 3}
 METRIC_KINDS = {"unit": 0, "diag": 1, "dense": 2}
 
 
+def _with_reference_cases(cases, ref_file):
+    """append the cases of a reference-generated file (tests/golden/gen_from_reference.jl run against the real
+    AdvancedHMC.jl) when it has been committed; their names get the prefix "ref:" """
+    path = os.path.join(HERE, "golden", ref_file)
+    if os.path.exists(path):
+        with open(path) as f:
+            for c in json.load(f)["cases"]:
+                c = dict(c)
+                c["name"] = "ref:" + c["name"]
+                cases.append(c)
+    return cases
+
+
+def reference_fixtures_present():
+    return all(os.path.exists(os.path.join(HERE, "golden", f)) for f in ("leapfrog_ref.json", "hmc_ref.json", "nuts_ref.json"))
+
+
 def golden_cases():
     with open(os.path.join(HERE, "golden", "leapfrog_mp50.json")) as f:
-        return json.load(f)
+        d = json.load(f)
+    d["cases"] = _with_reference_cases(d["cases"], "leapfrog_ref.json")
+    return d
 
 
 def nuts_golden_cases():
     """tests/golden/nuts_mp50.json: NUTS transitions from the recursive 50-digit restatement (gen_nuts_mp.py)."""
     with open(os.path.join(HERE, "golden", "nuts_mp50.json")) as f:
-        return json.load(f)["cases"]
+        return _with_reference_cases(json.load(f)["cases"], "nuts_ref.json")
 
 
 def hmc_golden_cases():
     """tests/golden/hmc_mp50.json: static HMC transitions (refresh, EndPointTS / MultinomialTS) from gen_hmc_mp.py."""
     with open(os.path.join(HERE, "golden", "hmc_mp50.json")) as f:
-        return json.load(f)["cases"]
+        return _with_reference_cases(json.load(f)["cases"], "hmc_ref.json")
 
 
 def case_arrays(case):
@@ -58,6 +77,25 @@ def rel_err_elem(a, b, floor=1e-6):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     if a.size == 0:
         return 0.0
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def rel_err_elem_scaled(a, b, floor_frac=1e-3):
+    """ELEMENT-WISE relative error, max_i |a_i - b_i| / max(|b_i|, floor_frac * max|b|): every coordinate must carry
+    its own correct digits; only coordinates below floor_frac of the largest one (values passing through zero) are
+    measured against that floor instead of against themselves.  The parity criterion of the state comparisons
+    (DESIGN.md section 4); `rel_err` (max-norm relative) is kept beside it."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    fin = np.isfinite(b)
+    if not fin.all():  # non-finite reference entries must match exactly; the rest is compared numerically
+        if not np.array_equal(a[~fin], b[~fin], equal_nan=True):
+            return float("inf")
+        a, b = a[fin], b[fin]
+        if a.size == 0:
+            return 0.0
+    floor = max(floor_frac * float(np.max(np.abs(b))), 1e-300)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
 
 

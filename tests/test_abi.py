@@ -155,10 +155,12 @@ def test_julia_shim_ccall_arity_matches_the_header():
 
     hdr = open(os.path.join(ROOT, "include", "ahmc_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    protos = {m.group(1): len(_split_top(m.group(2))) for m in re.finditer(r"\b(ahmc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)}
+    protos = {m.group(1): (0 if m.group(2).strip() == "void" else len(_split_top(m.group(2))))
+              for m in re.finditer(r"\b(ahmc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)}
     jl = open(os.path.join(ROOT, "julia", "AdvancedHMCB200Ext.jl")).read()
     seen = 0
-    for m in re.finditer(r"ccall\(\(:(ahmc_[a-z0-9_]+),\s*libahmc\),\s*(\w+),\s*\(", jl):
+    bound = set()
+    for m in re.finditer(r"ccall\(\(:(ahmc_[a-z0-9_]+),\s*libahmc\),\s*([\w{}]+),\s*\(", jl):
         name = m.group(1)
         assert name in protos, name
         # the type tuple starts at m.end() - 1
@@ -180,8 +182,12 @@ def test_julia_shim_ccall_arity_matches_the_header():
         values = [v for v in _split_top(jl[j + 1:k - 1].lstrip(", \n")) if v]
         assert len(types) == protos[name], (name, len(types), protos[name])
         assert len(values) == protos[name], (name, len(values), protos[name])
+        bound.add(name)
         seen += 1
-    assert seen >= 8
+    # EVERY entry point the header declares is bound by the shim
+    assert bound == set(protos), sorted(set(protos) - bound)
+    # device pointers enter the C structs as plain Ptr (pointer(::CuArray) is a CuPtr): through dptr()
+    assert "reinterpret(Ptr{T}, pointer(x))" in jl and "pointer(z.θ), pointer(z.r), pointer(z.ℓπ.value)" not in jl
 
 
 def test_julia_shim_struct_field_counts_match_the_c_structs():
@@ -190,7 +196,8 @@ def test_julia_shim_struct_field_counts_match_the_c_structs():
     from ahmc_b200 import _lib as L
 
     jl = open(os.path.join(ROOT, "julia", "AdvancedHMCB200Ext.jl")).read()
-    want = {"CMetric": L.Metric, "CPhasePoint": L.PhasePoint, "CStats": L.Stats, "CRng": L.Rng, "CAdaptCfg": L.AdaptCfg}
+    want = {"CMetric": L.Metric, "CPhasePoint": L.PhasePoint, "CStats": L.Stats, "CRng": L.Rng, "CAdaptCfg": L.AdaptCfg,
+            "CPooledCfg": L.PooledCfg}
     for name, cls in want.items():
         m = re.search(r"struct " + name + r"\n(.*?)\nend", jl, flags=re.S)
         assert m, name

@@ -69,18 +69,36 @@ def test_c3_nuts_diag_metric_d128():
 
 
 def test_c4_funnel_nuts_stan_adaptor_pooled():
-    """NUTS + StanHMCAdaptor on Neal's funnel (D=100 in BASELINE; D=20 here), pooled windows: v ~ N(0, 3^2)."""
-    D, N = 20, 1024
+    """C4 at BASELINE's own dimension: NUTS + StanHMCAdaptor on Neal's funnel D=100, pooled windows, the adaptor resident on
+    the device (ahmc_adapt_exchange_f64: no host synchronisation during warm-up): v ~ N(0, 3^2)."""
+    D, N = 100, 1024
     h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.Funnel(D))
     kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
-    adaptor = ad.StanHMCAdaptor(ad.WelfordVar(D), ad.NesterovDualAveraging(0.8, 0.1))
     th0 = torch.as_tensor(np.random.default_rng(1).normal(size=(N, D)) * 0.1, device=DEV)
-    res = ad.sample(A.PhiloxRNG(4), h, kern, th0, 260, adaptor, 200, keep_draws=True, drop_warmup=True)
-    v = torch.stack(res.draws)[:, :, 0].reshape(-1).cpu().numpy()
-    # the funnel's neck is famously under-sampled by NUTS; the bulk of v ~ N(0, 9) must be there
-    assert abs(np.median(v)) < 1.0 and 1.5 < v.std() < 3.6
+    res = ad.sample_pooled_device(A.PhiloxRNG(4), h, kern, th0, 200, 200, eps0=0.1)
     assert res.Minv is not None and res.Minv.shape == (D,) and res.Minv[0] > 1.0  # adapted: var(v) >> var at init
     assert 0.01 < res.eps < 2.0
+    # draws with the adapted eps / M^-1 (persistent launch, kept)
+    hd = A.Hamiltonian(A.DiagEuclideanMetric(res.Minv), A.Funnel(D))
+    kd = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(res.eps), A.GeneralisedNoUTurn()))
+    z = A.phasepoint(hd, res.theta, torch.zeros_like(res.theta))
+    zl, draws, st = A.sample_transitions(A.PhiloxRNG(9), hd, kd, z, 60)
+    v = draws[:, :, 0].reshape(-1).cpu().numpy()
+    # the funnel's neck is famously under-sampled by NUTS; the bulk of v ~ N(0, 9) must be there
+    assert abs(np.median(v)) < 1.0 and 1.5 < v.std() < 3.6
+
+
+def test_c4_funnel_host_pooled_adaptor_small():
+    """the host-side pooled loop (`sample`, adaptation.py) on a small funnel -- the path the gloo tests exercise"""
+    D, N = 20, 512
+    h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.Funnel(D))
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
+    adaptor = ad.StanHMCAdaptor(ad.WelfordVar(D), ad.NesterovDualAveraging(0.8, 0.1), init_buffer=20, term_buffer=20, window_size=10)
+    th0 = torch.as_tensor(np.random.default_rng(1).normal(size=(N, D)) * 0.1, device=DEV)
+    res = ad.sample(A.PhiloxRNG(4), h, kern, th0, 160, adaptor, 120, keep_draws=True, drop_warmup=True)
+    v = torch.stack(res.draws)[:, :, 0].reshape(-1).cpu().numpy()
+    assert abs(np.median(v)) < 1.2 and 1.2 < v.std() < 3.8
+    assert res.Minv is not None and res.Minv[0] > 1.0 and 0.01 < res.eps < 2.0
 
 
 def test_c5_nuts_dense_metric_d256():

@@ -1,6 +1,8 @@
 """GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against
 (i) the committed 50-digit known answers and (ii) the CPU oracle on the same seeded inputs.
 Tolerance: 1e-10 relative fp64 (BASELINE.json north_star), written out below as TOL."""
+import zlib
+
 import numpy as np
 import pytest
 import torch
@@ -8,7 +10,7 @@ import torch
 import ahmc_b200 as A
 from oracle import oracle_c as oc
 from tests.helpers import (METRIC_KINDS, MODEL_KINDS, case_arrays, golden_cases, hmc_golden_cases, nuts_golden_cases, rel_err,
-                           synth_diag_gauss)
+                           rel_err_elem_scaled, synth_diag_gauss)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -55,6 +57,8 @@ def assert_pp_close(z, ref, tol=TOL, fields=("theta", "r", "lp_gradient", "lp_va
     for f in fields:
         want = ref[f] if isinstance(ref, dict) else getattr(ref, f)
         assert rel_err(got[f], want) < tol, (f, rel_err(got[f], want))
+        # element-wise: every coordinate carries its own digits (floor: 1e-3 of the largest coordinate)
+        assert rel_err_elem_scaled(got[f], want) < 10 * tol, (f, "element-wise", rel_err_elem_scaled(got[f], want))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -103,7 +107,7 @@ METRICS = ["unit", "diag", "diag_perchain", "dense"]
 @pytest.mark.parametrize("metric", METRICS)
 @pytest.mark.parametrize("D,n_steps", [(6, 9), (40, -7), (130, 5)])
 def test_model_metric_matrix_vs_oracle(model, metric, D, n_steps):
-    rng = np.random.default_rng(abs(hash((model, metric, D))) % 2**31)
+    rng = np.random.default_rng(zlib.crc32(f"{model}/{metric}/{D}".encode()))  # a fixed seed per case (str hashes vary per process)
     N = 11
     p0 = p1 = None
     if model == "diag_gauss":
@@ -429,9 +433,11 @@ def _nuts_case(model, metric, D, N, eps, seed, max_depth=10, scale=1.0, sampler=
     ("std_normal", "unit", 10, 0.3, 1.0), ("diag_gauss", "diag", 128, 0.15, 1.0), ("diag_gauss", "unit", 5, 0.4, 1.0),
     ("funnel", "diag", 20, 0.12, 0.6), ("dense_gauss", "dense", 12, 0.25, 1.0), ("diag_gauss", "diag", 200, 0.1, 1.0),
     ("funnel", "unit", 3, 0.9, 2.0),
+    ("funnel", "diag", 100, 0.1, 0.5),        # BASELINE C4's own shape
+    ("dense_gauss", "dense", 256, 0.2, 1.0),  # BASELINE C5's own shape: E = 8 layout, level slots cache M^-1 r_first
 ])
 def test_nuts_transition_vs_oracle_with_tapes(model, metric, D, eps, scale):
-    N = 203
+    N = 203 if D < 256 else 48
     tr, zo, so = _nuts_case(model, metric, D, N, eps, seed=D * 7 + 1, scale=scale)
     st = tr.stat
     assert (F(st["tree_depth"]) == so.tree_depth).all(), (F(st["tree_depth"])[:20], so.tree_depth[:20])
@@ -511,7 +517,8 @@ def test_static_transitions_match_mp50_restatement(case):
     else:
         tau = A.Trajectory(A.MultinomialTS, A.Leapfrog(case["eps"]), A.FixedNSteps(case["n_steps"]))
         tr = A.transition(A.TapeRNG(normal=normals, exp=var, n_fwd=case["n_fwd"]), h, A.HMCKernel(tau), z0)
-        assert (tr.stat["tree_depth"].cpu().numpy() == np.array(case["expect"]["index"])).all()
+        if "index" in case["expect"]:  # (the reference does not report the drawn index: absent in reference-generated cases)
+            assert (tr.stat["tree_depth"].cpu().numpy() == np.array(case["expect"]["index"])).all()
     e, st, z = case["expect"], tr.stat, tr.z
     assert (st["is_accept"].cpu().numpy().astype(bool) == np.array(e["is_accept"])).all()
     for got, want in ((z.theta, e["theta"]), (z.r, e["r"]), (z.lp.gradient, e["lp_gradient"])):
@@ -656,10 +663,13 @@ def test_step_without_cached_gradient_equals_step_with_it(model, metric, D, N):
     zg = A.step(A.Leapfrog(0.07), h, z0, 9)
     zn = A.step(A.Leapfrog(0.07), h, A.PhasePoint(z0.theta, z0.r, A.DualValue(None, None), A.DualValue(None, None)), 9)
     for a, b in [(zg.theta, zn.theta), (zg.r, zn.r), (zg.lp.gradient, zn.lp.gradient), (zg.lp.value, zn.lp.value), (zg.lk.value, zn.lk.value)]:
-        assert torch.equal(a, b)
+        if "dense" in (model, metric):  # with the gradient: tiled DMMA kernel; without: warp-per-chain kernel (other summation order)
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-13
+        else:
+            assert torch.equal(a, b)
     thh, rh = np.ascontiguousarray(np.asarray(th).T), np.ascontiguousarray(np.asarray(r).T)
     zh = A.step(A.Leapfrog(0.07), h, A.PhasePoint(thh, rh, A.DualValue(None, None), A.DualValue(None, None)), 9)
-    assert np.array_equal(zh.theta, zg.theta.cpu().numpy()) and np.array_equal(zh.lp.gradient, zg.lp.gradient.cpu().numpy())
+    assert np.array_equal(zh.theta, zn.theta.cpu().numpy()) and np.array_equal(zh.lp.gradient, zn.lp.gradient.cpu().numpy())
     with pytest.raises(A.InvalidArgument):  # zero steps hands z back unchanged and needs the gradient to do so
         A.step(A.Leapfrog(0.07), h, A.PhasePoint(z0.theta, z0.r, A.DualValue(None, None), A.DualValue(None, None)), 0)
 
@@ -1098,3 +1108,20 @@ def test_device_pooled_warmup_runs_without_host_syncs_and_adapts_like_the_host_l
     assert np.allclose(rd.Minv, rh.Minv, rtol=1e-9)
     assert np.allclose(rd.Minv, s * s, rtol=0.35)  # and it learned the target's scales
     assert rd.leapfrog_steps == rh.leapfrog_steps
+
+
+def test_device_pooled_adaptor_over_nccl_two_ranks():
+    """the exchange over a real NCCL communicator created through the C ABI (ahmc_comm_create): 2 ranks, ragged chain counts,
+    equal to the host adaptors fed with the rank-ordered merge and bit-identical across ranks (scripts/nccl_exchange_check.py);
+    needs two GPUs (skipped on a one-GPU box; the driver's multi-GPU bench runs the same code path in `adapt_exchange`)."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pr = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                         "--master-port", "29517", os.path.join(root, "scripts", "nccl_exchange_check.py")],
+                        capture_output=True, text=True, cwd=root, timeout=600)
+    assert pr.returncode == 0 and "nccl exchange ok" in pr.stdout, pr.stdout[-1500:] + pr.stderr[-3000:]

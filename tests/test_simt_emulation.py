@@ -384,7 +384,8 @@ def test_multinomial_static_kernel_source_under_emulation_matches_mp50_fixtures(
                   acc=P(acc), index=P(idx))
         assert emu_mn.emu_multinomial(C.byref(q)) == 0, case["name"]
         e = case["expect"]
-        assert (idx == np.array(e["index"])).all(), case["name"]
+        if "index" in e:
+            assert (idx == np.array(e["index"])).all(), case["name"]
         assert rel_err(o["th"], np.array(e["theta"])) < 1e-10 and rel_err(o["r"], np.array(e["r"])) < 1e-10
         assert np.allclose(acc, e["acceptance_rate"], rtol=1e-10)
         assert np.allclose(lp_o, e["lp_value"], rtol=1e-10, atol=1e-10) and np.allclose(lk_o, e["lk_value"], rtol=1e-10, atol=1e-10)
