@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("AHMC_B200_LIB", os.path.join(HERE, "libahmc_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_CALLBACK = 0, -1, -2, -3, -4, -5
 METRIC_UNIT, METRIC_DIAG, METRIC_DENSE = 0, 1, 2
-MODEL_STD_NORMAL, MODEL_DIAG_GAUSS, MODEL_DENSE_GAUSS, MODEL_FUNNEL, MODEL_CALLBACK = 0, 1, 2, 3, 4
+MODEL_STD_NORMAL, MODEL_DIAG_GAUSS, MODEL_DENSE_GAUSS, MODEL_FUNNEL, MODEL_CALLBACK, MODEL_USER = 0, 1, 2, 3, 4, 5
 FLAG_HOST_BUFFERS, FLAG_COMPAT_BREAK_ALL, FLAG_ASYNC, FLAG_EXACT_CHECKS, FLAG_NO_REFRESH = 1, 2, 4, 8, 16
 FLAG_NUTS_SLICE_TS, FLAG_NUTS_CLASSIC, FLAG_NUTS_STRICT = 32, 64, 128
 STATUS_NONFINITE = 1
@@ -69,6 +69,8 @@ PROTOTYPES = {
     "ahmc_last_transport": (C.c_char_p, [_vp]),
     "ahmc_model_create": (C.c_int, [_vp, C.c_int32, C.c_int32, _dp, _dp, C.c_double, C.POINTER(_vp)]),
     "ahmc_model_create_callback": (C.c_int, [_vp, C.c_int32, LOGP_GRAD_FN, _vp, C.POINTER(_vp)]),
+    "ahmc_model_create_user": (C.c_int, [_vp, C.c_int32, C.c_char_p, _dp, C.c_int32, C.c_double, C.POINTER(_vp)]),
+    "ahmc_user_source_check": (C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int64]),
     "ahmc_model_destroy": (C.c_int, [_vp, _vp]),
     "ahmc_phasepoint_f64": (C.c_int, [_vp, _vp, C.POINTER(Metric), C.c_int32, C.c_int64, C.POINTER(PhasePoint),
                                       C.c_uint32]),

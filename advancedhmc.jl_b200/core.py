@@ -191,6 +191,38 @@ class Funnel(_Target):
         super().__init__(L.MODEL_FUNNEL, D, c0=c0)
 
 
+class UserTarget(_Target):
+    """A user-supplied log pi / grad log pi as CUDA source, compiled at run time INTO the fused kernels
+    (ahmc_model_create_user; the `h.dlp/dtheta` closure of src/hamiltonian.jl:45-48 as a device function).  `source` defines
+    `__device__ double ahmc_user_logp_grad(const double* theta, double* grad, int D, const double* params)` (PLUS gradient)
+    or, with `#define AHMC_USER_COORDWISE`, `__device__ double ahmc_user_coord(int d, double theta_d, const double* params,
+    double* grad_d)`.  Works with phasepoint, step, static HMC transitions, NUTS and find_good_stepsize_batched."""
+
+    def __init__(self, D: int, source: str, params=None, c0: float = 0.0):
+        self.kind, self.D, self.c0 = L.MODEL_USER, int(D), float(c0)
+        self.source = source
+        self.params = None if params is None else np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
+        self._handles = {}
+
+    def handle(self, ctx: "Context"):
+        h = self._handles.get(ctx.device)
+        if h is None:
+            h = C.c_void_p()
+            p = self.params
+            ctx.check(ctx.lib.ahmc_model_create_user(ctx.h, self.D, self.source.encode(), None if p is None else p.ctypes.data_as(L._dp),
+                                                     0 if p is None else p.size, self.c0, C.byref(h)))
+            self._handles[ctx.device] = h
+        return h
+
+    @staticmethod
+    def check_source(source: str, D: int, kernel: int = 1, metric_kind: int = 1):
+        """compile-only check (no GPU needed): raises InvalidArgument with the NVRTC log if `source` does not compile"""
+        log = C.create_string_buffer(8192)
+        rc = L.load().ahmc_user_source_check(source.encode(), kernel, metric_kind, D, log, 8192)
+        if rc != L.OK:
+            raise L.InvalidArgument(rc, log.value.decode())
+
+
 class _RawCuda:
     """zero-copy view of a raw device pointer for torch (via __cuda_array_interface__)."""
 

@@ -70,13 +70,14 @@ struct ahmc_model {
     double c0 = 0.0;
     ahmc_logp_grad_fn fn = nullptr;
     void* user = nullptr;
+    UserModule* rtc = nullptr;  // AHMC_MODEL_USER: run-time compiled kernels
 };
 
 namespace {
 
 int fail(ahmc_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {
-        char buf[512];
+        char buf[4096];
         va_list ap;
         va_start(ap, fmt);
         vsnprintf(buf, sizeof buf, fmt, ap);
@@ -89,9 +90,12 @@ int fail(ahmc_ctx* ctx, int code, const char* fmt, ...) {
 #define CU(call)                                                                                       \
     do {                                                                                               \
         cudaError_t e__ = (call);                                                                      \
-        if (e__ != cudaSuccess)                                                                        \
-            return fail(ctx, AHMC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
-                        __LINE__);                                                                     \
+        if (e__ != cudaSuccess) {                                                                      \
+            std::string ue__ = user_thread_error();                                                    \
+            user_thread_error_clear();                                                                 \
+            return fail(ctx, AHMC_ERR_CUDA, "%s failed: %s (%s:%d)%s%s", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__, ue__.empty() ? "" : " -- ", ue__.c_str());                           \
+        }                                                                                              \
     } while (0)
 
 struct DeviceGuard {
@@ -234,7 +238,7 @@ size_t metric_minv_count(const ahmc_metric* m, int32_t D, int64_t N) {
     return 0;
 }
 
-ModelDev model_dev(const ahmc_model* m) { return ModelDev{m->kind, m->D, m->d_p0, m->d_p1, m->c0}; }
+ModelDev model_dev(const ahmc_model* m) { return ModelDev{m->kind, m->D, m->d_p0, m->d_p1, m->c0, m->rtc}; }
 
 // stage the metric descriptor (device or host pointers) into a MetricDev
 int stage_metric(Stager& st, const ahmc_metric* m, int32_t D, int64_t N, MetricDev* out) {
@@ -546,6 +550,44 @@ int ahmc_model_create_callback(ahmc_ctx* ctx, int32_t D, ahmc_logp_grad_fn fn, v
     return AHMC_OK;
 }
 
+int ahmc_model_create_user(ahmc_ctx* ctx, int32_t D, const char* cuda_src, const double* params, int32_t n_params, double c0,
+                           ahmc_model** out) {
+    if (!ctx || !cuda_src || !out) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/source/out");
+    if (D < 1 || n_params < 0 || (n_params > 0 && !params)) return fail(ctx, AHMC_ERR_INVALID, "need D >= 1 and params for n_params > 0");
+    if (!strstr(cuda_src, "ahmc_user_logp_grad") && !strstr(cuda_src, "ahmc_user_coord"))
+        return fail(ctx, AHMC_ERR_INVALID, "the source must define ahmc_user_logp_grad(theta, grad, D, params) or, with "
+                                           "#define AHMC_USER_COORDWISE, ahmc_user_coord(d, theta_d, params, grad_d)");
+    DeviceGuard g(ctx->device);
+    char why[256];
+    UserModule* um = user_module_create(cuda_src, why, sizeof why);
+    if (!um) return fail(ctx, AHMC_ERR_UNSUPPORTED, "run-time compilation is unavailable: %s", why);
+    ahmc_model* m = new (std::nothrow) ahmc_model;
+    if (!m) {
+        user_module_destroy(um);
+        return fail(ctx, AHMC_ERR_NOMEM, "out of host memory");
+    }
+    m->kind = AHMC_MODEL_USER;
+    m->D = D;
+    m->c0 = c0;
+    m->rtc = um;
+    if (n_params > 0) {
+        if (cudaMalloc((void**)&m->d_p0, (size_t)n_params * 8) != cudaSuccess) {
+            user_module_destroy(um);
+            delete m;
+            return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc for the user parameters failed");
+        }
+        CU(cudaMemcpy(m->d_p0, params, (size_t)n_params * 8, cudaMemcpyHostToDevice));
+    }
+    *out = m;
+    return AHMC_OK;
+}
+
+int ahmc_user_source_check(const char* cuda_src, int32_t kernel, int32_t metric_kind, int32_t D, char* log, int64_t log_len) {
+    if (!cuda_src || kernel < 0 || kernel > 4 || metric_kind < 0 || metric_kind > 2 || D < 1) return AHMC_ERR_INVALID;
+    int rc = user_source_check(cuda_src, kernel, metric_kind, D, log, log_len > 0 ? (size_t)log_len : 0);
+    return rc == 0 ? AHMC_OK : (rc == -3 ? AHMC_ERR_UNSUPPORTED : AHMC_ERR_INVALID);
+}
+
 int ahmc_model_destroy(ahmc_ctx* ctx, ahmc_model* m) {
     if (!m) return AHMC_OK;
     if (ctx) {
@@ -553,6 +595,10 @@ int ahmc_model_destroy(ahmc_ctx* ctx, ahmc_model* m) {
         cudaFree(m->d_p0);
         cudaFree(m->d_p1);
         cudaFree(m->d_p1_pad);
+        if (m->rtc) {
+            cudaStreamSynchronize(ctx->stream);
+            user_module_destroy(m->rtc);
+        }
     }
     delete m;
     return AHMC_OK;
@@ -1241,7 +1287,7 @@ static int hmc_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* m
         LeapfrogArgs t = a;
         t.th_in = a.th_out; t.r_in = a.r_out; t.g_in = a.g_out; t.ld_in = a.ld_out;
         t.status = nullptr; t.steps_done = nullptr; t.only_mask = nullptr; t.min_break = nullptr;
-        const bool gauss = model->kind != AHMC_MODEL_FUNNEL && model->kind != AHMC_MODEL_CALLBACK;
+        const bool gauss = model->kind != AHMC_MODEL_FUNNEL && model->kind != AHMC_MODEL_CALLBACK && model->kind != AHMC_MODEL_USER;
         const bool metric_ok = a.metric.kind != AHMC_METRIC_DIAG || a.metric.chain_stride == 0;
         int Dp_, RB_, CB_;
         if (gauss && metric_ok && !(flags & AHMC_FLAG_EXACT_CHECKS) && dense_tile_shape(D, &Dp_, &RB_, &CB_)) {
@@ -1320,7 +1366,9 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     if ((flags & AHMC_FLAG_NUTS_CLASSIC) && (flags & AHMC_FLAG_NUTS_STRICT))
         return fail(ctx, AHMC_ERR_INVALID, "AHMC_FLAG_NUTS_CLASSIC and AHMC_FLAG_NUTS_STRICT are mutually exclusive");
     if (model->kind == AHMC_MODEL_CALLBACK)
-        return fail(ctx, AHMC_ERR_UNSUPPORTED, "NUTS needs a device-resident target: callback (split-step) models are supported by ahmc_leapfrog_f64 / ahmc_hmc_transition_f64 / ahmc_phasepoint_f64 only");
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "NUTS needs a device-resident target: callback (split-step) models are supported by ahmc_leapfrog_f64 / ahmc_hmc_transition_f64 / ahmc_phasepoint_f64 only; express the target as CUDA source (ahmc_model_create_user) to run NUTS on it");
+    if (model->kind == AHMC_MODEL_USER && (cfg || (flags & (AHMC_FLAG_NUTS_SLICE_TS | AHMC_FLAG_NUTS_CLASSIC | AHMC_FLAG_NUTS_STRICT))))
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "run-time compiled targets: MultinomialTS + GeneralisedNoUTurn without in-launch adaptation");
     if (metric->kind == AHMC_METRIC_DENSE && !metric->cholU && !(flags & AHMC_FLAG_NO_REFRESH))
         return fail(ctx, AHMC_ERR_INVALID, "Dense metric needs cholU for the momentum refresh (metric.jl:311-320)");
     if (z_out->lk_gradient)
@@ -1423,8 +1471,8 @@ int ahmc_leapfrog_trajectory_f64(ahmc_ctx* ctx, const ahmc_model* model, const a
     if (n_abs == 0 || N == 0) return AHMC_OK;  // res = Vector{P}(undef, 0)
     if ((rc = check_pp(ctx, traj, D, "traj", true, N))) return rc;
     if (step_stride < traj->ld * N) return fail(ctx, AHMC_ERR_INVALID, "step_stride must be >= ld*N");
-    if (model->kind == AHMC_MODEL_CALLBACK)
-        return fail(ctx, AHMC_ERR_UNSUPPORTED, "full_trajectory needs a device-resident target");
+    if (model->kind == AHMC_MODEL_CALLBACK || model->kind == AHMC_MODEL_USER)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "full_trajectory: built-in targets only (callback / run-time compiled targets: loop over ahmc_leapfrog_f64)");
     DeviceGuard g(ctx->device);
     Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);
     const size_t cin = (size_t)z_in->ld * N, ctraj = (size_t)step_stride * n_abs;
@@ -1467,8 +1515,8 @@ int ahmc_hmc_multinomial_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, 
     if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
     if (n_steps < 1 || n_steps_fwd < 0 || n_steps_fwd > n_steps)
         return fail(ctx, AHMC_ERR_INVALID, "need n_steps >= 1 and 0 <= n_steps_fwd <= n_steps (rand(0:n_steps), trajectory.jl:373)");
-    if (model->kind == AHMC_MODEL_CALLBACK)
-        return fail(ctx, AHMC_ERR_UNSUPPORTED, "MultinomialTS static transitions need a device-resident target");
+    if (model->kind == AHMC_MODEL_CALLBACK || model->kind == AHMC_MODEL_USER)
+        return fail(ctx, AHMC_ERR_UNSUPPORTED, "MultinomialTS static transitions: built-in targets only");
     if (metric->kind == AHMC_METRIC_DENSE && !metric->cholU && !(flags & AHMC_FLAG_NO_REFRESH))
         return fail(ctx, AHMC_ERR_INVALID, "Dense metric needs cholU for the momentum refresh (metric.jl:311-320)");
     if (z_out->lk_gradient)

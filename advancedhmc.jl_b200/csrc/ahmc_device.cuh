@@ -13,11 +13,34 @@
 //   PhasePoint -Inf mapping, isfinite src/hamiltonian.jl:95-104, 141-142
 //   one leapfrog step                 src/integrator.jl:233-247  (+ temper :198-209)
 #pragma once
+#if defined(__CUDACC_RTC__)
+// run-time compilation of the user-model kernels (ahmc_user.cu): no host headers are available to NVRTC
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#define CUDART_INF __longlong_as_double(0x7ff0000000000000LL)
+#define CUDART_NAN __longlong_as_double(0xfff8000000000000LL)
+#else
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#endif
 
 #include "../../include/ahmc_b200.h"
+
+#if defined(AHMC_NVRTC_USER_MODEL)
+// The user's target (AHMC_MODEL_USER, ahmc_model_create_user): CUDA source handed over at run time defines ONE of
+//   __device__ double ahmc_user_logp_grad(const double* theta, double* grad, int D, const double* params);
+//       log pi(theta) of one chain; writes the PLUS gradient into grad[0..D).  theta / grad are D-vectors in shared memory;
+//       one lane of the chain's group runs it.
+//   __device__ double ahmc_user_coord(int d, double theta_d, const double* params, double* grad_d);      (and #define AHMC_USER_COORDWISE)
+//       for targets that are a sum over coordinates: the term of coordinate d and its derivative; every lane evaluates
+//       its own coordinates and the terms are summed by warp shuffles (as fast as the built-in diagonal targets).
+__device__ double ahmc_user_logp_grad(const double* theta, double* grad, int D, const double* params);
+__device__ double ahmc_user_coord(int d, double theta_d, const double* params, double* grad_d);
+#endif
 
 namespace ahmc {
 
@@ -26,10 +49,16 @@ constexpr unsigned FULL = 0xffffffffu;
 struct ModelDev {
     int kind;
     int D;
-    const double* p0;  // DIAG_GAUSS: mean; DENSE_GAUSS: mean
+    const double* p0;  // DIAG_GAUSS: mean; DENSE_GAUSS: mean; USER: the user's parameter array
     const double* p1;  // DIAG_GAUSS: w = 1/s^2 ; DENSE_GAUSS: precision D x D (column-major)
     double c0;
+    const void* user;  // USER: host-side handle of the run-time compiled kernels (never dereferenced on the device)
 };
+
+// doubles of per-group shared-memory slab a kernel family needs: dense operators stage one D-vector, a user target a
+// second one for the gradient
+template <int MODEL>
+__host__ __device__ constexpr int slab_vectors() { return MODEL == AHMC_MODEL_USER ? 2 : 1; }
 
 struct MetricDev {
     int kind;
@@ -295,6 +324,8 @@ struct ModelOps {
             vload<G, E>(w, md.p1, l, D);
         } else if (MODEL == AHMC_MODEL_DENSE_GAUSS) {
             vload<G, E>(m, md.p0, l, D);
+        } else if (MODEL == AHMC_MODEL_USER) {
+            P = md.p0;  // the user's parameters
         }
     }
 
@@ -323,6 +354,40 @@ struct ModelOps {
 #pragma unroll
             for (int e = 0; e < E; ++e) part = fma(diff[e], g[e], part);
             return fma(-0.5, Grp<G>::sum(part), c0);
+        } else if (MODEL == AHMC_MODEL_USER) {
+#if defined(AHMC_NVRTC_USER_MODEL)
+#if defined(AHMC_USER_COORDWISE)
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = l + G * e;
+                double gd = 0.0, term = 0.0;
+                if (d < D) term = ahmc_user_coord(d, th[e], P, &gd);
+                g[e] = -gd;  // PhasePoint caches MINUS the gradient (hamiltonian.jl:45-48)
+                part += term;
+            }
+            return Grp<G>::sum(part) + c0;
+#else
+            double* gs = xs + D;  // second slab vector of this group
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = l + G * e;
+                if (d < D) xs[d] = th[e];
+            }
+            __syncwarp();
+            double lp = 0.0;
+            if (l == 0) lp = ahmc_user_logp_grad(xs, gs, D, P);
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = l + G * e;
+                g[e] = (d < D) ? -gs[d] : 0.0;
+            }
+            return Grp<G>::bcast(lp, 0) + c0;
+#endif
+#else
+            return 0.0;  // the user-target kernels exist only in run-time compiled modules
+#endif
         } else {  // FUNNEL
             double v = Grp<G>::bcast(th[0], 0);
             double ev = exp(-v);

@@ -248,13 +248,16 @@ bool dense_tile_shape(int D, int* Dp, int* RB, int* CB);
 // padded matrices (K4) are stored with the shared-memory stage's leading dimension: a 16-column chunk is one bulk copy
 __host__ __device__ constexpr int dense_lda(int Dp) { return Dp + 4; }
 __host__ __device__ constexpr size_t dense_mat_doubles(int Dp) { return (size_t)Dp * (size_t)dense_lda(Dp); }
+#ifndef __CUDACC_RTC__
 cudaError_t launch_dense_traj(const DenseTrajHost& h, cudaStream_t stream, int* n_launches);
 cudaError_t launch_pad_norm(const double* A, int D, int Dp, double* Ap, double* norm, cudaStream_t st);
 cudaError_t launch_vec_norm(const double* v, int D, double* norm, cudaStream_t st);
+#endif
 
 // choose (G, E) for a dimension: returns false if D is out of the register-resident range
 bool pick_layout(int D, int* G, int* E);
 
+#ifndef __CUDACC_RTC__  // host-side declarations (cudaError_t / cudaStream_t are unknown to NVRTC)
 // launchers (defined in the .cu files); all enqueue on `stream` and return the cudaError_t of the launch
 cudaError_t launch_leapfrog(const LeapfrogArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t stream, int* n_launches);
@@ -293,12 +296,27 @@ int nccl_comm_init(void** comm, int nranks, const void* id128, int rank);
 int nccl_comm_destroy(void* comm);
 int nccl_allgather_f64(const double* send, double* recv, size_t count, void* comm, cudaStream_t st);
 
+// user targets compiled at run time (ahmc_user.cu): NVRTC + the driver API, both bound with dlopen
+enum UserKernel { UK_PHASEPOINT = 0, UK_LEAPFROG = 1, UK_HMC = 2, UK_NUTS = 3, UK_FIND_EPS = 4 };
+struct UserModule;  // per-model cache of compiled kernels
+UserModule* user_module_create(const char* cuda_src, char* err, size_t err_len);
+void user_module_destroy(UserModule* m);
+// compile (first use) and launch kernel `which` of the user module for (metric, G, E); args = the kernel's argument block
+cudaError_t user_launch(UserModule* m, int which, int metric_kind, int G, int E, const void* args, unsigned blocks, size_t smem,
+                        cudaStream_t st);
+const char* user_last_error(const UserModule* m);
+int user_source_check(const char* cuda_src, int which, int metric_kind, int D, char* log, size_t log_len);
+const char* user_thread_error();  // message of the last failed user_launch on this thread ("" if none)
+void user_thread_error_clear();
+
+#endif  // __CUDACC_RTC__
+
 constexpr int kBlockThreads = 128;
 
 // dynamic shared memory needed by the dense paths: one D-double slab per group
 inline size_t smem_bytes(int model_kind, int metric_kind, int D, int G) {
-    bool dense = (model_kind == AHMC_MODEL_DENSE_GAUSS) || (metric_kind == AHMC_METRIC_DENSE);
-    return dense ? (size_t)(kBlockThreads / G) * (size_t)D * sizeof(double) : 0;
+    bool dense = (model_kind == AHMC_MODEL_DENSE_GAUSS) || (metric_kind == AHMC_METRIC_DENSE) || (model_kind == AHMC_MODEL_USER);
+    return dense ? (size_t)(kBlockThreads / G) * (size_t)(model_kind == AHMC_MODEL_USER ? 2 : 1) * (size_t)D * sizeof(double) : 0;
 }
 
 }  // namespace ahmc

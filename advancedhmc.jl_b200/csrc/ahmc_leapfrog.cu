@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC
     const long long chain0 = (long long)blockIdx.x * (kBlockThreads / G) + grp_in_block;
     const long long chain = chain0 < a.N ? chain0 : a.N - 1;  // tail groups shadow the last chain, never store
     const bool valid = chain0 < a.N && (!a.only_mask || a.only_mask[chain] != 0);
-    double* xs = smem + (size_t)grp_in_block * a.D;
+    double* xs = smem + (size_t)grp_in_block * slab_vectors<MODEL>() * a.D;
     double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
     eps = a.fwd ? eps : -eps;  // integrator.jl:226
     StepIO<G, E, CONTIG> io{a, chain, l};
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC
     const bool valid = chain0 < a.N;
     const long long chain = valid ? chain0 : a.N - 1;
     const int D = a.D;
-    double* xs = smem + (size_t)grp_in_block * D;
+    double* xs = smem + (size_t)grp_in_block * slab_vectors<MODEL>() * D;
     const double eps = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
 
     MetricOps<METRIC, G, E> me;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kBlockThreads) find_eps_kernel(const FindEpsAr
     const bool valid = chain0 < a.N;
     const long long chain = valid ? chain0 : a.N - 1;
     const int D = a.D;
-    double* xs = smem + (size_t)grp_in_block * D;
+    double* xs = smem + (size_t)grp_in_block * slab_vectors<MODEL>() * D;
     ModelOps<MODEL, G, E> mo;
     MetricOps<METRIC, G, E> me;
     mo.load(a.model, l, D);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kBlockThreads) phasepoint_kernel(const Phasepo
     const bool valid = chain0 < a.N;
     const long long chain = valid ? chain0 : a.N - 1;
     const int D = a.D;
-    double* xs = smem + (size_t)grp_in_block * D;
+    double* xs = smem + (size_t)grp_in_block * slab_vectors<MODEL>() * D;
     ModelOps<MODEL, G, E> mo;
     MetricOps<METRIC, G, E> me;
     mo.load(a.model, l, D);
@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(kBlockThreads) mh_select_kernel(const MhArgs a
 // ---------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------
+#ifndef __CUDACC_RTC__  // host launch code (the kernels above are also compiled at run time for user targets, ahmc_user.cu)
 // can the fast path of this launch use the lane-contiguous vector layout?  (full tile D == 32*E, rows and coefficient
 // vectors aligned to the vector width)
 template <int E>
@@ -693,6 +694,11 @@ cudaError_t launch_leapfrog(const LeapfrogArgs& a, cudaStream_t st, int* n_launc
     int G, E;
     if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
     if (n_launches) *n_launches += 1;
+    if (a.model.kind == AHMC_MODEL_USER) {  // run-time compiled kernels of a user target (ahmc_user.cu)
+        const int cpb = kBlockThreads / G;
+        return user_launch((UserModule*)a.model.user, UK_LEAPFROG, a.metric.kind, G, E, &a, (unsigned)((a.N + cpb - 1) / cpb),
+                           smem_bytes(AHMC_MODEL_USER, a.metric.kind, a.D, G), st);
+    }
     AHMC_DISPATCH_MM(lf_layout, a.model.kind, a.metric.kind);
 }
 
@@ -700,6 +706,11 @@ cudaError_t launch_find_eps(const FindEpsArgs& a, cudaStream_t st, int* n_launch
     int G, E;
     if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
     if (n_launches) *n_launches += 1;
+    if (a.model.kind == AHMC_MODEL_USER) {  // run-time compiled kernels of a user target (ahmc_user.cu)
+        const int cpb = kBlockThreads / G;
+        return user_launch((UserModule*)a.model.user, UK_FIND_EPS, a.metric.kind, G, E, &a, (unsigned)((a.N + cpb - 1) / cpb),
+                           smem_bytes(AHMC_MODEL_USER, a.metric.kind, a.D, G), st);
+    }
     AHMC_DISPATCH_MM(fe_layout, a.model.kind, a.metric.kind);
 }
 
@@ -707,6 +718,11 @@ cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t st, int* n_l
     int G, E;
     if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
     if (n_launches) *n_launches += 1;
+    if (a.model.kind == AHMC_MODEL_USER) {  // run-time compiled kernels of a user target (ahmc_user.cu)
+        const int cpb = kBlockThreads / G;
+        return user_launch((UserModule*)a.model.user, UK_PHASEPOINT, a.metric.kind, G, E, &a, (unsigned)((a.N + cpb - 1) / cpb),
+                           smem_bytes(AHMC_MODEL_USER, a.metric.kind, a.D, G), st);
+    }
     AHMC_DISPATCH_MM(pp_layout, a.model.kind, a.metric.kind);
 }
 
@@ -714,6 +730,11 @@ cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t st, int* n_launches) {
     int G, E;
     if (!pick_layout(a.lf.D, &G, &E)) return cudaErrorInvalidValue;
     if (n_launches) *n_launches += 1;
+    if (a.lf.model.kind == AHMC_MODEL_USER) {  // run-time compiled kernels of a user target (ahmc_user.cu)
+        const int cpb = kBlockThreads / G;
+        return user_launch((UserModule*)a.lf.model.user, UK_HMC, a.lf.metric.kind, G, E, &a, (unsigned)((a.lf.N + cpb - 1) / cpb),
+                           smem_bytes(AHMC_MODEL_USER, a.lf.metric.kind, a.lf.D, G), st);
+    }
     AHMC_DISPATCH_MM(hmc_layout, a.lf.model.kind, a.lf.metric.kind);
 }
 
@@ -759,5 +780,7 @@ cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t st, int* n_
 }
 
 #endif  // AHMC_SIMT_EMULATION
+
+#endif  // __CUDACC_RTC__
 
 }  // namespace ahmc

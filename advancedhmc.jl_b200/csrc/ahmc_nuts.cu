@@ -13,6 +13,14 @@ cudaError_t launch_nuts_adaptive(const NutsArgs& a, cudaStream_t st);  // ahmc_n
 
 cudaError_t launch_nuts(const NutsArgs& a, cudaStream_t st, int* n_launches) {
     if (n_launches) *n_launches += 1;
+    if (a.model.kind == AHMC_MODEL_USER) {  // run-time compiled kernel of a user target (default family only, ahmc_user.cu)
+        int G, E;
+        if (!pick_layout(a.D, &G, &E) || a.ad.enabled || a.sampler != 0 || a.criterion != 0) return cudaErrorInvalidValue;
+        const int cpb = kBlockThreads / G;
+        const int maxd = a.max_depth > 0 ? a.max_depth : 1;
+        const size_t sm = smem_bytes(AHMC_MODEL_USER, a.metric.kind, a.D, G) + (size_t)cpb * maxd * kLevelScalars * sizeof(double);
+        return user_launch((UserModule*)a.model.user, UK_NUTS, a.metric.kind, G, E, &a, (unsigned)((a.N + cpb - 1) / cpb), sm, st);
+    }
     if (a.ad.enabled) return launch_nuts_adaptive(a, st);
     if (a.sampler != 0 || a.criterion != 0) return launch_nuts_variants(a, st);
     return nuts_dispatch<false, false, false>(a, st);

@@ -86,10 +86,11 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     const bool valid = chain0 < a.N;
     const long long chain = valid ? chain0 : a.N - 1;
     const int D = FULL ? G * E : a.D;
-    const bool dense = (MODEL == AHMC_MODEL_DENSE_GAUSS) || (METRIC == AHMC_METRIC_DENSE);
-    double* xs = smem + (size_t)grp_in_block * D;  // dense slab (unused otherwise)
+    const bool dense = (MODEL == AHMC_MODEL_DENSE_GAUSS) || (METRIC == AHMC_METRIC_DENSE) || (MODEL == AHMC_MODEL_USER);
+    constexpr int kSlab = slab_vectors<MODEL>();
+    double* xs = smem + (size_t)grp_in_block * kSlab * D;  // dense / user-target slab (unused otherwise)
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
-    double* lv = smem + (dense ? (size_t)kGroups * D : 0) +
+    double* lv = smem + (dense ? (size_t)kGroups * kSlab * D : 0) +
                  (size_t)grp_in_block * maxd * kLevelScalars;
     double* LW = lv;
     double* SA = lv + maxd;
@@ -754,7 +755,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
 
 }
 
-#ifndef AHMC_SIMT_EMULATION  // host launch code (not compiled by the CPU SIMT emulation harness, tests/simt_emu/)
+#if !defined(AHMC_SIMT_EMULATION) && !defined(__CUDACC_RTC__)  // host launch code (skipped by the CPU SIMT emulation harness and by NVRTC)
 template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
 static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;

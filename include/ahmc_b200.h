@@ -26,7 +26,9 @@
 #ifndef AHMC_B200_H
 #define AHMC_B200_H
 
+#ifndef __CUDACC_RTC__ /* (the header is also seen by NVRTC when user-target kernels are compiled at run time) */
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -50,6 +52,7 @@ extern "C" {
 #define AHMC_MODEL_DENSE_GAUSS 2 /* p0 = mean[D], p1 = precision[DxD] col-major; lp = c0 - (th-mu)'P(th-mu)/2 */
 #define AHMC_MODEL_FUNNEL 3      /* Neal's funnel: v=th[0]; lp = c0 - v^2/18 - sum_{i>=1}(th_i^2 e^{-v} + v)/2 */
 #define AHMC_MODEL_CALLBACK 4    /* user-supplied gradient callback (split-step mode) */
+#define AHMC_MODEL_USER 5        /* user-supplied CUDA device function, compiled at run time INTO the fused kernels */
 
 /* flags */
 #define AHMC_FLAG_HOST_BUFFERS 0x1u    /* array arguments are host pointers (staged by the library) */
@@ -149,6 +152,23 @@ const char* ahmc_last_transport(const ahmc_ctx* ctx);
 int ahmc_model_create(ahmc_ctx* ctx, int32_t kind, int32_t D, const double* p0, const double* p1, double c0,
                       ahmc_model** out);
 int ahmc_model_create_callback(ahmc_ctx* ctx, int32_t D, ahmc_logp_grad_fn fn, void* user, ahmc_model** out);
+/* A user-supplied log pi / grad log pi FUSED into the kernels (the `h.dlp/dtheta` closure of src/hamiltonian.jl:45-48 as a CUDA
+ * device function): `cuda_src` is CUDA C++ source that defines ONE of
+ *     __device__ double ahmc_user_logp_grad(const double* theta, double* grad, int D, const double* params);
+ *         log pi of one chain; writes the PLUS gradient into grad[0..D) (theta / grad: D-vectors in shared memory)
+ *     #define AHMC_USER_COORDWISE
+ *     __device__ double ahmc_user_coord(int d, double theta_d, const double* params, double* grad_d);
+ *         for targets that are a sum over coordinates: term d and its derivative (every lane evaluates its own coordinates)
+ * It is compiled at run time (NVRTC, sm_100a) together with the library's own kernel sources on first use of each kernel, so
+ * phasepoint, the fused trajectory, the static HMC transition, NUTS (MultinomialTS + GeneralisedNoUTurn) and
+ * find_good_stepsize run on it exactly as on a built-in target: no host round trip per step.  params[n_params] (host) is
+ * copied to the device and handed to the function; lp = c0 + the function's value.  Compilation errors come back through
+ * ahmc_last_error of the first call that needs the kernel.  Needs libnvrtc + the driver library at run time (dlopen). */
+int ahmc_model_create_user(ahmc_ctx* ctx, int32_t D, const char* cuda_src, const double* params, int32_t n_params, double c0,
+                           ahmc_model** out);
+/* Compile-only check of a user target (no device, no context needed): kernel 0 phasepoint, 1 trajectory, 2 static HMC,
+ * 3 NUTS, 4 find_good_stepsize; the layout follows from D.  AHMC_OK, or AHMC_ERR_INVALID with the NVRTC log in `log`. */
+int ahmc_user_source_check(const char* cuda_src, int32_t kernel, int32_t metric_kind, int32_t D, char* log, int64_t log_len);
 int ahmc_model_destroy(ahmc_ctx* ctx, ahmc_model* model);
 
 /* ---- hot path -------------------------------------------------------------------------------- */

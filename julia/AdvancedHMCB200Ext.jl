@@ -167,6 +167,26 @@ function B200Target(f::Function, D::Integer)
     return B200Target(out[], D, (box, cfn))
 end
 
+"""
+User target as CUDA source compiled at run time INTO the fused kernels (ahmc_model_create_user): `src` defines
+`__device__ double ahmc_user_logp_grad(const double* theta, double* grad, int D, const double* params)` (or the
+coordinate-wise contract, see include/ahmc_b200.h).  Unlike a callback target it runs inside NUTS and costs no host round trip.
+"""
+function B200Target(src::String, D::Integer; params::Vector{Float64}=Float64[], c0=0.0)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve params check(ccall((:ahmc_model_create_user, libahmc), Cint,
+                                    (Ptr{Cvoid}, Int32, Cstring, Ptr{Float64}, Int32, Float64, Ref{Ptr{Cvoid}}),
+                                    context().h, D, src, isempty(params) ? C_NULL : pointer(params), length(params), c0, out))
+    return B200Target(out[], D, nothing)
+end
+"compile-only check of a user target (no GPU needed); returns the NVRTC log (empty = compiles)"
+function b200_user_source_check(src::String, D::Integer; kernel::Integer=1, metric_kind::Integer=1)
+    log = zeros(UInt8, 8192)
+    rc = GC.@preserve log ccall((:ahmc_user_source_check, libahmc), Cint, (Cstring, Int32, Int32, Int32, Ptr{UInt8}, Int64),
+                                src, kernel, metric_kind, D, pointer(log), length(log))
+    return rc == 0 ? "" : unsafe_string(pointer(log))
+end
+
 function destroy!(t::B200Target)
     check(ccall((:ahmc_model_destroy, libahmc), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), context().h, t.handle))
     t.handle = C_NULL

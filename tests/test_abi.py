@@ -203,3 +203,30 @@ def test_julia_shim_struct_field_counts_match_the_c_structs():
         assert m, name
         fields = [f for line in m.group(1).splitlines() for f in line.split("#")[0].split(";") if "::" in f]
         assert len(fields) == len(cls._fields_), (name, len(fields), len(cls._fields_))
+
+
+def test_user_target_sources_compile_under_nvrtc_without_a_gpu():
+    """ahmc_user_source_check: the library's embedded kernel sources + a user device function compile for sm_100a (NVRTC needs
+    no device), for every kernel a user target can run in and for both contracts; a broken source returns the NVRTC log."""
+    import ctypes as C
+
+    import ahmc_b200 as A
+
+    lib = A._lib.load()
+    general = ("__device__ double ahmc_user_logp_grad(const double* th, double* g, int D, const double* p) {\n"
+               "  double s = 0.0; for (int i = 0; i < D; ++i) { g[i] = -th[i] * p[0]; s += th[i] * th[i]; } return -0.5 * p[0] * s; }\n")
+    coord = ("#define AHMC_USER_COORDWISE\n__device__ double ahmc_user_coord(int d, double x, const double* p, double* gd) {\n"
+             "  *gd = -x * p[d]; return -0.5 * x * x * p[d]; }\n")
+    log = C.create_string_buffer(4096)
+    rc0 = lib.ahmc_user_source_check(general.encode(), 1, 1, 100, log, 4096)
+    if rc0 == A._lib.ERR_UNSUPPORTED:
+        pytest.skip("libnvrtc not available here: " + log.value.decode())
+    for src in (general, coord):
+        for kernel in range(5):
+            for metric, D in ((0, 10), (1, 128), (2, 40)):
+                assert lib.ahmc_user_source_check(src.encode(), kernel, metric, D, log, 4096) == 0, log.value.decode()
+    assert lib.ahmc_user_source_check(b"__device__ double ahmc_user_logp_grad(const double* t, double* g, int D, const double* p) { return q; }",
+                                      3, 1, 8, log, 4096) == A._lib.ERR_INVALID
+    assert b"q" in log.value and b"undefined" in log.value
+    with pytest.raises(A.InvalidArgument):
+        A.UserTarget.check_source("__device__ double ahmc_user_logp_grad(const double* t, double* g, int D, const double* p) { return q; }", 8)

@@ -1125,3 +1125,112 @@ def test_device_pooled_adaptor_over_nccl_two_ranks():
                          "--master-port", "29517", os.path.join(root, "scripts", "nccl_exchange_check.py")],
                         capture_output=True, text=True, cwd=root, timeout=600)
     assert pr.returncode == 0 and "nccl exchange ok" in pr.stdout, pr.stdout[-1500:] + pr.stderr[-3000:]
+
+
+# ------------------------------------------------------------------------------------------------ user target (NVRTC, fused)
+USER_FUNNEL = r'''
+__device__ double ahmc_user_logp_grad(const double* th, double* g, int D, const double* p) {
+    const double v = th[0], ev = exp(-v);
+    double S = 0.0;
+    for (int i = 1; i < D; ++i) { g[i] = -th[i] * ev; S += th[i] * th[i] * ev; }
+    g[0] = -v / 9.0 + (S - (D - 1)) * 0.5;
+    return -v * v / 18.0 - (S + (D - 1) * v) * 0.5;
+}
+'''
+USER_DIAG = r'''
+#define AHMC_USER_COORDWISE
+__device__ double ahmc_user_coord(int d, double x, const double* p, double* gd) {   // p = [mean_0, 1/s_0^2, mean_1, ...]
+    const double diff = x - p[2 * d], g = diff * p[2 * d + 1];
+    *gd = -g;
+    return -0.5 * diff * g;
+}
+'''
+
+
+@pytest.mark.parametrize("which,D,metric", [("funnel", 20, "diag"), ("funnel", 100, "unit"), ("diag", 128, "diag"), ("diag", 7, "dense")])
+def test_user_target_compiled_into_the_kernels_equals_the_builtin_target(which, D, metric):
+    """AHMC_MODEL_USER: the user's CUDA device function is compiled (NVRTC) into phasepoint / trajectory / static transition /
+    find_good_stepsize kernels; results equal the built-in target's (same arithmetic up to summation order: 1e-12), through
+    the exact per-step path, with and without a cached input gradient, on device and on host buffers."""
+    rng = np.random.default_rng(60 + D)
+    N = 77
+    Minv = None
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    elif metric == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+    if which == "funnel":
+        builtin, user = A.Funnel(D, 0.25), A.UserTarget(D, USER_FUNNEL, c0=0.25)
+        th = rng.normal(size=(D, N)) * 0.4
+    else:
+        m, s = rng.normal(size=D), np.exp(rng.uniform(-0.7, 0.7, D))
+        builtin = A.DiagGaussian(m, s, normalised=False)
+        builtin.c0 = 0.25
+        user = A.UserTarget(D, USER_DIAG, params=np.stack([m, 1.0 / s ** 2], axis=1), c0=0.25)
+        th = rng.normal(size=(D, N))
+    r = rng.normal(size=(D, N))
+    hb, hu = A.Hamiltonian(make_metric(metric, Minv, D), builtin), A.Hamiltonian(make_metric(metric, Minv, D), user)
+    zb, zu = A.phasepoint(hb, T(th), T(r)), A.phasepoint(hu, T(th), T(r))
+    tol = 1e-12
+    for a, b in [(zu.lp.value, zb.lp.value), (zu.lp.gradient, zb.lp.gradient), (zu.lk.value, zb.lk.value)]:
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < tol
+    z1b = A.step(A.Leapfrog(0.05), hb, zb, 11, flags=A.FLAG_EXACT_CHECKS)
+    z1u, info = A.step(A.Leapfrog(0.05), hu, zu, 11, return_info=True)
+    assert (F(info.steps_done) == 11).all()
+    for a, b in [(z1u.theta, z1b.theta), (z1u.r, z1b.r), (z1u.lp.gradient, z1b.lp.gradient), (z1u.lp.value, z1b.lp.value),
+                 (z1u.lk.value, z1b.lk.value)]:
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-11
+    z1n = A.step(A.Leapfrog(0.05), hu, A.PhasePoint(zu.theta, zu.r, A.DualValue(None, None), A.DualValue(None, None)), 11)
+    assert torch.equal(z1n.theta, z1u.theta) and torch.equal(z1n.lp.gradient, z1u.lp.gradient)
+    if metric != "dense":  # host buffers (the pipelined lane takes Unit / Diag metrics)
+        zh = A.step(A.Leapfrog(0.05), hu, A.PhasePoint(np.ascontiguousarray(th.T), np.ascontiguousarray(r.T), A.DualValue(None, None),
+                                                        A.DualValue(None, None)), 11)
+        assert np.array_equal(zh.theta, z1u.theta.cpu().numpy())
+    # static transition on identical tapes
+    nt, et = T(rng.normal(size=(D, N))), torch.as_tensor(rng.exponential(size=N), device=DEV)
+    kern = A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.1), A.FixedNSteps(7)))
+    tb = A.transition(A.TapeRNG(normal=nt, exp=et), hb, kern, zb, flags=A.FLAG_EXACT_CHECKS)
+    tu = A.transition(A.TapeRNG(normal=nt, exp=et), hu, kern, zu)
+    assert torch.equal(tu.stat["is_accept"], tb.stat["is_accept"]) and rel_err(tu.z.theta.cpu().numpy(), tb.z.theta.cpu().numpy()) < 1e-11
+    # find_good_stepsize in one launch
+    eb = A.find_good_stepsize_batched(A.TapeRNG(normal=nt), hb, T(th))
+    eu = A.find_good_stepsize_batched(A.TapeRNG(normal=nt), hu, T(th))
+    assert torch.equal(eb, eu)
+
+
+@pytest.mark.parametrize("D,eps,scale,metric", [(20, 0.12, 0.6, "diag"), (100, 0.1, 0.5, "diag"), (3, 0.9, 2.0, "unit")])
+def test_nuts_on_a_user_target_matches_the_recursive_oracle_on_tapes(D, eps, scale, metric):
+    """NUTS (K3) with the user's funnel compiled into the kernel: same trees, draws and statistics as the recursive oracle
+    running the built-in funnel, chain by chain, from shared random tapes."""
+    N, max_depth = 150, 10
+    rng = np.random.default_rng(D * 13 + 5)
+    Minv = np.exp(rng.uniform(-0.5, 0.5, D)) if metric == "diag" else None
+    th, nt = rng.normal(size=(D, N)) * scale, rng.normal(size=(D, N))
+    dirs = rng.integers(0, 2, size=(N, max_depth + 1)).astype(np.uint8)
+    exps = rng.exponential(size=(N, 1 << max_depth))
+    om, ome = oc.Model(oc.FUNNEL, D, None, None, 0.0), oc.Metric(METRIC_KINDS[metric], Minv)
+    zo, so, used = oc.nuts_transition(om, ome, eps, oc.phasepoint(om, ome, th, np.zeros((D, N))), nt, dirs, exps, max_depth=max_depth)
+    h = A.Hamiltonian(make_metric(metric, Minv, D), A.UserTarget(D, USER_FUNNEL))
+    z0 = A.phasepoint(h, T(th), T(np.zeros((D, N))))
+    tau = A.Trajectory(A.MultinomialTS, A.Leapfrog(eps), A.GeneralisedNoUTurn(max_depth, 1000.0))
+    tr = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(exps, device=DEV), dirs=torch.as_tensor(dirs, device=DEV)), h,
+                      A.HMCKernel(tau), z0)
+    st = tr.stat
+    assert (F(st["tree_depth"]) == so.tree_depth).all() and (F(st["n_steps"]) == so.n_steps).all()
+    assert (F(st["numerical_error"]) == so.numerical_error).all()
+    assert_pp_close(tr.z, zo)
+    assert rel_err(F(st["acceptance_rate"]), so.acceptance_rate) < 1e-9
+    # and a persistent multi-transition Philox run samples v ~ N(0, 9)-ish without errors
+    zl, draws, s2 = A.sample_transitions(A.PhiloxRNG(2), h, A.HMCKernel(tau), z0, 5)
+    assert torch.isfinite(zl.theta).all()
+
+
+def test_user_target_compile_errors_come_back_as_messages():
+    bad = "__device__ double ahmc_user_logp_grad(const double* th, double* g, int D, const double* p) { return nope; }"
+    h = A.Hamiltonian(A.UnitEuclideanMetric(4), A.UserTarget(4, bad))
+    with pytest.raises(A.AhmcError) as e:
+        A.phasepoint(h, torch.zeros((3, 4), dtype=torch.float64, device=DEV), torch.zeros((3, 4), dtype=torch.float64, device=DEV))
+    assert "nope" in str(e.value)
+    with pytest.raises(A.InvalidArgument):
+        A.UserTarget(4, "int x;").handle(A.get_context(0))
