@@ -31,7 +31,9 @@ def correlated_gaussian(D, seed):
 
 
 def run(name, world, rank, dev, scale, iters):
-    rng = np.random.Generator(np.random.PCG64(SEED + hash(name) % 1000 + rank))
+    import zlib
+
+    rng = np.random.Generator(np.random.PCG64(SEED + zlib.crc32(name.encode()) % 1000 + rank))
     t_adapt = 0
     if name == "c1":   # StaticTrajectory(Leapfrog(0.1), 32) + Unit, D=10 std-normal, 64 chains
         D, N = 10, 64
@@ -59,6 +61,13 @@ def run(name, world, rank, dev, scale, iters):
         adaptor = ad.StanHMCAdaptor(ad.WelfordVar(D), ad.NesterovDualAveraging(0.8, 0.1))
         n_samples = iters or 120
         n_adapts = int(n_samples * 0.8)
+    elif name == "c4d":  # C4, pooled StanHMCAdaptor resident on the DEVICE (ahmc_adapt_exchange_f64 over an ahmc_comm): no host syncs
+        D, N = 100, int(32768 * scale) // world
+        h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.Funnel(D))
+        kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
+        adaptor = "device"
+        n_samples = iters or 120
+        n_adapts = int(n_samples * 0.8)
     elif name == "c4v":  # C4 with the reference's vectorised (per-chain) adaptors: warm-up + sampling in ONE launch
         D, N = 100, int(32768 * scale) // world
         h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), A.Funnel(D))
@@ -74,15 +83,28 @@ def run(name, world, rank, dev, scale, iters):
         adaptor, n_adapts, n_samples = None, 0, iters or 5
     else:
         raise SystemExit(f"unknown config {name}")
-    theta0 = torch.as_tensor(rng.normal(size=(N, D)) * (0.1 if name == "c4" else 1.0), device=dev)
+    theta0 = torch.as_tensor(rng.normal(size=(N, D)) * (0.1 if name.startswith("c4") else 1.0), device=dev)
     prng = A.PhiloxRNG(SEED + 17 * rank)
     # warm-up launch (module load, workspace allocation)
     ad.sample(prng, h, kern, theta0, 1)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res = ad.sample(prng, h, kern, theta0, n_samples, adaptor, n_adapts, keep_draws=False)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    if adaptor == "device":
+        comm = ad.Comm.from_torch_distributed(dev.index or 0) if world > 1 else None
+        ad.sample_pooled_device(prng, h, kern, theta0, 3, 2, eps0=0.1, comm=comm)  # first NCCL call, buffers
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        res = ad.sample_pooled_device(prng, h, kern, theta0, n_samples, n_adapts, eps0=0.1, delta=0.8, comm=comm)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if comm is not None:
+            comm.destroy()
+    else:
+        t0 = time.perf_counter()
+        res = ad.sample(prng, h, kern, theta0, n_samples, adaptor, n_adapts, keep_draws=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
     tt = torch.tensor([dt, float(res.leapfrog_steps)], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
