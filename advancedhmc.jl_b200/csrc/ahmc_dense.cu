@@ -29,7 +29,7 @@ constexpr int kKC = 16;             // columns of A per pipeline stage
 //     instead of a CTA-wide __syncthreads per chunk;
 //   * three stages.  Shared memory: 68 KB per CTA at Dp = 128 (two CTAs per SM still fit), 232,272 of the 232,448 bytes a CTA
 //     may have at Dp = 512.
-constexpr int kStages = 3;
+constexpr int kStages = 3;  // 4 and 5 stages measured no faster (profiles/r02/k4_stages_ab.log): the wait is L2 latency per chunk, not depth
 constexpr int kBars = 2 * kStages;  // full[kStages] + empty[kStages]
 #ifdef AHMC_SIMT_EMULATION
 extern unsigned char* emu_dynamic_smem;  // the block's dynamic shared memory (blocks run one at a time)
