@@ -197,7 +197,7 @@ private:
     std::vector<Out> outs_;
 };
 
-int check_common(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N) {
+int check_common(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N, bool streaming_ok = false) {
     if (!ctx) return AHMC_ERR_INVALID;
     if (D < 1) return fail(ctx, AHMC_ERR_INVALID, "D must be >= 1 (got %d)", D);
     if (N < 0) return fail(ctx, AHMC_ERR_INVALID, "N must be >= 0 (got %lld)", (long long)N);
@@ -215,8 +215,14 @@ int check_common(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metr
                         (long long)metric->chain_stride, D);
     }
     int G, E;
-    if (!pick_layout(D, &G, &E))
-        return fail(ctx, AHMC_ERR_UNSUPPORTED, "D=%d is outside the register-resident range (1..512) of this build", D);
+    if (!pick_layout(D, &G, &E)) {
+        // D > 512: `step` and `phasepoint` stream the chain through registers tile by tile (ahmc_bigd.cu) for the separable
+        // targets and the funnel with Unit / Diag metrics; everything else is register-resident and stops at 512
+        if (streaming_ok && model && metric && bigd_supported(model->kind, metric->kind)) return AHMC_OK;
+        return fail(ctx, AHMC_ERR_UNSUPPORTED,
+                    "D=%d: this entry point / target / metric combination is register-resident (D <= 512); D > 512 is supported by "
+                    "ahmc_leapfrog_f64 and ahmc_phasepoint_f64 for std-normal, diagonal-Gaussian and funnel targets with Unit / Diag metrics", D);
+    }
     return AHMC_OK;
 }
 
@@ -608,7 +614,7 @@ int ahmc_model_destroy(ahmc_ctx* ctx, ahmc_model* m) {
 int ahmc_phasepoint_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
                         const ahmc_phasepoint* z, uint32_t flags) {
     if (!ctx || !model || !metric) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric");
-    int rc = check_common(ctx, model, metric, D, N);
+    int rc = check_common(ctx, model, metric, D, N, true);
     if (rc) return rc;
     if ((rc = check_pp(ctx, z, D, "z", true, N))) return rc;
     if (N == 0) return AHMC_OK;
@@ -984,7 +990,8 @@ int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric*
                       const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, uint32_t* status,
                       int32_t* steps_done, uint32_t flags) {
     if (!ctx || !model || !metric) return fail(ctx, AHMC_ERR_INVALID, "NULL ctx/model/metric");
-    int rc = check_common(ctx, model, metric, D, N);
+    int rc = check_common(ctx, model, metric, D, N, true);
+    if (!rc && D > 512 && temper_alpha > 0.0) rc = fail(ctx, AHMC_ERR_UNSUPPORTED, "TemperedLeapfrog at D > 512 is not built");
     if (rc) return rc;
     // z_in: only theta and r are required.  The cached energies are not read, and a NULL z_in->lp_gradient means "not
     // cached": built-in targets recompute dH/dtheta at the start point on the device (bit-identical to the value

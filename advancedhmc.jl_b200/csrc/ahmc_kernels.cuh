@@ -264,6 +264,10 @@ cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t stream, int*
 cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_find_eps(const FindEpsArgs& a, cudaStream_t stream, int* n_launches);
+// D > 512: streaming form of step / phasepoint (ahmc_bigd.cu)
+bool bigd_supported(int model_kind, int metric_kind);
+cudaError_t launch_leapfrog_big(const LeapfrogArgs& a, cudaStream_t st);
+cudaError_t launch_phasepoint_big(const PhasepointArgs& a, cudaStream_t st);
 cudaError_t launch_nuts(const NutsArgs& a, cudaStream_t stream, int* n_launches);
 long long nuts_scratch_doubles_per_chain(int D, int max_depth, bool adaptive);
 cudaError_t launch_trajectory(const TrajArgs& a, cudaStream_t stream, int* n_launches);

@@ -692,6 +692,10 @@ static cudaError_t mom_layout(const MomentumArgs& a, cudaStream_t st, int G, int
 
 cudaError_t launch_leapfrog(const LeapfrogArgs& a, cudaStream_t st, int* n_launches) {
     int G, E;
+    if (a.D > 512) {  // beyond the register-resident layouts: the streaming form (ahmc_bigd.cu)
+        if (n_launches) *n_launches += 1;
+        return launch_leapfrog_big(a, st);
+    }
     if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
     if (n_launches) *n_launches += 1;
     if (a.model.kind == AHMC_MODEL_USER) {  // run-time compiled kernels of a user target (ahmc_user.cu)
@@ -716,6 +720,10 @@ cudaError_t launch_find_eps(const FindEpsArgs& a, cudaStream_t st, int* n_launch
 
 cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t st, int* n_launches) {
     int G, E;
+    if (a.D > 512) {
+        if (n_launches) *n_launches += 1;
+        return launch_phasepoint_big(a, st);
+    }
     if (!pick_layout(a.D, &G, &E)) return cudaErrorInvalidValue;
     if (n_launches) *n_launches += 1;
     if (a.model.kind == AHMC_MODEL_USER) {  // run-time compiled kernels of a user target (ahmc_user.cu)

@@ -1234,3 +1234,58 @@ def test_user_target_compile_errors_come_back_as_messages():
     assert "nope" in str(e.value)
     with pytest.raises(A.InvalidArgument):
         A.UserTarget(4, "int x;").handle(A.get_context(0))
+
+
+# ------------------------------------------------------------------------------------------------ D > 512 (streaming form)
+@pytest.mark.parametrize("model,metric,D,N,n_steps", [("diag_gauss", "diag", 700, 9, 12), ("funnel", "diag", 1500, 5, 9), ("std_normal", "unit", 5000, 3, -6),
+                                                        ("diag_gauss", "diag_perchain", 513, 7, 5), ("funnel", "unit", 2049, 4, 1)])
+def test_step_and_phasepoint_beyond_512_dimensions_vs_oracle(model, metric, D, N, n_steps):
+    """the reference has no bound on D (src/metric.jl:52-72); beyond the register-resident layouts (D <= 512) `step` and
+    `phasepoint` stream the chain through registers in tiles of 512 coordinates (ahmc_bigd.cu): same oracle, same tolerance,
+    device and host buffers, with and without a cached gradient, per-chain step sizes, backward."""
+    rng = np.random.default_rng(D)
+    p0 = p1 = Minv = None
+    if model == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.7, 0.7, D))
+    mk = "diag" if metric == "diag_perchain" else metric
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.7, 0.7, D))
+    elif metric == "diag_perchain":
+        Minv = np.exp(rng.uniform(-0.7, 0.7, (D, N)))
+    th, r = rng.normal(size=(D, N)) * (0.05 if model == "funnel" else 1.0), rng.normal(size=(D, N))
+    eps = 0.02 * np.exp(rng.uniform(-0.3, 0.3, N))
+    om, ome = oc.Model(MODEL_KINDS[model], D, p0, p1, 0.5), oc.Metric(METRIC_KINDS[mk], Minv)
+    z0o = oc.phasepoint(om, ome, th, r)
+    zo, st_o, dn_o = oc.leapfrog(om, ome, eps, z0o, n_steps)
+    h = A.Hamiltonian(make_metric(mk, Minv, D), make_target(model, D, p0, p1, 0.5))
+    z0 = A.phasepoint(h, T(th), T(r))
+    assert_pp_close(z0, z0o, tol=1e-12, fields=("lp_gradient", "lp_value", "lk_value", "lk_gradient"))
+    lf = A.Leapfrog(torch.as_tensor(eps, device=DEV))
+    z1, info = A.step(lf, h, z0, n_steps, return_info=True)
+    assert (F(info.steps_done) == dn_o).all()
+    assert_pp_close(z1, zo, fields=("theta", "r", "lp_gradient", "lp_value", "lk_value", "lk_gradient"))
+    zn = A.step(lf, h, A.PhasePoint(z0.theta, z0.r, A.DualValue(None, None), A.DualValue(None, None)), n_steps)
+    assert torch.equal(zn.theta, z1.theta) and torch.equal(zn.lp.gradient, z1.lp.gradient)
+    zi = A.PhasePoint(z0.theta.clone(), z0.r.clone(), A.DualValue(z0.lp.value.clone(), z0.lp.gradient.clone()), A.DualValue(z0.lk.value.clone(), None))
+    zi2 = A.step(lf, h, zi, n_steps, out=zi)  # in place
+    assert torch.equal(zi2.theta, z1.theta) and torch.equal(zi2.r, z1.r)
+    if metric != "diag_perchain":
+        zh = A.step(A.Leapfrog(eps), h, A.PhasePoint(np.ascontiguousarray(th.T), np.ascontiguousarray(r.T), A.DualValue(None, None),
+                                                      A.DualValue(None, None)), n_steps)
+        assert np.array_equal(zh.theta, z1.theta.cpu().numpy()) and np.array_equal(zh.lk.value, z1.lk.value.cpu().numpy())
+
+
+def test_beyond_512_dimensions_nonfinite_freeze_and_unsupported_combinations():
+    D, N = 600, 4
+    h = A.Hamiltonian(A.UnitEuclideanMetric(D), A.StdNormal(D))
+    th = np.ones((N, D))
+    th[2, 77] = 1e200
+    z1, info = A.step(A.Leapfrog(0.1), h, A.phasepoint(h, torch.as_tensor(th, device=DEV), torch.ones((N, D), dtype=torch.float64, device=DEV)), 5,
+                      return_info=True)
+    assert list(F(info.steps_done)) == [5, 5, 1, 5] and list(F(info.status)) == [0, 0, 1, 0] and float(z1.lp.value[2]) == -np.inf
+    hd = A.Hamiltonian(A.DenseEuclideanMetric(np.eye(D)), A.StdNormal(D))
+    with pytest.raises(A.AhmcError):
+        A.phasepoint(hd, torch.zeros((N, D), dtype=torch.float64, device=DEV), torch.zeros((N, D), dtype=torch.float64, device=DEV))
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.1), A.GeneralisedNoUTurn()))
+    with pytest.raises(A.AhmcError):
+        A.transition(A.PhiloxRNG(1), h, kern, A.phasepoint(h, torch.zeros((N, D), dtype=torch.float64, device=DEV), torch.zeros((N, D), dtype=torch.float64, device=DEV)))
