@@ -1,15 +1,11 @@
 #!/bin/bash
-# multi-GPU pass (run under `gpurun --gpus 8`): weak-scaling bench at N=8 (+ optionally 2,4) and the sharded configs
+# 8-GPU evidence pass (one box): bench at N=8, the 8-rank NCCL exchange check, BASELINE configs C4 (three adaptation forms) and C5.
 set -u
 mkdir -p gpurun_out
-python advancedhmc.jl_b200/build.py > gpurun_out/build.log 2>&1
-for n in ${SCALE_NS:-8}; do
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) \
-      bench.py --gpus $n --steps 20 --warmup 5 --no-extras > gpurun_out/bench_${n}gpu.json 2> gpurun_out/bench_${n}gpu.err
-  python -c "import json;d=json.load(open('gpurun_out/bench_${n}gpu.json'));print($n, d['value'], d['ms_per_step'], d['e2e'])"
-done
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29700 \
-    scripts/run_configs.py c4 c4v c5 2> gpurun_out/configs_8gpu.err | grep '^{' > gpurun_out/configs_8gpu.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29701 \
-    scripts/run_configs.py c4 c4v --iters 1250 2>> gpurun_out/configs_8gpu.err | grep '^{' >> gpurun_out/configs_8gpu.log
-cat gpurun_out/configs_8gpu.log; tail -3 gpurun_out/configs_8gpu.err
+N=${1:-8}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29541 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err
+timeout 300 $TR --master-port 29542 scripts/nccl_exchange_check.py > gpurun_out/nccl_check_${N}gpu.log 2>&1
+timeout 900 $TR --master-port 29543 scripts/run_configs.py c4d c4 c4v --iters 1250 2>&1 | grep -v Warn > gpurun_out/configs_${N}gpu_1250.log
+timeout 600 $TR --master-port 29544 scripts/run_configs.py c5 c3 2>&1 | grep -v Warn > gpurun_out/configs_${N}gpu.log
+cut -c1-1200 gpurun_out/bench_${N}gpu.json; tail -2 gpurun_out/nccl_check_${N}gpu.log; cat gpurun_out/configs_${N}gpu_1250.log gpurun_out/configs_${N}gpu.log
