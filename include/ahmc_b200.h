@@ -181,7 +181,9 @@ int ahmc_phasepoint_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metri
  * (JitteredLeapfrog = caller passes the jittered per-chain eps, integrator.jl:140-156).
  *   eps_chain == NULL -> scalar step size `eps`; else per-chain eps_chain[N] (`AbstractScalarOrVec`).
  *   n_steps < 0 integrates backward (integrator.jl:221-226).  temper_alpha <= 0: no tempering.
- *   status[N] / steps_done[N] may be NULL. */
+ *   status[N] / steps_done[N] may be NULL.  z_in->lp_gradient may be NULL ("not cached": recomputed on the device).
+ *   D <= 512: every target x metric, chain state register-resident.  D > 512: std-normal / diagonal-Gaussian / funnel
+ *   targets with Unit / Diag metrics (the chain is streamed through registers tile by tile); same for ahmc_phasepoint_f64. */
 int ahmc_leapfrog_f64(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* metric, int32_t D, int64_t N,
                       double eps, const double* eps_chain, int32_t n_steps, double temper_alpha,
                       const ahmc_phasepoint* z_in, const ahmc_phasepoint* z_out, uint32_t* status,
