@@ -20,6 +20,9 @@
 //    exponent fields of (x, r) against 2^200 every floor(100/log2 K) steps PROVES every intermediate
 //    phase point (incl. its energies) was finite; a chain that fails a check (or whose parameters are
 //    outside the proof's range) is simply re-run by the exact path inside the same launch.
+#ifndef __CUDACC_RTC__
+#include <cstdlib>
+#endif
 #include "ahmc_kernels.cuh"
 #include "ahmc_traj.cuh"
 
@@ -529,10 +532,15 @@ static cudaError_t launch_lf_c(const LeapfrogArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;
     const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
     size_t sm = smem_bytes(MODEL, METRIC, a.D, G);
-    if (a.resident_blocks_per_sm > 0) {
+    int occ = a.resident_blocks_per_sm;
+    if (occ == 0) {
+        static const int env_occ = getenv("AHMC_K1_OCC") ? atoi(getenv("AHMC_K1_OCC")) : 0;  // A/B knob
+        occ = env_occ;
+    }
+    if (occ > 0) {
         // occupancy throttle (host-memory lanes): pad the dynamic shared memory so that only this many CTAs fit on
         // an SM; the grid then runs in staggered waves, some CTAs storing while others are still loading
-        const size_t pad = (size_t)(227 * 1024) / (size_t)a.resident_blocks_per_sm - 1024;
+        const size_t pad = (size_t)(227 * 1024) / (size_t)occ - 1024;
         if (pad > sm) sm = pad;
     }
     if (sm > 48 * 1024) {

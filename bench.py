@@ -64,6 +64,23 @@ def measured_traffic():
         return None
 
 
+class Extra:
+    """an extra measurement that fails is reported under "extras_failed" -- it must never cost the headline line"""
+    errors = {}
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is not None and issubclass(et, Exception):
+            Extra.errors[self.name] = f"{et.__name__}: {ev}"[:300]
+            return True
+        return False
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -271,177 +288,182 @@ def run_ours(args):
         # ---- HBM-honest shape: 2^20 chains x D=128, ONE leapfrog step per launch, in place (3 GiB of state)
         honest = None
         if rank == 0 and not args.no_extras:
-            Nh = 1 << 20
-            g = torch.Generator(device=dev).manual_seed(1)
-            st = torch.as_tensor(s, device=dev)
-            zh = A.phasepoint(h, torch.randn((Nh, DIM), generator=g, dtype=torch.float64, device=dev) * st,
-                              torch.randn((Nh, DIM), generator=g, dtype=torch.float64, device=dev) / st)
-            import ctypes as C
+            with Extra("honest"):
+                Nh = 1 << 20
+                g = torch.Generator(device=dev).manual_seed(1)
+                st = torch.as_tensor(s, device=dev)
+                zh = A.phasepoint(h, torch.randn((Nh, DIM), generator=g, dtype=torch.float64, device=dev) * st,
+                                  torch.randn((Nh, DIM), generator=g, dtype=torch.float64, device=dev) / st)
+                import ctypes as C
 
-            md, keep = h.metric._desc(DIM, Nh, zh.theta)
-            zc = zh._c(False)
-            call = lambda: ctx.check(ctx.lib.ahmc_leapfrog_f64(ctx.h, h.target.handle(ctx), C.byref(md), DIM, Nh, EPS, None, 1,
-                                                               0.0, C.byref(zc), C.byref(zc), None, None, A.FLAG_ASYNC))
-            for _ in range(3):
-                call()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 10
-            e0.record(stream)
-            for _ in range(reps):
-                call()
-            e1.record(stream)
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / reps
-            bytes_launch = Nh * DIM * 48 + Nh * 16
-            honest = {"workload": "2^20 chains x D=128, 1 step per launch, in place (3 GiB state >> L2)",
-                      "ms_per_launch": ms, "achieved": bytes_launch / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                      "frac": bytes_launch / ms / 1e6 / hbm_peak, "rate_steps_dims_per_s": Nh * DIM / ms * 1e3}
-            # ---- same kernel, fused L=32 steps at 2^20 chains: the large-batch regime where launch overhead is
-            # amortised and the register-resident trajectory is bound by its COMPULSORY HBM traffic
-            callL = lambda: ctx.check(ctx.lib.ahmc_leapfrog_f64(ctx.h, h.target.handle(ctx), C.byref(md), DIM, Nh, EPS, None,
-                                                                L_STEPS, 0.0, C.byref(zc), C.byref(zc), None, None, A.FLAG_ASYNC))
-            callL()
-            e0.record(stream)
-            for _ in range(5):
+                md, keep = h.metric._desc(DIM, Nh, zh.theta)
+                zc = zh._c(False)
+                call = lambda: ctx.check(ctx.lib.ahmc_leapfrog_f64(ctx.h, h.target.handle(ctx), C.byref(md), DIM, Nh, EPS, None, 1,
+                                                                   0.0, C.byref(zc), C.byref(zc), None, None, A.FLAG_ASYNC))
+                for _ in range(3):
+                    call()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 10
+                e0.record(stream)
+                for _ in range(reps):
+                    call()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                bytes_launch = Nh * DIM * 48 + Nh * 16
+                honest = {"workload": "2^20 chains x D=128, 1 step per launch, in place (3 GiB state >> L2)",
+                          "ms_per_launch": ms, "achieved": bytes_launch / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": bytes_launch / ms / 1e6 / hbm_peak, "rate_steps_dims_per_s": Nh * DIM / ms * 1e3}
+                # ---- same kernel, fused L=32 steps at 2^20 chains: the large-batch regime where launch overhead is
+                # amortised and the register-resident trajectory is bound by its COMPULSORY HBM traffic
+                callL = lambda: ctx.check(ctx.lib.ahmc_leapfrog_f64(ctx.h, h.target.handle(ctx), C.byref(md), DIM, Nh, EPS, None,
+                                                                    L_STEPS, 0.0, C.byref(zc), C.byref(zc), None, None, A.FLAG_ASYNC))
                 callL()
-            e1.record(stream)
-            torch.cuda.synchronize()
-            msL = e0.elapsed_time(e1) / 5
-            honest["fused_L32"] = {"workload": "2^20 chains x D=128, L=32 fused steps per launch, in place",
-                                   "ms_per_launch": msL, "rate_steps_dims_per_s": Nh * DIM * L_STEPS / msL * 1e3,
-                                   "achieved_compulsory": bytes_launch / msL / 1e6, "frac_compulsory": bytes_launch / msL / 1e6 / hbm_peak,
-                                   "fp64_tflops": Nh * DIM * L_STEPS * 4 / msL / 1e9}
-            del zh
+                e0.record(stream)
+                for _ in range(5):
+                    callL()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                msL = e0.elapsed_time(e1) / 5
+                honest["fused_L32"] = {"workload": "2^20 chains x D=128, L=32 fused steps per launch, in place",
+                                       "ms_per_launch": msL, "rate_steps_dims_per_s": Nh * DIM * L_STEPS / msL * 1e3,
+                                       "achieved_compulsory": bytes_launch / msL / 1e6, "frac_compulsory": bytes_launch / msL / 1e6 / hbm_peak,
+                                       "fp64_tflops": Nh * DIM * L_STEPS * 4 / msL / 1e9}
+                del zh
 
         # ---- K2: fused static-HMC transition (refresh + 32 steps + MH) on the same batch
         k2 = None
         if rank == 0 and not args.no_extras:
-            kern = A.HMCKernel(A.Trajectory(A.EndPointTS, lf, A.FixedNSteps(L_STEPS)))
-            prng = A.PhiloxRNG(7)
-            NT = 100  # transitions per chain inside ONE launch (ahmc_hmc_sample_f64): no host work between transitions
-            for _ in range(2):
-                A.sample_transitions(prng, h, kern, z0, NT, keep_draws=False)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record(stream)
-            A.sample_transitions(prng, h, kern, z0, NT, keep_draws=False, flags=A.FLAG_ASYNC)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            ms_k2 = e0.elapsed_time(e1) / NT
-            k2 = {"workload": "static HMC transitions (Philox refresh + 32 fused steps + MH), 4096x128, 100 transitions per chain in one launch",
-                  "ms_per_transition": ms_k2, "rate_steps_dims_per_s": units_per_step / ms_k2 * 1e3}
+            with Extra("k2"):
+                kern = A.HMCKernel(A.Trajectory(A.EndPointTS, lf, A.FixedNSteps(L_STEPS)))
+                prng = A.PhiloxRNG(7)
+                NT = 100  # transitions per chain inside ONE launch (ahmc_hmc_sample_f64): no host work between transitions
+                for _ in range(2):
+                    A.sample_transitions(prng, h, kern, z0, NT, keep_draws=False)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                A.sample_transitions(prng, h, kern, z0, NT, keep_draws=False, flags=A.FLAG_ASYNC)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms_k2 = e0.elapsed_time(e1) / NT
+                k2 = {"workload": "static HMC transitions (Philox refresh + 32 fused steps + MH), 4096x128, 100 transitions per chain in one launch",
+                      "ms_per_transition": ms_k2, "rate_steps_dims_per_s": units_per_step / ms_k2 * 1e3}
 
         # ---- the GENERAL path on the same shape: per-step reference op sequence with energies and isfinite tests (what every
         # non-Gaussian user model runs), the funnel target, and NUTS on the C3 shape (persistent launch, 20 transitions)
         general = None
         if rank == 0 and not args.no_extras:
-            general = {}
-            B = 48.0 + 24.0 / DIM
+            with Extra("general"):
+                general = {}
+                B = 48.0 + 24.0 / DIM
 
-            def timed(fn, reps):
-                for _ in range(3):
-                    fn()
+                def timed(fn, reps):
+                    for _ in range(3):
+                        fn()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    for _ in range(reps):
+                        fn()
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                    return e0.elapsed_time(e1) / reps
+
+                ex = A.StepPlan(lf, h, z0, L_STEPS, flags=A.FLAG_ASYNC | A.FLAG_EXACT_CHECKS)
+                ms = timed(ex, 20)
+                rate = units_per_step / ms * 1e3
+                general["exact_path"] = {"workload": "headline shape, AHMC_FLAG_EXACT_CHECKS: per-step energies + isfinite, no linear shortcut",
+                                         "ms_per_launch": ms, "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * B / 1e9 / hbm_peak,
+                                         "roofline_frac_compulsory": (N_CHAINS * DIM * 48 + N_CHAINS * 24) / ms / 1e6 / hbm_peak}
+                Df = 100
+                hf = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(Df)), A.Funnel(Df))
+                gf = torch.Generator(device=dev).manual_seed(3)
+                zf = A.phasepoint(hf, 0.5 * torch.randn((N_CHAINS, Df), generator=gf, dtype=torch.float64, device=dev),
+                                  torch.randn((N_CHAINS, Df), generator=gf, dtype=torch.float64, device=dev))
+                fp = A.StepPlan(A.Leapfrog(0.05), hf, zf, L_STEPS, flags=A.FLAG_ASYNC)
+                ms = timed(fp, 20)
+                rate = N_CHAINS * Df * L_STEPS / ms * 1e3
+                Bf = 48.0 + 24.0 / Df
+                general["funnel_trajectory"] = {"workload": "Neal's funnel D=100 (SURVEY 8c), 4096 chains, Diag metric, Leapfrog(0.05), L=32 fused",
+                                                "ms_per_launch": ms, "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * Bf / 1e9 / hbm_peak,
+                                                "roofline_frac_compulsory": (N_CHAINS * Df * 48 + N_CHAINS * 24) / ms / 1e6 / hbm_peak}
+                kn = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.4), A.GeneralisedNoUTurn()))
+                prn = A.PhiloxRNG(11)
+                zs = A.phasepoint(h, torch.as_tensor(th * s, device=dev), torch.as_tensor(r, device=dev))  # theta ~ target
+                TN = 20
+                zl, _, stn = A.sample_transitions(prn, h, kn, zs, TN, keep_draws=False, flags=A.FLAG_ASYNC)
+                torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                for _ in range(reps):
-                    fn()
+                zl, _, stn = A.sample_transitions(prn, h, kn, zl, TN, keep_draws=False, flags=A.FLAG_ASYNC)
                 e1.record(stream)
                 torch.cuda.synchronize()
-                return e0.elapsed_time(e1) / reps
-
-            ex = A.StepPlan(lf, h, z0, L_STEPS, flags=A.FLAG_ASYNC | A.FLAG_EXACT_CHECKS)
-            ms = timed(ex, 20)
-            rate = units_per_step / ms * 1e3
-            general["exact_path"] = {"workload": "headline shape, AHMC_FLAG_EXACT_CHECKS: per-step energies + isfinite, no linear shortcut",
-                                     "ms_per_launch": ms, "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * B / 1e9 / hbm_peak,
-                                     "roofline_frac_compulsory": (N_CHAINS * DIM * 48 + N_CHAINS * 24) / ms / 1e6 / hbm_peak}
-            Df = 100
-            hf = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(Df)), A.Funnel(Df))
-            gf = torch.Generator(device=dev).manual_seed(3)
-            zf = A.phasepoint(hf, 0.5 * torch.randn((N_CHAINS, Df), generator=gf, dtype=torch.float64, device=dev),
-                              torch.randn((N_CHAINS, Df), generator=gf, dtype=torch.float64, device=dev))
-            fp = A.StepPlan(A.Leapfrog(0.05), hf, zf, L_STEPS, flags=A.FLAG_ASYNC)
-            ms = timed(fp, 20)
-            rate = N_CHAINS * Df * L_STEPS / ms * 1e3
-            Bf = 48.0 + 24.0 / Df
-            general["funnel_trajectory"] = {"workload": "Neal's funnel D=100 (SURVEY 8c), 4096 chains, Diag metric, Leapfrog(0.05), L=32 fused",
-                                            "ms_per_launch": ms, "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * Bf / 1e9 / hbm_peak,
-                                            "roofline_frac_compulsory": (N_CHAINS * Df * 48 + N_CHAINS * 24) / ms / 1e6 / hbm_peak}
-            kn = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.4), A.GeneralisedNoUTurn()))
-            prn = A.PhiloxRNG(11)
-            zs = A.phasepoint(h, torch.as_tensor(th * s, device=dev), torch.as_tensor(r, device=dev))  # theta ~ target
-            TN = 20
-            zl, _, stn = A.sample_transitions(prn, h, kn, zs, TN, keep_draws=False, flags=A.FLAG_ASYNC)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            zl, _, stn = A.sample_transitions(prn, h, kn, zl, TN, keep_draws=False, flags=A.FLAG_ASYNC)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            nsteps = int(stn["n_steps"].sum().item())
-            msn = e0.elapsed_time(e1)
-            rate = nsteps * DIM / msn * 1e3
-            general["nuts_c3"] = {"workload": "C3: NUTS(MultinomialTS, GeneralisedNoUTurn) + DiagEuclidean, D=128 Gaussian, 4096 chains, eps=0.4, "
-                                              "20 transitions per chain in one persistent launch",
-                                  "ms_per_transition": msn / TN, "mean_leapfrog_steps_per_transition": nsteps / TN / N_CHAINS,
-                                  "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * B / 1e9 / hbm_peak}
+                nsteps = int(stn["n_steps"].sum().item())
+                msn = e0.elapsed_time(e1)
+                rate = nsteps * DIM / msn * 1e3
+                general["nuts_c3"] = {"workload": "C3: NUTS(MultinomialTS, GeneralisedNoUTurn) + DiagEuclidean, D=128 Gaussian, 4096 chains, eps=0.4, "
+                                                  "20 transitions per chain in one persistent launch",
+                                      "ms_per_transition": msn / TN, "mean_leapfrog_steps_per_transition": nsteps / TN / N_CHAINS,
+                                      "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * B / 1e9 / hbm_peak}
 
         # ---- K4: correlated (dense-precision) Gaussian target, Diag metric, same batch: fp64 tensor-MMA trajectory
         k4 = None
         if rank == 0 and not args.no_extras:
-            rng4 = np.random.Generator(np.random.PCG64(SEED))
-            Q, _ = np.linalg.qr(rng4.normal(size=(DIM, DIM)))
-            lam = np.exp(np.linspace(np.log(0.1), np.log(10.0), DIM))
-            hd = A.Hamiltonian(A.DiagEuclideanMetric(np.diag((Q * lam) @ Q.T).copy()), A.DenseGaussian(np.zeros(DIM), (Q / lam) @ Q.T))
-            zd = A.phasepoint(hd, torch.as_tensor(th, device=dev), torch.as_tensor(r, device=dev))
-            pd = A.StepPlan(A.Leapfrog(0.02), hd, zd, L_STEPS, flags=A.FLAG_ASYNC)
-            for _ in range(3):
-                pd()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(10):
-                pd()
-            e1.record(stream)
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 10
-            flops = 2.0 * DIM * DIM * N_CHAINS * L_STEPS
-            k4 = {"workload": "C2-style: 4096 chains x D=128 correlated Gaussian (dense precision), Diag metric, L=32 fused, tiled DMMA kernel",
-                  "ms_per_launch": ms, "rate_steps_dims_per_s": units_per_step / ms * 1e3, "fp64_tflops_gemm": flops / ms / 1e9}
-            # the same contraction through cuBLAS Dgemm: one [D x D] @ [D x N] product per step, 32 per
-            # trajectory, as a step-at-a-time implementation would issue them; and a large Dgemm for the DMMA peak
-            P64 = torch.as_tensor((Q / lam) @ Q.T, device=dev)
-            X64 = torch.as_tensor(th, device=dev).T.contiguous()
-            Y64 = torch.empty_like(X64)
-            for _ in range(3):
-                torch.matmul(P64, X64, out=Y64)
-            e0.record(stream)
-            for _ in range(10 * L_STEPS):
-                torch.matmul(P64, X64, out=Y64)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            ms_cb = e0.elapsed_time(e1) / 10
-            k4["cublas_dgemm_same_shape"] = {"what": "torch.matmul fp64 [128x128]@[128x4096], 32 calls = the gradient GEMMs of one trajectory (no leapfrog arithmetic)",
-                                             "ms_per_32": ms_cb, "tflops": flops / ms_cb / 1e9}
-            Ab = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
-            Cb = torch.empty_like(Ab)
-            torch.matmul(Ab, Ab, out=Cb)
-            e0.record(stream)
-            for _ in range(3):
+            with Extra("k4"):
+                rng4 = np.random.Generator(np.random.PCG64(SEED))
+                Q, _ = np.linalg.qr(rng4.normal(size=(DIM, DIM)))
+                lam = np.exp(np.linspace(np.log(0.1), np.log(10.0), DIM))
+                hd = A.Hamiltonian(A.DiagEuclideanMetric(np.diag((Q * lam) @ Q.T).copy()), A.DenseGaussian(np.zeros(DIM), (Q / lam) @ Q.T))
+                zd = A.phasepoint(hd, torch.as_tensor(th, device=dev), torch.as_tensor(r, device=dev))
+                pd = A.StepPlan(A.Leapfrog(0.02), hd, zd, L_STEPS, flags=A.FLAG_ASYNC)
+                for _ in range(3):
+                    pd()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(10):
+                    pd()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 10
+                flops = 2.0 * DIM * DIM * N_CHAINS * L_STEPS
+                k4 = {"workload": "C2-style: 4096 chains x D=128 correlated Gaussian (dense precision), Diag metric, L=32 fused, tiled DMMA kernel",
+                      "ms_per_launch": ms, "rate_steps_dims_per_s": units_per_step / ms * 1e3, "fp64_tflops_gemm": flops / ms / 1e9}
+                # the same contraction through cuBLAS Dgemm: one [D x D] @ [D x N] product per step, 32 per
+                # trajectory, as a step-at-a-time implementation would issue them; and a large Dgemm for the DMMA peak
+                P64 = torch.as_tensor((Q / lam) @ Q.T, device=dev)
+                X64 = torch.as_tensor(th, device=dev).T.contiguous()
+                Y64 = torch.empty_like(X64)
+                for _ in range(3):
+                    torch.matmul(P64, X64, out=Y64)
+                e0.record(stream)
+                for _ in range(10 * L_STEPS):
+                    torch.matmul(P64, X64, out=Y64)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms_cb = e0.elapsed_time(e1) / 10
+                k4["cublas_dgemm_same_shape"] = {"what": "torch.matmul fp64 [128x128]@[128x4096], 32 calls = the gradient GEMMs of one trajectory (no leapfrog arithmetic)",
+                                                 "ms_per_32": ms_cb, "tflops": flops / ms_cb / 1e9}
+                Ab = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+                Cb = torch.empty_like(Ab)
                 torch.matmul(Ab, Ab, out=Cb)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            k4["cublas_dgemm_4096_tflops"] = 2.0 * 4096 ** 3 * 3 / e0.elapsed_time(e1) / 1e9
-            del Ab, Cb
+                e0.record(stream)
+                for _ in range(3):
+                    torch.matmul(Ab, Ab, out=Cb)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                k4["cublas_dgemm_4096_tflops"] = 2.0 * 4096 ** 3 * 3 / e0.elapsed_time(e1) / 1e9
+                del Ab, Cb
 
         # ---- fp64 FMA-pipe peak (the bound of the fused fast path), measured by a DFMA microbenchmark
         dfma = None
         if rank == 0 and not args.no_extras:
-            import ctypes
-            mb = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "advancedhmc.jl_b200", "libahmc_microbench.so"))
-            tf, msb = ctypes.c_double(), ctypes.c_double()
-            rcmb = mb.ahmc_mb_dfma_peak(ctypes.c_int(local), ctypes.c_int(2048), ctypes.c_int(5), ctypes.byref(tf), ctypes.byref(msb))
-            if rcmb == 0:
-                dfma = {"tflops": tf.value, "ms": msb.value, "what": "148*8 blocks x 256 threads x 8 independent DFMA chains (libahmc_microbench.so)"}
+            with Extra("dfma"):
+                import ctypes
+                mb = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "advancedhmc.jl_b200", "libahmc_microbench.so"))
+                tf, msb = ctypes.c_double(), ctypes.c_double()
+                rcmb = mb.ahmc_mb_dfma_peak(ctypes.c_int(local), ctypes.c_int(2048), ctypes.c_int(5), ctypes.byref(tf), ctypes.byref(msb))
+                if rcmb == 0:
+                    dfma = {"tflops": tf.value, "ms": msb.value, "what": "148*8 blocks x 256 threads x 8 independent DFMA chains (libahmc_microbench.so)"}
 
     # ---- the path's one exchange, inside the driver-run line: pooled warm-up on the C4 shape (funnel D=100,
     # 4096 chains per GPU, NUTS).  Per iteration, on ONE stream and with no host synchronisation: NUTS transition (K3) ->
@@ -449,60 +471,61 @@ def run_ours(args):
     # kernel that writes eps / M^-1 where the next transition reads them (ahmc_adapt_exchange_f64).  All ranks take part.
     exchange = None
     if not args.no_extras:
-        from ahmc_b200 import adaptation as adp
+        with Extra("exchange"):
+            from ahmc_b200 import adaptation as adp
 
-        with torch.cuda.stream(stream):
-            comm = adp.Comm.from_torch_distributed(local) if world > 1 else None
-            Df, n_it = 100, 40
-            hf = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(Df)), A.Funnel(Df))
-            gf = torch.Generator(device=dev).manual_seed(100 + rank)
-            thf = 0.5 * torch.randn((N_CHAINS, Df), generator=gf, dtype=torch.float64, device=dev)
-            pad = adp.PooledDeviceAdaptor(local, Df, N_CHAINS, n_adapts=n_it + 10, eps0=0.1, init_buffer=10, term_buffer=5, window_size=8)
-            hdv = A.Hamiltonian(A.DiagEuclideanMetric(pad.Minv), hf.target)
-            kdv = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(pad.eps), A.GeneralisedNoUTurn()))
-            prf = A.PhiloxRNG(21 + rank)
-            zf = A.phasepoint(hdv, thf, torch.zeros_like(thf))
-            for _ in range(5):  # warm-up (also the first NCCL call)
-                trf = A.transition(prf, hdv, kdv, zf, flags=A.FLAG_ASYNC)
-                zf = trf.z
-                pad.exchange(zf.theta, trf.stat["acceptance_rate"], comm)
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            nsteps_dev = torch.zeros((), dtype=torch.int64, device=dev)
-            e0.record(stream)
-            for _ in range(n_it):
-                trf = A.transition(prf, hdv, kdv, zf, flags=A.FLAG_ASYNC)
-                zf = trf.z
-                pad.exchange(zf.theta, trf.stat["acceptance_rate"], comm)
-                nsteps_dev += trf.stat["n_steps"].sum()
-            e1.record(stream)
-            torch.cuda.synchronize()
-            ms_iter = e0.elapsed_time(e1) / n_it
-            e0.record(stream)
-            for _ in range(200):  # the exchange alone, back to back on fixed inputs
-                pad.exchange(zf.theta, trf.stat["acceptance_rate"], comm)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            us_x = e0.elapsed_time(e1) / 200 * 1e3
-            tx = torch.tensor([ms_iter, us_x], dtype=torch.float64, device=dev)
-            ns_all = nsteps_dev.clone()
-            if world > 1:
-                dist.all_reduce(tx, op=dist.ReduceOp.MAX)
-                dist.all_reduce(ns_all)
-            ms_iter_max, us_x_max = tx.tolist()
-            stt = pad.state()
-            exchange = {"workload": "C4 shape: Neal's funnel D=100, 4096 chains per GPU, NUTS(max_depth 10), pooled StanHMCAdaptor on the device, "
-                                    f"{n_it} warm-up iterations after 5 untimed",
-                        "ranks": world, "record_bytes_per_rank": (2 + 2 * Df) * 8,
-                        "warmup_iteration_ms": ms_iter_max, "exchange_us": us_x_max, "exchange_share": us_x_max * 1e-3 / ms_iter_max,
-                        "rate_steps_dims_per_s": float(ns_all.item()) * Df / (ms_iter_max * n_it) * 1e3,
-                        "host_syncs_per_iteration": 0, "eps_after": stt["eps"],
-                        "what": "exchange = K5 record + ncclAllGather + merge/adaptor kernel (ahmc_adapt_exchange_f64), max over ranks"}
-            pad.destroy()
-            if comm is not None:
-                comm.destroy()
+            with torch.cuda.stream(stream):
+                comm = adp.Comm.from_torch_distributed(local) if world > 1 else None
+                Df, n_it = 100, 40
+                hf = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(Df)), A.Funnel(Df))
+                gf = torch.Generator(device=dev).manual_seed(100 + rank)
+                thf = 0.5 * torch.randn((N_CHAINS, Df), generator=gf, dtype=torch.float64, device=dev)
+                pad = adp.PooledDeviceAdaptor(local, Df, N_CHAINS, n_adapts=n_it + 10, eps0=0.1, init_buffer=10, term_buffer=5, window_size=8)
+                hdv = A.Hamiltonian(A.DiagEuclideanMetric(pad.Minv), hf.target)
+                kdv = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(pad.eps), A.GeneralisedNoUTurn()))
+                prf = A.PhiloxRNG(21 + rank)
+                zf = A.phasepoint(hdv, thf, torch.zeros_like(thf))
+                for _ in range(5):  # warm-up (also the first NCCL call)
+                    trf = A.transition(prf, hdv, kdv, zf, flags=A.FLAG_ASYNC)
+                    zf = trf.z
+                    pad.exchange(zf.theta, trf.stat["acceptance_rate"], comm)
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nsteps_dev = torch.zeros((), dtype=torch.int64, device=dev)
+                e0.record(stream)
+                for _ in range(n_it):
+                    trf = A.transition(prf, hdv, kdv, zf, flags=A.FLAG_ASYNC)
+                    zf = trf.z
+                    pad.exchange(zf.theta, trf.stat["acceptance_rate"], comm)
+                    nsteps_dev += trf.stat["n_steps"].sum()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms_iter = e0.elapsed_time(e1) / n_it
+                e0.record(stream)
+                for _ in range(200):  # the exchange alone, back to back on fixed inputs
+                    pad.exchange(zf.theta, trf.stat["acceptance_rate"], comm)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                us_x = e0.elapsed_time(e1) / 200 * 1e3
+                tx = torch.tensor([ms_iter, us_x], dtype=torch.float64, device=dev)
+                ns_all = nsteps_dev.clone()
+                if world > 1:
+                    dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(ns_all)
+                ms_iter_max, us_x_max = tx.tolist()
+                stt = pad.state()
+                exchange = {"workload": "C4 shape: Neal's funnel D=100, 4096 chains per GPU, NUTS(max_depth 10), pooled StanHMCAdaptor on the device, "
+                                        f"{n_it} warm-up iterations after 5 untimed",
+                            "ranks": world, "record_bytes_per_rank": (2 + 2 * Df) * 8,
+                            "warmup_iteration_ms": ms_iter_max, "exchange_us": us_x_max, "exchange_share": us_x_max * 1e-3 / ms_iter_max,
+                            "rate_steps_dims_per_s": float(ns_all.item()) * Df / (ms_iter_max * n_it) * 1e3,
+                            "host_syncs_per_iteration": 0, "eps_after": stt["eps"],
+                            "what": "exchange = K5 record + ncclAllGather + merge/adaptor kernel (ahmc_adapt_exchange_f64), max over ranks"}
+                pad.destroy()
+                if comm is not None:
+                    comm.destroy()
 
     # ---- e2e: the public call with HOST (pinned) buffers, copies inside the timed region.  Contract of
     # src/integrator.jl:216-265: host arrays in (theta, r -- the cached gradient of a built-in target is recomputed on the
@@ -593,6 +616,8 @@ def run_ours(args):
         line["roofline_hbm_honest"] = honest
     if k2:
         line["hmc_transition"] = k2
+    if Extra.errors:
+        line["extras_failed"] = Extra.errors
     if exchange:
         line["adapt_exchange"] = exchange
     if general:
