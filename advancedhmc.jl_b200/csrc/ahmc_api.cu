@@ -1370,6 +1370,8 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
     if ((rc = check_pp(ctx, z_out, D, "z_out", true, N))) return rc;
     if (max_depth < 0 || max_depth > 20) return fail(ctx, AHMC_ERR_INVALID, "max_depth must be in 0..20");
+    if (cfg && max_depth == 0)  // no leaf is ever built: acceptance_rate = 0/0 (as in the reference) would poison dual averaging
+        return fail(ctx, AHMC_ERR_INVALID, "in-launch adaptation needs max_depth >= 1");
     if ((flags & AHMC_FLAG_NUTS_CLASSIC) && (flags & AHMC_FLAG_NUTS_STRICT))
         return fail(ctx, AHMC_ERR_INVALID, "AHMC_FLAG_NUTS_CLASSIC and AHMC_FLAG_NUTS_STRICT are mutually exclusive");
     if (model->kind == AHMC_MODEL_CALLBACK)

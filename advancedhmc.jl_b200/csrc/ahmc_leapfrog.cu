@@ -532,11 +532,7 @@ static cudaError_t launch_lf_c(const LeapfrogArgs& a, cudaStream_t st) {
     const int chains_per_block = kBlockThreads / G;
     const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
     size_t sm = smem_bytes(MODEL, METRIC, a.D, G);
-    int occ = a.resident_blocks_per_sm;
-    if (occ == 0) {
-        static const int env_occ = getenv("AHMC_K1_OCC") ? atoi(getenv("AHMC_K1_OCC")) : 0;  // A/B knob
-        occ = env_occ;
-    }
+    const int occ = a.resident_blocks_per_sm;
     if (occ > 0) {
         // occupancy throttle (host-memory lanes): pad the dynamic shared memory so that only this many CTAs fit on
         // an SM; the grid then runs in staggered waves, some CTAs storing while others are still loading

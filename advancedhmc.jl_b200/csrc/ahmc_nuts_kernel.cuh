@@ -458,7 +458,8 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                     double rsf[E], rl_p[E], tA[E], tB[E];
 #pragma unroll
                     for (int e = 0; e < E; ++e) rsf[e] = rl_p[e] = 0.0;
-                    if (do_comb) {
+                    if (do_comb && !term_c) {  // (a node that already terminated floats up unchanged: its level slots
+                                               //  below k were never written, and the verdict cannot change any more)
                         if (k == 0) {
 #pragma unroll
                             for (int e = 0; e < E; ++e) {
