@@ -11,10 +11,13 @@
 //                             the next transition reads (eps_chain[N], Minv[D]).
 // NCCL is bound at run time (dlopen): the library loads without it and a Julia host can hand over the communicator it
 // already owns (NCCL.jl) or let ahmc_comm_create make one from a broadcast unique id.
+#ifndef AHMC_SIMT_EMULATION
 #include <dlfcn.h>
+#endif
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "ahmc_kernels.cuh"
 
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(256) pooled_update_kernel(PooledState* st, con
     for (long long c = threadIdx.x; c < N; c += blockDim.x) eps_chain[c] = e;
 }
 
+#ifndef AHMC_SIMT_EMULATION  // host launch code and the NCCL binding (skipped by the CPU SIMT emulation harness, tests/simt_emu/)
 __global__ void fill_kernel(double* p, long long n, double v) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -154,6 +158,7 @@ cudaError_t launch_fill(double* p, long long n, double v, cudaStream_t st) {
     fill_kernel<<<(unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, st>>>(p, n, v);
     return cudaGetLastError();
 }
+#endif  // AHMC_SIMT_EMULATION
 size_t pooled_state_bytes() { return sizeof(PooledState); }
 
 // host image of the state for creation / read-back
@@ -187,6 +192,7 @@ void pooled_state_read(const void* host_image, double* eps, int* iteration, int*
     if (n_window) *n_window = s.n;
 }
 
+#ifndef AHMC_SIMT_EMULATION
 // ---------------------------------------------------------------------------------------------- NCCL (bound at run time)
 namespace {
 struct NcclApi {
@@ -200,9 +206,11 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 bool g_nccl_tried = false;
+std::mutex g_nccl_mutex;
 }  // namespace
 
 const char* nccl_bind() {  // nullptr on success, else a reason
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
     if (g_nccl.lib) return nullptr;
     if (g_nccl_tried) return g_nccl.why;
     g_nccl_tried = true;
@@ -240,5 +248,6 @@ int nccl_comm_destroy(void* comm) { return g_nccl.CommDestroy(comm); }
 int nccl_allgather_f64(const double* send, double* recv, size_t count, void* comm, cudaStream_t st) {
     return g_nccl.AllGather(send, recv, count, 8 /* ncclFloat64 */, comm, st);
 }
+#endif  // AHMC_SIMT_EMULATION
 
 }  // namespace ahmc

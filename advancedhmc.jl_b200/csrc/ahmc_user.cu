@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -49,6 +50,7 @@ struct Rtc {
     bool tried = false, ok = false;
 };
 Rtc g_rtc;
+std::mutex g_rtc_mutex;  // contexts of different host threads may bind / compile concurrently
 
 template <class F>
 bool sym(void* lib, const char* name, F& f) {
@@ -57,6 +59,7 @@ bool sym(void* lib, const char* name, F& f) {
 }
 
 const char* rtc_bind() {
+    std::lock_guard<std::mutex> lock(g_rtc_mutex);
     if (g_rtc.ok) return nullptr;
     if (g_rtc.tried) return g_rtc.why;
     g_rtc.tried = true;
@@ -85,6 +88,7 @@ const char* rtc_bind() {
 }
 
 const char* driver_bind() {  // the driver API, needed to load and launch (not to compile)
+    std::lock_guard<std::mutex> lock(g_rtc_mutex);
     if (g_rtc.cuda) return nullptr;
     g_rtc.cuda = dlopen("libcuda.so.1", RTLD_NOW);
     if (!g_rtc.cuda) {

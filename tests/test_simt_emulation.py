@@ -418,6 +418,58 @@ def test_adaptor_statistics_kernel_sources_under_emulation(tmp_path):
         assert np.allclose(cov, want, rtol=1e-11, atol=1e-11 * np.abs(want).max()) and np.array_equal(cov, cov.T)
 
 
+@pytest.mark.parametrize("R,adapt_metric", [(1, 1), (2, 1), (5, 1), (3, 0)])
+def test_pooled_adaptor_kernel_source_under_emulation_equals_host_adaptors(tmp_path, R, adapt_metric):
+    """The device-side exchange's arithmetic (`pooled_update_kernel`, ahmc_pooled.cu: rank-ordered Chan merge of R per-rank
+    records, NesterovDualAveraging, WelfordVar, Stan windows, reset / finalize) executed by the CPU emulator on the records R
+    ranks would all-gather, against the host-side pooled adaptors of adaptation.py fed with the merged record -- the N > 1
+    path of the exchange without a GPU or NCCL (the GPU suite repeats it over a real 2-rank communicator)."""
+    from ahmc_b200 import adaptation as ad
+
+    out = tmp_path / "libpooled_emu.so"
+    d = os.path.join(ROOT, "tests", "simt_emu")
+    subprocess.run(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-ffp-contract=off", "-x", "c++",
+                    "-I", os.path.join(d, "include"), "-I", os.path.join(ROOT, "advancedhmc.jl_b200", "csrc"),
+                    "-I", os.path.join(ROOT, "include"), os.path.join(d, "simt_emu.cpp"), os.path.join(d, "pooled_emu.cpp"),
+                    "-o", str(out)], check=True)
+    lib = C.CDLL(str(out))
+    lib.emu_pooled_create.restype = C.c_void_p
+    lib.emu_pooled_create.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.emu_pooled_update.argtypes = [C.c_void_p, _vp, C.c_int, _vp, _vp, _vp]
+    lib.emu_pooled_destroy.argtypes = [C.c_void_p]
+    D, n_adapts, windows = 13, 40, (5, 4, 6)
+    rng = np.random.default_rng(17 + R)
+    chains = [50 + 7 * r for r in range(R)]  # ragged shards
+    h = lib.emu_pooled_create(D, chains[0], n_adapts, *windows, 0.21, 0.8, adapt_metric, 3)
+    assert h
+    pc = ad.WelfordVar(D, n_min=3) if adapt_metric else ad.UnitMassMatrix()
+    host = ad.StanHMCAdaptor(pc, ad.NesterovDualAveraging(0.8, 0.21), *windows)
+    host.initialize(n_adapts)
+    scale = np.exp(rng.uniform(-1, 1, D))
+    for i in range(1, n_adapts + 1):
+        recs = []
+        for r in range(R):
+            th = rng.normal(size=(chains[r], D)) * scale + 0.2 * r
+            al = rng.uniform(0.1, 1.5, chains[r])
+            mu = th.mean(axis=0)
+            recs.append(np.concatenate([[chains[r], np.minimum(1.0, al).sum()], mu, ((th - mu) ** 2).sum(axis=0)]))
+        gathered = np.ascontiguousarray(np.stack(recs))
+        eps, minv, merged = C.c_double(), np.zeros(D), np.zeros(2 + 2 * D)
+        it = lib.emu_pooled_update(h, P(gathered), R, C.byref(eps), P(minv), P(merged))
+        assert it == i
+        want = ad.merge_records(recs)
+        assert np.allclose(merged, want, rtol=1e-13, atol=0)
+        host.adapt(want)
+        if i == n_adapts:
+            host.finalize()
+        assert abs(eps.value - host.eps) <= 1e-13 * host.eps, (i, eps.value, host.eps)
+        if adapt_metric:
+            assert np.allclose(minv, host.Minv, rtol=1e-12, atol=0), i
+        else:
+            assert (minv == 1.0).all()
+    lib.emu_pooled_destroy(h)
+
+
 def test_trajectory_kernel_emulated_nonfinite_freeze_tempering_and_fast_path_fallback(emu_lf):
     """K1 under emulation on the awkward inputs: a chain that overflows freezes on its own at the break step with -Inf
     energies while its warp-mates finish (integrator.jl:252-258, hamiltonian.jl:95-104); tempering (exact path,
