@@ -1,4 +1,5 @@
-"""GPU end-to-end checks of the five BASELINE.json configurations at reduced chain counts: the sampling loop
+"""GPU end-to-end checks of the five BASELINE.json configurations at their own dimensions (C2 / C3 at their own 4096 chains,
+C4 / C5 at one GPU's share or less of the chains): the sampling loop
 (src/sampler.jl:159-248 mirror) with pooled adaptation on top of the fused transition kernels recovers the
 targets' moments.  (Trajectory-level parity with the oracle is in test_gpu_parity.py.)"""
 import numpy as np
@@ -40,7 +41,7 @@ def test_c1_static_hmc_unit_metric_d10_64_chains():
 
 def test_c2_hmcda_diag_metric_correlated_gaussian():
     """HMCDA(0.8, lambda=1) + DiagEuclideanMetric on a D=128 correlated Gaussian; shared eps from pooled dual averaging."""
-    D, N = 128, 256
+    D, N = 128, 4096
     Sigma, P = _corr_gauss(D, 7)
     h = A.Hamiltonian(A.DiagEuclideanMetric(np.diag(Sigma).copy()), A.DenseGaussian(np.zeros(D), P))
     kern = A.HMCKernel(A.Trajectory(A.EndPointTS, A.Leapfrog(0.05), A.FixedIntegrationTime(1.0)))
@@ -51,13 +52,13 @@ def test_c2_hmcda_diag_metric_correlated_gaussian():
     assert 0.6 < acc < 0.95, acc          # dual averaging steers the pooled acceptance towards delta = 0.8
     assert 0.02 < res.eps < 1.0
     X = torch.stack(res.draws).reshape(-1, D).cpu().numpy()
-    assert np.abs(X.mean(axis=0)).max() < 0.35
+    assert np.abs(X.mean(axis=0)).max() < 0.2
     ratio = X.var(axis=0) / np.diag(Sigma)
     assert 0.7 < ratio.min() and ratio.max() < 1.35
 
 
 def test_c3_nuts_diag_metric_d128():
-    D, N = 128, 512
+    D, N = 128, 4096
     s = np.exp(np.linspace(np.log(0.1), np.log(10.0), D))
     h = A.Hamiltonian(A.DiagEuclideanMetric(s * s), A.DiagGaussian(np.zeros(D), s))
     kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.25), A.GeneralisedNoUTurn()))
@@ -103,8 +104,8 @@ def test_c4_funnel_host_pooled_adaptor_small():
 
 def test_c5_nuts_dense_metric_d256():
     """NUTS + DenseEuclideanMetric (Minv = Sigma) on a D=256 correlated Gaussian: with the exact metric the
-    sampler sees an isotropic problem."""
-    D, N = 256, 64
+    sampler sees an isotropic problem (1024 chains = one GPU's share of C5's 8192)."""
+    D, N = 256, 1024
     Sigma, P = _corr_gauss(D, 11)
     h = A.Hamiltonian(A.DenseEuclideanMetric(Sigma), A.DenseGaussian(np.zeros(D), P))
     kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.4), A.GeneralisedNoUTurn()))
