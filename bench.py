@@ -331,6 +331,33 @@ def run_ours(args):
                                        "fp64_tflops": Nh * DIM * L_STEPS * 4 / msL / 1e9}
                 del zh
 
+        # ---- fixed vs marginal cost of the headline launch: the same fused L=32 launch at 4x the chains, same cold-L2 protocol.
+        # (t_16384 - t_4096) / 3 is what 4096 more chains cost once the launch is under way; the rest is launch + cold start.
+        batch = None
+        if rank == 0 and not args.no_extras:
+            with Extra("batch"):
+                Nb = 4 * N_CHAINS
+                mb_, sb_, Minvb, thb, rb = synth(Nb, DIM, SEED + 99)
+                zb = A.phasepoint(h, torch.as_tensor(thb, device=dev), torch.as_tensor(rb, device=dev))
+                planb = A.StepPlan(lf, h, zb, L_STEPS, flags=A.FLAG_ASYNC)
+                for _ in range(3):
+                    flush_l2()
+                    planb()
+                evb = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+                for a_, b_ in evb:
+                    flush_l2()
+                    a_.record(stream)
+                    planb()
+                    b_.record(stream)
+                torch.cuda.synchronize()
+                t4 = float(np.median([a_.elapsed_time(b_) for a_, b_ in evb])) * 1e3  # us
+                t1 = float(np.median(step_ms)) * 1e3
+                marg = (t4 - t1) / 3.0
+                comp = N_CHAINS * DIM * 48 + N_CHAINS * 24
+                batch = {"what": "median CUDA-event time of the fused L=32 launch at 4096 and at 16384 chains, L2 flushed before each",
+                         "us_4096": t1, "us_16384": t4, "marginal_us_per_4096_chains": marg, "fixed_us": t1 - marg,
+                         "marginal_compulsory_GBps": comp / marg / 1e3, "marginal_frac_of_hbm": comp / marg / 1e3 / hbm_peak}
+
         # ---- K2: fused static-HMC transition (refresh + 32 steps + MH) on the same batch
         k2 = None
         if rank == 0 and not args.no_extras:
@@ -616,6 +643,8 @@ def run_ours(args):
         line["roofline_hbm_honest"] = honest
     if k2:
         line["hmc_transition"] = k2
+    if batch:
+        roofline["launch_fixed_vs_marginal"] = batch
     if Extra.errors:
         line["extras_failed"] = Extra.errors
     if exchange:
