@@ -237,6 +237,150 @@ __device__ __forceinline__ void matvec(const double* __restrict__ A, int D, cons
     }
 }
 
+// CTA-cooperative form of the product for kernels that own ONE chain per warp (G = 32) and whose warps can rendezvous:
+// every warp of the block calls it at the same point with its own chain's x; the matrix is streamed from L2 into shared
+// memory ONCE per block (instead of once per warp), warp w computes rows [w R, (w+1) R), R = ceil(D / nwarps), of the
+// product for ALL the block's chains (each matrix element read from shared memory feeds nwarps FMAs), and the results
+// return through a second slab.  Shared-memory layout (doubles, from `base`): X slab [nwarps][D] | Y slab [nwarps][D] |
+// A stage [kCoopKC][D].  Warps whose chain is idle still take part (their result is ignored by the caller).
+constexpr int kCoopKC = 8;      // matrix columns per stage
+// stages of the L2 -> shared-memory pipeline (cp.async, stages - 1 chunks in flight)
+__host__ __device__ constexpr int coop_stages(int D) { return 3; }  // (6 stages at D = 256 measured slower: 2.4e9 vs 3.4e9 on C5)
+constexpr int kCoopWarps = 8;   // warps (= chains) per block of the kernels that use it
+constexpr int kCoopThreads = 32 * kCoopWarps;
+// X slab is stored TRANSPOSED, [D][kCoopWarps]: the kCoopWarps values x_c[k] of one column index are adjacent (128-bit loads)
+__host__ __device__ constexpr int coop_smem_doubles(int D) { return 2 * kCoopWarps * D + coop_stages(D) * kCoopKC * (D + 4); }
+
+// The stages hold columns with a padded leading dimension (D + 4 doubles) so that the fragment loads of the fp64 MMA below --
+// 4 columns x 8 rows per warp instruction -- fall into distinct banks.
+__host__ __device__ constexpr int coop_lds(int D) { return D + 4; }
+
+// `ncols` columns of D doubles each (contiguous in global memory) -> shared columns of leading dimension coop_lds(D);
+// `async`: 16-byte cp.async (D even, 16-byte aligned source), completed by coop_wait below
+__device__ __forceinline__ void coop_fetch(double* dst, const double* __restrict__ src, int ncols, int D, bool async) {
+    // warp w moves column w of the chunk (kCoopKC == kCoopWarps): no index arithmetic beyond a stride
+    static_assert(kCoopKC == kCoopWarps, "one column per warp");
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k >= ncols) return;
+    double* d_col = dst + k * coop_lds(D);
+    const double* s_col = src + (long long)k * D;
+#if !defined(AHMC_SIMT_EMULATION)
+    if (async) {
+        for (int d = 2 * lane; d < D; d += 64) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(d_col + d);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(s_col + d) : "memory");
+        }
+        return;
+    }
+#endif
+    for (int d = lane; d < D; d += 32) d_col[d] = __ldg(s_col + d);
+}
+__device__ __forceinline__ void coop_commit() {
+#if !defined(AHMC_SIMT_EMULATION)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void coop_wait() {  // all but the N most recent groups of this thread have landed
+#if !defined(AHMC_SIMT_EMULATION)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+// mma.sync.aligned.m8n8k4.row.col.f64 (DMMA; tcgen05 has no f64 kind): lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4)+{0,1}]
+__device__ __forceinline__ void coop_dmma(double& d0, double& d1, double a, double b) {
+#if defined(AHMC_SIMT_EMULATION)
+    double A_[32], B_[32];
+    emu_gather2(a, b, A_, B_);
+    const int lane = emu_lane(), row = lane >> 2, c0 = 2 * (lane & 3);
+    for (int k = 0; k < 4; ++k) {
+        d0 = fma(A_[row * 4 + k], B_[c0 * 4 + k], d0);
+        d1 = fma(A_[row * 4 + k], B_[(c0 + 1) * 4 + k], d1);
+    }
+#else
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#endif
+}
+
+// Y[D x 8] = A[D x D] X[D x 8] for the block's 8 chains on the fp64 tensor pipe: warp w owns the 8-row blocks w, w+8, ...;
+// per 4 columns one B fragment (the 8 chains' x) and one A fragment + one DMMA per row block.
+template <int E, int kCoopStages>
+__device__ __forceinline__ void matvec_coop_s(const double* __restrict__ A, int D, const double (&x)[E], double (&y)[E],
+                                              double* base, int l) {
+    constexpr int nw = kCoopWarps;
+    static_assert(nw == 8, "the DMMA tile has 8 columns: one per chain of the block");
+    const int w = threadIdx.x >> 5;
+    double* Xs = base;                 // [D][nw]
+    double* Ys = base + nw * D;        // [nw][D]
+    double* As = base + 2 * nw * D;    // kCoopStages x [kCoopKC][D + 4]
+    // (no barrier needed on entry: the previous call's last barrier precedes every warp's read of ITS Y rows, and X / A are
+    //  only re-written here before / after barriers every warp reaches after those reads)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int d = l + 32 * e;
+        if (d < D) Xs[d * nw + w] = x[e];
+    }
+    constexpr int RBW = (E + 1) / 2;  // row blocks per warp: ceil(D / 8) <= 4 E blocks over 8 warps
+    double acc[RBW][2];
+#pragma unroll
+    for (int i = 0; i < RBW; ++i) acc[i][0] = acc[i][1] = 0.0;
+    const int lds = coop_lds(D);
+    const int nchunks = (D + kCoopKC - 1) / kCoopKC;
+    const int stage_doubles = kCoopKC * lds;
+    // 16-byte copies: an even number of doubles per column and 16-byte aligned sources
+    const bool async = ((D & 1) == 0) && ((reinterpret_cast<unsigned long long>(A) & 15ull) == 0);
+    auto chunk_cols = [&](int c) { return (D - c * kCoopKC < kCoopKC) ? D - c * kCoopKC : kCoopKC; };
+#pragma unroll
+    for (int c = 0; c < kCoopStages - 1; ++c) {  // prologue: chunks 0 .. S-2 in flight
+        if (c < nchunks) coop_fetch(As + c * stage_doubles, A + (long long)D * c * kCoopKC, chunk_cols(c), D, async);
+        coop_commit();
+    }
+    const int fk = l & 3, fr = l >> 2;  // fragment coordinates of this lane: column within the group of 4, row within the block of 8
+    for (int c = 0; c < nchunks; ++c) {
+        coop_wait<kCoopStages - 2>();  // this thread's copies of chunk c have landed ...
+        __syncthreads();               // ... and everyone's; every warp is also done with chunk c-1 (its stage is refilled next)
+        {
+            const int cn = c + kCoopStages - 1;
+            if (cn < nchunks) coop_fetch(As + (cn % kCoopStages) * stage_doubles, A + (long long)D * cn * kCoopKC, chunk_cols(cn), D, async);
+            coop_commit();
+        }
+        const double* as = As + (c % kCoopStages) * stage_doubles;
+        const int kc = chunk_cols(c), k0 = c * kCoopKC;
+#pragma unroll
+        for (int ks = 0; ks < kCoopKC / 4; ++ks) {
+            const int kl = 4 * ks + fk;            // column of this lane inside the chunk
+            const bool kin = kl < kc;
+            const double b = kin ? Xs[(k0 + kl) * nw + fr] : 0.0;  // B[k][chain = fr]
+#pragma unroll
+            for (int i = 0; i < RBW; ++i) {
+                const int r = 8 * (w + nw * i) + fr;
+                const double av = (kin && r < D) ? as[kl * lds + r] : 0.0;
+                coop_dmma(acc[i][0], acc[i][1], av, b);
+            }
+        }
+    }
+    coop_wait<0>();
+#pragma unroll
+    for (int i = 0; i < RBW; ++i) {
+        const int r = 8 * (w + nw * i) + fr;
+        if (r < D) {
+            Ys[(2 * fk) * D + r] = acc[i][0];
+            Ys[(2 * fk + 1) * D + r] = acc[i][1];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int d = l + 32 * e;
+        y[e] = (d < D) ? Ys[w * D + d] : 0.0;
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void matvec_coop(const double* __restrict__ A, int D, const double (&x)[E], double (&y)[E],
+                                            double* base, int l) {
+    matvec_coop_s<E, coop_stages(0)>(A, D, x, y, base, l);
+}
+
 // solve U x = z (U upper triangular, column-major) for a group-distributed vector; result in x.
 // Back substitution, one pivot per iteration (metric.jl:311-320 `ldiv!(cholMinv, r)`).
 template <int G, int E>
@@ -260,6 +404,57 @@ __device__ __forceinline__ void upper_solve(const double* __restrict__ U, int D,
     }
 }
 
+// CTA-cooperative back substitution U x = z (see matvec_coop): every warp of the block solves for ITS chain, but the columns
+// of U are streamed from L2 into shared memory once per block, last chunk first, through the same cp.async stages -- the
+// per-column dependency chain then waits on shared memory (tens of cycles) instead of on L2 (hundreds): the warp-private form
+// above costs ~600 cycles x D per transition at D = 256, more than the whole tree of a short NUTS transition.
+template <int E>
+__device__ __forceinline__ void upper_solve_coop(const double* __restrict__ U, int D, double (&x)[E], double* base, int l) {
+    constexpr int kCoopStages = 3;  // (any depth <= coop_stages(D) works: the stage region is the same)
+    double* As = base + 2 * kCoopWarps * D;
+    const int nchunks = (D + kCoopKC - 1) / kCoopKC;
+    const int lds = coop_lds(D);
+    const int stage_doubles = kCoopKC * lds;
+    const bool async = ((D & 1) == 0) && ((reinterpret_cast<unsigned long long>(U) & 15ull) == 0);
+    auto chunk_cols = [&](int c) { return (D - c * kCoopKC < kCoopKC) ? D - c * kCoopKC : kCoopKC; };
+    // chunk order: j = 0 .. nchunks-1 walks the column chunks from the LAST to the first
+#pragma unroll
+    for (int j = 0; j < kCoopStages - 1; ++j) {
+        const int c = nchunks - 1 - j;
+        if (c >= 0) coop_fetch(As + j * stage_doubles, U + (long long)D * c * kCoopKC, chunk_cols(c), D, async);
+        coop_commit();
+    }
+    for (int j = 0; j < nchunks; ++j) {
+        coop_wait<kCoopStages - 2>();
+        __syncthreads();
+        {
+            const int jn = j + kCoopStages - 1, cn = nchunks - 1 - jn;
+            if (cn >= 0) coop_fetch(As + (jn % kCoopStages) * stage_doubles, U + (long long)D * cn * kCoopKC, chunk_cols(cn), D, async);
+            coop_commit();
+        }
+        const int c = nchunks - 1 - j, k0 = c * kCoopKC;
+        const double* us = As + (j % kCoopStages) * stage_doubles;
+        for (int k = chunk_cols(c) - 1; k >= 0; --k) {
+            const int i = k0 + k;
+            const double* col = us + k * lds;
+            const int le = i & 31, ee = i >> 5;
+            double xi = 0.0;
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if (e == ee) xi = x[e];
+            xi = Grp<32>::bcast(xi, le) / col[i];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int d = l + 32 * e;
+                if (d == i) x[e] = xi;
+                else if (d < i) x[e] = fma(-col[d], xi, x[e]);
+            }
+        }
+    }
+    coop_wait<0>();
+    __syncthreads();  // the stages may be refilled by the next cooperative call
+}
+
 // ------------------------------------------------------------------------------------------------
 // metric:  dH/dr and the kinetic lane-partial  sum_e r_e * (dH/dr)_e   (neg_energy = -sum/2)
 // ------------------------------------------------------------------------------------------------
@@ -269,9 +464,11 @@ struct MetricOps {
     const double* A; // Dense only
     const double* U;
     int D;
+    double* coop;    // non-null: dense products are CTA-cooperative through this shared-memory region (matvec_coop)
 
     __device__ __forceinline__ void load(const MetricDev& m, long long chain, int l, int D_) {
         D = D_;
+        coop = nullptr;
         A = m.Minv;
         U = m.cholU;
         if (METRIC == AHMC_METRIC_DIAG) {
@@ -287,7 +484,8 @@ struct MetricOps {
 #pragma unroll
             for (int e = 0; e < E; ++e) dr[e] = Minv[e] * r[e];
         } else {
-            matvec<G, E>(A, D, r, dr, xs, l);
+            if (G == 32 && coop) matvec_coop<E>(A, D, r, dr, coop, l);
+            else matvec<G, E>(A, D, r, dr, xs, l);
         }
     }
     // r from standard normals z (metric.jl:290-320)
@@ -299,7 +497,8 @@ struct MetricOps {
                 r[e] = (d < D) ? r[e] / sqrt(Minv[e]) : 0.0;
             }
         } else if (METRIC == AHMC_METRIC_DENSE) {
-            upper_solve<G, E>(U, D, r, l);
+            if (G == 32 && coop) upper_solve_coop<E>(U, D, r, coop, l);
+            else upper_solve<G, E>(U, D, r, l);
         }
     }
 };
@@ -314,9 +513,11 @@ struct ModelOps {
     const double* P;
     double c0;
     int D;
+    double* coop;  // see MetricOps
 
     __device__ __forceinline__ void load(const ModelDev& md, int l, int D_) {
         D = D_;
+        coop = nullptr;
         c0 = md.c0;
         P = md.p1;
         if (MODEL == AHMC_MODEL_DIAG_GAUSS) {
@@ -350,7 +551,8 @@ struct ModelOps {
             double diff[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) diff[e] = th[e] - m[e];
-            matvec<G, E>(P, D, diff, g, xs, l);
+            if (G == 32 && coop) matvec_coop<E>(P, D, diff, g, coop, l);
+            else matvec<G, E>(P, D, diff, g, xs, l);
 #pragma unroll
             for (int e = 0; e < E; ++e) part = fma(diff[e], g[e], part);
             return fma(-0.5, Grp<G>::sum(part), c0);

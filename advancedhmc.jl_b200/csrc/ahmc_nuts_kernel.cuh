@@ -59,7 +59,7 @@ constexpr int kLevelScalars = 7;  // lw (m), sum_alpha, n_alpha, dH_max, cand lp
 //     combine, NO log / log1p anywhere in the tree walk (same events; oracle/nuts_iterative.py max_weights);
 //   * the acceptance statistic sum_alpha = sum over leaves of exp(min(0, -dH)) is order-free: a leaf parks dH in one
 //     lane's register and the exponentials are taken G at a time, one per lane;
-//   * FULL = true: the instantiation for D == G * E (64, 128, 256) in which D is a compile-time constant -- the `d < D`
+//   * FULLTILE = true: the instantiation for D == G * E (64, 128, 256) in which D is a compile-time constant -- the `d < D`
 //     guard of every vector load / store and most of the workspace address arithmetic fold away.
 
 // Occupancy: the tree walk is a long chain of dependent, mostly fixed-latency instructions, so throughput scales with
@@ -70,8 +70,23 @@ constexpr int nuts_min_blocks() { return E <= 4 ? 3 : (E <= 8 ? 2 : 1); }
 // VAR = false: MultinomialTS + GeneralisedNoUTurn only (what `NUTS(delta)` builds); VAR = true additionally compiles
 // SliceTS (trajectory.jl:102-109,144-145,164-166,178-189,202,500-502) and the Classic / StrictGeneralised criteria
 // (trajectory.jl:551-557, 579-613), selected at run time by a.sampler / a.criterion.
-template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT, bool FULL>
-__global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kernel(const NutsArgs a) {
+//
+// COOP = true (dense operators, one chain per warp, default family): the block has kCoopWarps warps and every D x D product
+// (dH/dr with a Dense metric, grad lp of a dense Gaussian) is a CTA-wide rendezvous -- the matrix is streamed from L2 into
+// shared memory once per BLOCK and each element feeds kCoopWarps FMAs (matvec_coop, ahmc_device.cuh) instead of every warp
+// re-reading the whole matrix from L2 for its own chain (1.5 MB per leaf per chain at D = 256: the r01 kernel was L2-bound).
+// All warps of a block must then reach the product sites together: the votes that steer the loop around them are block-wide,
+// and a warp whose chain is idle or finished keeps taking part (its results are ignored, like idle groups of a warp).
+// (the tile flag must not be called FULL: that is the namespace's all-lanes mask used by every *_sync below)
+template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT, bool FULLTILE, bool COOP = false>
+__global__ void __launch_bounds__(COOP ? kCoopThreads : kBlockThreads, COOP ? 1 : nuts_min_blocks<E>()) nuts_kernel(const NutsArgs a) {
+    static_assert(!COOP || (G == 32 && !VAR), "COOP: one chain per warp, default family");
+    constexpr int kThreads = COOP ? kCoopThreads : kBlockThreads;
+    // warp-uniform predicate -> uniform over everything that must stay in step (the warp, or the block when COOP)
+    auto any_peer = [](bool p) -> bool {
+        if constexpr (COOP) return __syncthreads_or(p ? 1 : 0) != 0;
+        else return __any_sync(FULL, p);
+    };
     // Dense metric: a merge needs dH/dr = M^-1 r of the pending half's first leaf -- a D x D product.  The default family
     // caches the vector (slot 1 of the level holds M^-1 r_first instead of r_first) so merges do no dense product at all.
     constexpr bool STORE_DR = !VAR && METRIC == AHMC_METRIC_DENSE;
@@ -81,16 +96,16 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     extern __shared__ double smem[];
     const int l = threadIdx.x % G;
     const int grp_in_block = threadIdx.x / G;
-    constexpr int kGroups = kBlockThreads / G;
+    constexpr int kGroups = kThreads / G;
     const long long chain0 = (long long)blockIdx.x * kGroups + grp_in_block;
     const bool valid = chain0 < a.N;
     const long long chain = valid ? chain0 : a.N - 1;
-    const int D = FULL ? G * E : a.D;
+    const int D = FULLTILE ? G * E : a.D;
     const bool dense = (MODEL == AHMC_MODEL_DENSE_GAUSS) || (METRIC == AHMC_METRIC_DENSE) || (MODEL == AHMC_MODEL_USER);
     constexpr int kSlab = slab_vectors<MODEL>();
-    double* xs = smem + (size_t)grp_in_block * kSlab * D;  // dense / user-target slab (unused otherwise)
+    double* xs = COOP ? smem : smem + (size_t)grp_in_block * kSlab * D;  // dense / user-target slab (unused otherwise)
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
-    double* lv = smem + (dense ? (size_t)kGroups * kSlab * D : 0) +
+    double* lv = smem + (COOP ? (size_t)coop_smem_doubles(D) : dense ? (size_t)kGroups * kSlab * D : 0) +
                  (size_t)grp_in_block * maxd * kLevelScalars;
     double* LW = lv;
     double* SA = lv + maxd;
@@ -118,6 +133,10 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
     MetricOps<METRIC, G, E> me;
     mo.load(a.model, l, D);
     me.load(a.metric, chain, l, D);
+    if constexpr (COOP) {
+        mo.coop = smem;
+        me.coop = smem;
+    }
 
     int nexp = 0, ndir = 0;
     uint64_t off = a.rng.offset;  // Philox transition counter of the transition this group is working on
@@ -198,7 +217,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         // ---------------------------------------------------------------- (I) begin a transition:
         // z0 = refresh (sampler.jl:55; hamiltonian.jl:213-220) with the cached lp / gradient;
         // tree = BinaryTree(z0, z0, rho = z0.r, 0, 0, 0); sampler = MultinomialTS(z0, lw = 0) (:682-688, :155)
-        if (__any_sync(FULL, need_init)) {
+        if (any_peer(need_init)) {
             const bool first = (t == 0);
             double rn[E], drn[E];
             if (need_init) {
@@ -373,7 +392,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 else finished = true;
             }
         }
-        if (__any_sync(FULL, need_init)) continue;
+        if (any_peer(need_init)) continue;
 
         // ---------------------------------------------------------------- (A) start a doubling (:691-706)
         const bool start = !finished && !done && !in_sub;
@@ -390,7 +409,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
                 in_sub = true;
             }
         }
-        if (!__any_sync(FULL, in_sub)) break;
+        if (!any_peer(in_sub)) break;
 
         // ---------------------------------------------------------------- (B) one leaf (:638-647)
         leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, v > 0 ? eps_c : -eps_c, dr, xs, l);
@@ -615,7 +634,7 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
         }
 
         // ---------------------------------------------------------------- (D) subtree complete (:707-722)
-        if (__any_sync(FULL, complete)) {
+        if (any_peer(complete)) {
             const bool sub_term = tnum_c || tdyn_c;
             bool accept = false;
             const double u_top = peek_u();
@@ -759,29 +778,47 @@ __global__ void __launch_bounds__(kBlockThreads, nuts_min_blocks<E>()) nuts_kern
 #if !defined(AHMC_SIMT_EMULATION) && !defined(__CUDACC_RTC__)  // host launch code (skipped by the CPU SIMT emulation harness and by NVRTC)
 template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
 static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
-    const int chains_per_block = kBlockThreads / G;
-    const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
-    size_t sm = smem_bytes(MODEL, METRIC, a.D, G) +
-                (size_t)chains_per_block * maxd * kLevelScalars * sizeof(double);
-    if constexpr (G == 32 && E >= 2 && E <= 8) {
-      if (a.D == G * E) {  // full tile: compile-time D
+    constexpr bool kDenseOps = MODEL == AHMC_MODEL_DENSE_GAUSS || METRIC == AHMC_METRIC_DENSE;
+    if constexpr (kDenseOps && G == 32 && !VAR) {
+        // dense operators, one chain per warp: blocks of kCoopWarps chains share every D x D product (COOP form)
+        const long long blocks = (a.N + kCoopWarps - 1) / kCoopWarps;
+        const size_t sm = ((size_t)coop_smem_doubles(a.D) + (size_t)kCoopWarps * maxd * kLevelScalars) * sizeof(double);
+        auto go = [&](auto kernel) -> cudaError_t {
+            if (sm > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                if (e != cudaSuccess) return e;
+            }
+            kernel<<<(unsigned)blocks, kCoopThreads, sm, st>>>(a);
+            return cudaGetLastError();
+        };
+        if constexpr (E >= 2 && E <= 8) {
+            if (a.D == G * E) return go(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true, true>);
+        }
+        return go(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, false, true>);
+    } else {
+        const int chains_per_block = kBlockThreads / G;
+        const long long blocks = (a.N + chains_per_block - 1) / chains_per_block;
+        size_t sm = smem_bytes(MODEL, METRIC, a.D, G) + (size_t)chains_per_block * maxd * kLevelScalars * sizeof(double);
+        if constexpr (G == 32 && E >= 2 && E <= 8) {
+            if (a.D == G * E) {  // full tile: compile-time D
+                if (sm > 48 * 1024) {
+                    cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true>,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                    if (e != cudaSuccess) return e;
+                }
+                nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+                return cudaGetLastError();
+            }
+        }
         if (sm > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true>,
+            cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, false>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             if (e != cudaSuccess) return e;
         }
-        nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
+        nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, false><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
         return cudaGetLastError();
-      }
     }
-    if (sm > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-    }
-    nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, false><<<(unsigned)blocks, kBlockThreads, sm, st>>>(a);
-    return cudaGetLastError();
 }
 
 template <int MODEL, int METRIC, bool VAR, bool ADAPT>

@@ -89,5 +89,6 @@ inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return emu_reduce
 
 // ---- block-level primitives
 void __syncthreads();
+int __syncthreads_or(int pred);
 inline void __threadfence() {}
 unsigned atomicAdd(unsigned* addr, unsigned v);

@@ -48,8 +48,17 @@ struct EmuNuts {
 };
 
 template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
+static constexpr bool coop_form() {  // like launch_nuts_v: dense operators, one chain per warp, default family
+    return (MODEL == AHMC_MODEL_DENSE_GAUSS || METRIC == AHMC_METRIC_DENSE) && G == 32 && !VAR;
+}
+template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
 static void thunk(const void* p) {
     const NutsArgs& a = *static_cast<const NutsArgs*>(p);
+    if constexpr (coop_form<MODEL, METRIC, G, E, VAR, ADAPT>()) {
+        if (E >= 2 && E <= 8 && a.D == G * E) nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true, true>(a);
+        else nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, false, true>(a);
+        return;
+    }
     if (G == 32 && E >= 2 && E <= 8 && a.D == G * E) {  // the full-tile instantiation (D a compile-time constant), like launch_nuts_v
         nuts_kernel<MODEL, METRIC, G, E, VAR, ADAPT, true>(a);
         return;
@@ -78,6 +87,10 @@ static KernelFn by_model(int model, int metric, int G, int E) {
     if (!ADAPT) {
         if (model == AHMC_MODEL_DENSE_GAUSS && metric == AHMC_METRIC_DENSE) return by_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DENSE, VAR, false>(G, E);
         if (model == AHMC_MODEL_DIAG_GAUSS && metric == AHMC_METRIC_UNIT) return by_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_UNIT, VAR, false>(G, E);
+        if (!VAR) {  // the other two dense-operator combinations of the COOP form
+            if (model == AHMC_MODEL_DENSE_GAUSS && metric == AHMC_METRIC_DIAG) return by_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DIAG, false, false>(G, E);
+            if (model == AHMC_MODEL_DIAG_GAUSS && metric == AHMC_METRIC_DENSE) return by_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DENSE, false, false>(G, E);
+        }
     }
     return nullptr;
 }
@@ -150,8 +163,11 @@ extern "C" int emu_nuts(const EmuNuts* q) {
                            : (var ? by_model<true, false>(q->model_kind, q->metric_kind, G, E)
                                   : by_model<false, false>(q->model_kind, q->metric_kind, G, E));
     if (!fn) return -2;
-    const int chains_per_block = kBlockThreads / G;
+    const bool dense_ops = q->model_kind == AHMC_MODEL_DENSE_GAUSS || q->metric_kind == AHMC_METRIC_DENSE;
+    const bool coop = dense_ops && G == 32 && !var;  // blocks of kCoopWarps chains sharing the D x D products
+    const int threads = coop ? kCoopThreads : kBlockThreads;
+    const int chains_per_block = threads / G;
     const int blocks = (int)((q->N + chains_per_block - 1) / chains_per_block);
-    emu_launch(fn, &a, blocks, kBlockThreads);
+    emu_launch(fn, &a, blocks, threads);
     return 0;
 }

@@ -28,6 +28,16 @@ thread_local pthread_barrier_t* tls_block_bar = nullptr;
 }  // namespace
 
 void __syncthreads() { pthread_barrier_wait(tls_block_bar); }
+static std::atomic<int> g_block_or{0};  // blocks run one at a time
+int __syncthreads_or(int pred) {
+    if (pred) g_block_or.store(1);
+    pthread_barrier_wait(tls_block_bar);
+    const int r = g_block_or.load();
+    pthread_barrier_wait(tls_block_bar);
+    if (threadIdx.x == 0) g_block_or.store(0);
+    pthread_barrier_wait(tls_block_bar);
+    return r;
+}
 unsigned atomicAdd(unsigned* addr, unsigned v) { return std::atomic_ref<unsigned>(*addr).fetch_add(v); }
 
 int emu_lane() { return tls_lane; }

@@ -242,8 +242,8 @@ def test_argument_errors_like_the_reference():
     with pytest.raises(ValueError):
         A.phasepoint(A.Hamiltonian(A.UnitEuclideanMetric(D), A.StdNormal(D)), th, torch.zeros((N, D + 1), dtype=torch.float64, device=DEV))
     big = torch.zeros((2, 513), dtype=torch.float64, device=DEV)
-    with pytest.raises(A.AhmcError, match="register-resident"):
-        A.phasepoint(A.Hamiltonian(A.UnitEuclideanMetric(513), A.StdNormal(513)), big, big.clone())
+    with pytest.raises(A.AhmcError, match="register-resident"):  # beyond 512 dimensions only the streaming combinations exist
+        A.phasepoint(A.Hamiltonian(A.DenseEuclideanMetric(np.eye(513)), A.StdNormal(513)), big, big.clone())
 
 
 # ------------------------------------------------------------------------------------------------ properties at scale

@@ -114,7 +114,10 @@ CASES = [
     ("diag_gauss", "unit", 5, 7, 0.3, "slice", "classic"),
     ("diag_gauss", "diag", 13, 5, 0.25, "multinomial", "generalised"),  # G=16: two chains per warp
     ("diag_gauss", "diag", 128, 2, 0.12, "multinomial", "generalised"),  # G=32, E=4: the headline layout
-    ("dense_gauss", "dense", 200, 1, 0.25, "multinomial", "generalised"),  # G=32, E=8 + dense slab: C5's layout
+    ("dense_gauss", "dense", 200, 1, 0.25, "multinomial", "generalised"),  # G=32, E=8: C5's layout; COOP block with 7 idle warps
+    ("dense_gauss", "dense", 40, 11, 0.3, "multinomial", "generalised"),   # COOP: a full block of 8 chains + a ragged one of 3
+    ("dense_gauss", "diag", 64, 9, 0.3, "multinomial", "generalised"),     # COOP, full tile (E=2), dense target only
+    ("diag_gauss", "dense", 33, 5, 0.3, "multinomial", "generalised"),     # COOP, dense metric only
 ]
 
 
@@ -648,7 +651,7 @@ def test_kernel_sources_are_data_race_free_under_thread_sanitizer(_race_bins, na
         assert races > 0 and "dense_traj_kernel" in r.stderr
     else:
         assert races == 0 and r.returncode == 0, r.stderr[-3000:] + r.stdout[-500:]
-        assert r.stdout.count("rc 0") == {"nuts": 7, "lf": 5, "dense": 4, "multinomial": 3, "adapt": 1}[name.split("-")[0]]
+        assert r.stdout.count("rc 0") == {"nuts": 8, "lf": 5, "dense": 4, "multinomial": 3, "adapt": 1}[name.split("-")[0]]
 
 
 def test_host_window_schedule_of_the_in_launch_adaptation_equals_the_oracle(emu):
