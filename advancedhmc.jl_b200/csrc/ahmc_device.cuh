@@ -243,13 +243,15 @@ __device__ __forceinline__ void matvec(const double* __restrict__ A, int D, cons
 // product for ALL the block's chains (each matrix element read from shared memory feeds nwarps FMAs), and the results
 // return through a second slab.  Shared-memory layout (doubles, from `base`): X slab [nwarps][D] | Y slab [nwarps][D] |
 // A stage [kCoopKC][D].  Warps whose chain is idle still take part (their result is ignored by the caller).
-constexpr int kCoopKC = 8;      // matrix columns per stage
+constexpr int kCoopKCMax = 16;
+// matrix columns per stage: 16 where three stages fit in shared memory beside the slabs (one barrier per 16 columns), else 8
+__host__ __device__ constexpr int coop_kc(int D) { return D <= 256 ? 16 : 8; }
 // stages of the L2 -> shared-memory pipeline (cp.async, stages - 1 chunks in flight)
 __host__ __device__ constexpr int coop_stages(int D) { return 3; }  // (6 stages at D = 256 measured slower: 2.4e9 vs 3.4e9 on C5)
 constexpr int kCoopWarps = 8;   // warps (= chains) per block of the kernels that use it
 constexpr int kCoopThreads = 32 * kCoopWarps;
 // X slab is stored TRANSPOSED, [D][kCoopWarps]: the kCoopWarps values x_c[k] of one column index are adjacent (128-bit loads)
-__host__ __device__ constexpr int coop_smem_doubles(int D) { return 2 * kCoopWarps * D + coop_stages(D) * kCoopKC * (D + 4); }
+__host__ __device__ constexpr int coop_smem_doubles(int D) { return 2 * kCoopWarps * D + coop_stages(D) * coop_kc(D) * (D + 4); }
 
 // The stages hold columns with a padded leading dimension (D + 4 doubles) so that the fragment loads of the fp64 MMA below --
 // 4 columns x 8 rows per warp instruction -- fall into distinct banks.
@@ -258,22 +260,22 @@ __host__ __device__ constexpr int coop_lds(int D) { return D + 4; }
 // `ncols` columns of D doubles each (contiguous in global memory) -> shared columns of leading dimension coop_lds(D);
 // `async`: 16-byte cp.async (D even, 16-byte aligned source), completed by coop_wait below
 __device__ __forceinline__ void coop_fetch(double* dst, const double* __restrict__ src, int ncols, int D, bool async) {
-    // warp w moves column w of the chunk (kCoopKC == kCoopWarps): no index arithmetic beyond a stride
-    static_assert(kCoopKC == kCoopWarps, "one column per warp");
-    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (k >= ncols) return;
-    double* d_col = dst + k * coop_lds(D);
-    const double* s_col = src + (long long)k * D;
+    // warp w moves columns w, w + 8, ... of the chunk: no index arithmetic beyond strides
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x >> 5; k < ncols; k += kCoopWarps) {
+        double* d_col = dst + k * coop_lds(D);
+        const double* s_col = src + (long long)k * D;
 #if !defined(AHMC_SIMT_EMULATION)
-    if (async) {
-        for (int d = 2 * lane; d < D; d += 64) {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(d_col + d);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(s_col + d) : "memory");
+        if (async) {
+            for (int d = 2 * lane; d < D; d += 64) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(d_col + d);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(s_col + d) : "memory");
+            }
+            continue;
         }
-        return;
-    }
 #endif
-    for (int d = lane; d < D; d += 32) d_col[d] = __ldg(s_col + d);
+        for (int d = lane; d < D; d += 32) d_col[d] = __ldg(s_col + d);
+    }
 }
 __device__ __forceinline__ void coop_commit() {
 #if !defined(AHMC_SIMT_EMULATION)
@@ -311,7 +313,7 @@ __device__ __forceinline__ void matvec_coop_s(const double* __restrict__ A, int 
     const int w = threadIdx.x >> 5;
     double* Xs = base;                 // [D][nw]
     double* Ys = base + nw * D;        // [nw][D]
-    double* As = base + 2 * nw * D;    // kCoopStages x [kCoopKC][D + 4]
+    double* As = base + 2 * nw * D;    // kCoopStages x [coop_kc(D)][D + 4]
     // (no barrier needed on entry: the previous call's last barrier precedes every warp's read of ITS Y rows, and X / A are
     //  only re-written here before / after barriers every warp reaches after those reads)
 #pragma unroll
@@ -324,6 +326,7 @@ __device__ __forceinline__ void matvec_coop_s(const double* __restrict__ A, int 
 #pragma unroll
     for (int i = 0; i < RBW; ++i) acc[i][0] = acc[i][1] = 0.0;
     const int lds = coop_lds(D);
+    const int kCoopKC = coop_kc(D);
     const int nchunks = (D + kCoopKC - 1) / kCoopKC;
     const int stage_doubles = kCoopKC * lds;
     // 16-byte copies: an even number of doubles per column and 16-byte aligned sources
@@ -345,7 +348,6 @@ __device__ __forceinline__ void matvec_coop_s(const double* __restrict__ A, int 
         }
         const double* as = As + (c % kCoopStages) * stage_doubles;
         const int kc = chunk_cols(c), k0 = c * kCoopKC;
-#pragma unroll
         for (int ks = 0; ks < kCoopKC / 4; ++ks) {
             const int kl = 4 * ks + fk;            // column of this lane inside the chunk
             const bool kin = kl < kc;
@@ -412,6 +414,7 @@ template <int E>
 __device__ __forceinline__ void upper_solve_coop(const double* __restrict__ U, int D, double (&x)[E], double* base, int l) {
     constexpr int kCoopStages = 3;  // (any depth <= coop_stages(D) works: the stage region is the same)
     double* As = base + 2 * kCoopWarps * D;
+    const int kCoopKC = coop_kc(D);
     const int nchunks = (D + kCoopKC - 1) / kCoopKC;
     const int lds = coop_lds(D);
     const int stage_doubles = kCoopKC * lds;
