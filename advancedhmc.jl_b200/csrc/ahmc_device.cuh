@@ -244,8 +244,8 @@ __device__ __forceinline__ void matvec(const double* __restrict__ A, int D, cons
 // return through a second slab.  Shared-memory layout (doubles, from `base`): X slab [nwarps][D] | Y slab [nwarps][D] |
 // A stage [kCoopKC][D].  Warps whose chain is idle still take part (their result is ignored by the caller).
 constexpr int kCoopKCMax = 16;
-// matrix columns per stage: 16 where three stages fit in shared memory beside the slabs (one barrier per 16 columns), else 8
-__host__ __device__ constexpr int coop_kc(int D) { return D <= 256 ? 16 : 8; }
+// matrix columns per stage
+__host__ __device__ constexpr int coop_kc(int D) { return 8; }  // (16 at D <= 256 measured the same: 4.4e9 on C5)
 // stages of the L2 -> shared-memory pipeline (cp.async, stages - 1 chunks in flight)
 __host__ __device__ constexpr int coop_stages(int D) { return 3; }  // (6 stages at D = 256 measured slower: 2.4e9 vs 3.4e9 on C5)
 constexpr int kCoopWarps = 8;   // warps (= chains) per block of the kernels that use it
