@@ -39,7 +39,7 @@ class Stats(C.Structure):
 class Rng(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("offset", C.c_uint64), ("normal_tape", _vp), ("exp_tape", _vp),
                 ("exp_stride", C.c_int64), ("dir_tape", _vp), ("dir_stride", C.c_int64),
-                ("partial_refresh_alpha", C.c_double)]
+                ("partial_refresh_alpha", C.c_double), ("temper_alpha", C.c_double)]
 
 
 class AdaptCfg(C.Structure):

@@ -553,7 +553,10 @@ def sample_pooled_device(rng, h: A.Hamiltonian, kappa: A.HMCKernel, theta, n_sam
     Minv0 = h.metric.Minv if A._is_host(h.metric.Minv) else h.metric.Minv.detach().cpu().numpy()
     ad = PooledDeviceAdaptor(dev.index or 0, D, N, n_adapts, eps0, delta, adapt_metric, *windows, Minv0=Minv0)
     hd = A.Hamiltonian(A.DiagEuclideanMetric(ad.Minv), h.target)
-    kd = A.HMCKernel(A.Trajectory(tau.sampler, A.Leapfrog(ad.eps), tau.termination_criterion), kappa.refreshment)
+    if isinstance(tau.integrator, A.JitteredLeapfrog):
+        raise A.L.AhmcError(A.L.ERR_UNSUPPORTED, "JitteredLeapfrog draws its step size on the host; use sample()")
+    lf_d = A.TemperedLeapfrog(ad.eps, tau.integrator.alpha) if isinstance(tau.integrator, A.TemperedLeapfrog) else A.Leapfrog(ad.eps)
+    kd = A.HMCKernel(A.Trajectory(tau.sampler, lf_d, tau.termination_criterion), kappa.refreshment)
     z = A.phasepoint(hd, theta, torch.zeros_like(theta))
     acc, nerr, nst = [], [], []
     t0 = time.perf_counter()

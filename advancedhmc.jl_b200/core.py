@@ -780,6 +780,10 @@ def _refresh_alpha(kappa) -> float:
     return float(r.alpha) if isinstance(r, PartialMomentumRefreshment) else 0.0
 
 
+def _temper_alpha(lf) -> float:
+    return float(lf.alpha) if isinstance(lf, TemperedLeapfrog) else 0.0
+
+
 @dataclass(frozen=True)
 class HMCKernel:
     """trajectory.jl:249-254."""
@@ -844,12 +848,10 @@ def transition(rng, h: Hamiltonian, kappa: Union[HMCKernel, Trajectory], z: Phas
         # transition, derived from the nominal one (so a dual-averaging update of eps0 takes effect).  The jitter uniforms
         # come from a host generator keyed by the transition's own rng state.
         lf = jitter(_jitter_generator(rng), lf)
-    if isinstance(lf, TemperedLeapfrog):
-        raise L.AhmcError(L.ERR_UNSUPPORTED, "TemperedLeapfrog inside a fused transition is not built (the transition kernels "
-                                              "run plain leapfrog); use step() for tempered trajectories")
     e, ep, keep2 = _eps_args(step_size(lf), z.theta, N)
     rc, keep3 = rng._c()
     rc.partial_refresh_alpha = _refresh_alpha(kappa)
+    rc.temper_alpha = _temper_alpha(lf)  # TemperedLeapfrog: every `step` of the transition tempers by its own n_steps
     tc = tau.termination_criterion
     nuts = isinstance(tc, _DYNAMIC)
     st, sc = _stats_buffers(z.theta, N, nuts or tau.sampler is MultinomialTS)
@@ -956,16 +958,16 @@ def sample_transitions(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: Phas
     out = _empty_pp(z.theta, with_lk_gradient=False)
     md, keep = h.metric._desc(D, N, z.theta)
     lf = tau.integrator
-    if type(lf) is not Leapfrog:
-        raise L.AhmcError(L.ERR_UNSUPPORTED, "multi-transition launches run plain Leapfrog (a JitteredLeapfrog draws a new step "
-                                              "size per transition on the host, a TemperedLeapfrog is not fused): loop over transition()")
+    if type(lf) not in (Leapfrog, TemperedLeapfrog):
+        raise L.AhmcError(L.ERR_UNSUPPORTED, "multi-transition launches run Leapfrog / TemperedLeapfrog (a JitteredLeapfrog draws a new "
+                                              "step size per transition on the host): loop over transition()")
     tc = tau.termination_criterion
     nuts = isinstance(tc, _DYNAMIC)
     if not nuts and tau.sampler is not EndPointTS:
         raise L.AhmcError(L.ERR_UNSUPPORTED, "multi-transition static launches implement EndPointTS (Metropolis end point); a static "
                                               "MultinomialTS trajectory needs one shared direction draw per transition: loop over transition()")
     e, ep, keep2 = _eps_args(step_size(lf), z.theta, N)
-    rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0, _refresh_alpha(kappa))
+    rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0, _refresh_alpha(kappa), _temper_alpha(kappa.tau.integrator))
     rng.offset += n_transitions
     st, sc = _stats_buffers(z.theta, N, nuts, T=n_transitions)
     draws = _like(z.theta, (n_transitions, N, D)) if keep_draws else None
@@ -1030,7 +1032,7 @@ def nuts_adapt_sample(rng: PhiloxRNG, h: Hamiltonian, kappa: HMCKernel, z: Phase
     cfg = L.AdaptCfg(n_adapts, adaptor.init_buffer, adaptor.term_buffer, adaptor.window_size, adaptor.delta, adaptor.gamma,
                      adaptor.t0, adaptor.kappa, 1 if adaptor.adapt_metric else 0, adaptor.n_min, _ptr(eps), _ptr(minv),
                      _ptr(trace))
-    rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0, _refresh_alpha(kappa))
+    rc = L.Rng(rng.seed, rng.offset, None, None, 0, None, 0, _refresh_alpha(kappa), _temper_alpha(kappa.tau.integrator))
     rng.offset += n_transitions
     tc = tau.termination_criterion
     st, sc = _stats_buffers(z.theta, N, True, T=n_transitions)

@@ -1170,6 +1170,7 @@ static int stage_rng(Stager& st, const ahmc_rng* r, int32_t D, int64_t N, bool n
     d->seed = r->seed;
     d->offset = r->offset;
     d->partial_alpha = r->partial_refresh_alpha;
+    d->temper_alpha = r->temper_alpha > 0.0 ? r->temper_alpha : 0.0;
     d->exp_stride = nuts ? r->exp_stride : 1;
     d->dir_stride = r->dir_stride;
     int rc;
@@ -1193,6 +1194,8 @@ static int hmc_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* m
         return fail(ctx, AHMC_ERR_UNSUPPORTED, "partial momentum refreshment is not wired into the split-step path");
     if (!(rng->partial_refresh_alpha > -1.0 && rng->partial_refresh_alpha < 1.0))
         return fail(ctx, AHMC_ERR_INVALID, "partial_refresh_alpha must be in (-1, 1)");
+    if (!(rng->temper_alpha >= 0.0) || std::isinf(rng->temper_alpha))
+        return fail(ctx, AHMC_ERR_INVALID, "temper_alpha must be 0 (plain Leapfrog) or a finite alpha > 0 (TemperedLeapfrog)");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
@@ -1272,7 +1275,7 @@ static int hmc_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* m
         CU(cp(a.th_out, a.th_in, a.ld_in));
         CU(cp(a.g_out, a.g_in, a.ld_in));
         CU(cp(a.r_out, w.r0, D));
-        rc = split_trajectory(ctx, model, a.metric, D, N, eps, a.eps_chain, n_steps, 1, 0.0, a.th_out, a.r_out, a.g_out,
+        rc = split_trajectory(ctx, model, a.metric, D, N, eps, a.eps_chain, n_steps, 1, h.rng.temper_alpha, a.th_out, a.r_out, a.g_out,
                               a.lp_out, a.lk_out, nullptr, a.ld_out, w.status, w.steps, w, false, &nl);
         if (rc) return rc;
         MhArgs m{};
@@ -1285,7 +1288,7 @@ static int hmc_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* m
         ctx->launches += nl;
         return finish_call(ctx, st, flags);
     }
-    if (n_transitions == 1 && a.th_out != a.th_in && h.rng.partial_alpha == 0.0 && !draws &&
+    if (n_transitions == 1 && a.th_out != a.th_in && h.rng.partial_alpha == 0.0 && !(h.rng.temper_alpha > 0.0) && !draws &&
         (model->kind == AHMC_MODEL_DENSE_GAUSS || a.metric.kind == AHMC_METRIC_DENSE)) {
         // GEMM-shaped operators: refresh -> tiled DMMA trajectory (in place on z_out) -> MH select; same semantics as
         // hmc_kernel.  (Falls through to the fused generic kernel when the tile kernel is not eligible.)
@@ -1365,6 +1368,8 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
         return fail(ctx, AHMC_ERR_INVALID, "random tapes describe ONE transition; multi-transition sampling uses the Philox streams");
     if (!(rng->partial_refresh_alpha > -1.0 && rng->partial_refresh_alpha < 1.0))
         return fail(ctx, AHMC_ERR_INVALID, "partial_refresh_alpha must be in (-1, 1)");
+    if (!(rng->temper_alpha >= 0.0) || std::isinf(rng->temper_alpha))
+        return fail(ctx, AHMC_ERR_INVALID, "temper_alpha must be 0 (plain Leapfrog) or a finite alpha > 0 (TemperedLeapfrog)");
     int rc = check_common(ctx, model, metric, D, N);
     if (rc) return rc;
     if ((rc = check_pp(ctx, z_in, D, "z_in", true, N))) return rc;
@@ -1532,6 +1537,8 @@ int ahmc_hmc_multinomial_transition_f64(ahmc_ctx* ctx, const ahmc_model* model, 
         return fail(ctx, AHMC_ERR_UNSUPPORTED, "transition entry points do not emit lk_gradient; call ahmc_phasepoint_f64 if needed");
     if (!(rng->partial_refresh_alpha > -1.0 && rng->partial_refresh_alpha < 1.0))
         return fail(ctx, AHMC_ERR_INVALID, "partial_refresh_alpha must be in (-1, 1)");
+    if (!(rng->temper_alpha >= 0.0) || std::isinf(rng->temper_alpha))
+        return fail(ctx, AHMC_ERR_INVALID, "temper_alpha must be 0 (plain Leapfrog) or a finite alpha > 0 (TemperedLeapfrog)");
     if (N == 0) return AHMC_OK;
     DeviceGuard g(ctx->device);
     Stager st(ctx, flags & AHMC_FLAG_HOST_BUFFERS);

@@ -533,7 +533,22 @@ struct ModelOps {
         }
     }
 
+    // true: eval_part already returns the finished log pi on every lane (the model needs its own collective anyway);
+    // false: it returns this lane's partial sum and log pi = finish(Grp::sum(partial)).
+#if defined(AHMC_NVRTC_USER_MODEL) && defined(AHMC_USER_COORDWISE)
+    static constexpr bool kLpReduced = MODEL == AHMC_MODEL_FUNNEL;
+#else
+    static constexpr bool kLpReduced = MODEL == AHMC_MODEL_FUNNEL || MODEL == AHMC_MODEL_USER;
+#endif
+    __device__ __forceinline__ double finish(double part_sum) const {
+        return MODEL == AHMC_MODEL_USER ? part_sum + c0 : fma(-0.5, part_sum, c0);
+    }
     __device__ __forceinline__ double eval(const double (&th)[E], double (&g)[E], double* xs, int l) const {
+        const double v = eval_part(th, g, xs, l);
+        if constexpr (kLpReduced) return v;
+        else return finish(Grp<G>::sum(v));
+    }
+    __device__ __forceinline__ double eval_part(const double (&th)[E], double (&g)[E], double* xs, int l) const {
         double part = 0.0;
         if (MODEL == AHMC_MODEL_STD_NORMAL) {
 #pragma unroll
@@ -541,7 +556,7 @@ struct ModelOps {
                 g[e] = th[e];
                 part = fma(th[e], th[e], part);
             }
-            return fma(-0.5, Grp<G>::sum(part), c0);
+            return part;
         } else if (MODEL == AHMC_MODEL_DIAG_GAUSS) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -549,7 +564,7 @@ struct ModelOps {
                 g[e] = diff * w[e];
                 part = fma(diff, g[e], part);
             }
-            return fma(-0.5, Grp<G>::sum(part), c0);
+            return part;
         } else if (MODEL == AHMC_MODEL_DENSE_GAUSS) {
             double diff[E];
 #pragma unroll
@@ -558,7 +573,7 @@ struct ModelOps {
             else matvec<G, E>(P, D, diff, g, xs, l);
 #pragma unroll
             for (int e = 0; e < E; ++e) part = fma(diff[e], g[e], part);
-            return fma(-0.5, Grp<G>::sum(part), c0);
+            return part;
         } else if (MODEL == AHMC_MODEL_USER) {
 #if defined(AHMC_NVRTC_USER_MODEL)
 #if defined(AHMC_USER_COORDWISE)
@@ -570,7 +585,7 @@ struct ModelOps {
                 g[e] = -gd;  // PhasePoint caches MINUS the gradient (hamiltonian.jl:45-48)
                 part += term;
             }
-            return Grp<G>::sum(part) + c0;
+            return part;
 #else
             double* gs = xs + D;  // second slab vector of this group
             __syncwarp();
@@ -620,10 +635,10 @@ struct ChainState {
     double lp, lk;
 };
 
-// neg kinetic energy and (optionally) dH/dr of the current r
+// dH/dr of the current r and this lane's share of r' dH/dr (neg kinetic energy = -sum/2)
 template <int METRIC, int G, int E>
-__device__ __forceinline__ double kinetic(const MetricOps<METRIC, G, E>& me, const double (&r)[E], double (&dr)[E],
-                                          double* xs, int l) {
+__device__ __forceinline__ double kinetic_part(const MetricOps<METRIC, G, E>& me, const double (&r)[E], double (&dr)[E],
+                                               double* xs, int l) {
     me.dHdr(r, dr, xs, l);
     double part = 0.0;
     if (METRIC == AHMC_METRIC_DIAG) {
@@ -634,18 +649,37 @@ __device__ __forceinline__ double kinetic(const MetricOps<METRIC, G, E>& me, con
 #pragma unroll
         for (int e = 0; e < E; ++e) part = fma(r[e], dr[e], part);
     }
-    return -0.5 * Grp<G>::sum(part);
+    return part;
+}
+
+// neg kinetic energy and (optionally) dH/dr of the current r
+template <int METRIC, int G, int E>
+__device__ __forceinline__ double kinetic(const MetricOps<METRIC, G, E>& me, const double (&r)[E], double (&dr)[E],
+                                          double* xs, int l) {
+    return -0.5 * Grp<G>::sum(kinetic_part<METRIC, G, E>(me, r, dr, xs, l));
 }
 
 // One leapfrog step (integrator.jl:235-247) with signed step size eps.  Returns isfinite(z)
 // (hamiltonian.jl:141-142), identical on all lanes of the group.  s.lp / s.lk get the -Inf mapping.
 // dr receives dH/dr of the final momentum (PhasePoint.lk.gradient).
 // temper_mul1/2: multiply r before the first / after the second half kick (1.0 = no tempering).
+// TemperedLeapfrog (integrator.jl:198-209): what r is multiplied by before the first / after the second half kick of
+// step i (1-based) of an n-step `step` call.  alpha <= 0: plain Leapfrog.
+__device__ __forceinline__ void temper_muls(double alpha, int i, int n, double& t1, double& t2) {
+    t1 = 1.0;
+    t2 = 1.0;
+    if (alpha > 0.0) {
+        const double sa = sqrt(alpha);
+        t1 = (2 * (i - 1) + 1 <= n) ? sa : 1.0 / sa;
+        t2 = (2 * (i - 1) + 2 <= n) ? sa : 1.0 / sa;
+    }
+}
+
 template <int MODEL, int METRIC, int G, int E>
-__device__ __forceinline__ bool leapfrog_step(ChainState<E>& s, const ModelOps<MODEL, G, E>& mo,
-                                              const MetricOps<METRIC, G, E>& me, double eps, double (&dr)[E],
-                                              double* xs, int l, double temper_mul1 = 1.0,
-                                              double temper_mul2 = 1.0) {
+__device__ __forceinline__ void leapfrog_moves(ChainState<E>& s, const ModelOps<MODEL, G, E>& mo,
+                                               const MetricOps<METRIC, G, E>& me, double eps, double (&dr)[E],
+                                               double* xs, int l, double temper_mul1, double temper_mul2,
+                                               double& lp_v, double& lk_part) {
     const double he = 0.5 * eps;
     if (temper_mul1 != 1.0) {
 #pragma unroll
@@ -656,17 +690,54 @@ __device__ __forceinline__ bool leapfrog_step(ChainState<E>& s, const ModelOps<M
     me.dHdr(s.r, dr, xs, l);
 #pragma unroll
     for (int e = 0; e < E; ++e) s.th[e] = fma(eps, dr[e], s.th[e]);  // theta + eps .* dH/dr
-    double lp = mo.eval(s.th, s.g, xs, l);                           // dH/dtheta
+    lp_v = mo.eval_part(s.th, s.g, xs, l);                           // dH/dtheta
 #pragma unroll
     for (int e = 0; e < E; ++e) s.r[e] = fma(-he, s.g[e], s.r[e]);
     if (temper_mul2 != 1.0) {
 #pragma unroll
         for (int e = 0; e < E; ++e) s.r[e] *= temper_mul2;
     }
-    double lk = kinetic<METRIC, G, E>(me, s.r, dr, xs, l);
+    lk_part = kinetic_part<METRIC, G, E>(me, s.r, dr, xs, l);
+}
+
+template <int MODEL, int METRIC, int G, int E>
+__device__ __forceinline__ bool leapfrog_step(ChainState<E>& s, const ModelOps<MODEL, G, E>& mo,
+                                              const MetricOps<METRIC, G, E>& me, double eps, double (&dr)[E],
+                                              double* xs, int l, double temper_mul1 = 1.0,
+                                              double temper_mul2 = 1.0) {
+    double lp, lk;
+    leapfrog_moves<MODEL, METRIC, G, E>(s, mo, me, eps, dr, xs, l, temper_mul1, temper_mul2, lp, lk);
+    if constexpr (!ModelOps<MODEL, G, E>::kLpReduced) lp = mo.finish(Grp<G>::sum(lp));
+    lk = -0.5 * Grp<G>::sum(lk);
     bool fin = true;
 #pragma unroll
     for (int e = 0; e < E; ++e) fin = fin && finite_d(s.g[e]) && finite_d(dr[e]);
+    fin = Grp<G>::all(fin) && finite_d(lp) && finite_d(lk);
+    s.lp = map_nonfinite(lp);
+    s.lk = map_nonfinite(lk);
+    return fin;
+}
+
+// The same step for a caller that needs the energies only at the step it stops on (the fused trajectory, K1 / K2):
+// `isfinite(z)` is decided from the lane partials when that is a proof -- every gradient entry finite and every
+// partial of log pi and of the kinetic energy below 2^990, so the 32-term sums are below 2^995 -- and the two
+// group reductions run only when `want_energies` (warp-uniform) or some group of the warp is outside the proof.
+// Then s.lp / s.lk are exactly leapfrog_step's; otherwise they are left untouched and the step is finite.
+template <int MODEL, int METRIC, int G, int E>
+__device__ __forceinline__ bool leapfrog_step_lean(ChainState<E>& s, const ModelOps<MODEL, G, E>& mo,
+                                                   const MetricOps<METRIC, G, E>& me, double eps, double (&dr)[E],
+                                                   double* xs, int l, double temper_mul1, double temper_mul2,
+                                                   bool want_energies) {
+    double lp, lk;
+    leapfrog_moves<MODEL, METRIC, G, E>(s, mo, me, eps, dr, xs, l, temper_mul1, temper_mul2, lp, lk);
+    constexpr int T990 = expo_bits(990);
+    bool fin = true;
+#pragma unroll
+    for (int e = 0; e < E; ++e) fin = fin && finite_d(s.g[e]) && finite_d(dr[e]);
+    const bool proven = fin && !big_d(lp, T990) && !big_d(lk, T990);
+    if (!want_energies && __all_sync(FULL, proven)) return true;
+    if constexpr (!ModelOps<MODEL, G, E>::kLpReduced) lp = mo.finish(Grp<G>::sum(lp));
+    lk = -0.5 * Grp<G>::sum(lk);
     fin = Grp<G>::all(fin) && finite_d(lp) && finite_d(lk);
     s.lp = map_nonfinite(lp);
     s.lk = map_nonfinite(lk);

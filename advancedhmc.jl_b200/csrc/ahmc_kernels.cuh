@@ -82,6 +82,7 @@ struct RngDev {
     const uint8_t* dir_tape;
     long long dir_stride;
     double partial_alpha;  // 0: full refresh; else r' = alpha r + sqrt(1-alpha^2) xi (hamiltonian.jl:243-254)
+    double temper_alpha;   // > 0: the transition integrates with TemperedLeapfrog(eps, alpha) (integrator.jl:174-209)
 };
 
 struct HmcArgs {

@@ -97,9 +97,22 @@ template <int MODEL, int METRIC, int E>
 constexpr int min_blocks_per_sm() {
     return (FastCapable<MODEL, METRIC>::value && E <= 4) ? 7 : 1;
 }
+// The funnel trajectory kernel (exact path only) sits at 95 registers uncapped = 5 blocks per SM = two waves for 4096
+// chains; capped it spills ~50 bytes outside the step loop and runs in one.  Its transition kernel would spill inside
+// the loop, so that one keeps the default.
+// The transition kernel of a general target: 128 registers (4 blocks per SM) are enough for E <= 4 without spills; left
+// alone it takes ~140 and loses a block per SM (measured on the funnel: 64 us per transition vs 53).
+template <int MODEL, int METRIC, int E>
+constexpr int min_blocks_hmc() {
+    return (FastCapable<MODEL, METRIC>::value && E <= 4) ? 7 : ((METRIC != AHMC_METRIC_DENSE && MODEL != AHMC_MODEL_DENSE_GAUSS && E <= 4) ? 4 : 1);
+}
+template <int MODEL, int METRIC, int E>
+constexpr int min_blocks_lf() {
+    return (MODEL == AHMC_MODEL_FUNNEL && METRIC != AHMC_METRIC_DENSE && E <= 4) ? 7 : min_blocks_per_sm<MODEL, METRIC, E>();
+}
 
 template <int MODEL, int METRIC, int G, int E, bool CONTIG = false>
-__global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC, E>()) leapfrog_kernel(const LeapfrogArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, min_blocks_lf<MODEL, METRIC, E>()) leapfrog_kernel(const LeapfrogArgs a) {
     extern __shared__ double smem[];
     const int l = threadIdx.x % G;
     const int grp_in_block = threadIdx.x / G;
@@ -194,7 +207,7 @@ struct HmcIO {
 // One launch = n_transitions static-HMC transitions per chain (the reference's `for i in 1:n_samples` loop,
 // sampler.jl:182, without adaptation): state is re-read from the output phase point, which stays L2-resident.
 template <int MODEL, int METRIC, int G, int E>
-__global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC, E>()) hmc_kernel(const HmcArgs h) {
+__global__ void __launch_bounds__(kBlockThreads, min_blocks_hmc<MODEL, METRIC, E>()) hmc_kernel(const HmcArgs h) {
     extern __shared__ double smem[];
     const LeapfrogArgs& a = h.lf;
     const int l = threadIdx.x % G;
@@ -241,7 +254,7 @@ __global__ void __launch_bounds__(kBlockThreads, min_blocks_per_sm<MODEL, METRIC
         io.lp0 = map_nonfinite(first ? a.lp_in[chain] : a.lp_out[chain]);
         io.H0 = -(io.lp0 + io.lk0);
         io.ex = h.rng.exp_tape ? h.rng.exp_tape[chain] : philox_exp(h.rng.seed, off, chain, 0);
-        run_trajectory<MODEL, METRIC, G, E>(a.model, a.metric, D, chain, valid, l, xs, eps, a.n_steps, 0.0, a.flags, io);
+        run_trajectory<MODEL, METRIC, G, E>(a.model, a.metric, D, chain, valid, l, xs, eps, a.n_steps, h.rng.temper_alpha, a.flags, io);
         __syncwarp();
     }
 }

@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(kBlockThreads) multinomial_kernel(const Multin
     {
         bool active = valid;
         for (int i = 1; i <= n_bwd; ++i) {
-            const bool fin = leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, -eps, dr, xs, l);
+            double t1, t2;
+            temper_muls(a.rng.temper_alpha, i, n_bwd, t1, t2);  // each leg is its own `step` call (trajectory.jl:374-376)
+            const bool fin = leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, -eps, dr, xs, l, t1, t2);
             if (active) {
                 if (l == 0) Hs[i - 1] = -(s.lp + s.lk);
                 nb = i;
@@ -134,7 +136,9 @@ __global__ void __launch_bounds__(kBlockThreads) multinomial_kernel(const Multin
     {
         bool active = valid;
         for (int i = 1; i <= n_fwd; ++i) {
-            const bool fin = leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, eps, dr, xs, l);
+            double t1, t2;
+            temper_muls(a.rng.temper_alpha, i, n_fwd, t1, t2);
+            const bool fin = leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, eps, dr, xs, l, t1, t2);
             if (active) {
                 if (l == 0) Hs[n_bwd + i - 1] = -(s.lp + s.lk);
                 nf = i;
@@ -209,7 +213,9 @@ __global__ void __launch_bounds__(kBlockThreads) multinomial_kernel(const Multin
     };
     if (valid && k == 0) emit();
     for (int i = 1; i <= kmax; ++i) {
-        leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, eps_dir, dr, xs, l);
+        double t1, t2;
+        temper_muls(a.rng.temper_alpha, i, (idx < nb) ? n_bwd : n_fwd, t1, t2);
+        leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, eps_dir, dr, xs, l, t1, t2);
         if (valid && i == k) emit();
     }
 }

@@ -412,7 +412,11 @@ __global__ void __launch_bounds__(COOP ? kCoopThreads : kBlockThreads, COOP ? 1 
         if (!any_peer(in_sub)) break;
 
         // ---------------------------------------------------------------- (B) one leaf (:638-647)
-        leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, v > 0 ? eps_c : -eps_c, dr, xs, l);
+        {
+            double t1, t2;  // a leaf is `step(lf, h, z, v)` with |v| = 1: sqrt(alpha) before, 1/sqrt(alpha) after
+            temper_muls(a.rng.temper_alpha, 1, 1, t1, t2);
+            leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, v > 0 ? eps_c : -eps_c, dr, xs, l, t1, t2);
+        }
         const double nE = s.lp + s.lk;  // neg_energy(z')
         const double H1 = -nE;
         const double dH = H1 - H0;

@@ -3,8 +3,9 @@
 //
 // Two code paths (see DESIGN.md "K1"):
 //
-//  * EXACT (every model x metric): per step the reference's op sequence with FMAs, energies reduced
-//    by warp shuffles, and the reference's `isfinite(z)` test (hamiltonian.jl:141-142).  A non-finite
+//  * EXACT (every model x metric): per step the reference's op sequence with FMAs and the reference's
+//    `isfinite(z)` test (hamiltonian.jl:141-142); the energies themselves are reduced by warp shuffles only at
+//    the step the chain stops on (leapfrog_step_lean: the per-step test is decided from lane partials).  A non-finite
 //    chain stops on its own and its phase point AT the break step is what is handed to `done`
 //    (integrator.jl:252-258 returns the non-finite z).
 //
@@ -170,7 +171,7 @@ __device__ __forceinline__ void run_trajectory(const ModelDev& model, const Metr
             t1 = (2 * (i - 1) + 1 <= n) ? sa : 1.0 / sa;
             t2 = (2 * (i - 1) + 2 <= n) ? sa : 1.0 / sa;
         }
-        const bool fin = leapfrog_step<MODEL, METRIC, G, E>(s, mo, me, eps, dr, xs, l, t1, t2);
+        const bool fin = leapfrog_step_lean<MODEL, METRIC, G, E>(s, mo, me, eps, dr, xs, l, t1, t2, i == n);
         if (active && (!fin || i == n)) {
             f.done(s.th, s.r, s.g, dr, s.lp, s.lk, fin, i);
             active = false;

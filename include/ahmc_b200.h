@@ -123,6 +123,9 @@ typedef struct ahmc_rng {
     int64_t dir_stride;
     double partial_refresh_alpha; /* 0: FullMomentumRefreshment; else PartialMomentumRefreshment(alpha):
                                      r' = alpha*r + sqrt(1-alpha^2)*rand_momentum (hamiltonian.jl:222-254) */
+    double temper_alpha;          /* 0: the transition integrates with Leapfrog; > 0: with TemperedLeapfrog(eps, alpha)
+                                     (integrator.jl:174-209) -- every `step` the reference's transition makes tempers by its own
+                                     n_steps: the static trajectory, each leg of the multinomial one, each NUTS leaf (n = 1) */
 } ahmc_rng;
 
 /* User gradient callback for AHMC_MODEL_CALLBACK (replaces the Julia closure h.dlp/dth, hamiltonian.jl:45-48).

@@ -61,6 +61,7 @@ struct CRng
     dir_tape::Ptr{UInt8}
     dir_stride::Int64
     partial_refresh_alpha::Float64
+    temper_alpha::Float64
 end
 struct CAdaptCfg
     n_adapts::Int32; init_buffer::Int32; term_buffer::Int32; window_size::Int32
@@ -197,8 +198,11 @@ end
 struct B200Leapfrog{T<:AdvancedHMC.AbstractScalarOrVec{<:AbstractFloat}} <: AbstractLeapfrog{T}
     ϵ::T
     target::B200Target
+    α::Float64          # 0: `Leapfrog(ϵ)`; > 0: `TemperedLeapfrog(ϵ, α)` (src/integrator.jl:174-209), in `step` and in transitions
 end
-AdvancedHMC.update_nom_step_size(lf::B200Leapfrog, ϵ) = B200Leapfrog(ϵ, lf.target)
+B200Leapfrog(ϵ, target::B200Target) = B200Leapfrog(ϵ, target, 0.0)
+AdvancedHMC.update_nom_step_size(lf::B200Leapfrog, ϵ) = B200Leapfrog(ϵ, lf.target, lf.α)
+temper_alpha(lf::B200Leapfrog) = lf.α
 
 cmetric(m::UnitEuclideanMetric, N) = CMetric(0, C_NULL, 0, C_NULL)
 cmetric(m::DiagEuclideanMetric, N) = CMetric(1, dptr(m.M⁻¹), ndims(m.M⁻¹) == 2 ? size(m.M⁻¹, 1) : 0, C_NULL)
@@ -222,7 +226,8 @@ refresh_alpha(r::PartialMomentumRefreshment) = Float64(r.α)
 eps_args(ϵ::AbstractFloat) = (Float64(ϵ), Ptr{Float64}(C_NULL))
 eps_args(ϵ::CuVector{Float64}) = (0.0, dptr(ϵ))
 
-philox(rng, κ) = CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, refresh_alpha(κ.refreshment))  # key drawn from the Julia rng
+# key drawn from the Julia rng; the transition's refreshment and integrator options ride in the same struct
+philox(rng, κ) = CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, refresh_alpha(κ.refreshment), temper_alpha(κ.τ.integrator))
 
 "`phasepoint(h, θ, r)` (src/hamiltonian.jl:115-119) for a B200 target."
 function b200_phasepoint(t::B200Target, h::Hamiltonian, θ::CuMatrix{Float64}, r::CuMatrix{Float64})
@@ -256,7 +261,7 @@ function AdvancedHMC.step(lf::B200Leapfrog, h::Hamiltonian, z::PhasePoint{<:CuMa
             check(ccall((:ahmc_leapfrog_trajectory_f64, libahmc), Cint,
                         (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CMetric}, Int32, Int64, Float64, Ptr{Float64}, Int32, Float64,
                          Ref{CPhasePoint}, Ref{CPhasePoint}, Int64, Ptr{Int32}, UInt32),
-                        context().h, lf.target.handle, md, D, N, ϵ, ϵp, n, 0.0, zi, tc, D * N, dptr(done), 0))
+                        context().h, lf.target.handle, md, D, N, ϵ, ϵp, n, lf.α, zi, tc, D * N, dptr(done), 0))
         end
         nmax = Int(maximum(Array(done)))   # like `resize!(res, i)` on an early break (integrator.jl:252-258)
         return [PhasePoint(θs[:, :, i], rs[:, :, i], DualValue(lps[:, i], gs[:, :, i]), DualValue(lks[:, i], drs[:, :, i]))
@@ -267,7 +272,7 @@ function AdvancedHMC.step(lf::B200Leapfrog, h::Hamiltonian, z::PhasePoint{<:CuMa
         check(ccall((:ahmc_leapfrog_f64, libahmc), Cint,
                     (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CMetric}, Int32, Int64, Float64, Ptr{Float64}, Int32, Float64,
                      Ref{CPhasePoint}, Ref{CPhasePoint}, Ptr{UInt32}, Ptr{Int32}, UInt32),
-                    context().h, lf.target.handle, md, D, N, ϵ, ϵp, n, 0.0, zi, zo, C_NULL, C_NULL, 0))
+                    context().h, lf.target.handle, md, D, N, ϵ, ϵp, n, lf.α, zi, zo, C_NULL, C_NULL, 0))
     end
     return zout
 end
@@ -291,7 +296,7 @@ function AdvancedHMC.step(lf::B200Leapfrog, h::Hamiltonian, z::PhasePoint{<:Matr
         check(ccall((:ahmc_leapfrog_f64, libahmc), Cint,
                     (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CMetric}, Int32, Int64, Float64, Ptr{Float64}, Int32, Float64,
                      Ref{CPhasePoint}, Ref{CPhasePoint}, Ptr{UInt32}, Ptr{Int32}, UInt32),
-                    context().h, lf.target.handle, md, D, N, ϵ, ϵp, n, 0.0, zi, zo, C_NULL, C_NULL, FLAG_HOST_BUFFERS))
+                    context().h, lf.target.handle, md, D, N, ϵ, ϵp, n, lf.α, zi, zo, C_NULL, C_NULL, FLAG_HOST_BUFFERS))
     end
     return zout
 end
@@ -302,7 +307,7 @@ function b200_rand_momentum(rng, h::Hamiltonian, θ::CuMatrix{Float64})
     r = similar(θ)
     U = dense_factor(h.metric)
     md = Ref(metric_desc(h.metric, N, U))
-    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, 0.0))
+    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, 0.0, 0.0))
     GC.@preserve r U check(ccall((:ahmc_rand_momentum_f64, libahmc), Cint,
                                  (Ptr{Cvoid}, Ref{CMetric}, Int32, Int64, Ref{CRng}, Ptr{Float64}, Int64, UInt32),
                                  context().h, md, D, N, rg, dptr(r), D, 0))
@@ -316,7 +321,7 @@ function b200_find_good_stepsize(rng, t::B200Target, h::Hamiltonian, θ::CuMatri
     ϵ = CUDA.zeros(Float64, N)
     U = dense_factor(h.metric)
     md = Ref(metric_desc(h.metric, N, U)); zc = Ref(cpp(z; lk_gradient=false))
-    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, 0.0))
+    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, 0.0, 0.0))
     GC.@preserve z ϵ U check(ccall((:ahmc_find_good_stepsize_f64, libahmc), Cint,
                                    (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CMetric}, Int32, Int64, Ref{CPhasePoint}, Ref{CRng}, Float64, Int32,
                                     Ptr{Float64}, Ptr{Float64}, UInt32),
@@ -470,7 +475,7 @@ function b200_sample_nuts(rng, h::Hamiltonian, lf::B200Leapfrog, tc::Generalised
     st = Ref(CStats(C_NULL, C_NULL, dptr(α), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
     cfg = Ref(CAdaptCfg(n_adapts, init_buffer, term_buffer, window_size, δ, 0.05, 10.0, 0.75, adapt_metric ? 1 : 0, 10,
                         dptr(ϵ), dptr(Minv), C_NULL))
-    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, 0.0))
+    rg = Ref(CRng(rand(rng, UInt64), 0, C_NULL, C_NULL, 0, C_NULL, 0, 0.0, 0.0))
     md = Ref(cmetric(h.metric, N)); zi = Ref(cpp(z)); zo = Ref(cpp(zout; lk_gradient=false))
     GC.@preserve z zout ϵ Minv draws α begin
         check(ccall((:ahmc_nuts_adapt_sample_f64, libahmc), Cint,

@@ -322,6 +322,11 @@ void orc_leapfrog_trajectory(const orc_model* m, const orc_metric* me, int32_t D
 
 static double g_partial_alpha = 0.0;
 void orc_set_partial_refresh(double alpha) { g_partial_alpha = alpha; }
+/* TemperedLeapfrog(eps, alpha) as the integrator of the transitions below (integrator.jl:174-209): every `step` call a
+   transition makes -- the static trajectory (trajectory.jl:337), each leg of the multinomial one (:374-376), each NUTS
+   leaf (:640, n_steps = +-1) -- tempers by its own n_steps. */
+static double g_temper_alpha = 0.0;
+void orc_set_tempering(double alpha) { g_temper_alpha = alpha > 0 ? alpha : 0.0; }
 /* refresh(rng, ref, h, z) (hamiltonian.jl:213-220 full, :243-254 partial) for chain c */
 static void refresh_momentum(const orc_metric* me, int D, int64_t c, const double* z_tape, const double* r_prev, double* r) {
     orc_rand_momentum(me, D, c, z_tape, r);
@@ -353,7 +358,7 @@ void orc_hmc_transition(const orc_model* m, const orc_metric* me, int32_t D, int
     }
     orc_make_phasepoint(m, me, D, N, &z0);
     /* z' = step(integrator, h, z, nsteps)  (trajectory.jl:337) */
-    leapfrog_impl(m, me, D, N, eps, eps_chain, n_steps, 0.0, &z0, &z1, NULL, 0, NULL, NULL, compat_break_all);
+    leapfrog_impl(m, me, D, N, eps, eps_chain, n_steps, g_temper_alpha, &z0, &z1, NULL, 0, NULL, NULL, compat_break_all);
     for (int64_t c = 0; c < N; ++c) {
         double H0 = -(z0.lp_value[c] + z0.lk_value[c]); /* energy(z) hamiltonian.jl:149,194 */
         double H1 = -(z1.lp_value[c] + z1.lk_value[c]);
@@ -429,7 +434,7 @@ void orc_hmc_multinomial_transition(const orc_model* m, const orc_metric* me, in
         memcpy(th, th0, sizeof(double) * (size_t)D); memcpy(r, r0, sizeof(double) * (size_t)D); memcpy(g, g0, sizeof(double) * (size_t)D);
         for (int i = 1; i <= nb_req; ++i) {
             double lp, lk;
-            int fin = lf_one_step(m, me, D, c, -e, i, nb_req, 0.0, th, r, g, &lp, &lk, dr, grad);
+            int fin = lf_one_step(m, me, D, c, -e, i, nb_req, g_temper_alpha, th, r, g, &lp, &lk, dr, grad);
             memcpy(bTH + (size_t)D * nb, th, sizeof(double) * (size_t)D);
             memcpy(bR + (size_t)D * nb, r, sizeof(double) * (size_t)D);
             memcpy(bG + (size_t)D * nb, g, sizeof(double) * (size_t)D);
@@ -452,7 +457,7 @@ void orc_hmc_multinomial_transition(const orc_model* m, const orc_metric* me, in
         memcpy(th, th0, sizeof(double) * (size_t)D); memcpy(r, r0, sizeof(double) * (size_t)D); memcpy(g, g0, sizeof(double) * (size_t)D);
         for (int i = 1; i <= nf_req; ++i) {
             double lp, lk;
-            int fin = lf_one_step(m, me, D, c, e, i, nf_req, 0.0, th, r, g, &lp, &lk, dr, grad);
+            int fin = lf_one_step(m, me, D, c, e, i, nf_req, g_temper_alpha, th, r, g, &lp, &lk, dr, grad);
             memcpy(TH + (size_t)D * len, th, sizeof(double) * (size_t)D);
             memcpy(R + (size_t)D * len, r, sizeof(double) * (size_t)D);
             memcpy(G + (size_t)D * len, g, sizeof(double) * (size_t)D);
@@ -628,7 +633,7 @@ static void build_tree(nuts_ctx* x, const pp_t* z, sampler_t sampler, int v, int
         memcpy(z1->r, z->r, sizeof(double) * (size_t)D);
         memcpy(z1->g, z->g, sizeof(double) * (size_t)D);
         double e = v > 0 ? x->eps : -x->eps; /* step(..., v): fwd = v>0 (integrator.jl:221-226) */
-        lf_one_step(x->m, x->me, D, x->c, e, 1, 1, 0.0, z1->theta, z1->r, z1->g, &z1->lp, &z1->lk, x->scratch,
+        lf_one_step(x->m, x->me, D, x->c, e, 1, 1, g_temper_alpha, z1->theta, z1->r, z1->g, &z1->lp, &z1->lk, x->scratch,
                     x->scratch + D);
         double H1 = -(z1->lp + z1->lk);
         double dH = H1 - H0;

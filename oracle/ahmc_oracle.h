@@ -129,6 +129,9 @@ void orc_hmc_multinomial_transition(const orc_model* m, const orc_metric* me, in
 /* PartialMomentumRefreshment(alpha) (hamiltonian.jl:222-254) for the transitions below: when non-zero, the
  * refreshed momentum is alpha*z_in.r + sqrt(1-alpha^2)*rand_momentum(tape).  Process-global test knob. */
 void orc_set_partial_refresh(double alpha);
+/* TemperedLeapfrog(eps, alpha) (integrator.jl:174-209) as the integrator of the transitions below; 0 = plain Leapfrog.
+ * Process-global test knob. */
+void orc_set_tempering(double alpha);
 
 /* NUTS transition, MultinomialTS + GeneralisedNoUTurn (trajectory.jl:626-742), one chain at a time
  * (the reference has no vectorised NUTS).  Tapes per chain c: dir_tape[c*dir_stride + k] = k-th

@@ -319,6 +319,11 @@ def set_partial_refresh(alpha: float):
     lib().orc_set_partial_refresh(C.c_double(alpha))
 
 
+def set_tempering(alpha: float):
+    """TemperedLeapfrog(eps, alpha) as the integrator of subsequent hmc / multinomial / nuts transitions (0 = plain Leapfrog)."""
+    lib().orc_set_tempering(C.c_double(alpha))
+
+
 def stan_windows(n_adapts, init_buffer=75, term_buffer=50, window_size=25):
     ws, we = C.c_int32(0), C.c_int32(0)
     splits = (C.c_int32 * 64)()

@@ -83,7 +83,7 @@ extern "C" int emu_leapfrog(const EmuLf* q) {
     a.flags = q->flags;
     HmcArgs h{};
     h.lf = a;
-    h.rng = RngDev{q->seed, q->offset, q->normal_tape, q->exp_tape, 1, nullptr, 0, 0.0};
+    h.rng = RngDev{q->seed, q->offset, q->normal_tape, q->exp_tape, 1, nullptr, 0, 0.0, q->temper_alpha > 0.0 ? q->temper_alpha : 0.0};
     h.st.is_accept = q->is_accept;
     h.st.acceptance_rate = q->acc;
     h.st.hamiltonian_energy_error = q->dH;

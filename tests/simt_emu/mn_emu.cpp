@@ -24,6 +24,7 @@ struct EmuMn {
     double *th_out, *r_out, *g_out, *lp_out, *lk_out;
     double* acc;
     int32_t* index;
+    double temper_alpha;
 };
 
 template <int MODEL, int METRIC, int G, int E>
@@ -54,7 +55,7 @@ extern "C" int emu_multinomial(const EmuMn* q) {
     a.n_steps = q->n_steps;
     a.n_fwd = q->n_fwd;
     a.refresh = 1;
-    a.rng = RngDev{1, 0, q->normal_tape, q->unif_tape, 1, nullptr, 0, 0.0};
+    a.rng = RngDev{1, 0, q->normal_tape, q->unif_tape, 1, nullptr, 0, 0.0, q->temper_alpha};
     a.th_in = q->th_in; a.r_in = r_in.data(); a.g_in = q->g_in; a.lp_in = q->lp_in;
     a.ld_in = D;
     a.th_out = q->th_out; a.r_out = q->r_out; a.g_out = q->g_out; a.lp_out = q->lp_out; a.lk_out = q->lk_out;

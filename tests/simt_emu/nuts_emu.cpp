@@ -45,6 +45,7 @@ struct EmuNuts {
     double delta, gamma, t0, kappa;
     int32_t adapt_metric, n_min;
     double *eps_rw, *minv_rw, *eps_trace;
+    double temper_alpha;
 };
 
 template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
@@ -126,7 +127,7 @@ extern "C" int emu_nuts(const EmuNuts* q) {
     a.delta_max = q->delta_max;
     a.sampler = q->sampler;
     a.criterion = q->criterion;
-    a.rng = RngDev{q->seed, q->offset, q->normal_tape, q->exp_tape, q->exp_stride, q->dir_tape, q->dir_stride, q->partial_alpha};
+    a.rng = RngDev{q->seed, q->offset, q->normal_tape, q->exp_tape, q->exp_stride, q->dir_tape, q->dir_stride, q->partial_alpha, q->temper_alpha};
     a.refresh = q->refresh;
     a.th_in = q->th_in; a.r_in = q->r_in; a.g_in = q->g_in; a.lp_in = q->lp_in;
     a.ld_in = D;

@@ -110,6 +110,7 @@ int main(void) {
     P("sizeof_stats", sizeof(ahmc_stats)); P("stats.numerical_error", offsetof(ahmc_stats, numerical_error));
     P("sizeof_rng", sizeof(ahmc_rng)); P("rng.exp_stride", offsetof(ahmc_rng, exp_stride));
     P("rng.partial_refresh_alpha", offsetof(ahmc_rng, partial_refresh_alpha));
+    P("rng.temper_alpha", offsetof(ahmc_rng, temper_alpha));
     P("sizeof_adapt_cfg", sizeof(ahmc_adapt_cfg)); P("adapt_cfg.delta", offsetof(ahmc_adapt_cfg, delta));
     P("adapt_cfg.adapt_metric", offsetof(ahmc_adapt_cfg, adapt_metric)); P("adapt_cfg.eps_chain", offsetof(ahmc_adapt_cfg, eps_chain));
     P("adapt_cfg.eps_trace", offsetof(ahmc_adapt_cfg, eps_trace));

@@ -873,6 +873,73 @@ def test_partial_momentum_refreshment_vs_oracle():
     assert not torch.equal(full.z.theta, tr.z.theta)
 
 
+@pytest.mark.parametrize("model,metric,D", [("diag_gauss", "diag", 128), ("funnel", "unit", 10), ("dense_gauss", "dense", 40),
+                                            ("diag_gauss", "dense", 256)])
+def test_tempered_leapfrog_inside_transitions_vs_oracle(model, metric, D):
+    """`TemperedLeapfrog(eps, alpha)` as the integrator of whole transitions (the reference's sampler matrix runs every
+    integrator through every trajectory, test/sampler.jl:81-91): static end point (one n-step `step`, trajectory.jl:337),
+    static multinomial (two legs, each tempering by its own n, :374-376) and NUTS (every leaf a 1-step `step`, :640)."""
+    rng = np.random.default_rng(900 + D)
+    N, alpha = 97, 1.07
+    p0 = p1 = Minv = None
+    if model == "diag_gauss":
+        p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.5, 0.5, D))
+    elif model == "dense_gauss":
+        B = rng.normal(size=(D, D))
+        p0, p1 = rng.normal(size=D), B @ B.T / D + np.eye(D)
+    if metric == "diag":
+        Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    elif metric == "dense":
+        B = rng.normal(size=(D, D))
+        Minv = B @ B.T / D + 0.5 * np.eye(D)
+    eps = {"diag_gauss": 0.3, "funnel": 0.15, "dense_gauss": 0.25}[model] * (0.5 if D > 200 else 1.0)
+    th = rng.normal(size=(D, N)) * (0.4 if model == "funnel" else 1.0)
+    nt, et, ut = rng.normal(size=(D, N)), rng.exponential(size=N) * 0.3, rng.uniform(size=N)
+    md = 6
+    dirs = rng.integers(0, 2, size=(N, md + 1)).astype(np.uint8)
+    exps = rng.exponential(size=(N, 1 << md))
+    om, ome = oc.Model(MODEL_KINDS[model], D, p0, p1, 0.0), oc.Metric(METRIC_KINDS[metric], Minv)
+    z0o = oc.phasepoint(om, ome, th, np.zeros((D, N)))
+    oc.set_tempering(alpha)
+    try:
+        zs, ss = oc.hmc_transition(om, ome, eps, 7, z0o, nt, et)
+        zm, sm = oc.hmc_multinomial_transition(om, ome, eps, 9, 4, z0o, nt, ut)
+        zn, sn, _ = oc.nuts_transition(om, ome, eps, z0o, nt, dirs, exps, max_depth=md)
+    finally:
+        oc.set_tempering(0.0)
+    zu, su, _ = oc.nuts_transition(om, ome, eps, z0o, nt, dirs, exps, max_depth=md)
+    h = A.Hamiltonian(make_metric(metric, Minv, D), make_target(model, D, p0, p1, 0.0))
+    z0 = A.phasepoint(h, T(th), T(np.zeros((D, N))))
+    lf = A.TemperedLeapfrog(eps, alpha)
+    ts = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(et, device=DEV)), h,
+                      A.HMCKernel(A.Trajectory(A.EndPointTS, lf, A.FixedNSteps(7))), z0)
+    assert (F(ts.stat["is_accept"]).astype(bool) == ss.is_accept.astype(bool)).all()
+    assert_pp_close(ts.z, zs)
+    assert rel_err(F(ts.stat["acceptance_rate"]), ss.acceptance_rate) < 1e-9
+    tm = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(ut, device=DEV), n_fwd=4), h,
+                      A.HMCKernel(A.Trajectory(A.MultinomialTS, lf, A.FixedNSteps(9))), z0)
+    assert (F(tm.stat["tree_depth"]) == sm.tree_depth).all()
+    assert_pp_close(tm.z, zm)
+    tn = A.transition(A.TapeRNG(normal=T(nt), exp=torch.as_tensor(exps, device=DEV), dirs=torch.as_tensor(dirs, device=DEV)), h,
+                      A.HMCKernel(A.Trajectory(A.MultinomialTS, lf, A.GeneralisedNoUTurn(md, 1000.0))), z0)
+    assert (F(tn.stat["n_steps"]) == sn.n_steps).all() and (F(tn.stat["tree_depth"]) == sn.tree_depth).all()
+    assert_pp_close(tn.z, zn)
+    assert rel_err(F(tn.stat["acceptance_rate"]), sn.acceptance_rate) < 1e-9
+    # tempering changes the trees: the untempered transition on the same tapes is a different one
+    assert not np.allclose(sn.acceptance_rate, su.acceptance_rate, rtol=1e-6)
+    # multi-transition launches accept the tempered integrator and agree with sequential single transitions (Philox)
+    if model != "dense_gauss" and metric != "dense":
+        k = A.HMCKernel(A.Trajectory(A.EndPointTS, lf, A.FixedNSteps(5)))
+        r1, r2 = A.PhiloxRNG(7), A.PhiloxRNG(7)
+        zl, draws, _ = A.sample_transitions(r1, h, k, z0, 3)
+        zq = z0
+        for _ in range(3):
+            zq = A.transition(r2, h, k, zq).z
+        assert torch.equal(zl.theta, zq.theta)
+    with pytest.raises(A.InvalidArgument):
+        A.transition(A.PhiloxRNG(1), h, A.HMCKernel(A.Trajectory(A.EndPointTS, A.TemperedLeapfrog(eps, float("nan")), A.FixedNSteps(3))), z0)
+
+
 def test_find_good_stepsize_batched_equals_per_chain_search():
     """N lock-step copies of the reference's search == the single-chain search run chain by chain on the same momenta;
     host (numpy) positions give the same step sizes as device positions."""

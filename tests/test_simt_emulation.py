@@ -28,7 +28,8 @@ class EmuNuts(C.Structure):
                 ("numerical", _vp), ("acc", _vp), ("dH", _vp), ("dHmax", _vp), ("n_transitions", C.c_int32), ("draws", _vp),
                 ("adapt", C.c_int32), ("n_adapts", C.c_int32), ("init_buffer", C.c_int32), ("term_buffer", C.c_int32),
                 ("window_size", C.c_int32), ("delta", C.c_double), ("gamma", C.c_double), ("t0", C.c_double), ("kappa", C.c_double),
-                ("adapt_metric", C.c_int32), ("n_min", C.c_int32), ("eps_rw", _vp), ("minv_rw", _vp), ("eps_trace", _vp)]
+                ("adapt_metric", C.c_int32), ("n_min", C.c_int32), ("eps_rw", _vp), ("minv_rw", _vp), ("eps_trace", _vp),
+                ("temper_alpha", C.c_double)]
 
 
 @pytest.fixture(scope="module")
@@ -51,7 +52,7 @@ KINDS = dict(std_normal=oc.STD_NORMAL, diag_gauss=oc.DIAG_GAUSS, dense_gauss=oc.
 MKINDS = dict(unit=oc.UNIT, diag=oc.DIAG, dense=oc.DENSE)
 
 
-def _case(lib, kind, mkind, D, N, eps, sampler, criterion, seed, max_depth=6, delta_max=1000.0, scale=1.0):
+def _case(lib, kind, mkind, D, N, eps, sampler, criterion, seed, max_depth=6, delta_max=1000.0, scale=1.0, temper=0.0):
     rng = np.random.default_rng(seed)
     p0 = p1 = Minv = cholU = None
     if kind == "diag_gauss":
@@ -74,8 +75,12 @@ def _case(lib, kind, mkind, D, N, eps, sampler, criterion, seed, max_depth=6, de
         else oc.Model(oc.DIAG_GAUSS, D, p0, p1, 0.0)
     metric = oc.Metric(MKINDS[mkind], None if Minv is None else np.asfortranarray(Minv))
     z0 = oc.phasepoint(model, metric, th.T, r.T)
-    zo, so, used = oc.nuts_transition(model, metric, eps, z0, None, dirs, var, max_depth=max_depth, delta_max=delta_max,
-                                      sampler=sampler, criterion=criterion)
+    oc.set_tempering(temper)  # TemperedLeapfrog(eps, alpha) as the transition's integrator (0: plain)
+    try:
+        zo, so, used = oc.nuts_transition(model, metric, eps, z0, None, dirs, var, max_depth=max_depth, delta_max=delta_max,
+                                          sampler=sampler, criterion=criterion)
+    finally:
+        oc.set_tempering(0.0)
     # what the device-side model holds: DIAG_GAUSS p1 = 1/s^2; DENSE_GAUSS p1 = precision (column-major == symmetric)
     dp1 = None if p1 is None else (1.0 / (p1 * p1) if kind == "diag_gauss" else np.ascontiguousarray(p1))
     g_in = np.ascontiguousarray(z0.lp_gradient.T)
@@ -90,7 +95,7 @@ def _case(lib, kind, mkind, D, N, eps, sampler, criterion, seed, max_depth=6, de
                 exp_tape=P(var), exp_stride=var.shape[1], dir_tape=P(dirs), dir_stride=dirs.shape[1], partial_alpha=0.0,
                 refresh=0, th_in=P(th), r_in=P(r), g_in=P(g_in), lp_in=P(lp_in), th_out=P(out["th"]), r_out=P(out["r"]),
                 g_out=P(out["g"]), lp_out=P(lp_o), lk_out=P(lk_o), n_steps=P(ns), tree_depth=P(td), numerical=P(ne), acc=P(acc),
-                dH=P(dH), dHmax=P(dHm), n_transitions=1, draws=None, adapt=0)
+                dH=P(dH), dHmax=P(dHm), n_transitions=1, draws=None, adapt=0, temper_alpha=temper)
     assert lib.emu_nuts(C.byref(q)) == 0
     assert (td == so.tree_depth).all() and (ns == so.n_steps).all() and (ne == so.numerical_error).all()
     assert rel_err(out["th"].T, zo.theta) < 1e-10 and rel_err(out["r"].T, zo.r) < 1e-10
@@ -144,6 +149,19 @@ def test_full_tile_instantiation_matches_oracle(emu, kind, mkind, D, N, eps, sam
     """D == G * E (G = 32, E in 2..8) takes the instantiation with a compile-time D (no `d < D` guards), every other D the
     general one."""
     _case(emu, kind, mkind, D, N, eps, sampler, criterion, seed=29 + D, scale=0.5 if kind == "funnel" else 1.0)
+
+
+@pytest.mark.parametrize("kind,mkind,D,N,eps,sampler,criterion,alpha", [
+    ("diag_gauss", "diag", 7, 9, 0.25, "multinomial", "generalised", 1.05),
+    ("funnel", "diag", 6, 6, 0.2, "slice", "strict", 0.9),
+    ("dense_gauss", "dense", 40, 9, 0.3, "multinomial", "generalised", 1.1),   # COOP form
+], ids=["diag", "funnel-slice-strict", "dense-coop"])
+def test_nuts_with_tempered_leapfrog_under_emulation_matches_oracle(emu, kind, mkind, D, N, eps, sampler, criterion, alpha):
+    """`TemperedLeapfrog(eps, alpha)` as the integrator of a NUTS transition: every leaf is `step(lf, h, z, +-1)`
+    (trajectory.jl:640), i.e. r * sqrt(alpha) before the first half kick and r / sqrt(alpha) after the second
+    (integrator.jl:198-209 with n_steps = 1)."""
+    so = _case(emu, kind, mkind, D, N, eps, sampler, criterion, seed=77 + D, temper=alpha)
+    assert so.n_steps.max() >= 3
 
 
 def test_kernel_source_emulated_wild_funnel_start(emu):
@@ -292,24 +310,31 @@ def test_trajectory_kernel_source_under_emulation_matches_oracle(emu_lf, kind, m
     assert rel_err(o["dr"].T, zo.lk_gradient) < 1e-10
 
 
-@pytest.mark.parametrize("kind,mkind,D,N,eps,n", [("diag_gauss", "diag", 7, 9, 0.6, 6), ("funnel", "diag", 5, 10, 0.45, 6),
-                                                  ("dense_gauss", "dense", 6, 6, 0.7, 5)],
-                         ids=["diag-fast", "funnel-exact", "dense"])
-def test_hmc_transition_kernel_source_under_emulation_matches_oracle(emu_lf, kind, mkind, D, N, eps, n):
-    """K2 (`hmc_kernel`: momentum refresh from a normal tape, trajectory, Metropolis step, revert, flip) vs the oracle."""
+@pytest.mark.parametrize("kind,mkind,D,N,eps,n,alpha", [("diag_gauss", "diag", 7, 9, 0.6, 6, 0.0), ("funnel", "diag", 5, 10, 0.45, 6, 0.0),
+                                                        ("dense_gauss", "dense", 6, 6, 0.7, 5, 0.0), ("diag_gauss", "diag", 7, 9, 0.6, 7, 1.1),
+                                                        ("funnel", "diag", 5, 10, 0.45, 6, 0.93)],
+                         ids=["diag-fast", "funnel-exact", "dense", "diag-tempered", "funnel-tempered"])
+def test_hmc_transition_kernel_source_under_emulation_matches_oracle(emu_lf, kind, mkind, D, N, eps, n, alpha):
+    """K2 (`hmc_kernel`: momentum refresh from a normal tape, trajectory, Metropolis step, revert, flip) vs the oracle;
+    alpha > 0: the trajectory is integrated by `TemperedLeapfrog(eps, alpha)` (odd and even n: the middle step of an odd
+    trajectory multiplies before and divides after, integrator.jl:198-209)."""
     rng = np.random.default_rng(21 + D)
     model, metric, p0, dp1, Minv, cholU = _lf_system(kind, mkind, D, rng)
     th = rng.normal(size=(N, D)) * (1.5 if kind == "funnel" else 1.0)
     nt, et = rng.normal(size=(N, D)), rng.exponential(size=N)
     z0 = oc.phasepoint(model, metric, th.T, np.zeros((D, N)))
-    zo, so = oc.hmc_transition(model, metric, eps, n, z0, nt.T, et)
+    oc.set_tempering(alpha)
+    try:
+        zo, so = oc.hmc_transition(model, metric, eps, n, z0, nt.T, et)
+    finally:
+        oc.set_tempering(0.0)
     g_in, lp_in = np.ascontiguousarray(z0.lp_gradient.T), np.ascontiguousarray(z0.lp_value)
     o = {k: np.zeros((N, D)) for k in ("th", "r", "g")}
     lp_o, lk_o, acc, dH = (np.zeros(N) for _ in range(4))
     isacc = np.zeros(N, dtype=np.uint8)
     r0 = np.zeros((N, D))
     q = EmuLf(model_kind=KINDS[kind], metric_kind=MKINDS[mkind], D=D, N=N, p0=P(p0), p1=P(dp1), c0=0.0, Minv=P(Minv),
-              minv_stride=0, cholU=P(cholU), eps=eps, eps_chain=None, n_steps=n, fwd=1, temper_alpha=0.0, th_in=P(th), r_in=P(r0),
+              minv_stride=0, cholU=P(cholU), eps=eps, eps_chain=None, n_steps=n, fwd=1, temper_alpha=alpha, th_in=P(th), r_in=P(r0),
               g_in=P(g_in), lp_in=P(lp_in), th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]), lp_out=P(lp_o), lk_out=P(lk_o),
               dr_out=None, status=None, steps_done=None, flags=0, hmc=1, refresh=1, n_transitions=1, seed=1, offset=0,
               normal_tape=P(nt), exp_tape=P(et), is_accept=P(isacc), acc=P(acc), dH=P(dH), draws=None)
@@ -342,7 +367,7 @@ class EmuMn(C.Structure):
     _fields_ = [("model_kind", C.c_int32), ("metric_kind", C.c_int32), ("D", C.c_int32), ("N", C.c_int64), ("p0", _vp), ("p1", _vp),
                 ("Minv", _vp), ("cholU", _vp), ("eps", C.c_double), ("n_steps", C.c_int32), ("n_fwd", C.c_int32),
                 ("normal_tape", _vp), ("unif_tape", _vp), ("th_in", _vp), ("g_in", _vp), ("lp_in", _vp), ("th_out", _vp),
-                ("r_out", _vp), ("g_out", _vp), ("lp_out", _vp), ("lk_out", _vp), ("acc", _vp), ("index", _vp)]
+                ("r_out", _vp), ("g_out", _vp), ("lp_out", _vp), ("lk_out", _vp), ("acc", _vp), ("index", _vp), ("temper_alpha", C.c_double)]
 
 
 @pytest.fixture(scope="module")
@@ -394,6 +419,40 @@ def test_multinomial_static_kernel_source_under_emulation_matches_mp50_fixtures(
         assert np.allclose(lp_o, e["lp_value"], rtol=1e-10, atol=1e-10) and np.allclose(lk_o, e["lk_value"], rtol=1e-10, atol=1e-10)
         done += 1
     assert done == 3
+
+
+@pytest.mark.parametrize("n,n_fwd", [(7, 3), (6, 6), (5, 0)])
+def test_multinomial_static_with_tempered_leapfrog_under_emulation_matches_oracle(emu_mn, n, n_fwd):
+    """MultinomialTS static transition integrated by `TemperedLeapfrog`: the forward and the backward leg are separate
+    `step` calls (trajectory.jl:374-376), each tempering by its OWN number of steps -- also in the replay that
+    re-materialises the drawn point."""
+    rng = np.random.default_rng(500 + n)
+    D, N, eps, alpha = 7, 9, 0.35, 1.08
+    p0, p1 = rng.normal(size=D), np.exp(rng.uniform(-0.5, 0.5, D))
+    Minv = np.exp(rng.uniform(-0.5, 0.5, D))
+    model, metric = oc.Model(oc.DIAG_GAUSS, D, p0, p1, 0.0), oc.Metric(oc.DIAG, Minv)
+    th, nt, ut = rng.normal(size=(N, D)), rng.normal(size=(N, D)), rng.uniform(size=N)
+    z0 = oc.phasepoint(model, metric, th.T, np.zeros((D, N)))
+    oc.set_tempering(alpha)
+    try:
+        zo, so = oc.hmc_multinomial_transition(model, metric, eps, n, n_fwd, z0, nt.T, ut)
+    finally:
+        oc.set_tempering(0.0)
+    g_in, lp_in = np.ascontiguousarray(z0.lp_gradient.T), np.ascontiguousarray(z0.lp_value)
+    o = {k: np.zeros((N, D)) for k in ("th", "r", "g")}
+    lp_o, lk_o, acc = np.zeros(N), np.zeros(N), np.zeros(N)
+    idx = np.zeros(N, dtype=np.int32)
+    q = EmuMn(model_kind=oc.DIAG_GAUSS, metric_kind=oc.DIAG, D=D, N=N, p0=P(p0), p1=P(1.0 / (p1 * p1)), Minv=P(Minv), cholU=None,
+              eps=eps, n_steps=n, n_fwd=n_fwd, normal_tape=P(nt), unif_tape=P(ut), th_in=P(th), g_in=P(g_in), lp_in=P(lp_in),
+              th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]), lp_out=P(lp_o), lk_out=P(lk_o), acc=P(acc), index=P(idx),
+              temper_alpha=alpha)
+    assert emu_mn.emu_multinomial(C.byref(q)) == 0
+    assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10
+    assert np.allclose(acc, so.acceptance_rate, rtol=1e-10)
+    assert np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10) and np.allclose(lk_o, zo.lk_value, rtol=1e-10, atol=1e-10)
+    # tempering is not volume preserving: the energies along the legs differ visibly from the untempered ones
+    zu, su = oc.hmc_multinomial_transition(model, metric, eps, n, n_fwd, z0, nt.T, ut)
+    assert not np.allclose(su.acceptance_rate, so.acceptance_rate, rtol=1e-6)
 
 
 def test_adaptor_statistics_kernel_sources_under_emulation(tmp_path):
