@@ -39,6 +39,8 @@ struct ahmc_ctx {
     double* mn_scratch = nullptr;  // multinomial-static per-chain energy tape
     size_t mn_scratch_bytes = 0;
     char* dense_scratch = nullptr;  // K4: padded Minv, norms, per-chain fallback mask
+    double* coop_scratch = nullptr;  // cooperative NUTS products: Minv and cholU with padded columns (coop_lds)
+    size_t coop_scratch_doubles = 0;
     size_t dense_scratch_bytes = 0;
     char* split_scratch = nullptr;   // callback (split-step) mode workspace
     size_t split_scratch_bytes = 0;
@@ -66,6 +68,7 @@ struct ahmc_model {
     double* d_p0 = nullptr;
     double* d_p1 = nullptr;
     double* d_p1_pad = nullptr;  // DENSE_GAUSS: precision zero-padded to Dp x Dp (K4), followed by |P|_inf
+    double* d_p1_coop = nullptr; // DENSE_GAUSS: precision with columns padded to coop_lds(D) (cooperative NUTS products)
     int Dp = 0;
     double c0 = 0.0;
     ahmc_logp_grad_fn fn = nullptr;
@@ -244,12 +247,14 @@ size_t metric_minv_count(const ahmc_metric* m, int32_t D, int64_t N) {
     return 0;
 }
 
-ModelDev model_dev(const ahmc_model* m) { return ModelDev{m->kind, m->D, m->d_p0, m->d_p1, m->c0, m->rtc}; }
+ModelDev model_dev(const ahmc_model* m) { return ModelDev{m->kind, m->D, m->d_p0, m->d_p1, m->c0, m->rtc, m->d_p1_coop}; }
 
 // stage the metric descriptor (device or host pointers) into a MetricDev
 int stage_metric(Stager& st, const ahmc_metric* m, int32_t D, int64_t N, MetricDev* out) {
     out->kind = m->kind;
     out->chain_stride = m->kind == AHMC_METRIC_DIAG ? m->chain_stride : 0;
+    out->Minv_coop = nullptr;
+    out->cholU_coop = nullptr;
     int rc = st.in(m->Minv, metric_minv_count(m, D, N), &out->Minv);
     if (rc) return rc;
     return st.in(m->kind == AHMC_METRIC_DENSE ? m->cholU : (const double*)nullptr, (size_t)D * D, &out->cholU);
@@ -460,6 +465,7 @@ int ahmc_destroy(ahmc_ctx* ctx) {
     cudaFree(ctx->adapt_scratch);
     cudaFree(ctx->mn_scratch);
     cudaFree(ctx->dense_scratch);
+    cudaFree(ctx->coop_scratch);
     cudaFree(ctx->split_scratch);
     for (int i = 0; i < ahmc_ctx::kPipeStreams; ++i) {
         if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
@@ -532,6 +538,14 @@ int ahmc_model_create(ahmc_ctx* ctx, int32_t kind, int32_t D, const double* p0, 
             launch_pad_norm(m->d_p1, D, m->Dp, m->d_p1_pad, m->d_p1_pad + dense_mat_doubles(m->Dp), ctx->stream);
             cudaStreamSynchronize(ctx->stream);
         }
+        if (D > 16 && D <= 512) {  // the layouts the cooperative NUTS form runs on (one chain per warp)
+            if (cudaMalloc((void**)&m->d_p1_coop, sizeof(double) * coop_padded_doubles(D)) != cudaSuccess) {
+                ahmc_model_destroy(ctx, m);
+                return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc for the column-padded precision failed");
+            }
+            launch_pad_columns(m->d_p1, D, m->d_p1_coop, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -601,6 +615,7 @@ int ahmc_model_destroy(ahmc_ctx* ctx, ahmc_model* m) {
         cudaFree(m->d_p0);
         cudaFree(m->d_p1);
         cudaFree(m->d_p1_pad);
+        cudaFree(m->d_p1_coop);
         if (m->rtc) {
             cudaStreamSynchronize(ctx->stream);
             user_module_destroy(m->rtc);
@@ -1410,6 +1425,30 @@ static int nuts_impl(ahmc_ctx* ctx, const ahmc_model* model, const ahmc_metric* 
     NutsArgs a{};
     a.model = model_dev(model);
     if ((rc = stage_metric(st, metric, D, N, &a.metric))) return rc;
+    int n_prep = 0;
+    if (a.metric.kind == AHMC_METRIC_DENSE && D > 16 && D <= 512) {
+        // the cooperative form streams Minv / cholU in chunks of columns: hand it copies whose columns are padded to the
+        // shared-memory leading dimension, so that a chunk is one bulk copy (two small kernels per call, on the stream)
+        const size_t per = coop_padded_doubles(D);
+        if (2 * per > ctx->coop_scratch_doubles) {
+            CU(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->coop_scratch);
+            ctx->coop_scratch = nullptr;
+            ctx->coop_scratch_doubles = 0;
+            if (cudaMalloc((void**)&ctx->coop_scratch, 2 * per * sizeof(double)) != cudaSuccess)
+                return fail(ctx, AHMC_ERR_NOMEM, "cudaMalloc for the column-padded metric failed");
+            ctx->coop_scratch_doubles = 2 * per;
+        }
+        CU(launch_pad_columns(a.metric.Minv, D, ctx->coop_scratch, ctx->stream));
+        a.metric.Minv_coop = ctx->coop_scratch;
+        ++n_prep;
+        if (a.metric.cholU) {
+            CU(launch_pad_columns(a.metric.cholU, D, ctx->coop_scratch + per, ctx->stream));
+            a.metric.cholU_coop = ctx->coop_scratch + per;
+            ++n_prep;
+        }
+    }
+    ctx->launches += n_prep;
     a.D = D;
     a.N = N;
     a.eps = eps;

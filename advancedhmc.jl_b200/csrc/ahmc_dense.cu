@@ -35,52 +35,7 @@ constexpr int kBars = 2 * kStages;  // full[kStages] + empty[kStages]
 extern unsigned char* emu_dynamic_smem;  // the block's dynamic shared memory (blocks run one at a time)
 #endif
 
-#ifdef AHMC_SIMT_EMULATION
-// CPU SIMT emulation (tests/simt_emu/dense_emu.cpp): the five PTX wrappers below are provided by the harness with the
-// same contracts -- an mbarrier as (completed phases, pending bytes), a synchronous bulk copy, the m8n8k4 fragment map.
-void mbar_init(uint64_t* bar, int count);
-void mbar_fence_init();
-void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
-void mbar_arrive(uint64_t* bar);
-void mbar_wait(uint64_t* bar, uint32_t parity);
-void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
-void dmma(double& d0, double& d1, double a, double b);
-#else
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-#endif  // AHMC_SIMT_EMULATION
+// (mbarrier / bulk-copy / DMMA wrappers: ahmc_device.cuh)
 
 // Y += A * X for the CTA's tile.  A: Dp x Dp column-major (padded, zero-filled) in global memory.
 // Xs: CT x Dx doubles in shared memory (chain-major, Dx = Dp + 4).  acc[rb][cb][2]: this thread's accumulators:

@@ -53,6 +53,8 @@ struct ModelDev {
     const double* p1;  // DIAG_GAUSS: w = 1/s^2 ; DENSE_GAUSS: precision D x D (column-major)
     double c0;
     const void* user;  // USER: host-side handle of the run-time compiled kernels (never dereferenced on the device)
+    const double* p1_coop;  // DENSE_GAUSS, nullable: the precision with padded columns (leading dimension coop_lds(D), zero
+                            // filled) -- the cooperative products then fetch a whole chunk of columns with ONE bulk copy
 };
 
 // doubles of per-group shared-memory slab a kernel family needs: dense operators stage one D-vector, a user target a
@@ -65,6 +67,8 @@ struct MetricDev {
     const double* Minv;
     long long chain_stride;
     const double* cholU;
+    const double* Minv_coop;   // Dense, nullable: Minv / cholU with padded columns (see ModelDev::p1_coop)
+    const double* cholU_coop;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -237,137 +241,233 @@ __device__ __forceinline__ void matvec(const double* __restrict__ A, int D, cons
     }
 }
 
-// CTA-cooperative form of the product for kernels that own ONE chain per warp (G = 32) and whose warps can rendezvous:
-// every warp of the block calls it at the same point with its own chain's x; the matrix is streamed from L2 into shared
-// memory ONCE per block (instead of once per warp), warp w computes rows [w R, (w+1) R), R = ceil(D / nwarps), of the
-// product for ALL the block's chains (each matrix element read from shared memory feeds nwarps FMAs), and the results
-// return through a second slab.  Shared-memory layout (doubles, from `base`): X slab [nwarps][D] | Y slab [nwarps][D] |
-// A stage [kCoopKC][D].  Warps whose chain is idle still take part (their result is ignored by the caller).
-constexpr int kCoopKCMax = 16;
-// matrix columns per stage
-__host__ __device__ constexpr int coop_kc(int D) { return 8; }  // (16 at D <= 256 measured the same: 4.4e9 on C5)
-// stages of the L2 -> shared-memory pipeline (cp.async, stages - 1 chunks in flight)
-__host__ __device__ constexpr int coop_stages(int D) { return 3; }  // (6 stages at D = 256 measured slower: 2.4e9 vs 3.4e9 on C5)
-constexpr int kCoopWarps = 8;   // warps (= chains) per block of the kernels that use it
-constexpr int kCoopThreads = 32 * kCoopWarps;
-// X slab is stored TRANSPOSED, [D][kCoopWarps]: the kCoopWarps values x_c[k] of one column index are adjacent (128-bit loads)
-__host__ __device__ constexpr int coop_smem_doubles(int D) { return 2 * kCoopWarps * D + coop_stages(D) * coop_kc(D) * (D + 4); }
-
-// The stages hold columns with a padded leading dimension (D + 4 doubles) so that the fragment loads of the fp64 MMA below --
-// 4 columns x 8 rows per warp instruction -- fall into distinct banks.
-__host__ __device__ constexpr int coop_lds(int D) { return D + 4; }
-
-// `ncols` columns of D doubles each (contiguous in global memory) -> shared columns of leading dimension coop_lds(D);
-// `async`: 16-byte cp.async (D even, 16-byte aligned source), completed by coop_wait below
-__device__ __forceinline__ void coop_fetch(double* dst, const double* __restrict__ src, int ncols, int D, bool async) {
-    // warp w moves columns w, w + 8, ... of the chunk: no index arithmetic beyond strides
-    const int lane = threadIdx.x & 31;
-    for (int k = threadIdx.x >> 5; k < ncols; k += kCoopWarps) {
-        double* d_col = dst + k * coop_lds(D);
-        const double* s_col = src + (long long)k * D;
-#if !defined(AHMC_SIMT_EMULATION)
-        if (async) {
-            for (int d = 2 * lane; d < D; d += 64) {
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(d_col + d);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(s_col + d) : "memory");
-            }
-            continue;
-        }
-#endif
-        for (int d = lane; d < D; d += 32) d_col[d] = __ldg(s_col + d);
-    }
-}
-__device__ __forceinline__ void coop_commit() {
-#if !defined(AHMC_SIMT_EMULATION)
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <int N>
-__device__ __forceinline__ void coop_wait() {  // all but the N most recent groups of this thread have landed
-#if !defined(AHMC_SIMT_EMULATION)
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-#endif
-}
-// mma.sync.aligned.m8n8k4.row.col.f64 (DMMA; tcgen05 has no f64 kind): lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4)+{0,1}]
-__device__ __forceinline__ void coop_dmma(double& d0, double& d1, double a, double b) {
-#if defined(AHMC_SIMT_EMULATION)
-    double A_[32], B_[32];
-    emu_gather2(a, b, A_, B_);
-    const int lane = emu_lane(), row = lane >> 2, c0 = 2 * (lane & 3);
-    for (int k = 0; k < 4; ++k) {
-        d0 = fma(A_[row * 4 + k], B_[c0 * 4 + k], d0);
-        d1 = fma(A_[row * 4 + k], B_[(c0 + 1) * 4 + k], d1);
-    }
+// ------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy / fp64-MMA wrappers (K4's tile product, ahmc_dense.cu, and the cooperative products below).
+// Under the CPU SIMT emulation the harness provides them with the same contracts (tests/simt_emu/simt_emu.cpp): an
+// mbarrier is (completed phases, pending arrivals, pending transaction bytes), `mbar_wait(parity)` returns once the phase
+// of that parity has completed, `bulk_g2s` copies synchronously and completes its bytes on the barrier, `dmma` is
+// mma.sync.aligned.m8n8k4.row.col.f64 (tcgen05 has no f64 kind): lane l holds A[l/4][l%4], B[l%4][l/4], C[l/4][2(l%4)+{0,1}].
+// ------------------------------------------------------------------------------------------------
+#ifdef AHMC_SIMT_EMULATION
+void mbar_init(uint64_t* bar, int count);
+void mbar_inval(uint64_t* bar);
+void mbar_fence_init();
+void mbar_expect_tx(uint64_t* bar, uint32_t bytes);
+void mbar_arrive(uint64_t* bar);
+void mbar_wait(uint64_t* bar, uint32_t parity);
+void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar);
+void dmma(double& d0, double& d1, double a, double b);
 #else
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+#endif  // AHMC_SIMT_EMULATION
+
+// ------------------------------------------------------------------------------------------------
+// CTA-cooperative dense products for kernels that own ONE chain per warp (G = 32) and whose warps can rendezvous (the
+// NUTS form for dense operators): all kCoopWarps warps of the block call at the same point, each with its own chain's
+// vector.  The matrix is streamed from L2 into shared memory ONCE per block, kCoopKC columns per stage, by bulk copies
+// (cp.async.bulk, one per column, issued by warp 0, completion on the stage's "full" mbarrier); a stage is handed back
+// through its "empty" mbarrier (one arrival per warp), which only the issuing warp waits on -- no block barrier inside the
+// product.  Y[D x 8] = A X[D x 8] runs on the fp64 tensor pipe: a warp owns 16-row blocks q = w, w + 8, ... ; lane
+// (fr = l/4, fk = l%4) reads rows 16q + 2fr + {0,1} of column fk as ONE 128-bit shared load = the A fragments of two
+// m8n8k4 tiles (tile j holds rows 16q + 2fr' + j, fr' = 0..7: which rows form a tile is free, C's rows follow), and the B
+// fragment (the 8 chains' x at 4 consecutive k) as one 64-bit load: 3 shared loads per 4 DMMAs at D = 256.
+// Shared-memory layout (doubles, from `base`): X slab [D][8] (transposed: the 8 chains' x[k] adjacent) | Y slab [8][D] |
+// coop_stages(D) stages [kCoopKC][lds] (lds = D rounded up to 16, + 4: the 16-row fragment blocks of a ragged D stay inside
+// their column -- rows beyond D are read, never used -- column starts are 16-byte aligned and the 128-bit fragment loads of
+// 4 columns fall into distinct banks) | 16 doubles of slack | 2 coop_stages(D) mbarriers.  Idle warps still take part.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCoopKC = 8;       // matrix columns per stage (16 measured the same on C5)
+// stages of the L2 -> shared-memory pipeline (stages - 1 chunks in flight): the kernels that use it run one block per SM,
+// so shared memory is there to spend on depth while a stage is D x 8 doubles
+#ifndef AHMC_COOP_STAGES
+#define AHMC_COOP_STAGES 6
 #endif
+__host__ __device__ constexpr int coop_stages(int D) { return D <= 256 ? AHMC_COOP_STAGES : 3; }
+constexpr int kCoopWarps = 8;    // warps (= chains) per block of the kernels that use it
+constexpr int kCoopThreads = 32 * kCoopWarps;
+__host__ __device__ constexpr int coop_lds(int D) { return ((D + 15) & ~15) + 4; }
+__host__ __device__ constexpr int coop_stage_doubles(int D) { return kCoopKC * coop_lds(D); }
+__host__ __device__ constexpr int coop_smem_doubles(int D) { return 2 * kCoopWarps * D + coop_stages(D) * coop_stage_doubles(D) + 16 + 2 * coop_stages(D); }
+
+// `ncols` columns (src + k*D, `rows` leading entries each) -> stage columns of leading dimension coop_lds(D); completes on
+// `full`.  Called by ALL lanes of warp 0, converged.  bulk: 16-byte aligned source columns and an even number of rows.
+// `padded` (nullable): the same columns in a copy of the matrix whose leading dimension already is coop_lds(D) -- the chunk
+// is then ONE contiguous bulk copy instead of one per column (a bulk copy costs the copy engine of the SM a fixed time
+// that 2 KB does not amortise: 3.8e9 -> 5.0e9 steps x dims/s on the C5 shape, even with unpadded, bank-conflicting stages).
+__device__ __forceinline__ void coop_issue(double* stage, const double* __restrict__ src, const double* __restrict__ padded, int ncols,
+                                           int rows, int D, bool bulk, uint64_t* full) {
+    const int lane = threadIdx.x & 31;
+    const int lds = coop_lds(D);
+    if (padded) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(ncols * lds * 8);
+            mbar_expect_tx(full, bytes);
+            bulk_g2s(stage, padded, bytes, full);
+        }
+        return;
+    }
+    if (bulk) {
+        if (lane == 0) mbar_expect_tx(full, (uint32_t)(ncols * rows * 8));
+        if (lane < ncols) bulk_g2s(stage + lane * lds, src + (long long)lane * D, (uint32_t)(rows * 8), full);
+    } else {
+        for (int k = 0; k < ncols; ++k)
+            for (int d = lane; d < rows; d += 32) stage[k * lds + d] = __ldg(src + (long long)k * D + d);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full);
+    }
+}
+// (re)arm the pipeline's barriers for one cooperative call; thread 0, before the call's first block barrier.  The kernel
+// initialises them once (coop_begin) so that every later call can invalidate and re-initialise: phases start at 0 per call.
+__device__ __forceinline__ uint64_t* coop_bars(double* base, int D) {
+    return reinterpret_cast<uint64_t*>(base + 2 * kCoopWarps * D + coop_stages(D) * coop_stage_doubles(D) + 16);
+}
+__device__ __forceinline__ void coop_arm(uint64_t* bars, int S, bool first) {
+    for (int s = 0; s < S; ++s) {
+        if (!first) {
+            mbar_inval(&bars[s]);
+            mbar_inval(&bars[S + s]);
+        }
+        mbar_init(&bars[s], 1);               // full: the issuing lane's arrival (+ the copied bytes)
+        mbar_init(&bars[S + s], kCoopWarps);  // empty: one arrival per warp
+    }
+    mbar_fence_init();
+}
+// once per kernel, by every thread of the block, before the first cooperative call
+__device__ __forceinline__ void coop_begin(double* base, int D) {
+    if (threadIdx.x == 0) coop_arm(coop_bars(base, D), coop_stages(D), true);
+    __syncthreads();
 }
 
-// Y[D x 8] = A[D x D] X[D x 8] for the block's 8 chains on the fp64 tensor pipe: warp w owns the 8-row blocks w, w+8, ...;
-// per 4 columns one B fragment (the 8 chains' x) and one A fragment + one DMMA per row block.
-template <int E, int kCoopStages>
-__device__ __forceinline__ void matvec_coop_s(const double* __restrict__ A, int D, const double (&x)[E], double (&y)[E],
-                                              double* base, int l) {
-    constexpr int nw = kCoopWarps;
+template <int E>
+__device__ __forceinline__ void matvec_coop(const double* __restrict__ A, const double* __restrict__ Ap, int D, const double (&x)[E],
+                                            double (&y)[E], double* base, int l) {
+    constexpr int nw = kCoopWarps, KC = kCoopKC;
+    const int S = coop_stages(D);
     static_assert(nw == 8, "the DMMA tile has 8 columns: one per chain of the block");
     const int w = threadIdx.x >> 5;
     double* Xs = base;                 // [D][nw]
     double* Ys = base + nw * D;        // [nw][D]
-    double* As = base + 2 * nw * D;    // kCoopStages x [coop_kc(D)][D + 4]
-    // (no barrier needed on entry: the previous call's last barrier precedes every warp's read of ITS Y rows, and X / A are
-    //  only re-written here before / after barriers every warp reaches after those reads)
+    double* As = base + 2 * nw * D;    // S x [KC][lds]
+    uint64_t* bars = coop_bars(base, D);
+    const int lds = coop_lds(D), stage_doubles = coop_stage_doubles(D);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int d = l + 32 * e;
         if (d < D) Xs[d * nw + w] = x[e];
     }
-    constexpr int RBW = (E + 1) / 2;  // row blocks per warp: ceil(D / 8) <= 4 E blocks over 8 warps
-    double acc[RBW][2];
+    if (threadIdx.x == 0) coop_arm(bars, S, false);
+    __syncthreads();  // X slab and barriers visible; every warp has left the previous cooperative call
+    const int nchunks = (D + KC - 1) / KC;
+    const bool bulk = ((D & 1) == 0) && ((reinterpret_cast<unsigned long long>(A) & 15ull) == 0);
+    auto chunk_cols = [&](int c) { return (D - c * KC < KC) ? D - c * KC : KC; };
+    if (w == 0)
+        for (int c = 0; c < S && c < nchunks; ++c)
+            coop_issue(As + c * stage_doubles, A + (long long)D * c * KC, Ap ? Ap + (long long)lds * c * KC : nullptr, chunk_cols(c), D, D,
+                       bulk, &bars[c]);
+    constexpr int PBW = (E + 3) / 4;  // 16-row blocks per warp: ceil(D / 16) <= 2 E blocks over 8 warps
+    double acc[PBW][2][2];            // [block][row 2fr + j][chain 2fk + jj]
 #pragma unroll
-    for (int i = 0; i < RBW; ++i) acc[i][0] = acc[i][1] = 0.0;
-    const int lds = coop_lds(D);
-    const int kCoopKC = coop_kc(D);
-    const int nchunks = (D + kCoopKC - 1) / kCoopKC;
-    const int stage_doubles = kCoopKC * lds;
-    // 16-byte copies: an even number of doubles per column and 16-byte aligned sources
-    const bool async = ((D & 1) == 0) && ((reinterpret_cast<unsigned long long>(A) & 15ull) == 0);
-    auto chunk_cols = [&](int c) { return (D - c * kCoopKC < kCoopKC) ? D - c * kCoopKC : kCoopKC; };
-#pragma unroll
-    for (int c = 0; c < kCoopStages - 1; ++c) {  // prologue: chunks 0 .. S-2 in flight
-        if (c < nchunks) coop_fetch(As + c * stage_doubles, A + (long long)D * c * kCoopKC, chunk_cols(c), D, async);
-        coop_commit();
-    }
-    const int fk = l & 3, fr = l >> 2;  // fragment coordinates of this lane: column within the group of 4, row within the block of 8
+    for (int p = 0; p < PBW; ++p) acc[p][0][0] = acc[p][0][1] = acc[p][1][0] = acc[p][1][1] = 0.0;
+    const int fk = l & 3, fr = l >> 2;
+    int stage = 0, pstage = 0;
+    uint32_t par = 0, ppar = 0;
     for (int c = 0; c < nchunks; ++c) {
-        coop_wait<kCoopStages - 2>();  // this thread's copies of chunk c have landed ...
-        __syncthreads();               // ... and everyone's; every warp is also done with chunk c-1 (its stage is refilled next)
-        {
-            const int cn = c + kCoopStages - 1;
-            if (cn < nchunks) coop_fetch(As + (cn % kCoopStages) * stage_doubles, A + (long long)D * cn * kCoopKC, chunk_cols(cn), D, async);
-            coop_commit();
-        }
-        const double* as = As + (c % kCoopStages) * stage_doubles;
-        const int kc = chunk_cols(c), k0 = c * kCoopKC;
-        for (int ks = 0; ks < kCoopKC / 4; ++ks) {
-            const int kl = 4 * ks + fk;            // column of this lane inside the chunk
-            const bool kin = kl < kc;
-            const double b = kin ? Xs[(k0 + kl) * nw + fr] : 0.0;  // B[k][chain = fr]
+        mbar_wait(&bars[stage], par);  // chunk c has landed
+        const double* as = As + stage * stage_doubles + 2 * fr;
+        const int kc = chunk_cols(c);
+        const double* xk = Xs + (c * KC) * nw + fr;
+        if (kc == KC) {
 #pragma unroll
-            for (int i = 0; i < RBW; ++i) {
-                const int r = 8 * (w + nw * i) + fr;
-                const double av = (kin && r < D) ? as[kl * lds + r] : 0.0;
-                coop_dmma(acc[i][0], acc[i][1], av, b);
+            for (int ks = 0; ks < KC / 4; ++ks) {
+                const int kl = 4 * ks + fk;
+                const double b = xk[kl * nw];  // B[k][chain = fr]
+#pragma unroll
+                for (int p = 0; p < PBW; ++p) {
+                    const int q = w + nw * p;
+                    if (16 * q < D) {  // (rows >= D of a ragged block: read, accumulated, never stored)
+                        const double2 a2 = *reinterpret_cast<const double2*>(as + kl * lds + 16 * q);
+                        dmma(acc[p][0][0], acc[p][0][1], a2.x, b);
+                        dmma(acc[p][1][0], acc[p][1][1], a2.y, b);
+                    }
+                }
+            }
+        } else {  // the ragged last chunk: columns >= D contribute exact zeros
+#pragma unroll
+            for (int ks = 0; ks < KC / 4; ++ks) {
+                const int kl = 4 * ks + fk;
+                const bool kin = kl < kc;
+                const double b = kin ? xk[kl * nw] : 0.0;
+#pragma unroll
+                for (int p = 0; p < PBW; ++p) {
+                    const int q = w + nw * p;
+                    if (16 * q < D) {
+                        double2 a2 = make_double2(0.0, 0.0);
+                        if (kin) a2 = *reinterpret_cast<const double2*>(as + kl * lds + 16 * q);
+                        dmma(acc[p][0][0], acc[p][0][1], a2.x, b);
+                        dmma(acc[p][1][0], acc[p][1][1], a2.y, b);
+                    }
+                }
             }
         }
-    }
-    coop_wait<0>();
-#pragma unroll
-    for (int i = 0; i < RBW; ++i) {
-        const int r = 8 * (w + nw * i) + fr;
-        if (r < D) {
-            Ys[(2 * fk) * D + r] = acc[i][0];
-            Ys[(2 * fk + 1) * D + r] = acc[i][1];
+        __syncwarp();
+        if (l == 0) mbar_arrive(&bars[S + stage]);  // this warp is done with the stage
+        // warp 0 refills the stage of the PREVIOUS chunk (its last readers are at most one chunk behind) with chunk c-1+S
+        if (w == 0 && c >= 1 && c - 1 + S < nchunks) {
+            mbar_wait(&bars[S + pstage], ppar);
+            const int cn = c - 1 + S;
+            coop_issue(As + pstage * stage_doubles, A + (long long)D * cn * KC, Ap ? Ap + (long long)lds * cn * KC : nullptr,
+                       chunk_cols(cn), D, D, bulk, &bars[pstage]);
         }
+        pstage = stage;
+        ppar = par;
+        if (++stage == S) {
+            stage = 0;
+            par ^= 1u;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < PBW; ++p) {
+        const int row = 16 * (w + nw * p) + 2 * fr;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            if (row + j < D) {
+                Ys[(2 * fk) * D + row + j] = acc[p][j][0];
+                Ys[(2 * fk + 1) * D + row + j] = acc[p][j][1];
+            }
     }
     __syncthreads();
 #pragma unroll
@@ -375,12 +475,6 @@ __device__ __forceinline__ void matvec_coop_s(const double* __restrict__ A, int 
         const int d = l + 32 * e;
         y[e] = (d < D) ? Ys[w * D + d] : 0.0;
     }
-}
-
-template <int E>
-__device__ __forceinline__ void matvec_coop(const double* __restrict__ A, int D, const double (&x)[E], double (&y)[E],
-                                            double* base, int l) {
-    matvec_coop_s<E, coop_stages(0)>(A, D, x, y, base, l);
 }
 
 // solve U x = z (U upper triangular, column-major) for a group-distributed vector; result in x.
@@ -406,56 +500,102 @@ __device__ __forceinline__ void upper_solve(const double* __restrict__ U, int D,
     }
 }
 
-// CTA-cooperative back substitution U x = z (see matvec_coop): every warp of the block solves for ITS chain, but the columns
-// of U are streamed from L2 into shared memory once per block, last chunk first, through the same cp.async stages -- the
-// per-column dependency chain then waits on shared memory (tens of cycles) instead of on L2 (hundreds): the warp-private form
-// above costs ~600 cycles x D per transition at D = 256, more than the whole tree of a short NUTS transition.
+// CTA-cooperative back substitution U X = Z for the block's 8 chains (see matvec_coop): blocked by 8 columns, last block
+// first.  Per block: (1) every warp solves ITS chain's 8 x 8 diagonal system from the staged columns (lanes 0..7 hold the
+// block's entries; 8 dependent steps of multiply-by-1/U_ii, shuffle, FMA); (2) after a block barrier the rows above the
+// block are updated for ALL chains at once on the fp64 tensor pipe, Z[rows][8] -= U[rows, block] X[block][8], the 16-row
+// blocks dealt round-robin to the warps as in matvec_coop.  The warp-private form above costs a serial chain of D pivots
+// each waiting on L2 (~600 cycles x D per transition at D = 256, more than the whole tree of a short NUTS transition);
+// the first cooperative version (pivot by pivot from shared memory) still spent 170 instructions per pivot per warp.
+// x / U_ii is computed as x * (1 / U_ii): one rounding more than the reference's `ldiv!` (metric.jl:311-320).
+// Only the upper triangle of U is ever used (what lies below may be anything, like the parent of Julia's `.U`).
 template <int E>
-__device__ __forceinline__ void upper_solve_coop(const double* __restrict__ U, int D, double (&x)[E], double* base, int l) {
-    constexpr int kCoopStages = 3;  // (any depth <= coop_stages(D) works: the stage region is the same)
-    double* As = base + 2 * kCoopWarps * D;
-    const int kCoopKC = coop_kc(D);
-    const int nchunks = (D + kCoopKC - 1) / kCoopKC;
-    const int lds = coop_lds(D);
-    const int stage_doubles = kCoopKC * lds;
-    const bool async = ((D & 1) == 0) && ((reinterpret_cast<unsigned long long>(U) & 15ull) == 0);
-    auto chunk_cols = [&](int c) { return (D - c * kCoopKC < kCoopKC) ? D - c * kCoopKC : kCoopKC; };
-    // chunk order: j = 0 .. nchunks-1 walks the column chunks from the LAST to the first
+__device__ __forceinline__ void upper_solve_coop(const double* __restrict__ U, const double* __restrict__ Up, int D, double (&x)[E],
+                                                 double* base, int l) {
+    constexpr int nw = kCoopWarps, KC = kCoopKC;
+    const int S = coop_stages(D);
+    const int w = threadIdx.x >> 5;
+    double* Xs = base;               // [D][nw]: right-hand sides in, solutions out
+    double* As = base + 2 * nw * D;  // S x [KC][lds]
+    uint64_t* bars = coop_bars(base, D);
+    const int lds = coop_lds(D), stage_doubles = coop_stage_doubles(D);
 #pragma unroll
-    for (int j = 0; j < kCoopStages - 1; ++j) {
-        const int c = nchunks - 1 - j;
-        if (c >= 0) coop_fetch(As + j * stage_doubles, U + (long long)D * c * kCoopKC, chunk_cols(c), D, async);
-        coop_commit();
+    for (int e = 0; e < E; ++e) {
+        const int d = l + 32 * e;
+        if (d < D) Xs[d * nw + w] = x[e];
     }
-    for (int j = 0; j < nchunks; ++j) {
-        coop_wait<kCoopStages - 2>();
-        __syncthreads();
-        {
-            const int jn = j + kCoopStages - 1, cn = nchunks - 1 - jn;
-            if (cn >= 0) coop_fetch(As + (jn % kCoopStages) * stage_doubles, U + (long long)D * cn * kCoopKC, chunk_cols(cn), D, async);
-            coop_commit();
+    if (threadIdx.x == 0) coop_arm(bars, S, false);
+    __syncthreads();
+    const int nb = (D + KC - 1) / KC;
+    const bool bulk = ((D & 1) == 0) && ((reinterpret_cast<unsigned long long>(U) & 15ull) == 0);
+    auto blk_cols = [&](int b) { return (D - b * KC < KC) ? D - b * KC : KC; };
+    auto blk_rows = [&](int b) { return (b * KC + KC < D) ? b * KC + KC : D; };  // rows 0 .. end of the diagonal block
+    // step j handles block b = nb - 1 - j
+    if (w == 0)
+        for (int j = 0; j < S && j < nb; ++j) {
+            const int b = nb - 1 - j;
+            coop_issue(As + j * stage_doubles, U + (long long)D * b * KC, Up ? Up + (long long)lds * b * KC : nullptr, blk_cols(b),
+                       blk_rows(b), D, bulk, &bars[j]);
         }
-        const int c = nchunks - 1 - j, k0 = c * kCoopKC;
-        const double* us = As + (j % kCoopStages) * stage_doubles;
-        for (int k = chunk_cols(c) - 1; k >= 0; --k) {
-            const int i = k0 + k;
-            const double* col = us + k * lds;
-            const int le = i & 31, ee = i >> 5;
-            double xi = 0.0;
+    const int fk = l & 3, fr = l >> 2;
+    int stage = 0;
+    uint32_t par = 0;
+    for (int j = 0; j < nb; ++j) {
+        const int b = nb - 1 - j, k0 = b * KC, kc = blk_cols(b);
+        mbar_wait(&bars[stage], par);
+        const double* us = As + stage * stage_doubles;
+        {   // (1) diagonal block, chain w: lane i < kc holds entry k0 + i
+            const bool in = l < kc;
+            double z = in ? Xs[(k0 + l) * nw + w] : 0.0;
+            const double inv = in ? 1.0 / us[l * lds + k0 + l] : 0.0;
 #pragma unroll
-            for (int e = 0; e < E; ++e)
-                if (e == ee) xi = x[e];
-            xi = Grp<32>::bcast(xi, le) / col[i];
+            for (int i = KC - 1; i >= 0; --i) {
+                if (i < kc) {  // (uniform)
+                    const double xi = __shfl_sync(FULL, z * inv, i);  // x_i = z_i / U_ii, final once every j > i is eliminated
+                    if (l == i) z = xi;
+                    else if (l < i) z = fma(-us[i * lds + k0 + l], xi, z);
+                }
+            }
+            if (in) Xs[(k0 + l) * nw + w] = z;
+        }
+        __syncthreads();  // the block's solutions of all 8 chains are in the slab
+        {   // (2) rows [0, k0) -= U[rows, block] * X[block]
+            const int npb = (k0 + 15) >> 4;
+            for (int q = w; q < npb; q += nw) {
+                const int row = 16 * q + 2 * fr;
+                double2 c0 = *reinterpret_cast<const double2*>(Xs + row * nw + 2 * fk);        // row,     chains 2fk, 2fk+1
+                double2 c1 = *reinterpret_cast<const double2*>(Xs + (row + 1) * nw + 2 * fk);  // row + 1  (rows >= k0: read, never stored)
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int d = l + 32 * e;
-                if (d == i) x[e] = xi;
-                else if (d < i) x[e] = fma(-col[d], xi, x[e]);
+                for (int ks = 0; ks < KC / 4; ++ks) {
+                    const int kl = 4 * ks + fk;
+                    const bool kin = kl < kc;
+                    const double bneg = kin ? -Xs[(k0 + kl) * nw + fr] : 0.0;
+                    double2 a2 = make_double2(0.0, 0.0);
+                    if (kin) a2 = *reinterpret_cast<const double2*>(us + kl * lds + row);
+                    dmma(c0.x, c0.y, a2.x, bneg);
+                    dmma(c1.x, c1.y, a2.y, bneg);
+                }
+                if (row < k0) *reinterpret_cast<double2*>(Xs + row * nw + 2 * fk) = c0;
+                if (row + 1 < k0) *reinterpret_cast<double2*>(Xs + (row + 1) * nw + 2 * fk) = c1;
             }
         }
+        __syncthreads();  // updated right-hand sides visible to the next block's diagonal solve; the stage is free
+        if (w == 0 && j + S < nb) {
+            const int bn = nb - 1 - (j + S);
+            coop_issue(As + stage * stage_doubles, U + (long long)D * bn * KC, Up ? Up + (long long)lds * bn * KC : nullptr, blk_cols(bn),
+                       blk_rows(bn), D, bulk, &bars[stage]);
+        }
+        if (++stage == S) {
+            stage = 0;
+            par ^= 1u;
+        }
     }
-    coop_wait<0>();
-    __syncthreads();  // the stages may be refilled by the next cooperative call
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int d = l + 32 * e;
+        if (d < D) x[e] = Xs[d * nw + w];
+    }
+    __syncthreads();  // every warp has its solution before the slab is reused
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,6 +606,7 @@ struct MetricOps {
     double Minv[E];  // Diag only
     const double* A; // Dense only
     const double* U;
+    const double *Ac, *Uc;  // their padded copies for the cooperative products (nullable)
     int D;
     double* coop;    // non-null: dense products are CTA-cooperative through this shared-memory region (matvec_coop)
 
@@ -474,6 +615,8 @@ struct MetricOps {
         coop = nullptr;
         A = m.Minv;
         U = m.cholU;
+        Ac = m.Minv_coop;
+        Uc = m.cholU_coop;
         if (METRIC == AHMC_METRIC_DIAG) {
             vload<G, E>(Minv, m.Minv + m.chain_stride * chain, l, D);
         }
@@ -487,7 +630,7 @@ struct MetricOps {
 #pragma unroll
             for (int e = 0; e < E; ++e) dr[e] = Minv[e] * r[e];
         } else {
-            if (G == 32 && coop) matvec_coop<E>(A, D, r, dr, coop, l);
+            if (G == 32 && coop) matvec_coop<E>(A, Ac, D, r, dr, coop, l);
             else matvec<G, E>(A, D, r, dr, xs, l);
         }
     }
@@ -500,7 +643,7 @@ struct MetricOps {
                 r[e] = (d < D) ? r[e] / sqrt(Minv[e]) : 0.0;
             }
         } else if (METRIC == AHMC_METRIC_DENSE) {
-            if (G == 32 && coop) upper_solve_coop<E>(U, D, r, coop, l);
+            if (G == 32 && coop) upper_solve_coop<E>(U, Uc, D, r, coop, l);
             else upper_solve<G, E>(U, D, r, l);
         }
     }
@@ -514,6 +657,7 @@ struct ModelOps {
     double m[E];
     double w[E];
     const double* P;
+    const double* Pc;  // DENSE_GAUSS: padded copy of P for the cooperative product (nullable)
     double c0;
     int D;
     double* coop;  // see MetricOps
@@ -523,6 +667,7 @@ struct ModelOps {
         coop = nullptr;
         c0 = md.c0;
         P = md.p1;
+        Pc = md.p1_coop;
         if (MODEL == AHMC_MODEL_DIAG_GAUSS) {
             vload<G, E>(m, md.p0, l, D);
             vload<G, E>(w, md.p1, l, D);
@@ -569,7 +714,7 @@ struct ModelOps {
             double diff[E];
 #pragma unroll
             for (int e = 0; e < E; ++e) diff[e] = th[e] - m[e];
-            if (G == 32 && coop) matvec_coop<E>(P, D, diff, g, coop, l);
+            if (G == 32 && coop) matvec_coop<E>(P, Pc, D, diff, g, coop, l);
             else matvec<G, E>(P, D, diff, g, xs, l);
 #pragma unroll
             for (int e = 0; e < E; ++e) part = fma(diff[e], g[e], part);

@@ -265,6 +265,10 @@ cudaError_t launch_phasepoint(const PhasepointArgs& a, cudaStream_t stream, int*
 cudaError_t launch_rand_momentum(const MomentumArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_hmc(const HmcArgs& a, cudaStream_t stream, int* n_launches);
 cudaError_t launch_find_eps(const FindEpsArgs& a, cudaStream_t stream, int* n_launches);
+// A (D x D column-major) -> out with leading dimension coop_lds(D), zero filled (the cooperative NUTS products fetch whole
+// chunks of such columns with one bulk copy); coop_padded_doubles(D) doubles
+size_t coop_padded_doubles(int D);
+cudaError_t launch_pad_columns(const double* A, int D, double* out, cudaStream_t st);
 // D > 512: streaming form of step / phasepoint (ahmc_bigd.cu)
 bool bigd_supported(int model_kind, int metric_kind);
 cudaError_t launch_leapfrog_big(const LeapfrogArgs& a, cudaStream_t st);

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(COOP ? kCoopThreads : kBlockThreads, COOP ? 1 
     if constexpr (COOP) {
         mo.coop = smem;
         me.coop = smem;
+        coop_begin(smem, D);  // the pipeline's mbarriers (block barrier inside)
     }
 
     int nexp = 0, ndir = 0;

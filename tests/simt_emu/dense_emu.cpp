@@ -1,10 +1,6 @@
 // dense_emu.cpp -- K4, the tile-per-CTA trajectory kernel for GEMM-shaped operators (advancedhmc.jl_b200/csrc/
 // ahmc_dense.cu: `dense_traj_kernel`, `pad_norm_kernel`, `vec_norm_kernel`, unmodified) under the CPU SIMT emulator.
-// The kernel's five PTX wrappers are restated here with the same contracts:
-//   * an mbarrier is (completed phases, pending arrivals, pending transaction bytes); `mbar_wait(parity)` returns once
-//     the phase of that parity has completed;
-//   * `bulk_g2s` copies synchronously and completes its bytes on the barrier;
-//   * `dmma` is `mma.sync.aligned.m8n8k4.row.col.f64`: lane l holds A[l/4][l%4], B[l%4][l/4] and C[l/4][2(l%4)+{0,1}].
+// The kernel's PTX wrappers (mbarrier, bulk copy, DMMA) are restated in simt_emu.cpp with the same contracts.
 // TEST INFRASTRUCTURE ONLY (tests/test_simt_emulation.py).
 #define AHMC_SIMT_EMULATION 1
 #define __shared__ static  // static shared variables; blocks run one at a time
@@ -18,65 +14,7 @@ void emu_launch(void (*kernel)(const void*), const void* args, int blocks, int t
 
 namespace ahmc {
 unsigned char* emu_dynamic_smem = nullptr;
-// An mbarrier lives in the kernel's shared memory as one 64-bit word; here: bits 0..19 completed phases, 20..31 pending
-// arrivals of the current phase, 32..63 pending transaction bytes (biased by 2^31: complete_tx may precede expect_tx).
-// The expected arrival count of each barrier is kept beside it (indexed by its address: at most 8 barriers per block).
-namespace {
-constexpr uint64_t kTxBias = 1ull << 31;
-struct BarInfo {
-    uint64_t* bar;
-    uint32_t count;
-};
-BarInfo bar_info[8];
-std::atomic<int> n_bar_info{0};
-uint32_t expected_arrivals(uint64_t* bar) {
-    for (int i = 0; i < n_bar_info.load(); ++i)
-        if (bar_info[i].bar == bar) return bar_info[i].count;
-    return 0;  // unreachable for an initialised barrier
-}
-// apply (arrivals, +/- bytes) atomically; complete the phase when both reach zero
-void bar_update(uint64_t* bar, uint32_t arrivals, int64_t tx) {
-    std::atomic_ref<uint64_t> b(*bar);
-    uint64_t old = b.load(), neu;
-    do {
-        uint64_t phases = old & 0xfffffu, pend = (old >> 20) & 0xfffu;
-        int64_t bytes = (int64_t)(old >> 32) - (int64_t)kTxBias + tx;
-        pend -= arrivals;
-        if (pend == 0 && bytes == 0) {
-            phases = (phases + 1) & 0xfffffu;
-            pend = expected_arrivals(bar);
-        }
-        neu = phases | (pend << 20) | ((uint64_t)(bytes + (int64_t)kTxBias) << 32);
-    } while (!b.compare_exchange_weak(old, neu));
-}
-}  // namespace
-void mbar_init(uint64_t* bar, int count) {  // thread 0 only, before the block barrier
-    int i = 0;
-    for (; i < n_bar_info.load(); ++i)
-        if (bar_info[i].bar == bar) break;
-    if (i == n_bar_info.load()) n_bar_info.store(i + 1);
-    bar_info[i] = BarInfo{bar, (uint32_t)count};
-    std::atomic_ref<uint64_t>(*bar).store(((uint64_t)count << 20) | (kTxBias << 32));
-}
-void mbar_fence_init() {}
-void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { bar_update(bar, 1, (int64_t)bytes); }
-void mbar_arrive(uint64_t* bar) { bar_update(bar, 1, 0); }
-void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while ((uint32_t)(std::atomic_ref<uint64_t>(*bar).load() & 1u) == parity) std::this_thread::yield();
-}
-void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    std::memcpy(dst, src, bytes);
-    bar_update(bar, 0, -(int64_t)bytes);
-}
-void dmma(double& d0, double& d1, double a, double b) {
-    double A[32], B[32];
-    emu_gather2(a, b, A, B);
-    const int lane = emu_lane(), row = lane >> 2, c0 = 2 * (lane & 3);
-    for (int k = 0; k < 4; ++k) {
-        d0 = fma(A[row * 4 + k], B[c0 * 4 + k], d0);
-        d1 = fma(A[row * 4 + k], B[(c0 + 1) * 4 + k], d1);
-    }
-}
+// (the mbarrier / bulk-copy / DMMA contracts live in simt_emu.cpp: the cooperative NUTS products use them too)
 }  // namespace ahmc
 using namespace ahmc;
 
@@ -117,7 +55,7 @@ struct EmuDense {
 
 extern "C" int emu_dense_stages() { return kStages; }
 extern "C" int emu_dense(EmuDense* q) {
-    n_bar_info.store(0);
+    // (mbarrier table: reset per block by emu_launch)
     int Dp, RB, CB;
     if (!dense_tile_shape(q->D, &Dp, &RB, &CB)) return -1;
     std::vector<double> Pp, Mp;

@@ -46,6 +46,7 @@ struct EmuNuts {
     int32_t adapt_metric, n_min;
     double *eps_rw, *minv_rw, *eps_trace;
     double temper_alpha;
+    int32_t coop_padded;  // 1: also hand the kernel column-padded copies of the dense matrices (one bulk copy per chunk)
 };
 
 template <int MODEL, int METRIC, int G, int E, bool VAR, bool ADAPT>
@@ -119,6 +120,21 @@ extern "C" int emu_nuts(const EmuNuts* q) {
     NutsArgs a{};
     a.model = ModelDev{q->model_kind, D, q->p0, q->p1, q->c0};
     a.metric = MetricDev{q->metric_kind, q->Minv, q->minv_stride, q->cholU};
+    std::vector<double> pad_p, pad_m, pad_u;
+    if (q->coop_padded) {  // what ahmc_model_create / nuts_impl prepare on the device (launch_pad_columns)
+        const int lds = coop_lds(D);
+        auto pad = [&](const double* A, std::vector<double>& out) {
+            out.assign((size_t)D * lds, 0.0);
+            for (int k = 0; k < D; ++k)
+                for (int r = 0; r < D; ++r) out[(size_t)k * lds + r] = A[(size_t)k * D + r];
+            return out.data();
+        };
+        if (q->model_kind == AHMC_MODEL_DENSE_GAUSS) a.model.p1_coop = pad(q->p1, pad_p);
+        if (q->metric_kind == AHMC_METRIC_DENSE) {
+            a.metric.Minv_coop = pad(q->Minv, pad_m);
+            if (q->cholU) a.metric.cholU_coop = pad(q->cholU, pad_u);
+        }
+    }
     a.D = D;
     a.N = q->N;
     a.eps = q->eps;

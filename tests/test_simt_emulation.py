@@ -29,7 +29,7 @@ class EmuNuts(C.Structure):
                 ("adapt", C.c_int32), ("n_adapts", C.c_int32), ("init_buffer", C.c_int32), ("term_buffer", C.c_int32),
                 ("window_size", C.c_int32), ("delta", C.c_double), ("gamma", C.c_double), ("t0", C.c_double), ("kappa", C.c_double),
                 ("adapt_metric", C.c_int32), ("n_min", C.c_int32), ("eps_rw", _vp), ("minv_rw", _vp), ("eps_trace", _vp),
-                ("temper_alpha", C.c_double)]
+                ("temper_alpha", C.c_double), ("coop_padded", C.c_int32)]
 
 
 @pytest.fixture(scope="module")
@@ -52,7 +52,7 @@ KINDS = dict(std_normal=oc.STD_NORMAL, diag_gauss=oc.DIAG_GAUSS, dense_gauss=oc.
 MKINDS = dict(unit=oc.UNIT, diag=oc.DIAG, dense=oc.DENSE)
 
 
-def _case(lib, kind, mkind, D, N, eps, sampler, criterion, seed, max_depth=6, delta_max=1000.0, scale=1.0, temper=0.0):
+def _case(lib, kind, mkind, D, N, eps, sampler, criterion, seed, max_depth=6, delta_max=1000.0, scale=1.0, temper=0.0, coop_padded=0):
     rng = np.random.default_rng(seed)
     p0 = p1 = Minv = cholU = None
     if kind == "diag_gauss":
@@ -95,7 +95,7 @@ def _case(lib, kind, mkind, D, N, eps, sampler, criterion, seed, max_depth=6, de
                 exp_tape=P(var), exp_stride=var.shape[1], dir_tape=P(dirs), dir_stride=dirs.shape[1], partial_alpha=0.0,
                 refresh=0, th_in=P(th), r_in=P(r), g_in=P(g_in), lp_in=P(lp_in), th_out=P(out["th"]), r_out=P(out["r"]),
                 g_out=P(out["g"]), lp_out=P(lp_o), lk_out=P(lk_o), n_steps=P(ns), tree_depth=P(td), numerical=P(ne), acc=P(acc),
-                dH=P(dH), dHmax=P(dHm), n_transitions=1, draws=None, adapt=0, temper_alpha=temper)
+                dH=P(dH), dHmax=P(dHm), n_transitions=1, draws=None, adapt=0, temper_alpha=temper, coop_padded=coop_padded)
     assert lib.emu_nuts(C.byref(q)) == 0
     assert (td == so.tree_depth).all() and (ns == so.n_steps).all() and (ne == so.numerical_error).all()
     assert rel_err(out["th"].T, zo.theta) < 1e-10 and rel_err(out["r"].T, zo.r) < 1e-10
@@ -130,6 +130,15 @@ CASES = [
                          ids=[f"{c[0]}-{c[1]}-D{c[2]}-{c[5]}-{c[6]}" for c in CASES])
 def test_kernel_source_under_cpu_simt_emulation_matches_oracle(emu, kind, mkind, D, N, eps, sampler, criterion):
     so = _case(emu, kind, mkind, D, N, eps, sampler, criterion, seed=5 + D)
+    assert so.n_steps.max() >= 7
+
+
+@pytest.mark.parametrize("kind,mkind,D,N", [("dense_gauss", "dense", 40, 11), ("dense_gauss", "diag", 64, 9), ("diag_gauss", "dense", 33, 5),
+                                            ("dense_gauss", "dense", 200, 1)])
+def test_cooperative_products_from_column_padded_matrices_match_oracle(emu, kind, mkind, D, N):
+    """the cooperative NUTS form with the column-padded copies of the dense matrices the library prepares (one bulk copy
+    per chunk of columns instead of one per column): same transitions as from the plain matrices"""
+    so = _case(emu, kind, mkind, D, N, 0.3 if D < 100 else 0.25, "multinomial", "generalised", seed=5 + D, coop_padded=1)
     assert so.n_steps.max() >= 7
 
 
