@@ -298,7 +298,7 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // ------------------------------------------------------------------------------------------------
 // CTA-cooperative dense products for kernels that own ONE chain per warp (G = 32) and whose warps can rendezvous (the
 // NUTS form for dense operators): all kCoopWarps warps of the block call at the same point, each with its own chain's
-// vector.  The matrix is streamed from L2 into shared memory ONCE per block, kCoopKC columns per stage, by bulk copies
+// vector.  The matrix is streamed from L2 into shared memory ONCE per block, coop_kc<E>() columns per stage, by bulk copies
 // (cp.async.bulk, one per column, issued by warp 0, completion on the stage's "full" mbarrier); a stage is handed back
 // through its "empty" mbarrier (one arrival per warp), which only the issuing warp waits on -- no block barrier inside the
 // product.  Y[D x 8] = A X[D x 8] runs on the fp64 tensor pipe: a warp owns 16-row blocks q = w, w + 8, ... ; lane
@@ -306,22 +306,23 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // m8n8k4 tiles (tile j holds rows 16q + 2fr' + j, fr' = 0..7: which rows form a tile is free, C's rows follow), and the B
 // fragment (the 8 chains' x at 4 consecutive k) as one 64-bit load: 3 shared loads per 4 DMMAs at D = 256.
 // Shared-memory layout (doubles, from `base`): X slab [D][8] (transposed: the 8 chains' x[k] adjacent) | Y slab [8][D] |
-// coop_stages(D) stages [kCoopKC][lds] (lds = D rounded up to 16, + 4: the 16-row fragment blocks of a ragged D stay inside
+// coop_stages(D) stages [coop_kc<E>()][lds] (lds = D rounded up to 16, + 4: the 16-row fragment blocks of a ragged D stay inside
 // their column -- rows beyond D are read, never used -- column starts are 16-byte aligned and the 128-bit fragment loads of
 // 4 columns fall into distinct banks) | 16 doubles of slack | 2 coop_stages(D) mbarriers.  Idle warps still take part.
 // ------------------------------------------------------------------------------------------------
-constexpr int kCoopKC = 8;       // matrix columns per stage (16 measured the same on C5)
+// matrix columns per stage = per bulk copy and per pair of barrier operations, by the kernel's layout (E coordinates per
+// lane, D <= 32 E).  Measured on the C5 shape (D = 256, steps x dims/s): 8 columns x 6 stages 5.8e9, 16 x 4 8.2e9,
+// 24 x 3 8.6e9, 32 x 2 6.9e9; beyond D = 256 the stages must shrink to fit 227 KB.
+template <int E>
+__host__ __device__ constexpr int coop_kc() { return E <= 8 ? 24 : 16; }
 // stages of the L2 -> shared-memory pipeline (stages - 1 chunks in flight): the kernels that use it run one block per SM,
 // so shared memory is there to spend on depth while a stage is D x 8 doubles
-#ifndef AHMC_COOP_STAGES
-#define AHMC_COOP_STAGES 6
-#endif
-__host__ __device__ constexpr int coop_stages(int D) { return D <= 256 ? AHMC_COOP_STAGES : 3; }
+__host__ __device__ constexpr int coop_stages(int D) { return D <= 256 ? 3 : 2; }
 constexpr int kCoopWarps = 8;    // warps (= chains) per block of the kernels that use it
 constexpr int kCoopThreads = 32 * kCoopWarps;
 __host__ __device__ constexpr int coop_lds(int D) { return ((D + 15) & ~15) + 4; }
-__host__ __device__ constexpr int coop_stage_doubles(int D) { return kCoopKC * coop_lds(D); }
-__host__ __device__ constexpr int coop_smem_doubles(int D) { return 2 * kCoopWarps * D + coop_stages(D) * coop_stage_doubles(D) + 16 + 2 * coop_stages(D); }
+__host__ __device__ constexpr int coop_stage_doubles(int D, int KC) { return KC * coop_lds(D); }
+__host__ __device__ constexpr int coop_smem_doubles(int D, int KC) { return 2 * kCoopWarps * D + coop_stages(D) * coop_stage_doubles(D, KC) + 16 + 2 * coop_stages(D); }
 
 // `ncols` columns (src + k*D, `rows` leading entries each) -> stage columns of leading dimension coop_lds(D); completes on
 // `full`.  Called by ALL lanes of warp 0, converged.  bulk: 16-byte aligned source columns and an even number of rows.
@@ -352,8 +353,8 @@ __device__ __forceinline__ void coop_issue(double* stage, const double* __restri
 }
 // (re)arm the pipeline's barriers for one cooperative call; thread 0, before the call's first block barrier.  The kernel
 // initialises them once (coop_begin) so that every later call can invalidate and re-initialise: phases start at 0 per call.
-__device__ __forceinline__ uint64_t* coop_bars(double* base, int D) {
-    return reinterpret_cast<uint64_t*>(base + 2 * kCoopWarps * D + coop_stages(D) * coop_stage_doubles(D) + 16);
+__device__ __forceinline__ uint64_t* coop_bars(double* base, int D, int KC) {
+    return reinterpret_cast<uint64_t*>(base + 2 * kCoopWarps * D + coop_stages(D) * coop_stage_doubles(D, KC) + 16);
 }
 __device__ __forceinline__ void coop_arm(uint64_t* bars, int S, bool first) {
     for (int s = 0; s < S; ++s) {
@@ -367,23 +368,24 @@ __device__ __forceinline__ void coop_arm(uint64_t* bars, int S, bool first) {
     mbar_fence_init();
 }
 // once per kernel, by every thread of the block, before the first cooperative call
+template <int E>
 __device__ __forceinline__ void coop_begin(double* base, int D) {
-    if (threadIdx.x == 0) coop_arm(coop_bars(base, D), coop_stages(D), true);
+    if (threadIdx.x == 0) coop_arm(coop_bars(base, D, coop_kc<E>()), coop_stages(D), true);
     __syncthreads();
 }
 
 template <int E>
 __device__ __forceinline__ void matvec_coop(const double* __restrict__ A, const double* __restrict__ Ap, int D, const double (&x)[E],
                                             double (&y)[E], double* base, int l) {
-    constexpr int nw = kCoopWarps, KC = kCoopKC;
+    constexpr int nw = kCoopWarps, KC = coop_kc<E>();
     const int S = coop_stages(D);
     static_assert(nw == 8, "the DMMA tile has 8 columns: one per chain of the block");
     const int w = threadIdx.x >> 5;
     double* Xs = base;                 // [D][nw]
     double* Ys = base + nw * D;        // [nw][D]
     double* As = base + 2 * nw * D;    // S x [KC][lds]
-    uint64_t* bars = coop_bars(base, D);
-    const int lds = coop_lds(D), stage_doubles = coop_stage_doubles(D);
+    uint64_t* bars = coop_bars(base, D, KC);
+    const int lds = coop_lds(D), stage_doubles = coop_stage_doubles(D, KC);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int d = l + 32 * e;
@@ -418,7 +420,7 @@ __device__ __forceinline__ void matvec_coop(const double* __restrict__ A, const 
 #pragma unroll
                 for (int p = 0; p < PBW; ++p) {
                     const int q = w + nw * p;
-                    if (16 * q < D) {  // (rows >= D of a ragged block: read, accumulated, never stored)
+                    if (D >= 16 * nw * PBW || 16 * q < D) {  // (rows >= D of a ragged block: read, accumulated, never stored)
                         const double2 a2 = *reinterpret_cast<const double2*>(as + kl * lds + 16 * q);
                         dmma(acc[p][0][0], acc[p][0][1], a2.x, b);
                         dmma(acc[p][1][0], acc[p][1][1], a2.y, b);
@@ -512,13 +514,13 @@ __device__ __forceinline__ void upper_solve(const double* __restrict__ U, int D,
 template <int E>
 __device__ __forceinline__ void upper_solve_coop(const double* __restrict__ U, const double* __restrict__ Up, int D, double (&x)[E],
                                                  double* base, int l) {
-    constexpr int nw = kCoopWarps, KC = kCoopKC;
+    constexpr int nw = kCoopWarps, KC = coop_kc<E>();
     const int S = coop_stages(D);
     const int w = threadIdx.x >> 5;
     double* Xs = base;               // [D][nw]: right-hand sides in, solutions out
     double* As = base + 2 * nw * D;  // S x [KC][lds]
-    uint64_t* bars = coop_bars(base, D);
-    const int lds = coop_lds(D), stage_doubles = coop_stage_doubles(D);
+    uint64_t* bars = coop_bars(base, D, KC);
+    const int lds = coop_lds(D), stage_doubles = coop_stage_doubles(D, KC);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int d = l + 32 * e;

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(COOP ? kCoopThreads : kBlockThreads, COOP ? 1 
     constexpr int kSlab = slab_vectors<MODEL>();
     double* xs = COOP ? smem : smem + (size_t)grp_in_block * kSlab * D;  // dense / user-target slab (unused otherwise)
     const int maxd = a.max_depth > 0 ? a.max_depth : 1;
-    double* lv = smem + (COOP ? (size_t)coop_smem_doubles(D) : dense ? (size_t)kGroups * kSlab * D : 0) +
+    double* lv = smem + (COOP ? (size_t)coop_smem_doubles(D, coop_kc<E>()) : dense ? (size_t)kGroups * kSlab * D : 0) +
                  (size_t)grp_in_block * maxd * kLevelScalars;
     double* LW = lv;
     double* SA = lv + maxd;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(COOP ? kCoopThreads : kBlockThreads, COOP ? 1 
     if constexpr (COOP) {
         mo.coop = smem;
         me.coop = smem;
-        coop_begin(smem, D);  // the pipeline's mbarriers (block barrier inside)
+        coop_begin<E>(smem, D);  // the pipeline's mbarriers (block barrier inside)
     }
 
     int nexp = 0, ndir = 0;
@@ -788,7 +788,7 @@ static cudaError_t launch_nuts_v(const NutsArgs& a, cudaStream_t st) {
     if constexpr (kDenseOps && G == 32 && !VAR) {
         // dense operators, one chain per warp: blocks of kCoopWarps chains share every D x D product (COOP form)
         const long long blocks = (a.N + kCoopWarps - 1) / kCoopWarps;
-        const size_t sm = ((size_t)coop_smem_doubles(a.D) + (size_t)kCoopWarps * maxd * kLevelScalars) * sizeof(double);
+        const size_t sm = ((size_t)coop_smem_doubles(a.D, coop_kc<E>()) + (size_t)kCoopWarps * maxd * kLevelScalars) * sizeof(double);
         auto go = [&](auto kernel) -> cudaError_t {
             if (sm > 48 * 1024) {
                 cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
