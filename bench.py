@@ -437,6 +437,38 @@ def run_ours(args):
                                       "mean_leapfrog_steps_per_transition": nsteps / TN / N_CHAINS,
                                       "rate_steps_dims_per_s": rate, "roofline_frac_contract": rate * B / 1e9 / hbm_peak}
 
+                # C5's shape on this GPU: NUTS with DENSE operators (Dense metric = Sigma, dense-precision Gaussian, D = 256): the
+                # block-cooperative form -- 8 chains share every D x D product (bulk-copied column chunks, fp64 MMA)
+                D5, N5, T5 = 256, 8192, 5
+                rng5 = np.random.Generator(np.random.PCG64(SEED + 5))
+                Q5, _ = np.linalg.qr(rng5.normal(size=(D5, D5)))
+                lam5 = np.exp(np.linspace(np.log(0.1), np.log(10.0), D5))
+                Sig5, P5 = (Q5 * lam5) @ Q5.T, (Q5 / lam5) @ Q5.T
+                h5 = A.Hamiltonian(A.DenseEuclideanMetric(Sig5), A.DenseGaussian(np.zeros(D5), P5))
+                k5 = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.5), A.GeneralisedNoUTurn()))
+                g5 = torch.Generator(device=dev).manual_seed(5)
+                th5 = torch.randn((N5, D5), generator=g5, dtype=torch.float64, device=dev)
+                z5 = A.phasepoint(h5, th5, torch.zeros_like(th5))
+                p5 = A.PhiloxRNG(12)
+                z5, _, st5 = A.sample_transitions(p5, h5, k5, z5, T5, keep_draws=False, flags=A.FLAG_ASYNC)
+                torch.cuda.synchronize()
+                reps5 = []
+                for _ in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    z5, _, st5 = A.sample_transitions(p5, h5, k5, z5, T5, keep_draws=False, flags=A.FLAG_ASYNC)
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                    reps5.append((e0.elapsed_time(e1), int(st5["n_steps"].sum().item())))
+                reps5.sort(key=lambda t: t[0] / t[1])
+                ms5, ns5 = reps5[1]
+                rate5 = ns5 * D5 / ms5 * 1e3
+                general["nuts_c5"] = {"workload": "C5 shape: NUTS + DenseEuclidean (M^-1 = Sigma) on a dense-precision Gaussian, D=256, 8192 chains, "
+                                                  "eps=0.5, 5 transitions per chain in one persistent launch (median of 3 launches)",
+                                      "ms_per_transition": ms5 / T5, "mean_leapfrog_steps_per_transition": ns5 / T5 / N5,
+                                      "rate_steps_dims_per_s": rate5,
+                                      "fp64_mma_tflops": rate5 * 4 * D5 / 1e12}  # two D x D products per leaf = 4 D flop per step x dim
+
         # ---- K4: correlated (dense-precision) Gaussian target, Diag metric, same batch: fp64 tensor-MMA trajectory
         k4 = None
         if rank == 0 and not args.no_extras:
