@@ -28,12 +28,14 @@
 
 namespace ahmc {
 
-// workspace layout per chain (doubles): LEFT edge (theta,r,g) | RIGHT edge | rho_tree | per level k (7 vectors):
-// 0 rho, 1 rfirst, 2 cand theta, 3 cand r, 4 cand g, 5 rlast (Strict), 6 theta_first (Classic)
+// workspace layout per chain (doubles): LEFT edge (theta,r,g) | RIGHT edge | rho_tree | M^-1 r of the LEFT edge | of the
+// RIGHT edge (Dense metric: the whole-tree criterion then needs no D x D product -- a leaf's dH/dr is parked when the leaf
+// becomes an edge) | per level k (7 vectors): 0 rho, 1 rfirst, 2 cand theta, 3 cand r, 4 cand g, 5 rlast (Strict),
+// 6 theta_first (Classic)
 constexpr int kLevelVecs = 7;
 // (+ 2 vectors at the end for the in-kernel Welford state of the adaptive form: mean, M2)
 __host__ __device__ inline long long nuts_level_doubles(int D, int max_depth) {
-    return (long long)(7 + kLevelVecs * (max_depth > 0 ? max_depth : 1)) * D;
+    return (long long)(9 + kLevelVecs * (max_depth > 0 ? max_depth : 1)) * D;
 }
 
 __device__ __forceinline__ double jl_min0(double x) {  // min(0, x), NaN-propagating like Julia
@@ -120,7 +122,9 @@ __global__ void __launch_bounds__(COOP ? kCoopThreads : kBlockThreads, COOP ? 1 
     double* LEFT = base;
     double* RIGHT = base + 3 * (long long)D;
     double* RHO = base + 6 * (long long)D;
-    auto level = [&](int k) { return base + (7 + kLevelVecs * (long long)k) * D; };
+    double* LEFT_DR = base + 7 * (long long)D;   // Dense metric only
+    double* RIGHT_DR = base + 8 * (long long)D;
+    auto level = [&](int k) { return base + (9 + kLevelVecs * (long long)k) * D; };
 
     double eps_c = a.eps_chain ? __ldg(a.eps_chain + chain) : a.eps;
     // adaptive family: per-chain dual-averaging state (all lanes of the group hold the same values) and the chain's
@@ -266,6 +270,10 @@ __global__ void __launch_bounds__(COOP ? kCoopThreads : kBlockThreads, COOP ? 1 
                 vstore<G, E>(RIGHT, s.th, l, D);
                 vstore<G, E>(RIGHT + D, s.r, l, D);
                 vstore<G, E>(RIGHT + 2 * (long long)D, s.g, l, D);
+                if constexpr (METRIC == AHMC_METRIC_DENSE) {  // M^-1 r0 (from the kinetic energy above) for both edges
+                    vstore<G, E>(LEFT_DR, drn, l, D);
+                    vstore<G, E>(RIGHT_DR, drn, l, D);
+                }
                 vstore<G, E>(RHO, s.r, l, D);
                 vstore<G, E>(a.th_out + a.ld_out * chain, s.th, l, D);
                 vstore<G, E>(a.r_out + a.ld_out * chain, s.r, l, D);
@@ -729,7 +737,16 @@ __global__ void __launch_bounds__(COOP ? kCoopThreads : kBlockThreads, COOP ? 1 
                 vstore<G, E>(edge + 2 * (long long)D, s.g, l, D);
                 vload_nc<G, E>(r_other, other + D, l, D);
             }
-            me.dHdr(r_other, t1, xs, l);
+            if constexpr (METRIC == AHMC_METRIC_DENSE) {  // dH/dr of both edges is parked: no product at the top level
+#pragma unroll
+                for (int e = 0; e < E; ++e) t1[e] = 0.0;
+                if (complete) {
+                    vstore<G, E>((v < 0) ? LEFT_DR : RIGHT_DR, dr, l, D);
+                    vload_nc<G, E>(t1, (v < 0) ? RIGHT_DR : LEFT_DR, l, D);
+                }
+            } else {
+                me.dHdr(r_other, t1, xs, l);
+            }
             double d1 = 0.0, d2 = 0.0;
             bool uturn_top;
             if (VAR && crit == 1) {  // ClassicNoUTurn on the whole tree: q = -(theta_right - theta_left)
