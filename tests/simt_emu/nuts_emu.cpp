@@ -86,6 +86,8 @@ static KernelFn by_model(int model, int metric, int G, int E) {
     if (model == AHMC_MODEL_STD_NORMAL && metric == AHMC_METRIC_UNIT) return by_layout<AHMC_MODEL_STD_NORMAL, AHMC_METRIC_UNIT, VAR, ADAPT>(G, E);
     if (model == AHMC_MODEL_DIAG_GAUSS && metric == AHMC_METRIC_DIAG) return by_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_DIAG, VAR, ADAPT>(G, E);
     if (model == AHMC_MODEL_FUNNEL && metric == AHMC_METRIC_DIAG) return by_layout<AHMC_MODEL_FUNNEL, AHMC_METRIC_DIAG, VAR, ADAPT>(G, E);
+    if (ADAPT && !VAR && model == AHMC_MODEL_DENSE_GAUSS && metric == AHMC_METRIC_DIAG)  // adaptive family, cooperative form
+        return by_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DIAG, false, true>(G, E);
     if (!ADAPT) {
         if (model == AHMC_MODEL_DENSE_GAUSS && metric == AHMC_METRIC_DENSE) return by_layout<AHMC_MODEL_DENSE_GAUSS, AHMC_METRIC_DENSE, VAR, false>(G, E);
         if (model == AHMC_MODEL_DIAG_GAUSS && metric == AHMC_METRIC_UNIT) return by_layout<AHMC_MODEL_DIAG_GAUSS, AHMC_METRIC_UNIT, VAR, false>(G, E);

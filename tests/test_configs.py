@@ -274,3 +274,26 @@ def test_in_launch_adaptation_degenerate_and_host_forms():
         A.nuts_adapt_sample(A.PhiloxRNG(1), h, ks, z0, 4, 2, ad0)
     with pytest.raises(A.AhmcError):
         A.nuts_adapt_sample(A.PhiloxRNG(1), h, kern, z0, 4, 5, ad0)  # n_adapts > n_transitions
+
+
+@pytest.mark.gpu
+def test_in_launch_adaptation_on_a_dense_precision_target_runs_the_cooperative_form():
+    """A dense-precision Gaussian with the Diag metric runs the adaptive family in the block-cooperative form (8 chains
+    share the precision product).  Written with a DIAGONAL precision it is the diagonal Gaussian: same trees, and step
+    sizes / adapted M^-1 / draws equal up to the summation order of the products."""
+    D, N, T, n_adapts = 64, 50, 14, 12
+    rng = np.random.default_rng(19)
+    sd, mu = np.exp(rng.uniform(-0.4, 0.4, D)), rng.normal(size=D) * 0.3
+    kern = A.HMCKernel(A.Trajectory(A.MultinomialTS, A.Leapfrog(0.2), A.GeneralisedNoUTurn(7, 1000.0)))
+    ad = A.VectorisedStanAdaptor(init_buffer=3, term_buffer=2, window_size=4, n_min=3)
+    th = torch.as_tensor(rng.normal(size=(N, D)), device=DEV)
+    out = []
+    for target in (A.DiagGaussian(mu, sd), A.DenseGaussian(mu, np.diag(1.0 / sd ** 2))):
+        h = A.Hamiltonian(A.DiagEuclideanMetric(np.ones(D)), target)
+        z0 = A.phasepoint(h, th, torch.zeros_like(th))
+        out.append(A.nuts_adapt_sample(A.PhiloxRNG(8), h, kern, z0, T, n_adapts, ad))
+    (zl0, d0, s0, e0, m0, _), (zl1, d1, s1, e1, m1, _) = out
+    # the unnormalised dense target has another constant c0: energies differ by it, trees must not
+    assert torch.equal(s0["n_steps"], s1["n_steps"]) and torch.equal(s0["tree_depth"], s1["tree_depth"])
+    assert torch.allclose(e0, e1, rtol=1e-6) and torch.allclose(m0, m1, rtol=1e-5) and torch.allclose(d0, d1, atol=1e-5)
+    assert (e0 != 0.2).all() and not torch.allclose(m0, torch.ones_like(m0))

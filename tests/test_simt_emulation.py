@@ -177,7 +177,8 @@ def test_kernel_source_emulated_wild_funnel_start(emu):
     _case(emu, "funnel", "diag", 4, 8, 2.5, "multinomial", "generalised", seed=6, delta_max=1000.0, scale=3.0)
 
 
-def _philox_run(lib, N, D, T, seed, n_adapts=0, adapt=False, eps0=0.3, Minv0=None, sd=None, mu=None, windows=(3, 2, 4), n_min=3):
+def _philox_run(lib, N, D, T, seed, n_adapts=0, adapt=False, eps0=0.3, Minv0=None, sd=None, mu=None, windows=(3, 2, 4), n_min=3,
+                dense_target=False, coop_padded=0):
     """Philox-mode run of the (adaptive or plain) persistent kernel: T transitions per chain from theta = 0."""
     th = np.zeros((N, D))
     th[:] = np.linspace(-1, 1, D)
@@ -193,7 +194,9 @@ def _philox_run(lib, N, D, T, seed, n_adapts=0, adapt=False, eps0=0.3, Minv0=Non
     draws = np.zeros((T, N, D))
     eps_rw, minv_rw, trace = np.full(N, eps0), np.zeros((N, D)), np.zeros((T, N))
     Minv = np.ones(D) if Minv0 is None else Minv0
-    q = EmuNuts(model_kind=oc.DIAG_GAUSS, metric_kind=oc.DIAG, D=D, N=N, p0=P(mu), p1=P(w), c0=0.0, Minv=P(Minv),
+    Pm = np.ascontiguousarray(np.diag(w))  # the same target written as a dense-precision Gaussian (the cooperative form)
+    q = EmuNuts(model_kind=oc.DENSE_GAUSS if dense_target else oc.DIAG_GAUSS, metric_kind=oc.DIAG, D=D, N=N, p0=P(mu),
+                p1=P(Pm) if dense_target else P(w), c0=0.0, Minv=P(Minv),
                 minv_stride=0 if Minv.ndim == 1 else D, cholU=None, eps=eps0, eps_chain=None, max_depth=6, delta_max=1000.0,
                 sampler=0, criterion=0, seed=seed, offset=0, normal_tape=None, exp_tape=None, exp_stride=0, dir_tape=None,
                 dir_stride=0, partial_alpha=0.0, refresh=1, th_in=P(th), r_in=P(r), g_in=P(g_in), lp_in=P(lp_in),
@@ -201,7 +204,7 @@ def _philox_run(lib, N, D, T, seed, n_adapts=0, adapt=False, eps0=0.3, Minv0=Non
                 tree_depth=P(td), numerical=P(ne), acc=P(acc), dH=P(dH), dHmax=P(dHm), n_transitions=T, draws=P(draws),
                 adapt=1 if adapt else 0, n_adapts=n_adapts, init_buffer=windows[0], term_buffer=windows[1], window_size=windows[2],
                 delta=0.8, gamma=0.05, t0=10.0, kappa=0.75, adapt_metric=1, n_min=n_min, eps_rw=P(eps_rw), minv_rw=P(minv_rw),
-                eps_trace=P(trace))
+                eps_trace=P(trace), coop_padded=coop_padded)
     assert lib.emu_nuts(C.byref(q)) == 0
     return dict(draws=draws, acc=acc.reshape(T, N), n_steps=ns.reshape(T, N), eps=eps_rw, minv=minv_rw, trace=trace, theta=out["th"])
 
@@ -351,6 +354,24 @@ def test_hmc_transition_kernel_source_under_emulation_matches_oracle(emu_lf, kin
     assert (isacc == so.is_accept).all()
     assert rel_err(o["th"].T, zo.theta) < 1e-10 and rel_err(o["r"].T, zo.r) < 1e-10
     assert np.allclose(acc, so.acceptance_rate, rtol=1e-10) and np.allclose(lp_o, zo.lp_value, rtol=1e-10, atol=1e-10)
+
+
+def test_in_launch_adaptation_in_the_cooperative_form_equals_the_diagonal_run(emu):
+    """A dense-precision Gaussian with the Diag metric runs the adaptive family in the block-cooperative form (8 chains
+    share the precision product).  Written with a DIAGONAL precision it is the same target as the diagonal Gaussian: step
+    size traces, adapted M^-1 and draws of the two kernels agree (products sum in a different order: 1e-7 after 10
+    transitions), from plain and from column-padded matrices."""
+    rng = np.random.default_rng(31)
+    D, N, T, n_adapts = 40, 9, 10, 8
+    sd, mu = np.exp(rng.uniform(-0.4, 0.4, D)), rng.normal(size=D) * 0.3
+    kw = dict(seed=4, n_adapts=n_adapts, adapt=True, eps0=0.2, sd=sd, mu=mu, windows=(2, 1, 3), n_min=2)
+    ref = _philox_run(emu, N, D, T, **kw)
+    for padded in (0, 1):
+        got = _philox_run(emu, N, D, T, dense_target=True, coop_padded=padded, **kw)
+        assert (got["n_steps"] == ref["n_steps"]).all()
+        assert np.allclose(got["trace"], ref["trace"], rtol=1e-7) and np.allclose(got["eps"], ref["eps"], rtol=1e-7)
+        assert np.allclose(got["minv"], ref["minv"], rtol=1e-6) and np.allclose(got["draws"], ref["draws"], atol=1e-6)
+    assert ref["n_steps"].max() >= 7 and not np.allclose(ref["minv"], 1.0)
 
 
 def test_kernel_source_emulated_randomised_configurations(emu):
