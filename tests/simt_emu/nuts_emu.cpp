@@ -78,6 +78,9 @@ static KernelFn by_layout(int G, int E) {
     if (G == 16 && E == 1) return thunk<MODEL, METRIC, 16, 1, VAR, ADAPT>;
     if (G == 32 && E == 4) return thunk<MODEL, METRIC, 32, 4, VAR, ADAPT>;
     if (G == 32 && E == 8) return thunk<MODEL, METRIC, 32, 8, VAR, ADAPT>;
+    if constexpr (MODEL == AHMC_MODEL_DENSE_GAUSS && METRIC == AHMC_METRIC_DENSE && !VAR && !ADAPT) {
+        if (G == 32 && E == 16) return thunk<MODEL, METRIC, 32, 16, VAR, ADAPT>;  // D in (256, 512]: 16-column chunks, 2 stages
+    }
     return nullptr;
 }
 
@@ -118,6 +121,7 @@ extern "C" int emu_nuts(const EmuNuts* q) {
     else if (D > 32 && D <= 64) G = 32, E = 2;
     else if (D > 64 && D <= 128) G = 32, E = 4;  // the headline layout
     else if (D > 128 && D <= 256) G = 32, E = 8;  // C5's layout
+    else if (D > 256 && D <= 512) G = 32, E = 16;
     else return -1;
     NutsArgs a{};
     a.model = ModelDev{q->model_kind, D, q->p0, q->p1, q->c0};

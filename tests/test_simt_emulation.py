@@ -123,6 +123,7 @@ CASES = [
     ("dense_gauss", "dense", 40, 11, 0.3, "multinomial", "generalised"),   # COOP: a full block of 8 chains + a ragged one of 3
     ("dense_gauss", "diag", 64, 9, 0.3, "multinomial", "generalised"),     # COOP, full tile (E=2), dense target only
     ("diag_gauss", "dense", 33, 5, 0.3, "multinomial", "generalised"),     # COOP, dense metric only
+    ("dense_gauss", "dense", 264, 1, 0.25, "multinomial", "generalised"),  # G=32, E=16 (D in 257..512): 16-column chunks, 2 stages
 ]
 
 
@@ -134,7 +135,7 @@ def test_kernel_source_under_cpu_simt_emulation_matches_oracle(emu, kind, mkind,
 
 
 @pytest.mark.parametrize("kind,mkind,D,N", [("dense_gauss", "dense", 40, 11), ("dense_gauss", "diag", 64, 9), ("diag_gauss", "dense", 33, 5),
-                                            ("dense_gauss", "dense", 200, 1)])
+                                            ("dense_gauss", "dense", 200, 1), ("dense_gauss", "dense", 264, 2)])
 def test_cooperative_products_from_column_padded_matrices_match_oracle(emu, kind, mkind, D, N):
     """the cooperative NUTS form with the column-padded copies of the dense matrices the library prepares (one bulk copy
     per chunk of columns instead of one per column): same transitions as from the plain matrices"""
