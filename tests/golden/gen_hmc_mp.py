@@ -58,15 +58,21 @@ class Sys:
         dr = dHdr_mp(self.mkind, self.Minv, r, self.D)
         return dict(th=th, r=r, lp=lp, g=[-x for x in grad], lk=-sum(a * b for a, b in zip(r, dr)) / 2)
 
-    def step(self, z, fwd):  # one leapfrog step (integrator.jl:233-247)
+    def step(self, z, fwd, i=1, n=1, alpha=None):  # leapfrog step i of an n-step `step` call (integrator.jl:233-247)
         e = self.eps if fwd else -self.eps
         D = self.D
-        r = [z["r"][d] - e / 2 * z["g"][d] for d in range(D)]
+        r0 = z["r"]
+        if alpha is not None:  # TemperedLeapfrog (integrator.jl:198-209): i_temper = 2(i-1) + 1 for the first half
+            sa = mp.sqrt(alpha)
+            r0 = [x * sa for x in r0] if 2 * (i - 1) + 1 <= n else [x / sa for x in r0]
+        r = [r0[d] - e / 2 * z["g"][d] for d in range(D)]
         dr = dHdr_mp(self.mkind, self.Minv, r, D)
         th = [z["th"][d] + e * dr[d] for d in range(D)]
         lp, grad = logp_grad_mp(self.kind, D, self.p0, self.p1, self.c0, th)
         g = [-x for x in grad]
         r = [r[d] - e / 2 * g[d] for d in range(D)]
+        if alpha is not None:  # second half: i_temper = 2(i-1) + 2
+            r = [x * sa for x in r] if 2 * (i - 1) + 2 <= n else [x / sa for x in r]
         dr = dHdr_mp(self.mkind, self.Minv, r, D)
         return dict(th=th, r=r, lp=lp, g=g, lk=-sum(a * b for a, b in zip(r, dr)) / 2)
 
@@ -75,7 +81,7 @@ def energy(z):
     return -(z["lp"] + z["lk"])
 
 
-def make_case(rng, name, kind, mkind, D, N, eps, n_steps, ts, n_fwd=None, scale=1.0):
+def make_case(rng, name, kind, mkind, D, N, eps, n_steps, ts, n_fwd=None, scale=1.0, temper=None):
     p0 = p1 = Minv = None
     c0 = 0.0
     if kind == "diag_gauss":
@@ -92,6 +98,7 @@ def make_case(rng, name, kind, mkind, D, N, eps, n_steps, ts, n_fwd=None, scale=
     pp1 = None if p1 is None else ([mpf_list(row) for row in p1] if kind == "dense_gauss" else mpf_list(p1))
     Mm = None if Minv is None else ([mpf_list(row) for row in Minv] if mkind == "dense" else mpf_list(Minv))
     S = Sys(kind, D, pp0, pp1, mp.mpf(c0), mkind, Mm, mp.mpf(float(eps)))
+    al = None if temper is None else mp.mpf(float(temper))
     while True:
         theta = rng.normal(size=(N, D)) * scale
         normals = rng.normal(size=(N, D))
@@ -105,8 +112,8 @@ def make_case(rng, name, kind, mkind, D, N, eps, n_steps, ts, n_fwd=None, scale=
             H0 = energy(z)
             if ts == "endpoint":
                 z1 = z
-                for _ in range(n_steps):
-                    z1 = S.step(z1, True)
+                for i in range(1, n_steps + 1):
+                    z1 = S.step(z1, True, i, n_steps, al)
                 H1 = energy(z1)
                 ex = mp.mpf(float(var[c]))
                 margin = min(margin, abs(H1 - (H0 + ex)) / max(abs(H1), abs(H0 + ex), 1))
@@ -117,12 +124,12 @@ def make_case(rng, name, kind, mkind, D, N, eps, n_steps, ts, n_fwd=None, scale=
             else:
                 fwd, bwd = [], []
                 zz = z
-                for _ in range(n_fwd):
-                    zz = S.step(zz, True)
+                for i in range(1, n_fwd + 1):  # each leg is its own `step` call: it tempers by its own number of steps
+                    zz = S.step(zz, True, i, n_fwd, al)
                     fwd.append(zz)
                 zz = z
-                for _ in range(n_steps - n_fwd):
-                    zz = S.step(zz, False)
+                for i in range(1, n_steps - n_fwd + 1):
+                    zz = S.step(zz, False, i, n_steps - n_fwd, al)
                     bwd.append(zz)
                 zs = list(reversed(bwd)) + [z] + fwd  # :377
                 lw = [-energy(q) for q in zs]
@@ -155,6 +162,7 @@ def make_case(rng, name, kind, mkind, D, N, eps, n_steps, ts, n_fwd=None, scale=
             break
     tolist = lambda a: None if a is None else np.asarray(a).tolist()
     return dict(name=name, model=kind, metric=mkind, D=D, N=N, eps=float(eps), n_steps=n_steps, sampler=ts, n_fwd=n_fwd,
+                temper_alpha=0.0 if temper is None else float(temper),
                 p0=tolist(p0), p1=tolist(p1), c0=c0, Minv=tolist(Minv), theta0=theta.tolist(), normals=normals.tolist(),
                 variates=var.tolist(), min_margin=float(margin), expect=out)
 
@@ -169,6 +177,10 @@ def main():
         make_case(rng, "mn_diag_diag", "diag_gauss", "diag", 5, 8, 0.5, 7, "multinomial", n_fwd=3),
         make_case(rng, "mn_dense_unit_allfwd", "dense_gauss", "unit", 4, 6, 0.4, 5, "multinomial", n_fwd=5),
         make_case(rng, "mn_funnel_dense_allbwd", "funnel", "dense", 3, 6, 0.3, 6, "multinomial", n_fwd=0),
+        # TemperedLeapfrog(eps, alpha) as the transition's integrator (appended: the cases above keep their random streams)
+        make_case(rng, "ep_diag_diag_tempered_odd", "diag_gauss", "diag", 6, 8, 0.5, 7, "endpoint", temper=1.1),
+        make_case(rng, "ep_funnel_unit_tempered", "funnel", "unit", 4, 8, 0.4, 6, "endpoint", temper=0.93),
+        make_case(rng, "mn_diag_diag_tempered", "diag_gauss", "diag", 5, 8, 0.45, 7, "multinomial", n_fwd=3, temper=1.08),
     ]
     with open(os.path.join(HERE, "hmc_mp50.json"), "w") as f:
         json.dump(dict(generator="tests/golden/gen_hmc_mp.py", digits=50, cases=cases), f)

@@ -511,11 +511,13 @@ def test_static_transitions_match_mp50_restatement(case):
     z0 = A.phasepoint(h, th0, torch.zeros_like(th0))
     normals = torch.as_tensor(np.array(case["normals"]), device=DEV)
     var = torch.as_tensor(np.array(case["variates"]), device=DEV)
+    alpha = case.get("temper_alpha", 0.0)  # > 0: the case's integrator is TemperedLeapfrog(eps, alpha)
+    lf = A.TemperedLeapfrog(case["eps"], alpha) if alpha > 0 else A.Leapfrog(case["eps"])
     if case["sampler"] == "endpoint":
-        tau = A.Trajectory(A.EndPointTS, A.Leapfrog(case["eps"]), A.FixedNSteps(case["n_steps"]))
+        tau = A.Trajectory(A.EndPointTS, lf, A.FixedNSteps(case["n_steps"]))
         tr = A.transition(A.TapeRNG(normal=normals, exp=var), h, A.HMCKernel(tau), z0)
     else:
-        tau = A.Trajectory(A.MultinomialTS, A.Leapfrog(case["eps"]), A.FixedNSteps(case["n_steps"]))
+        tau = A.Trajectory(A.MultinomialTS, lf, A.FixedNSteps(case["n_steps"]))
         tr = A.transition(A.TapeRNG(normal=normals, exp=var, n_fwd=case["n_fwd"]), h, A.HMCKernel(tau), z0)
         if "index" in case["expect"]:  # (the reference does not report the drawn index: absent in reference-generated cases)
             assert (tr.stat["tree_depth"].cpu().numpy() == np.array(case["expect"]["index"])).all()

@@ -412,13 +412,17 @@ def test_hmc_oracle_matches_mp50_restatement(case):
     model, metric = oc.Model(kinds[case["model"]], D, p0, p1, case["c0"]), oc.Metric(mkinds[case["metric"]], Minv)
     th, nt = np.array(case["theta0"]).T, np.array(case["normals"]).T
     z0 = oc.phasepoint(model, metric, th, np.zeros((D, N)))
-    if case["sampler"] == "endpoint":
-        z, st = oc.hmc_transition(model, metric, case["eps"], case["n_steps"], z0, nt, np.array(case["variates"]))
-    else:
-        z, st = oc.hmc_multinomial_transition(model, metric, case["eps"], case["n_steps"], case["n_fwd"], z0, nt,
-                                              np.array(case["variates"]))
-        if "index" in case["expect"]:
-            assert (st.tree_depth == np.array(case["expect"]["index"])).all()
+    oc.set_tempering(case.get("temper_alpha", 0.0))  # > 0: TemperedLeapfrog(eps, alpha) is the transition's integrator
+    try:
+        if case["sampler"] == "endpoint":
+            z, st = oc.hmc_transition(model, metric, case["eps"], case["n_steps"], z0, nt, np.array(case["variates"]))
+        else:
+            z, st = oc.hmc_multinomial_transition(model, metric, case["eps"], case["n_steps"], case["n_fwd"], z0, nt,
+                                                  np.array(case["variates"]))
+            if "index" in case["expect"]:
+                assert (st.tree_depth == np.array(case["expect"]["index"])).all()
+    finally:
+        oc.set_tempering(0.0)
     e = case["expect"]
     assert (st.is_accept.astype(bool) == np.array(e["is_accept"])).all()
     assert rel_err(z.theta, np.array(e["theta"]).T) < 1e-10 and rel_err(z.r, np.array(e["r"]).T) < 1e-10

@@ -414,7 +414,8 @@ def emu_mn(tmp_path_factory):
 
 def test_multinomial_static_kernel_source_under_emulation_matches_mp50_fixtures(emu_mn):
     """`multinomial_kernel` (energy pass, inverse-CDF draw, re-materialisation of the drawn point) executed by the emulator
-    on the 50-digit MultinomialTS fixtures of tests/golden/hmc_mp50.json (mixed, all-forward and all-backward splits)."""
+    on the 50-digit MultinomialTS fixtures of tests/golden/hmc_mp50.json (mixed, all-forward and all-backward splits, and one
+    integrated by TemperedLeapfrog)."""
     from tests.helpers import hmc_golden_cases
 
     done = 0
@@ -440,7 +441,7 @@ def test_multinomial_static_kernel_source_under_emulation_matches_mp50_fixtures(
         q = EmuMn(model_kind=KINDS[kind], metric_kind=MKINDS[mkind], D=D, N=N, p0=P(p0), p1=P(dp1), Minv=P(Minv), cholU=P(cholU),
                   eps=case["eps"], n_steps=case["n_steps"], n_fwd=case["n_fwd"], normal_tape=P(nt), unif_tape=P(ut), th_in=P(th),
                   g_in=P(g_in), lp_in=P(lp_in), th_out=P(o["th"]), r_out=P(o["r"]), g_out=P(o["g"]), lp_out=P(lp_o), lk_out=P(lk_o),
-                  acc=P(acc), index=P(idx))
+                  acc=P(acc), index=P(idx), temper_alpha=case.get("temper_alpha", 0.0))
         assert emu_mn.emu_multinomial(C.byref(q)) == 0, case["name"]
         e = case["expect"]
         if "index" in e:
@@ -449,7 +450,7 @@ def test_multinomial_static_kernel_source_under_emulation_matches_mp50_fixtures(
         assert np.allclose(acc, e["acceptance_rate"], rtol=1e-10)
         assert np.allclose(lp_o, e["lp_value"], rtol=1e-10, atol=1e-10) and np.allclose(lk_o, e["lk_value"], rtol=1e-10, atol=1e-10)
         done += 1
-    assert done == 3
+    assert done == 4  # mixed, all-forward, all-backward, and a tempered one
 
 
 @pytest.mark.parametrize("n,n_fwd", [(7, 3), (6, 6), (5, 0)])
