@@ -20,8 +20,9 @@ import numpy as np
 class System:
     """log-density + metric as plain numpy callables: grad(theta) -> (lp, -grad lp);  dHdr(r) -> M^-1 r."""
 
-    def __init__(self, logp_grad, dHdr, eps):
+    def __init__(self, logp_grad, dHdr, eps, temper_alpha=0.0):
         self.logp_grad, self.dHdr, self.eps = logp_grad, dHdr, eps
+        self.temper_alpha = temper_alpha  # > 0: TemperedLeapfrog(eps, alpha) (integrator.jl:174-209)
 
     def point(self, th, r):
         lp, g = self.logp_grad(th)
@@ -29,10 +30,11 @@ class System:
 
     def step(self, z, v):  # integrator.jl:216-265, n_steps = v
         e = self.eps if v > 0 else -self.eps
-        r = z["r"] - e / 2 * z["g"]
+        sa = math.sqrt(self.temper_alpha) if self.temper_alpha > 0 else 1.0  # a 1-step `step`: multiply before, divide after
+        r = z["r"] * sa - e / 2 * z["g"]
         th = z["th"] + e * self.dHdr(r)
         lp, g = self.logp_grad(th)
-        r = r - e / 2 * g
+        r = (r - e / 2 * g) / sa
         return dict(th=th, r=r, lp=lp, g=g, lk=-0.5 * float(r @ self.dHdr(r)))
 
 

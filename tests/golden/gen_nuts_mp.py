@@ -47,6 +47,7 @@ class Ctx:
         self.mkind, self.Minv, self.eps = mkind, Minv, eps
         self.sampler, self.criterion, self.max_depth, self.delta_max = sampler, criterion, max_depth, delta_max
         self.dirs, self.variates = list(dirs), list(variates)
+        self.temper = None  # mp.mpf alpha: the integrator is TemperedLeapfrog(eps, alpha) (integrator.jl:174-209)
         self.n_dir = self.n_var = 0
         self.min_margin = mp.mpf(1)
 
@@ -79,12 +80,17 @@ class Ctx:
     def step(self, z, v):  # integrator.jl:216-265 with n_steps = v = +-1
         e = self.eps if v > 0 else -self.eps
         D = self.D
-        r = [z.r[d] - e / 2 * z.g[d] for d in range(D)]
+        r0 = z.r
+        if self.temper is not None:  # n_steps = 1, i = 1: i_temper = 1 <= 1 -> multiply before the first half kick ...
+            r0 = [x * mp.sqrt(self.temper) for x in r0]
+        r = [r0[d] - e / 2 * z.g[d] for d in range(D)]
         dr = self.dHdr(r)
         th = [z.th[d] + e * dr[d] for d in range(D)]
         lp, grad = logp_grad_mp(self.kind, D, self.p0, self.p1, self.c0, th)
         g = [-x for x in grad]
         r = [r[d] - e / 2 * g[d] for d in range(D)]
+        if self.temper is not None:  # ... i_temper = 2 > 1 -> divide after the second
+            r = [x / mp.sqrt(self.temper) for x in r]
         dr = self.dHdr(r)
         return Z(th, r, lp, g, -sum(r[d] * dr[d] for d in range(D)) / 2)
 
@@ -238,7 +244,7 @@ def transition(c, z0):  # :677-742
                        tree_depth=j, numerical_error=bool(term[1]))
 
 
-def make_case(rng, name, kind, mkind, D, N, eps, sampler, criterion, max_depth=6, delta_max=1000.0, scale=1.0):
+def make_case(rng, name, kind, mkind, D, N, eps, sampler, criterion, max_depth=6, delta_max=1000.0, scale=1.0, temper=None):
     p0 = p1 = Minv = None
     c0 = 0.0
     if kind == "diag_gauss":
@@ -268,6 +274,7 @@ def make_case(rng, name, kind, mkind, D, N, eps, sampler, criterion, max_depth=6
         for ch in range(N):
             c = Ctx(kind, D, pp0, pp1, mp.mpf(c0), mkind, Mm, mp.mpf(float(eps)), sampler, criterion, max_depth,
                     mp.mpf(float(delta_max)), dirs[ch], mpf_list(var[ch]))
+            c.temper = None if temper is None else mp.mpf(float(temper))
             z0 = c.phasepoint(mpf_list(theta[ch]), mpf_list(r[ch]))
             zc, st = transition(c, z0)
             margin = min(margin, c.min_margin)
@@ -286,7 +293,7 @@ def make_case(rng, name, kind, mkind, D, N, eps, sampler, criterion, max_depth=6
             break
     tolist = lambda a: None if a is None else np.asarray(a).tolist()
     return dict(name=name, model=kind, metric=mkind, D=D, N=N, eps=float(eps), sampler=sampler, criterion=criterion,
-                max_depth=max_depth, delta_max=float(delta_max), p0=tolist(p0), p1=tolist(p1), c0=c0, Minv=tolist(Minv),
+                max_depth=max_depth, delta_max=float(delta_max), temper_alpha=0.0 if temper is None else float(temper), p0=tolist(p0), p1=tolist(p1), c0=c0, Minv=tolist(Minv),
                 theta0=theta.tolist(), r0=r.tolist(), dirs=dirs.tolist(), variates=var.tolist(),
                 min_margin=float(margin), expect=out)
 
@@ -308,6 +315,9 @@ def main():
         make_case(rng, "mn_strict_funnel_unit", "funnel", "unit", 4, 6, 0.3, "multinomial", "strict", scale=0.7),
         make_case(rng, "slice_strict_stdnormal_diag", "std_normal", "diag", 4, 6, 0.35, "slice", "strict"),
         make_case(rng, "slice_classic_diag_unit", "diag_gauss", "unit", 4, 6, 0.3, "slice", "classic"),
+        # TemperedLeapfrog as the integrator: every leaf is a 1-step `step` (appended: the cases above keep their streams)
+        make_case(rng, "mn_gen_diag_diag_tempered", "diag_gauss", "diag", 5, 6, 0.3, "multinomial", "generalised", temper=1.06),
+        make_case(rng, "mn_gen_dense_dense_tempered", "dense_gauss", "dense", 4, 5, 0.3, "multinomial", "generalised", temper=0.95),
     ]
     with open(os.path.join(HERE, "nuts_mp50.json"), "w") as f:
         json.dump(dict(generator="tests/golden/gen_nuts_mp.py", digits=50, cases=cases), f)

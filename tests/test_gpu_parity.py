@@ -544,7 +544,9 @@ def test_nuts_kernel_matches_mp50_recursive_restatement(case):
     Minv = None if case["Minv"] is None else np.array(case["Minv"])
     h = A.Hamiltonian(make_metric(case["metric"], Minv, D), make_target(case["model"], D, p0, p1, case["c0"]))
     z0 = A.phasepoint(h, torch.as_tensor(np.array(case["theta0"]), device=DEV), torch.as_tensor(np.array(case["r0"]), device=DEV))
-    tau = A.Trajectory(getattr(A, _SAMPLERS[case["sampler"]]), A.Leapfrog(case["eps"]),
+    alpha = case.get("temper_alpha", 0.0)  # > 0: the case's integrator is TemperedLeapfrog(eps, alpha)
+    lf = A.TemperedLeapfrog(case["eps"], alpha) if alpha > 0 else A.Leapfrog(case["eps"])
+    tau = A.Trajectory(getattr(A, _SAMPLERS[case["sampler"]]), lf,
                        getattr(A, _CRITERIA[case["criterion"]])(case["max_depth"], case["delta_max"]))
     rngt = A.TapeRNG(exp=torch.as_tensor(np.array(case["variates"]), device=DEV),
                      dirs=torch.as_tensor(np.array(case["dirs"], dtype=np.uint8), device=DEV))

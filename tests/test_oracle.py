@@ -378,9 +378,13 @@ def test_nuts_oracle_matches_mp50_recursive_restatement(case):
     model, metric = oc.Model(kinds[case["model"]], D, p0, p1, case["c0"]), oc.Metric(mkinds[case["metric"]], Minv)
     th, r = np.array(case["theta0"]).T, np.array(case["r0"]).T
     z0 = oc.phasepoint(model, metric, th, r)
-    z, st, used = oc.nuts_transition(model, metric, case["eps"], z0, None, np.array(case["dirs"], dtype=np.uint8),
-                                     np.array(case["variates"]), max_depth=case["max_depth"], delta_max=case["delta_max"],
-                                     sampler=case["sampler"], criterion=case["criterion"])
+    oc.set_tempering(case.get("temper_alpha", 0.0))  # > 0: every leaf is a TemperedLeapfrog step
+    try:
+        z, st, used = oc.nuts_transition(model, metric, case["eps"], z0, None, np.array(case["dirs"], dtype=np.uint8),
+                                         np.array(case["variates"]), max_depth=case["max_depth"], delta_max=case["delta_max"],
+                                         sampler=case["sampler"], criterion=case["criterion"])
+    finally:
+        oc.set_tempering(0.0)
     e = case["expect"]
     assert (st.tree_depth == np.array(e["tree_depth"])).all()
     assert (st.n_steps == np.array(e["n_steps"])).all()
@@ -549,6 +553,7 @@ def test_iterative_nuts_scheme_matches_mp50_recursion(case):
     from oracle import nuts_iterative as ni
 
     S = _np_system(case["model"], case["D"], case["p0"], case["p1"], case["metric"], case["Minv"], case["eps"])
+    S.temper_alpha = case.get("temper_alpha", 0.0)
     e = case["expect"]
     for c in range(case["N"]):
         z0 = S.point(np.array(case["theta0"][c]), np.array(case["r0"][c]))
