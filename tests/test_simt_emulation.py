@@ -360,10 +360,10 @@ def test_hmc_transition_kernel_source_under_emulation_matches_oracle(emu_lf, kin
 def test_in_launch_adaptation_in_the_cooperative_form_equals_the_diagonal_run(emu):
     """A dense-precision Gaussian with the Diag metric runs the adaptive family in the block-cooperative form (8 chains
     share the precision product).  Written with a DIAGONAL precision it is the same target as the diagonal Gaussian: step
-    size traces, adapted M^-1 and draws of the two kernels agree (products sum in a different order: 1e-7 after 10
+    size traces, adapted M^-1 and draws of the two kernels agree (products sum in a different order: 1e-7 after 8
     transitions), from plain and from column-padded matrices."""
     rng = np.random.default_rng(31)
-    D, N, T, n_adapts = 40, 9, 10, 8
+    D, N, T, n_adapts = 40, 8, 8, 6
     sd, mu = np.exp(rng.uniform(-0.4, 0.4, D)), rng.normal(size=D) * 0.3
     kw = dict(seed=4, n_adapts=n_adapts, adapt=True, eps0=0.2, sd=sd, mu=mu, windows=(2, 1, 3), n_min=2)
     ref = _philox_run(emu, N, D, T, **kw)
